@@ -1,0 +1,88 @@
+"""ctypes binding of libgp_b200.so (the C ABI declared in include/gp_b200.h).
+
+The product path has NO fallback: if the library is missing or a call fails, we raise.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'lib', 'libgp_b200.so')
+
+c_f = C.c_void_p      # device pointers travel as integers
+c_ll = C.c_longlong
+c_i = C.c_int
+
+
+class GpGemm(C.Structure):
+    _fields_ = [('A', c_f), ('B', c_f), ('C', c_f),
+                ('M', c_i), ('N', c_i), ('K', c_i), ('batch', c_i),
+                ('sAb', c_ll), ('sAm', c_ll), ('sAk', c_ll),
+                ('sBb', c_ll), ('sBk', c_ll), ('sBn', c_ll),
+                ('sCb', c_ll), ('sCm', c_ll), ('sCn', c_ll),
+                ('lim', c_f), ('lim_m', c_i), ('lim_n', c_i), ('lim_k', c_i),
+                ('alpha', C.c_float), ('beta', C.c_float),
+                ('alpha_dev', c_f), ('bias', c_f), ('relu', c_i), ('split_k', c_i)]
+
+
+# name -> argtypes (restype is int unless listed in _RESTYPES)
+_PROTOS = {
+    'gp_version': [],
+    'gp_last_error': [],
+    'gp_launch_count': [],
+    'gp_launch_count_reset': [],
+    'gp_bgemm_f32': [C.POINTER(GpGemm), c_f],
+    'gp_graphconv_fwd': [c_f, c_ll, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_ll, c_f, c_i, c_f],
+    'gp_graphconv_bwd': [c_f, c_f, c_f, c_ll, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_f, c_f,
+                         c_i, c_f],
+    'gp_relu_bn_fwd': [c_f, c_f, c_ll, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f],
+    'gp_gcn_layer_bwd': [c_f, c_ll, c_f, c_f, c_f, c_ll, c_f, c_ll, c_f, c_ll, c_f, c_f, c_i, c_i, c_i, c_i, c_i,
+                         c_i, c_f, c_f],
+    'gp_readout_max_fwd': [c_f, c_ll, c_f, c_i, c_i, c_i, c_f, c_f, c_ll, c_f],
+    'gp_softmax_mask_fwd': [c_f, c_f, c_i, c_i, c_i, c_f],
+    'gp_softmax_mask_bwd': [c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f],
+    'gp_pool_fwd': [c_f, c_f, c_ll, c_f, c_f, c_i, c_i, c_i, c_i, c_f, c_f, c_f, c_i, c_f],
+    'gp_pool_bwd': [c_f, c_f, c_f, c_f, c_ll, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f, c_ll, c_i, c_f, c_i, c_f,
+                    c_f, c_i, c_f],
+    'gp_linkloss_fwd': [c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f, c_f],
+    'gp_loss_finalize': [c_f, c_i, C.c_double, c_f, c_f, c_f, c_f],
+    'gp_ce_fwd': [c_f, c_f, c_i, c_i, c_f, c_f, c_f],
+    'gp_ce_bwd': [c_f, c_f, c_f, c_i, c_i, c_f, c_f],
+    'gp_colsum_f32': [c_f, c_ll, c_i, c_ll, c_f, c_i, c_f, c_f],
+    'gp_relu_mask_bwd': [c_f, c_f, c_ll, c_f, c_f],
+    'gp_fill_f32': [c_f, c_ll, C.c_float, c_f],
+    'gp_axpy_f32': [c_f, c_f, c_ll, C.c_float, c_f],
+}
+_RESTYPES = {'gp_last_error': C.c_char_p, 'gp_launch_count': c_ll, 'gp_launch_count_reset': None}
+
+EXPORTS = tuple(_PROTOS)
+_lib = None
+
+
+class GpError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GpError('libgp_b200.so not found at %s -- run `python -c "import __graft_entry__ as g; g.build()"` '
+                      '(there is no CPU or PyTorch fallback for the hot path)' % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, args in _PROTOS.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is missing
+        fn.argtypes = args
+        fn.restype = _RESTYPES.get(name, c_i)
+    _lib = lib
+    return lib
+
+
+def check(status, what):
+    if status != 0:
+        raise GpError('%s failed (%d): %s' % (what, status, load().gp_last_error().decode()))
+
+
+def call(name, *args):
+    check(getattr(load(), name)(*args), name)

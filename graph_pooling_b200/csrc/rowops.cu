@@ -1,0 +1,440 @@
+// Row / node-index reductions and epilogues of the DiffPool path (fp32, HBM-bound):
+//   bias + L2 normalize (encoders.py:323-326), ReLU + BatchNorm-per-node-index with batch
+//   statistics (encoders.py:1062-1064,1048-1052) and its backward fused with the ReLU mask, the
+//   max-readout scatter and the normalize backward, max readout (encoders.py:1097,1257,1287),
+//   masked assignment softmax (encoders.py:1273-1275), cross entropy (encoders.py:1127), colsum.
+// All reductions are warp-shuffle based over coalesced rows; no atomics, deterministic.
+#include "common.cuh"
+
+namespace gp {
+
+constexpr float kEpsNorm = 1e-12f;
+constexpr float kEpsBn = 1e-5f;
+
+// ---------------------------------------------------------------------------------------------
+// V (+bias) -> Y = V / max(||V||, eps), in place; one warp per row.
+// ---------------------------------------------------------------------------------------------
+__global__ void bias_normalize_kernel(float* __restrict__ v, const float* __restrict__ bias,
+                                      float* __restrict__ rnorm, long long rows, int d, long long ld,
+                                      int normalize) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp; r < rows; r += nwarps) {
+    float* p = v + r * ld;
+    float ss = 0.f;
+    for (int c = lane; c < d; c += 32) {
+      float x = p[c];
+      if (bias != nullptr) { x += bias[c]; p[c] = x; }
+      ss = fmaf(x, x, ss);
+    }
+    if (!normalize) { if (lane == 0 && rnorm) rnorm[r] = 1.f; continue; }
+    ss = warp_sum(ss);
+    const float nrm = fmaxf(sqrtf(ss), kEpsNorm);
+    if (lane == 0 && rnorm) rnorm[r] = nrm;
+    for (int c = lane; c < d; c += 32) p[c] = p[c] / nrm;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ReLU + BN over (batch, feature) per node index n.  One block per node (grid.x = N).
+// Two-pass mean / variance (the block re-reads its B*d elements from L1/L2), third pass writes.
+// ---------------------------------------------------------------------------------------------
+__global__ void relu_bn_fwd_kernel(const float* __restrict__ y, float* __restrict__ h, long long ldh,
+                                   float* __restrict__ mean, float* __restrict__ invstd,
+                                   int B, int N, int d, int relu, int bn) {
+  __shared__ float sh[33];
+  const int n = blockIdx.x;
+  const int total = B * d;
+  float mu = 0.f, is = 1.f;
+  if (bn) {
+    float s = 0.f;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      const int b = i / d, c = i - b * d;
+      float x = y[((long long)b * N + n) * d + c];
+      if (relu) x = fmaxf(x, 0.f);
+      s += x;
+    }
+    mu = block_sum(s, sh) / (float)total;
+    float q = 0.f;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      const int b = i / d, c = i - b * d;
+      float x = y[((long long)b * N + n) * d + c];
+      if (relu) x = fmaxf(x, 0.f);
+      const float t = x - mu;
+      q = fmaf(t, t, q);
+    }
+    const float var = block_sum(q, sh) / (float)total;
+    is = 1.0f / sqrtf(var + kEpsBn);
+    if (threadIdx.x == 0) { mean[n] = mu; invstd[n] = is; }
+  }
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int b = i / d, c = i - b * d;
+    float x = y[((long long)b * N + n) * d + c];
+    if (relu) x = fmaxf(x, 0.f);
+    h[((long long)b * N + n) * ldh + c] = (x - mu) * is;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Backward of [slot + readout scatter + next-layer dX] -> BN -> ReLU -> normalize.
+// One block per node index n; pass 1 block-reduces mean(g) and mean(g*Hhat); pass 2 is one warp
+// per (b, n) row: dR, ReLU mask, <Y,dY> by shuffle, dV.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float layer_g(const float* dz, long long lddz, const float* dxn, const float* dout,
+                                         const int32_t* argidx, long long ldo, int b, int n, int c, int N, int d) {
+  float g = 0.f;
+  const long long row = (long long)b * N + n;
+  if (dz != nullptr) g += dz[row * lddz + c];
+  if (dxn != nullptr) g += dxn[row * d + c];
+  if (dout != nullptr && argidx[(long long)b * ldo + c] == n) g += dout[(long long)b * ldo + c];
+  return g;
+}
+
+__global__ void gcn_layer_bwd_kernel(const float* __restrict__ dz, long long lddz, const float* __restrict__ dxn,
+                                     const float* __restrict__ dout, const int32_t* __restrict__ argidx,
+                                     long long ldo, const float* __restrict__ h, long long ldh,
+                                     const float* __restrict__ y, long long ldy, const float* __restrict__ rnorm,
+                                     const float* __restrict__ invstd, int B, int N, int d, int relu, int bn,
+                                     int normalize, float* __restrict__ dv) {
+  __shared__ float sh[33];
+  const int n = blockIdx.x;
+  const int total = B * d;
+  float m1 = 0.f, m2 = 0.f, is = 1.f;
+  if (bn) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      const int b = i / d, c = i - b * d;
+      const float g = layer_g(dz, lddz, dxn, dout, argidx, ldo, b, n, c, N, d);
+      s1 += g;
+      s2 = fmaf(g, h[((long long)b * N + n) * ldh + c], s2);
+    }
+    m1 = block_sum(s1, sh) / (float)total;
+    m2 = block_sum(s2, sh) / (float)total;
+    is = invstd[n];
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int b = w; b < B; b += nw) {
+    const long long row = (long long)b * N + n;
+    float dot = 0.f;
+    for (int c = lane; c < d; c += 32) {
+      float g = layer_g(dz, lddz, dxn, dout, argidx, ldo, b, n, c, N, d);
+      if (bn) g = (g - m1 - h[row * ldh + c] * m2) * is;
+      const float yy = y[row * ldy + c];
+      if (relu && !(yy > 0.f)) g = 0.f;
+      dot = fmaf(g, yy, dot);
+    }
+    float r = 1.f;
+    bool clamped = false;
+    if (normalize) {
+      dot = warp_sum(dot);
+      r = rnorm[row];
+      clamped = !(r > kEpsNorm);
+    }
+    for (int c = lane; c < d; c += 32) {
+      float g = layer_g(dz, lddz, dxn, dout, argidx, ldo, b, n, c, N, d);
+      if (bn) g = (g - m1 - h[row * ldh + c] * m2) * is;
+      const float yy = y[row * ldy + c];
+      if (relu && !(yy > 0.f)) g = 0.f;
+      if (normalize) g = clamped ? g / kEpsNorm : (g - yy * dot) / r;
+      dv[row * d + c] = g;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Max readout over nodes: block = 32 feature lanes x 8 row groups.
+// ---------------------------------------------------------------------------------------------
+__global__ void readout_max_kernel(const float* __restrict__ z, long long ldz, const int32_t* __restrict__ nb,
+                                   int N, int F, float* __restrict__ out, int32_t* __restrict__ argidx,
+                                   long long ldo) {
+  __shared__ float sv[8][33];
+  __shared__ int si[8][33];
+  const int b = blockIdx.y;
+  const int f = blockIdx.x * 32 + threadIdx.x;
+  const int nreal = nb != nullptr ? min(nb[b], N) : N;
+  float best = -INFINITY;
+  int bi = -1;
+  if (f < F) {
+    const float* p = z + (long long)b * N * ldz + f;
+    for (int n = threadIdx.y; n < nreal; n += 8) {
+      const float v = p[(long long)n * ldz];
+      if (v > best) { best = v; bi = n; }      // strict: lowest index kept within this thread
+    }
+  }
+  sv[threadIdx.y][threadIdx.x] = best;
+  si[threadIdx.y][threadIdx.x] = bi;
+  __syncthreads();
+  if (threadIdx.y == 0 && f < F) {
+    for (int g = 1; g < 8; ++g) {
+      const float v = sv[g][threadIdx.x];
+      const int i = si[g][threadIdx.x];
+      if (i >= 0 && (v > best || (v == best && i < bi) || bi < 0)) { best = v; bi = i; }
+    }
+    if (nreal < N) {                 // masked pad rows count as 0 (index nreal > every real index)
+      if (bi < 0 || 0.f > best) { best = 0.f; bi = -1; }
+    }
+    out[(long long)b * ldo + f] = best;
+    argidx[(long long)b * ldo + f] = bi;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Masked row softmax (in place) and its backward; one warp per row.
+// ---------------------------------------------------------------------------------------------
+__global__ void softmax_mask_fwd_kernel(float* __restrict__ t, const int32_t* __restrict__ nb, long long rows,
+                                        int N, int K) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp; r < rows; r += nwarps) {
+    float* p = t + r * K;
+    const int b = (int)(r / N), n = (int)(r % N);
+    if (nb != nullptr && n >= nb[b]) {
+      for (int c = lane; c < K; c += 32) p[c] = 0.f;
+      continue;
+    }
+    float mx = -INFINITY;
+    for (int c = lane; c < K; c += 32) mx = fmaxf(mx, p[c]);
+    mx = warp_max(mx);
+    float s = 0.f;
+    for (int c = lane; c < K; c += 32) { const float e = expf(p[c] - mx); p[c] = e; s += e; }
+    s = warp_sum(s);
+    for (int c = lane; c < K; c += 32) p[c] = p[c] / s;
+  }
+}
+
+__global__ void softmax_mask_bwd_kernel(const float* __restrict__ s, const float* __restrict__ ds,
+                                        const int32_t* __restrict__ nb, long long rows, int N, int K,
+                                        float* __restrict__ dt) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp; r < rows; r += nwarps) {
+    const int b = (int)(r / N), n = (int)(r % N);
+    const float* sp = s + r * K;
+    const float* gp = ds + r * K;
+    float* o = dt + r * K;
+    if (nb != nullptr && n >= nb[b]) {
+      for (int c = lane; c < K; c += 32) o[c] = 0.f;
+      continue;
+    }
+    float dot = 0.f;
+    for (int c = lane; c < K; c += 32) dot = fmaf(sp[c], gp[c], dot);
+    dot = warp_sum(dot);
+    for (int c = lane; c < K; c += 32) o[c] = sp[c] * (gp[c] - dot);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cross entropy (mean over batch), one block; probabilities saved for the backward.
+// ---------------------------------------------------------------------------------------------
+__global__ void ce_fwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__ label, int B, int C,
+                              float* __restrict__ loss, float* __restrict__ probs) {
+  __shared__ float sh[33];
+  float acc = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const float* p = logits + (long long)b * C;
+    float mx = -INFINITY;
+    for (int c = 0; c < C; ++c) mx = fmaxf(mx, p[c]);
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s += expf(p[c] - mx);
+    const float lse = mx + logf(s);
+    for (int c = 0; c < C; ++c) probs[(long long)b * C + c] = expf(p[c] - lse);
+    acc += lse - p[label[b]];
+  }
+  const float tot = block_sum(acc, sh);
+  if (threadIdx.x == 0) *loss = tot / (float)B;
+}
+
+__global__ void ce_bwd_kernel(const float* __restrict__ probs, const int64_t* __restrict__ label,
+                              const float* __restrict__ upstream, int B, int C, float* __restrict__ dlogits) {
+  const float g = (upstream != nullptr ? *upstream : 1.f) / (float)B;
+  const int total = B * C;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = i / C, c = i - b * C;
+    dlogits[i] = g * (probs[i] - (label[b] == c ? 1.f : 0.f));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Column sum, two deterministic stages: partial[R][d] then out[d].
+// ---------------------------------------------------------------------------------------------
+__global__ void colsum_stage1(const float* __restrict__ x, long long rows, int d, long long ld, int R,
+                              float* __restrict__ partial) {
+  __shared__ float sh[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int r = blockIdx.y;
+  const long long per = (rows + R - 1) / R;
+  const long long r0 = r * per, r1 = min(rows, r0 + per);
+  float s = 0.f;
+  if (c < d)
+    for (long long i = r0 + threadIdx.y; i < r1; i += 8) s += x[i * ld + c];
+  sh[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < d) {
+    for (int g = 1; g < 8; ++g) s += sh[g][threadIdx.x];
+    partial[(long long)r * d + c] = s;
+  }
+}
+__global__ void colsum_stage2(const float* __restrict__ partial, int R, int d, float* __restrict__ out,
+                              int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  float s = 0.f;
+  for (int r = 0; r < R; ++r) s += partial[(long long)r * d + c];
+  out[c] = accumulate ? out[c] + s : s;
+}
+
+__global__ void relu_mask_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, long long n,
+                                     float* __restrict__ dx) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dx[i] = y[i] > 0.f ? dy[i] : 0.f;
+}
+
+__global__ void fill_kernel(float* __restrict__ x, long long n, float v) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    x[i] = v;
+}
+__global__ void axpy_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float a) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = fmaf(a, x[i], y[i]);
+}
+
+static inline int warp_grid(long long rows, int threads) {
+  const long long per = threads / 32;
+  long long blocks = (rows + per - 1) / per;
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+int bias_normalize(float* v, const float* bias, float* rnorm, long long rows, int d, long long ld,
+                   int normalize, cudaStream_t st) {
+  bias_normalize_kernel<<<warp_grid(rows, 256), 256, 0, st>>>(v, bias, rnorm, rows, d, ld, normalize);
+  GP_LAUNCHED();
+  return GP_OK;
+}
+
+int colsum(const float* x, long long rows, int d, long long ld, float* out, int accumulate, float* ws,
+           cudaStream_t st) {
+  GP_REQUIRE(x && out && ws && d > 0, "colsum: bad args");
+  int R = (int)((rows + 63) / 64);
+  if (R > 256) R = 256;
+  if (R < 1) R = 1;
+  dim3 grid((d + 31) / 32, R), block(32, 8);
+  colsum_stage1<<<grid, block, 0, st>>>(x, rows, d, ld, R, ws);
+  GP_LAUNCHED();
+  colsum_stage2<<<(d + 127) / 128, 128, 0, st>>>(ws, R, d, out, accumulate);
+  GP_LAUNCHED();
+  return GP_OK;
+}
+
+}  // namespace gp
+
+using namespace gp;
+
+extern "C" int gp_relu_bn_fwd(const float* y, float* h, long long ldh, float* mean, float* invstd, int B, int N,
+                              int d, int relu, int bn, gp_stream_t stream) {
+  GP_REQUIRE(y && h && B > 0 && N > 0 && d > 0 && ldh >= d, "relu_bn_fwd: bad args");
+  GP_REQUIRE(!bn || (mean && invstd), "relu_bn_fwd: bn needs mean/invstd");
+  const int total = B * d;
+  const int threads = total >= 4096 ? 512 : (total >= 512 ? 256 : 128);
+  relu_bn_fwd_kernel<<<N, threads, 0, S(stream)>>>(y, h, ldh, mean, invstd, B, N, d, relu, bn);
+  GP_LAUNCHED();
+  return GP_OK;
+}
+
+extern "C" int gp_gcn_layer_bwd(const float* dz, long long lddz, const float* dxn, const float* dout,
+                                const int32_t* argidx, long long ldo, const float* h, long long ldh,
+                                const float* y, long long ldy, const float* rnorm, const float* invstd,
+                                int B, int N, int d, int relu, int bn, int normalize, float* dv,
+                                gp_stream_t stream) {
+  GP_REQUIRE(y && dv && B > 0 && N > 0 && d > 0, "gcn_layer_bwd: bad args");
+  GP_REQUIRE(!bn || (h && invstd), "gcn_layer_bwd: bn needs h/invstd");
+  GP_REQUIRE(!normalize || rnorm, "gcn_layer_bwd: normalize needs rnorm");
+  GP_REQUIRE(!dout || argidx, "gcn_layer_bwd: dout needs argidx");
+  const int total = B * d;
+  const int threads = total >= 4096 ? 512 : (total >= 512 ? 256 : 128);
+  gcn_layer_bwd_kernel<<<N, threads, 0, S(stream)>>>(dz, lddz, dxn, dout, argidx, ldo, h, ldh, y, ldy, rnorm,
+                                                      invstd, B, N, d, relu, bn, normalize, dv);
+  GP_LAUNCHED();
+  return GP_OK;
+}
+
+extern "C" int gp_readout_max_fwd(const float* z, long long ldz, const int32_t* nb, int B, int N, int F,
+                                  float* out, int32_t* argidx, long long ldo, gp_stream_t stream) {
+  GP_REQUIRE(z && out && argidx && B > 0 && N > 0 && F > 0, "readout_max_fwd: bad args");
+  GP_REQUIRE(B <= 65535, "readout_max_fwd: B too large");
+  dim3 grid((F + 31) / 32, B), block(32, 8);
+  readout_max_kernel<<<grid, block, 0, S(stream)>>>(z, ldz, nb, N, F, out, argidx, ldo);
+  GP_LAUNCHED();
+  return GP_OK;
+}
+
+extern "C" int gp_softmax_mask_fwd(float* t, const int32_t* nb, int B, int N, int K, gp_stream_t stream) {
+  GP_REQUIRE(t && B > 0 && N > 0 && K > 0, "softmax_mask_fwd: bad args");
+  const long long rows = (long long)B * N;
+  softmax_mask_fwd_kernel<<<warp_grid(rows, 256), 256, 0, S(stream)>>>(t, nb, rows, N, K);
+  GP_LAUNCHED();
+  return GP_OK;
+}
+
+extern "C" int gp_softmax_mask_bwd(const float* s, const float* ds, const int32_t* nb, int B, int N, int K,
+                                   float* dt, gp_stream_t stream) {
+  GP_REQUIRE(s && ds && dt && B > 0 && N > 0 && K > 0, "softmax_mask_bwd: bad args");
+  const long long rows = (long long)B * N;
+  softmax_mask_bwd_kernel<<<warp_grid(rows, 256), 256, 0, S(stream)>>>(s, ds, nb, rows, N, K, dt);
+  GP_LAUNCHED();
+  return GP_OK;
+}
+
+extern "C" int gp_ce_fwd(const float* logits, const int64_t* label, int B, int C, float* loss, float* probs,
+                         gp_stream_t stream) {
+  GP_REQUIRE(logits && label && loss && probs && B > 0 && C > 0, "ce_fwd: bad args");
+  ce_fwd_kernel<<<1, 256, 0, S(stream)>>>(logits, label, B, C, loss, probs);
+  GP_LAUNCHED();
+  return GP_OK;
+}
+
+extern "C" int gp_ce_bwd(const float* probs, const int64_t* label, const float* upstream, int B, int C,
+                         float* dlogits, gp_stream_t stream) {
+  GP_REQUIRE(probs && label && dlogits && B > 0 && C > 0, "ce_bwd: bad args");
+  const int total = B * C;
+  ce_bwd_kernel<<<(total + 255) / 256, 256, 0, S(stream)>>>(probs, label, upstream, B, C, dlogits);
+  GP_LAUNCHED();
+  return GP_OK;
+}
+
+extern "C" int gp_colsum_f32(const float* x, long long rows, int d, long long ld, float* out, int accumulate,
+                             float* ws, gp_stream_t stream) {
+  return colsum(x, rows, d, ld, out, accumulate, ws, S(stream));
+}
+
+extern "C" int gp_relu_mask_bwd(const float* dy, const float* y, long long n, float* dx, gp_stream_t stream) {
+  GP_REQUIRE(dy && y && dx && n > 0, "relu_mask_bwd: bad args");
+  long long blocks = (n + 255) / 256;
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  relu_mask_bwd_kernel<<<(int)blocks, 256, 0, S(stream)>>>(dy, y, n, dx);
+  GP_LAUNCHED();
+  return GP_OK;
+}
+
+extern "C" int gp_fill_f32(float* x, long long n, float v, gp_stream_t stream) {
+  GP_REQUIRE(x && n >= 0, "fill: bad args");
+  if (n == 0) return GP_OK;
+  long long blocks = (n + 255) / 256;
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  fill_kernel<<<(int)blocks, 256, 0, S(stream)>>>(x, n, v);
+  GP_LAUNCHED();
+  return GP_OK;
+}
+
+extern "C" int gp_axpy_f32(const float* x, float* y, long long n, float a, gp_stream_t stream) {
+  GP_REQUIRE(x && y && n > 0, "axpy: bad args");
+  long long blocks = (n + 255) / 256;
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  axpy_kernel<<<(int)blocks, 256, 0, S(stream)>>>(x, y, n, a);
+  GP_LAUNCHED();
+  return GP_OK;
+}

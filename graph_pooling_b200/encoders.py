@@ -1,0 +1,550 @@
+"""Drop-in replacement for the DiffPool half of the reference's ``encoders`` module.
+
+Same class names, constructor signatures, ``forward(x, adj, batch_num_nodes, assign_x=...)``,
+``loss(...)``, attributes (``assign_tensor``, ``link_loss``) and state-dict keys as
+``/root/reference/encoders.py:976-1334`` so that ``train.py`` / ``cross_val.py`` can run against
+it unchanged (``import encoders`` -> this module, see graph_pooling_b200/shim.py).
+
+Every tensor op of forward / loss / backward runs in hand-written sm_100a kernels behind the C
+ABI (include/gp_b200.h); see engine.py for the schedule.  Deviations from the shipped reference
+text are the documented repairs R1-R11 (oracle/diffpool_oracle.py header).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.autograd.function import once_differentiable
+
+from . import engine as E
+from ._lib import call
+
+__all__ = ['GraphConv', 'GcnEncoderGraph', 'GcnSet2SetEncoder', 'SoftPoolingGcnEncoder']
+
+
+# ------------------------------------------------------------------------------------------
+# autograd glue: one Function for the whole encoder, one for the loss
+# ------------------------------------------------------------------------------------------
+class _Plan:
+    """Static description of one forward call (indices into the flat parameter list)."""
+    pass
+
+
+def _wb(params, pair):
+    iw, ib = pair
+    return params[iw], (None if ib is None else params[ib])
+
+
+class _EncoderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan, x, adj, assign_x, *params):
+        ctx.set_materialize_grads(False)
+        st = E._stream()
+        ws = E.Workspace(x.device)
+        B, N, D = x.shape
+        prec = plan.precision
+        nb = plan.nb_dev
+        tape = {'plan': plan, 'params': params, 'B': B, 'N': N}
+        conv = lambda pairs: ([_wb(params, p)[0] for p in pairs], [_wb(params, p)[1] for p in pairs])
+        P = plan.num_pooling
+        Fw = plan.F
+        out = ws.f(B, Fw * (P + 1))
+        arg = ws.i(B, Fw * (P + 1))
+        ldo = Fw * (P + 1)
+
+        w0, b0 = conv(plan.emb)
+        z, c_emb = E.stack_forward(ws, x.data_ptr(), D, D, adj, nb, B, N, w0, b0, plan.add_self, plan.bn, prec)
+        # base path: no mask ever (encoders.py:1087 builds it, nothing uses it); soft: mask of :1078
+        call('gp_readout_max_fwd', z.data_ptr(), Fw, E._p(nb) if plan.soft else None, B, N, Fw,
+             out.data_ptr(), arg.data_ptr(), ldo, st)
+        tape['emb'] = c_emb
+        levels = []
+        S0 = None
+        if plan.soft:
+            xa_ptr, xa_d = assign_x.data_ptr(), assign_x.shape[2]
+            cur_adj, cur_nb, cur_N, cur_z = adj, nb, N, z
+            for i in range(P):
+                K = plan.assign_dims[i]
+                wa, ba = conv(plan.assign[i])
+                za, c_as = E.stack_forward(ws, xa_ptr, xa_d, xa_d, cur_adj, cur_nb, B, cur_N, wa, ba,
+                                           plan.add_self, True, prec)
+                Fa = za.shape[2]
+                wp, bp = _wb(params, plan.assign_pred[i])
+                # S = softmax(Linear(za)) * mask   (pad rows -> 0; masking za first is a no-op for real rows)
+                S = E.linear_fwd(ws, za.data_ptr(), Fa, B * cur_N, wp, bp, relu=False).view(B, cur_N, K)
+                call('gp_softmax_mask_fwd', S.data_ptr(), E._p(cur_nb), B, cur_N, K, st)
+                xp, t, ap = ws.f(B, K, Fw), ws.f(B, K, cur_N), ws.f(B, K, K)
+                call('gp_pool_fwd', S.data_ptr(), cur_z.data_ptr(), Fw, cur_adj.data_ptr(), E._p(cur_nb), B, cur_N,
+                     K, Fw, xp.data_ptr(), t.data_ptr(), ap.data_ptr(), prec, st)
+                wq, bq = conv(plan.post[i])
+                z2, c_post = E.stack_forward(ws, xp.data_ptr(), Fw, Fw, ap, None, B, K, wq, bq, plan.add_self,
+                                             plan.bn_post, prec)
+                call('gp_readout_max_fwd', z2.data_ptr(), Fw, None, B, K, Fw, out.data_ptr() + (i + 1) * Fw * 4,
+                     arg.data_ptr() + (i + 1) * Fw * 4, ldo, st)
+                levels.append(dict(K=K, N=cur_N, nb=cur_nb, adj=cur_adj, z=cur_z, S=S, za=za, Fa=Fa, c_as=c_as,
+                                   xp=xp, t=t, ap=ap, c_post=c_post, wp=wp, has_bp=bp is not None))
+                if i == 0:
+                    S0 = S
+                xa_ptr, xa_d = xp.data_ptr(), Fw
+                cur_adj, cur_nb, cur_N, cur_z = ap, None, K, z2
+        # concat=False (base only): the last layer's readout alone feeds pred_model (:1119)
+        pin_off = 0 if plan.concat else Fw - plan.douts_last
+        lin = [_wb(params, p) for p in plan.pred]
+        ypred, acts = E.mlp_fwd(ws, out.data_ptr() + pin_off * 4, ldo, B, lin)
+        tape.update(levels=levels, out=out, arg=arg, ldo=ldo, acts=acts, lin=lin, x=x, adj=adj, assign_x=assign_x)
+        ctx.tape = tape
+        if plan.soft:
+            plan.all_S = [lv['S'] for lv in levels]
+            return ypred, S0
+        return ypred
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dypred, dS0=None):
+        tape = ctx.tape
+        if tape is None:
+            raise RuntimeError('gp_b200: backward called twice (buffers were freed)')
+        ctx.tape = None
+        plan, params = tape['plan'], tape['params']
+        B, N = tape['B'], tape['N']
+        st = E._stream()
+        ws = E.Workspace(tape['x'].device)
+        prec = plan.precision
+        Fw = plan.F
+        P = plan.num_pooling
+        grads = [None] * len(params)
+
+        def put(pairs, gl):
+            for (iw, ib), (dw, db) in zip(pairs, gl):
+                grads[iw] = dw
+                if ib is not None:
+                    grads[ib] = db
+
+        ldo = tape['ldo']
+        if dypred is None:
+            dypred = ws.z(B, plan.label_dim)
+        dypred = E._chk(dypred, 'grad of ypred')
+        pin_off = 0 if plan.concat else Fw - plan.douts_last
+        dout = ws.f(B, ldo) if plan.concat else ws.z(B, ldo)
+        gl = E.mlp_bwd(ws, dypred, B, tape['acts'], tape['lin'], dout.data_ptr() + pin_off * 4, ldo)
+        put(plan.pred, gl)
+        dout_p, arg_p = dout.data_ptr(), tape['arg'].data_ptr()
+
+        dz_dense = None          # dense gradient of the current level's embedding concat buffer
+        if plan.soft:
+            levels = tape['levels']
+            d_ap = [ws.z(B, lv['K'], lv['K']) for lv in levels]
+            dxp_extra = [None] * P
+            dz_next = None
+            for i in reversed(range(P)):
+                lv = levels[i]
+                K, Ni = lv['K'], lv['N']
+                # 1. post-pool GCN
+                gl, dxp = E.stack_backward(ws, lv['c_post'], None if dz_next is None else dz_next.data_ptr(), Fw,
+                                           dout_p + (i + 1) * Fw * 4, arg_p + (i + 1) * Fw * 4, ldo, True,
+                                           d_ap[i], prec)
+                put(plan.post[i], gl)
+                if dxp_extra[i] is not None:
+                    call('gp_axpy_f32', dxp_extra[i].data_ptr(), dxp.data_ptr(), C.c_longlong(dxp.numel()),
+                         C.c_float(1.0), st)
+                # 2. pooling
+                dz = ws.f(B, Ni, Fw)
+                if i == 0 and dS0 is not None:
+                    ds, acc_ds = E._chk(dS0, 'grad of assign_tensor'), 1
+                else:
+                    ds, acc_ds = ws.f(B, Ni, K), 0
+                wsp = ws.f(B, Ni, K)
+                call('gp_pool_bwd', dxp.data_ptr(), d_ap[i].data_ptr(), lv['S'].data_ptr(), lv['z'].data_ptr(), Fw,
+                     lv['adj'].data_ptr(), lv['t'].data_ptr(), E._p(lv['nb']), B, Ni, K, Fw, dz.data_ptr(), Fw, 0,
+                     ds.data_ptr(), acc_ds, None if i == 0 else d_ap[i - 1].data_ptr(), wsp.data_ptr(), prec, st)
+                # 3. assignment head: softmax -> Linear
+                dt = ws.f(B, Ni, K)
+                call('gp_softmax_mask_bwd', lv['S'].data_ptr(), ds.data_ptr(), E._p(lv['nb']), B, Ni, K,
+                     dt.data_ptr(), st)
+                dwp, dbp, dza = E.linear_bwd(ws, dt, lv['za'].data_ptr(), lv['Fa'], B * Ni, lv['wp'], lv['has_bp'],
+                                             True)
+                iw, ib = plan.assign_pred[i]
+                grads[iw] = dwp
+                if ib is not None:
+                    grads[ib] = dbp
+                # 4. assignment GCN
+                gl, dxa = E.stack_backward(ws, lv['c_as'], dza.data_ptr(), lv['Fa'], None, None, 0, i > 0,
+                                           None if i == 0 else d_ap[i - 1], prec)
+                put(plan.assign[i], gl)
+                if i > 0:
+                    dxp_extra[i - 1] = dxa
+                dz_next = dz
+            dz_dense = dz_next
+        gl, _ = E.stack_backward(ws, tape['emb'], None if dz_dense is None else dz_dense.data_ptr(), Fw, dout_p,
+                                 arg_p, ldo, False, None, prec)
+        put(plan.emb, gl)
+        return (None, None, None, None) + tuple(grads)
+
+
+class _LossFn(torch.autograd.Function):
+    """CE (encoders.py:1127) [+ masked-BCE link loss (encoders.py:1311-1331)]."""
+
+    @staticmethod
+    def forward(ctx, plan, ypred, label, S, adj):
+        st = E._stream()
+        ws = E.Workspace(ypred.device)
+        B, Cc = ypred.shape
+        ypred = E._chk(ypred, 'pred')
+        if label.dtype != torch.int64 or not label.is_cuda:
+            raise ValueError('label must be a CUDA int64 tensor')
+        ce, probs = ws.f(1), ws.f(B, Cc)
+        call('gp_ce_fwd', ypred.data_ptr(), label.data_ptr(), B, Cc, ce.data_ptr(), probs.data_ptr(), st)
+        ctx.probs, ctx.label, ctx.B, ctx.C = probs, label, B, Cc
+        ctx.link = S is not None
+        if S is None:
+            return ce.view(())
+        Bn, N, K = S.shape
+        T = (N + 63) // 64
+        partial = ws.f(Bn * T * T)
+        need_grad = ctx.needs_input_grad[3]
+        gsym = ws.f(Bn, N, N) if need_grad else None
+        call('gp_linkloss_fwd', S.data_ptr(), adj.data_ptr(), E._p(plan.nb_dev), Bn, N, K, partial.data_ptr(),
+             E._p(gsym), st)
+        total, link = ws.f(1), ws.f(1)
+        inv = 1.0 / float(plan.num_entries)
+        call('gp_loss_finalize', partial.data_ptr(), Bn * T * T, C.c_double(inv), ce.data_ptr(), total.data_ptr(),
+             link.data_ptr(), st)
+        ctx.gsym, ctx.S, ctx.inv, ctx.nb = gsym, S, inv, plan.nb_dev
+        link = link.view(())
+        ctx.mark_non_differentiable(link)
+        return total.view(()), link
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g, _glink=None):
+        st = E._stream()
+        ws = E.Workspace(g.device)
+        g = E._chk(g, 'grad of loss')
+        dy = ws.f(ctx.B, ctx.C)
+        call('gp_ce_bwd', ctx.probs.data_ptr(), ctx.label.data_ptr(), g.data_ptr(), ctx.B, ctx.C, dy.data_ptr(), st)
+        dS = None
+        if ctx.link and ctx.gsym is not None:
+            S = ctx.S
+            Bn, N, K = S.shape
+            dS = ws.f(Bn, N, K)
+            lim = ctx.nb is not None
+            E.bgemm(ctx.gsym.data_ptr(), S.data_ptr(), dS.data_ptr(), N, K, N, Bn, (N * N, N, 1), (N * K, K, 1),
+                    (N * K, K, 1), lim=E._p(ctx.nb), lim_m=int(lim), lim_k=int(lim), alpha=ctx.inv,
+                    alpha_dev=g.data_ptr())
+            ctx.gsym = None
+        return None, dy, None, dS, None
+
+
+# ------------------------------------------------------------------------------------------
+# modules
+# ------------------------------------------------------------------------------------------
+class GraphConv(nn.Module):
+    """R1: the DiffPool GraphConv of encoders.py:296-328 (weight is [in, out], x@W layout)."""
+
+    def __init__(self, input_dim, output_dim, add_self=False, normalize_embedding=False,
+                 dropout=0.0, bias=True):
+        super().__init__()
+        self.add_self = add_self
+        self.dropout = dropout
+        if dropout > 0.001:
+            self.dropout_layer = nn.Dropout(p=dropout)
+        self.normalize_embedding = normalize_embedding
+        self.input_dim = input_dim
+        self.output_dim = output_dim
+        self.weight = nn.Parameter(torch.empty(input_dim, output_dim))
+        nn.init.xavier_uniform_(self.weight.data, gain=nn.init.calculate_gain('relu'))
+        if bias:
+            self.bias = nn.Parameter(torch.zeros(output_dim))
+        else:
+            self.bias = None
+
+    def forward(self, x, adj):
+        return _GraphConvFn.apply(x, adj, self.weight, self.bias, self.add_self, self.normalize_embedding)
+
+
+class _GraphConvFn(torch.autograd.Function):
+    """Stand-alone GraphConv (the encoders below run whole stacks through _EncoderFn instead)."""
+
+    @staticmethod
+    def forward(ctx, x, adj, w, b, add_self, normalize):
+        x, adj = E._chk(x, 'x'), E._chk(adj, 'adj')
+        B, N, din = x.shape
+        dout = w.shape[1]
+        ws = E.Workspace(x.device)
+        u, y, rn = ws.f(B, N, din), ws.f(B, N, dout), ws.f(B, N)
+        call('gp_graphconv_fwd', x.data_ptr(), din, adj.data_ptr(), w.data_ptr(), E._p(b), None, B, N, din, dout,
+             int(add_self), int(normalize), u.data_ptr(), y.data_ptr(), dout, rn.data_ptr(), E.F32, E._stream())
+        ctx.saved = (x, adj, w, b is not None, u, y, rn, add_self, normalize)
+        ctx.need = (ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, adj, w, has_b, u, y, rn, add_self, normalize = ctx.saved
+        B, N, din = x.shape
+        dout = w.shape[1]
+        ws = E.Workspace(x.device)
+        dy = E._chk(dy, 'dy')
+        dv = ws.f(B, N, dout)
+        call('gp_gcn_layer_bwd', dy.data_ptr(), dout, None, None, None, 0, None, 0, y.data_ptr(), dout,
+             rn.data_ptr(), None, B, N, dout, 0, 0, int(normalize), dv.data_ptr(), E._stream())
+        need_dx, need_da = ctx.need
+        dw, db = ws.f(din, dout), (ws.f(dout) if has_b else None)
+        du = ws.f(B, N, din) if (need_dx or need_da) else None
+        dx = ws.f(B, N, din) if need_dx else None
+        da = ws.z(B, N, N) if need_da else None
+        cs = ws.f(256 * dout)
+        call('gp_graphconv_bwd', dv.data_ptr(), u.data_ptr(), x.data_ptr(), din, adj.data_ptr(), w.data_ptr(), None,
+             B, N, din, dout, int(add_self), dw.data_ptr(), E._p(db), E._p(du), E._p(dx), E._p(da), cs.data_ptr(),
+             E.F32, E._stream())
+        return dx, da, dw, db, None, None
+
+
+class GcnEncoderGraph(nn.Module):
+    """encoders.py:976-1134 (method=base)."""
+
+    def __init__(self, input_dim, hidden_dim, embedding_dim, label_dim, num_layers,
+                 pred_hidden_dims=[], concat=True, bn=True, dropout=0.0, args=None):
+        super().__init__()
+        self.concat = concat
+        add_self = not concat
+        self.bn = bn
+        self.num_layers = num_layers
+        self.num_aggs = 1
+        self.precision = E.F32
+        self.bias = True
+        if args is not None:
+            self.bias = args.bias
+        if dropout > 0.001:
+            # only conv_block layers would use it (encoders.py:1015); callers default to 0.0
+            raise NotImplementedError('gp_b200: dropout > 0 is not implemented on the CUDA path')
+        self.conv_first, self.conv_block, self.conv_last = self.build_conv_layers(
+            input_dim, hidden_dim, embedding_dim, num_layers, add_self, normalize=True, dropout=dropout)
+        self.act = nn.ReLU()
+        self.label_dim = label_dim
+        if concat:
+            self.pred_input_dim = hidden_dim * (num_layers - 1) + embedding_dim
+        else:
+            self.pred_input_dim = embedding_dim
+        self.pred_model = self.build_pred_layers(self.pred_input_dim, pred_hidden_dims, label_dim,
+                                                 num_aggs=self.num_aggs)
+        self._reinit()
+
+    def _reinit(self):
+        for m in self.modules():                                             # encoders.py:1003-1007
+            if isinstance(m, GraphConv):
+                nn.init.xavier_uniform_(m.weight.data, gain=nn.init.calculate_gain('relu'))
+                if m.bias is not None:
+                    nn.init.constant_(m.bias.data, 0.0)
+
+    def build_conv_layers(self, input_dim, hidden_dim, embedding_dim, num_layers, add_self,
+                          normalize=False, dropout=0.0):
+        conv_first = GraphConv(input_dim=input_dim, output_dim=hidden_dim, add_self=add_self,
+                               normalize_embedding=normalize, bias=self.bias)
+        conv_block = nn.ModuleList(
+            [GraphConv(input_dim=hidden_dim, output_dim=hidden_dim, add_self=add_self,
+                       normalize_embedding=normalize, dropout=dropout, bias=self.bias)
+             for _ in range(num_layers - 2)])
+        conv_last = GraphConv(input_dim=hidden_dim, output_dim=embedding_dim, add_self=add_self,
+                              normalize_embedding=normalize, bias=self.bias)
+        return conv_first, conv_block, conv_last
+
+    def build_pred_layers(self, pred_input_dim, pred_hidden_dims, label_dim, num_aggs=1):
+        pred_input_dim = pred_input_dim * num_aggs
+        if len(pred_hidden_dims) == 0:
+            return nn.Linear(pred_input_dim, label_dim)
+        layers = []
+        for pred_dim in pred_hidden_dims:
+            layers.append(nn.Linear(pred_input_dim, pred_dim))
+            layers.append(self.act)
+            pred_input_dim = pred_dim
+        layers.append(nn.Linear(pred_dim, label_dim))
+        return nn.Sequential(*layers)
+
+    def construct_mask(self, max_nodes, batch_num_nodes):
+        """Kept for API compatibility (encoders.py:1035-1046); the kernels never materialise it."""
+        nb = torch.as_tensor(np.asarray(batch_num_nodes).astype(np.int64))
+        return (torch.arange(max_nodes)[None, :] < nb[:, None]).float().unsqueeze(2)
+
+    # ---- plan construction -----------------------------------------------------------------
+    def _conv_pairs(self, params, first, block, last):
+        pairs = []
+        for m in [first] + list(block) + [last]:
+            params.append(m.weight)
+            iw = len(params) - 1
+            ib = None
+            if m.bias is not None:
+                params.append(m.bias)
+                ib = len(params) - 1
+            pairs.append((iw, ib))
+        return pairs
+
+    def _pred_pairs(self, params, model):
+        mods = [model] if isinstance(model, nn.Linear) else [m for m in model if isinstance(m, nn.Linear)]
+        pairs = []
+        for m in mods:
+            params.append(m.weight)
+            iw = len(params) - 1
+            ib = None
+            if m.bias is not None:
+                params.append(m.bias)
+                ib = len(params) - 1
+            pairs.append((iw, ib))
+        return pairs
+
+    def _base_plan(self, x, adj, batch_num_nodes):
+        x, adj = E._chk(x, 'x'), E._chk(adj, 'adj')
+        if x.dim() != 3 or adj.dim() != 3 or adj.shape[1] != adj.shape[2] or adj.shape[:2] != x.shape[:2]:
+            raise ValueError('expected x [B,N,D] and adj [B,N,N], got %s and %s' % (tuple(x.shape), tuple(adj.shape)))
+        if x.shape[2] != self.conv_first.weight.shape[0]:
+            raise ValueError('input feature dim %d != conv_first input dim %d'
+                             % (x.shape[2], self.conv_first.weight.shape[0]))
+        plan = _Plan()
+        plan.precision = self.precision
+        plan.nb_dev, plan.nb_host = E.prep_nb(batch_num_nodes, adj.shape[1], x.device)
+        if plan.nb_host is not None and len(plan.nb_host) != x.shape[0]:
+            raise ValueError('batch_num_nodes has %d entries for a batch of %d' % (len(plan.nb_host), x.shape[0]))
+        plan.concat = self.concat
+        plan.add_self = not self.concat
+        plan.bn = self.bn
+        plan.label_dim = self.label_dim
+        params = []
+        plan.emb = self._conv_pairs(params, self.conv_first, self.conv_block, self.conv_last)
+        plan.F = sum(params[iw].shape[1] for iw, _ in plan.emb)
+        plan.douts_last = self.conv_last.weight.shape[1]
+        return plan, params, x, adj
+
+    def forward(self, x, adj, batch_num_nodes=None, **kwargs):
+        plan, params, x, adj = self._base_plan(x, adj, batch_num_nodes)
+        plan.soft = False
+        plan.num_pooling = 0
+        plan.pred = self._pred_pairs(params, self.pred_model)
+        self._plan = plan
+        return _EncoderFn.apply(plan, x, adj, None, *params)
+
+    def loss(self, pred, label, type='softmax'):
+        if type != 'softmax':
+            raise NotImplementedError("gp_b200: only type='softmax' is implemented (callers never pass 'margin')")
+        plan = getattr(self, '_plan', None) or _Plan()
+        return _LossFn.apply(plan, pred, label, None, None)
+
+
+class GcnSet2SetEncoder(GcnEncoderGraph):
+    """encoders.py:1137-1157 (method=base-set2set) -- outside the north-star path.
+    Constructible for import compatibility; forward is not implemented on the CUDA path yet."""
+
+    def __init__(self, input_dim, hidden_dim, embedding_dim, label_dim, num_layers,
+                 pred_hidden_dims=[], concat=True, bn=True, dropout=0.0, args=None):
+        super().__init__(input_dim, hidden_dim, embedding_dim, label_dim, num_layers, pred_hidden_dims, concat,
+                         bn, dropout, args=args)
+
+    def forward(self, x, adj, batch_num_nodes=None, **kwargs):
+        raise NotImplementedError('gp_b200: GcnSet2SetEncoder (Set2Set readout) is out of the hot-path scope')
+
+
+class SoftPoolingGcnEncoder(GcnEncoderGraph):
+    """encoders.py:1160-1334 (method=soft-assign, DiffPool)."""
+
+    def __init__(self, max_num_nodes, input_dim, hidden_dim, embedding_dim, label_dim, num_layers,
+                 assign_hidden_dim, assign_ratio=0.25, assign_num_layers=-1, num_pooling=1,
+                 pred_hidden_dims=[50], concat=True, bn=True, dropout=0.0, linkpred=True,
+                 assign_input_dim=-1, args=None):
+        # R8: bn / dropout are NOT forwarded to the first GCN (encoders.py:1172-1173)
+        super().__init__(input_dim, hidden_dim, embedding_dim, label_dim, num_layers,
+                         pred_hidden_dims=pred_hidden_dims, concat=concat, args=args)
+        if not concat:
+            # the reference's gcn_forward always concatenates (encoders.py:1078) while the post-pool
+            # GCN is sized for embedding_dim only (:1185-1186): concat=False cannot run there either.
+            raise NotImplementedError('gp_b200: SoftPoolingGcnEncoder requires concat=True (as the reference does)')
+        if dropout > 0.001:
+            raise NotImplementedError('gp_b200: dropout > 0 is not implemented on the CUDA path')
+        add_self = not concat
+        self.num_pooling = num_pooling
+        self.linkpred = linkpred
+        self.assign_ent = True
+
+        def reg(name, i, mod):                                               # R5
+            setattr(self, name if i == num_pooling - 1 else '%s_l%d' % (name, i), mod)
+            return mod
+
+        self.conv_first_after_pool, self.conv_block_after_pool, self.conv_last_after_pool = [], [], []
+        for i in range(num_pooling):
+            f, b, l = self.build_conv_layers(self.pred_input_dim, hidden_dim, embedding_dim, num_layers,
+                                             add_self, normalize=True, dropout=dropout)
+            self.conv_first_after_pool.append(reg('conv_first2', i, f))
+            self.conv_block_after_pool.append(reg('conv_block2', i, b))
+            self.conv_last_after_pool.append(reg('conv_last2', i, l))
+
+        if assign_num_layers == -1:
+            assign_num_layers = num_layers
+        if assign_input_dim == -1:
+            assign_input_dim = input_dim
+        self.assign_conv_first_modules, self.assign_conv_block_modules = [], []
+        self.assign_conv_last_modules, self.assign_pred_modules = [], []
+        self.assign_dims = []
+        assign_dim = int(max_num_nodes * assign_ratio)
+        for i in range(num_pooling):
+            if assign_dim < 1:
+                raise ValueError('assign_dim became 0 at pooling level %d' % i)
+            self.assign_dims.append(assign_dim)
+            f, b, l = self.build_conv_layers(assign_input_dim, assign_hidden_dim, assign_dim,
+                                             assign_num_layers, add_self, normalize=True)
+            apin = assign_hidden_dim * (num_layers - 1) + assign_dim if concat else assign_dim
+            ap = self.build_pred_layers(apin, [], assign_dim, num_aggs=1)
+            assign_input_dim = self.pred_input_dim                           # R6
+            assign_dim = int(assign_dim * assign_ratio)
+            self.assign_conv_first_modules.append(reg('assign_conv_first', i, f))
+            self.assign_conv_block_modules.append(reg('assign_conv_block', i, b))
+            self.assign_conv_last_modules.append(reg('assign_conv_last', i, l))
+            self.assign_pred_modules.append(reg('assign_pred', i, ap))
+
+        self.pred_model = self.build_pred_layers(self.pred_input_dim * (num_pooling + 1), pred_hidden_dims,
+                                                 label_dim, num_aggs=self.num_aggs)
+        self._reinit()
+
+    def forward(self, x, adj, batch_num_nodes, **kwargs):
+        plan, params, x, adj = self._base_plan(x, adj, batch_num_nodes)
+        x_a = E._chk(kwargs['assign_x'], 'assign_x') if 'assign_x' in kwargs else x
+        if x_a.shape[:2] != x.shape[:2]:
+            raise ValueError('assign_x batch/node dims differ from x')
+        plan.soft = True
+        plan.bn = True                   # R8: the first GCN always uses BN
+        plan.bn_post = True              # post-pool stacks share self.bn == True (ctor default, :1172)
+        plan.num_pooling = self.num_pooling
+        plan.assign_dims = list(self.assign_dims)
+        plan.post, plan.assign, plan.assign_pred = [], [], []
+        for i in range(self.num_pooling):
+            plan.post.append(self._conv_pairs(params, self.conv_first_after_pool[i], self.conv_block_after_pool[i],
+                                              self.conv_last_after_pool[i]))
+            plan.assign.append(self._conv_pairs(params, self.assign_conv_first_modules[i],
+                                                self.assign_conv_block_modules[i],
+                                                self.assign_conv_last_modules[i]))
+            plan.assign_pred.append(self._pred_pairs(params, self.assign_pred_modules[i])[0])
+        plan.pred = self._pred_pairs(params, self.pred_model)
+        self._plan = plan
+        ypred, S0 = _EncoderFn.apply(plan, x, adj, x_a, *params)
+        self.assign_tensors = [S0] + plan.all_S[1:]
+        self.assign_tensor = plan.all_S[-1] if self.num_pooling > 1 else S0   # last level's S (:1269,1273)
+        self._S0 = S0
+        return ypred
+
+    def loss(self, pred, label, adj=None, batch_num_nodes=None, adj_hop=1):
+        plan = self._plan
+        if not self.linkpred:
+            return _LossFn.apply(plan, pred, label, None, None)
+        if adj_hop != 1:
+            raise NotImplementedError('gp_b200: adj_hop > 1 is not implemented (callers never pass it)')
+        adj = E._chk(adj, 'adj')
+        S0 = self._S0                                                        # R7: level-0 S with level-0 adj
+        lp = _Plan()
+        lp.nb_dev, nb_host = E.prep_nb(batch_num_nodes, adj.shape[1], adj.device)
+        if nb_host is None:
+            lp.num_entries = adj.shape[1] * adj.shape[1] * adj.shape[0]
+            print('Warning: calculating link pred loss without masking')       # encoders.py:1324
+        else:
+            n64 = nb_host.astype(np.int64)                                   # R11
+            lp.num_entries = int(np.sum(n64 * n64))
+        total, link = _LossFn.apply(lp, pred, label, S0, adj)
+        self.link_loss = link
+        return total

@@ -1,0 +1,187 @@
+/* gp_b200.h -- C ABI of the B200-native DiffPool hot path (libgp_b200.so).
+ *
+ * Drop-in boundary for the hot path of JiaxuanYou/graph-pooling (encoders.py:976-1334 plus the
+ * DiffPool GraphConv at encoders.py:296-328).  The reference has no native code and no FFI; the
+ * functions below are what a binding for this path would bind, one per reference function or per
+ * fused group of ATen calls on the path.  Every pointer is a DEVICE pointer unless the name ends
+ * in `_host`; tensors are row-major fp32; `nb` is the per-graph node count (`batch_num_nodes`,
+ * train.py:200) as int32 on the device, or NULL for "no masking / no tile skipping".
+ *
+ * Conventions
+ *  - every function returns 0 on success and a negative gp_status on failure, never throws;
+ *    gp_last_error() returns a thread-local message for the last failure;
+ *  - every function is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *  - no function allocates device memory: workspaces are passed in (sizes documented per call);
+ *  - no global mutable state except a lazily initialised, read-only device-attribute cache.
+ *
+ * Zero-padding contract (graph_sampler.py:97-109): when `nb` is given, rows and columns of the
+ * level-0 adjacency at index >= nb[b] are zero.  The N^2-sized contractions use this to skip
+ * all-zero tiles; every other op processes pad rows densely, exactly as the reference does
+ * (pad rows carry normalize(bias) -> ReLU -> BN values and take part in the BN statistics,
+ * encoders.py:1061-1080).
+ */
+#ifndef GP_B200_H
+#define GP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* gp_stream_t; /* cudaStream_t */
+
+enum gp_status {
+  GP_OK = 0,
+  GP_ERR_INVALID = -1,   /* bad argument (shape, stride, null pointer)      */
+  GP_ERR_CUDA = -2,      /* a CUDA runtime call or launch failed             */
+  GP_ERR_UNSUPPORTED = -3 /* valid request outside what the kernel supports */
+};
+
+/* precision of the dense contractions */
+enum gp_precision {
+  GP_F32 = 0,    /* fp32 FFMA everywhere (parity anchor, <=1e-5 relative)                       */
+  GP_BF16 = 1,   /* bf16 operands on tcgen05 tensor cores, fp32 accumulation in TMEM             */
+  GP_BF16X2 = 2  /* {0,1} adjacency exact in bf16; real operand split hi+lo (2 MMAs) ~ fp32     */
+};
+
+int gp_version(void);
+const char* gp_last_error(void);
+/* number of kernels launched by this library on this thread since the last reset (bench.py's
+ * `gpu_launches`). */
+long long gp_launch_count(void);
+void gp_launch_count_reset(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Generic strided batched GEMM  C[b] = alpha * op(A[b]) . op(B[b]) (+bias) (relu) + beta*C[b]
+ * Replaces every aten::bmm / aten::mm / addmm on the path (torch.matmul at encoders.py:319,322,
+ * 1278,1279,1311; nn.Linear at :1024-1031).  Transposes are expressed through strides.
+ * With `lim` != NULL, lim_m/lim_n/lim_k select which logical dims are clipped to lim[b] for
+ * batch b (tile skipping); outputs outside the clipped range are written as beta*C (+0).
+ * split_k > 1 accumulates partial sums with atomics into C, which must hold the beta-term
+ * already (the wrapper zero-fills it when beta == 0).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct gp_gemm {
+  const float* A; const float* B; float* C;
+  int M, N, K, batch;
+  long long sAb, sAm, sAk;   /* element strides of A: batch, m, k */
+  long long sBb, sBk, sBn;
+  long long sCb, sCm, sCn;
+  const int32_t* lim;        /* per-batch limit or NULL */
+  int lim_m, lim_n, lim_k;   /* 1 = clip that dim to lim[b] */
+  float alpha, beta;
+  const float* alpha_dev;    /* optional device scalar multiplied into alpha */
+  const float* bias;         /* optional [N] added before relu */
+  int relu;
+  int split_k;               /* 0/1 = none */
+} gp_gemm;
+int gp_bgemm_f32(const gp_gemm* g, gp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * GraphConv  (encoders.py:315-328):  U = A.X (+X);  V = U.W + b;  Y = V / max(||V||_2, 1e-12)
+ *   x [B,N,din] row stride ldx;  adj [B,N,N];  w [din,dout];  bias [dout] or NULL
+ *   u [B,N,din] (saved for backward);  y [B,N,dout] row stride ldy;  rnorm [B,N] = max(||V||,eps)
+ * ------------------------------------------------------------------------------------------- */
+int gp_graphconv_fwd(const float* x, long long ldx, const float* adj, const float* w, const float* bias,
+                     const int32_t* nb, int B, int N, int din, int dout, int add_self, int normalize,
+                     float* u, float* y, long long ldy, float* rnorm, int precision, gp_stream_t stream);
+
+/* backward of GraphConv given dV (gradient w.r.t. the pre-normalisation V, see gp_gcn_layer_bwd):
+ *   dW = sum_b U^T dV ; db = colsum dV ; dU = dV W^T ; dX = A^T dU (+dU) ; dA += dU X^T
+ *   dx / dadj may be NULL (not needed).  du: workspace [B,N,din].  ws: >= 256*dout floats. */
+int gp_graphconv_bwd(const float* dv, const float* u, const float* x, long long ldx, const float* adj,
+                     const float* w, const int32_t* nb, int B, int N, int din, int dout, int add_self,
+                     float* dw, float* db, float* du, float* dx, float* dadj, float* ws,
+                     int precision, gp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * ReLU + BatchNorm1d(num_nodes) with batch statistics (encoders.py:1062-1064,1048-1052):
+ *   H[b,n,:] = (relu(Y[b,n,:]) - mean_n) * invstd_n, statistics over (b, feature) per node index.
+ *   y [B,N,d] contiguous; h row stride ldh (a column slot of the concat buffer, :1078).
+ *   relu/bn flags switch the two stages (last layer: neither -> plain copy).
+ * ------------------------------------------------------------------------------------------- */
+int gp_relu_bn_fwd(const float* y, float* h, long long ldh, float* mean, float* invstd,
+                   int B, int N, int d, int relu, int bn, gp_stream_t stream);
+
+/* Backward through [concat slot + readout scatter + next-layer dX] -> BN -> ReLU -> normalize:
+ *   g  = dz (dense slot gradient, row stride lddz, or NULL)
+ *      + dxn (gradient from the next layer's A^T dU, contiguous [B,N,d], or NULL)
+ *      + scatter(dout[b, c] at row argidx[b, c]) (max-readout backward, or NULL)
+ *   dR = (g - mean(g) - Hhat*mean(g*Hhat)) * invstd   (if bn);  dY = dR*[Y>0] (if relu)
+ *   dV = (dY - Y<Y,dY>)/r  (if normalize; rows whose norm was clamped: dV = dY/eps)
+ *   h: the forward output slot (Hhat), row stride ldh; y: forward Y (contiguous; for the last
+ *   layer y == h slot with ldy == ldh); dv [B,N,d] contiguous. */
+int gp_gcn_layer_bwd(const float* dz, long long lddz, const float* dxn, const float* dout,
+                     const int32_t* argidx, long long ldo, const float* h, long long ldh,
+                     const float* y, long long ldy, const float* rnorm, const float* invstd,
+                     int B, int N, int d, int relu, int bn, int normalize, float* dv,
+                     gp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Max readout (encoders.py:1097,1257,1287): out[b,f] = max_n Z[b,n,f], pad rows (n >= nb[b])
+ * counting as 0 when nb != NULL (the mask of :1078-1080).  argidx = winning row (lowest index on
+ * ties, as torch CPU), or -1 if a pad row won (its gradient is dropped by the mask).
+ * ------------------------------------------------------------------------------------------- */
+int gp_readout_max_fwd(const float* z, long long ldz, const int32_t* nb, int B, int N, int F,
+                       float* out, int32_t* argidx, long long ldo, gp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Assignment softmax (encoders.py:1273-1275): in place, S = softmax(T) on rows n < nb[b], 0 on
+ * pad rows.  Backward: dT = S*(dS - <dS,S>) on real rows, 0 on pad rows.
+ * ------------------------------------------------------------------------------------------- */
+int gp_softmax_mask_fwd(float* t, const int32_t* nb, int B, int N, int K, gp_stream_t stream);
+int gp_softmax_mask_bwd(const float* s, const float* ds, const int32_t* nb, int B, int N, int K,
+                        float* dt, gp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Pooling (encoders.py:1278-1279):  X' = S^T Z ;  T = S^T A ;  A' = T S
+ *   z row stride ldz (concat buffer, pad rows need no masking because S's pad rows are 0).
+ *   t [B,K,N] is saved for backward.
+ * Backward:  dZ (+)= S dX' ;  dS (+)= Z dX'^T + T^T dA' + A (S dA'^T) ;  dA = S dA' S^T (if dadj)
+ *   ws: workspace >= B*N*K floats.  accumulate_ds: 1 = dS already holds the link-loss term.
+ * ------------------------------------------------------------------------------------------- */
+int gp_pool_fwd(const float* s, const float* z, long long ldz, const float* adj, const int32_t* nb,
+                int B, int N, int K, int F, float* xp, float* t, float* ap, int precision,
+                gp_stream_t stream);
+int gp_pool_bwd(const float* dxp, const float* dap, const float* s, const float* z, long long ldz,
+                const float* adj, const float* t, const int32_t* nb, int B, int N, int K, int F,
+                float* dz, long long lddz, int accumulate_dz, float* ds, int accumulate_ds,
+                float* dadj, float* ws, int precision, gp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Link-prediction loss (encoders.py:1311-1331), masked BCE between P = S S^T and A:
+ *   partial[] <- per-tile sums of  -A log(P+1e-7) - (1-A) log(1-P+1e-7)  over the nb x nb block
+ *   gsym (optional, [B,N,N]) <- dl/dP + (dl/dP)^T, un-normalised, for the backward
+ *   n_partial = B * ceil(N/64)^2 floats.
+ * Backward: dS = (upstream * inv_entries) * gsym . S    (gp_bgemm_f32 with alpha_dev).
+ * gp_loss_finalize: total = ce (device scalar or NULL) + sum(partial) * inv_entries; link likewise.
+ * ------------------------------------------------------------------------------------------- */
+int gp_linkloss_fwd(const float* s, const float* adj, const int32_t* nb, int B, int N, int K,
+                    float* partial, float* gsym, gp_stream_t stream);
+int gp_loss_finalize(const float* partial, int n_partial, double inv_entries, const float* ce,
+                     float* total, float* link, gp_stream_t stream);
+
+/* Row entropy  -sum_k S log(S+eps) averaged over real rows, and the Frobenius variant of the
+ * link loss (north-star options, not in the reference).  TODO(next round). */
+
+/* ---------------------------------------------------------------------------------------------
+ * Cross entropy (encoders.py:1127): loss = mean_b -log softmax(logits)[label]; probs saved.
+ * Backward: dlogits = upstream * (probs - onehot) / B.
+ * ------------------------------------------------------------------------------------------- */
+int gp_ce_fwd(const float* logits, const int64_t* label, int B, int C, float* loss, float* probs,
+              gp_stream_t stream);
+int gp_ce_bwd(const float* probs, const int64_t* label, const float* upstream, int B, int C,
+              float* dlogits, gp_stream_t stream);
+
+/* colsum: out[c] (+)= sum_r x[r, c];  ws >= 256*d floats.  relu_mask_bwd: dx = dy * [y > 0]. */
+int gp_colsum_f32(const float* x, long long rows, int d, long long ld, float* out, int accumulate,
+                  float* ws, gp_stream_t stream);
+int gp_relu_mask_bwd(const float* dy, const float* y, long long n, float* dx, gp_stream_t stream);
+/* x[i] = v ;  y[i] += a*x[i]  (buffer initialisation / gradient accumulation for num_pooling >= 2) */
+int gp_fill_f32(float* x, long long n, float v, gp_stream_t stream);
+int gp_axpy_f32(const float* x, float* y, long long n, float a, gp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GP_B200_H */

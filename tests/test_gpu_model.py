@@ -1,0 +1,193 @@
+"""GPU: module-level parity of the drop-in encoders (forward, loss, every parameter gradient)
+against (a) the golden vectors produced by the actual reference and (b) the oracle on fresh
+seeded batches covering the reference's edge cases.
+
+Tolerance (fp32 path, BASELINE.json north_star "<=1e-5 relative"): outputs are graded by rel-L2
+against the fp64 result; gradients by  err(cand, fp64) <= max(1e-5, 4 x err(oracle_fp32, fp64))
+because the fp32 oracle itself is up to 1e-4 from fp64 on some bias gradients.
+"""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, golden_inputs, golden_model, load_golden, rel_l2, synth_batch
+from oracle import diffpool_oracle as orc
+
+pytestmark = pytest.mark.gpu
+OUT_TOL = 1e-5
+
+
+def enc():
+    from graph_pooling_b200 import encoders
+    return encoders
+
+
+def run_candidate(m, x, adj, nb, label, soft, assign_x=None, linkpred=True):
+    m.zero_grad()
+    xc, ac, lc = torch.as_tensor(x).cuda(), torch.as_tensor(adj).cuda(), torch.as_tensor(label).cuda()
+    if soft:
+        yp = m(xc, ac, nb, assign_x=xc if assign_x is None else torch.as_tensor(assign_x).cuda())
+        loss = m.loss(yp, lc, ac, nb) if linkpred else m.loss(yp, lc)
+    else:
+        yp = m(xc, ac, nb)
+        loss = m.loss(yp, lc)
+    loss.backward()
+    torch.cuda.synchronize()
+    return yp, loss
+
+
+def grade_grads(cand, g32, g64):
+    """cand/g32/g64: dict name -> numpy grad."""
+    for k in g64:
+        scale = max(np.linalg.norm(g64[k]), 1e-7)
+        e_c = np.linalg.norm(cand[k].astype(np.float64) - g64[k]) / scale
+        e_o = np.linalg.norm(g32[k].astype(np.float64) - g64[k]) / scale
+        assert e_c <= max(1e-5, 4 * e_o), '%s: cand err %.3g, fp32-oracle err %.3g' % (k, e_c, e_o)
+
+
+@pytest.mark.parametrize('name', GOLDEN)
+def test_golden_vectors(name):
+    g = load_golden(name)
+    soft = str(g['kind']) == 'soft'
+    m = golden_model(g, enc(), device='cuda')
+    x, adj, nb, label = golden_inputs(g)
+    yp, loss = run_candidate(m, x, adj, nb, label, soft)
+    assert rel_l2(yp.detach().cpu().numpy(), g['f64.ypred']) < OUT_TOL
+    assert abs(loss.item() - float(g['f64.loss'])) < OUT_TOL * max(1.0, abs(float(g['f64.loss'])))
+    if soft:
+        assert rel_l2(m.assign_tensor.detach().cpu().numpy(), g['f64.S']) < OUT_TOL
+        assert abs(m.link_loss.item() - float(g['f64.link_loss'])) < OUT_TOL
+    cand = {k: p.grad.cpu().numpy() for k, p in m.named_parameters()}
+    grade_grads(cand, {k: g['f32.grad.' + k] for k in cand}, {k: g['f64.grad.' + k] for k in cand})
+
+
+def oracle_vs_candidate(make, seed, B, N, D, C, nb_mode='rand', soft=True, symmetric=True, weighted=False,
+                        linkpred=True, density=0.12, bias_scale=0.3, assign_D=None):
+    torch.manual_seed(seed)
+    mo = make(orc)
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for k, p in mo.named_parameters():
+            if k.endswith('bias'):
+                p.copy_(bias_scale * torch.randn(p.shape, generator=g))
+    mc = make(enc())
+    mc.load_state_dict(mo.state_dict(), strict=True)
+    mc = mc.cuda()
+    n_min, n_max = {'rand': (1, N), 'full': (N, N), 'tiny': (1, 2)}[nb_mode if nb_mode != 'none' else 'full']
+    x, adj, nb, label = synth_batch(seed, B, N, D, n_min, n_max, C, density, symmetric, weighted)
+    ax = None
+    if assign_D is not None:
+        ax = np.random.RandomState(seed + 7).randn(B, N, assign_D).astype(np.float32)
+    nbo = None if nb_mode == 'none' else nb
+    res = {}
+    for tag, dt in (('f32', torch.float32), ('f64', torch.float64)):
+        m = copy.deepcopy(mo).to(dt)
+        xt, at = torch.tensor(x, dtype=dt), torch.tensor(adj, dtype=dt)
+        yp, loss = orc.train_step(m, xt, at, torch.tensor(label), nbo,
+                                  assign_x=None if ax is None else torch.tensor(ax, dtype=dt), linkpred=linkpred)
+        res[tag] = (yp.detach().numpy(), loss.item(), {k: p.grad.numpy() for k, p in m.named_parameters()},
+                    m.assign_tensors[0].detach().numpy() if soft else None)
+    yp, loss = run_candidate(mc, x, adj, nbo, label, soft, assign_x=ax, linkpred=linkpred)
+    y64, l64, g64, s64 = res['f64']
+    assert rel_l2(yp.detach().cpu().numpy(), y64) < OUT_TOL
+    assert abs(loss.item() - l64) < OUT_TOL * max(1.0, abs(l64))
+    if soft:
+        assert rel_l2(mc.assign_tensors[0].detach().cpu().numpy(), s64) < OUT_TOL
+    grade_grads({k: p.grad.cpu().numpy() for k, p in mc.named_parameters()}, res['f32'][2], g64)
+    return mc
+
+
+def soft_factory(N, D, H, E_, C, L=3, ratio=0.25, P=1, assign_D=-1, bias=True):
+    class A:
+        pass
+    a = A()
+    a.bias = bias
+    return lambda mod: mod.SoftPoolingGcnEncoder(N, D, H, E_, C, L, H, assign_ratio=ratio, num_pooling=P,
+                                                 assign_input_dim=assign_D, args=a)
+
+
+@pytest.mark.parametrize('nb_mode', ['rand', 'full', 'tiny', 'none'])
+def test_soft_enzymes_shape_nb_modes(nb_mode):
+    oracle_vs_candidate(soft_factory(100, 3, 30, 30, 6, ratio=0.1), 10, 20, 100, 3, 6, nb_mode=nb_mode)
+
+
+def test_soft_nonsymmetric_adj_and_separate_assign_features():
+    oracle_vs_candidate(soft_factory(48, 5, 16, 12, 3, assign_D=9), 11, 5, 48, 5, 3, symmetric=False, assign_D=9)
+
+
+def test_soft_weighted_adj_no_linkpred_no_bias():
+    oracle_vs_candidate(soft_factory(40, 4, 8, 8, 2, bias=False), 12, 4, 40, 4, 2, weighted=True, linkpred=False)
+
+
+def test_soft_wide_tiles():
+    # crosses the 64- and 128-wide tile boundaries of every contraction
+    oracle_vs_candidate(soft_factory(200, 20, 70, 40, 2, ratio=0.4), 13, 3, 200, 20, 2, density=0.05)
+
+
+def test_soft_two_layers_and_four_layers():
+    oracle_vs_candidate(soft_factory(32, 6, 10, 14, 2, L=2), 14, 4, 32, 6, 2)
+    oracle_vs_candidate(soft_factory(32, 6, 10, 14, 2, L=4), 15, 4, 32, 6, 2)
+
+
+def test_soft_num_pooling_2():
+    # repaired-intent P=2 (R5-R7): no runnable ground truth in the reference, oracle only
+    oracle_vs_candidate(soft_factory(64, 5, 12, 12, 2, ratio=0.25, P=2), 16, 4, 64, 5, 2)
+
+
+def test_soft_batch_of_one_graph_smaller_than_K():
+    oracle_vs_candidate(soft_factory(40, 3, 8, 8, 2, ratio=0.5), 17, 2, 40, 3, 2, nb_mode='tiny')
+
+
+@pytest.mark.parametrize('bn,concat,L', [(True, True, 3), (False, True, 3), (True, False, 3), (True, True, 2)])
+def test_base_variants(bn, concat, L):
+    make = lambda mod: mod.GcnEncoderGraph(7, 20, 24, 3, L, bn=bn, concat=concat)
+    oracle_vs_candidate(make, 20 + L, 5, 60, 7, 3, soft=False)
+
+
+def test_base_with_pred_hidden_and_dd_like_dims():
+    make = lambda mod: mod.GcnEncoderGraph(89, 20, 20, 2, 3, pred_hidden_dims=[50, 10])
+    oracle_vs_candidate(make, 30, 3, 150, 89, 2, soft=False, density=0.03)
+
+
+def test_padding_invariance_and_pad_row_features_ignored():
+    """SURVEY 8(a) probes: re-padding to a larger N (K fixed) and garbage in pad rows of x leave ypred unchanged."""
+    e = enc()
+    torch.manual_seed(0)
+    m = e.SoftPoolingGcnEncoder(40, 3, 16, 16, 4, 3, 16, assign_ratio=0.25).cuda()
+    x, adj, nb, label = synth_batch(5, 6, 40, 3, 2, 30, 4)
+    with torch.no_grad():
+        y0 = m(torch.tensor(x).cuda(), torch.tensor(adj).cuda(), nb).cpu()
+        x2 = x.copy()
+        for b in range(6):
+            x2[b, nb[b]:] = 123.0
+        y1 = m(torch.tensor(x2).cuda(), torch.tensor(adj).cuda(), nb).cpu()
+        xp = np.zeros((6, 56, 3), np.float32); xp[:, :40] = x
+        ap = np.zeros((6, 56, 56), np.float32); ap[:, :40, :40] = adj
+        y2 = m(torch.tensor(xp).cuda(), torch.tensor(ap).cuda(), nb).cpu()
+    assert torch.equal(y0, y1)
+    assert rel_l2(y2.numpy(), y0.numpy()) < 1e-6
+
+
+def test_training_loop_matches_oracle_for_20_steps():
+    """Same initial weights, batches and Adam/clip as train.py:173,209-210: losses track the oracle."""
+    e = enc()
+    torch.manual_seed(3)
+    mo = orc.SoftPoolingGcnEncoder(50, 3, 20, 20, 6, 3, 20, assign_ratio=0.2)
+    mc = e.SoftPoolingGcnEncoder(50, 3, 20, 20, 6, 3, 20, assign_ratio=0.2)
+    mc.load_state_dict(mo.state_dict())
+    mc = mc.cuda()
+    oo = torch.optim.Adam(mo.parameters(), lr=1e-3)
+    oc = torch.optim.Adam(mc.parameters(), lr=1e-3)
+    for step in range(20):
+        x, adj, nb, label = synth_batch(100 + step, 8, 50, 3, 3, 50, 6)
+        _, lo = orc.train_step(mo, torch.tensor(x), torch.tensor(adj), torch.tensor(label), nb, optimizer=oo)
+        mc.zero_grad()
+        xc, ac = torch.tensor(x).cuda(), torch.tensor(adj).cuda()
+        yp = mc(xc, ac, nb, assign_x=xc)
+        lc = mc.loss(yp, torch.tensor(label).cuda(), ac, nb)
+        lc.backward()
+        torch.nn.utils.clip_grad_norm_(mc.parameters(), 2.0)
+        oc.step()
+        assert abs(lc.item() - lo.item()) < 2e-4 * max(1.0, abs(lo.item())), step
