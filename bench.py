@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py -- DiffPool train-step throughput (graphs/s) on B200, with roofline and CPU baseline.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+
+A "step" is train.py:196-210 on one synthetic batch: zero_grad -> forward -> loss (CE + link
+prediction) -> backward -> clip_grad_norm(2.0) -> Adam(lr=1e-3).  `value` times it with the
+batch resident in HBM; `e2e` times the same step through the drop-in encoders with HOST (pinned)
+fp32 buffers, host->device copies and the loss read-back inside the timed region.
+N > 1 (torchrun): one process per GPU, each with its own batch of the same shape (weak scaling),
+one NCCL all-reduce of the flat gradient per step; time = max over ranks.
+
+--impl reference: the oracle restatement of the reference's PyTorch code (oracle/, the reference
+itself does not construct -- SURVEY.md 0-3) on the host CPU with all threads, on a bounded sample
+of the same workload (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'diffpool_train_graphs_per_sec'
+UNIT = 'graphs/s'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='cfg4_diffpool_256x2048')
+    ap.add_argument('--batch', type=int, default=None, help='override graphs per GPU per step')
+    ap.add_argument('--cpu-sample', type=int, default=None, help='graphs per CPU-baseline step')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--seed', type=int, default=0)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for t, line in self.rows:
+            if t < t0 or t > t1 + 0.15:
+                continue
+            f = [x.strip() for x in line.split(',')]
+            try:
+                sm.append(float(f[0]))
+                smax = float(f[1])
+            except Exception:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': smax, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d['hbm_gbs'], d['bf16_tflops_sustained'], d['bf16_tflops'], 'measured'
+    return 6650.0, 1400.0, 1590.0, 'fallback'
+
+
+# ------------------------------------------------------------------------------------------------
+def reference_arm(args, rank, world):
+    """Oracle (port of the reference) on the host CPU; rank 0 only."""
+    if rank != 0:
+        return
+    from graph_pooling_b200 import synth
+    from oracle import diffpool_oracle as orc
+    cfg = dict(synth.WORKLOADS[args.workload])
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample = args.cpu_sample or default_cpu_sample(cfg)
+    value, ms, desc = time_cpu_oracle(args.workload, sample, args.steps, args.warmup, args.seed)
+    out = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+           'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
+           'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'impl': 'reference',
+           'config': {'workload': args.workload, 'graphs_per_step': sample, 'sample': desc},
+           'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': desc},
+           'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+           'gpu_launches': 0}
+    print(json.dumps(out), flush=True)
+
+
+def default_cpu_sample(cfg):
+    # ~10-30 s of CPU work in total: scale the per-step sample with the per-graph cost
+    cost = cfg['N'] * cfg['N'] * (cfg['H'] * 6 + int(cfg['N'] * cfg['ratio']) * 6)
+    return int(max(2, min(cfg['B'], 2e10 / max(cost, 1))))
+
+
+def time_cpu_oracle(workload, sample, steps, warmup, seed):
+    from graph_pooling_b200 import synth
+    from oracle import diffpool_oracle as orc
+    batch = synth.make_batch(workload, seed=seed, device='cpu', B=sample)
+    cfg = batch['cfg']
+    torch.manual_seed(seed)
+    model = synth.build_model(orc, cfg)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    x, adj, nb, label = batch['x'], batch['adj'], batch['nb'], batch['label']
+    soft = cfg['kind'] == 'soft'
+    ts = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        orc.train_step(model, x, adj, label, nb, assign_x=x if soft else None, optimizer=opt)
+        ts.append(time.perf_counter() - t0)
+    t = float(np.mean(ts[warmup:]))
+    desc = ('%d graphs/step of %s (same shapes), %d warm-up + %d timed steps, torch %s CPU fp32, %d threads'
+            % (sample, workload, warmup, steps, torch.__version__, torch.get_num_threads()))
+    return sample / t, t * 1e3, desc
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        reference_arm(args, rank, world)
+        return
+
+    from graph_pooling_b200 import _lib, encoders, roofline, synth
+    from graph_pooling_b200 import engine as E
+    assert torch.cuda.is_available(), 'bench.py (impl=ours) needs a CUDA device: there is no CPU fallback'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    lib = _lib.load()
+
+    batch = synth.make_batch(args.workload, seed=args.seed + rank, device=dev, B=args.batch)
+    cfg = batch['cfg']
+    soft = cfg['kind'] == 'soft'
+    torch.manual_seed(args.seed)
+    model = synth.build_model(encoders, cfg).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    params = [p for p in model.parameters()]
+    x, adj, nb, label = batch['x'], batch['adj'], batch['nb'], batch['label']
+    B = x.shape[0]
+
+    def allreduce_grads():
+        if world == 1:
+            return
+        flat = torch._utils._flatten_dense_tensors([p.grad for p in params])
+        dist.all_reduce(flat)
+        flat.div_(world)
+        for p, g in zip(params, torch._utils._unflatten_dense_tensors(flat, [p.grad for p in params])):
+            p.grad.copy_(g)
+
+    def step(xd, ad, ld):
+        model.zero_grad()
+        yp = model(xd, ad, nb, assign_x=xd) if soft else model(xd, ad, nb)
+        loss = model.loss(yp, ld, ad, nb) if soft else model.loss(yp, ld)
+        loss.backward()
+        allreduce_grads()
+        torch.nn.utils.clip_grad_norm_(params, 2.0)
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- device-resident timing ---------------------------------------------------------------
+    for _ in range(args.warmup):
+        step(x, adj, label)
+    lib.gp_launch_count_reset()
+    sampler = ClockSampler(local) if rank == 0 else None
+    t0 = time.time()
+    ms = timed(lambda: step(x, adj, label), args.steps)
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1) if sampler else None
+    launches = int(lib.gp_launch_count())
+    ms_per_step = ms / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+
+    # ---- end to end: host pinned fp32 buffers -> H2D -> step -> loss read-back ----------------
+    e2e = None
+    if not args.no_e2e:
+        hx, ha, hl = x.cpu().pin_memory(), adj.cpu().pin_memory(), label.cpu().pin_memory()
+        dx, da, dl = torch.empty_like(x), torch.empty_like(adj), torch.empty_like(label)
+
+        def e2e_step():
+            dx.copy_(hx, non_blocking=True)
+            da.copy_(ha, non_blocking=True)
+            dl.copy_(hl, non_blocking=True)
+            return float(step(dx, da, dl).item())
+
+        for _ in range(min(args.warmup, 2)):
+            e2e_step()
+        ems = timed(e2e_step, args.steps) / args.steps
+        h2d = hx.numel() * 4 + ha.numel() * 4 + hl.numel() * 8 + nb.nbytes
+        e2e = {'value': world * B / (ems * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
+               'd2h_bytes_per_step': 4, 'ms_per_step': ems,
+               'note': 'dense fp32 adjacency from pinned host memory every step (reference feed contract)'}
+        del hx, ha, hl, dx, da, dl
+
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+        world_done = True
+    if rank != 0:
+        return
+
+    def timed_local(fn, steps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    # ---- roofline of the dominant kernel: the batched A.X contraction -------------------------
+    hbm, tf_sus, tf_burst, src = peaks()
+    H = cfg['H']
+    xin = torch.randn(B, cfg['N'], H, device=dev)
+    u = torch.empty(B, cfg['N'], H, device=dev)
+    nbd, _ = E.prep_nb(nb, cfg['N'], dev)
+    N = cfg['N']
+
+    def ax():
+        E.bgemm(adj.data_ptr(), xin.data_ptr(), u.data_ptr(), N, H, N, B, (N * N, N, 1), (N * H, H, 1),
+                (N * H, H, 1), lim=nbd.data_ptr(), lim_m=1, lim_k=1)
+    for _ in range(3):
+        ax()
+    reps = 10
+    kms = timed_local(lambda: ax(), reps) / reps
+    kfl, kby = roofline.ax_kernel_work(nb, H)
+    ai = kfl / kby
+    ridge = tf_sus * 1e12 / (hbm * 1e9)
+    if ai >= ridge or cfg['N'] >= 1024:
+        roof = {'bound': 'tensor', 'achieved': kfl / (kms * 1e-3) / 1e12, 'peak': tf_burst, 'unit': 'TFLOP/s'}
+    else:
+        roof = {'bound': 'hbm', 'achieved': kby / (kms * 1e-3) / 1e9, 'peak': hbm, 'unit': 'GB/s'}
+    roof['frac'] = roof['achieved'] / roof['peak']
+    roof['traffic'] = None
+    roof['kernel'] = 'bgemm_kernel (U = A.X, N=%d, din=%d, batch=%d)' % (N, H, B)
+    roof['ms_per_launch'] = kms
+    roof['peak_source'] = src + (' burst (kernel timed alone)' if roof['bound'] == 'tensor' else '')
+    fwd_fl, bwd_fl = roofline.step_flops(nb, cfg)
+    roof['step_algorithmic_tflop'] = (fwd_fl + bwd_fl) / 1e12
+    roof['step_tflops'] = (fwd_fl + bwd_fl) / (ms_per_step * 1e-3) / 1e12
+    roof['step_frac_of_sustained_bf16'] = roof['step_tflops'] / tf_sus
+    roof['step_algorithmic_gb'] = roofline.step_bytes(nb, cfg) / 1e9
+    roof['step_gbs'] = roof['step_algorithmic_gb'] / (ms_per_step * 1e-3)
+
+    # ---- CPU baseline (oracle port) on this box's host cores -----------------------------------
+    cpu = None
+    if not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        sample = args.cpu_sample or default_cpu_sample(cfg)
+        v, cms, desc = time_cpu_oracle(args.workload, sample, 2, 1, args.seed)
+        cpu = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': desc, 'ms_per_step': cms}
+
+    out = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+           'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+           'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+           'config': {'workload': args.workload, 'graphs_per_gpu_per_step': B, 'nodes': cfg['N'],
+                      'hidden': cfg['H'], 'assign_ratio': cfg['ratio'], 'num_pooling': cfg['P'],
+                      'step': 'zero_grad+forward+loss(CE+linkpred)+backward+clip_grad_norm+Adam (train.py:196-210)',
+                      'l2': 'inputs larger than L2 (adjacency %.1f GB)' % (adj.numel() * 4 / 1e9)
+                      if adj.numel() * 4 > 126e6 else 'inputs smaller than L2; not flushed',
+                      'parallelism': 'dp%d' % world},
+           'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roof, 'cpu_baseline': cpu}
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == '__main__':
+    main()

@@ -3,8 +3,11 @@ against (a) the golden vectors produced by the actual reference and (b) the orac
 seeded batches covering the reference's edge cases.
 
 Tolerance (fp32 path, BASELINE.json north_star "<=1e-5 relative"): outputs are graded by rel-L2
-against the fp64 result; gradients by  err(cand, fp64) <= max(1e-5, 4 x err(oracle_fp32, fp64))
-because the fp32 oracle itself is up to 1e-4 from fp64 on some bias gradients.
+against the fp64 result; gradients by
+    ||cand - g64|| <= max(1e-5, 4 x relerr(oracle_fp32, fp64)) * ||g64|| + 1e-7 * G
+because the fp32 oracle itself is up to 1e-4 from fp64 on some bias gradients; G is
+the largest parameter-gradient norm of the model, so the last term is an fp32-epsilon absolute floor
+for gradients that cancel to ~0 (e.g. the 2-class output bias, whose entries sum to zero).
 """
 import copy
 
@@ -40,11 +43,13 @@ def run_candidate(m, x, adj, nb, label, soft, assign_x=None, linkpred=True):
 
 def grade_grads(cand, g32, g64):
     """cand/g32/g64: dict name -> numpy grad."""
+    G = max(np.linalg.norm(v) for v in g64.values())
     for k in g64:
-        scale = max(np.linalg.norm(g64[k]), 1e-7)
-        e_c = np.linalg.norm(cand[k].astype(np.float64) - g64[k]) / scale
+        scale = max(np.linalg.norm(g64[k]), 1e-30)
+        a_c = np.linalg.norm(cand[k].astype(np.float64) - g64[k])
         e_o = np.linalg.norm(g32[k].astype(np.float64) - g64[k]) / scale
-        assert e_c <= max(1e-5, 4 * e_o), '%s: cand err %.3g, fp32-oracle err %.3g' % (k, e_c, e_o)
+        assert a_c <= max(1e-5, 4 * e_o) * scale + 1e-7 * G, \
+            '%s: cand err %.3g, fp32-oracle err %.3g' % (k, a_c / scale, e_o)
 
 
 @pytest.mark.parametrize('name', GOLDEN)
@@ -99,13 +104,13 @@ def oracle_vs_candidate(make, seed, B, N, D, C, nb_mode='rand', soft=True, symme
     return mc
 
 
-def soft_factory(N, D, H, E_, C, L=3, ratio=0.25, P=1, assign_D=-1, bias=True):
+def soft_factory(N, D, H, E_, C, L=3, ratio=0.25, P=1, assign_D=-1, bias=True, linkpred=True):
     class A:
         pass
     a = A()
     a.bias = bias
     return lambda mod: mod.SoftPoolingGcnEncoder(N, D, H, E_, C, L, H, assign_ratio=ratio, num_pooling=P,
-                                                 assign_input_dim=assign_D, args=a)
+                                                 assign_input_dim=assign_D, args=a, linkpred=linkpred)
 
 
 @pytest.mark.parametrize('nb_mode', ['rand', 'full', 'tiny', 'none'])
@@ -118,7 +123,7 @@ def test_soft_nonsymmetric_adj_and_separate_assign_features():
 
 
 def test_soft_weighted_adj_no_linkpred_no_bias():
-    oracle_vs_candidate(soft_factory(40, 4, 8, 8, 2, bias=False), 12, 4, 40, 4, 2, weighted=True, linkpred=False)
+    oracle_vs_candidate(soft_factory(40, 4, 8, 8, 2, bias=False, linkpred=False), 12, 4, 40, 4, 2, weighted=True, linkpred=False)
 
 
 def test_soft_wide_tiles():

@@ -66,7 +66,8 @@ def test_bgemm_splitk_bias_relu_beta():
     rs = np.random.RandomState(0)
     A, Bm = rs.randn(1, 40, 5000).astype(np.float32), rs.randn(1, 5000, 24).astype(np.float32)
     out = torch.zeros(1, 40, 24, device='cuda')
-    e.bgemm(dev(A).data_ptr(), dev(Bm).data_ptr(), out.data_ptr(), 40, 24, 5000, 1, (0, 5000, 1), (0, 24, 1),
+    Ad, Bd = dev(A), dev(Bm)
+    e.bgemm(Ad.data_ptr(), Bd.data_ptr(), out.data_ptr(), 40, 24, 5000, 1, (0, 5000, 1), (0, 24, 1),
             (0, 24, 1), split_k=8)
     ref = A.astype(np.float64) @ Bm.astype(np.float64)
     assert rel_l2(out.cpu().numpy(), ref) < TOL
@@ -143,8 +144,8 @@ def test_readout_max_ties_and_mask():
     assert (arg[0] == 2).all()
     assert arg[1, 3] == -1 and out[1, 3].item() == 0.0
     # unmasked
-    call('gp_readout_max_fwd', zc.data_ptr(), F, None, B, N, F, out.data_ptr(), dev(np.zeros((B, F), np.int32)).data_ptr(),
-         F, st())
+    arg2 = dev(np.zeros((B, F), np.int32))
+    call('gp_readout_max_fwd', zc.data_ptr(), F, None, B, N, F, out.data_ptr(), arg2.data_ptr(), F, st())
     assert torch.equal(out.cpu(), torch.max(torch.tensor(z), dim=1)[0])
 
 
@@ -195,7 +196,8 @@ def test_pool_fwd_bwd(B, N, K, F, use_nb, sym):
          ap.data_ptr(), 0, st())
     dz, dsb, ws = (torch.empty(B, N, F, device='cuda'), torch.empty(B, N, K, device='cuda'),
                    torch.empty(B, N, K, device='cuda'))
-    call('gp_pool_bwd', dev(gx).data_ptr(), dev(ga).data_ptr(), sc.data_ptr(), zc.data_ptr(), F, ac.data_ptr(),
+    gxc, gac = dev(gx), dev(ga)
+    call('gp_pool_bwd', gxc.data_ptr(), gac.data_ptr(), sc.data_ptr(), zc.data_ptr(), F, ac.data_ptr(),
          t.data_ptr(), nbp, B, N, K, F, dz.data_ptr(), F, 0, dsb.data_ptr(), 0, None, ws.data_ptr(), 0, st())
     torch.cuda.synchronize()
     assert rel_l2(xp.cpu().numpy(), xo.detach().numpy()) < TOL
