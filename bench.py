@@ -44,6 +44,8 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--seed', type=int, default=0)
+    ap.add_argument('--precision', default='auto', choices=['auto', 'f32', 'bf16'],
+                    help='auto: bf16 tensor-core path for N >= 512 (BASELINE configs[3]), fp32 FFMA otherwise')
     return ap.parse_args()
 
 
@@ -174,6 +176,8 @@ def main():
     soft = cfg['kind'] == 'soft'
     torch.manual_seed(args.seed)
     model = synth.build_model(encoders, cfg).to(dev)
+    prec = args.precision if args.precision != 'auto' else ('bf16' if cfg['N'] >= 512 else 'f32')
+    model.precision = 1 if prec == 'bf16' else 0
     opt = torch.optim.Adam(model.parameters(), lr=1e-3)
     params = [p for p in model.parameters()]
     x, adj, nb, label = batch['x'], batch['adj'], batch['nb'], batch['label']
@@ -277,14 +281,24 @@ def main():
     nbd, _ = E.prep_nb(nb, cfg['N'], dev)
     N = cfg['N']
 
-    def ax():
-        E.bgemm(adj.data_ptr(), xin.data_ptr(), u.data_ptr(), N, H, N, B, (N * N, N, 1), (N * H, H, 1),
-                (N * H, H, 1), lim=nbd.data_ptr(), lim_m=1, lim_k=1)
+    if prec == 'bf16':
+        from graph_pooling_b200 import engine_tc as T
+        wsb = E.Workspace(dev)
+        adjb = T.cvt(wsb, adj.data_ptr(), N, B * N, N, B=B)
+        xinb = T.cvt(wsb, xin.data_ptr(), H, B * N, H, B=B)
+        ub = T.bfbuf(wsb, B, N, H)
+
+        def ax():
+            T.tcgemm(adjb, T.KM, xinb, T.MN, N, H, N, B, Cb=ub, lim=nbd.data_ptr(), lim_m=1, lim_k=1)
+    else:
+        def ax():
+            E.bgemm(adj.data_ptr(), xin.data_ptr(), u.data_ptr(), N, H, N, B, (N * N, N, 1), (N * H, H, 1),
+                    (N * H, H, 1), lim=nbd.data_ptr(), lim_m=1, lim_k=1)
     for _ in range(3):
         ax()
     reps = 10
     kms = timed_local(lambda: ax(), reps) / reps
-    kfl, kby = roofline.ax_kernel_work(nb, H)
+    kfl, kby = roofline.ax_kernel_work(nb, H, elt=2 if prec == 'bf16' else 4)
     ai = kfl / kby
     ridge = tf_sus * 1e12 / (hbm * 1e9)
     if ai >= ridge or cfg['N'] >= 1024:
@@ -293,7 +307,8 @@ def main():
         roof = {'bound': 'hbm', 'achieved': kby / (kms * 1e-3) / 1e9, 'peak': hbm, 'unit': 'GB/s'}
     roof['frac'] = roof['achieved'] / roof['peak']
     roof['traffic'] = None
-    roof['kernel'] = 'bgemm_kernel (U = A.X, N=%d, din=%d, batch=%d)' % (N, H, B)
+    roof['kernel'] = '%s (U = A.X, N=%d, din=%d, batch=%d)' % (
+        'tc_gemm_kernel<128,3,K-major,N-major> tcgen05' if prec == 'bf16' else 'bgemm_kernel FFMA', N, H, B)
     roof['ms_per_launch'] = kms
     roof['peak_source'] = src + (' burst (kernel timed alone)' if roof['bound'] == 'tensor' else '')
     fwd_fl, bwd_fl = roofline.step_flops(nb, cfg)
@@ -314,8 +329,8 @@ def main():
 
     out = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
            'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
-           'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-           'config': {'workload': args.workload, 'graphs_per_gpu_per_step': B, 'nodes': cfg['N'],
+           'vs_baseline': None, 'dtype': prec, 'data': 'synthetic',
+           'config': {'workload': args.workload, 'precision': prec, 'graphs_per_gpu_per_step': B, 'nodes': cfg['N'],
                       'hidden': cfg['H'], 'assign_ratio': cfg['ratio'], 'num_pooling': cfg['P'],
                       'step': 'zero_grad+forward+loss(CE+linkpred)+backward+clip_grad_norm+Adam (train.py:196-210)',
                       'l2': 'inputs larger than L2 (adjacency %.1f GB)' % (adj.numel() * 4 / 1e9)

@@ -24,8 +24,21 @@ class GpGemm(C.Structure):
                 ('alpha_dev', c_f), ('bias', c_f), ('relu', c_i), ('split_k', c_i)]
 
 
+class GpGemmBf16(C.Structure):
+    _fields_ = [('A', c_f), ('B', c_f), ('C', c_f), ('Cb', c_f),
+                ('M', c_i), ('N', c_i), ('K', c_i), ('batch', c_i),
+                ('ldA', c_ll), ('sAb', c_ll), ('a_major', c_i),
+                ('ldB', c_ll), ('sBb', c_ll), ('b_major', c_i),
+                ('ldC', c_ll), ('sCb', c_ll), ('ldCb', c_ll), ('sCbb', c_ll),
+                ('lim', c_f), ('lim_m', c_i), ('lim_n', c_i), ('lim_k', c_i),
+                ('alpha', C.c_float), ('beta', C.c_float), ('alpha_dev', c_f),
+                ('bias', c_f), ('relu', c_i), ('split_k', c_i)]
+
+
 # name -> argtypes (restype is int unless listed in _RESTYPES)
 _PROTOS = {
+    'gp_bgemm_bf16': [C.POINTER(GpGemmBf16), c_f],
+    'gp_cvt_f32_bf16': [c_f, c_ll, c_f, c_ll, c_ll, c_i, c_i, c_f],
     'gp_version': [],
     'gp_last_error': [],
     'gp_launch_count': [],
@@ -45,10 +58,12 @@ _PROTOS = {
                     c_f, c_i, c_f],
     'gp_linkloss_fwd': [c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f, c_f],
     'gp_loss_finalize': [c_f, c_i, C.c_double, c_f, c_f, c_f, c_f],
+    'gp_linkloss_from_p': [c_f, c_f, c_f, c_i, c_i, c_ll, c_f, c_f, c_f],
     'gp_ce_fwd': [c_f, c_f, c_i, c_i, c_f, c_f, c_f],
     'gp_ce_bwd': [c_f, c_f, c_f, c_i, c_i, c_f, c_f],
     'gp_colsum_f32': [c_f, c_ll, c_i, c_ll, c_f, c_i, c_f, c_f],
     'gp_relu_mask_bwd': [c_f, c_f, c_ll, c_f, c_f],
+    'gp_bias_normalize_f32': [c_f, c_f, c_f, c_ll, c_i, c_ll, c_i, c_f],
     'gp_fill_f32': [c_f, c_ll, C.c_float, c_f],
     'gp_axpy_f32': [c_f, c_f, c_ll, C.c_float, c_f],
 }

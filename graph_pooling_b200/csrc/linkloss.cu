@@ -3,6 +3,7 @@
 // tile, and -- for training -- the symmetrised gradient dl/dP + (dl/dP)^T is written once so that
 // the backward is a single GEMM gsym.S.  P itself never touches HBM (the reference materialises
 // ~6 [B,N,N] temporaries here).  Tiles beyond a graph's node count exit immediately.
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace gp {
@@ -120,9 +121,69 @@ __global__ void loss_finalize_kernel(const float* __restrict__ partial, int n_pa
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tensor-core path: P = S S^T comes from gp_bgemm_bf16 (fp32, [B,N,N]); this pass fuses the masked
+// BCE reduction with the write of the symmetrised gradient as the bf16 operand of the backward GEMM.
+// 32x32 tiles; the transposed adjacency tile is staged through shared memory.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+linkloss_from_p_kernel(const float* __restrict__ P, const float* __restrict__ adj, const int32_t* __restrict__ nb,
+                       int N, long long ldg, float* __restrict__ partial, __nv_bfloat16* __restrict__ gsym) {
+  __shared__ float At[32][33];
+  __shared__ float sh[33];
+  const int b = blockIdx.z, i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  const int T = gridDim.x;
+  const int nreal = nb != nullptr ? min(nb[b], N) : N;
+  const int nfill = min(N, (nreal + 63) / 64 * 64);      // gsym must be finite up to the next 64 multiple
+  const long long pidx = ((long long)b * T + blockIdx.y) * T + blockIdx.x;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  if (i0 >= nfill || j0 >= nfill) {
+    if (threadIdx.x == 0) partial[pidx] = 0.f;
+    return;
+  }
+  const float* ab = adj + (long long)b * N * N;
+  const float* pb = P + (long long)b * N * N;
+  for (int r = ty; r < 32; r += 8) {
+    const int gr = j0 + r, gc = i0 + tx;
+    At[r][tx] = (gr < nreal && gc < nreal) ? ab[(long long)gr * N + gc] : 0.f;
+  }
+  __syncthreads();
+  float lsum = 0.f;
+  for (int r = ty; r < 32; r += 8) {
+    const int m = i0 + r, n = j0 + tx;
+    if (m >= N || n >= N) continue;
+    float g = 0.f;
+    if (m < nreal && n < nreal) {
+      float p = pb[(long long)m * N + n];
+      const bool over = p > 1.f;
+      if (over) p = 1.f;
+      float l, g1, l2, g2;
+      bce(ab[(long long)m * N + n], p, over, l, g1);
+      bce(At[tx][r], p, over, l2, g2);
+      lsum += l;
+      g = g1 + g2;
+    }
+    if (gsym != nullptr && m < nfill && n < nfill) gsym[((long long)b * N + m) * ldg + n] = __float2bfloat16_rn(g);
+  }
+  const float tot = block_sum(lsum, sh);
+  if (threadIdx.x == 0) partial[pidx] = tot;
+}
+
 }  // namespace gp
 
 using namespace gp;
+
+extern "C" int gp_linkloss_from_p(const float* P, const float* adj, const int32_t* nb, int B, int N, long long ldg,
+                                  float* partial, void* gsym_bf16, gp_stream_t stream) {
+  GP_REQUIRE(P && adj && partial && B > 0 && N > 0 && ldg >= N, "linkloss_from_p: bad args");
+  const int T = (N + 31) / 32;
+  GP_REQUIRE(B <= 65535 && T <= 65535, "linkloss_from_p: grid too large");
+  dim3 grid(T, T, B);
+  linkloss_from_p_kernel<<<grid, 256, 0, S(stream)>>>(P, adj, nb, N, ldg, partial,
+                                                       reinterpret_cast<__nv_bfloat16*>(gsym_bf16));
+  GP_LAUNCHED();
+  return GP_OK;
+}
 
 extern "C" int gp_linkloss_fwd(const float* s, const float* adj, const int32_t* nb, int B, int N, int K,
                                float* partial, float* gsym, gp_stream_t stream) {

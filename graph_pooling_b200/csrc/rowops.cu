@@ -420,6 +420,13 @@ extern "C" int gp_relu_mask_bwd(const float* dy, const float* y, long long n, fl
   return GP_OK;
 }
 
+extern "C" int gp_bias_normalize_f32(float* v, const float* bias, float* rnorm, long long rows, int d,
+                                     long long ld, int normalize, gp_stream_t stream) {
+  GP_REQUIRE(v && rows > 0 && d > 0 && ld >= d, "bias_normalize: bad args");
+  GP_REQUIRE(!normalize || rnorm, "bias_normalize: normalize needs rnorm");
+  return bias_normalize(v, bias, rnorm, rows, d, ld, normalize, S(stream));
+}
+
 extern "C" int gp_fill_f32(float* x, long long n, float v, gp_stream_t stream) {
   GP_REQUIRE(x && n >= 0, "fill: bad args");
   if (n == 0) return GP_OK;

@@ -17,6 +17,7 @@ import torch.nn as nn
 from torch.autograd.function import once_differentiable
 
 from . import engine as E
+from . import engine_tc as T
 from ._lib import call
 
 __all__ = ['GraphConv', 'GcnEncoderGraph', 'GcnSet2SetEncoder', 'SoftPoolingGcnEncoder']
@@ -35,10 +36,128 @@ def _wb(params, pair):
     return params[iw], (None if ib is None else params[ib])
 
 
+def _fwd_tc(ctx, plan, x, adj, assign_x, params):
+    """GP_BF16 forward: same schedule as _EncoderFn.forward with the contractions on tcgen05."""
+    st = E._stream()
+    ws = E.Workspace(x.device)
+    B, N, D = x.shape
+    nb = plan.nb_dev
+    conv = lambda pairs: ([_wb(params, p)[0] for p in pairs], [_wb(params, p)[1] for p in pairs])
+    P, Fw = plan.num_pooling, plan.F
+    ldo = Fw * (P + 1)
+    out, arg = ws.f(B, ldo), ws.i(B, ldo)
+    adjb = T.cvt(ws, adj.data_ptr(), N, B * N, N, B=B)
+    xb = T.cvt(ws, x.data_ptr(), D, B * N, D, B=B)
+    w0, b0 = conv(plan.emb)
+    z, zb, c_emb = T.stack_forward(ws, xb, D, adjb, nb, B, N, w0, b0, plan.bn)
+    call('gp_readout_max_fwd', z.data_ptr(), Fw, E._p(nb) if plan.soft else None, B, N, Fw,
+         out.data_ptr(), arg.data_ptr(), ldo, st)
+    levels, S0 = [], None
+    plan.adjb, plan.sb0 = adjb, None
+    if plan.soft:
+        if assign_x is x:
+            xab, xa_d = xb, D
+        else:
+            xa_d = assign_x.shape[2]
+            xab = T.cvt(ws, assign_x.data_ptr(), xa_d, B * N, xa_d, B=B)
+        cur_adjb, cur_nb, cur_N, cur_zb = adjb, nb, N, zb
+        for i in range(P):
+            K = plan.assign_dims[i]
+            wa, ba = conv(plan.assign[i])
+            za, zab, c_as = T.stack_forward(ws, xab, xa_d, cur_adjb, cur_nb, B, cur_N, wa, ba, True)
+            Fa = za.shape[2]
+            wp, bp = _wb(params, plan.assign_pred[i])
+            Tl, wpb = T.assign_linear_fwd(ws, zab, Fa, B * cur_N, wp, bp)
+            S = Tl.view(B, cur_N, K)
+            call('gp_softmax_mask_fwd', S.data_ptr(), E._p(cur_nb), B, cur_N, K, st)
+            sb, xp, xpb, tb, ap, apb = T.pool_forward(ws, S, cur_zb, cur_adjb, cur_nb, B, cur_N, K, Fw)
+            wq, bq = conv(plan.post[i])
+            z2, z2b, c_post = T.stack_forward(ws, xpb, Fw, apb, None, B, K, wq, bq, plan.bn_post)
+            call('gp_readout_max_fwd', z2.data_ptr(), Fw, None, B, K, Fw, out.data_ptr() + (i + 1) * Fw * 4,
+                 arg.data_ptr() + (i + 1) * Fw * 4, ldo, st)
+            levels.append(dict(K=K, N=cur_N, nb=cur_nb, adjb=cur_adjb, zb=cur_zb, S=S, sb=sb, zab=zab, Fa=Fa,
+                               c_as=c_as, tb=tb, c_post=c_post, wpb=wpb, has_bp=bp is not None))
+            if i == 0:
+                S0, plan.sb0 = S, sb
+            xab, xa_d = xpb, Fw
+            cur_adjb, cur_nb, cur_N, cur_zb = apb, None, K, z2b
+    lin = [_wb(params, p) for p in plan.pred]
+    ypred, acts = E.mlp_fwd(ws, out.data_ptr(), ldo, B, lin)
+    ctx.tape = dict(plan=plan, params=params, B=B, N=N, emb=c_emb, levels=levels, out=out, arg=arg, ldo=ldo,
+                    acts=acts, lin=lin, x=x, adj=adj)
+    if plan.soft:
+        plan.all_S = [lv['S'] for lv in levels]
+        return ypred, S0
+    return ypred
+
+
+def _bwd_tc(ctx, tape, dypred, dS0):
+    plan, params = tape['plan'], tape['params']
+    B = tape['B']
+    st = E._stream()
+    ws = E.Workspace(tape['x'].device)
+    Fw, P, ldo = plan.F, plan.num_pooling, tape['ldo']
+    grads = [None] * len(params)
+
+    def put(pairs, gl):
+        for (iw, ib), (dw, db) in zip(pairs, gl):
+            grads[iw] = dw
+            if ib is not None:
+                grads[ib] = db
+
+    if dypred is None:
+        dypred = ws.z(B, plan.label_dim)
+    dypred = E._chk(dypred, 'grad of ypred')
+    dout = ws.f(B, ldo)
+    put(plan.pred, E.mlp_bwd(ws, dypred, B, tape['acts'], tape['lin'], dout.data_ptr(), ldo))
+    dout_p, arg_p = dout.data_ptr(), tape['arg'].data_ptr()
+    dz_dense = None
+    if plan.soft:
+        levels = tape['levels']
+        d_ap = [ws.z(B, lv['K'], lv['K']) for lv in levels]
+        dxp_extra = [None] * P
+        dz_next = None
+        for i in reversed(range(P)):
+            lv = levels[i]
+            K, Ni = lv['K'], lv['N']
+            gl, dxp = T.stack_backward(ws, lv['c_post'], None if dz_next is None else dz_next.data_ptr(), Fw,
+                                       dout_p + (i + 1) * Fw * 4, arg_p + (i + 1) * Fw * 4, ldo, True, d_ap[i])
+            put(plan.post[i], gl)
+            if dxp_extra[i] is not None:
+                call('gp_axpy_f32', dxp_extra[i].data_ptr(), dxp.data_ptr(), C.c_longlong(dxp.numel()),
+                     C.c_float(1.0), st)
+            if i == 0 and dS0 is not None:
+                ds, acc_ds = E._chk(dS0, 'grad of assign_tensor'), 1
+            else:
+                ds, acc_ds = ws.f(B, Ni, K), 0
+            dz = T.pool_backward(ws, dxp, d_ap[i], lv['sb'], lv['zb'], lv['adjb'], lv['tb'], lv['nb'], B, Ni, K, Fw,
+                                 ds, acc_ds, None if i == 0 else d_ap[i - 1])
+            dt = ws.f(B, Ni, K)
+            call('gp_softmax_mask_bwd', lv['S'].data_ptr(), ds.data_ptr(), E._p(lv['nb']), B, Ni, K, dt.data_ptr(), st)
+            dwp, dbp, dza = T.assign_linear_bwd(ws, dt, lv['zab'], lv['Fa'], B * Ni, lv['wpb'], K, lv['has_bp'])
+            iw, ib = plan.assign_pred[i]
+            grads[iw] = dwp
+            if ib is not None:
+                grads[ib] = dbp
+            gl, dxa = T.stack_backward(ws, lv['c_as'], dza.data_ptr(), lv['Fa'], None, None, 0, i > 0,
+                                       None if i == 0 else d_ap[i - 1])
+            put(plan.assign[i], gl)
+            if i > 0:
+                dxp_extra[i - 1] = dxa
+            dz_next = dz
+        dz_dense = dz_next
+    gl, _ = T.stack_backward(ws, tape['emb'], None if dz_dense is None else dz_dense.data_ptr(), Fw, dout_p, arg_p,
+                             ldo, False, None)
+    put(plan.emb, gl)
+    return (None, None, None, None) + tuple(grads)
+
+
 class _EncoderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, plan, x, adj, assign_x, *params):
         ctx.set_materialize_grads(False)
+        if plan.precision == T.BF16:
+            return _fwd_tc(ctx, plan, x, adj, assign_x, params)
         st = E._stream()
         ws = E.Workspace(x.device)
         B, N, D = x.shape
@@ -105,6 +224,8 @@ class _EncoderFn(torch.autograd.Function):
         if tape is None:
             raise RuntimeError('gp_b200: backward called twice (buffers were freed)')
         ctx.tape = None
+        if tape['plan'].precision == T.BF16:
+            return _bwd_tc(ctx, tape, dypred, dS0)
         plan, params = tape['plan'], tape['params']
         B, N = tape['B'], tape['N']
         st = E._stream()
@@ -199,15 +320,20 @@ class _LossFn(torch.autograd.Function):
         if S is None:
             return ce.view(())
         Bn, N, K = S.shape
-        T = (N + 63) // 64
-        partial = ws.f(Bn * T * T)
         need_grad = ctx.needs_input_grad[3]
-        gsym = ws.f(Bn, N, N) if need_grad else None
-        call('gp_linkloss_fwd', S.data_ptr(), adj.data_ptr(), E._p(plan.nb_dev), Bn, N, K, partial.data_ptr(),
-             E._p(gsym), st)
+        ctx.sb = getattr(plan, 'sb0', None)
+        if ctx.sb is not None:                      # GP_BF16: P = S S^T on tensor cores
+            partial, npart, gsym = T.linkloss_forward(ws, ctx.sb, adj, plan.nb_dev, Bn, N, K, need_grad)
+        else:
+            nt = (N + 63) // 64
+            npart = Bn * nt * nt
+            partial = ws.f(npart)
+            gsym = ws.f(Bn, N, N) if need_grad else None
+            call('gp_linkloss_fwd', S.data_ptr(), adj.data_ptr(), E._p(plan.nb_dev), Bn, N, K, partial.data_ptr(),
+                 E._p(gsym), st)
         total, link = ws.f(1), ws.f(1)
         inv = 1.0 / float(plan.num_entries)
-        call('gp_loss_finalize', partial.data_ptr(), Bn * T * T, C.c_double(inv), ce.data_ptr(), total.data_ptr(),
+        call('gp_loss_finalize', partial.data_ptr(), npart, C.c_double(inv), ce.data_ptr(), total.data_ptr(),
              link.data_ptr(), st)
         ctx.gsym, ctx.S, ctx.inv, ctx.nb = gsym, S, inv, plan.nb_dev
         link = link.view(())
@@ -226,6 +352,10 @@ class _LossFn(torch.autograd.Function):
         if ctx.link and ctx.gsym is not None:
             S = ctx.S
             Bn, N, K = S.shape
+            if ctx.sb is not None:
+                dS = T.linkloss_backward(ws, ctx.gsym, ctx.sb, ctx.nb, Bn, N, K, ctx.inv, g.data_ptr())
+                ctx.gsym = None
+                return None, dy, None, dS, None
             dS = ws.f(Bn, N, K)
             lim = ctx.nb is not None
             E.bgemm(ctx.gsym.data_ptr(), S.data_ptr(), dS.data_ptr(), N, K, N, Bn, (N * N, N, 1), (N * K, K, 1),
@@ -407,6 +537,8 @@ class GcnEncoderGraph(nn.Module):
             raise ValueError('batch_num_nodes has %d entries for a batch of %d' % (len(plan.nb_host), x.shape[0]))
         plan.concat = self.concat
         plan.add_self = not self.concat
+        if plan.add_self:
+            plan.precision = E.F32           # the tensor-core schedule covers add_self=False (concat) only
         plan.bn = self.bn
         plan.label_dim = self.label_dim
         params = []
@@ -538,6 +670,7 @@ class SoftPoolingGcnEncoder(GcnEncoderGraph):
         adj = E._chk(adj, 'adj')
         S0 = self._S0                                                        # R7: level-0 S with level-0 adj
         lp = _Plan()
+        lp.sb0 = getattr(plan, 'sb0', None)
         lp.nb_dev, nb_host = E.prep_nb(batch_num_nodes, adj.shape[1], adj.device)
         if nb_host is None:
             lp.num_entries = adj.shape[1] * adj.shape[1] * adj.shape[0]

@@ -1,0 +1,246 @@
+"""Tensor-core (GP_BF16) schedule of the DiffPool path: every dense contraction runs on
+gp_bgemm_bf16 (TMA + tcgen05.mma, fp32 accumulation in TMEM); row/node reductions stay fp32.
+
+Operands are bf16 shadow buffers with row strides padded to 8 elements (TMA's 16-byte rule);
+they are produced either by a GEMM epilogue (bf16 copy output) or by gp_cvt_f32_bf16.  All
+products read their operands in natural row-major layout (K-major / MN-major UMMA descriptors),
+so nothing is ever transposed in HBM.  Same reference semantics as engine.py.
+"""
+import ctypes as C
+
+import torch
+
+from . import engine as E
+from ._lib import GpGemmBf16, call
+
+BF16 = 1
+KM, MN = 0, 1        # operand major-ness (see include/gp_b200.h)
+
+
+def r8(n):
+    return (int(n) + 7) & ~7
+
+
+class Op:
+    """bf16 operand view: device pointer, row stride, batch stride (elements), keep-alive tensor."""
+    __slots__ = ('ptr', 'ld', 'sb', 't')
+
+    def __init__(self, ptr, ld, sb, t=None):
+        self.ptr, self.ld, self.sb, self.t = ptr, ld, sb, t
+
+
+def bfbuf(ws, B, R, Ccols):
+    t = torch.empty(B, R, r8(Ccols), device=ws.device, dtype=torch.bfloat16)
+    return Op(t.data_ptr(), r8(Ccols), R * r8(Ccols), t)
+
+
+def cvt(ws, x_ptr, ldx, rows, cols, B=1, out=None):
+    """fp32 [rows, cols] (row stride ldx) -> bf16 operand [B, rows/B, r8(cols)]."""
+    if out is None:
+        out = bfbuf(ws, B, rows // B, cols)
+    call('gp_cvt_f32_bf16', x_ptr, ldx, out.ptr, out.ld, C.c_longlong(rows), cols, min(r8(cols), out.ld),
+         E._stream())
+    return out
+
+
+def tcgemm(A, a_major, Bo, b_major, M, N, K, batch, Cf=None, Cb=None, lim=None, lim_m=0, lim_n=0, lim_k=0,
+           alpha=1.0, beta=0.0, alpha_dev=None, bias=None, relu=0, split_k=0):
+    """Cf = (ptr, ld, sb) fp32 output, Cb = Op bf16 output; see gp_bgemm_bf16."""
+    cp, cld, csb = Cf if Cf is not None else (None, 0, 0)
+    g = GpGemmBf16(A.ptr, Bo.ptr, cp, None if Cb is None else Cb.ptr, M, N, K, batch,
+                   A.ld, A.sb, a_major, Bo.ld, Bo.sb, b_major, cld, csb,
+                   0 if Cb is None else Cb.ld, 0 if Cb is None else Cb.sb,
+                   lim, lim_m, lim_n, lim_k, alpha, beta, alpha_dev, bias, relu, split_k)
+    call('gp_bgemm_bf16', C.byref(g), E._stream())
+
+
+def pick_split(M, N, K):
+    tiles = ((M + 127) // 128) * ((N + 255) // 256 if N > 128 else 1)
+    kt = max(1, K // 64)
+    return int(max(1, min(kt, 1024, (296 + tiles - 1) // tiles)))
+
+
+# ------------------------------------------------------------------------------------------
+class StackCtxTC:
+    pass
+
+
+def stack_forward(ws, xb, din, adjb, nb, B, N, weights, biases, bn):
+    """TC version of engine.stack_forward (add_self unsupported).  xb/adjb: bf16 operands.
+    Returns (zcat fp32 [B,N,F], zb bf16 operand of the same concat, ctx)."""
+    st = E._stream()
+    L = len(weights)
+    douts = [int(w.shape[1]) for w in weights]
+    Fw = sum(douts)
+    zcat = ws.f(B, N, Fw)
+    zb = bfbuf(ws, B, N, Fw)
+    offs = [sum(douts[:l]) for l in range(L)]
+    aligned = all(o % 8 == 0 for o in offs)
+    ctx = StackCtxTC()
+    ctx.B, ctx.N, ctx.douts, ctx.F, ctx.adjb, ctx.nb, ctx.bn = B, N, douts, Fw, adjb, nb, bn
+    ctx.weights, ctx.biases, ctx.zcat, ctx.layers = weights, biases, zcat, []
+    nbp = E._p(nb)
+    lim = int(nb is not None)
+    cur, cur_d = xb, din
+    zp = zcat.data_ptr()
+    for l in range(L):
+        last = l == L - 1
+        dout, off = douts[l], offs[l]
+        w = weights[l]
+        wb = cvt(ws, w.data_ptr(), dout, cur_d, dout)                                   # [din, r8(dout)]
+        ub = bfbuf(ws, B, N, cur_d)
+        # U = A.X : A K-major, X N-major
+        tcgemm(adjb, KM, cur, MN, N, cur_d, N, B, Cb=ub, lim=nbp, lim_m=lim, lim_k=lim)
+        slot = zp + off * 4
+        if last:
+            y, y_ptr, ldy = None, slot, Fw
+        else:
+            y = ws.f(B, N, dout)
+            y_ptr, ldy = y.data_ptr(), dout
+        # V = U.W + b (rows flattened): U K-major, W N-major
+        uflat = Op(ub.ptr, ub.ld, 0)
+        tcgemm(uflat, KM, Op(wb.ptr, wb.ld, 0), MN, B * N, dout, cur_d, 1, Cf=(y_ptr, ldy, 0), bias=E._p(biases[l]))
+        rnorm = ws.f(B, N)
+        call('gp_bias_normalize_f32', y_ptr, None, rnorm.data_ptr(), C.c_longlong(B * N), dout, ldy, 1, st)
+        mean = invstd = None
+        if not last:
+            if bn:
+                mean, invstd = ws.f(N), ws.f(N)
+            call('gp_relu_bn_fwd', y_ptr, slot, Fw, E._p(mean), E._p(invstd), B, N, dout, 1, int(bn), st)
+        if aligned:
+            hb = Op(zb.ptr + off * 2, zb.ld, zb.sb, zb.t)
+            cvt(ws, slot, Fw, B * N, dout, out=Op(hb.ptr, zb.ld, zb.sb))
+        else:
+            hb = cvt(ws, slot, Fw, B * N, dout, B=B)
+        ctx.layers.append((cur, cur_d, dout, off, ub, y, rnorm, mean, invstd, wb))
+        cur, cur_d = hb, dout
+    if not aligned:
+        cvt(ws, zp, Fw, B * N, Fw, out=zb)
+    return zcat, zb, ctx
+
+
+def stack_backward(ws, ctx, dz_ptr, lddz, dout_ptr, arg_ptr, ldo, need_dx, dadj):
+    st = E._stream()
+    B, N, Fw = ctx.B, ctx.N, ctx.F
+    L = len(ctx.layers)
+    grads = [None] * L
+    dxn = None
+    zp = ctx.zcat.data_ptr()
+    cs = ws.f(256 * max(ctx.douts))
+    nbp = E._p(ctx.nb)
+    lim = int(ctx.nb is not None)
+    rows = B * N
+    for l in reversed(range(L)):
+        xb, din, dout, off, ub, y, rnorm, mean, invstd, wb = ctx.layers[l]
+        last = l == L - 1
+        slot = zp + off * 4
+        dv = ws.f(B, N, dout)
+        call('gp_gcn_layer_bwd',
+             None if dz_ptr is None else dz_ptr + off * 4, lddz, E._p(dxn),
+             None if dout_ptr is None else dout_ptr + off * 4, None if arg_ptr is None else arg_ptr + off * 4, ldo,
+             slot, Fw, slot if last else E._p(y), Fw if last else dout, E._p(rnorm), E._p(invstd),
+             B, N, dout, int(not last), int(ctx.bn and not last), 1, E._p(dv), st)
+        dvb = cvt(ws, dv.data_ptr(), dout, rows, dout)                                  # [rows, r8(dout)]
+        db = None
+        if ctx.biases[l] is not None:
+            db = ws.f(dout)
+            call('gp_colsum_f32', E._p(dv), C.c_longlong(rows), dout, C.c_longlong(dout), E._p(db), 0, E._p(cs), st)
+        # dW = U^T dV : U stored [rows, din] = M-major A ; dV N-major B ; split-K over the rows
+        dw = ws.f(din, dout)
+        tcgemm(Op(ub.ptr, ub.ld, 0), MN, Op(dvb.ptr, dvb.ld, 0), MN, din, dout, rows, 1, Cf=(dw.data_ptr(), dout, 0),
+               split_k=pick_split(din, dout, rows))
+        grads[l] = (dw, db)
+        need_dx_l = need_dx or l > 0
+        dx = None
+        if need_dx_l or dadj is not None:
+            # dU = dV W^T : dV K-major ; B[n=din, k=dout] = W stored [din rows, dout cols] = K-major
+            dub = bfbuf(ws, B, N, din)
+            tcgemm(Op(dvb.ptr, dvb.ld, 0), KM, Op(wb.ptr, wb.ld, 0), KM, rows, din, dout, 1, Cb=Op(dub.ptr, dub.ld, 0))
+            if need_dx_l:
+                # dX = A^T dU : A stored [k rows, m cols] = M-major ; dU N-major
+                dx = ws.f(B, N, din)
+                tcgemm(ctx.adjb, MN, dub, MN, N, din, N, B, Cf=(dx.data_ptr(), din, N * din), lim=nbp, lim_m=lim,
+                       lim_k=lim)
+            if dadj is not None:
+                # dA += dU X^T : dU K-major ; B[n=node, k=din] = X stored [node rows, din cols] = K-major
+                tcgemm(dub, KM, xb, KM, N, N, din, B, Cf=(dadj.data_ptr(), N, N * N), beta=1.0)
+        dxn = dx
+    return grads, dxn
+
+
+# ------------------------------------------------------------------------------------------
+def pool_forward(ws, S, zb, adjb, nb, B, N, K, Fw):
+    nbp, lim = E._p(nb), int(nb is not None)
+    sb = cvt(ws, S.data_ptr(), K, B * N, K, B=B)
+    xp, xpb = ws.f(B, K, Fw), bfbuf(ws, B, K, Fw)
+    tcgemm(sb, MN, zb, MN, K, Fw, N, B, Cf=(xp.data_ptr(), Fw, K * Fw), Cb=xpb, lim=nbp, lim_k=lim)
+    tb = bfbuf(ws, B, K, N)
+    tcgemm(sb, MN, adjb, MN, K, N, N, B, Cb=tb, lim=nbp, lim_k=lim, lim_n=lim)
+    ap, apb = ws.f(B, K, K), bfbuf(ws, B, K, K)
+    tcgemm(tb, KM, sb, MN, K, K, N, B, Cf=(ap.data_ptr(), K, K * K), Cb=apb, lim=nbp, lim_k=lim)
+    return sb, xp, xpb, tb, ap, apb
+
+
+def pool_backward(ws, dxp, dap, sb, zb, adjb, tb, nb, B, N, K, Fw, ds, acc_ds, dadj):
+    nbp, lim = E._p(nb), int(nb is not None)
+    dxpb = cvt(ws, dxp.data_ptr(), Fw, B * K, Fw, B=B)
+    dapb = cvt(ws, dap.data_ptr(), K, B * K, K, B=B)
+    dz = ws.f(B, N, Fw)
+    tcgemm(sb, KM, dxpb, MN, N, Fw, K, B, Cf=(dz.data_ptr(), Fw, N * Fw), lim=nbp, lim_m=lim)
+    dsf = (ds.data_ptr(), K, N * K)
+    tcgemm(zb, KM, dxpb, KM, N, K, Fw, B, Cf=dsf, beta=1.0 if acc_ds else 0.0, lim=nbp, lim_m=lim)
+    tcgemm(tb, MN, dapb, MN, N, K, K, B, Cf=dsf, beta=1.0, lim=nbp, lim_m=lim)
+    wsb = bfbuf(ws, B, N, K)
+    tcgemm(sb, KM, dapb, KM, N, K, K, B, Cb=wsb, lim=nbp, lim_m=lim)
+    tcgemm(adjb, KM, wsb, MN, N, K, N, B, Cf=dsf, beta=1.0, lim=nbp, lim_m=lim, lim_k=lim)
+    if dadj is not None:
+        w2b = bfbuf(ws, B, N, K)
+        tcgemm(sb, KM, dapb, MN, N, K, K, B, Cb=w2b)
+        tcgemm(w2b, KM, sb, KM, N, N, K, B, Cf=(dadj.data_ptr(), N, N * N), beta=1.0)
+    return dz
+
+
+def assign_linear_fwd(ws, zab, Fa, rows, wp, bp):
+    K = int(wp.shape[0])
+    wpb = cvt(ws, wp.data_ptr(), Fa, K, Fa)                                             # [K, r8(Fa)]
+    T = ws.f(rows, K)
+    tcgemm(Op(zab.ptr, zab.ld, 0), KM, Op(wpb.ptr, wpb.ld, 0), KM, rows, K, Fa, 1, Cf=(T.data_ptr(), K, 0),
+           bias=E._p(bp))
+    return T, wpb
+
+
+def assign_linear_bwd(ws, dt, zab, Fa, rows, wpb, K, has_bias):
+    st = E._stream()
+    dtb = cvt(ws, dt.data_ptr(), K, rows, K)
+    dwp = ws.f(K, Fa)
+    tcgemm(Op(dtb.ptr, dtb.ld, 0), MN, Op(zab.ptr, zab.ld, 0), MN, K, Fa, rows, 1, Cf=(dwp.data_ptr(), Fa, 0),
+           split_k=pick_split(K, Fa, rows))
+    dbp = None
+    if has_bias:
+        dbp = ws.f(K)
+        cs = ws.f(256 * K)
+        call('gp_colsum_f32', E._p(dt), C.c_longlong(rows), K, C.c_longlong(K), E._p(dbp), 0, E._p(cs), st)
+    dza = ws.f(rows, Fa)
+    tcgemm(Op(dtb.ptr, dtb.ld, 0), KM, Op(wpb.ptr, wpb.ld, 0), MN, rows, Fa, K, 1, Cf=(dza.data_ptr(), Fa, 0))
+    return dwp, dbp, dza
+
+
+def linkloss_forward(ws, sb, adj, nb, B, N, K, need_grad):
+    """P = S S^T on tensor cores, then the fused masked-BCE / gsym pass.  Returns (partial, n, gsym op)."""
+    nbp, lim = E._p(nb), int(nb is not None)
+    P = ws.f(B, N, N)
+    tcgemm(sb, KM, sb, KM, N, N, K, B, Cf=(P.data_ptr(), N, N * N), lim=nbp, lim_m=lim, lim_n=lim)
+    T = (N + 31) // 32
+    partial = ws.f(B * T * T)
+    gs = bfbuf(ws, B, N, N) if need_grad else None
+    call('gp_linkloss_from_p', P.data_ptr(), adj.data_ptr(), nbp, B, N, N if gs is None else gs.ld,
+         partial.data_ptr(), None if gs is None else gs.ptr, E._stream())
+    return partial, B * T * T, gs
+
+
+def linkloss_backward(ws, gs, sb, nb, B, N, K, inv, g_ptr):
+    nbp, lim = E._p(nb), int(nb is not None)
+    dS = ws.f(B, N, K)
+    tcgemm(gs, KM, sb, MN, N, K, N, B, Cf=(dS.data_ptr(), K, N * K), alpha=inv, alpha_dev=g_ptr, lim=nbp, lim_m=lim,
+           lim_k=lim)
+    return dS

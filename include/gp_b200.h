@@ -78,6 +78,32 @@ typedef struct gp_gemm {
 int gp_bgemm_f32(const gp_gemm* g, gp_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Tensor-core variant of the same contraction: bf16 operands (TMA -> shared memory, 128B swizzle),
+ * tcgen05.mma with fp32 accumulation in TMEM, fp32 output C and/or a bf16 copy Cb (so the next
+ * contraction needs no conversion pass).  Operands keep their natural row-major layout:
+ *   a_major 0: A stored [M rows][K cols] (K-major)   1: A stored [K rows][M cols] (M-major, "A^T")
+ *   b_major 0: B stored [N rows][K cols] (K-major)   1: B stored [K rows][N cols] (N-major)
+ * ldA/ldB/sAb/sBb in elements, multiples of 8; bases 16-byte aligned (TMA).  Operand buffers must
+ * be finite up to the next multiple of 64 beyond any clipped K extent (0 * NaN would poison a tile).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct gp_gemm_bf16 {
+  const void* A; const void* B;          /* bf16 */
+  float* C; void* Cb;                    /* fp32 and/or bf16 output (either may be NULL) */
+  int M, N, K, batch;
+  long long ldA, sAb; int a_major;
+  long long ldB, sBb; int b_major;
+  long long ldC, sCb, ldCb, sCbb;
+  const int32_t* lim; int lim_m, lim_n, lim_k;
+  float alpha, beta; const float* alpha_dev;
+  const float* bias; int relu;
+  int split_k;
+} gp_gemm_bf16;
+int gp_bgemm_bf16(const gp_gemm_bf16* g, gp_stream_t stream);
+/* y[r, 0:cols_pad] = bf16(x[r, 0:cols]) zero-padded to cols_pad (row strides ldx / ldy in elements) */
+int gp_cvt_f32_bf16(const float* x, long long ldx, void* y, long long ldy, long long rows, int cols,
+                    int cols_pad, gp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * GraphConv  (encoders.py:315-328):  U = A.X (+X);  V = U.W + b;  Y = V / max(||V||_2, 1e-12)
  *   x [B,N,din] row stride ldx;  adj [B,N,N];  w [din,dout];  bias [dout] or NULL
  *   u [B,N,din] (saved for backward);  y [B,N,dout] row stride ldy;  rnorm [B,N] = max(||V||,eps)
@@ -160,6 +186,11 @@ int gp_linkloss_fwd(const float* s, const float* adj, const int32_t* nb, int B, 
                     float* partial, float* gsym, gp_stream_t stream);
 int gp_loss_finalize(const float* partial, int n_partial, double inv_entries, const float* ce,
                      float* total, float* link, gp_stream_t stream);
+/* Tensor-core path: P = S S^T [B,N,N] fp32 from gp_bgemm_bf16; this pass does the masked BCE
+ * reduction (n_partial = B * ceil(N/32)^2) and writes gsym as the bf16 operand (row stride ldg) of
+ * the backward GEMM, zero-filled up to the next multiple of 64 beyond nb[b]. */
+int gp_linkloss_from_p(const float* P, const float* adj, const int32_t* nb, int B, int N, long long ldg,
+                       float* partial, void* gsym_bf16, gp_stream_t stream);
 
 /* Row entropy  -sum_k S log(S+eps) averaged over real rows, and the Frobenius variant of the
  * link loss (north-star options, not in the reference).  TODO(next round). */
@@ -177,6 +208,9 @@ int gp_ce_bwd(const float* probs, const int64_t* label, const float* upstream, i
 int gp_colsum_f32(const float* x, long long rows, int d, long long ld, float* out, int accumulate,
                   float* ws, gp_stream_t stream);
 int gp_relu_mask_bwd(const float* dy, const float* y, long long n, float* dx, gp_stream_t stream);
+/* in place: v (+bias) -> v / max(||v||_2, 1e-12) per row (encoders.py:323-326); rnorm[r] = the divisor */
+int gp_bias_normalize_f32(float* v, const float* bias, float* rnorm, long long rows, int d, long long ld,
+                          int normalize, gp_stream_t stream);
 /* x[i] = v ;  y[i] += a*x[i]  (buffer initialisation / gradient accumulation for num_pooling >= 2) */
 int gp_fill_f32(float* x, long long n, float v, gp_stream_t stream);
 int gp_axpy_f32(const float* x, float* y, long long n, float a, gp_stream_t stream);

@@ -1,0 +1,51 @@
+"""GPU: the GP_BF16 tensor-core mode of the drop-in encoders against the fp64 oracle.
+
+Stated bound of this mode (bf16 operands, fp32 accumulation; BASELINE.json north_star "bf16
+tensor-core path with its own stated bound"):
+  ypred, S: rel-L2 <= 2e-2;  loss: relative <= 5e-3;
+  full flattened parameter gradient: rel-L2 <= 0.15 and cosine similarity >= 0.99.
+(The fp32 mode's bound is 1e-5, tests/test_gpu_model.py.)"""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import rel_l2, synth_batch
+from oracle import diffpool_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('N,D,H,C,B,ratio,P,n_min,density', [
+    (64, 8, 16, 3, 4, 0.25, 1, 16, 0.1), (256, 16, 32, 2, 4, 0.25, 1, 64, 0.05),
+    (100, 3, 30, 6, 20, 0.1, 1, 2, 0.08), (512, 64, 64, 2, 3, 0.25, 1, 128, 0.02),
+    (200, 89, 24, 2, 3, 0.25, 2, 50, 0.05)])
+def test_bf16_mode_bounds(N, D, H, C, B, ratio, P, n_min, density):
+    from graph_pooling_b200 import encoders
+    torch.manual_seed(N)
+    mo = orc.SoftPoolingGcnEncoder(N, D, H, H, C, 3, H, assign_ratio=ratio, num_pooling=P)
+    g = torch.Generator().manual_seed(N + 1)
+    with torch.no_grad():
+        for k, p in mo.named_parameters():
+            if k.endswith('bias'):
+                p.copy_(0.2 * torch.randn(p.shape, generator=g))
+    mc = encoders.SoftPoolingGcnEncoder(N, D, H, H, C, 3, H, assign_ratio=ratio, num_pooling=P)
+    mc.load_state_dict(mo.state_dict())
+    mc = mc.cuda()
+    mc.precision = 1
+    x, adj, nb, label = synth_batch(N, B, N, D, n_min, N, C, density)
+    m64 = copy.deepcopy(mo).double()
+    yo, lo = orc.train_step(m64, torch.tensor(x).double(), torch.tensor(adj).double(), torch.tensor(label), nb)
+    xc, ac = torch.tensor(x).cuda(), torch.tensor(adj).cuda()
+    yp = mc(xc, ac, nb, assign_x=xc)
+    loss = mc.loss(yp, torch.tensor(label).cuda(), ac, nb)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert rel_l2(yp.detach().cpu().numpy(), yo.detach().numpy()) < 2e-2
+    assert rel_l2(mc.assign_tensors[0].detach().cpu().numpy(), m64.assign_tensors[0].detach().numpy()) < 2e-2
+    assert abs(loss.item() - lo.item()) < 5e-3 * abs(lo.item())
+    gc = np.concatenate([p.grad.cpu().numpy().ravel() for p in mc.parameters()]).astype(np.float64)
+    go = np.concatenate([p.grad.numpy().ravel() for p in m64.parameters()])
+    cos = float(gc @ go / (np.linalg.norm(gc) * np.linalg.norm(go)))
+    assert rel_l2(gc, go) < 0.15 and cos > 0.99, (rel_l2(gc, go), cos)
