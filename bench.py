@@ -228,7 +228,11 @@ def main():
     lib.gp_launch_count_reset()
     sampler = ClockSampler(local) if rank == 0 else None
     t0 = time.time()
+    if os.environ.get('GP_PROFILE'):            # ncu --profile-from-start off: capture the timed steps only
+        torch.cuda.cudart().cudaProfilerStart()
     ms = timed(lambda: step(x, adj, label), args.steps)
+    if os.environ.get('GP_PROFILE'):
+        torch.cuda.cudart().cudaProfilerStop()
     t1 = time.time()
     clocks = sampler.stop(t0, t1) if sampler else None
     launches = int(lib.gp_launch_count())

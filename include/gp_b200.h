@@ -83,8 +83,10 @@ int gp_bgemm_f32(const gp_gemm* g, gp_stream_t stream);
  * contraction needs no conversion pass).  Operands keep their natural row-major layout:
  *   a_major 0: A stored [M rows][K cols] (K-major)   1: A stored [K rows][M cols] (M-major, "A^T")
  *   b_major 0: B stored [N rows][K cols] (K-major)   1: B stored [K rows][N cols] (N-major)
- * ldA/ldB/sAb/sBb in elements, multiples of 8; bases 16-byte aligned (TMA).  Operand buffers must
- * be finite up to the next multiple of 64 beyond any clipped K extent (0 * NaN would poison a tile).
+ * ldA/ldB/sAb/sBb in elements, multiples of 8; bases 16-byte aligned (TMA).  lim_k skips whole
+ * 64-wide K tiles, it does not mask inside a tile: between lim[b] and the next multiple of 64 one
+ * operand must be ZERO and the other finite (true on the DiffPool path: zero-padded adjacency,
+ * masked S), otherwise use gp_bgemm_f32.
  * ------------------------------------------------------------------------------------------- */
 typedef struct gp_gemm_bf16 {
   const void* A; const void* B;          /* bf16 */

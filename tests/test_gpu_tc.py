@@ -61,6 +61,11 @@ def test_tc_gemm_limits_beta_alpha_bf16_copy():
     A, Bm, A64, B64 = mk(batch, M, N, K, 0, 1, 7)
     lim_np = np.array([384, 100, 257], np.int32)
     lim = torch.tensor(lim_np).cuda()
+    # contract of lim_k (include/gp_b200.h): one operand is ZERO beyond the clipped K extent, as the
+    # zero-padded adjacency / masked S are on the DiffPool path (tiles are skipped, not masked)
+    for b in range(batch):
+        A[b, :, lim_np[b]:] = 0
+        A64[b, :, lim_np[b]:] = 0
     C0 = torch.randn(batch, M, N, device='cuda')
     out, ob = run_tc(A, Bm, M, N, K, batch, 0, 1, lim=lim, lim_m=1, lim_k=1, alpha=0.5, beta=1.0, C0=C0,
                      want_bf16=True)
