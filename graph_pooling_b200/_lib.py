@@ -58,6 +58,7 @@ _PROTOS = {
                     c_f, c_i, c_f],
     'gp_linkloss_fwd': [c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f, c_f],
     'gp_loss_finalize': [c_f, c_i, C.c_double, c_f, c_f, c_f, c_f],
+    'gp_linkloss_tc': [c_f, c_ll, c_f, c_ll, c_f, c_i, c_i, c_i, c_f, c_f, c_ll, c_f],
     'gp_linkloss_from_p': [c_f, c_f, c_f, c_i, c_i, c_ll, c_f, c_f, c_f],
     'gp_ce_fwd': [c_f, c_f, c_i, c_i, c_f, c_f, c_f],
     'gp_ce_bwd': [c_f, c_f, c_f, c_i, c_i, c_f, c_f],

@@ -31,7 +31,12 @@ struct TcParams {
   float alpha, beta; const float* alpha_dev;
   const float* bias; int relu;
   int split_k;
+  // EPI == 1 (fused link-prediction loss): bf16 adjacency, bf16 gsym output (Cb), per-warp partial sums
+  const __nv_bfloat16* adjb; long long ldadj, sadjb;
+  float* partial;
 };
+
+constexpr float kEpsLinkTc = 1e-7f;
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -112,7 +117,7 @@ struct TcSmem {
 // ------------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------------
-template <int BN, int STAGES, bool A_MN, bool B_MN>
+template <int BN, int STAGES, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(192, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -223,6 +228,66 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     const bool row_ok = row < p.M;
     const bool row_in = row < Me;
+    if constexpr (EPI == 1) {
+      // ---- fused link-prediction loss (encoders.py:1311-1331): the accumulator tile is P = S S^T.
+      //   l = -a log(p+eps) - (1-a) log(1-p+eps) summed over the nb x nb block;
+      //   gsym = dl/dp(a[m,n]) + dl/dp(a[n,m])  (bf16, operand of the backward GEMM gsym.S)
+      float lsum = 0.f;
+      const __nv_bfloat16* ab = p.adjb + (long long)b * p.sadjb;
+      __nv_bfloat16* grow = p.Cb != nullptr ? p.Cb + (long long)b * p.sCbb + (long long)row * p.ldCb : nullptr;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        if (nk > 0) {
+          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
+        }
+        const int nbase = n0 + c * 32;
+        if (nk == 0 || !row_ok || nbase >= p.N) continue;
+        float g[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int n = nbase + j;
+          float gg = 0.f;
+          if (row_in && n < Ne) {
+            float pv = __uint_as_float(v[j]);
+            const bool over = pv > 1.f;
+            if (over) pv = 1.f;
+            const float a1 = __bfloat162float(ab[(long long)row * p.ldadj + n]);
+            const float a2 = __bfloat162float(ab[(long long)n * p.ldadj + row]);
+            const float pe = pv + kEpsLinkTc, qe = 1.f - pv + kEpsLinkTc;
+            lsum -= a1 * __logf(pe) + (1.f - a1) * __logf(qe);
+            if (!over) gg = -(a1 + a2) * __fdividef(1.f, pe) + (2.f - a1 - a2) * __fdividef(1.f, qe);
+          }
+          g[j] = gg;
+        }
+        if (grow != nullptr) {
+          if (nbase + 32 <= p.N && (p.ldCb % 8 == 0)) {
+            uint4* dst = reinterpret_cast<uint4*>(grow + nbase);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(g[8 * j], g[8 * j + 1]);
+              __nv_bfloat162 h1 = __floats2bfloat162_rn(g[8 * j + 2], g[8 * j + 3]);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(g[8 * j + 4], g[8 * j + 5]);
+              __nv_bfloat162 h3 = __floats2bfloat162_rn(g[8 * j + 6], g[8 * j + 7]);
+              uint4 o;
+              o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+              o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
+              dst[j] = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nbase + j < p.N) grow[nbase + j] = __float2bfloat16_rn(g[j]);
+          }
+        }
+      }
+      lsum = warp_sum(lsum);
+      if (lane == 0)
+        p.partial[(((long long)b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 4 + warp] = lsum;
+    } else {
     float* crow = p.C != nullptr ? p.C + (long long)b * p.sCb + (long long)row * p.ldC : nullptr;
     __nv_bfloat16* cbrow = p.Cb != nullptr ? p.Cb + (long long)b * p.sCbb + (long long)row * p.ldCb : nullptr;
     const bool vec4 = (p.ldC % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && (p.sCb % 4 == 0);
@@ -306,6 +371,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+    }  // EPI == 0
   }
 
   // teardown: everyone done with TMEM before the allocating warp frees it
@@ -386,10 +452,10 @@ static int make_map(CUtensorMap* tm, const void* ptr, long long cols, long long 
   return GP_OK;
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
+template <int BN, int STAGES, bool A_MN, bool B_MN, int EPI = 0>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t st) {
   using L = TcSmem<BN, STAGES>;
-  auto kern = tc_gemm_kernel<BN, STAGES, A_MN, B_MN>;
+  auto kern = tc_gemm_kernel<BN, STAGES, A_MN, B_MN, EPI>;
   static bool configured = false;
   if (!configured) {
     GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes));
@@ -455,6 +521,7 @@ extern "C" int gp_bgemm_bf16(const gp_gemm_bf16* g, gp_stream_t stream) {
   p.lim = g->lim; p.lim_m = g->lim_m; p.lim_n = g->lim_n; p.lim_k = g->lim_k;
   p.alpha = g->alpha; p.beta = g->beta; p.alpha_dev = g->alpha_dev;
   p.bias = g->bias; p.relu = g->relu; p.split_k = g->split_k;
+  p.adjb = nullptr; p.ldadj = p.sadjb = 0; p.partial = nullptr;
   if (split > 1 && p.beta != 1.f) {
     const long long total = (long long)g->batch * g->M * g->N;
     int blocks = (int)((total + 255) / 256);
@@ -478,4 +545,27 @@ extern "C" int gp_cvt_f32_bf16(const float* x, long long ldx, void* y, long long
                                                       cols_pad);
   GP_LAUNCHED();
   return GP_OK;
+}
+
+// Fused link-prediction loss on tensor cores: P = S S^T tiles (128 x 256) live only in TMEM; the
+// epilogue does the masked BCE against the bf16 adjacency, writes gsym (bf16) and one partial sum
+// per epilogue warp.  n_partial = batch * ceil(N/128) * ceil(N/256) * 4.
+extern "C" int gp_linkloss_tc(const void* s_bf16, long long lds, const void* adj_bf16, long long ldadj,
+                              const int32_t* nb, int B, int N, int K, float* partial, void* gsym_bf16,
+                              long long ldg, gp_stream_t stream) {
+  GP_REQUIRE(s_bf16 && adj_bf16 && partial && B > 0 && N > 0 && K > 0, "linkloss_tc: bad args");
+  GP_REQUIRE(lds % 8 == 0 && ldadj % 8 == 0 && (gsym_bf16 == nullptr || ldg >= N), "linkloss_tc: bad strides");
+  GP_REQUIRE(B <= 65535, "linkloss_tc: batch too large");
+  CUtensorMap tmA, tmB;
+  GP_TRY(make_map(&tmA, s_bf16, K, N, B, lds, (long long)N * lds, BM));
+  GP_TRY(make_map(&tmB, s_bf16, K, N, B, lds, (long long)N * lds, 256));
+  TcParams p;
+  p.C = nullptr; p.Cb = reinterpret_cast<__nv_bfloat16*>(gsym_bf16);
+  p.M = N; p.N = N; p.K = K; p.batch = B;
+  p.ldC = p.sCb = 0; p.ldCb = ldg; p.sCbb = (long long)N * ldg;
+  p.lim = nb; p.lim_m = p.lim_n = nb != nullptr; p.lim_k = 0;
+  p.alpha = 1.f; p.beta = 0.f; p.alpha_dev = nullptr; p.bias = nullptr; p.relu = 0; p.split_k = 0;
+  p.adjb = reinterpret_cast<const __nv_bfloat16*>(adj_bf16); p.ldadj = ldadj; p.sadjb = (long long)N * ldadj;
+  p.partial = partial;
+  return launch_tc<256, 4, false, false, 1>(tmA, tmB, p, S(stream));
 }

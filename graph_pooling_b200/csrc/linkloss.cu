@@ -102,6 +102,22 @@ linkloss_fwd_kernel(const float* __restrict__ s, const float* __restrict__ adj, 
   if (tid == 0) partial[pidx] = tot;
 }
 
+// stage 1 of the finalisation for large partial arrays: R blocks -> R sums appended after the array
+__global__ void loss_partial_reduce_kernel(float* __restrict__ partial, int n_partial, int R) {
+  __shared__ double shd[256];
+  const int per = (n_partial + R - 1) / R;
+  const int i0 = blockIdx.x * per, i1 = min(n_partial, i0 + per);
+  double s = 0.0;
+  for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) s += (double)partial[i];
+  shd[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) shd[threadIdx.x] += shd[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[n_partial + blockIdx.x] = (float)shd[0];
+}
+
 __global__ void loss_finalize_kernel(const float* __restrict__ partial, int n_partial, double inv_entries,
                                      const float* __restrict__ ce, float* __restrict__ total,
                                      float* __restrict__ link) {
@@ -199,6 +215,12 @@ extern "C" int gp_linkloss_fwd(const float* s, const float* adj, const int32_t* 
 extern "C" int gp_loss_finalize(const float* partial, int n_partial, double inv_entries, const float* ce,
                                 float* total, float* link, gp_stream_t stream) {
   GP_REQUIRE(partial && n_partial > 0, "loss_finalize: bad args");
+  if (n_partial > 8192) {     // two stages; the caller provides 256 floats of scratch after the array
+    loss_partial_reduce_kernel<<<256, 256, 0, S(stream)>>>(const_cast<float*>(partial), n_partial, 256);
+    GP_LAUNCHED();
+    partial += n_partial;
+    n_partial = 256;
+  }
   loss_finalize_kernel<<<1, 256, 0, S(stream)>>>(partial, n_partial, inv_entries, ce, total, link);
   GP_LAUNCHED();
   return GP_OK;

@@ -323,11 +323,11 @@ class _LossFn(torch.autograd.Function):
         need_grad = ctx.needs_input_grad[3]
         ctx.sb = getattr(plan, 'sb0', None)
         if ctx.sb is not None:                      # GP_BF16: P = S S^T on tensor cores
-            partial, npart, gsym = T.linkloss_forward(ws, ctx.sb, adj, plan.nb_dev, Bn, N, K, need_grad)
+            partial, npart, gsym = T.linkloss_forward(ws, ctx.sb, plan.adjb, plan.nb_dev, Bn, N, K, need_grad)
         else:
             nt = (N + 63) // 64
             npart = Bn * nt * nt
-            partial = ws.f(npart)
+            partial = ws.f(npart + 256)
             gsym = ws.f(Bn, N, N) if need_grad else None
             call('gp_linkloss_fwd', S.data_ptr(), adj.data_ptr(), E._p(plan.nb_dev), Bn, N, K, partial.data_ptr(),
                  E._p(gsym), st)
@@ -671,6 +671,7 @@ class SoftPoolingGcnEncoder(GcnEncoderGraph):
         S0 = self._S0                                                        # R7: level-0 S with level-0 adj
         lp = _Plan()
         lp.sb0 = getattr(plan, 'sb0', None)
+        lp.adjb = getattr(plan, 'adjb', None)
         lp.nb_dev, nb_host = E.prep_nb(batch_num_nodes, adj.shape[1], adj.device)
         if nb_host is None:
             lp.num_entries = adj.shape[1] * adj.shape[1] * adj.shape[0]

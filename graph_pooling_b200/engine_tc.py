@@ -225,17 +225,16 @@ def assign_linear_bwd(ws, dt, zab, Fa, rows, wpb, K, has_bias):
     return dwp, dbp, dza
 
 
-def linkloss_forward(ws, sb, adj, nb, B, N, K, need_grad):
-    """P = S S^T on tensor cores, then the fused masked-BCE / gsym pass.  Returns (partial, n, gsym op)."""
-    nbp, lim = E._p(nb), int(nb is not None)
-    P = ws.f(B, N, N)
-    tcgemm(sb, KM, sb, KM, N, N, K, B, Cf=(P.data_ptr(), N, N * N), lim=nbp, lim_m=lim, lim_n=lim)
-    T = (N + 31) // 32
-    partial = ws.f(B * T * T)
+def linkloss_forward(ws, sb, adjb, nb, B, N, K, need_grad):
+    """Fused tensor-core link loss: P = S S^T tiles stay in TMEM, the epilogue does the masked BCE
+    against the bf16 adjacency and writes gsym (bf16).  Returns (partial, n_partial, gsym op)."""
+    nbp = E._p(nb)
+    npart = B * ((N + 127) // 128) * ((N + 255) // 256) * 4
+    partial = ws.f(npart + 256)                      # +256: scratch of the two-stage finalisation
     gs = bfbuf(ws, B, N, N) if need_grad else None
-    call('gp_linkloss_from_p', P.data_ptr(), adj.data_ptr(), nbp, B, N, N if gs is None else gs.ld,
-         partial.data_ptr(), None if gs is None else gs.ptr, E._stream())
-    return partial, B * T * T, gs
+    call('gp_linkloss_tc', sb.ptr, sb.ld, adjb.ptr, adjb.ld, nbp, B, N, K, partial.data_ptr(),
+         None if gs is None else gs.ptr, N if gs is None else gs.ld, E._stream())
+    return partial, npart, gs
 
 
 def linkloss_backward(ws, gs, sb, nb, B, N, K, inv, g_ptr):

@@ -191,6 +191,13 @@ int gp_loss_finalize(const float* partial, int n_partial, double inv_entries, co
 /* Tensor-core path: P = S S^T [B,N,N] fp32 from gp_bgemm_bf16; this pass does the masked BCE
  * reduction (n_partial = B * ceil(N/32)^2) and writes gsym as the bf16 operand (row stride ldg) of
  * the backward GEMM, zero-filled up to the next multiple of 64 beyond nb[b]. */
+/* Fused tensor-core form: S (bf16, row stride lds) -> P = S S^T tiles in TMEM -> masked BCE against
+ * the bf16 adjacency in the epilogue; gsym (bf16, row stride ldg, may be NULL) and one partial per
+ * epilogue warp: n_partial = B * ceil(N/128) * ceil(N/256) * 4.  P never touches HBM.
+ * gp_loss_finalize with n_partial > 8192 uses 256 floats of scratch AFTER the partial array. */
+int gp_linkloss_tc(const void* s_bf16, long long lds, const void* adj_bf16, long long ldadj,
+                   const int32_t* nb, int B, int N, int K, float* partial, void* gsym_bf16, long long ldg,
+                   gp_stream_t stream);
 int gp_linkloss_from_p(const float* P, const float* adj, const int32_t* nb, int B, int N, long long ldg,
                        float* partial, void* gsym_bf16, gp_stream_t stream);
 

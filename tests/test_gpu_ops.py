@@ -223,7 +223,7 @@ def test_linkloss_fwd_bwd(B, N, K, use_nb, sym):
     nbc = dev(nb) if use_nb else None
     nbp = None if nbc is None else nbc.data_ptr()
     T = (N + 63) // 64
-    partial = torch.empty(B * T * T, device='cuda')
+    partial = torch.empty(B * T * T + 256, device='cuda')
     gsym = torch.empty(B, N, N, device='cuda')
     call('gp_linkloss_fwd', sc.data_ptr(), ac.data_ptr(), nbp, B, N, K, partial.data_ptr(), gsym.data_ptr(), st())
     entries = float(np.sum(nb.astype(np.int64) ** 2)) if use_nb else float(B * N * N)
