@@ -35,8 +35,25 @@ class GpGemmBf16(C.Structure):
                 ('bias', c_f), ('relu', c_i), ('split_k', c_i)]
 
 
+class GpOperandPair(C.Structure):
+    _fields_ = [('A', c_f), ('B', c_f), ('K', c_i),
+                ('ldA', c_ll), ('sAb', c_ll), ('a_major', c_i),
+                ('ldB', c_ll), ('sBb', c_ll), ('b_major', c_i), ('lim_k', c_i)]
+
+
+class GpGemmBf16x(C.Structure):
+    _fields_ = [('pair', GpOperandPair * 4), ('npairs', c_i),
+                ('C', c_f), ('Cb', c_f),
+                ('M', c_i), ('N', c_i), ('batch', c_i),
+                ('ldC', c_ll), ('sCb', c_ll), ('ldCb', c_ll), ('sCbb', c_ll),
+                ('lim', c_f), ('lim_m', c_i), ('lim_n', c_i),
+                ('alpha', C.c_float), ('beta', C.c_float), ('alpha_dev', c_f),
+                ('bias', c_f), ('relu', c_i), ('split_k', c_i)]
+
+
 # name -> argtypes (restype is int unless listed in _RESTYPES)
 _PROTOS = {
+    'gp_bgemm_bf16x': [C.POINTER(GpGemmBf16x), c_f],
     'gp_bgemm_bf16': [C.POINTER(GpGemmBf16), c_f],
     'gp_cvt_f32_bf16': [c_f, c_ll, c_f, c_ll, c_ll, c_i, c_i, c_f],
     'gp_version': [],

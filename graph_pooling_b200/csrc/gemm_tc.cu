@@ -231,7 +231,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if constexpr (EPI == 1) {
       // ---- fused link-prediction loss (encoders.py:1311-1331): the accumulator tile is P = S S^T.
       //   l = -a log(p+eps) - (1-a) log(1-p+eps) summed over the nb x nb block;
-      //   gsym = dl/dp(a[m,n]) + dl/dp(a[n,m])  (bf16, operand of the backward GEMM gsym.S)
+      //   G = dl/dp evaluated with a[m,n] only (bf16): the backward is dS = (G + G^T).S, computed as two
+      //   GEMMs G.S + G^T.S (G^T is just the M-major view of G), so the transposed adjacency is never read.
       float lsum = 0.f;
       const __nv_bfloat16* ab = p.adjb + (long long)b * p.sadjb;
       __nv_bfloat16* grow = p.Cb != nullptr ? p.Cb + (long long)b * p.sCbb + (long long)row * p.ldCb : nullptr;
@@ -246,6 +247,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         const int nbase = n0 + c * 32;
         if (nk == 0 || !row_ok || nbase >= p.N) continue;
+        // this thread's 32 adjacency entries a[row, nbase..nbase+31] (64 contiguous bytes)
+        __align__(16) __nv_bfloat16 a[32];
+        if (row_in && nbase + 32 <= p.N && (p.ldadj % 8 == 0)) {
+          const uint4* src = reinterpret_cast<const uint4*>(ab + (long long)row * p.ldadj + nbase);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(a)[j] = src[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            a[j] = (row_in && nbase + j < p.N) ? ab[(long long)row * p.ldadj + nbase + j] : __float2bfloat16_rn(0.f);
+        }
         float g[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -255,11 +267,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float pv = __uint_as_float(v[j]);
             const bool over = pv > 1.f;
             if (over) pv = 1.f;
-            const float a1 = __bfloat162float(ab[(long long)row * p.ldadj + n]);
-            const float a2 = __bfloat162float(ab[(long long)n * p.ldadj + row]);
+            const float a1 = __bfloat162float(a[j]);
             const float pe = pv + kEpsLinkTc, qe = 1.f - pv + kEpsLinkTc;
             lsum -= a1 * __logf(pe) + (1.f - a1) * __logf(qe);
-            if (!over) gg = -(a1 + a2) * __fdividef(1.f, pe) + (2.f - a1 - a2) * __fdividef(1.f, qe);
+            if (!over) gg = -a1 * __fdividef(1.f, pe) + (1.f - a1) * __fdividef(1.f, qe);
           }
           g[j] = gg;
         }
@@ -550,9 +561,11 @@ extern "C" int gp_cvt_f32_bf16(const float* x, long long ldx, void* y, long long
 // Fused link-prediction loss on tensor cores: P = S S^T tiles (128 x 256) live only in TMEM; the
 // epilogue does the masked BCE against the bf16 adjacency, writes gsym (bf16) and one partial sum
 // per epilogue warp.  n_partial = batch * ceil(N/128) * ceil(N/256) * 4.
-extern "C" int gp_linkloss_tc(const void* s_bf16, long long lds, const void* adj_bf16, long long ldadj,
-                              const int32_t* nb, int B, int N, int K, float* partial, void* gsym_bf16,
-                              long long ldg, gp_stream_t stream) {
+// (superseded by the persistent v2 kernel in gemm_tc2.cu, which exports gp_linkloss_tc; kept as the
+// single-tile-per-CTA reference implementation of the same epilogue)
+extern "C" int gp_linkloss_tc_v1(const void* s_bf16, long long lds, const void* adj_bf16, long long ldadj,
+                                 const int32_t* nb, int B, int N, int K, float* partial, void* gsym_bf16,
+                                 long long ldg, gp_stream_t stream) {
   GP_REQUIRE(s_bf16 && adj_bf16 && partial && B > 0 && N > 0 && K > 0, "linkloss_tc: bad args");
   GP_REQUIRE(lds % 8 == 0 && ldadj % 8 == 0 && (gsym_bf16 == nullptr || ldg >= N), "linkloss_tc: bad strides");
   GP_REQUIRE(B <= 65535, "linkloss_tc: batch too large");

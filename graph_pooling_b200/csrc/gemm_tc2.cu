@@ -1,0 +1,554 @@
+// v2 of the tcgen05 batched GEMM: persistent, warp-specialised, double-buffered TMEM.
+//
+//   C[b] (fp32 and/or bf16) = alpha * sum_q op(A_q[b]) . op(B_q[b])  (+bias)(relu) + beta * C[b]
+//
+// * persistent CTAs (one per SM) walk a tile list; 10 warps: 0-7 epilogue, 8 TMA producer, 9 MMA issuer;
+// * two TMEM accumulator buffers (2 x BN columns): the epilogue of tile i drains buffer i&1 while the
+//   tensor cores fill the other one with tile i+1 (tmem_full / tmem_empty mbarriers);
+// * up to 4 operand PAIRS are accumulated into the same accumulator (a K-concatenation of different
+//   products, each with its own TMA maps and operand major-ness).  The DiffPool backward uses this for
+//   dS = Z dX'^T + T^T dA' + A (S dA'^T) and for dS_link = (G + G^T) S, replacing read-modify-write
+//   chains over [B,N,K] buffers by one pass;
+// * epilogue: TMEM -> registers -> per-warp shared staging tile (transposed, conflict-free) -> fully
+//   coalesced 128-byte global stores (fp32), 64-byte (bf16);
+// * EPI == 1: fused link-prediction loss (encoders.py:1311-1331).  The accumulator tile is P = S S^T;
+//   the epilogue does the masked BCE against the bf16 adjacency (coalesced), writes G = dl/dP (bf16) and
+//   one partial sum per epilogue warp; P never touches HBM.  {0,1} adjacency tiles (warp-uniform test)
+//   take a fast path with one log and one reciprocal per element instead of two each.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+namespace gp {
+namespace v2 {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kMaxPairs = 4;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = (kEpiWarps + 2) * 32;
+constexpr float kEpsLink = 1e-7f;
+
+struct Maps { CUtensorMap a[kMaxPairs]; CUtensorMap b[kMaxPairs]; };
+
+struct Params {
+  float* C; __nv_bfloat16* Cb;
+  int M, N, batch;
+  long long ldC, sCb, ldCb, sCbb;
+  const int32_t* lim; int lim_m, lim_n;
+  float alpha, beta; const float* alpha_dev;
+  const float* bias; int relu;
+  int split_k;
+  int npairs;
+  int K[kMaxPairs]; int a_mn[kMaxPairs]; int b_mn[kMaxPairs]; int lim_k[kMaxPairs];
+  int tiles_m, tiles_n; long long total_work;
+  const __nv_bfloat16* adjb; long long ldadj, sadjb; float* partial;   // EPI == 1
+};
+
+struct Work {
+  int b, ks, m0, n0, Me, Ne;
+  int kt[kMaxPairs];     // k-tiles per pair (after clipping)
+  int kt0, kt1;          // this split's range over the concatenated k-tile sequence
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try(bar, parity)) {
+    if (++spins > (1u << 26)) { __trap(); }     // protocol bug: fail loudly instead of hanging the GPU
+  }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// UMMA smem descriptor, SWIZZLE_128B (see gemm_tc.cu)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int BN, int STAGES>
+struct Smem {
+  static constexpr int kA = BM * BK * 2;
+  static constexpr int kB = BN * BK * 2;
+  static constexpr int kStage = kA + kB;
+  static constexpr int kStaging = kEpiWarps * 32 * 33 * 4;
+  static constexpr int kBytes = STAGES * kStage + kStaging + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ Work get_work(const Params& p, long long w) {
+  Work k;
+  const int split = p.split_k > 1 ? p.split_k : 1;
+  const int nt = (int)(w % p.tiles_n);
+  const long long r = w / p.tiles_n;
+  const int mt = (int)(r % p.tiles_m);
+  const int z = (int)(r / p.tiles_m);
+  k.b = z / split; k.ks = z % split;
+  k.m0 = mt * BM; k.n0 = nt;        // n0 scaled by BN by the caller
+  int l = 0x7fffffff;
+  if (p.lim != nullptr) l = p.lim[k.b];
+  k.Me = p.lim_m ? min(p.M, l) : p.M;
+  k.Ne = p.lim_n ? min(p.N, l) : p.N;
+  int tot = 0;
+#pragma unroll
+  for (int q = 0; q < kMaxPairs; ++q) {
+    int t = 0;
+    if (q < p.npairs) {
+      const int Ke = p.lim_k[q] ? min(p.K[q], l) : p.K[q];
+      t = (Ke + BK - 1) / BK;
+    }
+    k.kt[q] = t;
+    tot += t;
+  }
+  k.kt0 = tot; k.kt1 = tot;          // filled by finish_work once n0 is known
+  return k;
+}
+
+template <int BN>
+__device__ __forceinline__ void finish_work(const Params& p, Work& k) {
+  k.n0 *= BN;
+  const int split = p.split_k > 1 ? p.split_k : 1;
+  int tot = k.kt1;
+  const bool live = (k.m0 < k.Me) && (k.n0 < k.Ne);
+  if (!live) tot = 0;
+  const int per = (tot + split - 1) / split;
+  k.kt0 = min(tot, k.ks * per);
+  k.kt1 = min(tot, k.kt0 + per);
+}
+
+// ---- kernel -------------------------------------------------------------------------------------
+template <int BN, int STAGES, int EPI>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  using L = Smem<BN, STAGES>;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));
+  float* staging = reinterpret_cast<float*>(smem_gen + STAGES * L::kStage);
+  const uint32_t bar_base = base + STAGES * L::kStage + L::kStaging;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * L::kStage + L::kStaging + 8 * (2 * STAGES + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;          // BN in {64,128,256} -> 128/256/512
+
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+      for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kEpiWarps); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+  }
+  if (warp == 8 && lane == 0) {
+    for (int q = 0; q < p.npairs; ++q) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.a[q])) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.b[q])) : "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 8) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      uint32_t it = 0;                                   // running stage counter across tiles
+      for (long long w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+        Work k = get_work(p, w);
+        finish_work<BN>(p, k);
+        int pos = 0;
+        for (int q = 0; q < p.npairs; ++q) {
+          const int lo = max(k.kt0, pos), hi = min(k.kt1, pos + k.kt[q]);
+          for (int g = lo; g < hi; ++g, ++it) {
+            const int s = it % STAGES, ph = (it / STAGES) & 1;
+            mbar_wait(empty_bar(s), ph ^ 1);
+            mbar_expect_tx(full_bar(s), L::kStage);
+            const uint32_t sa = base + s * L::kStage, sb = sa + L::kA;
+            const int k0 = (g - pos) * BK;
+            if (p.a_mn[q]) {
+              tma_load_3d(sa, &maps.a[q], full_bar(s), k.m0, k0, k.b);
+              tma_load_3d(sa + 8192, &maps.a[q], full_bar(s), k.m0 + 64, k0, k.b);
+            } else {
+              tma_load_3d(sa, &maps.a[q], full_bar(s), k0, k.m0, k.b);
+            }
+            if (p.b_mn[q]) {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_3d(sb + j * 8192, &maps.b[q], full_bar(s), k.n0 + 64 * j, k0, k.b);
+            } else {
+              tma_load_3d(sb, &maps.b[q], full_bar(s), k0, k.n0, k.b);
+            }
+          }
+          pos += k.kt[q];
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      uint32_t it = 0, nacc = 0;
+      for (long long w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+        Work k = get_work(p, w);
+        finish_work<BN>(p, k);
+        if (k.kt1 <= k.kt0) continue;
+        const uint32_t a = nacc & 1, aph = (nacc >> 1) & 1;
+        mbar_wait(tempty_bar(a), aph ^ 1);               // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tm = tmem_base + a * BN;
+        int pos = 0;
+        bool first = true;
+        for (int q = 0; q < p.npairs; ++q) {
+          const int lo = max(k.kt0, pos), hi = min(k.kt1, pos + k.kt[q]);
+          const bool amn = p.a_mn[q] != 0, bmn = p.b_mn[q] != 0;
+          const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((amn ? 1u : 0u) << 15) |
+                                 ((bmn ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+          for (int g = lo; g < hi; ++g, ++it) {
+            const int s = it % STAGES, ph = (it / STAGES) & 1;
+            mbar_wait(full_bar(s), ph);
+            tc_fence_after();
+            const uint32_t sa = base + s * L::kStage, sb = sa + L::kA;
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; ++kk) {
+              const uint64_t ad = amn ? umma_desc(sa + kk * 2048, 8192, 1024) : umma_desc(sa + kk * 32, 16, 1024);
+              const uint64_t bd = bmn ? umma_desc(sb + kk * 2048, 8192, 1024) : umma_desc(sb + kk * 32, 16, 1024);
+              tc_mma_bf16(tm, ad, bd, idesc, (first && kk == 0) ? 0u : 1u);
+            }
+            first = false;
+            tc_commit(empty_bar(s));
+          }
+          pos += k.kt[q];
+        }
+        tc_commit(tfull_bar(a));
+        ++nacc;
+      }
+    }
+  } else {
+    // ===== epilogue warps 0..7 =====
+    const int quarter = warp & 3, half = warp >> 2;
+    float* stg = staging + warp * (32 * 33);
+    float alpha = p.alpha;
+    if (p.alpha_dev != nullptr) alpha *= *p.alpha_dev;
+    const int split = p.split_k > 1 ? p.split_k : 1;
+    uint32_t nacc = 0;
+    for (long long w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+      Work k = get_work(p, w);
+      finish_work<BN>(p, k);
+      const bool has_acc = k.kt1 > k.kt0;
+      const uint32_t a = nacc & 1, aph = (nacc >> 1) & 1;
+      if (has_acc) {
+        mbar_wait(tfull_bar(a), aph);
+        tc_fence_after();
+      }
+      const int row0 = k.m0 + quarter * 32;
+      float lsum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < BN / 64; ++c) {
+        const int col = half * (BN / 2) + c * 32;
+        const int nbase = k.n0 + col;
+        uint32_t v[32];
+        if (has_acc) {
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * BN + col), v);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
+        }
+        if (row0 >= p.M || nbase >= p.N) continue;       // warp-uniform
+        if (EPI == 0 && !has_acc && p.beta == 1.f && p.bias == nullptr) continue;   // nothing to add
+        // registers (lane = row) -> staging (transposed access, bank = (lane + j) % 32: conflict-free)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(v[j]);
+        __syncwarp();
+        const int n = nbase + lane;                      // lane = column from here on
+        const bool n_ok = n < p.N, n_in = n < k.Ne;
+        if (EPI == 1) {
+          if (has_acc) {
+            const __nv_bfloat16* ab = p.adjb + (long long)k.b * p.sadjb;
+            __nv_bfloat16* gb = p.Cb != nullptr ? p.Cb + (long long)k.b * p.sCbb : nullptr;
+            // adjacency entries of this lane's column for the 32 rows (coalesced 64 B per row)
+            float av[32];
+            bool is01 = true;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+              const int row = row0 + r;
+              float x = 0.f;
+              if (row < k.Me && n_in) x = __bfloat162float(ab[(long long)row * p.ldadj + n]);
+              av[r] = x;
+              is01 = is01 && (x == 0.f || x == 1.f);
+            }
+            const bool fast = __all_sync(0xffffffffu, is01);
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+              const int row = row0 + r;
+              float gg = 0.f;
+              if (row < k.Me && n_in) {
+                float pv = stg[r * 33 + lane];
+                const bool over = pv > 1.f;
+                if (over) pv = 1.f;
+                const float pe = pv + kEpsLink, qe = 1.f - pv + kEpsLink;
+                const float a1 = av[r];
+                if (fast) {                              // a in {0,1}: one log, one reciprocal
+                  const float x = a1 != 0.f ? pe : qe;
+                  lsum -= __logf(x);
+                  gg = over ? 0.f : (a1 != 0.f ? -__fdividef(1.f, x) : __fdividef(1.f, x));
+                } else {
+                  lsum -= a1 * __logf(pe) + (1.f - a1) * __logf(qe);
+                  gg = over ? 0.f : (-a1 * __fdividef(1.f, pe) + (1.f - a1) * __fdividef(1.f, qe));
+                }
+              }
+              if (gb != nullptr && row < p.M && n_ok) gb[(long long)row * p.ldCb + n] = __float2bfloat16_rn(gg);
+            }
+          }
+        } else {
+          float* cb = p.C != nullptr ? p.C + (long long)k.b * p.sCb : nullptr;
+          __nv_bfloat16* cbb = p.Cb != nullptr ? p.Cb + (long long)k.b * p.sCbb : nullptr;
+          const float bias = (p.bias != nullptr && n_ok) ? p.bias[n] : 0.f;
+          if (n_ok) {
+#pragma unroll 4
+            for (int r = 0; r < 32; ++r) {
+              const int row = row0 + r;
+              if (row >= p.M) break;
+              float x = (row < k.Me && n_in) ? alpha * stg[r * 33 + lane] : 0.f;
+              if (split > 1) {
+                if (x != 0.f) atomicAdd(cb + (long long)row * p.ldC + n, x);
+                continue;
+              }
+              x += bias;
+              if (p.relu) x = fmaxf(x, 0.f);
+              if (cb != nullptr) {
+                float* dst = cb + (long long)row * p.ldC + n;
+                if (p.beta != 0.f) x += p.beta * (*dst);
+                *dst = x;
+              }
+              if (cbb != nullptr) cbb[(long long)row * p.ldCb + n] = __float2bfloat16_rn(x);
+            }
+          }
+        }
+        __syncwarp();
+      }
+      if (EPI == 1) {
+        lsum = warp_sum(lsum);
+        if (lane == 0) p.partial[w * kEpiWarps + warp] = lsum;
+      }
+      if (has_acc) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(a));
+        ++nacc;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---- host ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* q = nullptr;
+    cudaDriverEntryPointQueryResult st;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &st) == cudaSuccess &&
+        st == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(q);
+  }
+  return fn;
+}
+static int make_map(CUtensorMap* tm, const void* ptr, long long cols, long long rows, long long batch,
+                    long long ld, long long sb, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (enc == nullptr) return fail(GP_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)(batch > 1 ? sb : ld * rows) * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(GP_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): cols=%lld rows=%lld batch=%lld ld=%lld sb=%lld",
+                (int)r, cols, rows, batch, ld, sb);
+  return GP_OK;
+}
+
+template <int BN, int STAGES, int EPI>
+static int launch(const Maps& maps, Params& p, cudaStream_t st) {
+  using L = Smem<BN, STAGES>;
+  auto kern = tc_gemm2_kernel<BN, STAGES, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes));
+    configured = true;
+  }
+  const int split = p.split_k > 1 ? p.split_k : 1;
+  p.tiles_m = (p.M + BM - 1) / BM;
+  p.tiles_n = (p.N + BN - 1) / BN;
+  p.total_work = (long long)p.tiles_m * p.tiles_n * p.batch * split;
+  const int grid = (int)(p.total_work < kNumSMs ? p.total_work : kNumSMs);
+  kern<<<grid, kThreads, L::kBytes, st>>>(maps, p);
+  GP_LAUNCHED();
+  return GP_OK;
+}
+
+__global__ void scale_fill_kernel(float* c, long long sCb, long long ldC, int M, int N, int batch, float beta) {
+  const long long total = (long long)batch * M * N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i % N);
+    const long long r = i / N;
+    const int m = (int)(r % M);
+    const long long bb = r / M;
+    float* q = c + bb * sCb + (long long)m * ldC + n;
+    *q = beta == 0.f ? 0.f : beta * (*q);
+  }
+}
+
+int pick_bn(int N) { return N > 128 ? 256 : (N > 64 ? 128 : 64); }
+
+int run(const gp_gemm_bf16x* g, cudaStream_t st) {
+  GP_REQUIRE(g != nullptr, "bgemm_bf16x: null descriptor");
+  GP_REQUIRE(g->npairs >= 1 && g->npairs <= kMaxPairs, "bgemm_bf16x: npairs must be 1..4");
+  GP_REQUIRE(g->C || g->Cb, "bgemm_bf16x: no output");
+  GP_REQUIRE(g->M > 0 && g->N > 0 && g->batch > 0, "bgemm_bf16x: bad dims");
+  const int split = g->split_k > 1 ? g->split_k : 1;
+  GP_REQUIRE(split == 1 || (g->C && !g->Cb && !g->bias && !g->relu), "bgemm_bf16x: split_k needs fp32 C only");
+  Maps maps;
+  Params p;
+  const int BN = pick_bn(g->N);
+  for (int q = 0; q < g->npairs; ++q) {
+    const gp_operand_pair& o = g->pair[q];
+    GP_REQUIRE(o.A && o.B && o.K > 0, "bgemm_bf16x: pair %d: null operand or K <= 0", q);
+    GP_REQUIRE(o.ldA % 8 == 0 && o.ldB % 8 == 0 && (g->batch == 1 || (o.sAb % 8 == 0 && o.sBb % 8 == 0)),
+               "bgemm_bf16x: pair %d: strides must be multiples of 8 elements (TMA 16-byte rule)", q);
+    GP_REQUIRE((reinterpret_cast<uintptr_t>(o.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(o.B) & 15) == 0,
+               "bgemm_bf16x: pair %d: operand base must be 16-byte aligned", q);
+    if (o.a_major == 0) GP_TRY(make_map(&maps.a[q], o.A, o.K, g->M, g->batch, o.ldA, o.sAb, BM));
+    else                GP_TRY(make_map(&maps.a[q], o.A, g->M, o.K, g->batch, o.ldA, o.sAb, BK));
+    if (o.b_major == 0) GP_TRY(make_map(&maps.b[q], o.B, o.K, g->N, g->batch, o.ldB, o.sBb, BN));
+    else                GP_TRY(make_map(&maps.b[q], o.B, g->N, o.K, g->batch, o.ldB, o.sBb, BK));
+    p.K[q] = o.K; p.a_mn[q] = o.a_major; p.b_mn[q] = o.b_major; p.lim_k[q] = o.lim_k;
+  }
+  for (int q = g->npairs; q < kMaxPairs; ++q) {
+    maps.a[q] = maps.a[0]; maps.b[q] = maps.b[0];
+    p.K[q] = 0; p.a_mn[q] = p.b_mn[q] = p.lim_k[q] = 0;
+  }
+  p.C = g->C; p.Cb = reinterpret_cast<__nv_bfloat16*>(g->Cb);
+  p.M = g->M; p.N = g->N; p.batch = g->batch;
+  p.ldC = g->ldC; p.sCb = g->sCb; p.ldCb = g->ldCb; p.sCbb = g->sCbb;
+  p.lim = g->lim; p.lim_m = g->lim_m; p.lim_n = g->lim_n;
+  p.alpha = g->alpha; p.beta = g->beta; p.alpha_dev = g->alpha_dev;
+  p.bias = g->bias; p.relu = g->relu; p.split_k = g->split_k; p.npairs = g->npairs;
+  p.adjb = nullptr; p.ldadj = p.sadjb = 0; p.partial = nullptr;
+  if (split > 1 && p.beta != 1.f) {
+    const long long total = (long long)g->batch * g->M * g->N;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    scale_fill_kernel<<<blocks, 256, 0, st>>>(p.C, p.sCb, p.ldC, p.M, p.N, p.batch, p.beta);
+    GP_LAUNCHED();
+    p.beta = 1.f;
+  }
+  if (BN == 256) return launch<256, 4, 0>(maps, p, st);
+  if (BN == 128) return launch<128, 6, 0>(maps, p, st);
+  return launch<64, 6, 0>(maps, p, st);
+}
+
+int run_linkloss(const void* s_bf16, long long lds, const void* adj_bf16, long long ldadj, const int32_t* nb,
+                 int B, int N, int K, float* partial, void* g_bf16, long long ldg, cudaStream_t st) {
+  GP_REQUIRE(s_bf16 && adj_bf16 && partial && B > 0 && N > 0 && K > 0, "linkloss_tc: bad args");
+  GP_REQUIRE(lds % 8 == 0 && (g_bf16 == nullptr || ldg >= N), "linkloss_tc: bad strides");
+  Maps maps;
+  Params p;
+  GP_TRY(make_map(&maps.a[0], s_bf16, K, N, B, lds, (long long)N * lds, BM));
+  GP_TRY(make_map(&maps.b[0], s_bf16, K, N, B, lds, (long long)N * lds, 256));
+  for (int q = 1; q < kMaxPairs; ++q) { maps.a[q] = maps.a[0]; maps.b[q] = maps.b[0]; p.K[q] = 0; p.a_mn[q] = p.b_mn[q] = p.lim_k[q] = 0; }
+  p.K[0] = K; p.a_mn[0] = p.b_mn[0] = 0; p.lim_k[0] = 0; p.npairs = 1;
+  p.C = nullptr; p.Cb = reinterpret_cast<__nv_bfloat16*>(g_bf16);
+  p.M = N; p.N = N; p.batch = B;
+  p.ldC = p.sCb = 0; p.ldCb = ldg; p.sCbb = (long long)N * ldg;
+  p.lim = nb; p.lim_m = p.lim_n = nb != nullptr;
+  p.alpha = 1.f; p.beta = 0.f; p.alpha_dev = nullptr; p.bias = nullptr; p.relu = 0; p.split_k = 0;
+  p.adjb = reinterpret_cast<const __nv_bfloat16*>(adj_bf16); p.ldadj = ldadj; p.sadjb = (long long)N * ldadj;
+  p.partial = partial;
+  return launch<256, 4, 1>(maps, p, st);
+}
+
+}  // namespace v2
+}  // namespace gp
+
+extern "C" int gp_bgemm_bf16x(const gp_gemm_bf16x* g, gp_stream_t stream) {
+  return gp::v2::run(g, gp::S(stream));
+}
+
+// n_partial = batch * ceil(N/128) * ceil(N/256) * 8
+extern "C" int gp_linkloss_tc(const void* s_bf16, long long lds, const void* adj_bf16, long long ldadj,
+                              const int32_t* nb, int B, int N, int K, float* partial, void* g_bf16,
+                              long long ldg, gp_stream_t stream) {
+  return gp::v2::run_linkloss(s_bf16, lds, adj_bf16, ldadj, nb, B, N, K, partial, g_bf16, ldg, gp::S(stream));
+}

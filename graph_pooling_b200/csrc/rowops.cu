@@ -10,6 +10,7 @@ namespace gp {
 
 constexpr float kEpsNorm = 1e-12f;
 constexpr float kEpsBn = 1e-5f;
+constexpr size_t kNodeCacheMax = 200 * 1024;   // per-node working set staged in shared memory (<= 227 KB/CTA)
 
 // ---------------------------------------------------------------------------------------------
 // V (+bias) -> Y = V / max(||V||, eps), in place; one warp per row.
@@ -40,9 +41,12 @@ __global__ void bias_normalize_kernel(float* __restrict__ v, const float* __rest
 // ReLU + BN over (batch, feature) per node index n.  One block per node (grid.x = N).
 // Two-pass mean / variance (the block re-reads its B*d elements from L1/L2), third pass writes.
 // ---------------------------------------------------------------------------------------------
+// CACHE: the node's B*d activations are staged once in dynamic shared memory, so HBM is read once.
+template <bool CACHE>
 __global__ void relu_bn_fwd_kernel(const float* __restrict__ y, float* __restrict__ h, long long ldh,
                                    float* __restrict__ mean, float* __restrict__ invstd,
                                    int B, int N, int d, int relu, int bn) {
+  extern __shared__ float cache[];
   __shared__ float sh[33];
   const int n = blockIdx.x;
   const int total = B * d;
@@ -53,14 +57,20 @@ __global__ void relu_bn_fwd_kernel(const float* __restrict__ y, float* __restric
       const int b = i / d, c = i - b * d;
       float x = y[((long long)b * N + n) * d + c];
       if (relu) x = fmaxf(x, 0.f);
+      if (CACHE) cache[i] = x;
       s += x;
     }
     mu = block_sum(s, sh) / (float)total;
     float q = 0.f;
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
-      const int b = i / d, c = i - b * d;
-      float x = y[((long long)b * N + n) * d + c];
-      if (relu) x = fmaxf(x, 0.f);
+      float x;
+      if (CACHE) {
+        x = cache[i];
+      } else {
+        const int b = i / d, c = i - b * d;
+        x = y[((long long)b * N + n) * d + c];
+        if (relu) x = fmaxf(x, 0.f);
+      }
       const float t = x - mu;
       q = fmaf(t, t, q);
     }
@@ -70,8 +80,13 @@ __global__ void relu_bn_fwd_kernel(const float* __restrict__ y, float* __restric
   }
   for (int i = threadIdx.x; i < total; i += blockDim.x) {
     const int b = i / d, c = i - b * d;
-    float x = y[((long long)b * N + n) * d + c];
-    if (relu) x = fmaxf(x, 0.f);
+    float x;
+    if (CACHE && bn) {
+      x = cache[i];
+    } else {
+      x = y[((long long)b * N + n) * d + c];
+      if (relu) x = fmaxf(x, 0.f);
+    }
     h[((long long)b * N + n) * ldh + c] = (x - mu) * is;
   }
 }
@@ -91,12 +106,17 @@ __device__ __forceinline__ float layer_g(const float* dz, long long lddz, const 
   return g;
 }
 
+// CACHE: pass 1 stages the combined gradient g of the node's B*d entries in dynamic shared memory, so the
+// gradient sources are read from HBM once.  MAXE > 0: a row (d <= 32*MAXE) stays in registers between the
+// <Y,dY> reduction and the final write, so h / y are read once in pass 2.
+template <bool CACHE, int MAXE>
 __global__ void gcn_layer_bwd_kernel(const float* __restrict__ dz, long long lddz, const float* __restrict__ dxn,
                                      const float* __restrict__ dout, const int32_t* __restrict__ argidx,
                                      long long ldo, const float* __restrict__ h, long long ldh,
                                      const float* __restrict__ y, long long ldy, const float* __restrict__ rnorm,
                                      const float* __restrict__ invstd, int B, int N, int d, int relu, int bn,
                                      int normalize, float* __restrict__ dv) {
+  extern __shared__ float cache[];
   __shared__ float sh[33];
   const int n = blockIdx.x;
   const int total = B * d;
@@ -106,6 +126,7 @@ __global__ void gcn_layer_bwd_kernel(const float* __restrict__ dz, long long ldd
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
       const int b = i / d, c = i - b * d;
       const float g = layer_g(dz, lddz, dxn, dout, argidx, ldo, b, n, c, N, d);
+      if (CACHE) cache[i] = g;
       s1 += g;
       s2 = fmaf(g, h[((long long)b * N + n) * ldh + c], s2);
     }
@@ -113,31 +134,60 @@ __global__ void gcn_layer_bwd_kernel(const float* __restrict__ dz, long long ldd
     m2 = block_sum(s2, sh) / (float)total;
     is = invstd[n];
   }
+  const bool cached = CACHE && bn;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
   for (int b = w; b < B; b += nw) {
     const long long row = (long long)b * N + n;
-    float dot = 0.f;
-    for (int c = lane; c < d; c += 32) {
-      float g = layer_g(dz, lddz, dxn, dout, argidx, ldo, b, n, c, N, d);
-      if (bn) g = (g - m1 - h[row * ldh + c] * m2) * is;
-      const float yy = y[row * ldy + c];
-      if (relu && !(yy > 0.f)) g = 0.f;
-      dot = fmaf(g, yy, dot);
-    }
     float r = 1.f;
     bool clamped = false;
     if (normalize) {
-      dot = warp_sum(dot);
       r = rnorm[row];
       clamped = !(r > kEpsNorm);
     }
-    for (int c = lane; c < d; c += 32) {
-      float g = layer_g(dz, lddz, dxn, dout, argidx, ldo, b, n, c, N, d);
-      if (bn) g = (g - m1 - h[row * ldh + c] * m2) * is;
-      const float yy = y[row * ldy + c];
-      if (relu && !(yy > 0.f)) g = 0.f;
-      if (normalize) g = clamped ? g / kEpsNorm : (g - yy * dot) / r;
-      dv[row * d + c] = g;
+    if (MAXE > 0) {
+      float gv[MAXE > 0 ? MAXE : 1], yv[MAXE > 0 ? MAXE : 1];
+      float dot = 0.f;
+#pragma unroll
+      for (int e = 0; e < MAXE; ++e) {
+        const int c = lane + 32 * e;
+        float g = 0.f, yy = 0.f;
+        if (c < d) {
+          g = cached ? cache[b * d + c] : layer_g(dz, lddz, dxn, dout, argidx, ldo, b, n, c, N, d);
+          if (bn) g = (g - m1 - h[row * ldh + c] * m2) * is;
+          yy = y[row * ldy + c];
+          if (relu && !(yy > 0.f)) g = 0.f;
+          dot = fmaf(g, yy, dot);
+        }
+        gv[e] = g; yv[e] = yy;
+      }
+      if (normalize) dot = warp_sum(dot);
+#pragma unroll
+      for (int e = 0; e < MAXE; ++e) {
+        const int c = lane + 32 * e;
+        if (c < d) {
+          float g = gv[e];
+          if (normalize) g = clamped ? g / kEpsNorm : (g - yv[e] * dot) / r;
+          dv[row * d + c] = g;
+        }
+      }
+    } else {
+      float dot = 0.f;
+      for (int c = lane; c < d; c += 32) {
+        float g = cached ? cache[b * d + c] : layer_g(dz, lddz, dxn, dout, argidx, ldo, b, n, c, N, d);
+        if (bn) g = (g - m1 - h[row * ldh + c] * m2) * is;
+        const float yy = y[row * ldy + c];
+        if (relu && !(yy > 0.f)) g = 0.f;
+        dot = fmaf(g, yy, dot);
+      }
+      if (normalize) dot = warp_sum(dot);
+      for (int c = lane; c < d; c += 32) {
+        float g = cached ? cache[b * d + c] : layer_g(dz, lddz, dxn, dout, argidx, ldo, b, n, c, N, d);
+        if (bn) g = (g - m1 - h[row * ldh + c] * m2) * is;
+        const float yy = y[row * ldy + c];
+        if (relu && !(yy > 0.f)) g = 0.f;
+        if (normalize) g = clamped ? g / kEpsNorm : (g - yy * dot) / r;
+        dv[row * d + c] = g;
+      }
     }
   }
 }
@@ -339,8 +389,16 @@ extern "C" int gp_relu_bn_fwd(const float* y, float* h, long long ldh, float* me
   GP_REQUIRE(y && h && B > 0 && N > 0 && d > 0 && ldh >= d, "relu_bn_fwd: bad args");
   GP_REQUIRE(!bn || (mean && invstd), "relu_bn_fwd: bn needs mean/invstd");
   const int total = B * d;
-  const int threads = total >= 4096 ? 512 : (total >= 512 ? 256 : 128);
-  relu_bn_fwd_kernel<<<N, threads, 0, S(stream)>>>(y, h, ldh, mean, invstd, B, N, d, relu, bn);
+  const size_t cache_bytes = (size_t)total * sizeof(float);
+  if (bn && cache_bytes > 16 * 1024 && cache_bytes <= kNodeCacheMax) {
+    auto kern = relu_bn_fwd_kernel<true>;
+    static bool cfgd = false;
+    if (!cfgd) { GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNodeCacheMax)); cfgd = true; }
+    kern<<<N, 1024, cache_bytes, S(stream)>>>(y, h, ldh, mean, invstd, B, N, d, relu, bn);
+  } else {
+    const int threads = total >= 4096 ? 512 : (total >= 512 ? 256 : 128);
+    relu_bn_fwd_kernel<false><<<N, threads, 0, S(stream)>>>(y, h, ldh, mean, invstd, B, N, d, relu, bn);
+  }
   GP_LAUNCHED();
   return GP_OK;
 }
@@ -355,9 +413,27 @@ extern "C" int gp_gcn_layer_bwd(const float* dz, long long lddz, const float* dx
   GP_REQUIRE(!normalize || rnorm, "gcn_layer_bwd: normalize needs rnorm");
   GP_REQUIRE(!dout || argidx, "gcn_layer_bwd: dout needs argidx");
   const int total = B * d;
-  const int threads = total >= 4096 ? 512 : (total >= 512 ? 256 : 128);
-  gcn_layer_bwd_kernel<<<N, threads, 0, S(stream)>>>(dz, lddz, dxn, dout, argidx, ldo, h, ldh, y, ldy, rnorm,
-                                                      invstd, B, N, d, relu, bn, normalize, dv);
+  const size_t cache_bytes = (size_t)total * sizeof(float);
+  const bool use_cache = bn && cache_bytes > 16 * 1024 && cache_bytes <= kNodeCacheMax;
+  // 512 threads: the MAXE=16 variant needs 80 registers/thread (1024 threads would exceed the register file)
+  const int threads = use_cache ? 512 : (total >= 4096 ? 512 : (total >= 512 ? 256 : 128));
+  const int maxe = d <= 128 ? 4 : (d <= 512 ? 16 : 0);
+#define GP_LAUNCH_LBWD(C_, E_)                                                                              \
+  do {                                                                                                     \
+    auto kern = gcn_layer_bwd_kernel<C_, E_>;                                                              \
+    if (C_) {                                                                                              \
+      static bool cfgd = false;                                                                            \
+      if (!cfgd) { GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNodeCacheMax)); cfgd = true; } \
+    }                                                                                                      \
+    kern<<<N, threads, C_ ? cache_bytes : 0, S(stream)>>>(dz, lddz, dxn, dout, argidx, ldo, h, ldh, y, ldy, \
+                                                          rnorm, invstd, B, N, d, relu, bn, normalize, dv); \
+  } while (0)
+  if (use_cache) {
+    if (maxe == 4) GP_LAUNCH_LBWD(true, 4); else if (maxe == 16) GP_LAUNCH_LBWD(true, 16); else GP_LAUNCH_LBWD(true, 0);
+  } else {
+    if (maxe == 4) GP_LAUNCH_LBWD(false, 4); else if (maxe == 16) GP_LAUNCH_LBWD(false, 16); else GP_LAUNCH_LBWD(false, 0);
+  }
+#undef GP_LAUNCH_LBWD
   GP_LAUNCHED();
   return GP_OK;
 }

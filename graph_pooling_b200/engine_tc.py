@@ -7,11 +7,12 @@ products read their operands in natural row-major layout (K-major / MN-major UMM
 so nothing is ever transposed in HBM.  Same reference semantics as engine.py.
 """
 import ctypes as C
+import os
 
 import torch
 
 from . import engine as E
-from ._lib import GpGemmBf16, call
+from ._lib import GpGemmBf16, GpGemmBf16x, call
 
 BF16 = 1
 KM, MN = 0, 1        # operand major-ness (see include/gp_b200.h)
@@ -43,9 +44,38 @@ def cvt(ws, x_ptr, ldx, rows, cols, B=1, out=None):
     return out
 
 
+_USE_V1 = bool(os.environ.get('GP_TC_V1'))     # debug: single-tile-per-CTA kernel of gemm_tc.cu
+
+
+def tcgemm_multi(pairs, M, N, batch, Cf=None, Cb=None, lim=None, lim_m=0, lim_n=0, alpha=1.0, beta=0.0,
+                 alpha_dev=None, bias=None, relu=0, split_k=0):
+    """One persistent tcgen05 launch accumulating sum_q A_q.B_q (gp_bgemm_bf16x).
+    pairs: [(A Op, a_major, B Op, b_major, K, lim_k)]; Cf = (ptr, ld, sb) fp32 out, Cb = Op bf16 out."""
+    g = GpGemmBf16x()
+    g.npairs = len(pairs)
+    for q, (A, am, Bo, bm, K, lk) in enumerate(pairs):
+        pr = g.pair[q]
+        pr.A, pr.B, pr.K = A.ptr, Bo.ptr, K
+        pr.ldA, pr.sAb, pr.a_major = A.ld, A.sb, am
+        pr.ldB, pr.sBb, pr.b_major = Bo.ld, Bo.sb, bm
+        pr.lim_k = lk
+    cp, cld, csb = Cf if Cf is not None else (None, 0, 0)
+    g.C, g.Cb = cp, (None if Cb is None else Cb.ptr)
+    g.M, g.N, g.batch = M, N, batch
+    g.ldC, g.sCb = cld, csb
+    g.ldCb, g.sCbb = (0, 0) if Cb is None else (Cb.ld, Cb.sb)
+    g.lim, g.lim_m, g.lim_n = lim, lim_m, lim_n
+    g.alpha, g.beta, g.alpha_dev = alpha, beta, alpha_dev
+    g.bias, g.relu, g.split_k = bias, relu, split_k
+    call('gp_bgemm_bf16x', C.byref(g), E._stream())
+
+
 def tcgemm(A, a_major, Bo, b_major, M, N, K, batch, Cf=None, Cb=None, lim=None, lim_m=0, lim_n=0, lim_k=0,
            alpha=1.0, beta=0.0, alpha_dev=None, bias=None, relu=0, split_k=0):
-    """Cf = (ptr, ld, sb) fp32 output, Cb = Op bf16 output; see gp_bgemm_bf16."""
+    """Single product on tensor cores.  Cf = (ptr, ld, sb) fp32 output, Cb = Op bf16 output."""
+    if not _USE_V1:
+        return tcgemm_multi([(A, a_major, Bo, b_major, K, lim_k)], M, N, batch, Cf, Cb, lim, lim_m, lim_n, alpha,
+                            beta, alpha_dev, bias, relu, split_k)
     cp, cld, csb = Cf if Cf is not None else (None, 0, 0)
     g = GpGemmBf16(A.ptr, Bo.ptr, cp, None if Cb is None else Cb.ptr, M, N, K, batch,
                    A.ld, A.sb, a_major, Bo.ld, Bo.sb, b_major, cld, csb,
@@ -188,11 +218,11 @@ def pool_backward(ws, dxp, dap, sb, zb, adjb, tb, nb, B, N, K, Fw, ds, acc_ds, d
     dz = ws.f(B, N, Fw)
     tcgemm(sb, KM, dxpb, MN, N, Fw, K, B, Cf=(dz.data_ptr(), Fw, N * Fw), lim=nbp, lim_m=lim)
     dsf = (ds.data_ptr(), K, N * K)
-    tcgemm(zb, KM, dxpb, KM, N, K, Fw, B, Cf=dsf, beta=1.0 if acc_ds else 0.0, lim=nbp, lim_m=lim)
-    tcgemm(tb, MN, dapb, MN, N, K, K, B, Cf=dsf, beta=1.0, lim=nbp, lim_m=lim)
     wsb = bfbuf(ws, B, N, K)
     tcgemm(sb, KM, dapb, KM, N, K, K, B, Cb=wsb, lim=nbp, lim_m=lim)
-    tcgemm(adjb, KM, wsb, MN, N, K, N, B, Cf=dsf, beta=1.0, lim=nbp, lim_m=lim, lim_k=lim)
+    # dS (+)= Z dX'^T + T^T dA' + A (S dA'^T): three products accumulated in TMEM, one pass over dS
+    tcgemm_multi([(zb, KM, dxpb, KM, Fw, 0), (tb, MN, dapb, MN, K, 0), (adjb, KM, wsb, MN, N, lim)], N, K, B,
+                 Cf=dsf, beta=1.0 if acc_ds else 0.0, lim=nbp, lim_m=lim)
     if dadj is not None:
         w2b = bfbuf(ws, B, N, K)
         tcgemm(sb, KM, dapb, MN, N, K, K, B, Cb=w2b)
@@ -229,7 +259,7 @@ def linkloss_forward(ws, sb, adjb, nb, B, N, K, need_grad):
     """Fused tensor-core link loss: P = S S^T tiles stay in TMEM, the epilogue does the masked BCE
     against the bf16 adjacency and writes gsym (bf16).  Returns (partial, n_partial, gsym op)."""
     nbp = E._p(nb)
-    npart = B * ((N + 127) // 128) * ((N + 255) // 256) * 4
+    npart = B * ((N + 127) // 128) * ((N + 255) // 256) * 8
     partial = ws.f(npart + 256)                      # +256: scratch of the two-stage finalisation
     gs = bfbuf(ws, B, N, N) if need_grad else None
     call('gp_linkloss_tc', sb.ptr, sb.ld, adjb.ptr, adjb.ld, nbp, B, N, K, partial.data_ptr(),
@@ -240,6 +270,8 @@ def linkloss_forward(ws, sb, adjb, nb, B, N, K, need_grad):
 def linkloss_backward(ws, gs, sb, nb, B, N, K, inv, g_ptr):
     nbp, lim = E._p(nb), int(nb is not None)
     dS = ws.f(B, N, K)
-    tcgemm(gs, KM, sb, MN, N, K, N, B, Cf=(dS.data_ptr(), K, N * K), alpha=inv, alpha_dev=g_ptr, lim=nbp, lim_m=lim,
-           lim_k=lim)
+    # dS = (G + G^T).S : G K-major, then the same buffer read M-major (= G^T), accumulated
+    cf = (dS.data_ptr(), K, N * K)
+    tcgemm_multi([(gs, KM, sb, MN, N, lim), (gs, MN, sb, MN, N, lim)], N, K, B, Cf=cf, alpha=inv, alpha_dev=g_ptr,
+                 lim=nbp, lim_m=lim)
     return dS

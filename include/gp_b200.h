@@ -101,6 +101,33 @@ typedef struct gp_gemm_bf16 {
   int split_k;
 } gp_gemm_bf16;
 int gp_bgemm_bf16(const gp_gemm_bf16* g, gp_stream_t stream);
+
+/* Persistent multi-pair form (the one the engine uses):
+ *   C[b] = alpha * sum_{q < npairs} op(A_q[b]) . op(B_q[b]) (+bias)(relu) + beta * C[b]
+ * One launch accumulates up to 4 different products into the same TMEM accumulator tile, e.g. the
+ * pooling backward dS = Z dX'^T + T^T dA' + A (S dA'^T) (encoders.py:1278-1279) or the link-loss
+ * backward dS = G S + G^T S, instead of read-modify-write chains over [B,N,K] buffers.  CTAs are
+ * persistent (one per SM), the accumulator is double-buffered in TMEM so one tile's epilogue overlaps
+ * the next tile's MMAs, and the epilogue stores are staged through shared memory (coalesced).
+ * Same operand rules as gp_gemm_bf16; lim_k is per pair. */
+typedef struct gp_operand_pair {
+  const void* A; const void* B;          /* bf16 */
+  int K;
+  long long ldA, sAb; int a_major;
+  long long ldB, sBb; int b_major;
+  int lim_k;
+} gp_operand_pair;
+typedef struct gp_gemm_bf16x {
+  gp_operand_pair pair[4]; int npairs;
+  float* C; void* Cb;
+  int M, N, batch;
+  long long ldC, sCb, ldCb, sCbb;
+  const int32_t* lim; int lim_m, lim_n;
+  float alpha, beta; const float* alpha_dev;
+  const float* bias; int relu;
+  int split_k;
+} gp_gemm_bf16x;
+int gp_bgemm_bf16x(const gp_gemm_bf16x* g, gp_stream_t stream);
 /* y[r, 0:cols_pad] = bf16(x[r, 0:cols]) zero-padded to cols_pad (row strides ldx / ldy in elements) */
 int gp_cvt_f32_bf16(const float* x, long long ldx, void* y, long long ldy, long long rows, int cols,
                     int cols_pad, gp_stream_t stream);
@@ -192,8 +219,9 @@ int gp_loss_finalize(const float* partial, int n_partial, double inv_entries, co
  * reduction (n_partial = B * ceil(N/32)^2) and writes gsym as the bf16 operand (row stride ldg) of
  * the backward GEMM, zero-filled up to the next multiple of 64 beyond nb[b]. */
 /* Fused tensor-core form: S (bf16, row stride lds) -> P = S S^T tiles in TMEM -> masked BCE against
- * the bf16 adjacency in the epilogue; gsym (bf16, row stride ldg, may be NULL) and one partial per
- * epilogue warp: n_partial = B * ceil(N/128) * ceil(N/256) * 4.  P never touches HBM.
+ * the bf16 adjacency in the epilogue; G = dl/dP evaluated with a[m,n] (bf16, row stride ldg, may be
+ * NULL; the backward is dS = (G + G^T) S = two operand pairs of gp_bgemm_bf16x) and one partial per
+ * epilogue warp: n_partial = B * ceil(N/128) * ceil(N/256) * 8.  P never touches HBM.
  * gp_loss_finalize with n_partial > 8192 uses 256 floats of scratch AFTER the partial array. */
 int gp_linkloss_tc(const void* s_bf16, long long lds, const void* adj_bf16, long long ldadj,
                    const int32_t* nb, int B, int N, int K, float* partial, void* gsym_bf16, long long ldg,
