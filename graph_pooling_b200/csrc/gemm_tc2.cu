@@ -311,7 +311,7 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
           for (int j = 0; j < 32; ++j) v[j] = 0u;
         }
         if (row0 >= p.M || nbase >= p.N) continue;       // warp-uniform
-        if (EPI == 0 && !has_acc && p.beta == 1.f && p.bias == nullptr) continue;   // nothing to add
+        if (EPI == 0 && !has_acc && p.beta == 1.f && p.bias == nullptr && p.Cb == nullptr) continue;   // nothing to add
         // registers (lane = row) -> staging (transposed access, bank = (lane + j) % 32: conflict-free)
 #pragma unroll
         for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(v[j]);
