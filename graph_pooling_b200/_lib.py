@@ -76,6 +76,7 @@ _PROTOS = {
     'gp_linkloss_fwd': [c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f, c_f],
     'gp_loss_finalize': [c_f, c_i, C.c_double, c_f, c_f, c_f, c_f],
     'gp_linkloss_tc': [c_f, c_ll, c_f, c_ll, c_f, c_i, c_i, c_i, c_f, c_f, c_ll, c_f],
+    'gp_linkloss_tc_partials': [c_i, c_i],
     'gp_linkloss_from_p': [c_f, c_f, c_f, c_i, c_i, c_ll, c_f, c_f, c_f],
     'gp_ce_fwd': [c_f, c_f, c_i, c_i, c_f, c_f, c_f],
     'gp_ce_bwd': [c_f, c_f, c_f, c_i, c_i, c_f, c_f],

@@ -25,8 +25,10 @@ namespace v2 {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kMaxPairs = 4;
-constexpr int kEpiWarps = 8;
-constexpr int kThreads = (kEpiWarps + 2) * 32;
+constexpr int kLinkEW = 16;      // epilogue warps of the fused link-loss kernel (MUFU / latency bound)
+// Epilogue staging tile: 32 rows x 32 floats per warp, float4 slots XOR-swizzled by (row & 7): the lane=row
+// float4 writes and both coalesced read layouts (4 or 8 consecutive columns per lane) are bank-conflict-free.
+__device__ __forceinline__ int stg_off(int r, int c) { return r * 32 + ((((c >> 2) ^ r) & 7) << 2) + (c & 3); }
 constexpr float kEpsLink = 1e-7f;
 
 struct Maps { CUtensorMap a[kMaxPairs]; CUtensorMap b[kMaxPairs]; };
@@ -116,12 +118,12 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EW>
 struct Smem {
   static constexpr int kA = BM * BK * 2;
   static constexpr int kB = BN * BK * 2;
   static constexpr int kStage = kA + kB;
-  static constexpr int kStaging = kEpiWarps * 32 * 33 * 4;
+  static constexpr int kStaging = EW * 32 * 32 * 4;
   static constexpr int kBytes = STAGES * kStage + kStaging + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -165,12 +167,62 @@ __device__ __forceinline__ void finish_work(const Params& p, Work& k) {
   k.kt1 = min(tot, k.kt0 + per);
 }
 
+// ---- epilogue helpers --------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+}
+
+// Masked BCE (encoders.py:1321) of 8 consecutive columns of one row.  pv: P values, aw: 8 bf16 adjacency
+// entries, nvalid: number of leading columns inside the n_b x n_b block.  Accumulates the loss in LOG2 units
+// into *l2 (the caller multiplies the sum by -ln 2) and returns G = dl/dP packed as 8 bf16.
+//   FAST (adjacency in {0,1}):  x = a ? P + eps : 1 - P + eps ;  loss = -ln x ;  G = a ? -1/x : 1/x
+//   general:                    loss = -a ln(P+eps) - (1-a) ln(1-P+eps) ;  G = -a/(P+eps) + (1-a)/(1-P+eps)
+// P is clamped to <= 1 first (R3: min(P, 1), encoders.py:1317) and G = 0 where the clamp is active.
+template <bool FAST, bool FULL>
+__device__ __forceinline__ uint4 bce_row8(const float (&pv)[8], const uint4 aw, int nvalid, float* l2) {
+  const uint32_t wsrc[4] = {aw.x, aw.y, aw.z, aw.w};
+  float g[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const uint32_t bits = (e & 1) ? (wsrc[e >> 1] & 0xffff0000u) : (wsrc[e >> 1] << 16);
+    const float pc = fminf(pv[e], 1.f);
+    float gg, ll;
+    if (FAST) {
+      const bool one = bits != 0u;
+      const float x = fmaf(one ? 1.f : -1.f, pc, one ? kEpsLink : 1.f + kEpsLink);
+      ll = lg2_approx(x);
+      gg = rcp_approx(x) * (one ? -1.f : 1.f);
+    } else {
+      const float a1 = __uint_as_float(bits);
+      const float pe = pc + kEpsLink, qe = 1.f - pc + kEpsLink;
+      ll = a1 * lg2_approx(pe) + (1.f - a1) * lg2_approx(qe);
+      gg = (1.f - a1) * rcp_approx(qe) - a1 * rcp_approx(pe);
+    }
+    if (pv[e] > 1.f) gg = 0.f;
+    if (!FULL && e >= nvalid) { gg = 0.f; ll = 0.f; }
+    *l2 += ll;
+    g[e] = gg;
+  }
+  return make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]), pack_bf16x2(g[6], g[7]));
+}
+
 // ---- kernel -------------------------------------------------------------------------------------
-template <int BN, int STAGES, int EPI>
-__global__ void __launch_bounds__(kThreads, 1)
+// EW epilogue warps (8 or 16): warps 0..EW-1 epilogue, EW = TMA producer, EW+1 = MMA issuer.
+template <int BN, int STAGES, int EPI, int EW>
+__global__ void __launch_bounds__((EW + 2) * 32, 1)
 tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
   extern __shared__ uint8_t smem_raw[];
-  using L = Smem<BN, STAGES>;
+  using L = Smem<BN, STAGES, EW>;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));
   float* staging = reinterpret_cast<float*>(smem_gen + STAGES * L::kStage);
@@ -185,18 +237,19 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;          // BN in {64,128,256} -> 128/256/512
+  constexpr int kProd = EW, kMma = EW + 1;
 
-  if (warp == 9) {
+  if (warp == kMma) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-      for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kEpiWarps); }
+      for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EW); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
   }
-  if (warp == 8 && lane == 0) {
+  if (warp == kProd && lane == 0) {
     for (int q = 0; q < p.npairs; ++q) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.a[q])) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.b[q])) : "memory");
@@ -207,7 +260,7 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
-  if (warp == 8) {
+  if (warp == kProd) {
     // ===== TMA producer =====
     if (lane == 0) {
       uint32_t it = 0;                                   // running stage counter across tiles
@@ -241,7 +294,7 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == kMma) {
     // ===== MMA issuer =====
     if (lane == 0) {
       uint32_t it = 0, nacc = 0;
@@ -281,12 +334,23 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
       }
     }
   } else {
-    // ===== epilogue warps 0..7 =====
-    const int quarter = warp & 3, half = warp >> 2;
-    float* stg = staging + warp * (32 * 33);
+    // ===== epilogue warps 0..EW-1 =====
+    // warp -> TMEM lane quarter (hardware rule: warp w may touch lanes 32*(w%4)..+31) and a column group.
+    constexpr int CPW = BN / (EW / 4);                   // columns per warp
+    static_assert(CPW % 32 == 0, "each epilogue warp needs whole 32-column chunks");
+    const int quarter = warp & 3, cgrp = warp >> 2;
+    float* stg = staging + warp * (32 * 32);
     float alpha = p.alpha;
     if (p.alpha_dev != nullptr) alpha *= *p.alpha_dev;
     const int split = p.split_k > 1 ? p.split_k : 1;
+    const float beta = p.beta;
+    // vector-path eligibility (uniform over the kernel)
+    const bool vecC = p.C != nullptr && split == 1 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 &&
+                      (p.ldC & 3) == 0 && (p.sCb & 3) == 0;
+    const bool vecCb4 = p.Cb != nullptr && (reinterpret_cast<uintptr_t>(p.Cb) & 7) == 0 && (p.ldCb & 3) == 0 &&
+                        (p.sCbb & 3) == 0;
+    const bool vecCb8 = p.Cb != nullptr && (reinterpret_cast<uintptr_t>(p.Cb) & 15) == 0 && (p.ldCb & 7) == 0 &&
+                        (p.sCbb & 7) == 0;
     uint32_t nacc = 0;
     for (long long w = blockIdx.x; w < p.total_work; w += gridDim.x) {
       Work k = get_work(p, w);
@@ -300,8 +364,8 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
       const int row0 = k.m0 + quarter * 32;
       float lsum = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < BN / 64; ++c) {
-        const int col = half * (BN / 2) + c * 32;
+      for (int c = 0; c < CPW / 32; ++c) {
+        const int col = cgrp * CPW + c * 32;
         const int nbase = k.n0 + col;
         uint32_t v[32];
         if (has_acc) {
@@ -311,73 +375,173 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
           for (int j = 0; j < 32; ++j) v[j] = 0u;
         }
         if (row0 >= p.M || nbase >= p.N) continue;       // warp-uniform
-        if (EPI == 0 && !has_acc && p.beta == 1.f && p.bias == nullptr && p.Cb == nullptr) continue;   // nothing to add
-        // registers (lane = row) -> staging (transposed access, bank = (lane + j) % 32: conflict-free)
+        if (EPI == 1 && !has_acc) continue;
+        if (EPI == 0 && !has_acc && beta == 1.f && p.bias == nullptr && p.Cb == nullptr) continue;   // nothing to add
+        // registers (lane = row) -> staging tile [32 rows][32], swizzled; float4 stores, conflict-free
 #pragma unroll
-        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(v[j]);
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<uint4*>(&stg[stg_off(lane, 4 * q)]) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         __syncwarp();
-        const int n = nbase + lane;                      // lane = column from here on
-        const bool n_ok = n < p.N, n_in = n < k.Ne;
         if (EPI == 1) {
-          if (has_acc) {
-            const __nv_bfloat16* ab = p.adjb + (long long)k.b * p.sadjb;
-            __nv_bfloat16* gb = p.Cb != nullptr ? p.Cb + (long long)k.b * p.sCbb : nullptr;
-            // adjacency entries of this lane's column for the 32 rows (coalesced 64 B per row)
-            float av[32];
-            bool is01 = true;
+          // ---- fused link-prediction loss: 8 consecutive columns x 4 rows per lane, 16-byte accesses ----
+          const __nv_bfloat16* ab = p.adjb + (long long)k.b * p.sadjb;
+          __nv_bfloat16* gb = p.Cb != nullptr ? p.Cb + (long long)k.b * p.sCbb : nullptr;
+          const int cc = (lane & 3) * 8, n = nbase + cc;
+          const bool vecA = (reinterpret_cast<uintptr_t>(p.adjb) & 15) == 0 && (p.ldadj & 7) == 0 && (p.sadjb & 7) == 0;
+          // warp-uniform: the whole 32x32 chunk lies inside the n_b x n_b block and vector accesses are legal
+          const bool interior = vecA && (gb == nullptr || vecCb8) && row0 + 32 <= k.Me && nbase + 32 <= k.Ne;
+          uint4 aw[4];
+          if (interior) {
 #pragma unroll
-            for (int r = 0; r < 32; ++r) {
-              const int row = row0 + r;
-              float x = 0.f;
-              if (row < k.Me && n_in) x = __bfloat162float(ab[(long long)row * p.ldadj + n]);
-              av[r] = x;
-              is01 = is01 && (x == 0.f || x == 1.f);
-            }
-            const bool fast = __all_sync(0xffffffffu, is01);
-#pragma unroll
-            for (int r = 0; r < 32; ++r) {
-              const int row = row0 + r;
-              float gg = 0.f;
-              if (row < k.Me && n_in) {
-                float pv = stg[r * 33 + lane];
-                const bool over = pv > 1.f;
-                if (over) pv = 1.f;
-                const float pe = pv + kEpsLink, qe = 1.f - pv + kEpsLink;
-                const float a1 = av[r];
-                if (fast) {                              // a in {0,1}: one log, one reciprocal
-                  const float x = a1 != 0.f ? pe : qe;
-                  lsum -= __logf(x);
-                  gg = over ? 0.f : (a1 != 0.f ? -__fdividef(1.f, x) : __fdividef(1.f, x));
-                } else {
-                  lsum -= a1 * __logf(pe) + (1.f - a1) * __logf(qe);
-                  gg = over ? 0.f : (-a1 * __fdividef(1.f, pe) + (1.f - a1) * __fdividef(1.f, qe));
-                }
+            for (int i = 0; i < 4; ++i)
+              aw[i] = *reinterpret_cast<const uint4*>(ab + (long long)(row0 + 8 * i + (lane >> 2)) * p.ldadj + n);
+          } else {
+#pragma unroll 1
+            for (int i = 0; i < 4; ++i) {
+              const int row = row0 + 8 * i + (lane >> 2);
+              uint32_t t[4] = {0u, 0u, 0u, 0u};
+              if (row < k.Me) {
+                const __nv_bfloat16* src = ab + (long long)row * p.ldadj + n;
+                for (int e = 0; e < 8; ++e)
+                  if (n + e < k.Ne) t[e >> 1] |= (uint32_t)(*reinterpret_cast<const uint16_t*>(src + e)) << (16 * (e & 1));
               }
-              if (gb != nullptr && row < p.M && n_ok) gb[(long long)row * p.ldCb + n] = __float2bfloat16_rn(gg);
+              aw[i] = make_uint4(t[0], t[1], t[2], t[3]);
             }
           }
+          bool is01 = true;                              // bf16 0.0 = 0x0000, 1.0 = 0x3f80
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t t[4] = {aw[i].x, aw[i].y, aw[i].z, aw[i].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const uint32_t z = t[e] & ~0x3f803f80u;    // any bit outside the 1.0 pattern -> not {0,1}
+              const uint32_t lo = t[e] & 0xffffu, hi = t[e] >> 16;
+              is01 = is01 && z == 0u && (lo == 0u || lo == 0x3f80u) && (hi == 0u || hi == 0x3f80u);
+            }
+          }
+          const bool fast = __all_sync(0xffffffffu, is01);
+          float l2 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = 8 * i + (lane >> 2), row = row0 + r;
+            const float4 p0 = *reinterpret_cast<const float4*>(&stg[stg_off(r, cc)]);
+            const float4 p1 = *reinterpret_cast<const float4*>(&stg[stg_off(r, cc + 4)]);
+            const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+            if (interior) {
+              const uint4 gw = fast ? bce_row8<true, true>(pv, aw[i], 8, &l2) : bce_row8<false, true>(pv, aw[i], 8, &l2);
+              if (gb != nullptr) *reinterpret_cast<uint4*>(gb + (long long)row * p.ldCb + n) = gw;
+            } else {
+              const int nvalid = row < k.Me ? min(8, max(0, k.Ne - n)) : 0;
+              const uint4 gw = bce_row8<false, false>(pv, aw[i], nvalid, &l2);
+              if (gb != nullptr && row < p.M) {
+                __nv_bfloat16* dst = gb + (long long)row * p.ldCb + n;
+                if (vecCb8 && n + 8 <= p.ldCb) {
+                  *reinterpret_cast<uint4*>(dst) = gw;
+                } else {
+                  const uint32_t t[4] = {gw.x, gw.y, gw.z, gw.w};
+                  for (int e = 0; e < 8; ++e)
+                    if (n + e < p.N) *reinterpret_cast<uint16_t*>(dst + e) = (uint16_t)(t[e >> 1] >> (16 * (e & 1)));
+                }
+              }
+            }
+          }
+          lsum = fmaf(l2, -0.69314718055994531f, lsum);
         } else {
           float* cb = p.C != nullptr ? p.C + (long long)k.b * p.sCb : nullptr;
           __nv_bfloat16* cbb = p.Cb != nullptr ? p.Cb + (long long)k.b * p.sCbb : nullptr;
-          const float bias = (p.bias != nullptr && n_ok) ? p.bias[n] : 0.f;
-          if (n_ok) {
+          const bool full = nbase + 32 <= p.N;           // warp-uniform
+          const bool inter = row0 + 32 <= k.Me && nbase + 32 <= k.Ne;   // warp-uniform: no clipping in this chunk
+          if (cb != nullptr && vecC && full && (cbb == nullptr || vecCb4)) {
+            // ---- fp32 (+ optional bf16 copy): 4 consecutive columns x 8 rows per lane, 512 B per store instruction ----
+            const int cc = (lane & 7) * 4, n = nbase + cc;
+            float bs[4] = {0.f, 0.f, 0.f, 0.f};
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) bs[e] = __ldg(p.bias + n + e);
+            }
+            float4 old[8];
+            if (beta != 0.f) {                           // all read-modify-write loads in flight before any store
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int row = row0 + 4 * i + (lane >> 3);
+                old[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row < p.M) old[i] = *reinterpret_cast<const float4*>(cb + (long long)row * p.ldC + n);
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = 4 * i + (lane >> 3), row = row0 + r;
+              if (row >= p.M) continue;
+              const float4 acc = *reinterpret_cast<const float4*>(&stg[stg_off(r, cc)]);
+              float x[4] = {acc.x, acc.y, acc.z, acc.w};
+              const float o[4] = {old[i].x, old[i].y, old[i].z, old[i].w};
+              if (!inter) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (!(row < k.Me && n + e < k.Ne)) x[e] = 0.f;
+              }
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                x[e] = fmaf(alpha, x[e], bs[e]);
+                if (p.relu) x[e] = fmaxf(x[e], 0.f);
+                if (beta != 0.f) x[e] = fmaf(beta, o[e], x[e]);
+              }
+              *reinterpret_cast<float4*>(cb + (long long)row * p.ldC + n) = make_float4(x[0], x[1], x[2], x[3]);
+              if (cbb != nullptr)
+                *reinterpret_cast<uint2*>(cbb + (long long)row * p.ldCb + n) =
+                    make_uint2(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]));
+            }
+          } else if (cb == nullptr && vecCb8 && full) {
+            // ---- bf16 only: 8 consecutive columns x 4 rows per lane ----
+            const int cc = (lane & 3) * 8, n = nbase + cc;
+            float bs[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) bs[e] = p.bias != nullptr ? __ldg(p.bias + n + e) : 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = 8 * i + (lane >> 2), row = row0 + r;
+              if (row >= p.M) continue;
+              const float4 a0 = *reinterpret_cast<const float4*>(&stg[stg_off(r, cc)]);
+              const float4 a1 = *reinterpret_cast<const float4*>(&stg[stg_off(r, cc + 4)]);
+              float x[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+              if (!inter) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                  if (!(row < k.Me && n + e < k.Ne)) x[e] = 0.f;
+              }
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                x[e] = fmaf(alpha, x[e], bs[e]);
+                if (p.relu) x[e] = fmaxf(x[e], 0.f);
+              }
+              *reinterpret_cast<uint4*>(cbb + (long long)row * p.ldCb + n) =
+                  make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
+                             pack_bf16x2(x[6], x[7]));
+            }
+          } else {
+            // ---- generic scalar path (unaligned / ragged edge / split-K atomics): lane = column ----
+            const int n = nbase + lane;
+            const bool n_ok = n < p.N, n_in = n < k.Ne;
+            const float bias = (p.bias != nullptr && n_ok) ? p.bias[n] : 0.f;
+            if (n_ok) {
 #pragma unroll 4
-            for (int r = 0; r < 32; ++r) {
-              const int row = row0 + r;
-              if (row >= p.M) break;
-              float x = (row < k.Me && n_in) ? alpha * stg[r * 33 + lane] : 0.f;
-              if (split > 1) {
-                if (x != 0.f) atomicAdd(cb + (long long)row * p.ldC + n, x);
-                continue;
+              for (int r = 0; r < 32; ++r) {
+                const int row = row0 + r;
+                if (row >= p.M) break;
+                float x = (row < k.Me && n_in) ? alpha * stg[stg_off(r, lane)] : 0.f;
+                if (split > 1) {
+                  if (x != 0.f) atomicAdd(cb + (long long)row * p.ldC + n, x);
+                  continue;
+                }
+                x += bias;
+                if (p.relu) x = fmaxf(x, 0.f);
+                if (cb != nullptr) {
+                  float* dst = cb + (long long)row * p.ldC + n;
+                  if (beta != 0.f) x += beta * (*dst);
+                  *dst = x;
+                }
+                if (cbb != nullptr) cbb[(long long)row * p.ldCb + n] = __float2bfloat16_rn(x);
               }
-              x += bias;
-              if (p.relu) x = fmaxf(x, 0.f);
-              if (cb != nullptr) {
-                float* dst = cb + (long long)row * p.ldC + n;
-                if (p.beta != 0.f) x += p.beta * (*dst);
-                *dst = x;
-              }
-              if (cbb != nullptr) cbb[(long long)row * p.ldCb + n] = __float2bfloat16_rn(x);
             }
           }
         }
@@ -385,7 +549,7 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
       }
       if (EPI == 1) {
         lsum = warp_sum(lsum);
-        if (lane == 0) p.partial[w * kEpiWarps + warp] = lsum;
+        if (lane == 0) p.partial[w * EW + warp] = lsum;
       }
       if (has_acc) {
         tc_fence_before();
@@ -398,7 +562,7 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == kMma) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
@@ -438,10 +602,10 @@ static int make_map(CUtensorMap* tm, const void* ptr, long long cols, long long 
   return GP_OK;
 }
 
-template <int BN, int STAGES, int EPI>
+template <int BN, int STAGES, int EPI, int EW>
 static int launch(const Maps& maps, Params& p, cudaStream_t st) {
-  using L = Smem<BN, STAGES>;
-  auto kern = tc_gemm2_kernel<BN, STAGES, EPI>;
+  using L = Smem<BN, STAGES, EW>;
+  auto kern = tc_gemm2_kernel<BN, STAGES, EPI, EW>;
   static bool configured = false;
   if (!configured) {
     GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes));
@@ -452,7 +616,7 @@ static int launch(const Maps& maps, Params& p, cudaStream_t st) {
   p.tiles_n = (p.N + BN - 1) / BN;
   p.total_work = (long long)p.tiles_m * p.tiles_n * p.batch * split;
   const int grid = (int)(p.total_work < kNumSMs ? p.total_work : kNumSMs);
-  kern<<<grid, kThreads, L::kBytes, st>>>(maps, p);
+  kern<<<grid, (EW + 2) * 32, L::kBytes, st>>>(maps, p);
   GP_LAUNCHED();
   return GP_OK;
 }
@@ -514,9 +678,9 @@ int run(const gp_gemm_bf16x* g, cudaStream_t st) {
     GP_LAUNCHED();
     p.beta = 1.f;
   }
-  if (BN == 256) return launch<256, 4, 0>(maps, p, st);
-  if (BN == 128) return launch<128, 6, 0>(maps, p, st);
-  return launch<64, 6, 0>(maps, p, st);
+  if (BN == 256) return launch<256, 4, 0, 8>(maps, p, st);
+  if (BN == 128) return launch<128, 6, 0, 8>(maps, p, st);
+  return launch<64, 6, 0, 8>(maps, p, st);
 }
 
 int run_linkloss(const void* s_bf16, long long lds, const void* adj_bf16, long long ldadj, const int32_t* nb,
@@ -536,7 +700,7 @@ int run_linkloss(const void* s_bf16, long long lds, const void* adj_bf16, long l
   p.alpha = 1.f; p.beta = 0.f; p.alpha_dev = nullptr; p.bias = nullptr; p.relu = 0; p.split_k = 0;
   p.adjb = reinterpret_cast<const __nv_bfloat16*>(adj_bf16); p.ldadj = ldadj; p.sadjb = (long long)N * ldadj;
   p.partial = partial;
-  return launch<256, 4, 1>(maps, p, st);
+  return launch<256, 3, 1, kLinkEW>(maps, p, st);
 }
 
 }  // namespace v2
@@ -546,7 +710,10 @@ extern "C" int gp_bgemm_bf16x(const gp_gemm_bf16x* g, gp_stream_t stream) {
   return gp::v2::run(g, gp::S(stream));
 }
 
-// n_partial = batch * ceil(N/128) * ceil(N/256) * 8
+// n_partial = batch * ceil(N/128) * ceil(N/256) * (epilogue warps)
+extern "C" int gp_linkloss_tc_partials(int B, int N) {
+  return B * ((N + 127) / 128) * ((N + 255) / 256) * gp::v2::kLinkEW;
+}
 extern "C" int gp_linkloss_tc(const void* s_bf16, long long lds, const void* adj_bf16, long long ldadj,
                               const int32_t* nb, int B, int N, int K, float* partial, void* g_bf16,
                               long long ldg, gp_stream_t stream) {

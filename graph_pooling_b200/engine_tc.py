@@ -12,7 +12,7 @@ import os
 import torch
 
 from . import engine as E
-from ._lib import GpGemmBf16, GpGemmBf16x, call
+from ._lib import GpGemmBf16, GpGemmBf16x, call, load
 
 BF16 = 1
 KM, MN = 0, 1        # operand major-ness (see include/gp_b200.h)
@@ -259,7 +259,7 @@ def linkloss_forward(ws, sb, adjb, nb, B, N, K, need_grad):
     """Fused tensor-core link loss: P = S S^T tiles stay in TMEM, the epilogue does the masked BCE
     against the bf16 adjacency and writes gsym (bf16).  Returns (partial, n_partial, gsym op)."""
     nbp = E._p(nb)
-    npart = B * ((N + 127) // 128) * ((N + 255) // 256) * 8
+    npart = int(load().gp_linkloss_tc_partials(B, N))
     partial = ws.f(npart + 256)                      # +256: scratch of the two-stage finalisation
     gs = bfbuf(ws, B, N, N) if need_grad else None
     call('gp_linkloss_tc', sb.ptr, sb.ld, adjb.ptr, adjb.ld, nbp, B, N, K, partial.data_ptr(),

@@ -221,8 +221,10 @@ int gp_loss_finalize(const float* partial, int n_partial, double inv_entries, co
 /* Fused tensor-core form: S (bf16, row stride lds) -> P = S S^T tiles in TMEM -> masked BCE against
  * the bf16 adjacency in the epilogue; G = dl/dP evaluated with a[m,n] (bf16, row stride ldg, may be
  * NULL; the backward is dS = (G + G^T) S = two operand pairs of gp_bgemm_bf16x) and one partial per
- * epilogue warp: n_partial = B * ceil(N/128) * ceil(N/256) * 8.  P never touches HBM.
+ * epilogue warp: n_partial = gp_linkloss_tc_partials(B, N).  P never touches HBM.  s / adj / gsym
+ * bases 16-byte aligned with row strides that are multiples of 8 take the 16-byte vector path.
  * gp_loss_finalize with n_partial > 8192 uses 256 floats of scratch AFTER the partial array. */
+int gp_linkloss_tc_partials(int B, int N);
 int gp_linkloss_tc(const void* s_bf16, long long lds, const void* adj_bf16, long long ldadj,
                    const int32_t* nb, int B, int N, int K, float* partial, void* gsym_bf16, long long ldg,
                    gp_stream_t stream);
