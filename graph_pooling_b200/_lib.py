@@ -51,6 +51,14 @@ class GpGemmBf16x(C.Structure):
                 ('bias', c_f), ('relu', c_i), ('split_k', c_i)]
 
 
+class GpLayerBwd(C.Structure):
+    _fields_ = [('dz', c_f), ('lddz', c_ll), ('dxn', c_f), ('dout', c_f), ('argidx', c_f), ('ldo', c_ll),
+                ('h', c_f), ('ldh', c_ll), ('y', c_f), ('ldy', c_ll),
+                ('rnorm', c_f), ('mean', c_f), ('invstd', c_f),
+                ('B', c_i), ('N', c_i), ('d', c_i), ('relu', c_i), ('bn', c_i), ('normalize', c_i),
+                ('dv', c_f), ('dv_bf16', c_f), ('lddvb', c_ll), ('db', c_f), ('ws', c_f)]
+
+
 # name -> argtypes (restype is int unless listed in _RESTYPES)
 _PROTOS = {
     'gp_bgemm_bf16x': [C.POINTER(GpGemmBf16x), c_f],
@@ -67,6 +75,8 @@ _PROTOS = {
     'gp_relu_bn_fwd': [c_f, c_f, c_ll, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f],
     'gp_gcn_layer_bwd': [c_f, c_ll, c_f, c_f, c_f, c_ll, c_f, c_ll, c_f, c_ll, c_f, c_f, c_i, c_i, c_i, c_i, c_i,
                          c_i, c_f, c_f],
+    'gp_gcn_layer_bwd_x': [C.POINTER(GpLayerBwd), c_f],
+    'gp_gcn_layer_bwd_ws': [c_i, c_i, c_i, c_i],
     'gp_readout_max_fwd': [c_f, c_ll, c_f, c_i, c_i, c_i, c_f, c_f, c_ll, c_f],
     'gp_softmax_mask_fwd': [c_f, c_f, c_i, c_i, c_i, c_f],
     'gp_softmax_mask_bwd': [c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f],
@@ -86,7 +96,7 @@ _PROTOS = {
     'gp_fill_f32': [c_f, c_ll, C.c_float, c_f],
     'gp_axpy_f32': [c_f, c_f, c_ll, C.c_float, c_f],
 }
-_RESTYPES = {'gp_last_error': C.c_char_p, 'gp_launch_count': c_ll, 'gp_launch_count_reset': None}
+_RESTYPES = {'gp_last_error': C.c_char_p, 'gp_launch_count': c_ll, 'gp_gcn_layer_bwd_ws': c_ll, 'gp_launch_count_reset': None}
 
 EXPORTS = tuple(_PROTOS)
 _lib = None

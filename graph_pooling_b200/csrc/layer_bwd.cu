@@ -1,0 +1,370 @@
+// Vectorised single-pass backward of one GCN layer's element-wise tail (HBM-bound):
+//   [concat-slot gradient + next layer's dX + max-readout scatter] -> BatchNorm-per-node-index (batch
+//   statistics) -> ReLU -> L2-normalize   (encoders.py:1062-1064,1048-1052,323-326)
+// producing dV in fp32 and/or bf16 (the operand of the dW / dU contractions) and the column sums of dV
+// (= the bias gradient) in the same pass, so every input is read from HBM exactly once.
+//
+// Two kernels:
+//  * layer_bwd_bn_kernel   BN couples all graphs at one node index n.  A thread-block CLUSTER of CS CTAs owns
+//    node n; each CTA keeps its B/CS rows in registers (16-byte loads, everything in flight at once), the
+//    cluster reduces mean(g) and mean(g*Hhat) through distributed shared memory, then each CTA finishes its
+//    rows.  Several clusters are resident per SM, so one node's reduction overlaps another node's loads.
+//  * layer_bwd_row_kernel  no BN (last layer of a stack): rows are independent, one warp per row.
+// Shapes outside the fast paths (d % 4 != 0, unaligned strides, d > 512, ...) use rowops.cu's generic kernel.
+#include <cooperative_groups.h>
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace gp {
+
+constexpr float kEpsNormB = 1e-12f;
+
+int colsum(const float* x, long long rows, int d, long long ld, float* out, int accumulate, float* ws,
+           cudaStream_t st);
+int layer_bwd_generic(const gp_layer_bwd* a, cudaStream_t st);   // rowops.cu
+
+struct LbArgs {
+  const float* dz; long long lddz;
+  const float* dxn;
+  const float* dout; const int32_t* argidx; long long ldo;
+  const float* h; long long ldh;
+  const float* y; long long ldy;
+  const float* rnorm; const float* mean; const float* invstd;
+  int B, N, d, relu, bn, normalize;
+  float* dv; __nv_bfloat16* dvb; long long lddvb;
+  float* part;          // [blocks][d] partial column sums or NULL
+};
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// combined upstream gradient of 4 consecutive columns of row (b, n)
+__device__ __forceinline__ float4 load_g(const LbArgs& a, int b, int n, long long row, int c) {
+  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (a.dz != nullptr) g = ld4(a.dz + row * a.lddz + c);
+  if (a.dxn != nullptr) {
+    const float4 t = ld4(a.dxn + row * a.d + c);
+    g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+  }
+  if (a.dout != nullptr) {
+    const int4 i4 = *reinterpret_cast<const int4*>(a.argidx + (long long)b * a.ldo + c);
+    const float4 o = ld4(a.dout + (long long)b * a.ldo + c);
+    if (i4.x == n) g.x += o.x;
+    if (i4.y == n) g.y += o.y;
+    if (i4.z == n) g.z += o.z;
+    if (i4.w == n) g.w += o.w;
+  }
+  return g;
+}
+
+__device__ __forceinline__ void store_dv(const LbArgs& a, long long row, int c, float4 v) {
+  if (a.dv != nullptr) *reinterpret_cast<float4*>(a.dv + row * a.d + c) = v;
+  if (a.dvb != nullptr)
+    *reinterpret_cast<uint2*>(a.dvb + row * a.lddvb + c) = make_uint2(pack2(v.x, v.y), pack2(v.z, v.w));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// BN layers.  T threads, D4 = d/4 (power of two <= 32) threads per row, VPT rows per thread.
+// ---------------------------------------------------------------------------------------------------------
+template <int VPT, bool HAS_H>
+__global__ void __launch_bounds__(256) layer_bwd_bn_kernel(const LbArgs a, int CS, int rows_per_cta) {
+  constexpr int T = 256;
+  __shared__ float red[2][T / 32];
+  __shared__ float cta_part[2];
+  __shared__ __align__(16) float colacc[T * 4];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int n = blockIdx.x / CS;
+  const int rank = blockIdx.x - n * CS;
+  const int d4 = a.d >> 2;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c = (tid % d4) * 4;
+  const int rstep = T / d4;
+  const int b0 = rank * rows_per_cta;
+  const int b1 = min(a.B, b0 + rows_per_cta);
+  const float mu = a.mean != nullptr ? a.mean[n] : 0.f;
+  const float is = a.invstd[n];
+
+  float4 g[VPT], yv[VPT], hh[HAS_H ? VPT : 1];
+  float rn[VPT];
+  // ---- all loads in flight ----
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) {
+    const int b = b0 + tid / d4 + j * rstep;
+    g[j] = yv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (HAS_H) hh[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    rn[j] = 1.f;
+    if (b < b1) {
+      const long long row = (long long)b * a.N + n;
+      g[j] = load_g(a, b, n, row, c);
+      yv[j] = ld4(a.y + row * a.ldy + c);
+      if (HAS_H) hh[j] = ld4(a.h + row * a.ldh + c);
+      if (a.normalize) rn[j] = a.rnorm[row];
+    }
+  }
+  auto hhat = [&](int j) -> float4 {                     // stored BN output, or recomputed from Y and the statistics
+    if (HAS_H) return hh[j];
+    const float4 y = yv[j];
+    return make_float4(((a.relu ? fmaxf(y.x, 0.f) : y.x) - mu) * is, ((a.relu ? fmaxf(y.y, 0.f) : y.y) - mu) * is,
+                       ((a.relu ? fmaxf(y.z, 0.f) : y.z) - mu) * is, ((a.relu ? fmaxf(y.w, 0.f) : y.w) - mu) * is);
+  };
+  // ---- Hhat and the two batch means ----
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) {
+    const float4 hj = hhat(j);                           // rows beyond b1 have g == 0: they add nothing
+    s1 += (g[j].x + g[j].y) + (g[j].z + g[j].w);
+    s2 = fmaf(g[j].x, hj.x, s2); s2 = fmaf(g[j].y, hj.y, s2);
+    s2 = fmaf(g[j].z, hj.z, s2); s2 = fmaf(g[j].w, hj.w, s2);
+  }
+  s1 = warp_sum(s1); s2 = warp_sum(s2);
+  if (lane == 0) { red[0][warp] = s1; red[1][warp] = s2; }
+  __syncthreads();
+  if (tid == 0) {
+    float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int w = 0; w < T / 32; ++w) { t1 += red[0][w]; t2 += red[1][w]; }
+    cta_part[0] = t1; cta_part[1] = t2;
+  }
+  cluster.sync();                                        // every CTA's partial is visible cluster-wide
+  float S1 = 0.f, S2 = 0.f;
+  for (int r = 0; r < CS; ++r) {                         // same order in every CTA: bitwise-identical means
+    const float* rp = cluster.map_shared_rank(cta_part, r);
+    S1 += rp[0]; S2 += rp[1];
+  }
+  cluster.sync();                                        // nobody exits while its partial may still be read
+  const float inv_cnt = 1.f / ((float)a.B * (float)a.d);
+  const float m1 = S1 * inv_cnt, m2 = S2 * inv_cnt;
+
+  // ---- finish the rows ----
+  float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) {
+    const int b = b0 + tid / d4 + j * rstep;
+    const float4 hj = hhat(j);
+    float4 v;
+    v.x = (g[j].x - m1 - hj.x * m2) * is;
+    v.y = (g[j].y - m1 - hj.y * m2) * is;
+    v.z = (g[j].z - m1 - hj.z * m2) * is;
+    v.w = (g[j].w - m1 - hj.w * m2) * is;
+    const float4 y = yv[j];
+    if (a.relu) {
+      if (!(y.x > 0.f)) v.x = 0.f;
+      if (!(y.y > 0.f)) v.y = 0.f;
+      if (!(y.z > 0.f)) v.z = 0.f;
+      if (!(y.w > 0.f)) v.w = 0.f;
+    }
+    if (a.normalize) {
+      float dot = fmaf(v.x, y.x, fmaf(v.y, y.y, fmaf(v.z, y.z, v.w * y.w)));
+      for (int o = d4 >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      const float r = rn[j];
+      if (!(r > kEpsNormB)) {
+        v.x /= kEpsNormB; v.y /= kEpsNormB; v.z /= kEpsNormB; v.w /= kEpsNormB;
+      } else {
+        const float ir = 1.f / r;
+        v.x = (v.x - y.x * dot) * ir; v.y = (v.y - y.y * dot) * ir;
+        v.z = (v.z - y.z * dot) * ir; v.w = (v.w - y.w * dot) * ir;
+      }
+    }
+    if (b < b1) {
+      store_dv(a, (long long)b * a.N + n, c, v);
+      cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
+    }
+  }
+  if (a.part != nullptr) {                               // deterministic per-CTA column sums
+    *reinterpret_cast<float4*>(&colacc[tid * 4]) = cs;
+    __syncthreads();
+    if (tid < a.d) {
+      const int q = tid >> 2, e = tid & 3;               // column tid = 4*q + e lives in threads q, q+d4, ...
+      float t = 0.f;
+      for (int r = q; r < T; r += d4) t += colacc[r * 4 + e];
+      a.part[(long long)blockIdx.x * a.d + tid] = t;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// No BN: one warp per row, lane owns float4 columns lane, lane+32, ... (VPL of them).
+// ---------------------------------------------------------------------------------------------------------
+template <int VPL>
+__global__ void __launch_bounds__(256) layer_bwd_row_kernel(const LbArgs a, long long rows) {
+  __shared__ __align__(16) float colacc[8][VPL * 128];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int d4 = a.d >> 2;
+  const long long gw = (long long)blockIdx.x * 8 + warp, nw = (long long)gridDim.x * 8;
+  float4 cs[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) cs[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long row = gw; row < rows; row += nw) {
+    const int b = (int)(row / a.N), n = (int)(row - (long long)b * a.N);
+    float4 g[VPL], yv[VPL];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int c4 = lane + 32 * k;
+      g[k] = yv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c4 < d4) {
+        g[k] = load_g(a, b, n, row, c4 * 4);
+        yv[k] = ld4(a.y + row * a.ldy + c4 * 4);
+      }
+    }
+    const float r = a.normalize ? a.rnorm[row] : 1.f;
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      if (a.relu) {
+        if (!(yv[k].x > 0.f)) g[k].x = 0.f;
+        if (!(yv[k].y > 0.f)) g[k].y = 0.f;
+        if (!(yv[k].z > 0.f)) g[k].z = 0.f;
+        if (!(yv[k].w > 0.f)) g[k].w = 0.f;
+      }
+      dot = fmaf(g[k].x, yv[k].x, fmaf(g[k].y, yv[k].y, fmaf(g[k].z, yv[k].z, fmaf(g[k].w, yv[k].w, dot))));
+    }
+    if (a.normalize) {
+      dot = warp_sum(dot);
+      const bool clamped = !(r > kEpsNormB);
+      const float ir = clamped ? 1.f / kEpsNormB : 1.f / r;
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        if (clamped) {
+          g[k].x /= kEpsNormB; g[k].y /= kEpsNormB; g[k].z /= kEpsNormB; g[k].w /= kEpsNormB;
+        } else {
+          g[k].x = (g[k].x - yv[k].x * dot) * ir; g[k].y = (g[k].y - yv[k].y * dot) * ir;
+          g[k].z = (g[k].z - yv[k].z * dot) * ir; g[k].w = (g[k].w - yv[k].w * dot) * ir;
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int c4 = lane + 32 * k;
+      if (c4 < d4) {
+        store_dv(a, row, c4 * 4, g[k]);
+        cs[k].x += g[k].x; cs[k].y += g[k].y; cs[k].z += g[k].z; cs[k].w += g[k].w;
+      }
+    }
+  }
+  if (a.part != nullptr) {
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) *reinterpret_cast<float4*>(&colacc[warp][(lane + 32 * k) * 4]) = cs[k];
+    __syncthreads();
+    for (int cidx = threadIdx.x; cidx < a.d; cidx += blockDim.x) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += colacc[w][cidx];
+      a.part[(long long)blockIdx.x * a.d + cidx] = t;
+    }
+  }
+}
+
+static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// shape-level eligibility for the vectorised kernels (pointer alignment is checked per call)
+static bool shape_fast(int B, int d, int bn, int* CS_out) {
+  if (d % 4 != 0 || d > 512) return false;
+  if (!bn) return true;
+  const int d4 = d / 4;
+  if (d4 > 32 || (d4 & (d4 - 1)) != 0) return false;     // a row must fit a power-of-two slice of one warp
+  const int rstep = 256 / d4;
+  int CS = 1;
+  while (CS <= 8 && ((B + CS - 1) / CS + rstep - 1) / rstep > 8) CS *= 2;
+  if (CS > 8) return false;
+  if (CS_out) *CS_out = CS;
+  return true;
+}
+
+// floats gp_gcn_layer_bwd_x needs in `ws` when db != NULL
+static long long ws_floats(int B, int N, int d, int bn) {
+  long long blocks = (long long)N * 8;                   // upper bound on CTAs of either kernel
+  if (blocks < kNumSMs * 8) blocks = kNumSMs * 8;
+  long long f = blocks * d + 256LL * d;
+  if (!shape_fast(B, d, bn, nullptr)) f += (long long)B * N * d;   // generic path: fp32 dV scratch for the column sums
+  return f;
+}
+
+template <int VPT>
+static int launch_bn(const LbArgs& a, int CS, int rpc, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(a.N * CS));
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  if (a.h != nullptr) GP_CUDA(cudaLaunchKernelEx(&cfg, layer_bwd_bn_kernel<VPT, true>, a, CS, rpc));
+  else                GP_CUDA(cudaLaunchKernelEx(&cfg, layer_bwd_bn_kernel<VPT, false>, a, CS, rpc));
+  g_launches++;
+  return GP_OK;
+}
+
+int layer_bwd_fast(const gp_layer_bwd* q, cudaStream_t st, bool* handled) {
+  *handled = false;
+  const int d = q->d;
+  if (!al16(q->y) || q->ldy % 4 != 0) return GP_OK;
+  if (q->dz != nullptr && (!al16(q->dz) || q->lddz % 4 != 0)) return GP_OK;
+  if (q->dxn != nullptr && !al16(q->dxn)) return GP_OK;
+  if (q->dout != nullptr && (!al16(q->dout) || !al16(q->argidx) || q->ldo % 4 != 0)) return GP_OK;
+  if (q->h != nullptr && (!al16(q->h) || q->ldh % 4 != 0)) return GP_OK;
+  if (q->dv != nullptr && !al16(q->dv)) return GP_OK;
+  if (q->dv_bf16 != nullptr && ((reinterpret_cast<uintptr_t>(q->dv_bf16) & 7) != 0 || q->lddvb % 4 != 0)) return GP_OK;
+  if (q->bn && q->h == nullptr && q->mean == nullptr) return GP_OK;
+  LbArgs a;
+  a.dz = q->dz; a.lddz = q->lddz; a.dxn = q->dxn; a.dout = q->dout; a.argidx = q->argidx; a.ldo = q->ldo;
+  a.h = q->h; a.ldh = q->ldh; a.y = q->y; a.ldy = q->ldy; a.rnorm = q->rnorm; a.mean = q->mean; a.invstd = q->invstd;
+  a.B = q->B; a.N = q->N; a.d = d; a.relu = q->relu; a.bn = q->bn; a.normalize = q->normalize;
+  a.dv = q->dv; a.dvb = reinterpret_cast<__nv_bfloat16*>(q->dv_bf16); a.lddvb = q->lddvb;
+  a.part = q->db != nullptr ? q->ws : nullptr;
+  long long part_rows = 0;
+  int CS = 1;
+  if (!shape_fast(q->B, d, q->bn, &CS)) return GP_OK;
+  if (q->bn) {
+    const int rstep = 256 / (d / 4);
+    const int rpc = (q->B + CS - 1) / CS;
+    const int vpt = (rpc + rstep - 1) / rstep;
+    if (vpt <= 1) GP_TRY(launch_bn<1>(a, CS, rpc, st));
+    else if (vpt <= 2) GP_TRY(launch_bn<2>(a, CS, rpc, st));
+    else if (vpt <= 4) GP_TRY(launch_bn<4>(a, CS, rpc, st));
+    else GP_TRY(launch_bn<8>(a, CS, rpc, st));
+    part_rows = (long long)q->N * CS;
+  } else {
+    const long long rows = (long long)q->B * q->N;
+    long long blocks = (rows + 7) / 8;
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    const int d4 = d / 4;
+    if (d4 <= 32) layer_bwd_row_kernel<1><<<(int)blocks, 256, 0, st>>>(a, rows);
+    else if (d4 <= 64) layer_bwd_row_kernel<2><<<(int)blocks, 256, 0, st>>>(a, rows);
+    else layer_bwd_row_kernel<4><<<(int)blocks, 256, 0, st>>>(a, rows);
+    GP_LAUNCHED();
+    part_rows = blocks;
+  }
+  if (q->db != nullptr)
+    GP_TRY(colsum(q->ws, part_rows, d, d, q->db, 0, q->ws + part_rows * d, st));
+  *handled = true;
+  return GP_OK;
+}
+
+}  // namespace gp
+
+using namespace gp;
+
+extern "C" long long gp_gcn_layer_bwd_ws(int B, int N, int d, int bn) { return ws_floats(B, N, d, bn); }
+
+extern "C" int gp_gcn_layer_bwd_x(const gp_layer_bwd* q, gp_stream_t stream) {
+  GP_REQUIRE(q != nullptr, "gcn_layer_bwd_x: null descriptor");
+  GP_REQUIRE(q->y && (q->dv || q->dv_bf16) && q->B > 0 && q->N > 0 && q->d > 0, "gcn_layer_bwd_x: bad args");
+  GP_REQUIRE(!q->bn || (q->invstd && (q->h || q->mean)), "gcn_layer_bwd_x: bn needs invstd and h or mean");
+  GP_REQUIRE(!q->normalize || q->rnorm, "gcn_layer_bwd_x: normalize needs rnorm");
+  GP_REQUIRE(!q->dout || q->argidx, "gcn_layer_bwd_x: dout needs argidx");
+  GP_REQUIRE(!q->db || q->ws, "gcn_layer_bwd_x: db needs ws (gp_gcn_layer_bwd_ws floats)");
+  bool handled = false;
+  GP_TRY(layer_bwd_fast(q, S(stream), &handled));
+  if (handled) return GP_OK;
+  if (q->dv == nullptr && q->db != nullptr && shape_fast(q->B, q->d, q->bn, nullptr))
+    return fail(GP_ERR_UNSUPPORTED, "gcn_layer_bwd_x: db without dv needs 16-byte aligned operands "
+                                    "(ws was sized for the vectorised path)");
+  return layer_bwd_generic(q, S(stream));
+}

@@ -4,6 +4,7 @@
 //   max-readout scatter and the normalize backward, max readout (encoders.py:1097,1257,1287),
 //   masked assignment softmax (encoders.py:1273-1275), cross entropy (encoders.py:1127), colsum.
 // All reductions are warp-shuffle based over coalesced rows; no atomics, deterministic.
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace gp {
@@ -109,30 +110,46 @@ __device__ __forceinline__ float layer_g(const float* dz, long long lddz, const 
 // CACHE: pass 1 stages the combined gradient g of the node's B*d entries in dynamic shared memory, so the
 // gradient sources are read from HBM once.  MAXE > 0: a row (d <= 32*MAXE) stays in registers between the
 // <Y,dY> reduction and the final write, so h / y are read once in pass 2.
+// Hhat of one element: the stored BN output if available, else recomputed from Y and the saved statistics.
+__device__ __forceinline__ float hhat_of(const float* h, long long ldh, const float* y, long long ldy, long long row,
+                                         int c, int relu, float mu, float is) {
+  if (h != nullptr) return h[row * ldh + c];
+  float x = y[row * ldy + c];
+  if (relu) x = fmaxf(x, 0.f);
+  return (x - mu) * is;
+}
+__device__ __forceinline__ void put_dv(float* dv, __nv_bfloat16* dvb, long long lddvb, long long row, int d, int c,
+                                       float g) {
+  if (dv != nullptr) dv[row * d + c] = g;
+  if (dvb != nullptr) dvb[row * lddvb + c] = __float2bfloat16_rn(g);
+}
+
 template <bool CACHE, int MAXE>
 __global__ void gcn_layer_bwd_kernel(const float* __restrict__ dz, long long lddz, const float* __restrict__ dxn,
                                      const float* __restrict__ dout, const int32_t* __restrict__ argidx,
                                      long long ldo, const float* __restrict__ h, long long ldh,
                                      const float* __restrict__ y, long long ldy, const float* __restrict__ rnorm,
-                                     const float* __restrict__ invstd, int B, int N, int d, int relu, int bn,
-                                     int normalize, float* __restrict__ dv) {
+                                     const float* __restrict__ mean, const float* __restrict__ invstd, int B, int N,
+                                     int d, int relu, int bn, int normalize, float* __restrict__ dv,
+                                     __nv_bfloat16* __restrict__ dvb, long long lddvb) {
   extern __shared__ float cache[];
   __shared__ float sh[33];
   const int n = blockIdx.x;
   const int total = B * d;
-  float m1 = 0.f, m2 = 0.f, is = 1.f;
+  float m1 = 0.f, m2 = 0.f, is = 1.f, mu = 0.f;
   if (bn) {
+    is = invstd[n];
+    if (mean != nullptr) mu = mean[n];
     float s1 = 0.f, s2 = 0.f;
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
       const int b = i / d, c = i - b * d;
       const float g = layer_g(dz, lddz, dxn, dout, argidx, ldo, b, n, c, N, d);
       if (CACHE) cache[i] = g;
       s1 += g;
-      s2 = fmaf(g, h[((long long)b * N + n) * ldh + c], s2);
+      s2 = fmaf(g, hhat_of(h, ldh, y, ldy, (long long)b * N + n, c, relu, mu, is), s2);
     }
     m1 = block_sum(s1, sh) / (float)total;
     m2 = block_sum(s2, sh) / (float)total;
-    is = invstd[n];
   }
   const bool cached = CACHE && bn;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -153,7 +170,7 @@ __global__ void gcn_layer_bwd_kernel(const float* __restrict__ dz, long long ldd
         float g = 0.f, yy = 0.f;
         if (c < d) {
           g = cached ? cache[b * d + c] : layer_g(dz, lddz, dxn, dout, argidx, ldo, b, n, c, N, d);
-          if (bn) g = (g - m1 - h[row * ldh + c] * m2) * is;
+          if (bn) g = (g - m1 - hhat_of(h, ldh, y, ldy, row, c, relu, mu, is) * m2) * is;
           yy = y[row * ldy + c];
           if (relu && !(yy > 0.f)) g = 0.f;
           dot = fmaf(g, yy, dot);
@@ -167,14 +184,14 @@ __global__ void gcn_layer_bwd_kernel(const float* __restrict__ dz, long long ldd
         if (c < d) {
           float g = gv[e];
           if (normalize) g = clamped ? g / kEpsNorm : (g - yv[e] * dot) / r;
-          dv[row * d + c] = g;
+          put_dv(dv, dvb, lddvb, row, d, c, g);
         }
       }
     } else {
       float dot = 0.f;
       for (int c = lane; c < d; c += 32) {
         float g = cached ? cache[b * d + c] : layer_g(dz, lddz, dxn, dout, argidx, ldo, b, n, c, N, d);
-        if (bn) g = (g - m1 - h[row * ldh + c] * m2) * is;
+        if (bn) g = (g - m1 - hhat_of(h, ldh, y, ldy, row, c, relu, mu, is) * m2) * is;
         const float yy = y[row * ldy + c];
         if (relu && !(yy > 0.f)) g = 0.f;
         dot = fmaf(g, yy, dot);
@@ -182,11 +199,11 @@ __global__ void gcn_layer_bwd_kernel(const float* __restrict__ dz, long long ldd
       if (normalize) dot = warp_sum(dot);
       for (int c = lane; c < d; c += 32) {
         float g = cached ? cache[b * d + c] : layer_g(dz, lddz, dxn, dout, argidx, ldo, b, n, c, N, d);
-        if (bn) g = (g - m1 - h[row * ldh + c] * m2) * is;
+        if (bn) g = (g - m1 - hhat_of(h, ldh, y, ldy, row, c, relu, mu, is) * m2) * is;
         const float yy = y[row * ldy + c];
         if (relu && !(yy > 0.f)) g = 0.f;
         if (normalize) g = clamped ? g / kEpsNorm : (g - yy * dot) / r;
-        dv[row * d + c] = g;
+        put_dv(dv, dvb, lddvb, row, d, c, g);
       }
     }
   }
@@ -403,18 +420,20 @@ extern "C" int gp_relu_bn_fwd(const float* y, float* h, long long ldh, float* me
   return GP_OK;
 }
 
-extern "C" int gp_gcn_layer_bwd(const float* dz, long long lddz, const float* dxn, const float* dout,
-                                const int32_t* argidx, long long ldo, const float* h, long long ldh,
-                                const float* y, long long ldy, const float* rnorm, const float* invstd,
-                                int B, int N, int d, int relu, int bn, int normalize, float* dv,
-                                gp_stream_t stream) {
-  GP_REQUIRE(y && dv && B > 0 && N > 0 && d > 0, "gcn_layer_bwd: bad args");
-  GP_REQUIRE(!bn || (h && invstd), "gcn_layer_bwd: bn needs h/invstd");
-  GP_REQUIRE(!normalize || rnorm, "gcn_layer_bwd: normalize needs rnorm");
-  GP_REQUIRE(!dout || argidx, "gcn_layer_bwd: dout needs argidx");
+namespace gp {
+// Generic (any d, any alignment) path of gp_gcn_layer_bwd_x; the vectorised fast paths live in layer_bwd.cu.
+int layer_bwd_generic(const gp_layer_bwd* q, cudaStream_t st) {
+  const int B = q->B, N = q->N, d = q->d;
+  float* dv = q->dv;
+  float* cs_ws = q->ws;
+  if (dv == nullptr && q->db != nullptr) {               // column sums need an fp32 dV: borrow it from ws
+    dv = q->ws;
+    cs_ws = q->ws + (long long)B * N * d;
+  }
+  __nv_bfloat16* dvb = reinterpret_cast<__nv_bfloat16*>(q->dv_bf16);
   const int total = B * d;
   const size_t cache_bytes = (size_t)total * sizeof(float);
-  const bool use_cache = bn && cache_bytes > 16 * 1024 && cache_bytes <= kNodeCacheMax;
+  const bool use_cache = q->bn && cache_bytes > 16 * 1024 && cache_bytes <= kNodeCacheMax;
   // 512 threads: the MAXE=16 variant needs 80 registers/thread (1024 threads would exceed the register file)
   const int threads = use_cache ? 512 : (total >= 4096 ? 512 : (total >= 512 ? 256 : 128));
   const int maxe = d <= 128 ? 4 : (d <= 512 ? 16 : 0);
@@ -425,8 +444,9 @@ extern "C" int gp_gcn_layer_bwd(const float* dz, long long lddz, const float* dx
       static bool cfgd = false;                                                                            \
       if (!cfgd) { GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNodeCacheMax)); cfgd = true; } \
     }                                                                                                      \
-    kern<<<N, threads, C_ ? cache_bytes : 0, S(stream)>>>(dz, lddz, dxn, dout, argidx, ldo, h, ldh, y, ldy, \
-                                                          rnorm, invstd, B, N, d, relu, bn, normalize, dv); \
+    kern<<<N, threads, C_ ? cache_bytes : 0, st>>>(q->dz, q->lddz, q->dxn, q->dout, q->argidx, q->ldo, q->h, \
+                                                   q->ldh, q->y, q->ldy, q->rnorm, q->mean, q->invstd, B, N, d, \
+                                                   q->relu, q->bn, q->normalize, dv, dvb, q->lddvb);       \
   } while (0)
   if (use_cache) {
     if (maxe == 4) GP_LAUNCH_LBWD(true, 4); else if (maxe == 16) GP_LAUNCH_LBWD(true, 16); else GP_LAUNCH_LBWD(true, 0);
@@ -435,7 +455,22 @@ extern "C" int gp_gcn_layer_bwd(const float* dz, long long lddz, const float* dx
   }
 #undef GP_LAUNCH_LBWD
   GP_LAUNCHED();
+  if (q->db != nullptr) GP_TRY(colsum(dv, (long long)B * N, d, d, q->db, 0, cs_ws, st));
   return GP_OK;
+}
+}  // namespace gp
+
+extern "C" int gp_gcn_layer_bwd(const float* dz, long long lddz, const float* dxn, const float* dout,
+                                const int32_t* argidx, long long ldo, const float* h, long long ldh,
+                                const float* y, long long ldy, const float* rnorm, const float* invstd,
+                                int B, int N, int d, int relu, int bn, int normalize, float* dv,
+                                gp_stream_t stream) {
+  gp_layer_bwd q;
+  q.dz = dz; q.lddz = lddz; q.dxn = dxn; q.dout = dout; q.argidx = argidx; q.ldo = ldo;
+  q.h = h; q.ldh = ldh; q.y = y; q.ldy = ldy; q.rnorm = rnorm; q.mean = nullptr; q.invstd = invstd;
+  q.B = B; q.N = N; q.d = d; q.relu = relu; q.bn = bn; q.normalize = normalize;
+  q.dv = dv; q.dv_bf16 = nullptr; q.lddvb = 0; q.db = nullptr; q.ws = nullptr;
+  return gp_gcn_layer_bwd_x(&q, stream);
 }
 
 extern "C" int gp_readout_max_fwd(const float* z, long long ldz, const int32_t* nb, int B, int N, int F,

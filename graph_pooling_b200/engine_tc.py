@@ -12,7 +12,7 @@ import os
 import torch
 
 from . import engine as E
-from ._lib import GpGemmBf16, GpGemmBf16x, call, load
+from ._lib import GpGemmBf16, GpGemmBf16x, GpLayerBwd, call, load
 
 BF16 = 1
 KM, MN = 0, 1        # operand major-ness (see include/gp_b200.h)
@@ -156,7 +156,6 @@ def stack_backward(ws, ctx, dz_ptr, lddz, dout_ptr, arg_ptr, ldo, need_dx, dadj)
     grads = [None] * L
     dxn = None
     zp = ctx.zcat.data_ptr()
-    cs = ws.f(256 * max(ctx.douts))
     nbp = E._p(ctx.nb)
     lim = int(ctx.nb is not None)
     rows = B * N
@@ -164,17 +163,27 @@ def stack_backward(ws, ctx, dz_ptr, lddz, dout_ptr, arg_ptr, ldo, need_dx, dadj)
         xb, din, dout, off, ub, y, rnorm, mean, invstd, wb = ctx.layers[l]
         last = l == L - 1
         slot = zp + off * 4
-        dv = ws.f(B, N, dout)
-        call('gp_gcn_layer_bwd',
-             None if dz_ptr is None else dz_ptr + off * 4, lddz, E._p(dxn),
-             None if dout_ptr is None else dout_ptr + off * 4, None if arg_ptr is None else arg_ptr + off * 4, ldo,
-             slot, Fw, slot if last else E._p(y), Fw if last else dout, E._p(rnorm), E._p(invstd),
-             B, N, dout, int(not last), int(ctx.bn and not last), 1, E._p(dv), st)
-        dvb = cvt(ws, dv.data_ptr(), dout, rows, dout)                                  # [rows, r8(dout)]
-        db = None
-        if ctx.biases[l] is not None:
-            db = ws.f(dout)
-            call('gp_colsum_f32', E._p(dv), C.c_longlong(rows), dout, C.c_longlong(dout), E._p(db), 0, E._p(cs), st)
+        # element-wise tail backward: bf16 dV (operand of the contractions below) + db in ONE pass over HBM;
+        # Hhat is recomputed from Y and the saved statistics instead of re-reading the BN output
+        dvb = bfbuf(ws, 1, rows, dout)
+        has_b = ctx.biases[l] is not None
+        db = ws.f(dout) if has_b else None
+        q = GpLayerBwd()
+        q.dz, q.lddz = (None if dz_ptr is None else dz_ptr + off * 4), lddz
+        q.dxn = E._p(dxn)
+        q.dout = None if dout_ptr is None else dout_ptr + off * 4
+        q.argidx = None if arg_ptr is None else arg_ptr + off * 4
+        q.ldo = ldo
+        use_bn = bool(ctx.bn and not last)
+        q.h, q.ldh = None, Fw
+        q.y, q.ldy = (slot, Fw) if last else (E._p(y), dout)
+        q.rnorm, q.mean, q.invstd = E._p(rnorm), E._p(mean), E._p(invstd)
+        q.B, q.N, q.d = B, N, dout
+        q.relu, q.bn, q.normalize = int(not last), int(use_bn), 1
+        q.dv, q.dv_bf16, q.lddvb = None, dvb.ptr, dvb.ld
+        q.db = E._p(db)
+        q.ws = E._p(ws.f(int(load().gp_gcn_layer_bwd_ws(B, N, dout, int(use_bn))))) if has_b else None
+        call('gp_gcn_layer_bwd_x', C.byref(q), st)
         # dW = U^T dV : U stored [rows, din] = M-major A ; dV N-major B ; split-K over the rows
         dw = ws.f(din, dout)
         tcgemm(Op(ub.ptr, ub.ld, 0), MN, Op(dvb.ptr, dvb.ld, 0), MN, din, dout, rows, 1, Cf=(dw.data_ptr(), dout, 0),

@@ -172,6 +172,27 @@ int gp_gcn_layer_bwd(const float* dz, long long lddz, const float* dxn, const fl
                      int B, int N, int d, int relu, int bn, int normalize, float* dv,
                      gp_stream_t stream);
 
+/* Extended form (the one the engines use): optional bf16 copy of dV (the operand of the tensor-core dW / dU
+ * contractions), the bias gradient db = colsum(dV) produced in the same pass, and Hhat recomputed from Y and
+ * the saved statistics (h == NULL, mean != NULL) so the BN output need not be re-read.  16-byte aligned
+ * inputs with d in {32, 64, 128} (bn) or d % 4 == 0, d <= 512 (no bn) take a single-pass vectorised kernel
+ * (a thread-block cluster per node index, batch means reduced through distributed shared memory).
+ * ws: gp_gcn_layer_bwd_ws(B, N, d, bn) floats, needed when db != NULL.  db without dv on a shape that
+ * qualifies for the vectorised kernel requires the alignment above (GP_ERR_UNSUPPORTED otherwise). */
+typedef struct gp_layer_bwd {
+  const float* dz; long long lddz;
+  const float* dxn;
+  const float* dout; const int32_t* argidx; long long ldo;
+  const float* h; long long ldh;
+  const float* y; long long ldy;
+  const float* rnorm; const float* mean; const float* invstd;
+  int B, N, d, relu, bn, normalize;
+  float* dv; void* dv_bf16; long long lddvb;
+  float* db; float* ws;
+} gp_layer_bwd;
+int gp_gcn_layer_bwd_x(const gp_layer_bwd* q, gp_stream_t stream);
+long long gp_gcn_layer_bwd_ws(int B, int N, int d, int bn);
+
 /* ---------------------------------------------------------------------------------------------
  * Max readout (encoders.py:1097,1257,1287): out[b,f] = max_n Z[b,n,f], pad rows (n >= nb[b])
  * counting as 0 when nb != NULL (the mask of :1078-1080).  argidx = winning row (lowest index on
