@@ -63,6 +63,12 @@ class GpLayerBwd(C.Structure):
 _PROTOS = {
     'gp_bgemm_bf16x': [C.POINTER(GpGemmBf16x), c_f],
     'gp_bgemm_bf16': [C.POINTER(GpGemmBf16), c_f],
+    'gp_bgemm_bf16_norm': [C.POINTER(GpGemmBf16x), c_f, c_f, c_i, c_f],
+    'gp_bn_finalize': [c_f, c_i, c_i, c_i, c_f, c_f, c_f],
+    'gp_bn_apply': [c_f, c_ll, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f, c_ll, c_f, c_ll, c_f],
+    'gp_bias_normalize_x': [c_f, c_f, c_f, c_ll, c_i, c_ll, c_i, c_f, c_ll, c_f],
+    'gp_softmax_mask_fwd_x': [c_f, c_f, c_i, c_i, c_i, c_f, c_ll, c_f],
+    'gp_softmax_mask_bwd_x': [c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f, c_ll, c_f, c_f, c_f],
     'gp_cvt_f32_bf16': [c_f, c_ll, c_f, c_ll, c_ll, c_i, c_i, c_f],
     'gp_version': [],
     'gp_last_error': [],

@@ -15,6 +15,10 @@
 //   the epilogue does the masked BCE against the bf16 adjacency (coalesced), writes G = dl/dP (bf16) and
 //   one partial sum per epilogue warp; P never touches HBM.  {0,1} adjacency tiles (warp-uniform test)
 //   take a fast path with one log and one reciprocal per element instead of two each.
+// * EPI == 2: fused GraphConv tail (encoders.py:322-326): V = U.W + b, Y = V / max(||V||_2, 1e-12) with the
+//   row norm taken in the epilogue (N <= BN: a thread owns a whole output row in TMEM, so the reduction is
+//   thread-local; the accumulator is read twice, once for the norm and once for the normalised write), plus
+//   the per-row sums of relu(Y) and relu(Y)^2 that the following BatchNorm-per-node needs (encoders.py:1062).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include "common.cuh"
@@ -45,6 +49,7 @@ struct Params {
   int K[kMaxPairs]; int a_mn[kMaxPairs]; int b_mn[kMaxPairs]; int lim_k[kMaxPairs];
   int tiles_m, tiles_n; long long total_work;
   const __nv_bfloat16* adjb; long long ldadj, sadjb; float* partial;   // EPI == 1
+  float* rnorm; float2* rowstat; int stat_relu;                        // EPI == 2
 };
 
 struct Work {
@@ -124,7 +129,7 @@ struct Smem {
   static constexpr int kB = BN * BK * 2;
   static constexpr int kStage = kA + kB;
   static constexpr int kStaging = EW * 32 * 32 * 4;
-  static constexpr int kBytes = STAGES * kStage + kStaging + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kBytes = STAGES * kStage + kStaging + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*bias*/;
 };
 
 __device__ __forceinline__ Work get_work(const Params& p, long long w) {
@@ -259,6 +264,11 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  float* sbias = reinterpret_cast<float*>(smem_gen + STAGES * L::kStage + L::kStaging + 256);
+  if (EPI == 2) {                                        // bias (zero beyond N) staged once per CTA
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sbias[i] = (p.bias != nullptr && i < p.N) ? p.bias[i] : 0.f;
+    __syncthreads();
+  }
 
   if (warp == kProd) {
     // ===== TMA producer =====
@@ -362,6 +372,90 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
         tc_fence_after();
       }
       const int row0 = k.m0 + quarter * 32;
+      if (EPI == 2) {
+        // ---- bias + L2 normalize + BN row statistics; EW == 4: this warp owns rows row0..row0+31 entirely ----
+        const int row = row0 + lane;
+        const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * BN);
+        float ssp[4] = {0.f, 0.f, 0.f, 0.f};             // 4 independent chains
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          if (c * 32 >= p.N) break;
+          uint32_t v[32];
+          tmem_ld32(trow + c * 32, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float x = fmaf(alpha, __uint_as_float(v[j]), sbias[c * 32 + j]);
+            ssp[j & 3] = fmaf(x, x, ssp[j & 3]);
+          }
+        }
+        const float ss = (ssp[0] + ssp[1]) + (ssp[2] + ssp[3]);
+        const float nrm = fmaxf(sqrtf(ss), 1e-12f);
+        const float inv = 1.f / nrm;
+        if (row < p.M && p.rnorm != nullptr) p.rnorm[row] = nrm;
+        float s1p[2] = {0.f, 0.f}, s2p[2] = {0.f, 0.f};
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          const int nbase = c * 32;
+          if (nbase >= p.N) break;
+          uint32_t v[32];
+          tmem_ld32(trow + c * 32, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float x = fmaf(alpha, __uint_as_float(v[j]), sbias[nbase + j]) * inv;
+            const float r = p.stat_relu ? fmaxf(x, 0.f) : x;
+            s1p[j & 1] += r;
+            s2p[j & 1] = fmaf(r, r, s2p[j & 1]);
+            v[j] = __float_as_uint(x);
+          }
+          if (row0 >= p.M) continue;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<uint4*>(&stg[stg_off(lane, 4 * q)]) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          __syncwarp();
+          const bool full = nbase + 32 <= p.N;
+          if (p.C != nullptr) {
+            if (vecC && full) {
+              const int cc = (lane & 7) * 4;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int r = 4 * i + (lane >> 3);
+                if (row0 + r < p.M)
+                  *reinterpret_cast<float4*>(p.C + (long long)(row0 + r) * p.ldC + nbase + cc) =
+                      *reinterpret_cast<const float4*>(&stg[stg_off(r, cc)]);
+              }
+            } else if (nbase + lane < p.N) {
+              for (int r = 0; r < 32 && row0 + r < p.M; ++r)
+                p.C[(long long)(row0 + r) * p.ldC + nbase + lane] = stg[stg_off(r, lane)];
+            }
+          }
+          if (p.Cb != nullptr) {
+            if (vecCb8 && full) {
+              const int cc = (lane & 3) * 8;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int r = 8 * i + (lane >> 2);
+                if (row0 + r < p.M) {
+                  const float4 a0 = *reinterpret_cast<const float4*>(&stg[stg_off(r, cc)]);
+                  const float4 a1 = *reinterpret_cast<const float4*>(&stg[stg_off(r, cc + 4)]);
+                  *reinterpret_cast<uint4*>(p.Cb + (long long)(row0 + r) * p.ldCb + nbase + cc) =
+                      make_uint4(pack_bf16x2(a0.x, a0.y), pack_bf16x2(a0.z, a0.w), pack_bf16x2(a1.x, a1.y),
+                                 pack_bf16x2(a1.z, a1.w));
+                }
+              }
+            } else if (nbase + lane < p.N) {
+              for (int r = 0; r < 32 && row0 + r < p.M; ++r)
+                p.Cb[(long long)(row0 + r) * p.ldCb + nbase + lane] = __float2bfloat16_rn(stg[stg_off(r, lane)]);
+            }
+          }
+          __syncwarp();
+        }
+        if (row < p.M && p.rowstat != nullptr) p.rowstat[row] = make_float2(s1p[0] + s1p[1], s2p[0] + s2p[1]);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(a));
+        ++nacc;
+        continue;
+      }
       float lsum = 0.f;
 #pragma unroll 1
       for (int c = 0; c < CPW / 32; ++c) {
@@ -670,6 +764,7 @@ int run(const gp_gemm_bf16x* g, cudaStream_t st) {
   p.alpha = g->alpha; p.beta = g->beta; p.alpha_dev = g->alpha_dev;
   p.bias = g->bias; p.relu = g->relu; p.split_k = g->split_k; p.npairs = g->npairs;
   p.adjb = nullptr; p.ldadj = p.sadjb = 0; p.partial = nullptr;
+  p.rnorm = nullptr; p.rowstat = nullptr; p.stat_relu = 0;
   if (split > 1 && p.beta != 1.f) {
     const long long total = (long long)g->batch * g->M * g->N;
     int blocks = (int)((total + 255) / 256);
@@ -681,6 +776,38 @@ int run(const gp_gemm_bf16x* g, cudaStream_t st) {
   if (BN == 256) return launch<256, 4, 0, 8>(maps, p, st);
   if (BN == 128) return launch<128, 6, 0, 8>(maps, p, st);
   return launch<64, 6, 0, 8>(maps, p, st);
+}
+
+// V = A.B + bias -> Y = V / max(||V||, eps) (fp32 C and/or bf16 Cb), rnorm, rowstat = (sum relu(Y), sum relu(Y)^2)
+int run_norm(const gp_gemm_bf16x* g, float* rnorm, float* rowstat, int stat_relu, cudaStream_t st) {
+  GP_REQUIRE(g != nullptr && g->npairs == 1, "bgemm_bf16_norm: exactly one operand pair");
+  GP_REQUIRE(g->C || g->Cb, "bgemm_bf16_norm: no output");
+  GP_REQUIRE(g->M > 0 && g->N > 0 && g->N <= 256 && g->batch == 1, "bgemm_bf16_norm: needs batch == 1 and N <= 256");
+  GP_REQUIRE(g->beta == 0.f && !g->relu && g->split_k <= 1 && g->lim == nullptr,
+             "bgemm_bf16_norm: beta / relu / split_k / lim are not supported");
+  GP_REQUIRE(rowstat == nullptr || (reinterpret_cast<uintptr_t>(rowstat) & 7) == 0, "bgemm_bf16_norm: rowstat alignment");
+  const gp_operand_pair& o = g->pair[0];
+  GP_REQUIRE(o.A && o.B && o.K > 0 && o.ldA % 8 == 0 && o.ldB % 8 == 0, "bgemm_bf16_norm: bad operand");
+  GP_REQUIRE((reinterpret_cast<uintptr_t>(o.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(o.B) & 15) == 0,
+             "bgemm_bf16_norm: operand base must be 16-byte aligned");
+  Maps maps;
+  Params p;
+  const int BN = g->N > 128 ? 256 : 128;
+  if (o.a_major == 0) GP_TRY(make_map(&maps.a[0], o.A, o.K, g->M, 1, o.ldA, o.sAb, BM));
+  else                GP_TRY(make_map(&maps.a[0], o.A, g->M, o.K, 1, o.ldA, o.sAb, BK));
+  if (o.b_major == 0) GP_TRY(make_map(&maps.b[0], o.B, o.K, g->N, 1, o.ldB, o.sBb, BN));
+  else                GP_TRY(make_map(&maps.b[0], o.B, g->N, o.K, 1, o.ldB, o.sBb, BK));
+  p.K[0] = o.K; p.a_mn[0] = o.a_major; p.b_mn[0] = o.b_major; p.lim_k[0] = 0;
+  for (int q = 1; q < kMaxPairs; ++q) { maps.a[q] = maps.a[0]; maps.b[q] = maps.b[0]; p.K[q] = 0; p.a_mn[q] = p.b_mn[q] = p.lim_k[q] = 0; }
+  p.C = g->C; p.Cb = reinterpret_cast<__nv_bfloat16*>(g->Cb);
+  p.M = g->M; p.N = g->N; p.batch = 1;
+  p.ldC = g->ldC; p.sCb = 0; p.ldCb = g->ldCb; p.sCbb = 0;
+  p.lim = nullptr; p.lim_m = p.lim_n = 0;
+  p.alpha = g->alpha; p.beta = 0.f; p.alpha_dev = g->alpha_dev; p.bias = g->bias; p.relu = 0; p.split_k = 0; p.npairs = 1;
+  p.adjb = nullptr; p.ldadj = p.sadjb = 0; p.partial = nullptr;
+  p.rnorm = rnorm; p.rowstat = reinterpret_cast<float2*>(rowstat); p.stat_relu = stat_relu;
+  if (BN == 256) return launch<256, 3, 2, 4>(maps, p, st);
+  return launch<128, 4, 2, 4>(maps, p, st);
 }
 
 int run_linkloss(const void* s_bf16, long long lds, const void* adj_bf16, long long ldadj, const int32_t* nb,
@@ -700,11 +827,17 @@ int run_linkloss(const void* s_bf16, long long lds, const void* adj_bf16, long l
   p.alpha = 1.f; p.beta = 0.f; p.alpha_dev = nullptr; p.bias = nullptr; p.relu = 0; p.split_k = 0;
   p.adjb = reinterpret_cast<const __nv_bfloat16*>(adj_bf16); p.ldadj = ldadj; p.sadjb = (long long)N * ldadj;
   p.partial = partial;
+  p.rnorm = nullptr; p.rowstat = nullptr; p.stat_relu = 0;
   return launch<256, 3, 1, kLinkEW>(maps, p, st);
 }
 
 }  // namespace v2
 }  // namespace gp
+
+extern "C" int gp_bgemm_bf16_norm(const gp_gemm_bf16x* g, float* rnorm, float* rowstat, int stat_relu,
+                                  gp_stream_t stream) {
+  return gp::v2::run_norm(g, rnorm, rowstat, stat_relu, gp::S(stream));
+}
 
 extern "C" int gp_bgemm_bf16x(const gp_gemm_bf16x* g, gp_stream_t stream) {
   return gp::v2::run(g, gp::S(stream));

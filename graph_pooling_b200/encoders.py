@@ -64,13 +64,15 @@ def _fwd_tc(ctx, plan, x, adj, assign_x, params):
         for i in range(P):
             K = plan.assign_dims[i]
             wa, ba = conv(plan.assign[i])
-            za, zab, c_as = T.stack_forward(ws, xab, xa_d, cur_adjb, cur_nb, B, cur_N, wa, ba, True)
+            # level 0 with assign_x == x: both GCNs start from the same U = A.x -- compute it once
+            u0 = c_emb.layers[0][4] if (i == 0 and xab is xb) else None
+            za, zab, c_as = T.stack_forward(ws, xab, xa_d, cur_adjb, cur_nb, B, cur_N, wa, ba, True, u0=u0)
             Fa = za.shape[2]
             wp, bp = _wb(params, plan.assign_pred[i])
             Tl, wpb = T.assign_linear_fwd(ws, zab, Fa, B * cur_N, wp, bp)
             S = Tl.view(B, cur_N, K)
-            call('gp_softmax_mask_fwd', S.data_ptr(), E._p(cur_nb), B, cur_N, K, st)
-            sb, xp, xpb, tb, ap, apb = T.pool_forward(ws, S, cur_zb, cur_adjb, cur_nb, B, cur_N, K, Fw)
+            sb = T.softmax_forward(ws, S, cur_nb, B, cur_N, K)
+            sb, xp, xpb, tb, ap, apb = T.pool_forward(ws, sb, cur_zb, cur_adjb, cur_nb, B, cur_N, K, Fw)
             wq, bq = conv(plan.post[i])
             z2, z2b, c_post = T.stack_forward(ws, xpb, Fw, apb, None, B, K, wq, bq, plan.bn_post)
             call('gp_readout_max_fwd', z2.data_ptr(), Fw, None, B, K, Fw, out.data_ptr() + (i + 1) * Fw * 4,
@@ -132,9 +134,8 @@ def _bwd_tc(ctx, tape, dypred, dS0):
                 ds, acc_ds = ws.f(B, Ni, K), 0
             dz = T.pool_backward(ws, dxp, d_ap[i], lv['sb'], lv['zb'], lv['adjb'], lv['tb'], lv['nb'], B, Ni, K, Fw,
                                  ds, acc_ds, None if i == 0 else d_ap[i - 1])
-            dt = ws.f(B, Ni, K)
-            call('gp_softmax_mask_bwd', lv['S'].data_ptr(), ds.data_ptr(), E._p(lv['nb']), B, Ni, K, dt.data_ptr(), st)
-            dwp, dbp, dza = T.assign_linear_bwd(ws, dt, lv['zab'], lv['Fa'], B * Ni, lv['wpb'], K, lv['has_bp'])
+            dwp, dbp, dza = T.assign_head_bwd(ws, lv['S'], ds, lv['nb'], B, Ni, lv['zab'], lv['Fa'], lv['wpb'], K,
+                                              lv['has_bp'])
             iw, ib = plan.assign_pred[i]
             grads[iw] = dwp
             if ib is not None:

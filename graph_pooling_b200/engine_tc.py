@@ -95,8 +95,31 @@ class StackCtxTC:
     pass
 
 
-def stack_forward(ws, xb, din, adjb, nb, B, N, weights, biases, bn):
+def _norm_gemm(A, Bo, M, N, K, bias, Cf, Cb, rnorm, rowstat, stat_relu):
+    """V = A.B + bias, Y = V / max(||V||, eps) in the GEMM epilogue (gp_bgemm_bf16_norm); A K-major, B N-major."""
+    g = GpGemmBf16x()
+    g.npairs = 1
+    pr = g.pair[0]
+    pr.A, pr.B, pr.K = A.ptr, Bo.ptr, K
+    pr.ldA, pr.sAb, pr.a_major = A.ld, 0, KM
+    pr.ldB, pr.sBb, pr.b_major = Bo.ld, 0, MN
+    pr.lim_k = 0
+    cp, cld, _ = Cf if Cf is not None else (None, 0, 0)
+    g.C, g.Cb = cp, (None if Cb is None else Cb.ptr)
+    g.M, g.N, g.batch = M, N, 1
+    g.ldC, g.sCb = cld, 0
+    g.ldCb, g.sCbb = (0, 0) if Cb is None else (Cb.ld, 0)
+    g.lim, g.lim_m, g.lim_n = None, 0, 0
+    g.alpha, g.beta, g.alpha_dev = 1.0, 0.0, None
+    g.bias, g.relu, g.split_k = bias, 0, 0
+    call('gp_bgemm_bf16_norm', C.byref(g), rnorm, rowstat, int(stat_relu), E._stream())
+
+
+def stack_forward(ws, xb, din, adjb, nb, B, N, weights, biases, bn, u0=None):
     """TC version of engine.stack_forward (add_self unsupported).  xb/adjb: bf16 operands.
+    Per layer:  U = A.X (tcgen05)  ->  Y = normalize(U.W + b) with the row norm and the BatchNorm row sums
+    taken in the GEMM epilogue  ->  H = BN(relu(Y)) written once as fp32 (concat slot) and bf16 (next operand).
+    u0: optional precomputed U of the first layer (shared with another stack that has the same A and X).
     Returns (zcat fp32 [B,N,F], zb bf16 operand of the same concat, ctx)."""
     st = E._stream()
     L = len(weights)
@@ -113,39 +136,58 @@ def stack_forward(ws, xb, din, adjb, nb, B, N, weights, biases, bn):
     lim = int(nb is not None)
     cur, cur_d = xb, din
     zp = zcat.data_ptr()
+    rows = B * N
     for l in range(L):
         last = l == L - 1
         dout, off = douts[l], offs[l]
         w = weights[l]
         wb = cvt(ws, w.data_ptr(), dout, cur_d, dout)                                   # [din, r8(dout)]
-        ub = bfbuf(ws, B, N, cur_d)
-        # U = A.X : A K-major, X N-major
-        tcgemm(adjb, KM, cur, MN, N, cur_d, N, B, Cb=ub, lim=nbp, lim_m=lim, lim_k=lim)
+        if l == 0 and u0 is not None:
+            ub = u0
+        else:
+            ub = bfbuf(ws, B, N, cur_d)
+            # U = A.X : A K-major, X N-major
+            tcgemm(adjb, KM, cur, MN, N, cur_d, N, B, Cb=ub, lim=nbp, lim_m=lim, lim_k=lim)
         slot = zp + off * 4
+        # bf16 operand copy of this layer's output: a column slot of zb when 16-byte aligned, else its own buffer
+        hb = Op(zb.ptr + off * 2, zb.ld, zb.sb, zb.t) if aligned else bfbuf(ws, B, N, dout)
+        hb_flat = Op(hb.ptr, hb.ld, 0)
         if last:
             y, y_ptr, ldy = None, slot, Fw
         else:
             y = ws.f(B, N, dout)
             y_ptr, ldy = y.data_ptr(), dout
-        # V = U.W + b (rows flattened): U K-major, W N-major
-        uflat = Op(ub.ptr, ub.ld, 0)
-        tcgemm(uflat, KM, Op(wb.ptr, wb.ld, 0), MN, B * N, dout, cur_d, 1, Cf=(y_ptr, ldy, 0), bias=E._p(biases[l]))
         rnorm = ws.f(B, N)
-        call('gp_bias_normalize_f32', y_ptr, None, rnorm.data_ptr(), C.c_longlong(B * N), dout, ldy, 1, st)
+        use_bn = bool(bn and not last)
+        uflat, wflat = Op(ub.ptr, ub.ld, 0), Op(wb.ptr, wb.ld, 0)
         mean = invstd = None
-        if not last:
-            if bn:
+        if dout <= 256:
+            rowstat = ws.f(rows, 2) if use_bn else None
+            _norm_gemm(uflat, wflat, rows, dout, cur_d, E._p(biases[l]), (y_ptr, ldy, 0), hb_flat if last else None,
+                       rnorm.data_ptr(), E._p(rowstat), 1)
+            if use_bn:
                 mean, invstd = ws.f(N), ws.f(N)
-            call('gp_relu_bn_fwd', y_ptr, slot, Fw, E._p(mean), E._p(invstd), B, N, dout, 1, int(bn), st)
-        if aligned:
-            hb = Op(zb.ptr + off * 2, zb.ld, zb.sb, zb.t)
-            cvt(ws, slot, Fw, B * N, dout, out=Op(hb.ptr, zb.ld, zb.sb))
+                call('gp_bn_finalize', rowstat.data_ptr(), B, N, dout, mean.data_ptr(), invstd.data_ptr(), st)
+            if not last:
+                call('gp_bn_apply', y_ptr, ldy, E._p(mean), E._p(invstd), B, N, dout, 1, int(use_bn), slot, Fw,
+                     hb.ptr, hb.ld, st)
         else:
-            hb = cvt(ws, slot, Fw, B * N, dout, B=B)
+            # wide layer (e.g. the assignment GCN's last layer, dout = K): plain GEMM, then one normalize pass
+            tcgemm(uflat, KM, wflat, MN, rows, dout, cur_d, 1, Cf=(y_ptr, ldy, 0), bias=E._p(biases[l]))
+            yb_ok = dout % 4 == 0 and dout <= 1024 and ldy % 4 == 0
+            call('gp_bias_normalize_x', y_ptr, None, rnorm.data_ptr(), C.c_longlong(rows), dout, ldy, 1,
+                 hb.ptr if (last and yb_ok) else None, hb.ld, st)
+            if last and not yb_ok:
+                cvt(ws, slot, Fw, rows, dout, out=hb_flat)
+            if not last:
+                if use_bn:
+                    mean, invstd = ws.f(N), ws.f(N)
+                call('gp_relu_bn_fwd', y_ptr, slot, Fw, E._p(mean), E._p(invstd), B, N, dout, 1, int(use_bn), st)
+                cvt(ws, slot, Fw, rows, dout, out=hb_flat)
         ctx.layers.append((cur, cur_d, dout, off, ub, y, rnorm, mean, invstd, wb))
         cur, cur_d = hb, dout
     if not aligned:
-        cvt(ws, zp, Fw, B * N, Fw, out=zb)
+        cvt(ws, zp, Fw, rows, Fw, out=zb)
     return zcat, zb, ctx
 
 
@@ -208,9 +250,19 @@ def stack_backward(ws, ctx, dz_ptr, lddz, dout_ptr, arg_ptr, ldo, need_dx, dadj)
 
 
 # ------------------------------------------------------------------------------------------
-def pool_forward(ws, S, zb, adjb, nb, B, N, K, Fw):
+def softmax_forward(ws, S, nb, B, N, K):
+    """In-place masked softmax (encoders.py:1273-1275) that also emits the bf16 operand copy of S."""
+    sb = bfbuf(ws, B, N, K)
+    if K % 4 == 0 and K <= 1024:
+        call('gp_softmax_mask_fwd_x', S.data_ptr(), E._p(nb), B, N, K, sb.ptr, sb.ld, E._stream())
+    else:
+        call('gp_softmax_mask_fwd', S.data_ptr(), E._p(nb), B, N, K, E._stream())
+        cvt(ws, S.data_ptr(), K, B * N, K, out=Op(sb.ptr, sb.ld, 0))
+    return sb
+
+
+def pool_forward(ws, sb, zb, adjb, nb, B, N, K, Fw):
     nbp, lim = E._p(nb), int(nb is not None)
-    sb = cvt(ws, S.data_ptr(), K, B * N, K, B=B)
     xp, xpb = ws.f(B, K, Fw), bfbuf(ws, B, K, Fw)
     tcgemm(sb, MN, zb, MN, K, Fw, N, B, Cf=(xp.data_ptr(), Fw, K * Fw), Cb=xpb, lim=nbp, lim_k=lim)
     tb = bfbuf(ws, B, K, N)
@@ -248,17 +300,27 @@ def assign_linear_fwd(ws, zab, Fa, rows, wp, bp):
     return T, wpb
 
 
-def assign_linear_bwd(ws, dt, zab, Fa, rows, wpb, K, has_bias):
+def assign_head_bwd(ws, S, ds, nb, B, N, zab, Fa, wpb, K, has_bias):
+    """Backward of S = softmax(assign_pred(za)) * mask: dT (bf16 operand + bias gradient in one pass), then
+    dWp = dT^T za (split-K) and dza = dT Wp."""
     st = E._stream()
-    dtb = cvt(ws, dt.data_ptr(), K, rows, K)
+    rows = B * N
+    dtb = bfbuf(ws, 1, rows, K)
+    dbp = ws.f(K) if has_bias else None
+    if K % 4 == 0 and K <= 512:
+        wsb = ws.f((148 * 16 + 256) * K) if has_bias else None
+        call('gp_softmax_mask_bwd_x', S.data_ptr(), ds.data_ptr(), E._p(nb), B, N, K, None, dtb.ptr, dtb.ld,
+             E._p(dbp), E._p(wsb), st)
+    else:
+        dt = ws.f(B, N, K)
+        call('gp_softmax_mask_bwd', S.data_ptr(), ds.data_ptr(), E._p(nb), B, N, K, dt.data_ptr(), st)
+        cvt(ws, dt.data_ptr(), K, rows, K, out=dtb)
+        if has_bias:
+            cs = ws.f(256 * K)
+            call('gp_colsum_f32', E._p(dt), C.c_longlong(rows), K, C.c_longlong(K), E._p(dbp), 0, E._p(cs), st)
     dwp = ws.f(K, Fa)
     tcgemm(Op(dtb.ptr, dtb.ld, 0), MN, Op(zab.ptr, zab.ld, 0), MN, K, Fa, rows, 1, Cf=(dwp.data_ptr(), Fa, 0),
            split_k=pick_split(K, Fa, rows))
-    dbp = None
-    if has_bias:
-        dbp = ws.f(K)
-        cs = ws.f(256 * K)
-        call('gp_colsum_f32', E._p(dt), C.c_longlong(rows), K, C.c_longlong(K), E._p(dbp), 0, E._p(cs), st)
     dza = ws.f(rows, Fa)
     tcgemm(Op(dtb.ptr, dtb.ld, 0), KM, Op(wpb.ptr, wpb.ld, 0), MN, rows, Fa, K, 1, Cf=(dza.data_ptr(), Fa, 0))
     return dwp, dbp, dza

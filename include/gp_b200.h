@@ -128,6 +128,26 @@ typedef struct gp_gemm_bf16x {
   int split_k;
 } gp_gemm_bf16x;
 int gp_bgemm_bf16x(const gp_gemm_bf16x* g, gp_stream_t stream);
+/* Fused GraphConv tail on tensor cores (encoders.py:322-326): one operand pair, batch == 1, N <= 256:
+ *   V = alpha * A.B + bias ;  Y = V / max(||V||_2, 1e-12) per row  -> C (fp32) and/or Cb (bf16)
+ *   rnorm[M] (optional) = the divisor;  rowstat[M][2] (optional) = (sum_c r, sum_c r^2) with r = relu(Y) if
+ *   stat_relu else Y: the per-row sums from which gp_bn_finalize derives the BatchNorm-per-node statistics
+ *   (encoders.py:1062-1064) without another pass over Y. */
+int gp_bgemm_bf16_norm(const gp_gemm_bf16x* g, float* rnorm, float* rowstat, int stat_relu, gp_stream_t stream);
+/* mean[n], invstd[n] over (batch, feature) from rowstat[b*N + n] (biased variance, eps 1e-5). */
+int gp_bn_finalize(const float* rowstat, int B, int N, int d, float* mean, float* invstd, gp_stream_t stream);
+/* H[b,n,:] = (relu?(Y[b,n,:]) - mean[n]) * invstd[n] -> fp32 h (row stride ldh) and/or bf16 copy. */
+int gp_bn_apply(const float* y, long long ldy, const float* mean, const float* invstd, int B, int N, int d,
+                int relu, int bn, float* h, long long ldh, void* h_bf16, long long ldhb, gp_stream_t stream);
+/* gp_bias_normalize_f32 / gp_softmax_mask_fwd / _bwd with the bf16 operand copy written in the same pass;
+ * softmax backward can also return dcol = colsum(dT) (the assign_pred bias gradient, encoders.py:1273);
+ * ws >= (148*16 + 256) * K floats. */
+int gp_bias_normalize_x(float* v, const float* bias, float* rnorm, long long rows, int d, long long ld,
+                        int normalize, void* y_bf16, long long ldyb, gp_stream_t stream);
+int gp_softmax_mask_fwd_x(float* t, const int32_t* nb, int B, int N, int K, void* s_bf16, long long ldsb,
+                          gp_stream_t stream);
+int gp_softmax_mask_bwd_x(const float* s, const float* ds, const int32_t* nb, int B, int N, int K, float* dt,
+                          void* dt_bf16, long long lddtb, float* dcol, float* ws, gp_stream_t stream);
 /* y[r, 0:cols_pad] = bf16(x[r, 0:cols]) zero-padded to cols_pad (row strides ldx / ldy in elements) */
 int gp_cvt_f32_bf16(const float* x, long long ldx, void* y, long long ldy, long long rows, int cols,
                     int cols_pad, gp_stream_t stream);
