@@ -183,22 +183,17 @@ def main():
     x, adj, nb, label = batch['x'], batch['adj'], batch['nb'], batch['label']
     B = x.shape[0]
 
-    def allreduce_grads():
-        if world == 1:
-            return
-        flat = torch._utils._flatten_dense_tensors([p.grad for p in params])
-        dist.all_reduce(flat)
-        flat.div_(world)
-        for p, g in zip(params, torch._utils._unflatten_dense_tensors(flat, [p.grad for p in params])):
-            p.grad.copy_(g)
+    # gradients live in ONE flat buffer (dp.FlatGradients): the all-reduce and the clip need no gather copies
+    from graph_pooling_b200 import dp
+    flat = dp.FlatGradients(params)
 
     def step(xd, ad, ld):
-        model.zero_grad()
+        flat.zero()
         yp = model(xd, ad, nb, assign_x=xd) if soft else model(xd, ad, nb)
         loss = model.loss(yp, ld, ad, nb) if soft else model.loss(yp, ld)
         loss.backward()
-        allreduce_grads()
-        torch.nn.utils.clip_grad_norm_(params, 2.0)
+        flat.all_reduce(average=True)                # one NCCL all-reduce per step (no-op at world == 1)
+        flat.clip_(2.0)                              # train.py:209
         opt.step()
         return loss
 
@@ -305,22 +300,55 @@ def main():
     kfl, kby = roofline.ax_kernel_work(nb, H, elt=2 if prec == 'bf16' else 4)
     ai = kfl / kby
     ridge = tf_sus * 1e12 / (hbm * 1e9)
-    if ai >= ridge or cfg['N'] >= 1024:
+    # the dominant launch of the step (12 of ~160 launches, ~22 % of the step's device time, the largest single
+    # shape): at din=128 columns its arithmetic intensity (~128 flop/B in bf16) is BELOW the ridge -> HBM-bound
+    if ai >= ridge:
         roof = {'bound': 'tensor', 'achieved': kfl / (kms * 1e-3) / 1e12, 'peak': tf_burst, 'unit': 'TFLOP/s'}
     else:
         roof = {'bound': 'hbm', 'achieved': kby / (kms * 1e-3) / 1e9, 'peak': hbm, 'unit': 'GB/s'}
     roof['frac'] = roof['achieved'] / roof['peak']
-    roof['traffic'] = None
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
+    tj = json.load(open(tpath)) if os.path.exists(tpath) else {}
+    if prec == 'bf16' and args.workload == 'cfg4_diffpool_256x2048' and B == 256 and 'ax_gemm' in tj:
+        traffic = tj['ax_gemm']['dram_bytes_per_launch']           # ncu --set full, same shape (profiles/)
+    roof['traffic'] = traffic
+    roof['algorithmic_bytes_per_launch'] = kby
+    roof['algorithmic_flops_per_launch'] = kfl
+    roof['arithmetic_intensity_flop_per_byte'] = ai
     roof['kernel'] = '%s (U = A.X, N=%d, din=%d, batch=%d)' % (
-        'tc_gemm_kernel<128,3,K-major,N-major> tcgen05' if prec == 'bf16' else 'bgemm_kernel FFMA', N, H, B)
+        'gp::v2::tc_gemm2_kernel<128,6,0,8> tcgen05+TMA persistent' if prec == 'bf16' else 'gp::bgemm_kernel FFMA',
+        N, H, B)
     roof['ms_per_launch'] = kms
-    roof['peak_source'] = src + (' burst (kernel timed alone)' if roof['bound'] == 'tensor' else '')
+    roof['tflops'] = kfl / (kms * 1e-3) / 1e12
+    roof['peak_source'] = src + ' (MEASURED_PEAKS.json; kernel timed alone -> burst figures)'
     fwd_fl, bwd_fl = roofline.step_flops(nb, cfg)
     roof['step_algorithmic_tflop'] = (fwd_fl + bwd_fl) / 1e12
     roof['step_tflops'] = (fwd_fl + bwd_fl) / (ms_per_step * 1e-3) / 1e12
     roof['step_frac_of_sustained_bf16'] = roof['step_tflops'] / tf_sus
     roof['step_algorithmic_gb'] = roofline.step_bytes(nb, cfg) / 1e9
     roof['step_gbs'] = roof['step_algorithmic_gb'] / (ms_per_step * 1e-3)
+    # the large-N tensor-bound contraction of the pooling step, T = S^T A (encoders.py:1279), timed live too
+    if prec == 'bf16' and soft:
+        K0 = int(N * cfg['ratio'])
+        sprob = torch.rand(B, N, K0, device=dev).bfloat16()
+        sop = T.Op(sprob.data_ptr(), K0, N * K0, sprob)
+        tbuf = T.bfbuf(wsb, B, K0, N)
+
+        def tsa():
+            T.tcgemm(sop, T.MN, adjb, T.MN, K0, N, N, B, Cb=tbuf, lim=nbd.data_ptr(), lim_k=1, lim_n=1)
+        for _ in range(3):
+            tsa()
+        tms = timed_local(tsa, reps) / reps
+        nbf = np.asarray(nb, dtype=np.float64)
+        tfl = float(np.sum(2.0 * K0 * nbf * nbf))
+        roof['tensor_contraction'] = {
+            'kernel': 'gp::v2::tc_gemm2_kernel<256,4,0,8> (T = S^T.A, K=%d, N=%d, batch=%d)' % (K0, N, B),
+            'bound': 'tensor', 'achieved': tfl / (tms * 1e-3) / 1e12, 'peak': tf_burst, 'unit': 'TFLOP/s',
+            'frac': tfl / (tms * 1e-3) / 1e12 / tf_burst, 'ms_per_launch': tms,
+            'traffic': tj.get('tsa_gemm', {}).get('dram_bytes_per_launch') if (B == 256 and N == 2048) else None,
+            'ncu_tensor_pipe_active_pct': tj.get('tsa_gemm', {}).get('tensor_pipe_active_pct')}
+        del sprob, tbuf
 
     # ---- CPU baseline (oracle port) on this box's host cores -----------------------------------
     cpu = None

@@ -5,7 +5,7 @@
 namespace gp {
 
 thread_local char g_err[512] = "";
-thread_local long long g_launches = 0;
+std::atomic<long long> g_launches{0};
 
 int bgemm_f32(const gp_gemm& g, cudaStream_t st);
 int bias_normalize(float* v, const float* bias, float* rnorm, long long rows, int d, long long ld,
@@ -37,8 +37,8 @@ using namespace gp;
 
 extern "C" int gp_version(void) { return 100; }
 extern "C" const char* gp_last_error(void) { return g_err; }
-extern "C" long long gp_launch_count(void) { return g_launches; }
-extern "C" void gp_launch_count_reset(void) { g_launches = 0; }
+extern "C" long long gp_launch_count(void) { return g_launches.load(); }
+extern "C" void gp_launch_count_reset(void) { g_launches.store(0); }
 
 extern "C" int gp_graphconv_fwd(const float* x, long long ldx, const float* adj, const float* w, const float* bias,
                                 const int32_t* nb, int B, int N, int din, int dout, int add_self, int normalize,

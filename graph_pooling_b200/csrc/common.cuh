@@ -4,12 +4,13 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <atomic>
 #include "../../include/gp_b200.h"
 
 namespace gp {
 
 extern thread_local char g_err[512];
-extern thread_local long long g_launches;
+extern std::atomic<long long> g_launches;   // process-wide: autograd runs the backward on its own thread
 
 inline int fail(int code, const char* fmt, ...) {
   va_list ap; va_start(ap, fmt);

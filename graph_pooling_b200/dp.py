@@ -1,0 +1,133 @@
+"""Data-parallel training of the DiffPool encoders: one process per GPU, graphs sharded across ranks, ONE
+all-reduce of a flat fp32 gradient buffer per step (NCCL over NVLink on the GPUs; gloo in the CPU tests).
+Nothing else crosses GPUs: BatchNorm statistics stay shard-local, exactly as the reference
+run on that shard would compute them (encoders.py:1048-1052).
+
+Two loss conventions:
+  'shard_mean'   every rank computes the reference loss of its own shard (CE mean over the shard, link loss
+                 normalised by the shard's sum of n_b^2, encoders.py:1127,1326-1331); gradients are AVERAGED.
+                 G ranks == the mean of G single-GPU reference runs on the shards.
+  'global_norm'  the loss is that of the whole batch: CE weighted by shard_size / global_batch and the link
+                 loss normalised by the GLOBAL sum of n_b^2 (every rank knows all n_b on the host);
+                 gradients are SUMMED.
+
+Parameter gradients live as views of one flat buffer, so the collective needs no gather / scatter copies, and
+gradient clipping (train.py:209) uses the norm of the reduced buffer, which every rank holds: no second
+collective.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_items, world, rank):
+    """Contiguous, balanced shard [lo, hi) of `n_items` for `rank` (first n_items % world ranks get one more)."""
+    base, extra = divmod(int(n_items), int(world))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_batch(rank, world, x, adj, batch_num_nodes, label, assign_x=None):
+    """Slice one global padded batch (train.py:197-201 tensors) into this rank's shard."""
+    lo, hi = shard_bounds(x.shape[0], world, rank)
+    nb = None if batch_num_nodes is None else np.asarray(batch_num_nodes)[lo:hi]
+    out = dict(x=x[lo:hi], adj=adj[lo:hi], nb=nb, label=label[lo:hi])
+    out['assign_x'] = None if assign_x is None else assign_x[lo:hi]
+    return out
+
+
+class FlatGradients:
+    """One contiguous fp32 buffer holding every parameter's gradient (p.grad are views into it)."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError('no trainable parameters')
+        dev, dt = self.params[0].device, self.params[0].dtype
+        n = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(n, device=dev, dtype=dt)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero(self):
+        self.flat.zero_()
+        off = 0
+        for p in self.params:                       # re-attach if someone replaced / dropped p.grad
+            if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + off * self.flat.element_size():
+                p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def all_reduce(self, group=None, average=True):
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if world > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            if average:
+                self.flat.div_(world)
+        return self.flat
+
+    def clip_(self, max_norm):
+        """torch.nn.utils.clip_grad_norm_ semantics on the (already reduced) flat buffer; returns the norm."""
+        norm = self.flat.norm(2)
+        coef = torch.clamp(max_norm / (norm + 1e-6), max=1.0)
+        self.flat.mul_(coef)
+        return norm
+
+
+class DataParallelTrainer:
+    """Runs train.py:196-210 (zero_grad -> forward -> loss -> backward -> clip -> optimizer step) on this rank's
+    shard and synchronises gradients with one all-reduce.  `model` is one of the drop-in encoders (or any module
+    with the same forward / loss signatures, e.g. the oracle in the CPU tests)."""
+
+    def __init__(self, model, optimizer=None, clip=2.0, mode='shard_mean', group=None, linkpred=True):
+        if mode not in ('shard_mean', 'global_norm'):
+            raise ValueError("mode must be 'shard_mean' or 'global_norm'")
+        self.model, self.optimizer, self.clip, self.mode, self.group = model, optimizer, clip, mode, group
+        self.linkpred = linkpred
+        self.grads = FlatGradients(model.parameters())
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def broadcast_parameters(self, src=0):
+        if self.world > 1:
+            for p in self.model.parameters():
+                dist.broadcast(p.data, src=src, group=self.group)
+
+    def _loss(self, ypred, label, adj, nb, global_nb, global_batch):
+        m = self.model
+        soft = hasattr(m, 'num_pooling') and getattr(m, 'linkpred', False) and self.linkpred
+        if self.mode == 'shard_mean' or self.world == 1:
+            return m.loss(ypred, label, adj, nb) if soft else m.loss(ypred, label)
+        ce_scale = float(ypred.shape[0]) / float(global_batch)
+        if not soft:
+            return m.loss(ypred, label) * ce_scale
+        g64 = np.asarray(global_nb).astype(np.int64)
+        entries_global = int(np.sum(g64 * g64))
+        if hasattr(m, 'set_loss_scaling'):             # CUDA encoders: folded into the loss kernels' scalars
+            m.set_loss_scaling(ce_scale, entries_global)
+            try:
+                return m.loss(ypred, label, adj, nb)
+            finally:
+                m.set_loss_scaling(1.0, None)
+        total = m.loss(ypred, label, adj, nb)           # generic module: total = CE + link (both differentiable)
+        l64 = np.asarray(nb).astype(np.int64)
+        link = m.link_loss
+        return (total - link) * ce_scale + link * (float(np.sum(l64 * l64)) / float(entries_global))
+
+    def step(self, x, adj, batch_num_nodes, label, assign_x=None, global_num_nodes=None, global_batch=None):
+        """One training step on this rank's shard.  global_num_nodes / global_batch: every rank's n_b (host) and
+        the global batch size; needed by mode='global_norm' only.  Returns (ypred, loss) of the shard."""
+        self.grads.zero()
+        kw = {} if assign_x is None else {'assign_x': assign_x}
+        ypred = self.model(x, adj, batch_num_nodes, **kw)
+        if self.mode == 'global_norm' and self.world > 1 and (global_num_nodes is None or global_batch is None):
+            raise ValueError("mode='global_norm' needs global_num_nodes and global_batch")
+        loss = self._loss(ypred, label, adj, batch_num_nodes, global_num_nodes, global_batch)
+        loss.backward()
+        self.grads.all_reduce(self.group, average=(self.mode == 'shard_mean'))
+        if self.clip is not None:
+            self.grads.clip_(self.clip)
+        if self.optimizer is not None:
+            self.optimizer.step()
+        return ypred, loss

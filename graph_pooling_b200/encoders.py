@@ -316,6 +316,9 @@ class _LossFn(torch.autograd.Function):
             raise ValueError('label must be a CUDA int64 tensor')
         ce, probs = ws.f(1), ws.f(B, Cc)
         call('gp_ce_fwd', ypred.data_ptr(), label.data_ptr(), B, Cc, ce.data_ptr(), probs.data_ptr(), st)
+        ctx.ce_scale = float(getattr(plan, 'ce_scale', 1.0))
+        if ctx.ce_scale != 1.0:                      # data-parallel CE weight shard_size / global_batch (dp.py)
+            call('gp_axpy_f32', ce.data_ptr(), ce.data_ptr(), C.c_longlong(1), C.c_float(ctx.ce_scale - 1.0), st)
         ctx.probs, ctx.label, ctx.B, ctx.C = probs, label, B, Cc
         ctx.link = S is not None
         if S is None:
@@ -349,6 +352,8 @@ class _LossFn(torch.autograd.Function):
         g = E._chk(g, 'grad of loss')
         dy = ws.f(ctx.B, ctx.C)
         call('gp_ce_bwd', ctx.probs.data_ptr(), ctx.label.data_ptr(), g.data_ptr(), ctx.B, ctx.C, dy.data_ptr(), st)
+        if ctx.ce_scale != 1.0:
+            call('gp_axpy_f32', dy.data_ptr(), dy.data_ptr(), C.c_longlong(dy.numel()), C.c_float(ctx.ce_scale - 1.0), st)
         dS = None
         if ctx.link and ctx.gsym is not None:
             S = ctx.S
@@ -444,6 +449,7 @@ class GcnEncoderGraph(nn.Module):
         self.num_layers = num_layers
         self.num_aggs = 1
         self.precision = E.F32
+        self._ce_scale, self._entries_override = 1.0, None
         self.bias = True
         if args is not None:
             self.bias = args.bias
@@ -559,8 +565,15 @@ class GcnEncoderGraph(nn.Module):
     def loss(self, pred, label, type='softmax'):
         if type != 'softmax':
             raise NotImplementedError("gp_b200: only type='softmax' is implemented (callers never pass 'margin')")
-        plan = getattr(self, '_plan', None) or _Plan()
+        plan = _Plan()
+        plan.ce_scale = self._ce_scale
         return _LossFn.apply(plan, pred, label, None, None)
+
+    def set_loss_scaling(self, ce_scale=1.0, num_entries=None):
+        """Data-parallel hook (dp.py, mode='global_norm'): weight of this shard's CE mean and the GLOBAL sum of
+        n_b^2 that normalises the link loss instead of the shard-local one (encoders.py:1326)."""
+        self._ce_scale = float(ce_scale)
+        self._entries_override = None if num_entries is None else int(num_entries)
 
 
 class GcnSet2SetEncoder(GcnEncoderGraph):
@@ -665,7 +678,9 @@ class SoftPoolingGcnEncoder(GcnEncoderGraph):
     def loss(self, pred, label, adj=None, batch_num_nodes=None, adj_hop=1):
         plan = self._plan
         if not self.linkpred:
-            return _LossFn.apply(plan, pred, label, None, None)
+            lp0 = _Plan()
+            lp0.ce_scale = self._ce_scale
+            return _LossFn.apply(lp0, pred, label, None, None)
         if adj_hop != 1:
             raise NotImplementedError('gp_b200: adj_hop > 1 is not implemented (callers never pass it)')
         adj = E._chk(adj, 'adj')
@@ -680,6 +695,9 @@ class SoftPoolingGcnEncoder(GcnEncoderGraph):
         else:
             n64 = nb_host.astype(np.int64)                                   # R11
             lp.num_entries = int(np.sum(n64 * n64))
+        if self._entries_override is not None:
+            lp.num_entries = self._entries_override
+        lp.ce_scale = self._ce_scale
         total, link = _LossFn.apply(lp, pred, label, S0, adj)
         self.link_loss = link
         return total

@@ -47,8 +47,8 @@ enum gp_precision {
 
 int gp_version(void);
 const char* gp_last_error(void);
-/* number of kernels launched by this library on this thread since the last reset (bench.py's
- * `gpu_launches`). */
+/* number of kernels launched by this library (all threads of the process: autograd runs the backward on
+ * its own thread) since the last reset (bench.py's `gpu_launches`). */
 long long gp_launch_count(void);
 void gp_launch_count_reset(void);
 

@@ -28,6 +28,11 @@ x = torch.randn(B, N, H, device=dev).bfloat16()
 if which in ('all', 'ax'):
     ub = T.bfbuf(ws, B, N, H)
     timeit('A.X  bf16 out', lambda: T.tcgemm(op(adj), 0, op(x), 1, N, H, N, B, Cb=ub), 2.0 * B * N * N * H, B * (N * N + 2 * N * H) * 2)
+if which in ('all', 'tsa'):
+    # pooling contraction T = S^T A (encoders.py:1279): M=K, N=N, k=N ; S M-major, A N-major
+    s_ = torch.rand(B, N, K, device=dev).bfloat16()
+    tb = T.bfbuf(ws, B, K, N)
+    timeit('T=S^T.A bf16 out', lambda: T.tcgemm(op(s_), 1, op(adj), 1, K, N, N, B, Cb=tb), 2.0 * B * K * N * N, B * (N * N + 2 * N * K) * 2)
 if which in ('all', 'uw'):
     u = torch.randn(1, B * N, H, device=dev).bfloat16(); w = torch.randn(1, H, H, device=dev).bfloat16()
     y = torch.empty(B * N, H, device=dev)

@@ -1,0 +1,50 @@
+"""CUDA side of the data-parallel path (dp.py): the loss-scaling hook of the drop-in encoders (CE weight
+shard_size / global_batch, link loss normalised by the GLOBAL sum of n_b^2) and the flat
+gradient buffer, on one GPU, against the oracle evaluating the same formula in fp64."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import rel_l2, synth_batch
+from oracle import diffpool_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def test_global_norm_shard_loss_and_flat_gradients():
+    from graph_pooling_b200 import dp, encoders
+    B, N, D, H, C = 6, 40, 5, 16, 3
+    x, adj, nb, label = synth_batch(4, B, N, D, 3, N, C, density=0.2)
+    torch.manual_seed(1)
+    mo = orc.SoftPoolingGcnEncoder(N, D, H, H, C, 3, H, assign_ratio=0.25)
+    mc = encoders.SoftPoolingGcnEncoder(N, D, H, H, C, 3, H, assign_ratio=0.25)
+    mc.load_state_dict(mo.state_dict())
+    mc, mo = mc.cuda(), mo.double()
+    # pretend this process is rank 1 of 2: its shard is graphs 3..5 of a global batch of 6
+    sh = dp.shard_batch(1, 2, torch.tensor(x), torch.tensor(adj), nb, torch.tensor(label))
+    ce_scale = 3.0 / 6.0
+    g64, l64 = nb.astype(np.int64), sh['nb'].astype(np.int64)
+    e_glob, e_loc = float(np.sum(g64 * g64)), float(np.sum(l64 * l64))
+
+    xo, ao = sh['x'].double(), sh['adj'].double()
+    yo = mo(xo, ao, sh['nb'], assign_x=xo)
+    tot = mo.loss(yo, sh['label'], ao, sh['nb'])
+    want = (tot - mo.link_loss) * ce_scale + mo.link_loss * (e_loc / e_glob)
+    want.backward()
+
+    tr = dp.DataParallelTrainer(mc, optimizer=None, clip=None, mode='global_norm')
+    tr.world = 2                                         # exercise the scaling branch without a process group
+    xc, ac, lc = sh['x'].cuda(), sh['adj'].cuda(), sh['label'].cuda()
+    tr.grads.zero()
+    yp = mc(xc, ac, sh['nb'], assign_x=xc)
+    loss = tr._loss(yp, lc, ac, sh['nb'], nb, B)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - want.item()) < 1e-5 * max(1.0, abs(want.item()))
+    assert mc._ce_scale == 1.0 and mc._entries_override is None        # hook restored
+    flat_ref = torch.cat([p.grad.reshape(-1) for p in mo.parameters()]).numpy()
+    assert rel_l2(tr.grads.flat.cpu().numpy(), flat_ref) < 2e-5
+    off = 0
+    for p in tr.grads.params:
+        assert p.grad.data_ptr() == tr.grads.flat.data_ptr() + off * 4
+        off += p.numel()
