@@ -331,8 +331,10 @@ def main():
     # the large-N tensor-bound contraction of the pooling step, T = S^T A (encoders.py:1279), timed live too
     if prec == 'bf16' and soft:
         K0 = int(N * cfg['ratio'])
-        sprob = torch.rand(B, N, K0, device=dev).bfloat16()
-        sop = T.Op(sprob.data_ptr(), K0, N * K0, sprob)
+        sop = T.bfbuf(wsb, B, N, K0)                       # row stride padded to 8 elements (TMA 16-byte rule)
+        sprob = sop.t
+        sprob.copy_(torch.rand(B, N, sprob.shape[2], device=dev))
+        sprob[:, :, K0:] = 0
         tbuf = T.bfbuf(wsb, B, K0, N)
 
         def tsa():

@@ -301,17 +301,24 @@ static int launch_bn(const LbArgs& a, int CS, int rpc, cudaStream_t st) {
   return GP_OK;
 }
 
+// full eligibility of one call for the vectorised kernels: shape AND pointer / stride alignment
+static bool fast_eligible(const gp_layer_bwd* q, int* CS_out) {
+  if (!al16(q->y) || q->ldy % 4 != 0) return false;
+  if (q->dz != nullptr && (!al16(q->dz) || q->lddz % 4 != 0)) return false;
+  if (q->dxn != nullptr && !al16(q->dxn)) return false;
+  if (q->dout != nullptr && (!al16(q->dout) || !al16(q->argidx) || q->ldo % 4 != 0)) return false;
+  if (q->h != nullptr && (!al16(q->h) || q->ldh % 4 != 0)) return false;
+  if (q->dv != nullptr && !al16(q->dv)) return false;
+  if (q->dv_bf16 != nullptr && ((reinterpret_cast<uintptr_t>(q->dv_bf16) & 7) != 0 || q->lddvb % 4 != 0)) return false;
+  if (q->bn && q->h == nullptr && q->mean == nullptr) return false;
+  return shape_fast(q->B, q->d, q->bn, CS_out);
+}
+
 int layer_bwd_fast(const gp_layer_bwd* q, cudaStream_t st, bool* handled) {
   *handled = false;
   const int d = q->d;
-  if (!al16(q->y) || q->ldy % 4 != 0) return GP_OK;
-  if (q->dz != nullptr && (!al16(q->dz) || q->lddz % 4 != 0)) return GP_OK;
-  if (q->dxn != nullptr && !al16(q->dxn)) return GP_OK;
-  if (q->dout != nullptr && (!al16(q->dout) || !al16(q->argidx) || q->ldo % 4 != 0)) return GP_OK;
-  if (q->h != nullptr && (!al16(q->h) || q->ldh % 4 != 0)) return GP_OK;
-  if (q->dv != nullptr && !al16(q->dv)) return GP_OK;
-  if (q->dv_bf16 != nullptr && ((reinterpret_cast<uintptr_t>(q->dv_bf16) & 7) != 0 || q->lddvb % 4 != 0)) return GP_OK;
-  if (q->bn && q->h == nullptr && q->mean == nullptr) return GP_OK;
+  int CS = 1;
+  if (!fast_eligible(q, &CS)) return GP_OK;
   LbArgs a;
   a.dz = q->dz; a.lddz = q->lddz; a.dxn = q->dxn; a.dout = q->dout; a.argidx = q->argidx; a.ldo = q->ldo;
   a.h = q->h; a.ldh = q->ldh; a.y = q->y; a.ldy = q->ldy; a.rnorm = q->rnorm; a.mean = q->mean; a.invstd = q->invstd;
@@ -319,8 +326,6 @@ int layer_bwd_fast(const gp_layer_bwd* q, cudaStream_t st, bool* handled) {
   a.dv = q->dv; a.dvb = reinterpret_cast<__nv_bfloat16*>(q->dv_bf16); a.lddvb = q->lddvb;
   a.part = q->db != nullptr ? q->ws : nullptr;
   long long part_rows = 0;
-  int CS = 1;
-  if (!shape_fast(q->B, d, q->bn, &CS)) return GP_OK;
   if (q->bn) {
     const int rstep = 256 / (d / 4);
     const int rpc = (q->B + CS - 1) / CS;
@@ -353,6 +358,16 @@ using namespace gp;
 
 extern "C" long long gp_gcn_layer_bwd_ws(int B, int N, int d, int bn) { return ws_floats(B, N, d, bn); }
 
+// exact workspace of ONE call (ws / db fields ignored): the generic kernel borrows an fp32 dV from ws when the
+// caller asked for the bias gradient without an fp32 dV and the operands miss the vectorised path's alignment.
+extern "C" long long gp_gcn_layer_bwd_ws_x(const gp_layer_bwd* q) {
+  if (q == nullptr) return 0;
+  long long f = ws_floats(q->B, q->N, q->d, q->bn);
+  if (shape_fast(q->B, q->d, q->bn, nullptr) && !fast_eligible(q, nullptr) && q->dv == nullptr)
+    f += (long long)q->B * q->N * q->d;
+  return f;
+}
+
 extern "C" int gp_gcn_layer_bwd_x(const gp_layer_bwd* q, gp_stream_t stream) {
   GP_REQUIRE(q != nullptr, "gcn_layer_bwd_x: null descriptor");
   GP_REQUIRE(q->y && (q->dv || q->dv_bf16) && q->B > 0 && q->N > 0 && q->d > 0, "gcn_layer_bwd_x: bad args");
@@ -363,8 +378,6 @@ extern "C" int gp_gcn_layer_bwd_x(const gp_layer_bwd* q, gp_stream_t stream) {
   bool handled = false;
   GP_TRY(layer_bwd_fast(q, S(stream), &handled));
   if (handled) return GP_OK;
-  if (q->dv == nullptr && q->db != nullptr && shape_fast(q->B, q->d, q->bn, nullptr))
-    return fail(GP_ERR_UNSUPPORTED, "gcn_layer_bwd_x: db without dv needs 16-byte aligned operands "
-                                    "(ws was sized for the vectorised path)");
+  // generic path: with db but no fp32 dV it borrows B*N*d floats from ws -- size ws with gp_gcn_layer_bwd_ws_x
   return layer_bwd_generic(q, S(stream));
 }

@@ -224,7 +224,9 @@ def stack_backward(ws, ctx, dz_ptr, lddz, dout_ptr, arg_ptr, ldo, need_dx, dadj)
         q.relu, q.bn, q.normalize = int(not last), int(use_bn), 1
         q.dv, q.dv_bf16, q.lddvb = None, dvb.ptr, dvb.ld
         q.db = E._p(db)
-        q.ws = E._p(ws.f(int(load().gp_gcn_layer_bwd_ws(B, N, dout, int(use_bn))))) if has_b else None
+        q.ws = None
+        wsf = ws.f(int(load().gp_gcn_layer_bwd_ws_x(C.byref(q)))) if has_b else None
+        q.ws = E._p(wsf)
         call('gp_gcn_layer_bwd_x', C.byref(q), st)
         # dW = U^T dV : U stored [rows, din] = M-major A ; dV N-major B ; split-K over the rows
         dw = ws.f(din, dout)

@@ -197,8 +197,8 @@ int gp_gcn_layer_bwd(const float* dz, long long lddz, const float* dxn, const fl
  * the saved statistics (h == NULL, mean != NULL) so the BN output need not be re-read.  16-byte aligned
  * inputs with d in {32, 64, 128} (bn) or d % 4 == 0, d <= 512 (no bn) take a single-pass vectorised kernel
  * (a thread-block cluster per node index, batch means reduced through distributed shared memory).
- * ws: gp_gcn_layer_bwd_ws(B, N, d, bn) floats, needed when db != NULL.  db without dv on a shape that
- * qualifies for the vectorised kernel requires the alignment above (GP_ERR_UNSUPPORTED otherwise). */
+ * ws: gp_gcn_layer_bwd_ws_x(q) floats, needed when db != NULL (gp_gcn_layer_bwd_ws(B, N, d, bn) is the
+ * shape-only bound, valid when every operand meets the alignment above or dv != NULL). */
 typedef struct gp_layer_bwd {
   const float* dz; long long lddz;
   const float* dxn;
@@ -212,6 +212,7 @@ typedef struct gp_layer_bwd {
 } gp_layer_bwd;
 int gp_gcn_layer_bwd_x(const gp_layer_bwd* q, gp_stream_t stream);
 long long gp_gcn_layer_bwd_ws(int B, int N, int d, int bn);
+long long gp_gcn_layer_bwd_ws_x(const gp_layer_bwd* q);
 
 /* ---------------------------------------------------------------------------------------------
  * Max readout (encoders.py:1097,1257,1287): out[b,f] = max_n Z[b,n,f], pad rows (n >= nb[b])

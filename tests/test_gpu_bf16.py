@@ -20,7 +20,10 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize('N,D,H,C,B,ratio,P,n_min,density', [
     (64, 8, 16, 3, 4, 0.25, 1, 16, 0.1), (256, 16, 32, 2, 4, 0.25, 1, 64, 0.05),
     (100, 3, 30, 6, 20, 0.1, 1, 2, 0.08), (512, 64, 64, 2, 3, 0.25, 1, 128, 0.02),
-    (200, 89, 24, 2, 3, 0.25, 2, 50, 0.05)])
+    (200, 89, 24, 2, 3, 0.25, 2, 50, 0.05),
+    # hidden width on the vectorised layer-backward path but concat strides that miss its alignment
+    # (Fa = 2*64+30 = 158, the cfg3 / cfg5 situation: K = 250 / 1250)
+    (120, 10, 64, 2, 3, 0.25, 2, 30, 0.05), (600, 12, 32, 2, 2, 0.25, 1, 40, 0.02)])
 def test_bf16_mode_bounds(N, D, H, C, B, ratio, P, n_min, density):
     from graph_pooling_b200 import encoders
     torch.manual_seed(N)
