@@ -92,7 +92,14 @@ _PROTOS = {
                     c_f, c_i, c_f],
     'gp_linkloss_fwd': [c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f, c_f],
     'gp_loss_finalize': [c_f, c_i, C.c_double, c_f, c_f, c_f, c_f],
-    'gp_linkloss_tc': [c_f, c_ll, c_f, c_ll, c_f, c_i, c_i, c_i, c_f, c_f, c_ll, c_f],
+    'gp_linkloss_tc': [c_f, c_ll, c_f, c_ll, c_f, c_i, c_i, c_i, c_f, c_f, c_ll, c_i, c_f],
+    'gp_frob_link_fwd': [c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f, c_f],
+    'gp_frob_finalize': [c_f, c_i, c_i, c_f, c_f, c_f, c_f, c_f, c_f],
+    'gp_scale_rows_batch': [c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_ll, c_f, c_ll, c_i, c_f],
+    'gp_entropy_partials': [c_i, c_i],
+    'gp_entropy_fwd': [c_f, c_f, c_i, c_i, c_i, c_f, c_f],
+    'gp_entropy_bwd': [c_f, c_f, c_i, c_i, c_i, c_f, C.c_float, c_f, c_i, c_f],
+    'gp_add_scaled': [c_f, c_f, C.c_float, c_f, c_f],
     'gp_linkloss_tc_partials': [c_i, c_i],
     'gp_linkloss_from_p': [c_f, c_f, c_f, c_i, c_i, c_ll, c_f, c_f, c_f],
     'gp_ce_fwd': [c_f, c_f, c_i, c_i, c_f, c_f, c_f],

@@ -48,7 +48,7 @@ struct Params {
   int npairs;
   int K[kMaxPairs]; int a_mn[kMaxPairs]; int b_mn[kMaxPairs]; int lim_k[kMaxPairs];
   int tiles_m, tiles_n; long long total_work;
-  const __nv_bfloat16* adjb; long long ldadj, sadjb; float* partial;   // EPI == 1
+  const __nv_bfloat16* adjb; long long ldadj, sadjb; float* partial; int link_mode;   // EPI == 1
   float* rnorm; float2* rowstat; int stat_relu;                        // EPI == 2
 };
 
@@ -193,8 +193,10 @@ __device__ __forceinline__ float rcp_approx(float x) {
 //   FAST (adjacency in {0,1}):  x = a ? P + eps : 1 - P + eps ;  loss = -ln x ;  G = a ? -1/x : 1/x
 //   general:                    loss = -a ln(P+eps) - (1-a) ln(1-P+eps) ;  G = -a/(P+eps) + (1-a)/(1-P+eps)
 // P is clamped to <= 1 first (R3: min(P, 1), encoders.py:1317) and G = 0 where the clamp is active.
-template <bool FAST, bool FULL>
+//   MODE 2 (Frobenius option, not in the reference):  d = a - P ;  *l2 += d^2 ;  G = -d  (no clamp)
+template <int MODE, bool FULL>
 __device__ __forceinline__ uint4 bce_row8(const float (&pv)[8], const uint4 aw, int nvalid, float* l2) {
+  constexpr bool FAST = MODE == 1;
   const uint32_t wsrc[4] = {aw.x, aw.y, aw.z, aw.w};
   float g[8];
 #pragma unroll
@@ -202,7 +204,11 @@ __device__ __forceinline__ uint4 bce_row8(const float (&pv)[8], const uint4 aw, 
     const uint32_t bits = (e & 1) ? (wsrc[e >> 1] & 0xffff0000u) : (wsrc[e >> 1] << 16);
     const float pc = fminf(pv[e], 1.f);
     float gg, ll;
-    if (FAST) {
+    if (MODE == 2) {
+      const float d = __uint_as_float(bits) - pv[e];
+      ll = d * d;
+      gg = -d;
+    } else if (FAST) {
       const bool one = bits != 0u;
       const float x = fmaf(one ? 1.f : -1.f, pc, one ? kEpsLink : 1.f + kEpsLink);
       ll = lg2_approx(x);
@@ -213,7 +219,7 @@ __device__ __forceinline__ uint4 bce_row8(const float (&pv)[8], const uint4 aw, 
       ll = a1 * lg2_approx(pe) + (1.f - a1) * lg2_approx(qe);
       gg = (1.f - a1) * rcp_approx(qe) - a1 * rcp_approx(pe);
     }
-    if (pv[e] > 1.f) gg = 0.f;
+    if (MODE != 2 && pv[e] > 1.f) gg = 0.f;
     if (!FULL && e >= nvalid) { gg = 0.f; ll = 0.f; }
     *l2 += ll;
     g[e] = gg;
@@ -514,6 +520,7 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
             }
           }
           const bool fast = __all_sync(0xffffffffu, is01);
+          const bool frob = p.link_mode == 1;
           float l2 = 0.f;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -522,11 +529,12 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
             const float4 p1 = *reinterpret_cast<const float4*>(&stg[stg_off(r, cc + 4)]);
             const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
             if (interior) {
-              const uint4 gw = fast ? bce_row8<true, true>(pv, aw[i], 8, &l2) : bce_row8<false, true>(pv, aw[i], 8, &l2);
+              const uint4 gw = frob ? bce_row8<2, true>(pv, aw[i], 8, &l2)
+                                    : (fast ? bce_row8<1, true>(pv, aw[i], 8, &l2) : bce_row8<0, true>(pv, aw[i], 8, &l2));
               if (gb != nullptr) *reinterpret_cast<uint4*>(gb + (long long)row * p.ldCb + n) = gw;
             } else {
               const int nvalid = row < k.Me ? min(8, max(0, k.Ne - n)) : 0;
-              const uint4 gw = bce_row8<false, false>(pv, aw[i], nvalid, &l2);
+              const uint4 gw = frob ? bce_row8<2, false>(pv, aw[i], nvalid, &l2) : bce_row8<0, false>(pv, aw[i], nvalid, &l2);
               if (gb != nullptr && row < p.M) {
                 __nv_bfloat16* dst = gb + (long long)row * p.ldCb + n;
                 if (vecCb8 && n + 8 <= p.ldCb) {
@@ -539,7 +547,7 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
               }
             }
           }
-          lsum = fmaf(l2, -0.69314718055994531f, lsum);
+          lsum = frob ? lsum + l2 : fmaf(l2, -0.69314718055994531f, lsum);
         } else {
           float* cb = p.C != nullptr ? p.C + (long long)k.b * p.sCb : nullptr;
           __nv_bfloat16* cbb = p.Cb != nullptr ? p.Cb + (long long)k.b * p.sCbb : nullptr;
@@ -763,7 +771,7 @@ int run(const gp_gemm_bf16x* g, cudaStream_t st) {
   p.lim = g->lim; p.lim_m = g->lim_m; p.lim_n = g->lim_n;
   p.alpha = g->alpha; p.beta = g->beta; p.alpha_dev = g->alpha_dev;
   p.bias = g->bias; p.relu = g->relu; p.split_k = g->split_k; p.npairs = g->npairs;
-  p.adjb = nullptr; p.ldadj = p.sadjb = 0; p.partial = nullptr;
+  p.adjb = nullptr; p.ldadj = p.sadjb = 0; p.partial = nullptr; p.link_mode = 0;
   p.rnorm = nullptr; p.rowstat = nullptr; p.stat_relu = 0;
   if (split > 1 && p.beta != 1.f) {
     const long long total = (long long)g->batch * g->M * g->N;
@@ -804,15 +812,16 @@ int run_norm(const gp_gemm_bf16x* g, float* rnorm, float* rowstat, int stat_relu
   p.ldC = g->ldC; p.sCb = 0; p.ldCb = g->ldCb; p.sCbb = 0;
   p.lim = nullptr; p.lim_m = p.lim_n = 0;
   p.alpha = g->alpha; p.beta = 0.f; p.alpha_dev = g->alpha_dev; p.bias = g->bias; p.relu = 0; p.split_k = 0; p.npairs = 1;
-  p.adjb = nullptr; p.ldadj = p.sadjb = 0; p.partial = nullptr;
+  p.adjb = nullptr; p.ldadj = p.sadjb = 0; p.partial = nullptr; p.link_mode = 0;
   p.rnorm = rnorm; p.rowstat = reinterpret_cast<float2*>(rowstat); p.stat_relu = stat_relu;
   if (BN == 256) return launch<256, 3, 2, 4>(maps, p, st);
   return launch<128, 4, 2, 4>(maps, p, st);
 }
 
 int run_linkloss(const void* s_bf16, long long lds, const void* adj_bf16, long long ldadj, const int32_t* nb,
-                 int B, int N, int K, float* partial, void* g_bf16, long long ldg, cudaStream_t st) {
+                 int B, int N, int K, float* partial, void* g_bf16, long long ldg, int mode, cudaStream_t st) {
   GP_REQUIRE(s_bf16 && adj_bf16 && partial && B > 0 && N > 0 && K > 0, "linkloss_tc: bad args");
+  GP_REQUIRE(mode == 0 || mode == 1, "linkloss_tc: mode must be 0 (BCE) or 1 (Frobenius)");
   GP_REQUIRE(lds % 8 == 0 && (g_bf16 == nullptr || ldg >= N), "linkloss_tc: bad strides");
   Maps maps;
   Params p;
@@ -826,7 +835,7 @@ int run_linkloss(const void* s_bf16, long long lds, const void* adj_bf16, long l
   p.lim = nb; p.lim_m = p.lim_n = nb != nullptr;
   p.alpha = 1.f; p.beta = 0.f; p.alpha_dev = nullptr; p.bias = nullptr; p.relu = 0; p.split_k = 0;
   p.adjb = reinterpret_cast<const __nv_bfloat16*>(adj_bf16); p.ldadj = ldadj; p.sadjb = (long long)N * ldadj;
-  p.partial = partial;
+  p.partial = partial; p.link_mode = mode;
   p.rnorm = nullptr; p.rowstat = nullptr; p.stat_relu = 0;
   return launch<256, 3, 1, kLinkEW>(maps, p, st);
 }
@@ -849,6 +858,6 @@ extern "C" int gp_linkloss_tc_partials(int B, int N) {
 }
 extern "C" int gp_linkloss_tc(const void* s_bf16, long long lds, const void* adj_bf16, long long ldadj,
                               const int32_t* nb, int B, int N, int K, float* partial, void* g_bf16,
-                              long long ldg, gp_stream_t stream) {
-  return gp::v2::run_linkloss(s_bf16, lds, adj_bf16, ldadj, nb, B, N, K, partial, g_bf16, ldg, gp::S(stream));
+                              long long ldg, int mode, gp_stream_t stream) {
+  return gp::v2::run_linkloss(s_bf16, lds, adj_bf16, ldadj, nb, B, N, K, partial, g_bf16, ldg, mode, gp::S(stream));
 }

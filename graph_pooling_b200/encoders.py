@@ -22,6 +22,9 @@ from ._lib import call
 
 __all__ = ['GraphConv', 'GcnEncoderGraph', 'GcnSet2SetEncoder', 'SoftPoolingGcnEncoder']
 
+# precision new encoders start with: 0 = fp32 FFMA (parity anchor), 1 = bf16 tensor cores; `model.precision` overrides
+DEFAULT_PRECISION = E.F32
+
 
 # ------------------------------------------------------------------------------------------
 # autograd glue: one Function for the whole encoder, one for the loss
@@ -304,7 +307,8 @@ class _EncoderFn(torch.autograd.Function):
 
 
 class _LossFn(torch.autograd.Function):
-    """CE (encoders.py:1127) [+ masked-BCE link loss (encoders.py:1311-1331)]."""
+    """CE (encoders.py:1127) [+ link loss: masked BCE (encoders.py:1311-1331) or the Frobenius option]
+    [+ entropy_weight * row entropy of S (north-star option)]."""
 
     @staticmethod
     def forward(ctx, plan, ypred, label, S, adj):
@@ -320,33 +324,60 @@ class _LossFn(torch.autograd.Function):
         if ctx.ce_scale != 1.0:                      # data-parallel CE weight shard_size / global_batch (dp.py)
             call('gp_axpy_f32', ce.data_ptr(), ce.data_ptr(), C.c_longlong(1), C.c_float(ctx.ce_scale - 1.0), st)
         ctx.probs, ctx.label, ctx.B, ctx.C = probs, label, B, Cc
-        ctx.link = S is not None
-        if S is None:
-            return ce.view(())
+        link_kind = getattr(plan, 'link_kind', None) if adj is not None else None     # None | 'bce' | 'frobenius'
+        ent_w = float(getattr(plan, 'ent_w', 0.0))
+        ctx.link_kind, ctx.ent_w = link_kind, ent_w
+        if S is None or (link_kind is None and ent_w == 0.0):
+            ctx.link_kind, ctx.ent_w = None, 0.0
+            return (ce.view(()),)
         Bn, N, K = S.shape
         need_grad = ctx.needs_input_grad[3]
         ctx.sb = getattr(plan, 'sb0', None)
-        if ctx.sb is not None:                      # GP_BF16: P = S S^T on tensor cores
-            partial, npart, gsym = T.linkloss_forward(ws, ctx.sb, plan.adjb, plan.nb_dev, Bn, N, K, need_grad)
-        else:
-            nt = (N + 63) // 64
-            npart = Bn * nt * nt
-            partial = ws.f(npart + 256)
-            gsym = ws.f(Bn, N, N) if need_grad else None
-            call('gp_linkloss_fwd', S.data_ptr(), adj.data_ptr(), E._p(plan.nb_dev), Bn, N, K, partial.data_ptr(),
-                 E._p(gsym), st)
-        total, link = ws.f(1), ws.f(1)
-        inv = 1.0 / float(plan.num_entries)
-        call('gp_loss_finalize', partial.data_ptr(), npart, C.c_double(inv), ce.data_ptr(), total.data_ptr(),
-             link.data_ptr(), st)
-        ctx.gsym, ctx.S, ctx.inv, ctx.nb = gsym, S, inv, plan.nb_dev
-        link = link.view(())
-        ctx.mark_non_differentiable(link)
-        return total.view(()), link
+        ctx.S, ctx.nb, ctx.gsym = S, plan.nb_dev, None
+        total, link, ent = ce, None, None
+        if link_kind is not None:
+            frob = link_kind == 'frobenius'
+            total, link = ws.f(1), ws.f(1)
+            if ctx.sb is not None:                      # GP_BF16: P = S S^T on tensor cores, loss in the epilogue
+                partial, npart, gsym = T.linkloss_forward(ws, ctx.sb, plan.adjb, plan.nb_dev, Bn, N, K, need_grad,
+                                                          mode=int(frob))
+            else:
+                nt = (N + 63) // 64
+                npart = Bn * nt * nt
+                partial = ws.f(npart + 256)
+                gsym = ws.f(Bn, N, N) if need_grad else None
+                call('gp_frob_link_fwd' if frob else 'gp_linkloss_fwd', S.data_ptr(), adj.data_ptr(),
+                     E._p(plan.nb_dev), Bn, N, K, partial.data_ptr(), E._p(gsym), st)
+            if frob:
+                ctx.coef = ws.f(Bn)
+                call('gp_frob_finalize', partial.data_ptr(), npart // Bn, Bn, ce.data_ptr(), total.data_ptr(),
+                     link.data_ptr(), ws.f(Bn).data_ptr(), ctx.coef.data_ptr(), st)
+            else:
+                ctx.inv = 1.0 / float(plan.num_entries)
+                call('gp_loss_finalize', partial.data_ptr(), npart, C.c_double(ctx.inv), ce.data_ptr(),
+                     total.data_ptr(), link.data_ptr(), st)
+            ctx.gsym = gsym
+        if ent_w != 0.0:
+            npe = int(T.load().gp_entropy_partials(Bn, N))
+            pe, ent, tot2 = ws.f(npe + 256), ws.f(1), ws.f(1)
+            call('gp_entropy_fwd', S.data_ptr(), E._p(plan.nb_dev), Bn, N, K, pe.data_ptr(), st)
+            ctx.ent_scale = ent_w / float(plan.num_real_rows)
+            call('gp_loss_finalize', pe.data_ptr(), npe, C.c_double(1.0 / float(plan.num_real_rows)), None, None,
+                 ent.data_ptr(), st)
+            call('gp_add_scaled', total.data_ptr(), ent.data_ptr(), C.c_float(ent_w), tot2.data_ptr(), st)
+            total = tot2
+        outs = [total.view(())]
+        for t in (link, ent):
+            if t is not None:
+                t = t.view(())
+                ctx.mark_non_differentiable(t)
+                outs.append(t)
+        ctx.n_out = len(outs)
+        return tuple(outs)
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, g, _glink=None):
+    def backward(ctx, g, *_unused):
         st = E._stream()
         ws = E.Workspace(g.device)
         g = E._chk(g, 'grad of loss')
@@ -355,19 +386,40 @@ class _LossFn(torch.autograd.Function):
         if ctx.ce_scale != 1.0:
             call('gp_axpy_f32', dy.data_ptr(), dy.data_ptr(), C.c_longlong(dy.numel()), C.c_float(ctx.ce_scale - 1.0), st)
         dS = None
-        if ctx.link and ctx.gsym is not None:
+        if ctx.link_kind is not None and ctx.gsym is not None:
             S = ctx.S
             Bn, N, K = S.shape
-            if ctx.sb is not None:
-                dS = T.linkloss_backward(ws, ctx.gsym, ctx.sb, ctx.nb, Bn, N, K, ctx.inv, g.data_ptr())
-                ctx.gsym = None
-                return None, dy, None, dS, None
-            dS = ws.f(Bn, N, K)
+            frob = ctx.link_kind == 'frobenius'
             lim = ctx.nb is not None
-            E.bgemm(ctx.gsym.data_ptr(), S.data_ptr(), dS.data_ptr(), N, K, N, Bn, (N * N, N, 1), (N * K, K, 1),
-                    (N * K, K, 1), lim=E._p(ctx.nb), lim_m=int(lim), lim_k=int(lim), alpha=ctx.inv,
-                    alpha_dev=g.data_ptr())
+            if ctx.sb is not None:
+                if frob:        # per-graph factor coef[b] * upstream folded into a scaled bf16 copy of S
+                    ssb = T.bfbuf(ws, Bn, N, K)
+                    call('gp_scale_rows_batch', S.data_ptr(), ctx.coef.data_ptr(), g.data_ptr(), Bn, N, K, None, 0,
+                         ssb.ptr, ssb.ld, ssb.ld, st)
+                    dS = T.linkloss_backward(ws, ctx.gsym, ssb, ctx.nb, Bn, N, K, 1.0, None)
+                else:
+                    dS = T.linkloss_backward(ws, ctx.gsym, ctx.sb, ctx.nb, Bn, N, K, ctx.inv, g.data_ptr())
+            else:
+                dS = ws.f(Bn, N, K)
+                if frob:
+                    ss = ws.f(Bn, N, K)
+                    call('gp_scale_rows_batch', S.data_ptr(), ctx.coef.data_ptr(), g.data_ptr(), Bn, N, K,
+                         ss.data_ptr(), K, None, 0, K, st)
+                    E.bgemm(ctx.gsym.data_ptr(), ss.data_ptr(), dS.data_ptr(), N, K, N, Bn, (N * N, N, 1),
+                            (N * K, K, 1), (N * K, K, 1), lim=E._p(ctx.nb), lim_m=int(lim), lim_k=int(lim))
+                else:
+                    E.bgemm(ctx.gsym.data_ptr(), S.data_ptr(), dS.data_ptr(), N, K, N, Bn, (N * N, N, 1),
+                            (N * K, K, 1), (N * K, K, 1), lim=E._p(ctx.nb), lim_m=int(lim), lim_k=int(lim),
+                            alpha=ctx.inv, alpha_dev=g.data_ptr())
             ctx.gsym = None
+        if ctx.ent_w != 0.0 and ctx.needs_input_grad[3]:
+            S = ctx.S
+            Bn, N, K = S.shape
+            acc = dS is not None
+            if dS is None:
+                dS = ws.f(Bn, N, K)
+            call('gp_entropy_bwd', S.data_ptr(), E._p(ctx.nb), Bn, N, K, g.data_ptr(), C.c_float(ctx.ent_scale),
+                 dS.data_ptr(), int(acc), st)
         return None, dy, None, dS, None
 
 
@@ -448,7 +500,7 @@ class GcnEncoderGraph(nn.Module):
         self.bn = bn
         self.num_layers = num_layers
         self.num_aggs = 1
-        self.precision = E.F32
+        self.precision = DEFAULT_PRECISION
         self._ce_scale, self._entries_override = 1.0, None
         self.bias = True
         if args is not None:
@@ -567,7 +619,7 @@ class GcnEncoderGraph(nn.Module):
             raise NotImplementedError("gp_b200: only type='softmax' is implemented (callers never pass 'margin')")
         plan = _Plan()
         plan.ce_scale = self._ce_scale
-        return _LossFn.apply(plan, pred, label, None, None)
+        return _LossFn.apply(plan, pred, label, None, None)[0]
 
     def set_loss_scaling(self, ce_scale=1.0, num_entries=None):
         """Data-parallel hook (dp.py, mode='global_norm'): weight of this shard's CE mean and the GLOBAL sum of
@@ -595,7 +647,9 @@ class SoftPoolingGcnEncoder(GcnEncoderGraph):
     def __init__(self, max_num_nodes, input_dim, hidden_dim, embedding_dim, label_dim, num_layers,
                  assign_hidden_dim, assign_ratio=0.25, assign_num_layers=-1, num_pooling=1,
                  pred_hidden_dims=[50], concat=True, bn=True, dropout=0.0, linkpred=True,
-                 assign_input_dim=-1, args=None):
+                 assign_input_dim=-1, args=None, link_loss='bce', entropy_weight=0.0):
+        # link_loss / entropy_weight: north-star options appended AFTER the reference's arguments (defaults
+        # reproduce the reference: masked-BCE link loss, no entropy term -- SURVEY.md appendix A.6).
         # R8: bn / dropout are NOT forwarded to the first GCN (encoders.py:1172-1173)
         super().__init__(input_dim, hidden_dim, embedding_dim, label_dim, num_layers,
                          pred_hidden_dims=pred_hidden_dims, concat=concat, args=args)
@@ -609,6 +663,10 @@ class SoftPoolingGcnEncoder(GcnEncoderGraph):
         self.num_pooling = num_pooling
         self.linkpred = linkpred
         self.assign_ent = True
+        if link_loss not in ('bce', 'frobenius'):
+            raise ValueError("link_loss must be 'bce' (the reference) or 'frobenius'")
+        self.link_loss_kind = link_loss
+        self.entropy_weight = float(entropy_weight)
 
         def reg(name, i, mod):                                               # R5
             setattr(self, name if i == num_pooling - 1 else '%s_l%d' % (name, i), mod)
@@ -677,27 +735,41 @@ class SoftPoolingGcnEncoder(GcnEncoderGraph):
 
     def loss(self, pred, label, adj=None, batch_num_nodes=None, adj_hop=1):
         plan = self._plan
-        if not self.linkpred:
+        ent_w = self.entropy_weight
+        if not self.linkpred and ent_w == 0.0:
             lp0 = _Plan()
             lp0.ce_scale = self._ce_scale
-            return _LossFn.apply(lp0, pred, label, None, None)
+            return _LossFn.apply(lp0, pred, label, None, None)[0]
         if adj_hop != 1:
             raise NotImplementedError('gp_b200: adj_hop > 1 is not implemented (callers never pass it)')
-        adj = E._chk(adj, 'adj')
         S0 = self._S0                                                        # R7: level-0 S with level-0 adj
         lp = _Plan()
         lp.sb0 = getattr(plan, 'sb0', None)
         lp.adjb = getattr(plan, 'adjb', None)
-        lp.nb_dev, nb_host = E.prep_nb(batch_num_nodes, adj.shape[1], adj.device)
-        if nb_host is None:
-            lp.num_entries = adj.shape[1] * adj.shape[1] * adj.shape[0]
-            print('Warning: calculating link pred loss without masking')       # encoders.py:1324
-        else:
-            n64 = nb_host.astype(np.int64)                                   # R11
-            lp.num_entries = int(np.sum(n64 * n64))
-        if self._entries_override is not None:
-            lp.num_entries = self._entries_override
         lp.ce_scale = self._ce_scale
-        total, link = _LossFn.apply(lp, pred, label, S0, adj)
-        self.link_loss = link
-        return total
+        lp.ent_w = ent_w
+        lp.link_kind = self.link_loss_kind if self.linkpred else None
+        N0 = S0.shape[1]
+        if batch_num_nodes is None and adj is None:
+            lp.nb_dev, nb_host = plan.nb_dev, plan.nb_host                   # 2-argument call: the forward's n_b
+        else:
+            lp.nb_dev, nb_host = E.prep_nb(batch_num_nodes, N0, S0.device)
+        lp.num_real_rows = S0.shape[0] * N0 if nb_host is None else max(int(np.sum(nb_host.astype(np.int64))), 1)
+        if self.linkpred:
+            adj = E._chk(adj, 'adj')
+            if nb_host is None:
+                lp.num_entries = adj.shape[1] * adj.shape[1] * adj.shape[0]
+                print('Warning: calculating link pred loss without masking')       # encoders.py:1324
+            else:
+                n64 = nb_host.astype(np.int64)                                   # R11
+                lp.num_entries = int(np.sum(n64 * n64))
+            if self._entries_override is not None:
+                lp.num_entries = self._entries_override
+        outs = _LossFn.apply(lp, pred, label, S0, adj if self.linkpred else None)
+        k = 1
+        if self.linkpred:
+            self.link_loss = outs[k]
+            k += 1
+        if ent_w != 0.0:
+            self.entropy_loss = outs[k]
+        return outs[0]

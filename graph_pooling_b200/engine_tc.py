@@ -328,7 +328,7 @@ def assign_head_bwd(ws, S, ds, nb, B, N, zab, Fa, wpb, K, has_bias):
     return dwp, dbp, dza
 
 
-def linkloss_forward(ws, sb, adjb, nb, B, N, K, need_grad):
+def linkloss_forward(ws, sb, adjb, nb, B, N, K, need_grad, mode=0):
     """Fused tensor-core link loss: P = S S^T tiles stay in TMEM, the epilogue does the masked BCE
     against the bf16 adjacency and writes gsym (bf16).  Returns (partial, n_partial, gsym op)."""
     nbp = E._p(nb)
@@ -336,13 +336,14 @@ def linkloss_forward(ws, sb, adjb, nb, B, N, K, need_grad):
     partial = ws.f(npart + 256)                      # +256: scratch of the two-stage finalisation
     gs = bfbuf(ws, B, N, N) if need_grad else None
     call('gp_linkloss_tc', sb.ptr, sb.ld, adjb.ptr, adjb.ld, nbp, B, N, K, partial.data_ptr(),
-         None if gs is None else gs.ptr, N if gs is None else gs.ld, E._stream())
+         None if gs is None else gs.ptr, N if gs is None else gs.ld, mode, E._stream())
     return partial, npart, gs
 
 
-def linkloss_backward(ws, gs, sb, nb, B, N, K, inv, g_ptr):
+def linkloss_backward(ws, gs, sb, nb, B, N, K, inv, g_ptr, dS=None):
     nbp, lim = E._p(nb), int(nb is not None)
-    dS = ws.f(B, N, K)
+    if dS is None:
+        dS = ws.f(B, N, K)
     # dS = (G + G^T).S : G K-major, then the same buffer read M-major (= G^T), accumulated
     cf = (dS.data_ptr(), K, N * K)
     tcgemm_multi([(gs, KM, sb, MN, N, lim), (gs, MN, sb, MN, N, lim)], N, K, B, Cf=cf, alpha=inv, alpha_dev=g_ptr,

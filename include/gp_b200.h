@@ -267,14 +267,42 @@ int gp_loss_finalize(const float* partial, int n_partial, double inv_entries, co
  * bases 16-byte aligned with row strides that are multiples of 8 take the 16-byte vector path.
  * gp_loss_finalize with n_partial > 8192 uses 256 floats of scratch AFTER the partial array. */
 int gp_linkloss_tc_partials(int B, int N);
+/* mode 0: masked BCE (the reference).  mode 1: Frobenius option -- partial sums of (A - P)^2 (per graph
+ * contiguous: gp_linkloss_tc_partials(1, N) each, feed gp_frob_finalize) and G = -(A - P). */
 int gp_linkloss_tc(const void* s_bf16, long long lds, const void* adj_bf16, long long ldadj,
                    const int32_t* nb, int B, int N, int K, float* partial, void* gsym_bf16, long long ldg,
-                   gp_stream_t stream);
+                   int mode, gp_stream_t stream);
 int gp_linkloss_from_p(const float* P, const float* adj, const int32_t* nb, int B, int N, long long ldg,
                        float* partial, void* gsym_bf16, gp_stream_t stream);
 
-/* Row entropy  -sum_k S log(S+eps) averaged over real rows, and the Frobenius variant of the
- * link loss (north-star options, not in the reference).  TODO(next round). */
+/* ---------------------------------------------------------------------------------------------
+ * North-star loss options that the reference does NOT contain (oracle: the DiffPool paper's definitions,
+ * oracle/diffpool_oracle.py frobenius_link_loss / row_entropy_loss; parity unpinned by the reference).
+ *
+ * Frobenius link loss  L_F = mean_b || (A_b - S_b S_b^T) over the n_b x n_b block ||_F :
+ *   gp_frob_link_fwd   partial[B * ceil(N/64)^2] <- per-tile sums of d^2 (per graph contiguous);
+ *                      gsym (optional, [B,N,N]) <- -(d + d^T), un-normalised
+ *   gp_frob_finalize   norm[b] = sqrt(sum of graph b's `per_graph` partials); coef[b] = 1/(B*norm[b]);
+ *                      link = mean_b norm[b]; total = ce (device scalar or NULL) + link
+ *   backward           dS[b] = upstream * coef[b] * gsym[b] . S[b]  -- gp_scale_rows_batch makes the scaled copy
+ *                      of S (fp32 and/or bf16 operand, zero-padded to cols_pad), then one GEMM.
+ * Row entropy  L_E = (1/sum_b n_b) sum_{b, n<n_b} -sum_k S log(S + 1e-7):
+ *   gp_entropy_fwd     partial[gp_entropy_partials(B, N)] <- per-block sums (finish with gp_loss_finalize)
+ *   gp_entropy_bwd     ds (+)= upstream * scale * -(log(S+eps) + S/(S+eps)) on real rows
+ * gp_add_scaled: total = (base ? *base : 0) + w * (*term)   (device scalars)
+ * ------------------------------------------------------------------------------------------- */
+int gp_frob_link_fwd(const float* s, const float* adj, const int32_t* nb, int B, int N, int K,
+                     float* partial, float* gsym, gp_stream_t stream);
+int gp_frob_finalize(const float* partial, int per_graph, int B, const float* ce, float* total, float* link,
+                     float* norm, float* coef, gp_stream_t stream);
+int gp_scale_rows_batch(const float* x, const float* scale, const float* upstream, int B, int rows_per_batch,
+                        int cols, float* out, long long ldo, void* out_bf16, long long ldob, int cols_pad,
+                        gp_stream_t stream);
+int gp_entropy_partials(int B, int N);
+int gp_entropy_fwd(const float* s, const int32_t* nb, int B, int N, int K, float* partial, gp_stream_t stream);
+int gp_entropy_bwd(const float* s, const int32_t* nb, int B, int N, int K, const float* upstream, float scale,
+                   float* ds, int accumulate, gp_stream_t stream);
+int gp_add_scaled(const float* base, const float* term, float w, float* total, gp_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Cross entropy (encoders.py:1127): loss = mean_b -log softmax(logits)[label]; probs saved.

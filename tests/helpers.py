@@ -57,3 +57,23 @@ def synth_batch(seed, B, N, D, n_min, n_max, C, density=0.1, symmetric=True, wei
         x[b, :n] = rs.randn(n, D).astype(np.float32)
     label = rs.randint(0, C, size=B).astype(np.int64)
     return x, adj, nb, label
+
+
+def load_enzymes(max_nodes=100):
+    """tests/golden/enzymes.npz (made by make_enzymes_fixture.py through the reference's loader) -> padded
+    arrays exactly as graph_sampler.py:97-109 + train.py:477-481 feed them: dense {0,1} adjacency, one-hot
+    node-label features, zero padding.  Returns x [G,N,D], adj [G,N,N], nb [G], label [G] (0-based)."""
+    z = np.load(os.path.join(HERE, 'golden', 'enzymes.npz'))
+    n, eptr, edges, nlabel = z['n'].astype(np.int64), z['eptr'], z['edges'].astype(np.int64), z['nlabel']
+    G, D = len(n), int(z['num_node_labels'])
+    adj = np.zeros((G, max_nodes, max_nodes), np.float32)
+    x = np.zeros((G, max_nodes, D), np.float32)
+    off = 0
+    for g in range(G):
+        e = edges[eptr[g]:eptr[g + 1]]
+        adj[g, e[:, 0], e[:, 1]] = 1.0
+        adj[g, e[:, 1], e[:, 0]] = 1.0
+        x[g, np.arange(n[g]), nlabel[off:off + n[g]]] = 1.0
+        off += n[g]
+    label = z['glabel'].astype(np.int64)
+    return x, adj, n.astype(np.int32), label - label.min()

@@ -1,0 +1,86 @@
+"""GPU: end-to-end check on the reference's bundled ENZYMES data (BASELINE.json configs[0]: DiffPool, batch 20,
+hidden/output 30, assign-ratio 0.1, num_pool 1, max_nodes 100, link prediction on).
+
+The graphs come from tests/golden/enzymes.npz, produced through the reference's own loader
+(tests/golden/make_enzymes_fixture.py).  Oracle (CPU fp32) and candidate (CUDA, fp32 mode) start from identical
+weights, see identical batches in identical order, and run train.py:196-210 (Adam lr 1e-3, clip 2.0) for a fixed
+number of epochs; per-epoch mean loss and the final train / validation accuracy must match.
+
+Tolerance: training amplifies rounding differences -- the fp32 and fp64 ORACLES already differ by 1.5e-3 in
+epoch loss and 0.015 in train accuracy after 6 epochs on this data.  Bounds: epoch loss 1e-2 relative,
+accuracy 0.04 absolute (fp32), 0.08 (bf16 tensor-core mode, loss 3e-2)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_enzymes
+from oracle import diffpool_oracle as orc
+
+pytestmark = pytest.mark.gpu
+EPOCHS, BATCH = 6, 20
+
+
+def _splits(nb):
+    rs = np.random.RandomState(0)
+    perm = rs.permutation(len(nb))
+    return rs, perm[:537], perm[537:]
+
+
+def _train(model, dev, dtype, x, adj, nb, label, step_fn):
+    rs, tr, va = _splits(nb)
+    X, A, L = torch.tensor(x).to(dev, dtype), torch.tensor(adj).to(dev, dtype), torch.tensor(label).to(dev)
+    losses = []
+    for _ in range(EPOCHS):
+        order = tr[rs.permutation(len(tr))]
+        tot, cnt = 0.0, 0
+        for i in range(0, len(order), BATCH):
+            idx = order[i:i + BATCH]
+            ti = torch.as_tensor(idx, device=dev)
+            tot += step_fn(model, X[ti], A[ti], L[ti], nb[idx])
+            cnt += 1
+        losses.append(tot / cnt)
+
+    def acc(ids):
+        c = 0
+        for i in range(0, len(ids), BATCH):
+            idx = ids[i:i + BATCH]
+            ti = torch.as_tensor(idx, device=dev)
+            with torch.no_grad():
+                c += int((model(X[ti], A[ti], nb[idx], assign_x=X[ti]).argmax(1) == L[ti]).sum().item())
+        return c / len(ids)
+    return losses, acc(tr), acc(va)
+
+
+@pytest.mark.parametrize('precision,loss_tol,acc_tol', [(0, 1e-2, 0.04), (1, 3e-2, 0.08)])
+def test_enzymes_training_matches_oracle(precision, loss_tol, acc_tol):
+    from graph_pooling_b200 import encoders
+    x, adj, nb, label = load_enzymes()
+    torch.manual_seed(0)
+    mo = orc.SoftPoolingGcnEncoder(100, 3, 30, 30, 6, 3, 30, assign_ratio=0.1, num_pooling=1, linkpred=True)
+    mc = encoders.SoftPoolingGcnEncoder(100, 3, 30, 30, 6, 3, 30, assign_ratio=0.1, num_pooling=1, linkpred=True)
+    mc.load_state_dict(mo.state_dict())
+    mc = mc.cuda()
+    mc.precision = precision
+    oo = torch.optim.Adam(mo.parameters(), lr=1e-3)
+    oc = torch.optim.Adam(mc.parameters(), lr=1e-3)
+
+    def step_o(m, X, A, L, n):
+        return orc.train_step(m, X, A, L, n, assign_x=X, optimizer=oo)[1].item()
+
+    def step_c(m, X, A, L, n):
+        m.zero_grad()
+        yp = m(X, A, n, assign_x=X)
+        loss = m.loss(yp, L, A, n)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(m.parameters(), 2.0)
+        oc.step()
+        return loss.item()
+
+    lo, tro, vao = _train(mo, 'cpu', torch.float32, x, adj, nb, label, step_o)
+    lc, trc, vac = _train(mc, 'cuda', torch.float32, x, adj, nb, label, step_c)
+    print('oracle   ', lo, tro, vao)
+    print('candidate', lc, trc, vac)
+    for a, b in zip(lc, lo):
+        assert abs(a - b) <= loss_tol * abs(b), (lc, lo)
+    assert lo[-1] < lo[0] - 0.1                      # it actually learns
+    assert abs(trc - tro) <= acc_tol and abs(vac - vao) <= acc_tol + 0.03, (trc, tro, vac, vao)
