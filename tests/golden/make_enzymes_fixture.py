@@ -1,4 +1,4 @@
-"""Generates tests/golden/enzymes.npz from the reference's bundled data THROUGH the reference's own loader
+"""Generates tests/golden/dataset_enzymes.npz from the reference's bundled data THROUGH the reference's own loader
 (load_data.read_graphfile, /root/reference/load_data.py:7-109; node order = its relabelling, isolated nodes dropped,
 graphs > max_nodes dropped), so the fixture is exactly what train.py would feed (train.py:470-481: node-label
 one-hot features).  Run in the build container (needs /root/reference); the GPU box only reads the .npz.
@@ -27,7 +27,7 @@ for G in graphs:
     for u, v in G.edges():
         edges.append((min(u, v), max(u, v)))
     eptr.append(len(edges))
-out = os.path.join(HERE, 'enzymes.npz')
+out = os.path.join(HERE, 'dataset_enzymes.npz')
 np.savez_compressed(out, n=np.asarray(n, np.int16), glabel=np.asarray(glabel, np.int8),
                     nlabel=np.asarray(nlabel, np.int8), eptr=np.asarray(eptr, np.int32),
                     edges=np.asarray(edges, np.int16), num_node_labels=np.int32(len(graphs[0].node[0]['label'])))

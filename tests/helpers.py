@@ -6,7 +6,8 @@ import numpy as np
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-GOLDEN = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(HERE, 'golden', '*.npz')))
+GOLDEN = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(HERE, 'golden', '*.npz'))
+                if not os.path.basename(p).startswith('dataset_'))
 
 
 def load_golden(name):
@@ -60,10 +61,10 @@ def synth_batch(seed, B, N, D, n_min, n_max, C, density=0.1, symmetric=True, wei
 
 
 def load_enzymes(max_nodes=100):
-    """tests/golden/enzymes.npz (made by make_enzymes_fixture.py through the reference's loader) -> padded
+    """tests/golden/dataset_enzymes.npz (made by make_enzymes_fixture.py through the reference's loader) -> padded
     arrays exactly as graph_sampler.py:97-109 + train.py:477-481 feed them: dense {0,1} adjacency, one-hot
     node-label features, zero padding.  Returns x [G,N,D], adj [G,N,N], nb [G], label [G] (0-based)."""
-    z = np.load(os.path.join(HERE, 'golden', 'enzymes.npz'))
+    z = np.load(os.path.join(HERE, 'golden', 'dataset_enzymes.npz'))
     n, eptr, edges, nlabel = z['n'].astype(np.int64), z['eptr'], z['edges'].astype(np.int64), z['nlabel']
     G, D = len(n), int(z['num_node_labels'])
     adj = np.zeros((G, max_nodes, max_nodes), np.float32)

@@ -1,7 +1,7 @@
 """GPU: end-to-end check on the reference's bundled ENZYMES data (BASELINE.json configs[0]: DiffPool, batch 20,
 hidden/output 30, assign-ratio 0.1, num_pool 1, max_nodes 100, link prediction on).
 
-The graphs come from tests/golden/enzymes.npz, produced through the reference's own loader
+The graphs come from tests/golden/dataset_enzymes.npz, produced through the reference's own loader
 (tests/golden/make_enzymes_fixture.py).  Oracle (CPU fp32) and candidate (CUDA, fp32 mode) start from identical
 weights, see identical batches in identical order, and run train.py:196-210 (Adam lr 1e-3, clip 2.0) for a fixed
 number of epochs; per-epoch mean loss and the final train / validation accuracy must match.
