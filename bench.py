@@ -234,26 +234,62 @@ def main():
     ms_per_step = ms / args.steps
     value = world * B / (ms_per_step * 1e-3)
 
-    # ---- end to end: host pinned fp32 buffers -> H2D -> step -> loss read-back ----------------
+    # ---- end to end: host pinned buffers -> H2D -> step -> loss read-back ---------------------------
+    # Double-buffered: the copy of step i+1's inputs runs on a copy stream while step i computes (what a
+    # DataLoader with pin_memory + non_blocking .cuda() gives train.py:197-201); every step's inputs cross PCIe
+    # and every step's loss is read back inside the timed region.
     e2e = None
+    e2e_u8 = None
     if not args.no_e2e:
-        hx, ha, hl = x.cpu().pin_memory(), adj.cpu().pin_memory(), label.cpu().pin_memory()
-        dx, da, dl = torch.empty_like(x), torch.empty_like(adj), torch.empty_like(label)
+        def run_e2e(adj_host_dtype):
+            hx, hl = x.cpu().pin_memory(), label.cpu().pin_memory()
+            ha = (adj.to(adj_host_dtype) if adj_host_dtype != adj.dtype else adj).cpu().pin_memory()
+            bufs = [(torch.empty_like(x), torch.empty(adj.shape, device=dev, dtype=adj_host_dtype),
+                     torch.empty_like(label)) for _ in range(2)]
+            copy_stream = torch.cuda.Stream(device=dev)
+            ready = [torch.cuda.Event(), torch.cuda.Event()]
+            freed = [torch.cuda.Event(), torch.cuda.Event()]
+            state = {'i': 0}
 
-        def e2e_step():
-            dx.copy_(hx, non_blocking=True)
-            da.copy_(ha, non_blocking=True)
-            dl.copy_(hl, non_blocking=True)
-            return float(step(dx, da, dl).item())
+            def issue(slot):
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(freed[slot])          # the step that last used this slot is done
+                    dx, da, dl = bufs[slot]
+                    dx.copy_(hx, non_blocking=True)
+                    da.copy_(ha, non_blocking=True)
+                    dl.copy_(hl, non_blocking=True)
+                    ready[slot].record(copy_stream)
 
-        for _ in range(min(args.warmup, 2)):
-            e2e_step()
-        ems = timed(e2e_step, args.steps) / args.steps
-        h2d = hx.numel() * 4 + ha.numel() * 4 + hl.numel() * 8 + nb.nbytes
-        e2e = {'value': world * B / (ems * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
-               'd2h_bytes_per_step': 4, 'ms_per_step': ems,
-               'note': 'dense fp32 adjacency from pinned host memory every step (reference feed contract)'}
-        del hx, ha, hl, dx, da, dl
+            for sl in range(2):
+                freed[sl].record(torch.cuda.current_stream())
+            issue(0)
+
+            def e2e_step():
+                slot = state['i'] & 1
+                state['i'] += 1
+                issue(slot ^ 1)                                  # prefetch the next step's inputs
+                torch.cuda.current_stream().wait_event(ready[slot])
+                dx, da, dl = bufs[slot]
+                loss = step(dx, da, dl)
+                freed[slot].record(torch.cuda.current_stream())
+                return float(loss.item())                        # D2H read-back of the step's result
+
+            for _ in range(min(args.warmup, 3)):
+                e2e_step()
+            ems = timed(e2e_step, args.steps) / args.steps
+            torch.cuda.synchronize()
+            h2d = hx.numel() * 4 + ha.numel() * ha.element_size() + hl.numel() * 8 + nb.nbytes
+            return {'value': world * B / (ems * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
+                    'd2h_bytes_per_step': 4, 'ms_per_step': ems}
+
+        e2e = run_e2e(torch.float32)
+        e2e['note'] = ('dense fp32 adjacency from pinned host memory every step (the reference feed contract, '
+                       'train.py:197-201); H2D of step i+1 overlaps step i on a copy stream')
+        if prec == 'bf16':
+            # SURVEY 8(f) N2 preview: the same step fed a uint8 {0,1} adjacency (a quarter of the PCIe bytes);
+            # NOT the headline e2e -- the reference's train.py feeds fp32.
+            e2e_u8 = run_e2e(torch.uint8)
+            e2e_u8['note'] = 'uint8 adjacency feed (compact-feed extension, not the reference contract)'
 
     if world > 1:
         dist.barrier()
@@ -370,7 +406,7 @@ def main():
                       'l2': 'inputs larger than L2 (adjacency %.1f GB)' % (adj.numel() * 4 / 1e9)
                       if adj.numel() * 4 > 126e6 else 'inputs smaller than L2; not flushed',
                       'parallelism': 'dp%d' % world},
-           'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roof, 'cpu_baseline': cpu}
+           'clocks': clocks, 'e2e': e2e, 'e2e_u8_feed': e2e_u8, 'gpu_launches': launches, 'roofline': roof, 'cpu_baseline': cpu}
     print(json.dumps(out), flush=True)
 
 

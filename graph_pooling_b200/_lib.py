@@ -48,7 +48,8 @@ class GpGemmBf16x(C.Structure):
                 ('ldC', c_ll), ('sCb', c_ll), ('ldCb', c_ll), ('sCbb', c_ll),
                 ('lim', c_f), ('lim_m', c_i), ('lim_n', c_i),
                 ('alpha', C.c_float), ('beta', C.c_float), ('alpha_dev', c_f),
-                ('bias', c_f), ('relu', c_i), ('split_k', c_i)]
+                ('bias', c_f), ('relu', c_i), ('split_k', c_i),
+                ('cond', c_f), ('cond_npairs', c_i), ('cond_alpha', C.c_float)]
 
 
 class GpLayerBwd(C.Structure):
@@ -69,6 +70,8 @@ _PROTOS = {
     'gp_bias_normalize_x': [c_f, c_f, c_f, c_ll, c_i, c_ll, c_i, c_f, c_ll, c_f],
     'gp_softmax_mask_fwd_x': [c_f, c_f, c_i, c_i, c_i, c_f, c_ll, c_f],
     'gp_softmax_mask_bwd_x': [c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f, c_ll, c_f, c_f, c_f],
+    'gp_adj_prepare': [c_f, c_i, c_f, c_i, c_i, c_f, c_ll, c_f, c_f],
+    'gp_sym_select_bf16': [c_f, c_i, c_i, c_f, c_f, c_ll, c_f],
     'gp_cvt_f32_bf16': [c_f, c_ll, c_f, c_ll, c_ll, c_i, c_i, c_f],
     'gp_version': [],
     'gp_last_error': [],

@@ -1,0 +1,173 @@
+// Adjacency preparation for the tensor-core path (HBM-bound, one pass):
+//   adj [B,N,N] (fp32 as train.py:197 feeds it, or uint8 {0,1} from a compact feed) -> bf16 operand [B,N,ld]
+// and, in the same pass, two facts the later kernels exploit:
+//   flags[0] != 0  <=>  some graph's adjacency is NOT symmetric
+//   flags[1] != 0  <=>  some entry is outside {0,1}
+// Each CTA owns a PAIR of mirrored 64x64 tiles (ti <= tj): both are read once (coalesced 16-byte loads),
+// converted and written, and tile (ti,tj) is compared with the transpose of tile (tj,ti) through shared
+// memory.  Tiles beyond a graph's node count are all-zero by the feed contract (graph_sampler.py:97-109):
+// they are written as zeros without being read (padding-aware schedule).
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+namespace gp {
+
+constexpr int AT = 64;
+
+template <typename T> struct Ld4;
+template <> struct Ld4<float> {
+  static __device__ __forceinline__ void ld(const float* p, bool vec, int nvalid, float (&v)[4]) {
+    if (vec) { const float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    else { for (int e = 0; e < 4; ++e) v[e] = e < nvalid ? p[e] : 0.f; }
+  }
+};
+template <> struct Ld4<uint8_t> {
+  static __device__ __forceinline__ void ld(const uint8_t* p, bool vec, int nvalid, float (&v)[4]) {
+    if (vec) { const uchar4 t = *reinterpret_cast<const uchar4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    else { for (int e = 0; e < 4; ++e) v[e] = e < nvalid ? (float)p[e] : 0.f; }
+  }
+};
+
+__device__ __forceinline__ uint32_t pk2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// loads tile rows r0.., cols c0.. of graph b into regs (4 passes of 16 rows, one float4 per thread), writes bf16
+template <typename T>
+__device__ __forceinline__ void tile_io(const T* __restrict__ ab, __nv_bfloat16* __restrict__ ob, int N, long long ld,
+                                        int r0, int c0, int nreal, bool vec_in, bool vec_out, float (&v)[4][4],
+                                        int* non01) {
+  const int tr = threadIdx.x >> 4, tc = (threadIdx.x & 15) * 4;
+  const bool live = r0 < nreal && c0 < nreal;           // otherwise all-zero by contract: do not read
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + tr + 16 * i, c = c0 + tc;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[i][e] = 0.f;
+    if (live && r < N && c < N) Ld4<T>::ld(ab + (long long)r * N + c, vec_in && c + 4 <= N, N - c, v[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + tr + 16 * i, c = c0 + tc;
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (v[i][e] != 0.f && v[i][e] != 1.f) *non01 = 1;
+    if (r < N && c < ld) {
+      __nv_bfloat16* dst = ob + (long long)r * ld + c;
+      if (vec_out && c + 4 <= ld) {
+        *reinterpret_cast<uint2*>(dst) = make_uint2(pk2(v[i][0], v[i][1]), pk2(v[i][2], v[i][3]));
+      } else {
+        for (int e = 0; e < 4 && c + e < ld; ++e) dst[e] = __float2bfloat16_rn(v[i][e]);
+      }
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+adj_prepare_kernel(const T* __restrict__ adj, const int32_t* __restrict__ nb, int N, __nv_bfloat16* __restrict__ out,
+                   long long ld, int tiles, int* __restrict__ flags, bool vec_in, bool vec_out) {
+  __shared__ float X[AT][AT + 1];
+  // blockIdx.x enumerates pairs (ti <= tj) row by row
+  int ti = 0, rem = blockIdx.x;
+  while (rem >= tiles - ti) { rem -= tiles - ti; ++ti; }
+  const int tj = ti + rem;
+  const int b = blockIdx.y;
+  const int nreal = nb != nullptr ? min(nb[b], N) : N;
+  const T* ab = adj + (long long)b * N * N;
+  __nv_bfloat16* ob = out + (long long)b * N * ld;
+  const int tr = threadIdx.x >> 4, tc = (threadIdx.x & 15) * 4;
+  int non01 = 0, asym = 0;
+  float v[4][4];
+  tile_io<T>(ab, ob, N, ld, ti * AT, tj * AT, nreal, vec_in, vec_out, v, &non01);
+  // the last tile column also owns the zero fill of the operand's padding columns [tiles*64, ld) -- none here:
+  // ld - N < 8 < 64, so they fall inside tile tj == tiles-1 and tile_io's `c < ld` bound covers them.
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) X[tr + 16 * i][tc + e] = v[i][e];
+  __syncthreads();
+  if (tj != ti) {
+    tile_io<T>(ab, ob, N, ld, tj * AT, ti * AT, nreal, vec_in, vec_out, v, &non01);
+  }
+  // compare (tj,ti)[r][c] with (ti,tj)[c][r]; on the diagonal the tile is compared with its own transpose
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (v[i][e] != X[tc + e][tr + 16 * i]) asym = 1;
+  asym = __syncthreads_or(asym);
+  non01 = __syncthreads_or(non01);
+  if (threadIdx.x == 0 && flags != nullptr) {
+    if (asym) atomicOr(&flags[0], 1);
+    if (non01) atomicOr(&flags[1], 1);
+  }
+}
+
+// out[b] = bf16( (*cond == 0) ? x[b] + x[b]^T : x[b] ), x [B,K,K] fp32 (the pooled-adjacency gradient dA').
+// 32x32 tiles; the mirrored tile is read coalesced and transposed through shared memory.
+__global__ void __launch_bounds__(256)
+sym_select_kernel(const float* __restrict__ x, int K, const int32_t* __restrict__ cond,
+                  __nv_bfloat16* __restrict__ out, long long ld) {
+  __shared__ float Tt[32][33];
+  const bool sym = cond != nullptr && *cond == 0;
+  const float* xb = x + (long long)blockIdx.z * K * K;
+  __nv_bfloat16* ob = out + (long long)blockIdx.z * K * ld;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  if (sym) {
+    for (int r = ty; r < 32; r += 8) {                   // mirrored tile rows c0.., cols r0..
+      const int gr = c0 + r, gc = r0 + tx;
+      Tt[r][tx] = (gr < K && gc < K) ? xb[(long long)gr * K + gc] : 0.f;
+    }
+    __syncthreads();
+  }
+  for (int r = ty; r < 32; r += 8) {
+    const int gr = r0 + r, gc = c0 + tx;
+    if (gr >= K || gc >= ld) continue;
+    float v = 0.f;
+    if (gc < K) {
+      v = xb[(long long)gr * K + gc];
+      if (sym) v += Tt[tx][r];
+    }
+    ob[(long long)gr * ld + gc] = __float2bfloat16_rn(v);
+  }
+}
+
+}  // namespace gp
+
+using namespace gp;
+
+extern "C" int gp_sym_select_bf16(const float* x, int B, int K, const int32_t* cond, void* out_bf16, long long ld,
+                                  gp_stream_t stream) {
+  GP_REQUIRE(x && out_bf16 && B > 0 && K > 0 && ld >= K && B <= 65535, "sym_select_bf16: bad args");
+  sym_select_kernel<<<dim3((unsigned)((ld + 31) / 32), (unsigned)((K + 31) / 32), (unsigned)B), 256, 0, S(stream)>>>(
+      x, K, cond, reinterpret_cast<__nv_bfloat16*>(out_bf16), ld);
+  GP_LAUNCHED();
+  return GP_OK;
+}
+
+extern "C" int gp_adj_prepare(const void* adj, int adj_dtype, const int32_t* nb, int B, int N, void* adj_bf16,
+                              long long ld, int32_t* flags, gp_stream_t stream) {
+  GP_REQUIRE(adj && adj_bf16 && B > 0 && N > 0 && ld >= N && ld - N < 8, "adj_prepare: bad args (need N <= ld < N+8)");
+  GP_REQUIRE(adj_dtype == 0 || adj_dtype == 1, "adj_prepare: adj_dtype must be 0 (fp32) or 1 (uint8)");
+  GP_REQUIRE(B <= 65535, "adj_prepare: B too large");
+  const int tiles = (N + AT - 1) / AT;
+  const long long pairs = (long long)tiles * (tiles + 1) / 2;
+  GP_REQUIRE(pairs < (1LL << 31), "adj_prepare: N too large");
+  if (flags != nullptr) GP_CUDA(cudaMemsetAsync(flags, 0, 2 * sizeof(int32_t), S(stream)));
+  dim3 grid((unsigned)pairs, (unsigned)B);
+  const bool vec_out = (reinterpret_cast<uintptr_t>(adj_bf16) & 7) == 0 && ld % 4 == 0;
+  if (adj_dtype == 0) {
+    const bool vec_in = (reinterpret_cast<uintptr_t>(adj) & 15) == 0 && N % 4 == 0;
+    adj_prepare_kernel<float><<<grid, 256, 0, S(stream)>>>(reinterpret_cast<const float*>(adj), nb, N,
+        reinterpret_cast<__nv_bfloat16*>(adj_bf16), ld, tiles, flags, vec_in, vec_out);
+  } else {
+    const bool vec_in = (reinterpret_cast<uintptr_t>(adj) & 3) == 0 && N % 4 == 0;
+    adj_prepare_kernel<uint8_t><<<grid, 256, 0, S(stream)>>>(reinterpret_cast<const uint8_t*>(adj), nb, N,
+        reinterpret_cast<__nv_bfloat16*>(adj_bf16), ld, tiles, flags, vec_in, vec_out);
+  }
+  GP_LAUNCHED();
+  return GP_OK;
+}

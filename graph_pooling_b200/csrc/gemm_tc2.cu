@@ -50,6 +50,7 @@ struct Params {
   int tiles_m, tiles_n; long long total_work;
   const __nv_bfloat16* adjb; long long ldadj, sadjb; float* partial; int link_mode;   // EPI == 1
   float* rnorm; float2* rowstat; int stat_relu;                        // EPI == 2
+  const int32_t* cond; int cond_npairs; float cond_alpha;              // device-side switch (see gp_gemm_bf16x)
 };
 
 struct Work {
@@ -132,7 +133,7 @@ struct Smem {
   static constexpr int kBytes = STAGES * kStage + kStaging + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*bias*/;
 };
 
-__device__ __forceinline__ Work get_work(const Params& p, long long w) {
+__device__ __forceinline__ Work get_work(const Params& p, long long w, int npairs) {
   Work k;
   const int split = p.split_k > 1 ? p.split_k : 1;
   const int nt = (int)(w % p.tiles_n);
@@ -149,7 +150,7 @@ __device__ __forceinline__ Work get_work(const Params& p, long long w) {
 #pragma unroll
   for (int q = 0; q < kMaxPairs; ++q) {
     int t = 0;
-    if (q < p.npairs) {
+    if (q < npairs) {
       const int Ke = p.lim_k[q] ? min(p.K[q], l) : p.K[q];
       t = (Ke + BK - 1) / BK;
     }
@@ -270,6 +271,16 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  // device-side switch: when *cond == 0 (e.g. "the adjacency is symmetric", adjprep.cu) only the first cond_npairs
+  // operand pairs are accumulated and alpha is scaled by cond_alpha; cond_npairs == 0 turns the launch into a no-op.
+  int npairs = p.npairs;
+  float alpha_mul = 1.f;
+  long long total_work = p.total_work;
+  if (p.cond != nullptr && *p.cond == 0) {
+    npairs = p.cond_npairs;
+    alpha_mul = p.cond_alpha;
+    if (npairs == 0) total_work = 0;
+  }
   float* sbias = reinterpret_cast<float*>(smem_gen + STAGES * L::kStage + L::kStaging + 256);
   if (EPI == 2) {                                        // bias (zero beyond N) staged once per CTA
     for (int i = threadIdx.x; i < 256; i += blockDim.x) sbias[i] = (p.bias != nullptr && i < p.N) ? p.bias[i] : 0.f;
@@ -280,11 +291,11 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
     // ===== TMA producer =====
     if (lane == 0) {
       uint32_t it = 0;                                   // running stage counter across tiles
-      for (long long w = blockIdx.x; w < p.total_work; w += gridDim.x) {
-        Work k = get_work(p, w);
+      for (long long w = blockIdx.x; w < total_work; w += gridDim.x) {
+        Work k = get_work(p, w, npairs);
         finish_work<BN>(p, k);
         int pos = 0;
-        for (int q = 0; q < p.npairs; ++q) {
+        for (int q = 0; q < npairs; ++q) {
           const int lo = max(k.kt0, pos), hi = min(k.kt1, pos + k.kt[q]);
           for (int g = lo; g < hi; ++g, ++it) {
             const int s = it % STAGES, ph = (it / STAGES) & 1;
@@ -314,8 +325,8 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
     // ===== MMA issuer =====
     if (lane == 0) {
       uint32_t it = 0, nacc = 0;
-      for (long long w = blockIdx.x; w < p.total_work; w += gridDim.x) {
-        Work k = get_work(p, w);
+      for (long long w = blockIdx.x; w < total_work; w += gridDim.x) {
+        Work k = get_work(p, w, npairs);
         finish_work<BN>(p, k);
         if (k.kt1 <= k.kt0) continue;
         const uint32_t a = nacc & 1, aph = (nacc >> 1) & 1;
@@ -324,7 +335,7 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
         const uint32_t tm = tmem_base + a * BN;
         int pos = 0;
         bool first = true;
-        for (int q = 0; q < p.npairs; ++q) {
+        for (int q = 0; q < npairs; ++q) {
           const int lo = max(k.kt0, pos), hi = min(k.kt1, pos + k.kt[q]);
           const bool amn = p.a_mn[q] != 0, bmn = p.b_mn[q] != 0;
           const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((amn ? 1u : 0u) << 15) |
@@ -356,7 +367,7 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
     static_assert(CPW % 32 == 0, "each epilogue warp needs whole 32-column chunks");
     const int quarter = warp & 3, cgrp = warp >> 2;
     float* stg = staging + warp * (32 * 32);
-    float alpha = p.alpha;
+    float alpha = p.alpha * alpha_mul;
     if (p.alpha_dev != nullptr) alpha *= *p.alpha_dev;
     const int split = p.split_k > 1 ? p.split_k : 1;
     const float beta = p.beta;
@@ -368,8 +379,8 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
     const bool vecCb8 = p.Cb != nullptr && (reinterpret_cast<uintptr_t>(p.Cb) & 15) == 0 && (p.ldCb & 7) == 0 &&
                         (p.sCbb & 7) == 0;
     uint32_t nacc = 0;
-    for (long long w = blockIdx.x; w < p.total_work; w += gridDim.x) {
-      Work k = get_work(p, w);
+    for (long long w = blockIdx.x; w < total_work; w += gridDim.x) {
+      Work k = get_work(p, w, npairs);
       finish_work<BN>(p, k);
       const bool has_acc = k.kt1 > k.kt0;
       const uint32_t a = nacc & 1, aph = (nacc >> 1) & 1;
@@ -773,6 +784,8 @@ int run(const gp_gemm_bf16x* g, cudaStream_t st) {
   p.bias = g->bias; p.relu = g->relu; p.split_k = g->split_k; p.npairs = g->npairs;
   p.adjb = nullptr; p.ldadj = p.sadjb = 0; p.partial = nullptr; p.link_mode = 0;
   p.rnorm = nullptr; p.rowstat = nullptr; p.stat_relu = 0;
+  p.cond = g->cond; p.cond_npairs = g->cond_npairs; p.cond_alpha = g->cond_alpha;
+  GP_REQUIRE(g->cond == nullptr || (g->cond_npairs >= 0 && g->cond_npairs <= g->npairs), "bgemm_bf16x: bad cond_npairs");
   if (split > 1 && p.beta != 1.f) {
     const long long total = (long long)g->batch * g->M * g->N;
     int blocks = (int)((total + 255) / 256);
@@ -814,6 +827,7 @@ int run_norm(const gp_gemm_bf16x* g, float* rnorm, float* rowstat, int stat_relu
   p.alpha = g->alpha; p.beta = 0.f; p.alpha_dev = g->alpha_dev; p.bias = g->bias; p.relu = 0; p.split_k = 0; p.npairs = 1;
   p.adjb = nullptr; p.ldadj = p.sadjb = 0; p.partial = nullptr; p.link_mode = 0;
   p.rnorm = rnorm; p.rowstat = reinterpret_cast<float2*>(rowstat); p.stat_relu = stat_relu;
+  p.cond = nullptr; p.cond_npairs = 0; p.cond_alpha = 1.f;
   if (BN == 256) return launch<256, 3, 2, 4>(maps, p, st);
   return launch<128, 4, 2, 4>(maps, p, st);
 }
@@ -837,6 +851,7 @@ int run_linkloss(const void* s_bf16, long long lds, const void* adj_bf16, long l
   p.adjb = reinterpret_cast<const __nv_bfloat16*>(adj_bf16); p.ldadj = ldadj; p.sadjb = (long long)N * ldadj;
   p.partial = partial; p.link_mode = mode;
   p.rnorm = nullptr; p.rowstat = nullptr; p.stat_relu = 0;
+  p.cond = nullptr; p.cond_npairs = 0; p.cond_alpha = 1.f;
   return launch<256, 3, 1, kLinkEW>(maps, p, st);
 }
 

@@ -12,6 +12,7 @@
 //  * layer_bwd_row_kernel  no BN (last layer of a stack): rows are independent, one warp per row.
 // Shapes outside the fast paths (d % 4 != 0, unaligned strides, d > 512, ...) use rowops.cu's generic kernel.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 #include <cuda_bf16.h>
 #include "common.cuh"
 
@@ -268,8 +269,18 @@ static bool shape_fast(int B, int d, int bn, int* CS_out) {
   const int d4 = d / 4;
   if (d4 > 32 || (d4 & (d4 - 1)) != 0) return false;     // a row must fit a power-of-two slice of one warp
   const int rstep = 256 / d4;
+  static int max_vpt = 0;                                // rows per thread before the node is split over more CTAs
+  if (max_vpt == 0) {
+    const char* e = getenv("GP_LBWD_VPT");
+    max_vpt = e != nullptr ? atoi(e) : 8;
+    if (max_vpt != 1 && max_vpt != 2 && max_vpt != 4 && max_vpt != 8) max_vpt = 8;
+  }
   int CS = 1;
-  while (CS <= 8 && ((B + CS - 1) / CS + rstep - 1) / rstep > 8) CS *= 2;
+  while (CS <= 8 && ((B + CS - 1) / CS + rstep - 1) / rstep > max_vpt) CS *= 2;
+  if (CS > 8 && max_vpt < 8) {                           // cluster limit reached: fall back to more rows per thread
+    CS = 1;
+    while (CS <= 8 && ((B + CS - 1) / CS + rstep - 1) / rstep > 8) CS *= 2;
+  }
   if (CS > 8) return false;
   if (CS_out) *CS_out = CS;
   return true;

@@ -49,14 +49,14 @@ def _fwd_tc(ctx, plan, x, adj, assign_x, params):
     P, Fw = plan.num_pooling, plan.F
     ldo = Fw * (P + 1)
     out, arg = ws.f(B, ldo), ws.i(B, ldo)
-    adjb = T.cvt(ws, adj.data_ptr(), N, B * N, N, B=B)
+    adjb, aflags = T.adj_prepare(ws, adj, nb, B, N)       # bf16 operand + [not symmetric, not {0,1}] device flags
     xb = T.cvt(ws, x.data_ptr(), D, B * N, D, B=B)
     w0, b0 = conv(plan.emb)
     z, zb, c_emb = T.stack_forward(ws, xb, D, adjb, nb, B, N, w0, b0, plan.bn)
     call('gp_readout_max_fwd', z.data_ptr(), Fw, E._p(nb) if plan.soft else None, B, N, Fw,
          out.data_ptr(), arg.data_ptr(), ldo, st)
     levels, S0 = [], None
-    plan.adjb, plan.sb0 = adjb, None
+    plan.adjb, plan.sb0, plan.asym = adjb, None, aflags[0:1]
     if plan.soft:
         if assign_x is x:
             xab, xa_d = xb, D
@@ -81,7 +81,8 @@ def _fwd_tc(ctx, plan, x, adj, assign_x, params):
             call('gp_readout_max_fwd', z2.data_ptr(), Fw, None, B, K, Fw, out.data_ptr() + (i + 1) * Fw * 4,
                  arg.data_ptr() + (i + 1) * Fw * 4, ldo, st)
             levels.append(dict(K=K, N=cur_N, nb=cur_nb, adjb=cur_adjb, zb=cur_zb, S=S, sb=sb, zab=zab, Fa=Fa,
-                               c_as=c_as, tb=tb, c_post=c_post, wpb=wpb, has_bp=bp is not None))
+                               c_as=c_as, tb=tb, c_post=c_post, wpb=wpb, has_bp=bp is not None,
+                               asym=plan.asym if i == 0 else None))
             if i == 0:
                 S0, plan.sb0 = S, sb
             xab, xa_d = xpb, Fw
@@ -136,7 +137,7 @@ def _bwd_tc(ctx, tape, dypred, dS0):
             else:
                 ds, acc_ds = ws.f(B, Ni, K), 0
             dz = T.pool_backward(ws, dxp, d_ap[i], lv['sb'], lv['zb'], lv['adjb'], lv['tb'], lv['nb'], B, Ni, K, Fw,
-                                 ds, acc_ds, None if i == 0 else d_ap[i - 1])
+                                 ds, acc_ds, None if i == 0 else d_ap[i - 1], asym=lv['asym'])
             dwp, dbp, dza = T.assign_head_bwd(ws, lv['S'], ds, lv['nb'], B, Ni, lv['zab'], lv['Fa'], lv['wpb'], K,
                                               lv['has_bp'])
             iw, ib = plan.assign_pred[i]
@@ -333,6 +334,7 @@ class _LossFn(torch.autograd.Function):
         Bn, N, K = S.shape
         need_grad = ctx.needs_input_grad[3]
         ctx.sb = getattr(plan, 'sb0', None)
+        ctx.asym = getattr(plan, 'asym', None)
         ctx.S, ctx.nb, ctx.gsym = S, plan.nb_dev, None
         total, link, ent = ce, None, None
         if link_kind is not None:
@@ -396,9 +398,9 @@ class _LossFn(torch.autograd.Function):
                     ssb = T.bfbuf(ws, Bn, N, K)
                     call('gp_scale_rows_batch', S.data_ptr(), ctx.coef.data_ptr(), g.data_ptr(), Bn, N, K, None, 0,
                          ssb.ptr, ssb.ld, ssb.ld, st)
-                    dS = T.linkloss_backward(ws, ctx.gsym, ssb, ctx.nb, Bn, N, K, 1.0, None)
+                    dS = T.linkloss_backward(ws, ctx.gsym, ssb, ctx.nb, Bn, N, K, 1.0, None, asym=ctx.asym)
                 else:
-                    dS = T.linkloss_backward(ws, ctx.gsym, ctx.sb, ctx.nb, Bn, N, K, ctx.inv, g.data_ptr())
+                    dS = T.linkloss_backward(ws, ctx.gsym, ctx.sb, ctx.nb, Bn, N, K, ctx.inv, g.data_ptr(), asym=ctx.asym)
             else:
                 dS = ws.f(Bn, N, K)
                 if frob:
@@ -583,7 +585,7 @@ class GcnEncoderGraph(nn.Module):
         return pairs
 
     def _base_plan(self, x, adj, batch_num_nodes):
-        x, adj = E._chk(x, 'x'), E._chk(adj, 'adj')
+        x, adj = E._chk(x, 'x'), E._chk_adj(adj, self.precision == T.BF16 and self.concat)
         if x.dim() != 3 or adj.dim() != 3 or adj.shape[1] != adj.shape[2] or adj.shape[:2] != x.shape[:2]:
             raise ValueError('expected x [B,N,D] and adj [B,N,N], got %s and %s' % (tuple(x.shape), tuple(adj.shape)))
         if x.shape[2] != self.conv_first.weight.shape[0]:
@@ -746,6 +748,7 @@ class SoftPoolingGcnEncoder(GcnEncoderGraph):
         lp = _Plan()
         lp.sb0 = getattr(plan, 'sb0', None)
         lp.adjb = getattr(plan, 'adjb', None)
+        lp.asym = getattr(plan, 'asym', None)
         lp.ce_scale = self._ce_scale
         lp.ent_w = ent_w
         lp.link_kind = self.link_loss_kind if self.linkpred else None
@@ -756,7 +759,7 @@ class SoftPoolingGcnEncoder(GcnEncoderGraph):
             lp.nb_dev, nb_host = E.prep_nb(batch_num_nodes, N0, S0.device)
         lp.num_real_rows = S0.shape[0] * N0 if nb_host is None else max(int(np.sum(nb_host.astype(np.int64))), 1)
         if self.linkpred:
-            adj = E._chk(adj, 'adj')
+            adj = E._chk_adj(adj, lp.sb0 is not None)
             if nb_host is None:
                 lp.num_entries = adj.shape[1] * adj.shape[1] * adj.shape[0]
                 print('Warning: calculating link pred loss without masking')       # encoders.py:1324

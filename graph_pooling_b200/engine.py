@@ -40,6 +40,16 @@ def _chk(t, name):
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _chk_adj(t, allow_u8):
+    """adjacency: float32 (the reference feed, train.py:197) or -- tensor-core mode only -- uint8 {0,1} (compact
+    feed: a quarter of the host->device bytes; expanded to the bf16 operand by gp_adj_prepare)."""
+    if allow_u8 and t.dtype == torch.uint8:
+        if not t.is_cuda:
+            raise RuntimeError('adj must be a CUDA tensor: the gp_b200 hot path has no CPU fallback')
+        return t if t.is_contiguous() else t.contiguous()
+    return _chk(t, 'adj')
+
+
 class Workspace:
     """Allocation helper: fresh torch buffers on the current device (caching allocator)."""
 

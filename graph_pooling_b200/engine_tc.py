@@ -44,11 +44,20 @@ def cvt(ws, x_ptr, ldx, rows, cols, B=1, out=None):
     return out
 
 
+def adj_prepare(ws, adj, nb, B, N):
+    """adj [B,N,N] fp32 (or uint8) -> (bf16 operand, flags int32[2] on device: [not symmetric, not {0,1}])."""
+    out = bfbuf(ws, B, N, N)
+    flags = torch.empty(2, device=ws.device, dtype=torch.int32)
+    call('gp_adj_prepare', adj.data_ptr(), 1 if adj.dtype == torch.uint8 else 0, E._p(nb), B, N, out.ptr, out.ld,
+         flags.data_ptr(), E._stream())
+    return out, flags
+
+
 _USE_V1 = bool(os.environ.get('GP_TC_V1'))     # debug: single-tile-per-CTA kernel of gemm_tc.cu
 
 
 def tcgemm_multi(pairs, M, N, batch, Cf=None, Cb=None, lim=None, lim_m=0, lim_n=0, alpha=1.0, beta=0.0,
-                 alpha_dev=None, bias=None, relu=0, split_k=0):
+                 alpha_dev=None, bias=None, relu=0, split_k=0, cond=None, cond_npairs=0, cond_alpha=1.0):
     """One persistent tcgen05 launch accumulating sum_q A_q.B_q (gp_bgemm_bf16x).
     pairs: [(A Op, a_major, B Op, b_major, K, lim_k)]; Cf = (ptr, ld, sb) fp32 out, Cb = Op bf16 out."""
     g = GpGemmBf16x()
@@ -67,15 +76,16 @@ def tcgemm_multi(pairs, M, N, batch, Cf=None, Cb=None, lim=None, lim_m=0, lim_n=
     g.lim, g.lim_m, g.lim_n = lim, lim_m, lim_n
     g.alpha, g.beta, g.alpha_dev = alpha, beta, alpha_dev
     g.bias, g.relu, g.split_k = bias, relu, split_k
+    g.cond, g.cond_npairs, g.cond_alpha = cond, cond_npairs, cond_alpha
     call('gp_bgemm_bf16x', C.byref(g), E._stream())
 
 
 def tcgemm(A, a_major, Bo, b_major, M, N, K, batch, Cf=None, Cb=None, lim=None, lim_m=0, lim_n=0, lim_k=0,
-           alpha=1.0, beta=0.0, alpha_dev=None, bias=None, relu=0, split_k=0):
+           alpha=1.0, beta=0.0, alpha_dev=None, bias=None, relu=0, split_k=0, cond=None, cond_npairs=0):
     """Single product on tensor cores.  Cf = (ptr, ld, sb) fp32 output, Cb = Op bf16 output."""
     if not _USE_V1:
         return tcgemm_multi([(A, a_major, Bo, b_major, K, lim_k)], M, N, batch, Cf, Cb, lim, lim_m, lim_n, alpha,
-                            beta, alpha_dev, bias, relu, split_k)
+                            beta, alpha_dev, bias, relu, split_k, cond, cond_npairs)
     cp, cld, csb = Cf if Cf is not None else (None, 0, 0)
     g = GpGemmBf16(A.ptr, Bo.ptr, cp, None if Cb is None else Cb.ptr, M, N, K, batch,
                    A.ld, A.sb, a_major, Bo.ld, Bo.sb, b_major, cld, csb,
@@ -112,6 +122,7 @@ def _norm_gemm(A, Bo, M, N, K, bias, Cf, Cb, rnorm, rowstat, stat_relu):
     g.lim, g.lim_m, g.lim_n = None, 0, 0
     g.alpha, g.beta, g.alpha_dev = 1.0, 0.0, None
     g.bias, g.relu, g.split_k = bias, 0, 0
+    g.cond, g.cond_npairs, g.cond_alpha = None, 0, 1.0
     call('gp_bgemm_bf16_norm', C.byref(g), rnorm, rowstat, int(stat_relu), E._stream())
 
 
@@ -274,7 +285,10 @@ def pool_forward(ws, sb, zb, adjb, nb, B, N, K, Fw):
     return sb, xp, xpb, tb, ap, apb
 
 
-def pool_backward(ws, dxp, dap, sb, zb, adjb, tb, nb, B, N, K, Fw, ds, acc_ds, dadj):
+def pool_backward(ws, dxp, dap, sb, zb, adjb, tb, nb, B, N, K, Fw, ds, acc_ds, dadj, asym=None):
+    """asym: device flag from adj_prepare (0 = every adjacency of the batch is symmetric) or None.  For a symmetric
+    A, T^T = A S, so T^T dA' + A (S dA'^T) = T^T (dA' + dA'^T): the N x N x K product and S dA'^T are skipped
+    on the device (no host sync): the kernels read the flag."""
     nbp, lim = E._p(nb), int(nb is not None)
     dxpb = cvt(ws, dxp.data_ptr(), Fw, B * K, Fw, B=B)
     dapb = cvt(ws, dap.data_ptr(), K, B * K, K, B=B)
@@ -282,10 +296,15 @@ def pool_backward(ws, dxp, dap, sb, zb, adjb, tb, nb, B, N, K, Fw, ds, acc_ds, d
     tcgemm(sb, KM, dxpb, MN, N, Fw, K, B, Cf=(dz.data_ptr(), Fw, N * Fw), lim=nbp, lim_m=lim)
     dsf = (ds.data_ptr(), K, N * K)
     wsb = bfbuf(ws, B, N, K)
-    tcgemm(sb, KM, dapb, KM, N, K, K, B, Cb=wsb, lim=nbp, lim_m=lim)
+    cond = E._p(asym)
+    tcgemm(sb, KM, dapb, KM, N, K, K, B, Cb=wsb, lim=nbp, lim_m=lim, cond=cond, cond_npairs=0)
+    dapx = dapb
+    if asym is not None:                                 # dA' + dA'^T when symmetric, dA' otherwise
+        dapx = bfbuf(ws, B, K, K)
+        call('gp_sym_select_bf16', dap.data_ptr(), B, K, cond, dapx.ptr, dapx.ld, E._stream())
     # dS (+)= Z dX'^T + T^T dA' + A (S dA'^T): three products accumulated in TMEM, one pass over dS
-    tcgemm_multi([(zb, KM, dxpb, KM, Fw, 0), (tb, MN, dapb, MN, K, 0), (adjb, KM, wsb, MN, N, lim)], N, K, B,
-                 Cf=dsf, beta=1.0 if acc_ds else 0.0, lim=nbp, lim_m=lim)
+    tcgemm_multi([(zb, KM, dxpb, KM, Fw, 0), (tb, MN, dapx, MN, K, 0), (adjb, KM, wsb, MN, N, lim)], N, K, B,
+                 Cf=dsf, beta=1.0 if acc_ds else 0.0, lim=nbp, lim_m=lim, cond=cond, cond_npairs=2)
     if dadj is not None:
         w2b = bfbuf(ws, B, N, K)
         tcgemm(sb, KM, dapb, MN, N, K, K, B, Cb=w2b)
@@ -340,12 +359,13 @@ def linkloss_forward(ws, sb, adjb, nb, B, N, K, need_grad, mode=0):
     return partial, npart, gs
 
 
-def linkloss_backward(ws, gs, sb, nb, B, N, K, inv, g_ptr, dS=None):
+def linkloss_backward(ws, gs, sb, nb, B, N, K, inv, g_ptr, dS=None, asym=None):
     nbp, lim = E._p(nb), int(nb is not None)
     if dS is None:
         dS = ws.f(B, N, K)
-    # dS = (G + G^T).S : G K-major, then the same buffer read M-major (= G^T), accumulated
+    # dS = (G + G^T).S : G K-major, then the same buffer read M-major (= G^T), accumulated.  A symmetric adjacency
+    # makes G symmetric (P = S S^T is): the kernel then runs the first product only, with alpha doubled.
     cf = (dS.data_ptr(), K, N * K)
     tcgemm_multi([(gs, KM, sb, MN, N, lim), (gs, MN, sb, MN, N, lim)], N, K, B, Cf=cf, alpha=inv, alpha_dev=g_ptr,
-                 lim=nbp, lim_m=lim)
+                 lim=nbp, lim_m=lim, cond=E._p(asym), cond_npairs=1, cond_alpha=2.0)
     return dS

@@ -126,6 +126,11 @@ typedef struct gp_gemm_bf16x {
   float alpha, beta; const float* alpha_dev;
   const float* bias; int relu;
   int split_k;
+  /* device-side switch, evaluated by the kernel (no host sync): if cond != NULL and *cond == 0, only the first
+   * cond_npairs pairs are accumulated and alpha is multiplied by cond_alpha; cond_npairs == 0 makes the launch a
+   * no-op (C untouched).  The DiffPool backward passes gp_adj_prepare's "adjacency is not symmetric" flag: for a
+   * symmetric A, (G + G^T).S = 2 G.S and T^T dA' + A.(S dA'^T) = T^T (dA' + dA'^T). */
+  const int32_t* cond; int cond_npairs; float cond_alpha;
 } gp_gemm_bf16x;
 int gp_bgemm_bf16x(const gp_gemm_bf16x* g, gp_stream_t stream);
 /* Fused GraphConv tail on tensor cores (encoders.py:322-326): one operand pair, batch == 1, N <= 256:
@@ -148,6 +153,15 @@ int gp_softmax_mask_fwd_x(float* t, const int32_t* nb, int B, int N, int K, void
                           gp_stream_t stream);
 int gp_softmax_mask_bwd_x(const float* s, const float* ds, const int32_t* nb, int B, int N, int K, float* dt,
                           void* dt_bf16, long long lddtb, float* dcol, float* ws, gp_stream_t stream);
+/* Adjacency preparation (one HBM pass): adj [B,N,N] fp32 (adj_dtype 0, train.py:197) or uint8 {0,1} (adj_dtype 1,
+ * compact feed) -> bf16 operand [B,N,ld] (N <= ld < N+8, zero padded); flags[0] != 0 iff some graph's adjacency
+ * is NOT symmetric, flags[1] != 0 iff some entry is outside {0,1}.  With nb, tiles beyond nb[b] are written as
+ * zeros without being read (feed contract graph_sampler.py:97-109). */
+int gp_adj_prepare(const void* adj, int adj_dtype, const int32_t* nb, int B, int N, void* adj_bf16, long long ld,
+                   int32_t* flags, gp_stream_t stream);
+/* out[b] = bf16((cond && *cond == 0) ? x[b] + x[b]^T : x[b]), x [B,K,K] fp32, out row stride ld (zero padded). */
+int gp_sym_select_bf16(const float* x, int B, int K, const int32_t* cond, void* out_bf16, long long ld,
+                       gp_stream_t stream);
 /* y[r, 0:cols_pad] = bf16(x[r, 0:cols]) zero-padded to cols_pad (row strides ldx / ldy in elements) */
 int gp_cvt_f32_bf16(const float* x, long long ldx, void* y, long long ldy, long long rows, int cols,
                     int cols_pad, gp_stream_t stream);

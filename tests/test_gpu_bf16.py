@@ -52,3 +52,57 @@ def test_bf16_mode_bounds(N, D, H, C, B, ratio, P, n_min, density):
     go = np.concatenate([p.grad.numpy().ravel() for p in m64.parameters()])
     cos = float(gc @ go / (np.linalg.norm(gc) * np.linalg.norm(go)))
     assert rel_l2(gc, go) < 0.15 and cos > 0.99, (rel_l2(gc, go), cos)
+
+
+@pytest.mark.parametrize('B,N,sym,weighted,use_nb,u8', [(3, 200, 1, 0, 1, 0), (2, 130, 0, 0, 1, 0), (2, 64, 1, 1, 0, 0),
+                                                       (3, 257, 1, 0, 1, 1), (2, 96, 0, 0, 0, 1)])
+def test_adj_prepare_flags_and_values(B, N, sym, weighted, use_nb, u8):
+    """gp_adj_prepare: exact bf16 copy (zero padded), 'not symmetric' / 'not {0,1}' flags, fp32 and uint8 feeds."""
+    from graph_pooling_b200 import engine as E, engine_tc as T
+    _, adj, nb, _ = synth_batch(N + sym, B, N, 2, N // 2, N, 2, 0.2, symmetric=bool(sym), weighted=bool(weighted))
+    a = torch.tensor(adj).cuda()
+    if u8:
+        a = a.to(torch.uint8)
+    nbd = torch.tensor(nb).cuda() if use_nb else None
+    op, flags = T.adj_prepare(E.Workspace(a.device), a, nbd, B, N)
+    torch.cuda.synchronize()
+    out = op.t.float().cpu().numpy()
+    assert out.shape == (B, N, (N + 7) // 8 * 8)
+    assert np.array_equal(out[:, :, :N], torch.tensor(adj).bfloat16().float().numpy()) and not out[:, :, N:].any()
+    assert flags.cpu().tolist() == [int(not sym), int(bool(weighted))]
+
+
+def test_bf16_mode_nonsymmetric_and_u8_feed():
+    """Non-symmetric adjacency takes the general (two-product) backward; a uint8 adjacency feed gives the same
+    result as the fp32 feed bit for bit (both become the same bf16 operand)."""
+    from graph_pooling_b200 import encoders
+    N, D, H, C, B = 192, 8, 32, 3, 3
+    outs = {}
+    for sym in (0, 1):
+        torch.manual_seed(7)
+        mo = orc.SoftPoolingGcnEncoder(N, D, H, H, C, 3, H, assign_ratio=0.25)
+        mc = encoders.SoftPoolingGcnEncoder(N, D, H, H, C, 3, H, assign_ratio=0.25)
+        mc.load_state_dict(mo.state_dict())
+        mc = mc.cuda()
+        mc.precision = 1
+        x, adj, nb, label = synth_batch(31, B, N, D, 60, N, C, 0.06, symmetric=bool(sym))
+        m64 = copy.deepcopy(mo).double()
+        yo, lo = orc.train_step(m64, torch.tensor(x).double(), torch.tensor(adj).double(), torch.tensor(label), nb)
+        go = np.concatenate([p.grad.numpy().ravel() for p in m64.parameters()])
+        for feed in ('f32', 'u8'):
+            mc.zero_grad()
+            xc, ac = torch.tensor(x).cuda(), torch.tensor(adj).cuda()
+            if feed == 'u8':
+                ac = ac.to(torch.uint8)
+            yp = mc(xc, ac, nb, assign_x=xc)
+            loss = mc.loss(yp, torch.tensor(label).cuda(), ac, nb)
+            loss.backward()
+            torch.cuda.synchronize()
+            gc = np.concatenate([p.grad.cpu().numpy().ravel() for p in mc.parameters()]).astype(np.float64)
+            cos = float(gc @ go / (np.linalg.norm(gc) * np.linalg.norm(go)))
+            assert abs(loss.item() - lo.item()) < 5e-3 * abs(lo.item())
+            assert rel_l2(gc, go) < 0.15 and cos > 0.99, (sym, feed, rel_l2(gc, go), cos)
+            outs[(sym, feed)] = (yp.detach().cpu().numpy(), gc)
+        assert np.array_equal(outs[(sym, 'f32')][0], outs[(sym, 'u8')][0])
+        # gradients: the split-K weight-gradient GEMMs accumulate with atomics (order varies run to run)
+        assert rel_l2(outs[(sym, 'u8')][1], outs[(sym, 'f32')][1]) < 1e-5
