@@ -57,7 +57,7 @@ class GpLayerBwd(C.Structure):
                 ('h', c_f), ('ldh', c_ll), ('y', c_f), ('ldy', c_ll),
                 ('rnorm', c_f), ('mean', c_f), ('invstd', c_f),
                 ('B', c_i), ('N', c_i), ('d', c_i), ('relu', c_i), ('bn', c_i), ('normalize', c_i),
-                ('dv', c_f), ('dv_bf16', c_f), ('lddvb', c_ll), ('db', c_f), ('ws', c_f)]
+                ('dv', c_f), ('dv_bf16', c_f), ('lddvb', c_ll), ('db', c_f), ('ws', c_f), ('lddxn', c_ll)]
 
 
 # name -> argtypes (restype is int unless listed in _RESTYPES)
@@ -66,7 +66,7 @@ _PROTOS = {
     'gp_bgemm_bf16': [C.POINTER(GpGemmBf16), c_f],
     'gp_bgemm_bf16_norm': [C.POINTER(GpGemmBf16x), c_f, c_f, c_i, c_f],
     'gp_bn_finalize': [c_f, c_i, c_i, c_i, c_f, c_f, c_f],
-    'gp_bn_apply': [c_f, c_ll, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f, c_ll, c_f, c_ll, c_f],
+    'gp_bn_apply': [c_f, c_ll, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f, c_ll, c_f, c_ll, c_f, c_ll, c_f],
     'gp_bias_normalize_x': [c_f, c_f, c_f, c_ll, c_i, c_ll, c_i, c_f, c_ll, c_f],
     'gp_softmax_mask_fwd_x': [c_f, c_f, c_i, c_i, c_i, c_f, c_ll, c_f],
     'gp_softmax_mask_bwd_x': [c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f, c_ll, c_f, c_f, c_f],

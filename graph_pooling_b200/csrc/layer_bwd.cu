@@ -28,7 +28,7 @@ int layer_bwd_generic(const gp_layer_bwd* a, cudaStream_t st);   // rowops.cu
 
 struct LbArgs {
   const float* dz; long long lddz;
-  const float* dxn;
+  const float* dxn; long long lddxn;
   const float* dout; const int32_t* argidx; long long ldo;
   const float* h; long long ldh;
   const float* y; long long ldy;
@@ -49,7 +49,7 @@ __device__ __forceinline__ float4 load_g(const LbArgs& a, int b, int n, long lon
   float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
   if (a.dz != nullptr) g = ld4(a.dz + row * a.lddz + c);
   if (a.dxn != nullptr) {
-    const float4 t = ld4(a.dxn + row * a.d + c);
+    const float4 t = ld4(a.dxn + row * a.lddxn + c);
     g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
   }
   if (a.dout != nullptr) {
@@ -316,7 +316,7 @@ static int launch_bn(const LbArgs& a, int CS, int rpc, cudaStream_t st) {
 static bool fast_eligible(const gp_layer_bwd* q, int* CS_out) {
   if (!al16(q->y) || q->ldy % 4 != 0) return false;
   if (q->dz != nullptr && (!al16(q->dz) || q->lddz % 4 != 0)) return false;
-  if (q->dxn != nullptr && !al16(q->dxn)) return false;
+  if (q->dxn != nullptr && (!al16(q->dxn) || q->lddxn % 4 != 0)) return false;
   if (q->dout != nullptr && (!al16(q->dout) || !al16(q->argidx) || q->ldo % 4 != 0)) return false;
   if (q->h != nullptr && (!al16(q->h) || q->ldh % 4 != 0)) return false;
   if (q->dv != nullptr && !al16(q->dv)) return false;
@@ -331,7 +331,7 @@ int layer_bwd_fast(const gp_layer_bwd* q, cudaStream_t st, bool* handled) {
   int CS = 1;
   if (!fast_eligible(q, &CS)) return GP_OK;
   LbArgs a;
-  a.dz = q->dz; a.lddz = q->lddz; a.dxn = q->dxn; a.dout = q->dout; a.argidx = q->argidx; a.ldo = q->ldo;
+  a.dz = q->dz; a.lddz = q->lddz; a.dxn = q->dxn; a.lddxn = q->lddxn > 0 ? q->lddxn : (long long)q->d; a.dout = q->dout; a.argidx = q->argidx; a.ldo = q->ldo;
   a.h = q->h; a.ldh = q->ldh; a.y = q->y; a.ldy = q->ldy; a.rnorm = q->rnorm; a.mean = q->mean; a.invstd = q->invstd;
   a.B = q->B; a.N = q->N; a.d = d; a.relu = q->relu; a.bn = q->bn; a.normalize = q->normalize;
   a.dv = q->dv; a.dvb = reinterpret_cast<__nv_bfloat16*>(q->dv_bf16); a.lddvb = q->lddvb;

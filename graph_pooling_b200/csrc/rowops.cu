@@ -97,12 +97,13 @@ __global__ void relu_bn_fwd_kernel(const float* __restrict__ y, float* __restric
 // One block per node index n; pass 1 block-reduces mean(g) and mean(g*Hhat); pass 2 is one warp
 // per (b, n) row: dR, ReLU mask, <Y,dY> by shuffle, dV.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float layer_g(const float* dz, long long lddz, const float* dxn, const float* dout,
-                                         const int32_t* argidx, long long ldo, int b, int n, int c, int N, int d) {
+__device__ __forceinline__ float layer_g(const float* dz, long long lddz, const float* dxn, long long lddxn,
+                                         const float* dout, const int32_t* argidx, long long ldo, int b, int n, int c,
+                                         int N, int d) {
   float g = 0.f;
   const long long row = (long long)b * N + n;
   if (dz != nullptr) g += dz[row * lddz + c];
-  if (dxn != nullptr) g += dxn[row * d + c];
+  if (dxn != nullptr) g += dxn[row * lddxn + c];
   if (dout != nullptr && argidx[(long long)b * ldo + c] == n) g += dout[(long long)b * ldo + c];
   return g;
 }
@@ -126,6 +127,7 @@ __device__ __forceinline__ void put_dv(float* dv, __nv_bfloat16* dvb, long long 
 
 template <bool CACHE, int MAXE>
 __global__ void gcn_layer_bwd_kernel(const float* __restrict__ dz, long long lddz, const float* __restrict__ dxn,
+                                     long long lddxn,
                                      const float* __restrict__ dout, const int32_t* __restrict__ argidx,
                                      long long ldo, const float* __restrict__ h, long long ldh,
                                      const float* __restrict__ y, long long ldy, const float* __restrict__ rnorm,
@@ -143,7 +145,7 @@ __global__ void gcn_layer_bwd_kernel(const float* __restrict__ dz, long long ldd
     float s1 = 0.f, s2 = 0.f;
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
       const int b = i / d, c = i - b * d;
-      const float g = layer_g(dz, lddz, dxn, dout, argidx, ldo, b, n, c, N, d);
+      const float g = layer_g(dz, lddz, dxn, lddxn, dout, argidx, ldo, b, n, c, N, d);
       if (CACHE) cache[i] = g;
       s1 += g;
       s2 = fmaf(g, hhat_of(h, ldh, y, ldy, (long long)b * N + n, c, relu, mu, is), s2);
@@ -169,7 +171,7 @@ __global__ void gcn_layer_bwd_kernel(const float* __restrict__ dz, long long ldd
         const int c = lane + 32 * e;
         float g = 0.f, yy = 0.f;
         if (c < d) {
-          g = cached ? cache[b * d + c] : layer_g(dz, lddz, dxn, dout, argidx, ldo, b, n, c, N, d);
+          g = cached ? cache[b * d + c] : layer_g(dz, lddz, dxn, lddxn, dout, argidx, ldo, b, n, c, N, d);
           if (bn) g = (g - m1 - hhat_of(h, ldh, y, ldy, row, c, relu, mu, is) * m2) * is;
           yy = y[row * ldy + c];
           if (relu && !(yy > 0.f)) g = 0.f;
@@ -190,7 +192,7 @@ __global__ void gcn_layer_bwd_kernel(const float* __restrict__ dz, long long ldd
     } else {
       float dot = 0.f;
       for (int c = lane; c < d; c += 32) {
-        float g = cached ? cache[b * d + c] : layer_g(dz, lddz, dxn, dout, argidx, ldo, b, n, c, N, d);
+        float g = cached ? cache[b * d + c] : layer_g(dz, lddz, dxn, lddxn, dout, argidx, ldo, b, n, c, N, d);
         if (bn) g = (g - m1 - hhat_of(h, ldh, y, ldy, row, c, relu, mu, is) * m2) * is;
         const float yy = y[row * ldy + c];
         if (relu && !(yy > 0.f)) g = 0.f;
@@ -198,7 +200,7 @@ __global__ void gcn_layer_bwd_kernel(const float* __restrict__ dz, long long ldd
       }
       if (normalize) dot = warp_sum(dot);
       for (int c = lane; c < d; c += 32) {
-        float g = cached ? cache[b * d + c] : layer_g(dz, lddz, dxn, dout, argidx, ldo, b, n, c, N, d);
+        float g = cached ? cache[b * d + c] : layer_g(dz, lddz, dxn, lddxn, dout, argidx, ldo, b, n, c, N, d);
         if (bn) g = (g - m1 - hhat_of(h, ldh, y, ldy, row, c, relu, mu, is) * m2) * is;
         const float yy = y[row * ldy + c];
         if (relu && !(yy > 0.f)) g = 0.f;
@@ -444,7 +446,7 @@ int layer_bwd_generic(const gp_layer_bwd* q, cudaStream_t st) {
       static bool cfgd = false;                                                                            \
       if (!cfgd) { GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNodeCacheMax)); cfgd = true; } \
     }                                                                                                      \
-    kern<<<N, threads, C_ ? cache_bytes : 0, st>>>(q->dz, q->lddz, q->dxn, q->dout, q->argidx, q->ldo, q->h, \
+    kern<<<N, threads, C_ ? cache_bytes : 0, st>>>(q->dz, q->lddz, q->dxn, (q->lddxn > 0 ? q->lddxn : (long long)d), q->dout, q->argidx, q->ldo, q->h, \
                                                    q->ldh, q->y, q->ldy, q->rnorm, q->mean, q->invstd, B, N, d, \
                                                    q->relu, q->bn, q->normalize, dv, dvb, q->lddvb);       \
   } while (0)
@@ -469,7 +471,7 @@ extern "C" int gp_gcn_layer_bwd(const float* dz, long long lddz, const float* dx
   q.dz = dz; q.lddz = lddz; q.dxn = dxn; q.dout = dout; q.argidx = argidx; q.ldo = ldo;
   q.h = h; q.ldh = ldh; q.y = y; q.ldy = ldy; q.rnorm = rnorm; q.mean = nullptr; q.invstd = invstd;
   q.B = B; q.N = N; q.d = d; q.relu = relu; q.bn = bn; q.normalize = normalize;
-  q.dv = dv; q.dv_bf16 = nullptr; q.lddvb = 0; q.db = nullptr; q.ws = nullptr;
+  q.dv = dv; q.dv_bf16 = nullptr; q.lddvb = 0; q.db = nullptr; q.ws = nullptr; q.lddxn = 0;
   return gp_gcn_layer_bwd_x(&q, stream);
 }
 

@@ -49,7 +49,8 @@ __global__ void bn_finalize_kernel(const float2* __restrict__ rowstat, int B, in
 template <bool VEC>
 __global__ void bn_apply_kernel(const float* __restrict__ y, long long ldy, const float* __restrict__ mean,
                                 const float* __restrict__ invstd, long long rows, int N, int d, int relu, int bn,
-                                float* __restrict__ h, long long ldh, __nv_bfloat16* __restrict__ hb, long long ldhb) {
+                                float* __restrict__ h, long long ldh, __nv_bfloat16* __restrict__ hb, long long ldhb,
+                                __nv_bfloat16* __restrict__ hb2, long long ldhb2) {
   const int lane = threadIdx.x & 31;
   const long long gw = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -62,7 +63,9 @@ __global__ void bn_apply_kernel(const float* __restrict__ y, long long ldy, cons
         if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
         v.x = (v.x - mu) * is; v.y = (v.y - mu) * is; v.z = (v.z - mu) * is; v.w = (v.w - mu) * is;
         if (h != nullptr) *reinterpret_cast<float4*>(h + r * ldh + c) = v;
-        if (hb != nullptr) *reinterpret_cast<uint2*>(hb + r * ldhb + c) = make_uint2(packx(v.x, v.y), packx(v.z, v.w));
+        const uint2 pk = make_uint2(packx(v.x, v.y), packx(v.z, v.w));
+        if (hb != nullptr) *reinterpret_cast<uint2*>(hb + r * ldhb + c) = pk;
+        if (hb2 != nullptr) *reinterpret_cast<uint2*>(hb2 + r * ldhb2 + c) = pk;
       }
     } else {
       for (int c = lane; c < d; c += 32) {
@@ -71,6 +74,7 @@ __global__ void bn_apply_kernel(const float* __restrict__ y, long long ldy, cons
         v = (v - mu) * is;
         if (h != nullptr) h[r * ldh + c] = v;
         if (hb != nullptr) hb[r * ldhb + c] = __float2bfloat16_rn(v);
+        if (hb2 != nullptr) hb2[r * ldhb2 + c] = __float2bfloat16_rn(v);
       }
     }
   }
@@ -237,16 +241,17 @@ extern "C" int gp_bn_finalize(const float* rowstat, int B, int N, int d, float* 
 }
 
 extern "C" int gp_bn_apply(const float* y, long long ldy, const float* mean, const float* invstd, int B, int N, int d,
-                           int relu, int bn, float* h, long long ldh, void* h_bf16, long long ldhb,
-                           gp_stream_t stream) {
+                           int relu, int bn, float* h, long long ldh, void* h_bf16, long long ldhb, void* h_bf16_2,
+                           long long ldhb2, gp_stream_t stream) {
   GP_REQUIRE(y && (h || h_bf16) && B > 0 && N > 0 && d > 0 && ldy >= d, "bn_apply: bad args");
   GP_REQUIRE(!bn || (mean && invstd), "bn_apply: bn needs mean/invstd");
   const long long rows = (long long)B * N;
   __nv_bfloat16* hb = reinterpret_cast<__nv_bfloat16*>(h_bf16);
+  __nv_bfloat16* hb2 = reinterpret_cast<__nv_bfloat16*>(h_bf16_2);
   const bool vec = d % 4 == 0 && al16x(y) && ldy % 4 == 0 && (!h || (al16x(h) && ldh % 4 == 0)) &&
-                   (!hb || (al8x(hb) && ldhb % 4 == 0));
-  if (vec) bn_apply_kernel<true><<<row_grid(rows), 256, 0, S(stream)>>>(y, ldy, mean, invstd, rows, N, d, relu, bn, h, ldh, hb, ldhb);
-  else     bn_apply_kernel<false><<<row_grid(rows), 256, 0, S(stream)>>>(y, ldy, mean, invstd, rows, N, d, relu, bn, h, ldh, hb, ldhb);
+                   (!hb || (al8x(hb) && ldhb % 4 == 0)) && (!hb2 || (al8x(hb2) && ldhb2 % 4 == 0));
+  if (vec) bn_apply_kernel<true><<<row_grid(rows), 256, 0, S(stream)>>>(y, ldy, mean, invstd, rows, N, d, relu, bn, h, ldh, hb, ldhb, hb2, ldhb2);
+  else     bn_apply_kernel<false><<<row_grid(rows), 256, 0, S(stream)>>>(y, ldy, mean, invstd, rows, N, d, relu, bn, h, ldh, hb, ldhb, hb2, ldhb2);
   GP_LAUNCHED();
   return GP_OK;
 }

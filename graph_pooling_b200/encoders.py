@@ -10,6 +10,7 @@ ABI (include/gp_b200.h); see engine.py for the schedule.  Deviations from the sh
 text are the documented repairs R1-R11 (oracle/diffpool_oracle.py header).
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -52,24 +53,34 @@ def _fwd_tc(ctx, plan, x, adj, assign_x, params):
     adjb, aflags = T.adj_prepare(ws, adj, nb, B, N)       # bf16 operand + [not symmetric, not {0,1}] device flags
     xb = T.cvt(ws, x.data_ptr(), D, B * N, D, B=B)
     w0, b0 = conv(plan.emb)
-    z, zb, c_emb = T.stack_forward(ws, xb, D, adjb, nb, B, N, w0, b0, plan.bn)
+    xab, xa_d, pre_as = xb, D, None
+    if plan.soft and assign_x is not x:
+        xa_d = assign_x.shape[2]
+        xab = T.cvt(ws, assign_x.data_ptr(), xa_d, B * N, xa_d, B=B)
+    dual = False
+    if plan.soft:
+        wa0, ba0 = conv(plan.assign[0])
+        dual = T.dual_ok(w0, wa0) and not os.environ.get('GP_NO_DUAL')
+    if dual:        # embedding + level-0 assignment GCN in lock-step: one pass over A per layer for both
+        (z, zb, c_emb), pre_as = T.dual_stack_forward(ws, xb, D, xab, xa_d, adjb, nb, B, N, w0, b0, plan.bn, wa0, ba0,
+                                                      True)
+    else:
+        z, zb, c_emb = T.stack_forward(ws, xb, D, adjb, nb, B, N, w0, b0, plan.bn)
     call('gp_readout_max_fwd', z.data_ptr(), Fw, E._p(nb) if plan.soft else None, B, N, Fw,
          out.data_ptr(), arg.data_ptr(), ldo, st)
     levels, S0 = [], None
     plan.adjb, plan.sb0, plan.asym = adjb, None, aflags[0:1]
     if plan.soft:
-        if assign_x is x:
-            xab, xa_d = xb, D
-        else:
-            xa_d = assign_x.shape[2]
-            xab = T.cvt(ws, assign_x.data_ptr(), xa_d, B * N, xa_d, B=B)
         cur_adjb, cur_nb, cur_N, cur_zb = adjb, nb, N, zb
         for i in range(P):
             K = plan.assign_dims[i]
             wa, ba = conv(plan.assign[i])
-            # level 0 with assign_x == x: both GCNs start from the same U = A.x -- compute it once
-            u0 = c_emb.layers[0][4] if (i == 0 and xab is xb) else None
-            za, zab, c_as = T.stack_forward(ws, xab, xa_d, cur_adjb, cur_nb, B, cur_N, wa, ba, True, u0=u0)
+            if i == 0 and pre_as is not None:
+                za, zab, c_as = pre_as
+            else:
+                # level 0 with assign_x == x: both GCNs start from the same U = A.x -- compute it once
+                u0 = c_emb.layers[0][4] if (i == 0 and xab is xb) else None
+                za, zab, c_as = T.stack_forward(ws, xab, xa_d, cur_adjb, cur_nb, B, cur_N, wa, ba, True, u0=u0)
             Fa = za.shape[2]
             wp, bp = _wb(params, plan.assign_pred[i])
             Tl, wpb = T.assign_linear_fwd(ws, zab, Fa, B * cur_N, wp, bp)
@@ -90,7 +101,7 @@ def _fwd_tc(ctx, plan, x, adj, assign_x, params):
     lin = [_wb(params, p) for p in plan.pred]
     ypred, acts = E.mlp_fwd(ws, out.data_ptr(), ldo, B, lin)
     ctx.tape = dict(plan=plan, params=params, B=B, N=N, emb=c_emb, levels=levels, out=out, arg=arg, ldo=ldo,
-                    acts=acts, lin=lin, x=x, adj=adj)
+                    acts=acts, lin=lin, x=x, adj=adj, dual=dual)
     if plan.soft:
         plan.all_S = [lv['S'] for lv in levels]
         return ypred, S0
@@ -144,6 +155,13 @@ def _bwd_tc(ctx, tape, dypred, dS0):
             grads[iw] = dwp
             if ib is not None:
                 grads[ib] = dbp
+            if i == 0 and tape['dual']:
+                # embedding + assignment GCN backward in lock-step (one A^T.dU pass per layer for both)
+                gE, gA = T.dual_stack_backward(ws, tape['emb'], lv['c_as'], dz.data_ptr(), Fw, dout_p, arg_p, ldo,
+                                               dza.data_ptr(), lv['Fa'])
+                put(plan.emb, gE)
+                put(plan.assign[0], gA)
+                return (None, None, None, None) + tuple(grads)
             gl, dxa = T.stack_backward(ws, lv['c_as'], dza.data_ptr(), lv['Fa'], None, None, 0, i > 0,
                                        None if i == 0 else d_ap[i - 1])
             put(plan.assign[i], gl)

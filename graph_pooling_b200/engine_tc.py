@@ -126,130 +126,209 @@ def _norm_gemm(A, Bo, M, N, K, bias, Cf, Cb, rnorm, rowstat, stat_relu):
     call('gp_bgemm_bf16_norm', C.byref(g), rnorm, rowstat, int(stat_relu), E._stream())
 
 
-def stack_forward(ws, xb, din, adjb, nb, B, N, weights, biases, bn, u0=None):
-    """TC version of engine.stack_forward (add_self unsupported).  xb/adjb: bf16 operands.
-    Per layer:  U = A.X (tcgen05)  ->  Y = normalize(U.W + b) with the row norm and the BatchNorm row sums
-    taken in the GEMM epilogue  ->  H = BN(relu(Y)) written once as fp32 (concat slot) and bf16 (next operand).
-    u0: optional precomputed U of the first layer (shared with another stack that has the same A and X).
-    Returns (zcat fp32 [B,N,F], zb bf16 operand of the same concat, ctx)."""
-    st = E._stream()
+def _stack_begin(ws, xb, din, adjb, nb, B, N, weights, biases, bn):
     L = len(weights)
     douts = [int(w.shape[1]) for w in weights]
     Fw = sum(douts)
-    zcat = ws.f(B, N, Fw)
-    zb = bfbuf(ws, B, N, Fw)
-    offs = [sum(douts[:l]) for l in range(L)]
-    aligned = all(o % 8 == 0 for o in offs)
     ctx = StackCtxTC()
     ctx.B, ctx.N, ctx.douts, ctx.F, ctx.adjb, ctx.nb, ctx.bn = B, N, douts, Fw, adjb, nb, bn
-    ctx.weights, ctx.biases, ctx.zcat, ctx.layers = weights, biases, zcat, []
-    nbp = E._p(nb)
-    lim = int(nb is not None)
-    cur, cur_d = xb, din
-    zp = zcat.data_ptr()
+    ctx.weights, ctx.biases, ctx.layers = weights, biases, []
+    ctx.zcat = ws.f(B, N, Fw)
+    ctx.zb = bfbuf(ws, B, N, Fw)
+    ctx.offs = [sum(douts[:l]) for l in range(L)]
+    ctx.aligned = all(o % 8 == 0 for o in ctx.offs)
+    ctx.cur, ctx.cur_d = xb, din
+    return ctx
+
+
+def _layer_forward(ws, ctx, l, ub, hb2=None):
+    """Layer l of a stack given its U = A.X operand `ub` (bf16 Op, possibly a column half of a wider buffer):
+    Y = normalize(U.W + b) with the row norm and the BatchNorm row sums taken in the GEMM epilogue, then
+    H = BN(relu(Y)) written once as fp32 (concat slot) and bf16 (concat operand slot, plus `hb2` if given)."""
+    st = E._stream()
+    B, N, Fw, zb = ctx.B, ctx.N, ctx.F, ctx.zb
+    L = len(ctx.weights)
+    last = l == L - 1
+    dout, off = ctx.douts[l], ctx.offs[l]
+    cur, cur_d = ctx.cur, ctx.cur_d
+    w = ctx.weights[l]
     rows = B * N
-    for l in range(L):
-        last = l == L - 1
-        dout, off = douts[l], offs[l]
-        w = weights[l]
-        wb = cvt(ws, w.data_ptr(), dout, cur_d, dout)                                   # [din, r8(dout)]
+    zp = ctx.zcat.data_ptr()
+    wb = cvt(ws, w.data_ptr(), dout, cur_d, dout)                                   # [din, r8(dout)]
+    slot = zp + off * 4
+    # bf16 operand copy of this layer's output: a column slot of zb when 16-byte aligned, else its own buffer
+    hb = Op(zb.ptr + off * 2, zb.ld, zb.sb, zb.t) if ctx.aligned else bfbuf(ws, B, N, dout)
+    hb_flat = Op(hb.ptr, hb.ld, 0)
+    if last:
+        y, y_ptr, ldy = None, slot, Fw
+    else:
+        y = ws.f(B, N, dout)
+        y_ptr, ldy = y.data_ptr(), dout
+    rnorm = ws.f(B, N)
+    use_bn = bool(ctx.bn and not last)
+    uflat, wflat = Op(ub.ptr, ub.ld, 0), Op(wb.ptr, wb.ld, 0)
+    mean = invstd = None
+    if dout <= 256:
+        rowstat = ws.f(rows, 2) if use_bn else None
+        _norm_gemm(uflat, wflat, rows, dout, cur_d, E._p(ctx.biases[l]), (y_ptr, ldy, 0), hb_flat if last else None,
+                   rnorm.data_ptr(), E._p(rowstat), 1)
+        if use_bn:
+            mean, invstd = ws.f(N), ws.f(N)
+            call('gp_bn_finalize', rowstat.data_ptr(), B, N, dout, mean.data_ptr(), invstd.data_ptr(), st)
+        if not last:
+            call('gp_bn_apply', y_ptr, ldy, E._p(mean), E._p(invstd), B, N, dout, 1, int(use_bn), slot, Fw,
+                 hb.ptr, hb.ld, None if hb2 is None else hb2.ptr, 0 if hb2 is None else hb2.ld, st)
+    else:
+        # wide layer (e.g. the assignment GCN's last layer, dout = K): plain GEMM, then one normalize pass
+        tcgemm(uflat, KM, wflat, MN, rows, dout, cur_d, 1, Cf=(y_ptr, ldy, 0), bias=E._p(ctx.biases[l]))
+        yb_ok = dout % 4 == 0 and dout <= 1024 and ldy % 4 == 0
+        call('gp_bias_normalize_x', y_ptr, None, rnorm.data_ptr(), C.c_longlong(rows), dout, ldy, 1,
+             hb.ptr if (last and yb_ok) else None, hb.ld, st)
+        if last and not yb_ok:
+            cvt(ws, slot, Fw, rows, dout, out=hb_flat)
+        if not last:
+            if use_bn:
+                mean, invstd = ws.f(N), ws.f(N)
+            call('gp_relu_bn_fwd', y_ptr, slot, Fw, E._p(mean), E._p(invstd), B, N, dout, 1, int(use_bn), st)
+            cvt(ws, slot, Fw, rows, dout, out=hb_flat)
+            if hb2 is not None:
+                cvt(ws, slot, Fw, rows, dout, out=Op(hb2.ptr, hb2.ld, 0))
+    ctx.layers.append((cur, cur_d, dout, off, ub, y, rnorm, mean, invstd, wb))
+    ctx.cur, ctx.cur_d = hb, dout
+
+
+def _stack_end(ws, ctx):
+    if not ctx.aligned:
+        cvt(ws, ctx.zcat.data_ptr(), ctx.F, ctx.B * ctx.N, ctx.F, out=ctx.zb)
+    return ctx.zcat, ctx.zb, ctx
+
+
+def stack_forward(ws, xb, din, adjb, nb, B, N, weights, biases, bn, u0=None):
+    """TC version of engine.stack_forward (add_self unsupported).  xb/adjb: bf16 operands.
+    Per layer:  U = A.X (tcgen05)  ->  _layer_forward.
+    u0: optional precomputed U of the first layer (shared with another stack that has the same A and X).
+    Returns (zcat fp32 [B,N,F], zb bf16 operand of the same concat, ctx)."""
+    ctx = _stack_begin(ws, xb, din, adjb, nb, B, N, weights, biases, bn)
+    nbp, lim = E._p(nb), int(nb is not None)
+    for l in range(len(weights)):
         if l == 0 and u0 is not None:
             ub = u0
         else:
-            ub = bfbuf(ws, B, N, cur_d)
+            ub = bfbuf(ws, B, N, ctx.cur_d)
             # U = A.X : A K-major, X N-major
-            tcgemm(adjb, KM, cur, MN, N, cur_d, N, B, Cb=ub, lim=nbp, lim_m=lim, lim_k=lim)
-        slot = zp + off * 4
-        # bf16 operand copy of this layer's output: a column slot of zb when 16-byte aligned, else its own buffer
-        hb = Op(zb.ptr + off * 2, zb.ld, zb.sb, zb.t) if aligned else bfbuf(ws, B, N, dout)
-        hb_flat = Op(hb.ptr, hb.ld, 0)
-        if last:
-            y, y_ptr, ldy = None, slot, Fw
-        else:
-            y = ws.f(B, N, dout)
-            y_ptr, ldy = y.data_ptr(), dout
-        rnorm = ws.f(B, N)
-        use_bn = bool(bn and not last)
-        uflat, wflat = Op(ub.ptr, ub.ld, 0), Op(wb.ptr, wb.ld, 0)
-        mean = invstd = None
-        if dout <= 256:
-            rowstat = ws.f(rows, 2) if use_bn else None
-            _norm_gemm(uflat, wflat, rows, dout, cur_d, E._p(biases[l]), (y_ptr, ldy, 0), hb_flat if last else None,
-                       rnorm.data_ptr(), E._p(rowstat), 1)
-            if use_bn:
-                mean, invstd = ws.f(N), ws.f(N)
-                call('gp_bn_finalize', rowstat.data_ptr(), B, N, dout, mean.data_ptr(), invstd.data_ptr(), st)
-            if not last:
-                call('gp_bn_apply', y_ptr, ldy, E._p(mean), E._p(invstd), B, N, dout, 1, int(use_bn), slot, Fw,
-                     hb.ptr, hb.ld, st)
-        else:
-            # wide layer (e.g. the assignment GCN's last layer, dout = K): plain GEMM, then one normalize pass
-            tcgemm(uflat, KM, wflat, MN, rows, dout, cur_d, 1, Cf=(y_ptr, ldy, 0), bias=E._p(biases[l]))
-            yb_ok = dout % 4 == 0 and dout <= 1024 and ldy % 4 == 0
-            call('gp_bias_normalize_x', y_ptr, None, rnorm.data_ptr(), C.c_longlong(rows), dout, ldy, 1,
-                 hb.ptr if (last and yb_ok) else None, hb.ld, st)
-            if last and not yb_ok:
-                cvt(ws, slot, Fw, rows, dout, out=hb_flat)
-            if not last:
-                if use_bn:
-                    mean, invstd = ws.f(N), ws.f(N)
-                call('gp_relu_bn_fwd', y_ptr, slot, Fw, E._p(mean), E._p(invstd), B, N, dout, 1, int(use_bn), st)
-                cvt(ws, slot, Fw, rows, dout, out=hb_flat)
-        ctx.layers.append((cur, cur_d, dout, off, ub, y, rnorm, mean, invstd, wb))
-        cur, cur_d = hb, dout
-    if not aligned:
-        cvt(ws, zp, Fw, rows, Fw, out=zb)
-    return zcat, zb, ctx
+            tcgemm(adjb, KM, ctx.cur, MN, N, ctx.cur_d, N, B, Cb=ub, lim=nbp, lim_m=lim, lim_k=lim)
+        _layer_forward(ws, ctx, l, ub)
+    return _stack_end(ws, ctx)
 
 
-def stack_backward(ws, ctx, dz_ptr, lddz, dout_ptr, arg_ptr, ldo, need_dx, dadj):
+def dual_ok(wE, wA):
+    """Two GCN stacks over the same adjacency can run in lock-step (one A.X per layer for both) when they have the
+    same depth and their hidden widths keep both column halves 16-byte aligned and inside the fused-epilogue limit."""
+    if len(wE) != len(wA) or len(wE) < 2:
+        return False
+    for l in range(len(wE) - 1):
+        de, da = int(wE[l].shape[1]), int(wA[l].shape[1])
+        if de % 8 or da % 8 or de > 256 or da > 256:
+            return False
+    return True
+
+
+def dual_stack_forward(ws, xb, din, xab, dina, adjb, nb, B, N, wE, bE, bnE, wA, bA, bnA):
+    """Embedding GCN and assignment GCN of one level in lock-step: both multiply the SAME
+    adjacency, so layer l's two inputs sit side by side in one [B,N,He+Ha] operand and ONE pass over A produces
+    both U's (A.X at 128 columns is HBM-bound on reading A: sharing the pass halves that traffic)."""
+    cE = _stack_begin(ws, xb, din, adjb, nb, B, N, wE, bE, bnE)
+    cA = _stack_begin(ws, xab, dina, adjb, nb, B, N, wA, bA, bnA)
+    nbp, lim = E._p(nb), int(nb is not None)
+    L = len(wE)
+    hcat = None
+    for l in range(L):
+        if l == 0:
+            uE = bfbuf(ws, B, N, din)
+            tcgemm(adjb, KM, xb, MN, N, din, N, B, Cb=uE, lim=nbp, lim_m=lim, lim_k=lim)
+            if xab is xb:                                # same A, same X: one U for both first layers
+                uA = uE
+            else:
+                uA = bfbuf(ws, B, N, dina)
+                tcgemm(adjb, KM, xab, MN, N, dina, N, B, Cb=uA, lim=nbp, lim_m=lim, lim_k=lim)
+        else:
+            de, da = cE.douts[l - 1], cA.douts[l - 1]
+            ucat = bfbuf(ws, B, N, de + da)
+            tcgemm(adjb, KM, hcat, MN, N, de + da, N, B, Cb=ucat, lim=nbp, lim_m=lim, lim_k=lim)
+            uE = Op(ucat.ptr, ucat.ld, ucat.sb, ucat.t)
+            uA = Op(ucat.ptr + de * 2, ucat.ld, ucat.sb, ucat.t)
+        h2E = h2A = None
+        if l < L - 1:
+            de, da = cE.douts[l], cA.douts[l]
+            hcat = bfbuf(ws, B, N, de + da)              # next layer's side-by-side input, filled by both tails
+            h2E = Op(hcat.ptr, hcat.ld, hcat.sb, hcat.t)
+            h2A = Op(hcat.ptr + de * 2, hcat.ld, hcat.sb, hcat.t)
+        _layer_forward(ws, cE, l, uE, h2E)
+        _layer_forward(ws, cA, l, uA, h2A)
+    return _stack_end(ws, cE), _stack_end(ws, cA)
+
+
+def _layer_backward_head(ws, ctx, l, dz_ptr, lddz, dxn, lddxn, dout_ptr, arg_ptr, ldo):
+    """Element-wise tail backward of layer l (bf16 dV + db in ONE pass over HBM; Hhat is recomputed from Y and the
+    saved statistics) and dW = U^T dV.  Returns (dvb, dw, db)."""
     st = E._stream()
     B, N, Fw = ctx.B, ctx.N, ctx.F
     L = len(ctx.layers)
+    xb, din, dout, off, ub, y, rnorm, mean, invstd, wb = ctx.layers[l]
+    last = l == L - 1
+    rows = B * N
+    slot = ctx.zcat.data_ptr() + off * 4
+    dvb = bfbuf(ws, 1, rows, dout)
+    has_b = ctx.biases[l] is not None
+    db = ws.f(dout) if has_b else None
+    q = GpLayerBwd()
+    q.dz, q.lddz = (None if dz_ptr is None else dz_ptr + off * 4), lddz
+    q.dxn, q.lddxn = dxn, lddxn
+    q.dout = None if dout_ptr is None else dout_ptr + off * 4
+    q.argidx = None if arg_ptr is None else arg_ptr + off * 4
+    q.ldo = ldo
+    use_bn = bool(ctx.bn and not last)
+    q.h, q.ldh = None, Fw
+    q.y, q.ldy = (slot, Fw) if last else (E._p(y), dout)
+    q.rnorm, q.mean, q.invstd = E._p(rnorm), E._p(mean), E._p(invstd)
+    q.B, q.N, q.d = B, N, dout
+    q.relu, q.bn, q.normalize = int(not last), int(use_bn), 1
+    q.dv, q.dv_bf16, q.lddvb = None, dvb.ptr, dvb.ld
+    q.db = E._p(db)
+    q.ws = None
+    wsf = ws.f(int(load().gp_gcn_layer_bwd_ws_x(C.byref(q)))) if has_b else None
+    q.ws = E._p(wsf)
+    call('gp_gcn_layer_bwd_x', C.byref(q), st)
+    # dW = U^T dV : U stored [rows, din] = M-major A ; dV N-major B ; split-K over the rows
+    dw = ws.f(din, dout)
+    tcgemm(Op(ub.ptr, ub.ld, 0), MN, Op(dvb.ptr, dvb.ld, 0), MN, din, dout, rows, 1, Cf=(dw.data_ptr(), dout, 0),
+           split_k=pick_split(din, dout, rows))
+    return dvb, dw, db
+
+
+def _layer_du(ws, ctx, l, dvb, dub):
+    """dU = dV W^T -> bf16 `dub` ([B*N, din] view, possibly a column half): dV K-major; W stored [din, dout] = K-major B."""
+    xb, din, dout, off, ub, y, rnorm, mean, invstd, wb = ctx.layers[l]
+    rows = ctx.B * ctx.N
+    tcgemm(Op(dvb.ptr, dvb.ld, 0), KM, Op(wb.ptr, wb.ld, 0), KM, rows, din, dout, 1, Cb=Op(dub.ptr, dub.ld, 0))
+
+
+def stack_backward(ws, ctx, dz_ptr, lddz, dout_ptr, arg_ptr, ldo, need_dx, dadj):
+    B, N = ctx.B, ctx.N
+    L = len(ctx.layers)
     grads = [None] * L
     dxn = None
-    zp = ctx.zcat.data_ptr()
     nbp = E._p(ctx.nb)
     lim = int(ctx.nb is not None)
-    rows = B * N
     for l in reversed(range(L)):
-        xb, din, dout, off, ub, y, rnorm, mean, invstd, wb = ctx.layers[l]
-        last = l == L - 1
-        slot = zp + off * 4
-        # element-wise tail backward: bf16 dV (operand of the contractions below) + db in ONE pass over HBM;
-        # Hhat is recomputed from Y and the saved statistics instead of re-reading the BN output
-        dvb = bfbuf(ws, 1, rows, dout)
-        has_b = ctx.biases[l] is not None
-        db = ws.f(dout) if has_b else None
-        q = GpLayerBwd()
-        q.dz, q.lddz = (None if dz_ptr is None else dz_ptr + off * 4), lddz
-        q.dxn = E._p(dxn)
-        q.dout = None if dout_ptr is None else dout_ptr + off * 4
-        q.argidx = None if arg_ptr is None else arg_ptr + off * 4
-        q.ldo = ldo
-        use_bn = bool(ctx.bn and not last)
-        q.h, q.ldh = None, Fw
-        q.y, q.ldy = (slot, Fw) if last else (E._p(y), dout)
-        q.rnorm, q.mean, q.invstd = E._p(rnorm), E._p(mean), E._p(invstd)
-        q.B, q.N, q.d = B, N, dout
-        q.relu, q.bn, q.normalize = int(not last), int(use_bn), 1
-        q.dv, q.dv_bf16, q.lddvb = None, dvb.ptr, dvb.ld
-        q.db = E._p(db)
-        q.ws = None
-        wsf = ws.f(int(load().gp_gcn_layer_bwd_ws_x(C.byref(q)))) if has_b else None
-        q.ws = E._p(wsf)
-        call('gp_gcn_layer_bwd_x', C.byref(q), st)
-        # dW = U^T dV : U stored [rows, din] = M-major A ; dV N-major B ; split-K over the rows
-        dw = ws.f(din, dout)
-        tcgemm(Op(ub.ptr, ub.ld, 0), MN, Op(dvb.ptr, dvb.ld, 0), MN, din, dout, rows, 1, Cf=(dw.data_ptr(), dout, 0),
-               split_k=pick_split(din, dout, rows))
+        xb, din = ctx.layers[l][0], ctx.layers[l][1]
+        dvb, dw, db = _layer_backward_head(ws, ctx, l, dz_ptr, lddz, E._p(dxn), 0, dout_ptr, arg_ptr, ldo)
         grads[l] = (dw, db)
         need_dx_l = need_dx or l > 0
         dx = None
         if need_dx_l or dadj is not None:
-            # dU = dV W^T : dV K-major ; B[n=din, k=dout] = W stored [din rows, dout cols] = K-major
             dub = bfbuf(ws, B, N, din)
-            tcgemm(Op(dvb.ptr, dvb.ld, 0), KM, Op(wb.ptr, wb.ld, 0), KM, rows, din, dout, 1, Cb=Op(dub.ptr, dub.ld, 0))
+            _layer_du(ws, ctx, l, dvb, dub)
             if need_dx_l:
                 # dX = A^T dU : A stored [k rows, m cols] = M-major ; dU N-major
                 dx = ws.f(B, N, din)
@@ -260,6 +339,35 @@ def stack_backward(ws, ctx, dz_ptr, lddz, dout_ptr, arg_ptr, ldo, need_dx, dadj)
                 tcgemm(dub, KM, xb, KM, N, N, din, B, Cf=(dadj.data_ptr(), N, N * N), beta=1.0)
         dxn = dx
     return grads, dxn
+
+
+def dual_stack_backward(ws, cE, cA, dzE_ptr, lddzE, doutE_ptr, argE_ptr, ldo, dzA_ptr, lddzA):
+    """Backward of dual_stack_forward (level 0: no dX of the first layer, no dA): per layer both tails, then ONE
+    dX = A^T [dU_e | dU_a] pass over the adjacency for both stacks."""
+    B, N = cE.B, cE.N
+    L = len(cE.layers)
+    gE, gA = [None] * L, [None] * L
+    nbp, lim = E._p(cE.nb), int(cE.nb is not None)
+    dxcat, wcat, de_in = None, 0, 0
+    for l in reversed(range(L)):
+        dinE, dinA = cE.layers[l][1], cA.layers[l][1]
+        if dxcat is None:
+            xE = xA = None
+        else:
+            xE, xA = dxcat.data_ptr(), dxcat.data_ptr() + de_in * 4
+        dvE, dw, db = _layer_backward_head(ws, cE, l, dzE_ptr, lddzE, xE, wcat, doutE_ptr, argE_ptr, ldo)
+        gE[l] = (dw, db)
+        dvA, dw, db = _layer_backward_head(ws, cA, l, dzA_ptr, lddzA, xA, wcat, None, None, 0)
+        gA[l] = (dw, db)
+        if l > 0:
+            wcat, de_in = dinE + dinA, dinE
+            ducat = bfbuf(ws, B, N, wcat)
+            _layer_du(ws, cE, l, dvE, Op(ducat.ptr, ducat.ld, 0))
+            _layer_du(ws, cA, l, dvA, Op(ducat.ptr + dinE * 2, ducat.ld, 0))
+            dxcat = ws.f(B, N, wcat)
+            tcgemm(cE.adjb, MN, ducat, MN, N, wcat, N, B, Cf=(dxcat.data_ptr(), wcat, N * wcat), lim=nbp, lim_m=lim,
+                   lim_k=lim)
+    return gE, gA
 
 
 # ------------------------------------------------------------------------------------------

@@ -142,8 +142,11 @@ int gp_bgemm_bf16_norm(const gp_gemm_bf16x* g, float* rnorm, float* rowstat, int
 /* mean[n], invstd[n] over (batch, feature) from rowstat[b*N + n] (biased variance, eps 1e-5). */
 int gp_bn_finalize(const float* rowstat, int B, int N, int d, float* mean, float* invstd, gp_stream_t stream);
 /* H[b,n,:] = (relu?(Y[b,n,:]) - mean[n]) * invstd[n] -> fp32 h (row stride ldh) and/or bf16 copy. */
+/* h_bf16_2 (optional): a second bf16 destination -- the column half of the operand that feeds ONE A.X
+ * contraction for two GCN stacks sharing the adjacency (embedding + assignment GCN). */
 int gp_bn_apply(const float* y, long long ldy, const float* mean, const float* invstd, int B, int N, int d,
-                int relu, int bn, float* h, long long ldh, void* h_bf16, long long ldhb, gp_stream_t stream);
+                int relu, int bn, float* h, long long ldh, void* h_bf16, long long ldhb, void* h_bf16_2,
+                long long ldhb2, gp_stream_t stream);
 /* gp_bias_normalize_f32 / gp_softmax_mask_fwd / _bwd with the bf16 operand copy written in the same pass;
  * softmax backward can also return dcol = colsum(dT) (the assign_pred bias gradient, encoders.py:1273);
  * ws >= (148*16 + 256) * K floats. */
@@ -223,6 +226,7 @@ typedef struct gp_layer_bwd {
   int B, N, d, relu, bn, normalize;
   float* dv; void* dv_bf16; long long lddvb;
   float* db; float* ws;
+  long long lddxn;           /* row stride of dxn in elements; 0 = contiguous (d) */
 } gp_layer_bwd;
 int gp_gcn_layer_bwd_x(const gp_layer_bwd* q, gp_stream_t stream);
 long long gp_gcn_layer_bwd_ws(int B, int N, int d, int bn);

@@ -106,3 +106,38 @@ def test_bf16_mode_nonsymmetric_and_u8_feed():
         assert np.array_equal(outs[(sym, 'f32')][0], outs[(sym, 'u8')][0])
         # gradients: the split-K weight-gradient GEMMs accumulate with atomics (order varies run to run)
         assert rel_l2(outs[(sym, 'u8')][1], outs[(sym, 'f32')][1]) < 1e-5
+
+
+def test_dual_stack_matches_separate_stacks(monkeypatch):
+    """Lock-step embedding + assignment GCN (one A.X / A^T.dU pass per layer for both) must give the same result
+    as running the two stacks separately (GP_NO_DUAL=1): same kernels, same operands, only the launch grouping
+    differs -- identical forward, gradients equal up to the split-K atomics' summation order."""
+    from graph_pooling_b200 import encoders
+    N, D, H, C, B = 160, 12, 32, 3, 4
+    torch.manual_seed(3)
+    mc = encoders.SoftPoolingGcnEncoder(N, D, H, H, C, 3, H, assign_ratio=0.25).cuda()
+    mc.precision = 1
+    with torch.no_grad():
+        for k, p in mc.named_parameters():
+            if k.endswith('bias'):
+                p.normal_(0, 0.2)
+    x, adj, nb, label = synth_batch(5, B, N, D, 40, N, C, 0.06)
+    res = {}
+    for mode, same_x in (('dual', True), ('sep', True), ('dual', False), ('sep', False)):
+        if mode == 'sep':
+            monkeypatch.setenv('GP_NO_DUAL', '1')
+        else:
+            monkeypatch.delenv('GP_NO_DUAL', raising=False)
+        mc.zero_grad()
+        xc, ac = torch.tensor(x).cuda(), torch.tensor(adj).cuda()
+        xa = xc if same_x else (xc * 0.5 + 0.1).contiguous()
+        yp = mc(xc, ac, nb, assign_x=xa)
+        loss = mc.loss(yp, torch.tensor(label).cuda(), ac, nb)
+        loss.backward()
+        torch.cuda.synchronize()
+        res[(mode, same_x)] = (yp.detach().cpu().numpy(), loss.item(),
+                               np.concatenate([p.grad.cpu().numpy().ravel() for p in mc.parameters()]))
+    for same_x in (True, False):
+        a, b = res[('dual', same_x)], res[('sep', same_x)]
+        assert np.array_equal(a[0], b[0]) and a[1] == b[1]
+        assert rel_l2(a[2], b[2]) < 1e-5

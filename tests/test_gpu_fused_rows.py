@@ -66,9 +66,11 @@ def test_norm_gemm_and_bn(B, N, din, dout, off, Fw, relu):
     y32 = ycat[:, off:off + dout].contiguous()
     h = torch.zeros(rows, Fw, device='cuda')
     hbb = torch.zeros(rows, (dout + 7) // 8 * 8, device='cuda', dtype=torch.bfloat16)
+    hbb2 = torch.zeros(rows, (dout + 7) // 8 * 8 + 16, device='cuda', dtype=torch.bfloat16)
     call('gp_bn_apply', y32.data_ptr(), dout, mean.data_ptr(), invstd.data_ptr(), B, N, dout, relu, 1,
-         h.data_ptr() + off * 4, Fw, hbb.data_ptr(), hbb.shape[1], st())
+         h.data_ptr() + off * 4, Fw, hbb.data_ptr(), hbb.shape[1], hbb2.data_ptr() + 8 * 2, hbb2.shape[1], st())
     torch.cuda.synchronize()
+    assert torch.equal(hbb2[:, 8:8 + dout], hbb[:, :dout])          # second bf16 destination (column half)
     r3 = r.reshape(B, N, dout)
     h_ref = orc.bn_per_node(r3).reshape(rows, dout)
     assert rel_l2(mean.cpu().numpy(), r3.mean(dim=(0, 2)).numpy()) < 1e-5
