@@ -95,7 +95,7 @@ _PROTOS = {
                     c_f, c_i, c_f],
     'gp_linkloss_fwd': [c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f, c_f],
     'gp_loss_finalize': [c_f, c_i, C.c_double, c_f, c_f, c_f, c_f],
-    'gp_linkloss_tc': [c_f, c_ll, c_f, c_ll, c_f, c_i, c_i, c_i, c_f, c_f, c_ll, c_i, c_f],
+    'gp_linkloss_tc': [c_f, c_ll, c_f, c_ll, c_f, c_i, c_i, c_i, c_f, c_f, c_ll, c_i, c_f, c_f],
     'gp_frob_link_fwd': [c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f, c_f],
     'gp_frob_finalize': [c_f, c_i, c_i, c_f, c_f, c_f, c_f, c_f, c_f],
     'gp_scale_rows_batch': [c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_ll, c_f, c_ll, c_i, c_f],

@@ -51,6 +51,7 @@ struct Params {
   const __nv_bfloat16* adjb; long long ldadj, sadjb; float* partial; int link_mode;   // EPI == 1
   float* rnorm; float2* rowstat; int stat_relu;                        // EPI == 2
   const int32_t* cond; int cond_npairs; float cond_alpha;              // device-side switch (see gp_gemm_bf16x)
+  const int32_t* adj_flags; long long sym_total; int sym_per_graph;    // EPI == 1: gp_adj_prepare flags, upper-band tiles
 };
 
 struct Work {
@@ -82,7 +83,8 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try(bar, parity)) {
-    if (++spins > (1u << 26)) { __trap(); }     // protocol bug: fail loudly instead of hanging the GPU
+    if (++spins > 4) __nanosleep(40);           // leave the issue slots to the epilogue warps while polling
+    if (spins > (1u << 24)) { __trap(); }       // protocol bug: fail loudly instead of hanging the GPU
   }
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
@@ -133,13 +135,36 @@ struct Smem {
   static constexpr int kBytes = STAGES * kStage + kStaging + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*bias*/;
 };
 
-__device__ __forceinline__ Work get_work(const Params& p, long long w, int npairs) {
+template <int BN>
+__device__ __forceinline__ Work get_work(const Params& p, long long w, int npairs, bool sym_upper) {
   Work k;
   const int split = p.split_k > 1 ? p.split_k : 1;
-  const int nt = (int)(w % p.tiles_n);
-  const long long r = w / p.tiles_n;
-  const int mt = (int)(r % p.tiles_m);
-  const int z = (int)(r / p.tiles_m);
+  int nt, mt, z;
+  if (sym_upper) {
+    // compact enumeration of the tiles that intersect the upper diagonal band (n0 + BN > m0), so that the
+    // persistent CTAs share them evenly; work items beyond sym_total are empty (they only zero their partials)
+    if (w >= p.sym_total) {
+      k.b = 0; k.ks = 0; k.m0 = 0; k.n0 = 0; k.Me = 0; k.Ne = 0;
+#pragma unroll
+      for (int q = 0; q < kMaxPairs; ++q) k.kt[q] = 0;
+      k.kt0 = k.kt1 = 0;
+      return k;
+    }
+    z = (int)(w / p.sym_per_graph);
+    int r = (int)(w - (long long)z * p.sym_per_graph);
+    mt = 0; nt = 0;
+    for (; mt < p.tiles_m; ++mt) {
+      const int first = (mt * BM) / BN;
+      const int c = p.tiles_n > first ? p.tiles_n - first : 0;
+      if (r < c) { nt = first + r; break; }
+      r -= c;
+    }
+  } else {
+    nt = (int)(w % p.tiles_n);
+    const long long r = w / p.tiles_n;
+    mt = (int)(r % p.tiles_m);
+    z = (int)(r / p.tiles_m);
+  }
   k.b = z / split; k.ks = z % split;
   k.m0 = mt * BM; k.n0 = nt;        // n0 scaled by BN by the caller
   int l = 0x7fffffff;
@@ -161,12 +186,14 @@ __device__ __forceinline__ Work get_work(const Params& p, long long w, int npair
   return k;
 }
 
+// sym_upper (fused link loss over a symmetric adjacency): P = S S^T and G are symmetric, so tiles lying entirely
+// below the diagonal band are not computed -- the mirrored tiles' epilogues write their transposes.
 template <int BN>
-__device__ __forceinline__ void finish_work(const Params& p, Work& k) {
+__device__ __forceinline__ void finish_work(const Params& p, Work& k, bool sym_upper = false) {
   k.n0 *= BN;
   const int split = p.split_k > 1 ? p.split_k : 1;
   int tot = k.kt1;
-  const bool live = (k.m0 < k.Me) && (k.n0 < k.Ne);
+  const bool live = (k.m0 < k.Me) && (k.n0 < k.Ne) && !(sym_upper && k.n0 + BN <= k.m0);
   if (!live) tot = 0;
   const int per = (tot + split - 1) / split;
   k.kt0 = min(tot, k.ks * per);
@@ -228,6 +255,26 @@ __device__ __forceinline__ uint4 bce_row8(const float (&pv)[8], const uint4 aw, 
   return make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]), pack_bf16x2(g[6], g[7]));
 }
 
+// {0,1} adjacency (flag from gp_adj_prepare), branch-free: with s = +1 / -1 for a = 1 / 0,
+//   x = s*min(P,1) + (a ? eps : 1+eps) ;  loss = -ln x (accumulated in log2 units) ;  G = -s / x  (0 where P > 1).
+__device__ __forceinline__ uint4 bce01_row8(const float (&pv)[8], const uint4 aw, float* l2) {
+  const uint32_t wsrc[4] = {aw.x, aw.y, aw.z, aw.w};
+  float g[8];
+  float acc = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const uint32_t bits = (e & 1) ? (wsrc[e >> 1] >> 16) : (wsrc[e >> 1] & 0xffffu);
+    const bool one = bits != 0u;
+    const float s = one ? 1.f : -1.f;
+    const float x = fmaf(s, fminf(pv[e], 1.f), one ? kEpsLink : 1.f + kEpsLink);
+    acc += lg2_approx(x);
+    const float gg = -s * rcp_approx(x);
+    g[e] = pv[e] > 1.f ? 0.f : gg;
+  }
+  *l2 += acc;
+  return make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]), pack_bf16x2(g[6], g[7]));
+}
+
 // ---- kernel -------------------------------------------------------------------------------------
 // EW epilogue warps (8 or 16): warps 0..EW-1 epilogue, EW = TMA producer, EW+1 = MMA issuer.
 template <int BN, int STAGES, int EPI, int EW>
@@ -276,7 +323,15 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
   int npairs = p.npairs;
   float alpha_mul = 1.f;
   long long total_work = p.total_work;
-  if (p.cond != nullptr && *p.cond == 0) {
+  bool sym_upper = false, adj01 = false;
+  if (EPI == 1) {
+    if (p.adj_flags != nullptr) {
+      // link loss over a symmetric adjacency: compute the upper band only, mirror the rest (BCE mode: the
+      // Frobenius finalisation needs per-graph partial blocks, which the compact enumeration does not keep)
+      sym_upper = p.adj_flags[0] == 0 && p.link_mode == 0;
+      adj01 = p.adj_flags[1] == 0;
+    }
+  } else if (p.cond != nullptr && *p.cond == 0) {
     npairs = p.cond_npairs;
     alpha_mul = p.cond_alpha;
     if (npairs == 0) total_work = 0;
@@ -292,8 +347,8 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
     if (lane == 0) {
       uint32_t it = 0;                                   // running stage counter across tiles
       for (long long w = blockIdx.x; w < total_work; w += gridDim.x) {
-        Work k = get_work(p, w, npairs);
-        finish_work<BN>(p, k);
+        Work k = get_work<BN>(p, w, npairs, sym_upper);
+        finish_work<BN>(p, k, sym_upper);
         int pos = 0;
         for (int q = 0; q < npairs; ++q) {
           const int lo = max(k.kt0, pos), hi = min(k.kt1, pos + k.kt[q]);
@@ -326,8 +381,8 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
     if (lane == 0) {
       uint32_t it = 0, nacc = 0;
       for (long long w = blockIdx.x; w < total_work; w += gridDim.x) {
-        Work k = get_work(p, w, npairs);
-        finish_work<BN>(p, k);
+        Work k = get_work<BN>(p, w, npairs, sym_upper);
+        finish_work<BN>(p, k, sym_upper);
         if (k.kt1 <= k.kt0) continue;
         const uint32_t a = nacc & 1, aph = (nacc >> 1) & 1;
         mbar_wait(tempty_bar(a), aph ^ 1);               // epilogue has drained this accumulator
@@ -380,8 +435,8 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
                         (p.sCbb & 7) == 0;
     uint32_t nacc = 0;
     for (long long w = blockIdx.x; w < total_work; w += gridDim.x) {
-      Work k = get_work(p, w, npairs);
-      finish_work<BN>(p, k);
+      Work k = get_work<BN>(p, w, npairs, sym_upper);
+      finish_work<BN>(p, k, sym_upper);
       const bool has_acc = k.kt1 > k.kt0;
       const uint32_t a = nacc & 1, aph = (nacc >> 1) & 1;
       if (has_acc) {
@@ -519,20 +574,26 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
               aw[i] = make_uint4(t[0], t[1], t[2], t[3]);
             }
           }
-          bool is01 = true;                              // bf16 0.0 = 0x0000, 1.0 = 0x3f80
+          bool fast = adj01;                             // kernel-uniform flag from gp_adj_prepare, or ...
+          if (p.adj_flags == nullptr) {                  // ... a warp-uniform test of this chunk's entries
+            bool is01 = true;                            // bf16 0.0 = 0x0000, 1.0 = 0x3f80
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint32_t t[4] = {aw[i].x, aw[i].y, aw[i].z, aw[i].w};
+            for (int i = 0; i < 4; ++i) {
+              const uint32_t t[4] = {aw[i].x, aw[i].y, aw[i].z, aw[i].w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const uint32_t z = t[e] & ~0x3f803f80u;    // any bit outside the 1.0 pattern -> not {0,1}
-              const uint32_t lo = t[e] & 0xffffu, hi = t[e] >> 16;
-              is01 = is01 && z == 0u && (lo == 0u || lo == 0x3f80u) && (hi == 0u || hi == 0x3f80u);
+              for (int e = 0; e < 4; ++e) {
+                const uint32_t z = t[e] & ~0x3f803f80u;  // any bit outside the 1.0 pattern -> not {0,1}
+                const uint32_t lo = t[e] & 0xffffu, hi = t[e] >> 16;
+                is01 = is01 && z == 0u && (lo == 0u || lo == 0x3f80u) && (hi == 0u || hi == 0x3f80u);
+              }
             }
+            fast = __all_sync(0xffffffffu, is01);
           }
-          const bool fast = __all_sync(0xffffffffu, is01);
           const bool frob = p.link_mode == 1;
+          // symmetric mode: does this chunk's mirror image (rows nbase.., cols row0..) fall into a skipped tile?
+          const bool mirror = sym_upper && ((row0 / BN) * BN + BN <= (nbase / BM) * BM);
           float l2 = 0.f;
+          uint4 gwv[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int r = 8 * i + (lane >> 2), row = row0 + r;
@@ -541,11 +602,13 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
             const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
             if (interior) {
               const uint4 gw = frob ? bce_row8<2, true>(pv, aw[i], 8, &l2)
-                                    : (fast ? bce_row8<1, true>(pv, aw[i], 8, &l2) : bce_row8<0, true>(pv, aw[i], 8, &l2));
+                                    : (fast ? bce01_row8(pv, aw[i], &l2) : bce_row8<0, true>(pv, aw[i], 8, &l2));
               if (gb != nullptr) *reinterpret_cast<uint4*>(gb + (long long)row * p.ldCb + n) = gw;
+              gwv[i] = gw;
             } else {
               const int nvalid = row < k.Me ? min(8, max(0, k.Ne - n)) : 0;
               const uint4 gw = frob ? bce_row8<2, false>(pv, aw[i], nvalid, &l2) : bce_row8<0, false>(pv, aw[i], nvalid, &l2);
+              gwv[i] = gw;
               if (gb != nullptr && row < p.M) {
                 __nv_bfloat16* dst = gb + (long long)row * p.ldCb + n;
                 if (vecCb8 && n + 8 <= p.ldCb) {
@@ -554,6 +617,35 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
                   const uint32_t t[4] = {gw.x, gw.y, gw.z, gw.w};
                   for (int e = 0; e < 8; ++e)
                     if (n + e < p.N) *reinterpret_cast<uint16_t*>(dst + e) = (uint16_t)(t[e >> 1] >> (16 * (e & 1)));
+                }
+              }
+            }
+          }
+          if (mirror) {
+            l2 *= 2.f;                                   // the mirrored entries' loss terms are identical
+            if (gb != nullptr) {
+              // G^T chunk: transpose the 32x32 bf16 block through the warp's staging tile (pitch 36 halfwords)
+              uint16_t* tt = reinterpret_cast<uint16_t*>(stg);
+              __syncwarp();                              // every lane has read its P values
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int r = 8 * i + (lane >> 2);
+                const uint32_t t[4] = {gwv[i].x, gwv[i].y, gwv[i].z, gwv[i].w};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) tt[(cc + e) * 36 + r] = (uint16_t)(t[e >> 1] >> (16 * (e & 1)));
+              }
+              __syncwarp();
+              if (interior) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const int tr = 4 * j + (lane >> 3), seg = (lane & 7) * 4;
+                  const uint2 v = *reinterpret_cast<const uint2*>(&tt[tr * 36 + seg]);
+                  *reinterpret_cast<uint2*>(gb + (long long)(nbase + tr) * p.ldCb + row0 + seg) = v;
+                }
+              } else {
+                for (int j = 0; j < 32; ++j) {           // ragged edge: lane = mirrored column, bounds-checked
+                  const int mr = nbase + j, mc = row0 + lane;
+                  if (mr < p.M && mc < p.N) *reinterpret_cast<uint16_t*>(gb + (long long)mr * p.ldCb + mc) = tt[j * 36 + lane];
                 }
               }
             }
@@ -785,6 +877,7 @@ int run(const gp_gemm_bf16x* g, cudaStream_t st) {
   p.adjb = nullptr; p.ldadj = p.sadjb = 0; p.partial = nullptr; p.link_mode = 0;
   p.rnorm = nullptr; p.rowstat = nullptr; p.stat_relu = 0;
   p.cond = g->cond; p.cond_npairs = g->cond_npairs; p.cond_alpha = g->cond_alpha;
+  p.adj_flags = nullptr; p.sym_total = 0; p.sym_per_graph = 0;
   GP_REQUIRE(g->cond == nullptr || (g->cond_npairs >= 0 && g->cond_npairs <= g->npairs), "bgemm_bf16x: bad cond_npairs");
   if (split > 1 && p.beta != 1.f) {
     const long long total = (long long)g->batch * g->M * g->N;
@@ -828,12 +921,14 @@ int run_norm(const gp_gemm_bf16x* g, float* rnorm, float* rowstat, int stat_relu
   p.adjb = nullptr; p.ldadj = p.sadjb = 0; p.partial = nullptr; p.link_mode = 0;
   p.rnorm = rnorm; p.rowstat = reinterpret_cast<float2*>(rowstat); p.stat_relu = stat_relu;
   p.cond = nullptr; p.cond_npairs = 0; p.cond_alpha = 1.f;
+  p.adj_flags = nullptr; p.sym_total = 0; p.sym_per_graph = 0;
   if (BN == 256) return launch<256, 3, 2, 4>(maps, p, st);
   return launch<128, 4, 2, 4>(maps, p, st);
 }
 
 int run_linkloss(const void* s_bf16, long long lds, const void* adj_bf16, long long ldadj, const int32_t* nb,
-                 int B, int N, int K, float* partial, void* g_bf16, long long ldg, int mode, cudaStream_t st) {
+                 int B, int N, int K, float* partial, void* g_bf16, long long ldg, int mode, const int32_t* adj_flags,
+                 cudaStream_t st) {
   GP_REQUIRE(s_bf16 && adj_bf16 && partial && B > 0 && N > 0 && K > 0, "linkloss_tc: bad args");
   GP_REQUIRE(mode == 0 || mode == 1, "linkloss_tc: mode must be 0 (BCE) or 1 (Frobenius)");
   GP_REQUIRE(lds % 8 == 0 && (g_bf16 == nullptr || ldg >= N), "linkloss_tc: bad strides");
@@ -852,6 +947,13 @@ int run_linkloss(const void* s_bf16, long long lds, const void* adj_bf16, long l
   p.partial = partial; p.link_mode = mode;
   p.rnorm = nullptr; p.rowstat = nullptr; p.stat_relu = 0;
   p.cond = nullptr; p.cond_npairs = 0; p.cond_alpha = 1.f;
+  p.adj_flags = adj_flags;
+  {
+    const int tm = (N + BM - 1) / BM, tn = (N + 255) / 256;
+    int per = 0;
+    for (int mt = 0; mt < tm; ++mt) { const int first = (mt * BM) / 256; per += tn > first ? tn - first : 0; }
+    p.sym_per_graph = per; p.sym_total = (long long)per * B;
+  }
   return launch<256, 3, 1, kLinkEW>(maps, p, st);
 }
 
@@ -873,6 +975,7 @@ extern "C" int gp_linkloss_tc_partials(int B, int N) {
 }
 extern "C" int gp_linkloss_tc(const void* s_bf16, long long lds, const void* adj_bf16, long long ldadj,
                               const int32_t* nb, int B, int N, int K, float* partial, void* g_bf16,
-                              long long ldg, int mode, gp_stream_t stream) {
-  return gp::v2::run_linkloss(s_bf16, lds, adj_bf16, ldadj, nb, B, N, K, partial, g_bf16, ldg, mode, gp::S(stream));
+                              long long ldg, int mode, const int32_t* adj_flags, gp_stream_t stream) {
+  return gp::v2::run_linkloss(s_bf16, lds, adj_bf16, ldadj, nb, B, N, K, partial, g_bf16, ldg, mode, adj_flags,
+                              gp::S(stream));
 }

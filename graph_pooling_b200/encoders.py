@@ -69,7 +69,7 @@ def _fwd_tc(ctx, plan, x, adj, assign_x, params):
     call('gp_readout_max_fwd', z.data_ptr(), Fw, E._p(nb) if plan.soft else None, B, N, Fw,
          out.data_ptr(), arg.data_ptr(), ldo, st)
     levels, S0 = [], None
-    plan.adjb, plan.sb0, plan.asym = adjb, None, aflags[0:1]
+    plan.adjb, plan.sb0, plan.asym, plan.adj_flags = adjb, None, aflags[0:1], aflags
     if plan.soft:
         cur_adjb, cur_nb, cur_N, cur_zb = adjb, nb, N, zb
         for i in range(P):
@@ -360,7 +360,7 @@ class _LossFn(torch.autograd.Function):
             total, link = ws.f(1), ws.f(1)
             if ctx.sb is not None:                      # GP_BF16: P = S S^T on tensor cores, loss in the epilogue
                 partial, npart, gsym = T.linkloss_forward(ws, ctx.sb, plan.adjb, plan.nb_dev, Bn, N, K, need_grad,
-                                                          mode=int(frob))
+                                                          mode=int(frob), adj_flags=getattr(plan, 'adj_flags', None))
             else:
                 nt = (N + 63) // 64
                 npart = Bn * nt * nt
@@ -767,6 +767,7 @@ class SoftPoolingGcnEncoder(GcnEncoderGraph):
         lp.sb0 = getattr(plan, 'sb0', None)
         lp.adjb = getattr(plan, 'adjb', None)
         lp.asym = getattr(plan, 'asym', None)
+        lp.adj_flags = getattr(plan, 'adj_flags', None)
         lp.ce_scale = self._ce_scale
         lp.ent_w = ent_w
         lp.link_kind = self.link_loss_kind if self.linkpred else None

@@ -455,7 +455,7 @@ def assign_head_bwd(ws, S, ds, nb, B, N, zab, Fa, wpb, K, has_bias):
     return dwp, dbp, dza
 
 
-def linkloss_forward(ws, sb, adjb, nb, B, N, K, need_grad, mode=0):
+def linkloss_forward(ws, sb, adjb, nb, B, N, K, need_grad, mode=0, adj_flags=None):
     """Fused tensor-core link loss: P = S S^T tiles stay in TMEM, the epilogue does the masked BCE
     against the bf16 adjacency and writes gsym (bf16).  Returns (partial, n_partial, gsym op)."""
     nbp = E._p(nb)
@@ -463,7 +463,7 @@ def linkloss_forward(ws, sb, adjb, nb, B, N, K, need_grad, mode=0):
     partial = ws.f(npart + 256)                      # +256: scratch of the two-stage finalisation
     gs = bfbuf(ws, B, N, N) if need_grad else None
     call('gp_linkloss_tc', sb.ptr, sb.ld, adjb.ptr, adjb.ld, nbp, B, N, K, partial.data_ptr(),
-         None if gs is None else gs.ptr, N if gs is None else gs.ld, mode, E._stream())
+         None if gs is None else gs.ptr, N if gs is None else gs.ld, mode, E._p(adj_flags), E._stream())
     return partial, npart, gs
 
 

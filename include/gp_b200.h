@@ -287,9 +287,14 @@ int gp_loss_finalize(const float* partial, int n_partial, double inv_entries, co
 int gp_linkloss_tc_partials(int B, int N);
 /* mode 0: masked BCE (the reference).  mode 1: Frobenius option -- partial sums of (A - P)^2 (per graph
  * contiguous: gp_linkloss_tc_partials(1, N) each, feed gp_frob_finalize) and G = -(A - P). */
+/* adj_flags (optional): gp_adj_prepare's flags[2].  flags[1] == 0 (entries in {0,1}) selects the one-log / one-rcp
+ * form for the whole launch (without flags the test is made per 32x32 chunk).  flags[0] == 0 (every adjacency
+ * symmetric, BCE mode): P and G are symmetric, so only the tiles of the upper diagonal band are computed (56 % of
+ * them at N = 2048, enumerated compactly so the persistent CTAs stay balanced); their epilogues also write the
+ * transposed G chunks of the skipped tiles and count those loss terms twice. */
 int gp_linkloss_tc(const void* s_bf16, long long lds, const void* adj_bf16, long long ldadj,
                    const int32_t* nb, int B, int N, int K, float* partial, void* gsym_bf16, long long ldg,
-                   int mode, gp_stream_t stream);
+                   int mode, const int32_t* adj_flags, gp_stream_t stream);
 int gp_linkloss_from_p(const float* P, const float* adj, const int32_t* nb, int B, int N, long long ldg,
                        float* partial, void* gsym_bf16, gp_stream_t stream);
 
