@@ -290,7 +290,7 @@ static bool shape_fast(int B, int d, int bn, int* CS_out) {
 static long long ws_floats(int B, int N, int d, int bn) {
   long long blocks = (long long)N * 8;                   // upper bound on CTAs of either kernel
   if (blocks < kNumSMs * 8) blocks = kNumSMs * 8;
-  long long f = blocks * d + 256LL * d;
+  long long f = blocks * d + 256LL * d + (long long)N * 128;   // + batch-split partials of the generic path
   if (!shape_fast(B, d, bn, nullptr)) f += (long long)B * N * d;   // generic path: fp32 dV scratch for the column sums
   return f;
 }
@@ -385,7 +385,7 @@ extern "C" int gp_gcn_layer_bwd_x(const gp_layer_bwd* q, gp_stream_t stream) {
   GP_REQUIRE(!q->bn || (q->invstd && (q->h || q->mean)), "gcn_layer_bwd_x: bn needs invstd and h or mean");
   GP_REQUIRE(!q->normalize || q->rnorm, "gcn_layer_bwd_x: normalize needs rnorm");
   GP_REQUIRE(!q->dout || q->argidx, "gcn_layer_bwd_x: dout needs argidx");
-  GP_REQUIRE(!q->db || q->ws, "gcn_layer_bwd_x: db needs ws (gp_gcn_layer_bwd_ws floats)");
+  GP_REQUIRE(!q->db || q->ws, "gcn_layer_bwd_x: db needs ws (gp_gcn_layer_bwd_ws_x floats)");
   bool handled = false;
   GP_TRY(layer_bwd_fast(q, S(stream), &handled));
   if (handled) return GP_OK;

@@ -93,6 +93,85 @@ __global__ void relu_bn_fwd_kernel(const float* __restrict__ y, float* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
+// Batch-split variants for SMALL N and LARGE B (ENZYMES-sized graphs in big batches): one CTA per node index
+// would leave most of the 148 SMs idle (N = 100 -> 100 CTAs, each walking B*d elements), so a node's batch is
+// cut into S slices: grid (N, S).  Statistics are combined with Chan's parallel mean / M2 update (exact
+// two-pass quality, no E[x^2] - mean^2 cancellation); everything stays deterministic.
+// ---------------------------------------------------------------------------------------------
+__global__ void bn_split_stats_kernel(const float* __restrict__ y, int B, int N, int d, int relu, int bs,
+                                      float* __restrict__ part) {
+  __shared__ float sh[33];
+  const int n = blockIdx.x, sidx = blockIdx.y;
+  const int b0 = sidx * bs, b1 = min(B, b0 + bs);
+  const int total = (b1 - b0) * d;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int b = b0 + i / d, c = i % d;
+    float x = y[((long long)b * N + n) * d + c];
+    if (relu) x = fmaxf(x, 0.f);
+    s += x;
+  }
+  const float mu = total > 0 ? block_sum(s, sh) / (float)total : 0.f;
+  float q = 0.f;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int b = b0 + i / d, c = i % d;
+    float x = y[((long long)b * N + n) * d + c];
+    if (relu) x = fmaxf(x, 0.f);
+    const float t = x - mu;
+    q = fmaf(t, t, q);
+  }
+  const float m2 = block_sum(q, sh);
+  if (threadIdx.x == 0) {
+    float* o = part + ((long long)n * gridDim.y + sidx) * 3;
+    o[0] = (float)total; o[1] = mu; o[2] = m2;
+  }
+}
+
+__global__ void bn_split_apply_kernel(const float* __restrict__ y, float* __restrict__ h, long long ldh,
+                                      float* __restrict__ mean, float* __restrict__ invstd, int B, int N, int d,
+                                      int relu, int bs, const float* __restrict__ part) {
+  __shared__ float sh_mu, sh_is;
+  const int n = blockIdx.x, sidx = blockIdx.y, S = gridDim.y;
+  if (threadIdx.x == 0) {                                // Chan et al. combination, same order in every CTA
+    double cnt = 0.0, mu = 0.0, m2 = 0.0;
+    for (int j = 0; j < S; ++j) {
+      const float* o = part + ((long long)n * S + j) * 3;
+      const double c = o[0], m = o[1], q = o[2];
+      if (c <= 0.0) continue;
+      const double tot = cnt + c, dlt = m - mu;
+      m2 += q + dlt * dlt * cnt * c / tot;
+      mu += dlt * c / tot;
+      cnt = tot;
+    }
+    const float is = (float)(1.0 / sqrt(m2 / cnt + (double)kEpsBn));
+    sh_mu = (float)mu; sh_is = is;
+    if (sidx == 0) { mean[n] = (float)mu; invstd[n] = is; }
+  }
+  __syncthreads();
+  const float mu = sh_mu, is = sh_is;
+  const int b0 = sidx * bs, b1 = min(B, b0 + bs);
+  const int total = (b1 - b0) * d;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int b = b0 + i / d, c = i % d;
+    float x = y[((long long)b * N + n) * d + c];
+    if (relu) x = fmaxf(x, 0.f);
+    h[((long long)b * N + n) * ldh + c] = (x - mu) * is;
+  }
+}
+
+// number of batch slices for the split kernels (0 = keep the one-CTA-per-node kernels)
+static int split_slices(int B, int N, int d) {
+  const long long total = (long long)B * d;
+  if (N >= 2 * kNumSMs || total < 16384) return 0;
+  long long S = (total + 4095) / 4096;                   // ~4K elements per CTA
+  const long long want = (4LL * kNumSMs + N - 1) / N;    // enough CTAs for ~4 per SM
+  if (S > want) S = want;
+  if (S > 64) S = 64;
+  if (S > B) S = B;
+  return S < 2 ? 0 : (int)S;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Backward of [slot + readout scatter + next-layer dX] -> BN -> ReLU -> normalize.
 // One block per node index n; pass 1 block-reduces mean(g) and mean(g*Hhat); pass 2 is one warp
 // per (b, n) row: dR, ReLU mask, <Y,dY> by shuffle, dV.
@@ -125,42 +204,29 @@ __device__ __forceinline__ void put_dv(float* dv, __nv_bfloat16* dvb, long long 
   if (dvb != nullptr) dvb[row * lddvb + c] = __float2bfloat16_rn(g);
 }
 
-template <bool CACHE, int MAXE>
-__global__ void gcn_layer_bwd_kernel(const float* __restrict__ dz, long long lddz, const float* __restrict__ dxn,
-                                     long long lddxn,
-                                     const float* __restrict__ dout, const int32_t* __restrict__ argidx,
-                                     long long ldo, const float* __restrict__ h, long long ldh,
-                                     const float* __restrict__ y, long long ldy, const float* __restrict__ rnorm,
-                                     const float* __restrict__ mean, const float* __restrict__ invstd, int B, int N,
-                                     int d, int relu, int bn, int normalize, float* __restrict__ dv,
-                                     __nv_bfloat16* __restrict__ dvb, long long lddvb) {
-  extern __shared__ float cache[];
-  __shared__ float sh[33];
-  const int n = blockIdx.x;
-  const int total = B * d;
-  float m1 = 0.f, m2 = 0.f, is = 1.f, mu = 0.f;
-  if (bn) {
-    is = invstd[n];
-    if (mean != nullptr) mu = mean[n];
-    float s1 = 0.f, s2 = 0.f;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-      const int b = i / d, c = i - b * d;
-      const float g = layer_g(dz, lddz, dxn, lddxn, dout, argidx, ldo, b, n, c, N, d);
-      if (CACHE) cache[i] = g;
-      s1 += g;
-      s2 = fmaf(g, hhat_of(h, ldh, y, ldy, (long long)b * N + n, c, relu, mu, is), s2);
-    }
-    m1 = block_sum(s1, sh) / (float)total;
-    m2 = block_sum(s2, sh) / (float)total;
-  }
-  const bool cached = CACHE && bn;
+struct LbG {
+  const float* dz; long long lddz; const float* dxn; long long lddxn;
+  const float* dout; const int32_t* argidx; long long ldo;
+  const float* h; long long ldh; const float* y; long long ldy;
+  const float* rnorm; const float* mean; const float* invstd;
+  int B, N, d, relu, bn, normalize;
+  float* dv; __nv_bfloat16* dvb; long long lddvb;
+};
+
+// rows b_lo..b_hi-1 of node n: dR (BN backward with the batch means m1, m2), ReLU mask, <Y,dY> by shuffle, dV.
+// One warp per row.  cache: optional per-node staging of g (indexed [b * d + c]) or nullptr.
+template <int MAXE>
+__device__ __forceinline__ void layer_bwd_rows(const LbG& a, int n, int b_lo, int b_hi, float m1, float m2, float mu,
+                                               float is, const float* cache) {
+  const int d = a.d, N = a.N;
+  const bool cached = cache != nullptr;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int b = w; b < B; b += nw) {
+  for (int b = b_lo + w; b < b_hi; b += nw) {
     const long long row = (long long)b * N + n;
     float r = 1.f;
     bool clamped = false;
-    if (normalize) {
-      r = rnorm[row];
+    if (a.normalize) {
+      r = a.rnorm[row];
       clamped = !(r > kEpsNorm);
     }
     if (MAXE > 0) {
@@ -171,44 +237,113 @@ __global__ void gcn_layer_bwd_kernel(const float* __restrict__ dz, long long ldd
         const int c = lane + 32 * e;
         float g = 0.f, yy = 0.f;
         if (c < d) {
-          g = cached ? cache[b * d + c] : layer_g(dz, lddz, dxn, lddxn, dout, argidx, ldo, b, n, c, N, d);
-          if (bn) g = (g - m1 - hhat_of(h, ldh, y, ldy, row, c, relu, mu, is) * m2) * is;
-          yy = y[row * ldy + c];
-          if (relu && !(yy > 0.f)) g = 0.f;
+          g = cached ? cache[b * d + c] : layer_g(a.dz, a.lddz, a.dxn, a.lddxn, a.dout, a.argidx, a.ldo, b, n, c, N, d);
+          if (a.bn) g = (g - m1 - hhat_of(a.h, a.ldh, a.y, a.ldy, row, c, a.relu, mu, is) * m2) * is;
+          yy = a.y[row * a.ldy + c];
+          if (a.relu && !(yy > 0.f)) g = 0.f;
           dot = fmaf(g, yy, dot);
         }
         gv[e] = g; yv[e] = yy;
       }
-      if (normalize) dot = warp_sum(dot);
+      if (a.normalize) dot = warp_sum(dot);
 #pragma unroll
       for (int e = 0; e < MAXE; ++e) {
         const int c = lane + 32 * e;
         if (c < d) {
           float g = gv[e];
-          if (normalize) g = clamped ? g / kEpsNorm : (g - yv[e] * dot) / r;
-          put_dv(dv, dvb, lddvb, row, d, c, g);
+          if (a.normalize) g = clamped ? g / kEpsNorm : (g - yv[e] * dot) / r;
+          put_dv(a.dv, a.dvb, a.lddvb, row, d, c, g);
         }
       }
     } else {
       float dot = 0.f;
       for (int c = lane; c < d; c += 32) {
-        float g = cached ? cache[b * d + c] : layer_g(dz, lddz, dxn, lddxn, dout, argidx, ldo, b, n, c, N, d);
-        if (bn) g = (g - m1 - hhat_of(h, ldh, y, ldy, row, c, relu, mu, is) * m2) * is;
-        const float yy = y[row * ldy + c];
-        if (relu && !(yy > 0.f)) g = 0.f;
+        float g = cached ? cache[b * d + c] : layer_g(a.dz, a.lddz, a.dxn, a.lddxn, a.dout, a.argidx, a.ldo, b, n, c, N, d);
+        if (a.bn) g = (g - m1 - hhat_of(a.h, a.ldh, a.y, a.ldy, row, c, a.relu, mu, is) * m2) * is;
+        const float yy = a.y[row * a.ldy + c];
+        if (a.relu && !(yy > 0.f)) g = 0.f;
         dot = fmaf(g, yy, dot);
       }
-      if (normalize) dot = warp_sum(dot);
+      if (a.normalize) dot = warp_sum(dot);
       for (int c = lane; c < d; c += 32) {
-        float g = cached ? cache[b * d + c] : layer_g(dz, lddz, dxn, lddxn, dout, argidx, ldo, b, n, c, N, d);
-        if (bn) g = (g - m1 - hhat_of(h, ldh, y, ldy, row, c, relu, mu, is) * m2) * is;
-        const float yy = y[row * ldy + c];
-        if (relu && !(yy > 0.f)) g = 0.f;
-        if (normalize) g = clamped ? g / kEpsNorm : (g - yy * dot) / r;
-        put_dv(dv, dvb, lddvb, row, d, c, g);
+        float g = cached ? cache[b * d + c] : layer_g(a.dz, a.lddz, a.dxn, a.lddxn, a.dout, a.argidx, a.ldo, b, n, c, N, d);
+        if (a.bn) g = (g - m1 - hhat_of(a.h, a.ldh, a.y, a.ldy, row, c, a.relu, mu, is) * m2) * is;
+        const float yy = a.y[row * a.ldy + c];
+        if (a.relu && !(yy > 0.f)) g = 0.f;
+        if (a.normalize) g = clamped ? g / kEpsNorm : (g - yy * dot) / r;
+        put_dv(a.dv, a.dvb, a.lddvb, row, d, c, g);
       }
     }
   }
+}
+
+template <bool CACHE, int MAXE>
+__global__ void gcn_layer_bwd_kernel(const LbG a) {
+  extern __shared__ float cache[];
+  __shared__ float sh[33];
+  const int n = blockIdx.x;
+  const int B = a.B, N = a.N, d = a.d;
+  const int total = B * d;
+  float m1 = 0.f, m2 = 0.f, is = 1.f, mu = 0.f;
+  if (a.bn) {
+    is = a.invstd[n];
+    if (a.mean != nullptr) mu = a.mean[n];
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      const int b = i / d, c = i - b * d;
+      const float g = layer_g(a.dz, a.lddz, a.dxn, a.lddxn, a.dout, a.argidx, a.ldo, b, n, c, N, d);
+      if (CACHE) cache[i] = g;
+      s1 += g;
+      s2 = fmaf(g, hhat_of(a.h, a.ldh, a.y, a.ldy, (long long)b * N + n, c, a.relu, mu, is), s2);
+    }
+    m1 = block_sum(s1, sh) / (float)total;
+    m2 = block_sum(s2, sh) / (float)total;
+  }
+  layer_bwd_rows<MAXE>(a, n, 0, B, m1, m2, mu, is, (CACHE && a.bn) ? cache : nullptr);
+}
+
+// batch-split variants (see bn_split_stats_kernel): grid (N, S); partial sums of g and g*Hhat per slice, then the
+// row pass with the combined batch means (slices summed in a fixed order: deterministic).
+__global__ void layer_bwd_split_stats_kernel(const LbG a, int bs, float* __restrict__ part) {
+  __shared__ float sh[33];
+  const int n = blockIdx.x, sidx = blockIdx.y;
+  const int d = a.d, N = a.N;
+  const int b0 = sidx * bs, b1 = min(a.B, b0 + bs);
+  const int total = (b1 - b0) * d;
+  const float is = a.invstd[n];
+  const float mu = a.mean != nullptr ? a.mean[n] : 0.f;
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int b = b0 + i / d, c = i % d;
+    const float g = layer_g(a.dz, a.lddz, a.dxn, a.lddxn, a.dout, a.argidx, a.ldo, b, n, c, N, d);
+    s1 += g;
+    s2 = fmaf(g, hhat_of(a.h, a.ldh, a.y, a.ldy, (long long)b * N + n, c, a.relu, mu, is), s2);
+  }
+  s1 = block_sum(s1, sh);
+  s2 = block_sum(s2, sh);
+  if (threadIdx.x == 0) {
+    float* o = part + ((long long)n * gridDim.y + sidx) * 2;
+    o[0] = s1; o[1] = s2;
+  }
+}
+
+template <int MAXE>
+__global__ void layer_bwd_split_apply_kernel(const LbG a, int bs, const float* __restrict__ part) {
+  const int n = blockIdx.x, sidx = blockIdx.y, S = gridDim.y;
+  float m1 = 0.f, m2 = 0.f, is = 1.f, mu = 0.f;
+  if (a.bn) {
+    is = a.invstd[n];
+    if (a.mean != nullptr) mu = a.mean[n];
+    double t1 = 0.0, t2 = 0.0;
+    for (int j = 0; j < S; ++j) {                        // every thread: S <= 64 L1-resident values, fixed order
+      t1 += (double)part[((long long)n * S + j) * 2];
+      t2 += (double)part[((long long)n * S + j) * 2 + 1];
+    }
+    const double inv = 1.0 / ((double)a.B * (double)a.d);
+    m1 = (float)(t1 * inv); m2 = (float)(t2 * inv);
+  }
+  const int b0 = sidx * bs, b1 = min(a.B, b0 + bs);
+  layer_bwd_rows<MAXE>(a, n, b0, b1, m1, m2, mu, is, nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -403,6 +538,27 @@ int colsum(const float* x, long long rows, int d, long long ld, float* out, int 
 
 using namespace gp;
 
+extern "C" long long gp_relu_bn_fwd_ws(int B, int N, int d) {
+  return (long long)N * split_slices(B, N, d) * 3;
+}
+
+extern "C" int gp_relu_bn_fwd_x(const float* y, float* h, long long ldh, float* mean, float* invstd, int B, int N,
+                                int d, int relu, int bn, float* ws, gp_stream_t stream) {
+  GP_REQUIRE(y && h && B > 0 && N > 0 && d > 0 && ldh >= d, "relu_bn_fwd: bad args");
+  GP_REQUIRE(!bn || (mean && invstd), "relu_bn_fwd: bn needs mean/invstd");
+  const int S = (bn && ws != nullptr) ? split_slices(B, N, d) : 0;
+  if (S > 0) {
+    const int bs = (B + S - 1) / S;
+    dim3 grid(N, S);
+    bn_split_stats_kernel<<<grid, 256, 0, gp::S(stream)>>>(y, B, N, d, relu, bs, ws);
+    GP_LAUNCHED();
+    bn_split_apply_kernel<<<grid, 256, 0, gp::S(stream)>>>(y, h, ldh, mean, invstd, B, N, d, relu, bs, ws);
+    GP_LAUNCHED();
+    return GP_OK;
+  }
+  return gp_relu_bn_fwd(y, h, ldh, mean, invstd, B, N, d, relu, bn, stream);
+}
+
 extern "C" int gp_relu_bn_fwd(const float* y, float* h, long long ldh, float* mean, float* invstd, int B, int N,
                               int d, int relu, int bn, gp_stream_t stream) {
   GP_REQUIRE(y && h && B > 0 && N > 0 && d > 0 && ldh >= d, "relu_bn_fwd: bad args");
@@ -426,19 +582,42 @@ namespace gp {
 // Generic (any d, any alignment) path of gp_gcn_layer_bwd_x; the vectorised fast paths live in layer_bwd.cu.
 int layer_bwd_generic(const gp_layer_bwd* q, cudaStream_t st) {
   const int B = q->B, N = q->N, d = q->d;
+  // ws layout of this path: [N * 128 floats: batch-split partials][B*N*d: borrowed fp32 dV (only when the caller
+  // wants db without dv)][column-sum scratch]
+  float* split_ws = q->ws;
+  float* rest = q->ws != nullptr ? q->ws + (long long)N * 128 : nullptr;
   float* dv = q->dv;
-  float* cs_ws = q->ws;
+  float* cs_ws = rest;
   if (dv == nullptr && q->db != nullptr) {               // column sums need an fp32 dV: borrow it from ws
-    dv = q->ws;
-    cs_ws = q->ws + (long long)B * N * d;
+    dv = rest;
+    cs_ws = rest + (long long)B * N * d;
   }
-  __nv_bfloat16* dvb = reinterpret_cast<__nv_bfloat16*>(q->dv_bf16);
+  LbG a;
+  a.dz = q->dz; a.lddz = q->lddz; a.dxn = q->dxn; a.lddxn = q->lddxn > 0 ? q->lddxn : (long long)d;
+  a.dout = q->dout; a.argidx = q->argidx; a.ldo = q->ldo;
+  a.h = q->h; a.ldh = q->ldh; a.y = q->y; a.ldy = q->ldy;
+  a.rnorm = q->rnorm; a.mean = q->mean; a.invstd = q->invstd;
+  a.B = B; a.N = N; a.d = d; a.relu = q->relu; a.bn = q->bn; a.normalize = q->normalize;
+  a.dv = dv; a.dvb = reinterpret_cast<__nv_bfloat16*>(q->dv_bf16); a.lddvb = q->lddvb;
   const int total = B * d;
-  const size_t cache_bytes = (size_t)total * sizeof(float);
-  const bool use_cache = q->bn && cache_bytes > 16 * 1024 && cache_bytes <= kNodeCacheMax;
-  // 512 threads: the MAXE=16 variant needs 80 registers/thread (1024 threads would exceed the register file)
-  const int threads = use_cache ? 512 : (total >= 4096 ? 512 : (total >= 512 ? 256 : 128));
   const int maxe = d <= 128 ? 4 : (d <= 512 ? 16 : 0);
+  const int S = split_ws != nullptr ? split_slices(B, N, d) : 0;
+  if (S > 0) {
+    const int bs = (B + S - 1) / S;
+    dim3 grid(N, S);
+    if (q->bn) {
+      layer_bwd_split_stats_kernel<<<grid, 256, 0, st>>>(a, bs, split_ws);
+      GP_LAUNCHED();
+    }
+    if (maxe == 4) layer_bwd_split_apply_kernel<4><<<grid, 256, 0, st>>>(a, bs, split_ws);
+    else if (maxe == 16) layer_bwd_split_apply_kernel<16><<<grid, 256, 0, st>>>(a, bs, split_ws);
+    else layer_bwd_split_apply_kernel<0><<<grid, 256, 0, st>>>(a, bs, split_ws);
+    GP_LAUNCHED();
+  } else {
+    const size_t cache_bytes = (size_t)total * sizeof(float);
+    const bool use_cache = q->bn && cache_bytes > 16 * 1024 && cache_bytes <= kNodeCacheMax;
+    // 512 threads: the MAXE=16 variant needs 80 registers/thread (1024 threads would exceed the register file)
+    const int threads = use_cache ? 512 : (total >= 4096 ? 512 : (total >= 512 ? 256 : 128));
 #define GP_LAUNCH_LBWD(C_, E_)                                                                              \
   do {                                                                                                     \
     auto kern = gcn_layer_bwd_kernel<C_, E_>;                                                              \
@@ -446,17 +625,16 @@ int layer_bwd_generic(const gp_layer_bwd* q, cudaStream_t st) {
       static bool cfgd = false;                                                                            \
       if (!cfgd) { GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNodeCacheMax)); cfgd = true; } \
     }                                                                                                      \
-    kern<<<N, threads, C_ ? cache_bytes : 0, st>>>(q->dz, q->lddz, q->dxn, (q->lddxn > 0 ? q->lddxn : (long long)d), q->dout, q->argidx, q->ldo, q->h, \
-                                                   q->ldh, q->y, q->ldy, q->rnorm, q->mean, q->invstd, B, N, d, \
-                                                   q->relu, q->bn, q->normalize, dv, dvb, q->lddvb);       \
+    kern<<<N, threads, C_ ? cache_bytes : 0, st>>>(a);                                                     \
   } while (0)
-  if (use_cache) {
-    if (maxe == 4) GP_LAUNCH_LBWD(true, 4); else if (maxe == 16) GP_LAUNCH_LBWD(true, 16); else GP_LAUNCH_LBWD(true, 0);
-  } else {
-    if (maxe == 4) GP_LAUNCH_LBWD(false, 4); else if (maxe == 16) GP_LAUNCH_LBWD(false, 16); else GP_LAUNCH_LBWD(false, 0);
-  }
+    if (use_cache) {
+      if (maxe == 4) GP_LAUNCH_LBWD(true, 4); else if (maxe == 16) GP_LAUNCH_LBWD(true, 16); else GP_LAUNCH_LBWD(true, 0);
+    } else {
+      if (maxe == 4) GP_LAUNCH_LBWD(false, 4); else if (maxe == 16) GP_LAUNCH_LBWD(false, 16); else GP_LAUNCH_LBWD(false, 0);
+    }
 #undef GP_LAUNCH_LBWD
-  GP_LAUNCHED();
+    GP_LAUNCHED();
+  }
   if (q->db != nullptr) GP_TRY(colsum(dv, (long long)B * N, d, d, q->db, 0, cs_ws, st));
   return GP_OK;
 }

@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import GpGemm, call
+from ._lib import GpGemm, GpLayerBwd, call
 
 F32 = 0  # gp_precision
 
@@ -118,7 +118,9 @@ def stack_forward(ws, x_ptr, ldx, din, adj, nb, B, N, weights, biases, add_self,
         if not last:
             if bn:
                 mean, invstd = ws.f(N), ws.f(N)
-            call('gp_relu_bn_fwd', y_ptr, slot, Fw, _p(mean), _p(invstd), B, N, dout, 1, int(bn), st)
+            nws = int(_lib.load().gp_relu_bn_fwd_ws(B, N, dout)) if bn else 0
+            call('gp_relu_bn_fwd_x', y_ptr, slot, Fw, _p(mean), _p(invstd), B, N, dout, 1, int(bn),
+                 _p(ws.f(nws)) if nws else None, st)
         ctx.layers.append((cur_ptr, cur_ld, cur_d, dout, off, u, y, rnorm, mean, invstd))
         cur_ptr, cur_ld, cur_d = slot, Fw, dout
         off += dout
@@ -141,11 +143,21 @@ def stack_backward(ws, ctx, dz_ptr, lddz, dout_ptr, arg_ptr, ldo, need_dx, dadj,
         last = l == L - 1
         slot = zp + off * 4
         dv = ws.f(B, N, dout)
-        call('gp_gcn_layer_bwd',
-             None if dz_ptr is None else dz_ptr + off * 4, lddz, _p(dxn),
-             None if dout_ptr is None else dout_ptr + off * 4, None if arg_ptr is None else arg_ptr + off * 4, ldo,
-             slot, Fw, slot if last else _p(y), Fw if last else dout, _p(rnorm), _p(invstd),
-             B, N, dout, int(not last), int(ctx.bn and not last), 1, _p(dv), st)
+        q = GpLayerBwd()
+        q.dz, q.lddz = (None if dz_ptr is None else dz_ptr + off * 4), lddz
+        q.dxn, q.lddxn = _p(dxn), 0
+        q.dout = None if dout_ptr is None else dout_ptr + off * 4
+        q.argidx = None if arg_ptr is None else arg_ptr + off * 4
+        q.ldo = ldo
+        q.h, q.ldh = slot, Fw
+        q.y, q.ldy = (slot, Fw) if last else (_p(y), dout)
+        q.rnorm, q.mean, q.invstd = _p(rnorm), None, _p(invstd)
+        q.B, q.N, q.d = B, N, dout
+        q.relu, q.bn, q.normalize = int(not last), int(ctx.bn and not last), 1
+        q.dv, q.dv_bf16, q.lddvb, q.db, q.ws = _p(dv), None, 0, None, None
+        wsf = ws.f(int(_lib.load().gp_gcn_layer_bwd_ws_x(C.byref(q))))
+        q.ws = _p(wsf)
+        call('gp_gcn_layer_bwd_x', C.byref(q), st)
         need_dx_l = need_dx or l > 0
         w = ctx.weights[l]
         dw = ws.f(din, dout)

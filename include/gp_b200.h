@@ -194,6 +194,12 @@ int gp_graphconv_bwd(const float* dv, const float* u, const float* x, long long 
  * ------------------------------------------------------------------------------------------- */
 int gp_relu_bn_fwd(const float* y, float* h, long long ldh, float* mean, float* invstd,
                    int B, int N, int d, int relu, int bn, gp_stream_t stream);
+/* Same, with a workspace of gp_relu_bn_fwd_ws(B, N, d) floats (may be 0): for SMALL N and LARGE B (ENZYMES-sized
+ * graphs in big batches) one CTA per node index would leave most SMs idle, so each node's batch is cut into
+ * slices (grid N x S) whose statistics are combined exactly (Chan's parallel mean / M2 update). */
+long long gp_relu_bn_fwd_ws(int B, int N, int d);
+int gp_relu_bn_fwd_x(const float* y, float* h, long long ldh, float* mean, float* invstd,
+                     int B, int N, int d, int relu, int bn, float* ws, gp_stream_t stream);
 
 /* Backward through [concat slot + readout scatter + next-layer dX] -> BN -> ReLU -> normalize:
  *   g  = dz (dense slot gradient, row stride lddz, or NULL)
@@ -215,7 +221,8 @@ int gp_gcn_layer_bwd(const float* dz, long long lddz, const float* dxn, const fl
  * inputs with d in {32, 64, 128} (bn) or d % 4 == 0, d <= 512 (no bn) take a single-pass vectorised kernel
  * (a thread-block cluster per node index, batch means reduced through distributed shared memory).
  * ws: gp_gcn_layer_bwd_ws_x(q) floats, needed when db != NULL (gp_gcn_layer_bwd_ws(B, N, d, bn) is the
- * shape-only bound, valid when every operand meets the alignment above or dv != NULL). */
+ * shape-only bound, valid when every operand meets the alignment above or dv != NULL); optional otherwise --
+ * with it the generic kernel may split a node's batch over several CTAs (small N, large B). */
 typedef struct gp_layer_bwd {
   const float* dz; long long lddz;
   const float* dxn;

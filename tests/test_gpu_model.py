@@ -196,3 +196,11 @@ def test_training_loop_matches_oracle_for_20_steps():
         torch.nn.utils.clip_grad_norm_(mc.parameters(), 2.0)
         oc.step()
         assert abs(lc.item() - lo.item()) < 2e-4 * max(1.0, abs(lo.item())), step
+
+
+def test_soft_large_batch_of_small_graphs_uses_batch_split_bn():
+    """ENZYMES-sized graphs in a large batch (B*d >= 16384 with N < 296): the BatchNorm forward / backward kernels
+    split each node's batch over several CTAs (Chan-combined statistics) -- same parity bar as everywhere else."""
+    oracle_vs_candidate(soft_factory(40, 3, 30, 30, 6, ratio=0.1), 18, 640, 40, 3, 6, nb_mode='rand')
+    make = lambda mod: mod.GcnEncoderGraph(5, 36, 20, 3, 3, bn=True)
+    oracle_vs_candidate(make, 19, 512, 24, 5, 3, soft=False)
