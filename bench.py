@@ -44,6 +44,9 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--seed', type=int, default=0)
+    ap.add_argument('--graph', default='auto', choices=['auto', 'on', 'off'],
+                    help='replay the step from a CUDA graph (graphed.GraphedTrainStep); auto: on when the batch '
+                         'adjacency is <= 256 MB (launch-bound steps), off for the multi-GB batches')
     ap.add_argument('--precision', default='auto', choices=['auto', 'f32', 'bf16'],
                     help='auto: bf16 tensor-core path for N >= 512 (BASELINE configs[3]), fp32 FFMA otherwise')
     return ap.parse_args()
@@ -187,7 +190,17 @@ def main():
     from graph_pooling_b200 import dp
     flat = dp.FlatGradients(params)
 
+    use_graph = (args.graph == 'on' or (args.graph == 'auto' and adj.numel() * 4 <= 256e6)) and world == 1
+    gstep = None
+    if use_graph:
+        from graph_pooling_b200 import graphed
+        gstep = graphed.GraphedTrainStep(model, lr=1e-3, clip=2.0)
+        flat, opt = gstep.grads, gstep.optimizer
+        nb_dev = torch.from_numpy(np.ascontiguousarray(nb.astype(np.int32))).to(dev)
+
     def step(xd, ad, ld):
+        if gstep is not None:                       # all kernels replayed from one CUDA graph, node counts on device
+            return gstep.step(xd, ad, nb_dev, ld)[1]
         flat.zero()
         yp = model(xd, ad, nb, assign_x=xd) if soft else model(xd, ad, nb)
         loss = model.loss(yp, ld, ad, nb) if soft else model.loss(yp, ld)
@@ -221,6 +234,8 @@ def main():
     for _ in range(args.warmup):
         step(x, adj, label)
     lib.gp_launch_count_reset()
+    if gstep is not None:
+        gstep.replayed_launches = 0
     sampler = ClockSampler(local) if rank == 0 else None
     t0 = time.time()
     if os.environ.get('GP_PROFILE'):            # ncu --profile-from-start off: capture the timed steps only
@@ -230,7 +245,7 @@ def main():
         torch.cuda.cudart().cudaProfilerStop()
     t1 = time.time()
     clocks = sampler.stop(t0, t1) if sampler else None
-    launches = int(lib.gp_launch_count())
+    launches = int(lib.gp_launch_count()) + (gstep.replayed_launches if gstep is not None else 0)
     ms_per_step = ms / args.steps
     value = world * B / (ms_per_step * 1e-3)
 
@@ -405,6 +420,7 @@ def main():
                       'step': 'zero_grad+forward+loss(CE+linkpred)+backward+clip_grad_norm+Adam (train.py:196-210)',
                       'l2': 'inputs larger than L2 (adjacency %.1f GB)' % (adj.numel() * 4 / 1e9)
                       if adj.numel() * 4 > 126e6 else 'inputs smaller than L2; not flushed',
+                      'cuda_graph': bool(use_graph),
                       'parallelism': 'dp%d' % world},
            'clocks': clocks, 'e2e': e2e, 'e2e_u8_feed': e2e_u8, 'gpu_launches': launches, 'roofline': roof, 'cpu_baseline': cpu}
     print(json.dumps(out), flush=True)

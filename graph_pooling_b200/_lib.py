@@ -104,6 +104,8 @@ _PROTOS = {
     'gp_entropy_partials': [c_i, c_i],
     'gp_entropy_fwd': [c_f, c_f, c_i, c_i, c_i, c_f, c_f],
     'gp_entropy_bwd': [c_f, c_f, c_i, c_i, c_i, c_f, C.c_float, c_f, c_i, c_f],
+    'gp_nb_stats': [c_f, c_i, c_f, c_f],
+    'gp_mul_add_dev': [c_f, c_f, c_f, c_f, c_f, c_f],
     'gp_add_scaled': [c_f, c_f, C.c_float, c_f, c_f],
     'gp_linkloss_tc_partials': [c_i, c_i],
     'gp_linkloss_from_p': [c_f, c_f, c_f, c_i, c_i, c_ll, c_f, c_f, c_f],

@@ -196,6 +196,34 @@ __global__ void frob_mean_kernel(const float* __restrict__ norm, int B, const fl
   }
 }
 
+// out[0] = 1 / sum_b n_b^2 ; out[1] = 1 / sum_b n_b   (the link-loss / entropy normalisers when the node counts live
+// on the device only, e.g. inside a captured CUDA graph: no host round trip)
+__global__ void nb_stats_kernel(const int32_t* __restrict__ nb, int B, float* __restrict__ out) {
+  __shared__ double s2[256], s1[256];
+  double a = 0.0, b = 0.0;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    const double n = (double)nb[i];
+    a += n * n; b += n;
+  }
+  s2[threadIdx.x] = a; s1[threadIdx.x] = b;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { s2[threadIdx.x] += s2[threadIdx.x + o]; s1[threadIdx.x] += s1[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out[0] = s2[0] > 0.0 ? (float)(1.0 / s2[0]) : 0.f;
+    out[1] = s1[0] > 0.0 ? (float)(1.0 / s1[0]) : 0.f;
+  }
+}
+
+// prod = (*a) * (*b) ; total = (c ? *c : 0) + prod
+__global__ void mul_add_dev_kernel(const float* a, const float* b, const float* c, float* total, float* prod) {
+  const float p = (*a) * (*b);
+  if (prod != nullptr) *prod = p;
+  if (total != nullptr) *total = (c != nullptr ? *c : 0.f) + p;
+}
+
 static int grid_for(long long n, int per_block) {
   long long b = (n + per_block - 1) / per_block;
   if (b > kNumSMs * 8) b = kNumSMs * 8;
@@ -266,6 +294,21 @@ extern "C" int gp_entropy_bwd(const float* s, const int32_t* nb, int B, int N, i
 extern "C" int gp_add_scaled(const float* base, const float* term, float w, float* total, gp_stream_t stream) {
   GP_REQUIRE(term && total, "add_scaled: bad args");
   add_scaled_kernel<<<1, 1, 0, S(stream)>>>(base, term, w, total);
+  GP_LAUNCHED();
+  return GP_OK;
+}
+
+extern "C" int gp_nb_stats(const int32_t* nb, int B, float* out, gp_stream_t stream) {
+  GP_REQUIRE(nb && out && B > 0, "nb_stats: bad args");
+  nb_stats_kernel<<<1, 256, 0, S(stream)>>>(nb, B, out);
+  GP_LAUNCHED();
+  return GP_OK;
+}
+
+extern "C" int gp_mul_add_dev(const float* a, const float* b, const float* c, float* total, float* prod,
+                              gp_stream_t stream) {
+  GP_REQUIRE(a && b && (total || prod), "mul_add_dev: bad args");
+  mul_add_dev_kernel<<<1, 1, 0, S(stream)>>>(a, b, c, total, prod);
   GP_LAUNCHED();
   return GP_OK;
 }

@@ -372,8 +372,14 @@ class _LossFn(torch.autograd.Function):
                 ctx.coef = ws.f(Bn)
                 call('gp_frob_finalize', partial.data_ptr(), npart // Bn, Bn, ce.data_ptr(), total.data_ptr(),
                      link.data_ptr(), ws.f(Bn).data_ptr(), ctx.coef.data_ptr(), st)
+            elif getattr(plan, 'inv_dev', None) is not None:   # 1 / sum n_b^2 lives on the device (graphed.py)
+                ctx.inv, ctx.inv_dev = 1.0, plan.inv_dev
+                raw = ws.f(1)
+                call('gp_loss_finalize', partial.data_ptr(), npart, C.c_double(1.0), None, None, raw.data_ptr(), st)
+                call('gp_mul_add_dev', raw.data_ptr(), ctx.inv_dev.data_ptr(), ce.data_ptr(), total.data_ptr(),
+                     link.data_ptr(), st)
             else:
-                ctx.inv = 1.0 / float(plan.num_entries)
+                ctx.inv, ctx.inv_dev = 1.0 / float(plan.num_entries), None
                 call('gp_loss_finalize', partial.data_ptr(), npart, C.c_double(ctx.inv), ce.data_ptr(),
                      total.data_ptr(), link.data_ptr(), st)
             ctx.gsym = gsym
@@ -411,6 +417,12 @@ class _LossFn(torch.autograd.Function):
             Bn, N, K = S.shape
             frob = ctx.link_kind == 'frobenius'
             lim = ctx.nb is not None
+            if not frob and getattr(ctx, 'inv_dev', None) is not None:       # upstream * (1 / sum n_b^2), on device
+                gi = ws.f(1)
+                call('gp_mul_add_dev', g.data_ptr(), ctx.inv_dev.data_ptr(), None, None, gi.data_ptr(), st)
+                g_link = gi
+            else:
+                g_link = g
             if ctx.sb is not None:
                 if frob:        # per-graph factor coef[b] * upstream folded into a scaled bf16 copy of S
                     ssb = T.bfbuf(ws, Bn, N, K)
@@ -418,7 +430,7 @@ class _LossFn(torch.autograd.Function):
                          ssb.ptr, ssb.ld, ssb.ld, st)
                     dS = T.linkloss_backward(ws, ctx.gsym, ssb, ctx.nb, Bn, N, K, 1.0, None, asym=ctx.asym)
                 else:
-                    dS = T.linkloss_backward(ws, ctx.gsym, ctx.sb, ctx.nb, Bn, N, K, ctx.inv, g.data_ptr(), asym=ctx.asym)
+                    dS = T.linkloss_backward(ws, ctx.gsym, ctx.sb, ctx.nb, Bn, N, K, ctx.inv, g_link.data_ptr(), asym=ctx.asym)
             else:
                 dS = ws.f(Bn, N, K)
                 if frob:
@@ -430,7 +442,7 @@ class _LossFn(torch.autograd.Function):
                 else:
                     E.bgemm(ctx.gsym.data_ptr(), S.data_ptr(), dS.data_ptr(), N, K, N, Bn, (N * N, N, 1),
                             (N * K, K, 1), (N * K, K, 1), lim=E._p(ctx.nb), lim_m=int(lim), lim_k=int(lim),
-                            alpha=ctx.inv, alpha_dev=g.data_ptr())
+                            alpha=ctx.inv, alpha_dev=g_link.data_ptr())
             ctx.gsym = None
         if ctx.ent_w != 0.0 and ctx.needs_input_grad[3]:
             S = ctx.S
@@ -776,10 +788,18 @@ class SoftPoolingGcnEncoder(GcnEncoderGraph):
             lp.nb_dev, nb_host = plan.nb_dev, plan.nb_host                   # 2-argument call: the forward's n_b
         else:
             lp.nb_dev, nb_host = E.prep_nb(batch_num_nodes, N0, S0.device)
+        lp.inv_dev = None
+        dev_only = nb_host is None and lp.nb_dev is not None               # node counts on the device only
+        if dev_only and ent_w != 0.0:
+            raise NotImplementedError('gp_b200: entropy_weight with device-resident batch_num_nodes')
         lp.num_real_rows = S0.shape[0] * N0 if nb_host is None else max(int(np.sum(nb_host.astype(np.int64))), 1)
         if self.linkpred:
             adj = E._chk_adj(adj, lp.sb0 is not None)
-            if nb_host is None:
+            if dev_only:
+                st = torch.empty(2, device=S0.device, dtype=torch.float32)
+                call('gp_nb_stats', lp.nb_dev.data_ptr(), S0.shape[0], st.data_ptr(), E._stream())
+                lp.inv_dev, lp.num_entries = st[0:1], 1
+            elif nb_host is None:
                 lp.num_entries = adj.shape[1] * adj.shape[1] * adj.shape[0]
                 print('Warning: calculating link pred loss without masking')       # encoders.py:1324
             else:

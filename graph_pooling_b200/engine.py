@@ -238,6 +238,12 @@ def prep_nb(batch_num_nodes, N, device):
     """batch_num_nodes (host numpy / list / tensor, train.py:200) -> (int32 device tensor, host array)."""
     if batch_num_nodes is None:
         return None, None
+    if torch.is_tensor(batch_num_nodes) and batch_num_nodes.is_cuda:
+        # device-resident node counts (int32): used as they are, no host copy, no synchronisation -- what a captured
+        # CUDA graph needs (graphed.py).  The host never sees the values: range checks are the caller's job.
+        if batch_num_nodes.dtype != torch.int32 or batch_num_nodes.dim() != 1:
+            raise ValueError('device batch_num_nodes must be a 1-D int32 tensor')
+        return batch_num_nodes.contiguous(), None
     if torch.is_tensor(batch_num_nodes):
         host = batch_num_nodes.detach().cpu().numpy()
     else:

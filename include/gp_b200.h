@@ -333,6 +333,11 @@ int gp_entropy_fwd(const float* s, const int32_t* nb, int B, int N, int K, float
 int gp_entropy_bwd(const float* s, const int32_t* nb, int B, int N, int K, const float* upstream, float scale,
                    float* ds, int accumulate, gp_stream_t stream);
 int gp_add_scaled(const float* base, const float* term, float w, float* total, gp_stream_t stream);
+/* Device-resident normalisers (node counts known on the device only, e.g. inside a captured CUDA graph):
+ *   gp_nb_stats     out[0] = 1 / sum_b nb[b]^2 (encoders.py:1326) ; out[1] = 1 / sum_b nb[b]
+ *   gp_mul_add_dev  prod = (*a) * (*b) ; total = (c ? *c : 0) + prod      (all device scalars; outputs optional) */
+int gp_nb_stats(const int32_t* nb, int B, float* out, gp_stream_t stream);
+int gp_mul_add_dev(const float* a, const float* b, const float* c, float* total, float* prod, gp_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Cross entropy (encoders.py:1127): loss = mean_b -log softmax(logits)[label]; probs saved.
