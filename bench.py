@@ -348,6 +348,17 @@ def main():
         ax()
     reps = 10
     kms = timed_local(lambda: ax(), reps) / reps
+    # the same contraction with the padding-aware schedule switched off (every tile of the padded N x N computed):
+    # identical result (the padding is zero), reported to show what the tile skip saves on ragged batches
+    if prec == 'bf16':
+        def ax_dense():
+            T.tcgemm(adjb, T.KM, xinb, T.MN, N, H, N, B, Cb=ub)
+    else:
+        def ax_dense():
+            E.bgemm(adj.data_ptr(), xin.data_ptr(), u.data_ptr(), N, H, N, B, (N * N, N, 1), (N * H, H, 1),
+                    (N * H, H, 1))
+    ax_dense()
+    kms_dense = timed_local(ax_dense, reps) / reps
     kfl, kby = roofline.ax_kernel_work(nb, H, elt=2 if prec == 'bf16' else 4)
     ai = kfl / kby
     ridge = tf_sus * 1e12 / (hbm * 1e9)
@@ -371,6 +382,9 @@ def main():
         'gp::v2::tc_gemm2_kernel<128,6,0,8> tcgen05+TMA persistent' if prec == 'bf16' else 'gp::bgemm_kernel FFMA',
         N, H, B)
     roof['ms_per_launch'] = kms
+    roof['ms_per_launch_without_tile_skip'] = kms_dense
+    nbf_ = np.asarray(nb, dtype=np.float64)
+    roof['occupancy_sum_nb2_over_B_N2'] = float(np.sum(nbf_ * nbf_) / (len(nbf_) * float(N) * N))
     roof['tflops'] = kfl / (kms * 1e-3) / 1e12
     roof['peak_source'] = src + ' (MEASURED_PEAKS.json; kernel timed alone -> burst figures)'
     fwd_fl, bwd_fl = roofline.step_flops(nb, cfg)

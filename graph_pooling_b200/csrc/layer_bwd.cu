@@ -189,6 +189,192 @@ __global__ void __launch_bounds__(256) layer_bwd_bn_kernel(const LbArgs a, int C
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Pipelined BN variant: PERSISTENT clusters.  The one-node-per-cluster kernel above spends most of a CTA's life
+// outside its load phase (cluster syncs, reduction, launch of the next cluster), so HBM idles: measured 2.5 TB/s.
+// Here a cluster of CS CTAs walks nodes n = cluster, cluster + G, ...; the rows of node i+1 stream into the other
+// shared-memory stage with cp.async (16 B per thread) while node i is reduced and finished, so loads are always in
+// flight.  One cluster.sync per node (the exchanged partial is double-buffered by iteration parity).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int NKEEP>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NKEEP) : "memory"); }
+
+template <int T, int NST>
+__global__ void __launch_bounds__(T, 1)
+layer_bwd_bn_pipe_kernel(const LbArgs a, int CS, int rows_per_cta, int nclusters) {
+  extern __shared__ __align__(16) float smem_f[];
+  __shared__ float red[2][T / 32];
+  __shared__ float cta_part[2][2];
+  __shared__ __align__(16) float colacc[T * 4];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int cl = blockIdx.x / CS;
+  const int rank = blockIdx.x - cl * CS;
+  const int d = a.d, d4 = d >> 2;
+  const int lg4 = 31 - __clz(d4);                        // d4 is a power of two: divisions become shifts
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c = (tid & (d4 - 1)) * 4;
+  const int rstep = T >> lg4;
+  const int b0 = rank * rows_per_cta;
+  const int b1 = min(a.B, b0 + rows_per_cta);
+  const int nrows = max(b1 - b0, 0);
+  const bool has_dz = a.dz != nullptr, has_dx = a.dxn != nullptr;
+  const int nstreams = 1 + (has_dz ? 1 : 0) + (has_dx ? 1 : 0);
+  const int plane = rows_per_cta * d;                    // floats per stream per stage
+  const int rn_f = (rows_per_cta + 3) & ~3;              // per-row divisors of the L2 normalisation ride along
+  const int stage_f = plane * nstreams + rn_f;
+  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem_f);
+
+  auto issue = [&](int n, int stage) {                   // rows of node n -> stage (planes: y, dz, dxn)
+    const uint32_t sb = smem_base + (uint32_t)(stage * stage_f) * 4u;
+    const int per = nrows * d4;
+    for (int idx = tid; idx < per; idx += T) {
+      const int r = idx >> lg4, c4 = idx & (d4 - 1);
+      const long long row = (long long)(b0 + r) * a.N + n;
+      const uint32_t off = (uint32_t)(r * d + c4 * 4) * 4u;
+      cp_async16(sb + off, a.y + row * a.ldy + c4 * 4);
+      int pl = 1;
+      if (has_dz) { cp_async16(sb + (uint32_t)(pl * plane) * 4u + off, a.dz + row * a.lddz + c4 * 4); ++pl; }
+      if (has_dx) { cp_async16(sb + (uint32_t)(pl * plane) * 4u + off, a.dxn + row * a.lddxn + c4 * 4); }
+    }
+    if (a.normalize)
+      for (int r = tid; r < nrows; r += T)
+        cp_async4(sb + (uint32_t)(plane * nstreams + r) * 4u, a.rnorm + (long long)(b0 + r) * a.N + n);
+    cp_async_commit();
+  };
+
+  float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float inv_cnt = 1.f / ((float)a.B * (float)d);
+  int it = 0;
+  int n = cl;
+  // prologue: NST-1 nodes in flight (empty groups keep the wait_group arithmetic uniform at the tail)
+#pragma unroll
+  for (int j = 0; j < NST - 1; ++j) {
+    const int nj = cl + j * nclusters;
+    if (nj < a.N) issue(nj, j); else cp_async_commit();
+  }
+  for (; n < a.N; n += nclusters, ++it) {
+    const int stage = it % NST;
+    const int nn = n + (NST - 1) * nclusters;
+    const float mu = a.mean[n], is = a.invstd[n];        // issued before the wait below: latency overlaps it
+    if (nn < a.N) issue(nn, (it + NST - 1) % NST); else cp_async_commit();
+    cp_async_wait<NST - 1>();
+    __syncthreads();
+    float* sy = smem_f + stage * stage_f;
+    float* sg = sy + plane;                              // plane 1 holds dz (or dxn if no dz); becomes g in place
+    float* sx = sy + 2 * plane;
+    const float* srn = sy + plane * nstreams;
+    // ---- pass 1: g (kept in shared memory), the two batch sums ----
+    float s1 = 0.f, s2 = 0.f;
+    for (int r = tid >> lg4; r < nrows; r += rstep) {     // (no warp collectives inside: lanes may drop out)
+      const int b = b0 + r;
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (nstreams >= 2) g = *reinterpret_cast<const float4*>(sg + r * d + c);
+      if (nstreams == 3) {
+        const float4 t = *reinterpret_cast<const float4*>(sx + r * d + c);
+        g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+      }
+      if (a.dout != nullptr) {
+        const int4 i4 = *reinterpret_cast<const int4*>(a.argidx + (long long)b * a.ldo + c);
+        const float4 o = ld4(a.dout + (long long)b * a.ldo + c);
+        if (i4.x == n) g.x += o.x;
+        if (i4.y == n) g.y += o.y;
+        if (i4.z == n) g.z += o.z;
+        if (i4.w == n) g.w += o.w;
+      }
+      const float4 y = *reinterpret_cast<const float4*>(sy + r * d + c);
+      const float hx = ((a.relu ? fmaxf(y.x, 0.f) : y.x) - mu) * is, hy = ((a.relu ? fmaxf(y.y, 0.f) : y.y) - mu) * is;
+      const float hz = ((a.relu ? fmaxf(y.z, 0.f) : y.z) - mu) * is, hw = ((a.relu ? fmaxf(y.w, 0.f) : y.w) - mu) * is;
+      s1 += (g.x + g.y) + (g.z + g.w);
+      s2 = fmaf(g.x, hx, s2); s2 = fmaf(g.y, hy, s2); s2 = fmaf(g.z, hz, s2); s2 = fmaf(g.w, hw, s2);
+      if (nstreams >= 2) *reinterpret_cast<float4*>(sg + r * d + c) = g;   // same thread re-reads it in pass 2
+      else if (a.dout != nullptr) { /* g lives only in the scatter: recomputed in pass 2 */ }
+    }
+    s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if (lane == 0) { red[0][warp] = s1; red[1][warp] = s2; }
+    __syncthreads();
+    if (tid == 0) {
+      float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+      for (int w = 0; w < T / 32; ++w) { t1 += red[0][w]; t2 += red[1][w]; }
+      cta_part[it & 1][0] = t1; cta_part[it & 1][1] = t2;
+    }
+    cluster.sync();
+    float S1 = 0.f, S2 = 0.f;
+    for (int r = 0; r < CS; ++r) {                       // same order in every CTA: bitwise-identical means
+      const float* rp = cluster.map_shared_rank(&cta_part[it & 1][0], r);
+      S1 += rp[0]; S2 += rp[1];
+    }
+    const float m1 = S1 * inv_cnt, m2 = S2 * inv_cnt;
+    // ---- pass 2: finish the rows (block-uniform trip count: the row's dot product is a warp shuffle) ----
+    for (int r0 = 0; r0 < nrows; r0 += rstep) {
+      const int r = r0 + (tid >> lg4);
+      const bool live = r < nrows;
+      const int b = b0 + r;
+      const long long row = (long long)b * a.N + n;
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!live) {
+        // nothing to load: g = y = 0
+      } else if (nstreams >= 2) {
+        g = *reinterpret_cast<const float4*>(sg + r * d + c);
+      } else if (a.dout != nullptr) {
+        const int4 i4 = *reinterpret_cast<const int4*>(a.argidx + (long long)b * a.ldo + c);
+        const float4 o = ld4(a.dout + (long long)b * a.ldo + c);
+        if (i4.x == n) g.x += o.x;
+        if (i4.y == n) g.y += o.y;
+        if (i4.z == n) g.z += o.z;
+        if (i4.w == n) g.w += o.w;
+      }
+      const float4 y = live ? *reinterpret_cast<const float4*>(sy + r * d + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float hx = ((a.relu ? fmaxf(y.x, 0.f) : y.x) - mu) * is, hy = ((a.relu ? fmaxf(y.y, 0.f) : y.y) - mu) * is;
+      const float hz = ((a.relu ? fmaxf(y.z, 0.f) : y.z) - mu) * is, hw = ((a.relu ? fmaxf(y.w, 0.f) : y.w) - mu) * is;
+      float4 v;
+      v.x = (g.x - m1 - hx * m2) * is; v.y = (g.y - m1 - hy * m2) * is;
+      v.z = (g.z - m1 - hz * m2) * is; v.w = (g.w - m1 - hw * m2) * is;
+      if (a.relu) {
+        if (!(y.x > 0.f)) v.x = 0.f;
+        if (!(y.y > 0.f)) v.y = 0.f;
+        if (!(y.z > 0.f)) v.z = 0.f;
+        if (!(y.w > 0.f)) v.w = 0.f;
+      }
+      if (a.normalize) {
+        float dot = fmaf(v.x, y.x, fmaf(v.y, y.y, fmaf(v.z, y.z, v.w * y.w)));
+        for (int o = d4 >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        const float rr = live ? srn[r] : 1.f;
+        if (!(rr > kEpsNormB)) {
+          v.x /= kEpsNormB; v.y /= kEpsNormB; v.z /= kEpsNormB; v.w /= kEpsNormB;
+        } else {
+          const float ir = 1.f / rr;
+          v.x = (v.x - y.x * dot) * ir; v.y = (v.y - y.y * dot) * ir;
+          v.z = (v.z - y.z * dot) * ir; v.w = (v.w - y.w * dot) * ir;
+        }
+      }
+      if (live) {
+        store_dv(a, row, c, v);
+        cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
+      }
+    }
+    __syncthreads();                                     // this stage may be refilled two iterations from now
+  }
+  if (a.part != nullptr) {                               // deterministic per-CTA column sums over all its nodes
+    *reinterpret_cast<float4*>(&colacc[tid * 4]) = cs;
+    __syncthreads();
+    if (tid < d) {
+      const int q = tid >> 2, e = tid & 3;
+      float t = 0.f;
+      for (int r = q; r < T; r += d4) t += colacc[r * 4 + e];
+      a.part[(long long)blockIdx.x * d + tid] = t;
+    }
+  }
+  cluster.sync();                                        // nobody exits while its partials may still be read
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // No BN: one warp per row, lane owns float4 columns lane, lane+32, ... (VPL of them).
 // ---------------------------------------------------------------------------------------------------------
 template <int VPL>
@@ -337,6 +523,74 @@ int layer_bwd_fast(const gp_layer_bwd* q, cudaStream_t st, bool* handled) {
   a.dv = q->dv; a.dvb = reinterpret_cast<__nv_bfloat16*>(q->dv_bf16); a.lddvb = q->lddvb;
   a.part = q->db != nullptr ? q->ws : nullptr;
   long long part_rows = 0;
+  static int use_pipe = -1;
+  // opt-in (GP_LBWD_PIPE=1): measured r1 on B=256, N=2048, d=128: 0.371 ms (2 stages, 512 threads) vs 0.380 ms for
+  // the one-node-per-cluster kernel -- both ~2.5 TB/s; the per-node cluster sync + reduction chain bounds them,
+  // not HBM.  Kept for the next step (several nodes per iteration to amortise the sync).
+  if (use_pipe < 0) { const char* e = getenv("GP_LBWD_PIPE"); use_pipe = (e != nullptr && atoi(e) != 0) ? 1 : 0; }
+  if (q->bn && use_pipe && q->h == nullptr && q->mean != nullptr) {
+    // persistent pipelined variant when two stages of a CTA's rows fit in shared memory
+    int PCS = 1;
+    const int nstreams = 1 + (q->dz ? 1 : 0) + (q->dxn ? 1 : 0);
+    auto stage_bytes = [&](int cs_) {
+      const size_t rpc_ = (size_t)((q->B + cs_ - 1) / cs_);
+      return (rpc_ * d * nstreams + ((rpc_ + 3) & ~(size_t)3)) * 4;
+    };
+    static int pipe_stages = 0;
+    if (pipe_stages == 0) {
+      const char* e = getenv("GP_LBWD_STAGES");
+      pipe_stages = e != nullptr ? atoi(e) : 2;
+      if (pipe_stages < 2 || pipe_stages > 4) pipe_stages = 2;
+    }
+    while (PCS <= 8 && stage_bytes(PCS) * pipe_stages > 200 * 1024) PCS *= 2;
+    if (PCS <= 8 && q->N >= 64) {
+      const int rpc = (q->B + PCS - 1) / PCS;
+      const size_t smem = stage_bytes(PCS) * pipe_stages;
+      int ncl = kNumSMs / PCS;
+      if (ncl > q->N) ncl = q->N;
+      static int pipe_threads = 0;
+      if (pipe_threads == 0) {
+        const char* e = getenv("GP_LBWD_THREADS");
+        pipe_threads = e != nullptr ? atoi(e) : 512;
+        if (pipe_threads != 256 && pipe_threads != 512 && pipe_threads != 1024) pipe_threads = 512;
+      }
+      using PipeFn = void (*)(const LbArgs, int, int, int);
+      PipeFn pipe_kern = nullptr;
+#define GP_PIPE_SEL(T_, S_) if (pipe_threads == T_ && pipe_stages == S_) pipe_kern = layer_bwd_bn_pipe_kernel<T_, S_>;
+      GP_PIPE_SEL(256, 2) GP_PIPE_SEL(256, 3) GP_PIPE_SEL(256, 4)
+      GP_PIPE_SEL(512, 2) GP_PIPE_SEL(512, 3) GP_PIPE_SEL(512, 4)
+      GP_PIPE_SEL(1024, 2) GP_PIPE_SEL(1024, 3) GP_PIPE_SEL(1024, 4)
+#undef GP_PIPE_SEL
+      static bool cfgd = false;
+      if (!cfgd) { GP_CUDA(cudaFuncSetAttribute(pipe_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); cfgd = true; }
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)(ncl * PCS));
+      cfg.blockDim = dim3(pipe_threads);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = PCS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      // persistent clusters must all be co-resident: GPC sizes are not multiples of every cluster size
+      static int max_clusters[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      if (max_clusters[PCS] == 0) {
+        int mc = 0;
+        if (cudaOccupancyMaxActiveClusters(&mc, pipe_kern, &cfg) != cudaSuccess || mc < 1) mc = 1;
+        max_clusters[PCS] = mc;
+        if (getenv("GP_DEBUG")) fprintf(stderr, "[gp] layer_bwd_bn_pipe: cluster %d, smem %zu B -> max active clusters %d\n", PCS, smem, mc);
+      }
+      if (ncl > max_clusters[PCS]) ncl = max_clusters[PCS];
+      cfg.gridDim = dim3((unsigned)(ncl * PCS));
+      GP_CUDA(cudaLaunchKernelEx(&cfg, pipe_kern, a, PCS, rpc, ncl));
+      g_launches++;
+      part_rows = (long long)ncl * PCS;
+      if (q->db != nullptr)
+        GP_TRY(colsum(q->ws, part_rows, d, d, q->db, 0, q->ws + part_rows * d, st));
+      *handled = true;
+      return GP_OK;
+    }
+  }
   if (q->bn) {
     const int rstep = 256 / (d / 4);
     const int rpc = (q->B + CS - 1) / CS;
