@@ -28,6 +28,12 @@ x = torch.randn(B, N, H, device=dev).bfloat16()
 if which in ('all', 'ax'):
     ub = T.bfbuf(ws, B, N, H)
     timeit('A.X  bf16 out', lambda: T.tcgemm(op(adj), 0, op(x), 1, N, H, N, B, Cb=ub), 2.0 * B * N * N * H, B * (N * N + 2 * N * H) * 2)
+if which in ('all', 'ax2'):
+    # the lock-step embedding + assignment GCN contraction: U = A.[h | a], 256 columns (engine_tc.dual_stack_forward)
+    x2 = torch.randn(B, N, 2 * H, device=dev).bfloat16()
+    ub2 = T.bfbuf(ws, B, N, 2 * H)
+    timeit('A.[h|a] 256 cols bf16 out', lambda: T.tcgemm(op(adj), 0, op(x2), 1, N, 2 * H, N, B, Cb=ub2),
+           2.0 * B * N * N * 2 * H, B * (N * N + 2 * N * 2 * H) * 2)
 if which in ('all', 'tsa'):
     # pooling contraction T = S^T A (encoders.py:1279): M=K, N=N, k=N ; S M-major, A N-major
     s_ = torch.rand(B, N, K, device=dev).bfloat16()
