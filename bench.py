@@ -359,33 +359,57 @@ def main():
                     (N * H, H, 1))
     ax_dense()
     kms_dense = timed_local(ax_dense, reps) / reps
-    kfl, kby = roofline.ax_kernel_work(nb, H, elt=2 if prec == 'bf16' else 4)
+    # The dominant launch shape of the step.  bf16 DiffPool: embedding and assignment GCN run in lock-step, so the
+    # N x N contraction is U = A.[h | a] at 2H columns (4 launches / ~11 % of the cfg4 step, the largest share of one
+    # shape; profiles/r1u_launches_cfg4_bf16.md) -- timed live here.  Otherwise: the H-column U = A.X.
+    dual = prec == 'bf16' and soft and H % 8 == 0 and H <= 256
+    cols = 2 * H if dual else H
+    if dual:
+        x2 = T.bfbuf(wsb, B, N, cols)
+        x2.t.normal_()
+        u2 = T.bfbuf(wsb, B, N, cols)
+
+        def ax2():
+            T.tcgemm(adjb, T.KM, x2, T.MN, N, cols, N, B, Cb=u2, lim=nbd.data_ptr(), lim_m=1, lim_k=1)
+        for _ in range(3):
+            ax2()
+        kms_dom = timed_local(ax2, reps) / reps
+        del x2, u2
+    else:
+        kms_dom = kms
+    kfl, kby = roofline.ax_kernel_work(nb, cols, elt=2 if prec == 'bf16' else 4)
     ai = kfl / kby
     ridge = tf_sus * 1e12 / (hbm * 1e9)
-    # the dominant launch of the step (12 of ~160 launches, ~22 % of the step's device time, the largest single
-    # shape): at din=128 columns its arithmetic intensity (~128 flop/B in bf16) is BELOW the ridge -> HBM-bound
-    if ai >= ridge:
-        roof = {'bound': 'tensor', 'achieved': kfl / (kms * 1e-3) / 1e12, 'peak': tf_burst, 'unit': 'TFLOP/s'}
+    # which roof binds THIS launch: the larger of its HBM time and its tensor time at the measured peaks
+    t_hbm, t_tc = kby / (hbm * 1e9), kfl / (tf_burst * 1e12)
+    if prec == 'bf16' and t_tc > t_hbm:
+        roof = {'bound': 'tensor', 'achieved': kfl / (kms_dom * 1e-3) / 1e12, 'peak': tf_burst, 'unit': 'TFLOP/s'}
     else:
-        roof = {'bound': 'hbm', 'achieved': kby / (kms * 1e-3) / 1e9, 'peak': hbm, 'unit': 'GB/s'}
+        roof = {'bound': 'hbm', 'achieved': kby / (kms_dom * 1e-3) / 1e9, 'peak': hbm, 'unit': 'GB/s'}
     roof['frac'] = roof['achieved'] / roof['peak']
     traffic = None
     tpath = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
     tj = json.load(open(tpath)) if os.path.exists(tpath) else {}
-    if prec == 'bf16' and args.workload == 'cfg4_diffpool_256x2048' and B == 256 and 'ax_gemm' in tj:
-        traffic = tj['ax_gemm']['dram_bytes_per_launch']           # ncu --set full, same shape (profiles/)
+    tkey = 'ax2_gemm' if dual else 'ax_gemm'
+    if prec == 'bf16' and args.workload == 'cfg4_diffpool_256x2048' and B == 256 and tkey in tj:
+        traffic = tj[tkey]['dram_bytes_per_launch']               # ncu --set full, same shape (profiles/)
+        roof['ncu_tensor_pipe_active_pct'] = tj[tkey].get('tensor_pipe_active_pct')
     roof['traffic'] = traffic
     roof['algorithmic_bytes_per_launch'] = kby
     roof['algorithmic_flops_per_launch'] = kfl
     roof['arithmetic_intensity_flop_per_byte'] = ai
-    roof['kernel'] = '%s (U = A.X, N=%d, din=%d, batch=%d)' % (
-        'gp::v2::tc_gemm2_kernel<128,6,0,8> tcgen05+TMA persistent' if prec == 'bf16' else 'gp::bgemm_kernel FFMA',
-        N, H, B)
-    roof['ms_per_launch'] = kms
-    roof['ms_per_launch_without_tile_skip'] = kms_dense
+    roof['kernel'] = '%s (U = A.%s, N=%d, %d columns, batch=%d)' % (
+        ('gp::v2::tc_gemm2_kernel<%s,0,8> tcgen05+TMA persistent' % ('256,4' if cols > 128 else '128,6'))
+        if prec == 'bf16' else 'gp::bgemm_kernel FFMA', '[h|a]' if dual else 'X', N, cols, B)
+    roof['tflops'] = kfl / (kms_dom * 1e-3) / 1e12
+    roof['frac_of_tensor_peak'] = roof['tflops'] / tf_burst if prec == 'bf16' else None
+    roof['frac_of_hbm_peak'] = kby / (kms_dom * 1e-3) / 1e9 / hbm
+    roof['h_column_ax'] = {'ms_per_launch': kms, 'gbs_algorithmic':
+                           roofline.ax_kernel_work(nb, H, elt=2 if prec == 'bf16' else 4)[1] / (kms * 1e-3) / 1e9}
+    roof['ms_per_launch'] = kms_dom
+    roof['h_column_ax']['ms_per_launch_without_tile_skip'] = kms_dense
     nbf_ = np.asarray(nb, dtype=np.float64)
     roof['occupancy_sum_nb2_over_B_N2'] = float(np.sum(nbf_ * nbf_) / (len(nbf_) * float(N) * N))
-    roof['tflops'] = kfl / (kms * 1e-3) / 1e12
     roof['peak_source'] = src + ' (MEASURED_PEAKS.json; kernel timed alone -> burst figures)'
     fwd_fl, bwd_fl = roofline.step_flops(nb, cfg)
     roof['step_algorithmic_tflop'] = (fwd_fl + bwd_fl) / 1e12
