@@ -84,3 +84,30 @@ def test_enzymes_training_matches_oracle(precision, loss_tol, acc_tol):
         assert abs(a - b) <= loss_tol * abs(b), (lc, lo)
     assert lo[-1] < lo[0] - 0.1                      # it actually learns
     assert abs(trc - tro) <= acc_tol and abs(vac - vao) <= acc_tol + 0.03, (trc, tro, vac, vao)
+
+
+def test_device_batch_feed_and_uint8_step():
+    """GPU-resident feed (data.GraphSet): batches assembled on the device from the edge list equal the padded
+    arrays of the reference's sampler, and a uint8-adjacency train step (tensor-core mode, CUDA-graph replay)
+    gives the same loss as the fp32-adjacency step."""
+    import os
+    from helpers import HERE
+    from graph_pooling_b200 import encoders, graphed
+    from graph_pooling_b200.data import GraphSet
+    x, adj, nb, label = load_enzymes()
+    z = np.load(os.path.join(HERE, 'golden', 'dataset_enzymes.npz'))
+    gs = GraphSet(z['n'], z['glabel'].astype(np.int64) - int(z['glabel'].min()), z['nlabel'], z['eptr'], z['edges'],
+                  int(z['num_node_labels'])).to('cuda')
+    idx = np.array([3, 77, 590, 12, 400, 250, 9, 101])
+    bx, badj, bnb, bl = gs.batch(idx, 100)
+    assert badj.dtype == torch.uint8
+    assert np.array_equal(bx.cpu().numpy(), x[idx]) and np.array_equal(badj.cpu().numpy().astype(np.float32), adj[idx])
+    assert np.array_equal(bnb.cpu().numpy(), nb[idx]) and np.array_equal(bl.cpu().numpy(), label[idx])
+    torch.manual_seed(0)
+    m = encoders.SoftPoolingGcnEncoder(100, 3, 32, 32, 6, 3, 32, assign_ratio=0.1).cuda()
+    m.precision = 1
+    yp = m(bx, badj.float(), bnb, assign_x=bx)
+    l_f32 = m.loss(yp, bl, badj.float(), bnb).item()
+    g = graphed.GraphedTrainStep(m)
+    _, l_u8 = g.step(bx, badj, bnb, bl)
+    assert abs(l_u8.item() - l_f32) < 1e-6 * abs(l_f32)
