@@ -91,7 +91,7 @@ def _fwd_tc(ctx, plan, x, adj, assign_x, params):
             z2, z2b, c_post = T.stack_forward(ws, xpb, Fw, apb, None, B, K, wq, bq, plan.bn_post)
             call('gp_readout_max_fwd', z2.data_ptr(), Fw, None, B, K, Fw, out.data_ptr() + (i + 1) * Fw * 4,
                  arg.data_ptr() + (i + 1) * Fw * 4, ldo, st)
-            levels.append(dict(K=K, N=cur_N, nb=cur_nb, adjb=cur_adjb, zb=cur_zb, S=S, sb=sb, zab=zab, Fa=Fa,
+            levels.append(dict(K=K, N=cur_N, nb=cur_nb, adjb=cur_adjb, zb=cur_zb, S=S.detach(), sb=sb, zab=zab, Fa=Fa,
                                c_as=c_as, tb=tb, c_post=c_post, wpb=wpb, has_bp=bp is not None,
                                asym=plan.asym if i == 0 else None))
             if i == 0:
@@ -103,7 +103,9 @@ def _fwd_tc(ctx, plan, x, adj, assign_x, params):
     ctx.tape = dict(plan=plan, params=params, B=B, N=N, emb=c_emb, levels=levels, out=out, arg=arg, ldo=ldo,
                     acts=acts, lin=lin, x=x, adj=adj, dual=dual)
     if plan.soft:
-        plan.all_S = [lv['S'] for lv in levels]
+        # detached aliases: the tape holds `plan` and the returned S0 gets this node as grad_fn; storing S0
+        # itself would close a reference cycle through the autograd node that only backward() breaks
+        plan.all_S = [lv['S'].detach() for lv in levels]
         return ypred, S0
     return ypred
 
@@ -223,7 +225,7 @@ class _EncoderFn(torch.autograd.Function):
                                              plan.bn_post, prec)
                 call('gp_readout_max_fwd', z2.data_ptr(), Fw, None, B, K, Fw, out.data_ptr() + (i + 1) * Fw * 4,
                      arg.data_ptr() + (i + 1) * Fw * 4, ldo, st)
-                levels.append(dict(K=K, N=cur_N, nb=cur_nb, adj=cur_adj, z=cur_z, S=S, za=za, Fa=Fa, c_as=c_as,
+                levels.append(dict(K=K, N=cur_N, nb=cur_nb, adj=cur_adj, z=cur_z, S=S.detach(), za=za, Fa=Fa, c_as=c_as,
                                    xp=xp, t=t, ap=ap, c_post=c_post, wp=wp, has_bp=bp is not None))
                 if i == 0:
                     S0 = S
@@ -236,7 +238,9 @@ class _EncoderFn(torch.autograd.Function):
         tape.update(levels=levels, out=out, arg=arg, ldo=ldo, acts=acts, lin=lin, x=x, adj=adj, assign_x=assign_x)
         ctx.tape = tape
         if plan.soft:
-            plan.all_S = [lv['S'] for lv in levels]
+            # detached aliases: the tape holds `plan` and the returned S0 gets this node as grad_fn; storing S0
+            # itself would close a reference cycle through the autograd node that only backward() breaks
+            plan.all_S = [lv['S'].detach() for lv in levels]
             return ypred, S0
         return ypred
 
@@ -494,7 +498,8 @@ class _GraphConvFn(torch.autograd.Function):
         u, y, rn = ws.f(B, N, din), ws.f(B, N, dout), ws.f(B, N)
         call('gp_graphconv_fwd', x.data_ptr(), din, adj.data_ptr(), w.data_ptr(), E._p(b), None, B, N, din, dout,
              int(add_self), int(normalize), u.data_ptr(), y.data_ptr(), dout, rn.data_ptr(), E.F32, E._stream())
-        ctx.saved = (x, adj, w, b is not None, u, y, rn, add_self, normalize)
+        # y is this node's output: keep a detached alias (saving the output object itself would form a cycle)
+        ctx.saved = (x, adj, w, b is not None, u, y.detach(), rn, add_self, normalize)
         ctx.need = (ctx.needs_input_grad[0], ctx.needs_input_grad[1])
         return y
 

@@ -209,7 +209,9 @@ def mlp_fwd(ws, x_ptr, ldx, rows, linears):
     for i, (w, b) in enumerate(linears):
         h = linear_fwd(ws, ptr, ld, rows, w, b, relu=(i < len(linears) - 1))
         ptr, ld = h.data_ptr(), h.shape[1]
-        acts.append((ptr, ld, h))
+        # the last activation is the encoder's OUTPUT (ypred): the tape keeps a detached alias, never the output
+        # object itself (that would close a reference cycle through the autograd node)
+        acts.append((ptr, ld, h.detach()))
     return h, acts
 
 

@@ -9,6 +9,10 @@ disappears.  Node counts live in a device int32 buffer (the padding-aware tile s
 device; the link-loss normaliser 1/sum n_b^2 is computed on the device too), so a replay needs no host data
 beyond the copies into the static inputs.
 
+Capture rule inherited from PyTorch: no autograd graph built on the default stream with this model may still be
+alive when a shape is first captured (its AccumulateGrad nodes would tie the capture to the legacy stream) --
+drop earlier outputs / losses first.
+
 The captured kernels are exactly the ones the eager path launches (same C-ABI calls, made once at capture
 time); tests/test_gpu_graphed.py checks graph replays against the eager path and the oracle.
 """
@@ -48,6 +52,14 @@ class GraphedTrainStep:
 
     def _capture(self, key, x, adj, label, assign_x):
         dev = x.device
+        # the module stashes outputs of earlier eager calls (assign_tensor, link_loss, ...): they keep those autograd
+        # graphs -- and their default-stream AccumulateGrad nodes -- alive, which would poison the capture
+        for attr in ('assign_tensor', 'assign_tensors', '_S0', 'link_loss', 'entropy_loss', '_plan'):
+            if hasattr(self.model, attr):
+                try:
+                    delattr(self.model, attr)
+                except AttributeError:
+                    pass
         st = {'x': torch.empty_like(x), 'adj': torch.empty_like(adj), 'label': torch.empty_like(label),
               'nb': torch.empty(x.shape[0], device=dev, dtype=torch.int32)}
         st['ax'] = st['x'] if assign_x is None else torch.empty_like(assign_x)

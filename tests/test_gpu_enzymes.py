@@ -108,6 +108,7 @@ def test_device_batch_feed_and_uint8_step():
     m.precision = 1
     yp = m(bx, badj.float(), bnb, assign_x=bx)
     l_f32 = m.loss(yp, bl, badj.float(), bnb).item()
+    del yp                                  # no autograd graph from the default stream may survive into the capture
     g = graphed.GraphedTrainStep(m)
     _, l_u8 = g.step(bx, badj, bnb, bl)
     assert abs(l_u8.item() - l_f32) < 1e-6 * abs(l_f32)

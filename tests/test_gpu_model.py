@@ -204,3 +204,25 @@ def test_soft_large_batch_of_small_graphs_uses_batch_split_bn():
     oracle_vs_candidate(soft_factory(40, 3, 30, 30, 6, ratio=0.1), 18, 640, 40, 3, 6, nb_mode='rand')
     make = lambda mod: mod.GcnEncoderGraph(5, 36, 20, 3, 3, bn=True)
     oracle_vs_candidate(make, 19, 512, 24, 5, 3, soft=False)
+
+
+def test_forward_without_backward_does_not_leak():
+    """evaluate() in train.py runs forwards that are never back-propagated: the autograd tape must not keep the
+    step's buffers alive through a reference cycle (outputs are stored in the tape as detached aliases)."""
+    import gc
+    m = enc().SoftPoolingGcnEncoder(64, 4, 16, 16, 3, 3, 16, assign_ratio=0.25).cuda()
+    x, adj, nb, label = synth_batch(3, 8, 64, 4, 8, 64, 3)
+    xc, ac = torch.tensor(x).cuda(), torch.tensor(adj).cuda()
+    for prec in (0, 1):
+        m.precision = prec
+        m(xc, ac, nb, assign_x=xc)
+        torch.cuda.synchronize()
+        gc.collect()
+        base = torch.cuda.memory_allocated()
+        for _ in range(20):
+            yp = m(xc, ac, nb, assign_x=xc)
+            m.loss(yp, torch.tensor(label).cuda(), ac, nb)
+        del yp
+        gc.collect()
+        torch.cuda.synchronize()
+        assert torch.cuda.memory_allocated() <= base + (1 << 20), (prec, torch.cuda.memory_allocated() - base)
