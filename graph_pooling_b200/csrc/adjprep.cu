@@ -108,18 +108,18 @@ adj_prepare_kernel(const T* __restrict__ adj, const int32_t* __restrict__ nb, in
 // out[b] = bf16( (*cond == 0) ? x[b] + x[b]^T : x[b] ), x [B,K,K] fp32 (the pooled-adjacency gradient dA').
 // 32x32 tiles; the mirrored tile is read coalesced and transposed through shared memory.
 __global__ void __launch_bounds__(256)
-sym_select_kernel(const float* __restrict__ x, int K, const int32_t* __restrict__ cond,
+sym_select_kernel(const float* __restrict__ x, long long ldx, int K, const int32_t* __restrict__ cond,
                   __nv_bfloat16* __restrict__ out, long long ld) {
   __shared__ float Tt[32][33];
   const bool sym = cond != nullptr && *cond == 0;
-  const float* xb = x + (long long)blockIdx.z * K * K;
+  const float* xb = x + (long long)blockIdx.z * K * ldx;
   __nv_bfloat16* ob = out + (long long)blockIdx.z * K * ld;
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   if (sym) {
     for (int r = ty; r < 32; r += 8) {                   // mirrored tile rows c0.., cols r0..
       const int gr = c0 + r, gc = r0 + tx;
-      Tt[r][tx] = (gr < K && gc < K) ? xb[(long long)gr * K + gc] : 0.f;
+      Tt[r][tx] = (gr < K && gc < K) ? xb[(long long)gr * ldx + gc] : 0.f;
     }
     __syncthreads();
   }
@@ -128,7 +128,7 @@ sym_select_kernel(const float* __restrict__ x, int K, const int32_t* __restrict_
     if (gr >= K || gc >= ld) continue;
     float v = 0.f;
     if (gc < K) {
-      v = xb[(long long)gr * K + gc];
+      v = xb[(long long)gr * ldx + gc];
       if (sym) v += Tt[tx][r];
     }
     ob[(long long)gr * ld + gc] = __float2bfloat16_rn(v);
@@ -139,11 +139,11 @@ sym_select_kernel(const float* __restrict__ x, int K, const int32_t* __restrict_
 
 using namespace gp;
 
-extern "C" int gp_sym_select_bf16(const float* x, int B, int K, const int32_t* cond, void* out_bf16, long long ld,
-                                  gp_stream_t stream) {
-  GP_REQUIRE(x && out_bf16 && B > 0 && K > 0 && ld >= K && B <= 65535, "sym_select_bf16: bad args");
+extern "C" int gp_sym_select_bf16(const float* x, long long ldx, int B, int K, const int32_t* cond, void* out_bf16,
+                                  long long ld, gp_stream_t stream) {
+  GP_REQUIRE(x && out_bf16 && B > 0 && K > 0 && ld >= K && ldx >= K && B <= 65535, "sym_select_bf16: bad args");
   sym_select_kernel<<<dim3((unsigned)((ld + 31) / 32), (unsigned)((K + 31) / 32), (unsigned)B), 256, 0, S(stream)>>>(
-      x, K, cond, reinterpret_cast<__nv_bfloat16*>(out_bf16), ld);
+      x, ldx, K, cond, reinterpret_cast<__nv_bfloat16*>(out_bf16), ld);
   GP_LAUNCHED();
   return GP_OK;
 }

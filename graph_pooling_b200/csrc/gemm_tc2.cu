@@ -134,7 +134,7 @@ struct Smem {
   static constexpr int kB = BN * BK * 2;
   static constexpr int kStage = kA + kB;
   static constexpr int kStaging = EW * 32 * 32 * 4;
-  static constexpr int kBytes = STAGES * kStage + kStaging + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*bias*/;
+  static constexpr int kBytes = STAGES * kStage + kStaging + 1024 /*align slack*/ + 256 /*barriers*/ + (BN > 256 ? 2048 : 1024) /*bias*/;
 };
 
 template <int BN>
@@ -297,7 +297,13 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
       reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * L::kStage + L::kStaging + 8 * (2 * STAGES + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;          // BN in {64,128,256} -> 128/256/512
+  // BN <= 256: two accumulator buffers (the epilogue of tile i overlaps the MMAs of tile i+1).  BN == 512 (row-owning
+  // epilogues over rows wider than 256: the assignment GCN's last layer): ONE buffer filling all 512 TMEM columns,
+  // two N = 256 MMAs per k-step; MMA and epilogue of a CTA then alternate (the epilogue is HBM-write-bound).
+  constexpr int NACC = BN > 256 ? 1 : 2;
+  constexpr int MMA_N = BN > 256 ? 256 : BN;
+  constexpr int NHALF = BN / MMA_N;
+  constexpr int TMEM_COLS = NACC * BN < 32 ? 32 : NACC * BN;   // 128 / 256 / 512
   constexpr int kProd = EW, kMma = EW + 1;
 
   if (warp == kMma) {
@@ -305,7 +311,7 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-      for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EW); }
+      for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EW); }   // NACC == 1 uses a = 0
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -340,7 +346,7 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
   }
   float* sbias = reinterpret_cast<float*>(smem_gen + STAGES * L::kStage + L::kStaging + 256);
   if (EPI == 2) {                                        // bias (zero beyond N) staged once per CTA
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) sbias[i] = (p.bias != nullptr && i < p.N) ? p.bias[i] : 0.f;
+    for (int i = threadIdx.x; i < (BN > 256 ? 512 : 256); i += blockDim.x) sbias[i] = (p.bias != nullptr && i < p.N) ? p.bias[i] : 0.f;
     __syncthreads();
   }
 
@@ -371,7 +377,9 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
               for (int j = 0; j < BN / 64; ++j)
                 tma_load_3d(sb + j * 8192, &maps.b[q], full_bar(s), k.n0 + 64 * j, k0, k.b);
             } else {
-              tma_load_3d(sb, &maps.b[q], full_bar(s), k0, k.n0, k.b);
+#pragma unroll
+              for (int j = 0; j < NHALF; ++j)            // TMA boxes are at most 256 rows
+                tma_load_3d(sb + j * (MMA_N * 128), &maps.b[q], full_bar(s), k0, k.n0 + MMA_N * j, k.b);
             }
           }
           pos += k.kt[q];
@@ -386,7 +394,7 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
         Work k = get_work<BN>(p, w, npairs, sym_upper);
         finish_work<BN>(p, k, sym_upper);
         if (k.kt1 <= k.kt0) continue;
-        const uint32_t a = nacc & 1, aph = (nacc >> 1) & 1;
+        const uint32_t a = NACC == 2 ? (nacc & 1) : 0u, aph = NACC == 2 ? ((nacc >> 1) & 1) : (nacc & 1);
         mbar_wait(tempty_bar(a), aph ^ 1);               // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tm = tmem_base + a * BN;
@@ -396,7 +404,7 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
           const int lo = max(k.kt0, pos), hi = min(k.kt1, pos + k.kt[q]);
           const bool amn = p.a_mn[q] != 0, bmn = p.b_mn[q] != 0;
           const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((amn ? 1u : 0u) << 15) |
-                                 ((bmn ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                                 ((bmn ? 1u : 0u) << 16) | ((uint32_t)(MMA_N >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
           for (int g = lo; g < hi; ++g, ++it) {
             const int s = it % STAGES, ph = (it / STAGES) & 1;
             mbar_wait(full_bar(s), ph);
@@ -405,8 +413,12 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
 #pragma unroll
             for (int kk = 0; kk < BK / 16; ++kk) {
               const uint64_t ad = amn ? umma_desc(sa + kk * 2048, 8192, 1024) : umma_desc(sa + kk * 32, 16, 1024);
-              const uint64_t bd = bmn ? umma_desc(sb + kk * 2048, 8192, 1024) : umma_desc(sb + kk * 32, 16, 1024);
-              tc_mma_bf16(tm, ad, bd, idesc, (first && kk == 0) ? 0u : 1u);
+#pragma unroll
+              for (int h = 0; h < NHALF; ++h) {          // N-major B: 64-column groups 8 KB apart; K-major: rows 128 B
+                const uint32_t sbh = sb + (bmn ? h * (MMA_N / 64) * 8192 : h * MMA_N * 128);
+                const uint64_t bd = bmn ? umma_desc(sbh + kk * 2048, 8192, 1024) : umma_desc(sbh + kk * 32, 16, 1024);
+                tc_mma_bf16(tm + h * MMA_N, ad, bd, idesc, (first && kk == 0) ? 0u : 1u);
+              }
             }
             first = false;
             tc_commit(empty_bar(s));
@@ -440,7 +452,7 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
       Work k = get_work<BN>(p, w, npairs, sym_upper);
       finish_work<BN>(p, k, sym_upper);
       const bool has_acc = k.kt1 > k.kt0;
-      const uint32_t a = nacc & 1, aph = (nacc >> 1) & 1;
+      const uint32_t a = NACC == 2 ? (nacc & 1) : 0u, aph = NACC == 2 ? ((nacc >> 1) & 1) : (nacc & 1);
       if (has_acc) {
         mbar_wait(tfull_bar(a), aph);
         tc_fence_after();
@@ -898,7 +910,7 @@ int run(const gp_gemm_bf16x* g, cudaStream_t st) {
 int run_norm(const gp_gemm_bf16x* g, float* rnorm, float* rowstat, int stat_relu, cudaStream_t st) {
   GP_REQUIRE(g != nullptr && g->npairs == 1, "bgemm_bf16_norm: exactly one operand pair");
   GP_REQUIRE(g->C || g->Cb, "bgemm_bf16_norm: no output");
-  GP_REQUIRE(g->M > 0 && g->N > 0 && g->N <= 256 && g->batch == 1, "bgemm_bf16_norm: needs batch == 1 and N <= 256");
+  GP_REQUIRE(g->M > 0 && g->N > 0 && g->N <= 512 && g->batch == 1, "bgemm_bf16_norm: needs batch == 1 and N <= 512");
   GP_REQUIRE(g->beta == 0.f && !g->relu && g->split_k <= 1 && g->lim == nullptr,
              "bgemm_bf16_norm: beta / relu / split_k / lim are not supported");
   GP_REQUIRE(rowstat == nullptr || (reinterpret_cast<uintptr_t>(rowstat) & 7) == 0, "bgemm_bf16_norm: rowstat alignment");
@@ -908,10 +920,10 @@ int run_norm(const gp_gemm_bf16x* g, float* rnorm, float* rowstat, int stat_relu
              "bgemm_bf16_norm: operand base must be 16-byte aligned");
   Maps maps;
   Params p;
-  const int BN = g->N > 128 ? 256 : 128;
+  const int BN = g->N > 256 ? 512 : (g->N > 128 ? 256 : 128);
   if (o.a_major == 0) GP_TRY(make_map(&maps.a[0], o.A, o.K, g->M, 1, o.ldA, o.sAb, BM));
   else                GP_TRY(make_map(&maps.a[0], o.A, g->M, o.K, 1, o.ldA, o.sAb, BK));
-  if (o.b_major == 0) GP_TRY(make_map(&maps.b[0], o.B, o.K, g->N, 1, o.ldB, o.sBb, BN));
+  if (o.b_major == 0) GP_TRY(make_map(&maps.b[0], o.B, o.K, g->N, 1, o.ldB, o.sBb, BN > 256 ? 256 : BN));
   else                GP_TRY(make_map(&maps.b[0], o.B, g->N, o.K, 1, o.ldB, o.sBb, BK));
   p.K[0] = o.K; p.a_mn[0] = o.a_major; p.b_mn[0] = o.b_major; p.lim_k[0] = 0;
   for (int q = 1; q < kMaxPairs; ++q) { maps.a[q] = maps.a[0]; maps.b[q] = maps.b[0]; p.K[q] = 0; p.a_mn[q] = p.b_mn[q] = p.lim_k[q] = 0; }
@@ -924,6 +936,7 @@ int run_norm(const gp_gemm_bf16x* g, float* rnorm, float* rowstat, int stat_relu
   p.rnorm = rnorm; p.rowstat = reinterpret_cast<float2*>(rowstat); p.stat_relu = stat_relu;
   p.cond = nullptr; p.cond_npairs = 0; p.cond_alpha = 1.f;
   p.adj_flags = nullptr; p.sym_total = 0; p.sym_per_graph = 0;
+  if (BN == 512) return launch<512, 2, 2, 4>(maps, p, st);
   if (BN == 256) return launch<256, 3, 2, 4>(maps, p, st);
   return launch<128, 4, 2, 4>(maps, p, st);
 }

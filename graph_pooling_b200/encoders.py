@@ -133,7 +133,9 @@ def _bwd_tc(ctx, tape, dypred, dS0):
     dz_dense = None
     if plan.soft:
         levels = tape['levels']
-        d_ap = [ws.z(B, lv['K'], lv['K']) for lv in levels]
+        # dA' accumulators: row stride padded to 4 floats so the read-modify-write GEMM epilogues stay on their
+        # 16-byte vector path for any K (K = 250 / 1250 at the DD / ragged configs)
+        d_ap = [ws.z(B, lv['K'], (lv['K'] + 3) & ~3) for lv in levels]
         dxp_extra = [None] * P
         dz_next = None
         for i in reversed(range(P)):

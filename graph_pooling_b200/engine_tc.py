@@ -168,7 +168,7 @@ def _layer_forward(ws, ctx, l, ub, hb2=None):
     use_bn = bool(ctx.bn and not last)
     uflat, wflat = Op(ub.ptr, ub.ld, 0), Op(wb.ptr, wb.ld, 0)
     mean = invstd = None
-    if dout <= 256:
+    if dout <= 512:                                      # rows up to 512 wide stay in TMEM for the fused tail
         rowstat = ws.f(rows, 2) if use_bn else None
         _norm_gemm(uflat, wflat, rows, dout, cur_d, E._p(ctx.biases[l]), (y_ptr, ldy, 0), hb_flat if last else None,
                    rnorm.data_ptr(), E._p(rowstat), 1)
@@ -336,7 +336,7 @@ def stack_backward(ws, ctx, dz_ptr, lddz, dout_ptr, arg_ptr, ldo, need_dx, dadj)
                        lim_k=lim)
             if dadj is not None:
                 # dA += dU X^T : dU K-major ; B[n=node, k=din] = X stored [node rows, din cols] = K-major
-                tcgemm(dub, KM, xb, KM, N, N, din, B, Cf=(dadj.data_ptr(), N, N * N), beta=1.0)
+                tcgemm(dub, KM, xb, KM, N, N, din, B, Cf=(dadj.data_ptr(), dadj.shape[2], N * dadj.shape[2]), beta=1.0)
         dxn = dx
     return grads, dxn
 
@@ -399,7 +399,8 @@ def pool_backward(ws, dxp, dap, sb, zb, adjb, tb, nb, B, N, K, Fw, ds, acc_ds, d
     on the device (no host sync): the kernels read the flag."""
     nbp, lim = E._p(nb), int(nb is not None)
     dxpb = cvt(ws, dxp.data_ptr(), Fw, B * K, Fw, B=B)
-    dapb = cvt(ws, dap.data_ptr(), K, B * K, K, B=B)
+    ldap = dap.shape[2]                                  # dA' rows may be padded (see _bwd_tc)
+    dapb = cvt(ws, dap.data_ptr(), ldap, B * K, K, B=B)
     dz = ws.f(B, N, Fw)
     tcgemm(sb, KM, dxpb, MN, N, Fw, K, B, Cf=(dz.data_ptr(), Fw, N * Fw), lim=nbp, lim_m=lim)
     dsf = (ds.data_ptr(), K, N * K)
@@ -409,14 +410,14 @@ def pool_backward(ws, dxp, dap, sb, zb, adjb, tb, nb, B, N, K, Fw, ds, acc_ds, d
     dapx = dapb
     if asym is not None:                                 # dA' + dA'^T when symmetric, dA' otherwise
         dapx = bfbuf(ws, B, K, K)
-        call('gp_sym_select_bf16', dap.data_ptr(), B, K, cond, dapx.ptr, dapx.ld, E._stream())
+        call('gp_sym_select_bf16', dap.data_ptr(), C.c_longlong(ldap), B, K, cond, dapx.ptr, dapx.ld, E._stream())
     # dS (+)= Z dX'^T + T^T dA' + A (S dA'^T): three products accumulated in TMEM, one pass over dS
     tcgemm_multi([(zb, KM, dxpb, KM, Fw, 0), (tb, MN, dapx, MN, K, 0), (adjb, KM, wsb, MN, N, lim)], N, K, B,
                  Cf=dsf, beta=1.0 if acc_ds else 0.0, lim=nbp, lim_m=lim, cond=cond, cond_npairs=2)
     if dadj is not None:
         w2b = bfbuf(ws, B, N, K)
         tcgemm(sb, KM, dapb, MN, N, K, K, B, Cb=w2b)
-        tcgemm(w2b, KM, sb, KM, N, N, K, B, Cf=(dadj.data_ptr(), N, N * N), beta=1.0)
+        tcgemm(w2b, KM, sb, KM, N, N, K, B, Cf=(dadj.data_ptr(), dadj.shape[2], N * dadj.shape[2]), beta=1.0)
     return dz
 
 

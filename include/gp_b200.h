@@ -162,9 +162,10 @@ int gp_softmax_mask_bwd_x(const float* s, const float* ds, const int32_t* nb, in
  * zeros without being read (feed contract graph_sampler.py:97-109). */
 int gp_adj_prepare(const void* adj, int adj_dtype, const int32_t* nb, int B, int N, void* adj_bf16, long long ld,
                    int32_t* flags, gp_stream_t stream);
-/* out[b] = bf16((cond && *cond == 0) ? x[b] + x[b]^T : x[b]), x [B,K,K] fp32, out row stride ld (zero padded). */
-int gp_sym_select_bf16(const float* x, int B, int K, const int32_t* cond, void* out_bf16, long long ld,
-                       gp_stream_t stream);
+/* out[b] = bf16((cond && *cond == 0) ? x[b] + x[b]^T : x[b]), x [B,K,K] fp32 with row stride ldx, out row stride
+ * ld (zero padded). */
+int gp_sym_select_bf16(const float* x, long long ldx, int B, int K, const int32_t* cond, void* out_bf16,
+                       long long ld, gp_stream_t stream);
 /* y[r, 0:cols_pad] = bf16(x[r, 0:cols]) zero-padded to cols_pad (row strides ldx / ldy in elements) */
 int gp_cvt_f32_bf16(const float* x, long long ldx, void* y, long long ldy, long long rows, int cols,
                     int cols_pad, gp_stream_t stream);

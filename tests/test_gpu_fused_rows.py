@@ -23,7 +23,10 @@ def dev(a, dt=torch.float32):
 
 
 @pytest.mark.parametrize('B,N,din,dout,off,Fw,relu', [(16, 40, 128, 128, 0, 128, 1), (3, 50, 64, 64, 64, 200, 1),
-                                                       (5, 33, 40, 200, 0, 200, 0), (2, 70, 128, 20, 8, 36, 1)])
+                                                       (5, 33, 40, 200, 0, 200, 0), (2, 70, 128, 20, 8, 36, 1),
+                                                       # rows wider than 256: the single-buffer 512-column variant
+                                                       (4, 70, 128, 512, 0, 512, 0), (3, 50, 96, 320, 64, 392, 1),
+                                                       (2, 140, 128, 500, 256, 756, 0)])
 def test_norm_gemm_and_bn(B, N, din, dout, off, Fw, relu):
     from graph_pooling_b200 import engine as E, engine_tc as T
     from graph_pooling_b200._lib import call
