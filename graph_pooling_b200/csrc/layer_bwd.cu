@@ -189,6 +189,122 @@ __global__ void __launch_bounds__(256) layer_bwd_bn_kernel(const LbArgs a, int C
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// One-CTA-per-node BN variant (no cluster).  Cluster barriers and distributed-shared-memory exchanges cost
+// microseconds (measured: they, not HBM, bound the cluster kernel at 2.5 TB/s).  When a node's whole batch fits
+// ONE 1024-thread CTA (B * d <= 32768 elements at 8 float4 per thread), the two batch means are a plain block
+// reduction: phase 1 loads every gradient source and Y with everything in flight (up to 384 KB per CTA), keeps only
+// g in registers; phase 2 re-reads Y (L2-resident: the CTA just read it) and finishes the rows.
+// ---------------------------------------------------------------------------------------------------------
+template <int VPT>
+__global__ void __launch_bounds__(1024, 1) layer_bwd_bn_cta_kernel(const LbArgs a) {
+  constexpr int T = 1024;
+  __shared__ float red[2][T / 32];
+  __shared__ float tot[2];
+  __shared__ __align__(16) float colacc[T * 4];
+  const int n = blockIdx.x;
+  const int d4 = a.d >> 2;
+  const int lg4 = 31 - __clz(d4);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c = (tid & (d4 - 1)) * 4;
+  const int rstep = T >> lg4;
+  const int r0 = tid >> lg4;
+  const float mu = a.mean[n], is = a.invstd[n];
+  auto hhat4 = [&](const float4 y) -> float4 {
+    return make_float4(((a.relu ? fmaxf(y.x, 0.f) : y.x) - mu) * is, ((a.relu ? fmaxf(y.y, 0.f) : y.y) - mu) * is,
+                       ((a.relu ? fmaxf(y.z, 0.f) : y.z) - mu) * is, ((a.relu ? fmaxf(y.w, 0.f) : y.w) - mu) * is);
+  };
+  float4 g[VPT];
+  float s1 = 0.f, s2 = 0.f;
+  {
+    float4 yv[VPT];
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {                      // ---- all loads in flight ----
+      const int b = r0 + j * rstep;
+      g[j] = yv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (b < a.B) {
+        const long long row = (long long)b * a.N + n;
+        g[j] = load_g(a, b, n, row, c);
+        yv[j] = ld4(a.y + row * a.ldy + c);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      const float4 hj = hhat4(yv[j]);                    // rows beyond B have g == 0: they add nothing
+      s1 += (g[j].x + g[j].y) + (g[j].z + g[j].w);
+      s2 = fmaf(g[j].x, hj.x, s2); s2 = fmaf(g[j].y, hj.y, s2);
+      s2 = fmaf(g[j].z, hj.z, s2); s2 = fmaf(g[j].w, hj.w, s2);
+    }
+  }
+  // phase 2 operands: issue the Y / rnorm re-reads before the reduction so their latency overlaps it
+  float4 y2[VPT];
+  float rn[VPT];
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) {
+    const int b = r0 + j * rstep;
+    y2[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    rn[j] = 1.f;
+    if (b < a.B) {
+      const long long row = (long long)b * a.N + n;
+      y2[j] = ld4(a.y + row * a.ldy + c);
+      if (a.normalize) rn[j] = a.rnorm[row];
+    }
+  }
+  s1 = warp_sum(s1); s2 = warp_sum(s2);
+  if (lane == 0) { red[0][warp] = s1; red[1][warp] = s2; }
+  __syncthreads();
+  if (warp == 0) {
+    float t1 = red[0][lane], t2 = red[1][lane];          // T / 32 == 32 partials
+    t1 = warp_sum(t1); t2 = warp_sum(t2);
+    if (lane == 0) { tot[0] = t1; tot[1] = t2; }
+  }
+  __syncthreads();
+  const float inv_cnt = 1.f / ((float)a.B * (float)a.d);
+  const float m1 = tot[0] * inv_cnt, m2 = tot[1] * inv_cnt;
+  float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) {
+    const int b = r0 + j * rstep;
+    const float4 y = y2[j];
+    const float4 hj = hhat4(y);
+    float4 v;
+    v.x = (g[j].x - m1 - hj.x * m2) * is; v.y = (g[j].y - m1 - hj.y * m2) * is;
+    v.z = (g[j].z - m1 - hj.z * m2) * is; v.w = (g[j].w - m1 - hj.w * m2) * is;
+    if (a.relu) {
+      if (!(y.x > 0.f)) v.x = 0.f;
+      if (!(y.y > 0.f)) v.y = 0.f;
+      if (!(y.z > 0.f)) v.z = 0.f;
+      if (!(y.w > 0.f)) v.w = 0.f;
+    }
+    if (a.normalize) {
+      float dot = fmaf(v.x, y.x, fmaf(v.y, y.y, fmaf(v.z, y.z, v.w * y.w)));
+      for (int o = d4 >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      const float r = rn[j];
+      if (!(r > kEpsNormB)) {
+        v.x /= kEpsNormB; v.y /= kEpsNormB; v.z /= kEpsNormB; v.w /= kEpsNormB;
+      } else {
+        const float ir = 1.f / r;
+        v.x = (v.x - y.x * dot) * ir; v.y = (v.y - y.y * dot) * ir;
+        v.z = (v.z - y.z * dot) * ir; v.w = (v.w - y.w * dot) * ir;
+      }
+    }
+    if (b < a.B) {
+      store_dv(a, (long long)b * a.N + n, c, v);
+      cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
+    }
+  }
+  if (a.part != nullptr) {                               // deterministic per-CTA column sums
+    *reinterpret_cast<float4*>(&colacc[tid * 4]) = cs;
+    __syncthreads();
+    if (tid < a.d) {
+      const int q = tid >> 2, e = tid & 3;
+      float t = 0.f;
+      for (int r = q; r < T; r += d4) t += colacc[r * 4 + e];
+      a.part[(long long)blockIdx.x * a.d + tid] = t;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Pipelined BN variant: PERSISTENT clusters.  The one-node-per-cluster kernel above spends most of a CTA's life
 // outside its load phase (cluster syncs, reduction, launch of the next cluster), so HBM idles: measured 2.5 TB/s.
 // Here a cluster of CS CTAs walks nodes n = cluster, cluster + G, ...; the rows of node i+1 stream into the other
@@ -523,6 +639,24 @@ int layer_bwd_fast(const gp_layer_bwd* q, cudaStream_t st, bool* handled) {
   a.dv = q->dv; a.dvb = reinterpret_cast<__nv_bfloat16*>(q->dv_bf16); a.lddvb = q->lddvb;
   a.part = q->db != nullptr ? q->ws : nullptr;
   long long part_rows = 0;
+  static int use_cta = -1;
+  if (use_cta < 0) { const char* e = getenv("GP_LBWD_CTA"); use_cta = (e == nullptr || atoi(e) != 0) ? 1 : 0; }
+  if (q->bn && use_cta && q->h == nullptr && q->mean != nullptr) {
+    const int d4 = d / 4;
+    const int rstep = 1024 / d4;
+    const int vpt = (q->B + rstep - 1) / rstep;
+    if (vpt <= 8) {
+      if (vpt <= 2) layer_bwd_bn_cta_kernel<2><<<q->N, 1024, 0, st>>>(a);
+      else if (vpt <= 4) layer_bwd_bn_cta_kernel<4><<<q->N, 1024, 0, st>>>(a);
+      else layer_bwd_bn_cta_kernel<8><<<q->N, 1024, 0, st>>>(a);
+      GP_LAUNCHED();
+      part_rows = q->N;
+      if (q->db != nullptr)
+        GP_TRY(colsum(q->ws, part_rows, d, d, q->db, 0, q->ws + part_rows * d, st));
+      *handled = true;
+      return GP_OK;
+    }
+  }
   static int use_pipe = -1;
   // opt-in (GP_LBWD_PIPE=1): measured r1 on B=256, N=2048, d=128: 0.371 ms (2 stages, 512 threads) vs 0.380 ms for
   // the one-node-per-cluster kernel -- both ~2.5 TB/s; the per-node cluster sync + reduction chain bounds them,
