@@ -452,7 +452,9 @@ def main():
 
     out = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
            'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
-           'vs_baseline': None, 'dtype': prec, 'data': 'synthetic',
+           'vs_baseline': None, 'dtype': prec,
+           'data': 'real: bundled ENZYMES graphs (tests/golden/dataset_enzymes.npz, made through the reference loader)'
+           if cfg.get('fixture') else 'synthetic',
            'config': {'workload': args.workload, 'precision': prec, 'graphs_per_gpu_per_step': B, 'nodes': cfg['N'],
                       'hidden': cfg['H'], 'assign_ratio': cfg['ratio'], 'num_pooling': cfg['P'],
                       'step': 'zero_grad+forward+loss(CE+linkpred)+backward+clip_grad_norm+Adam (train.py:196-210)',

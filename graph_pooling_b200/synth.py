@@ -23,6 +23,10 @@ WORKLOADS = {
     # configs[4]: ragged batch, n_b ~ U{50..5000}
     'cfg5_ragged_64x5000': dict(kind='soft', B=64, N=5000, D=128, H=128, E=128, C=2, L=3, ratio=0.25, P=1,
                                 n_min=50, n_max=5000, mean_degree=8.0),
+    # configs[0] on the REAL bundled ENZYMES graphs (tests/golden/dataset_enzymes.npz, produced through the reference's
+    # own loader): batches of real graphs assembled on the device by data.GraphSet
+    'cfg1_enzymes_real': dict(kind='soft', B=20, N=100, D=3, H=30, E=30, C=6, L=3, ratio=0.1, P=1,
+                              n_min=2, n_max=100, fixture='dataset_enzymes.npz'),
     # small smoke-sized DiffPool
     'tiny': dict(kind='soft', B=8, N=64, D=8, H=16, E=16, C=3, L=3, ratio=0.25, P=1, n_min=4, n_max=64,
                  density=0.1),
@@ -49,6 +53,16 @@ def make_batch(name, seed=0, device='cuda', B=None):
         cfg['B'] = B
     B, N, D, C = cfg['B'], cfg['N'], cfg['D'], cfg['C']
     rs = np.random.RandomState(seed)
+    if cfg.get('fixture'):
+        import os
+        from .data import GraphSet
+        z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden',
+                                 cfg['fixture']))
+        gs = GraphSet(z['n'], z['glabel'].astype(np.int64) - int(z['glabel'].min()), z['nlabel'], z['eptr'],
+                      z['edges'], int(z['num_node_labels'])).to(device)
+        idx = rs.choice(len(gs), size=B, replace=B > len(gs))
+        x, adj, nbd, label = gs.batch(idx, N, adj_dtype=torch.float32)
+        return dict(x=x.contiguous(), adj=adj, nb=nbd.cpu().numpy().astype(np.int32), label=label, cfg=cfg)
     nb = node_counts(cfg, B, rs)
     g = torch.Generator(device=device).manual_seed(seed)
     nbt = torch.as_tensor(nb.astype(np.int64), device=device)
