@@ -443,7 +443,7 @@ def main():
 
     # ---- CPU baseline (oracle port) on this box's host cores -----------------------------------
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:       # rank 0 at N = 1 only (other ranks would contend for the cores)
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
         sample = args.cpu_sample or default_cpu_sample(cfg)
