@@ -81,6 +81,7 @@ _PROTOS = {
     'gp_graphconv_fwd': [c_f, c_ll, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_ll, c_f, c_i, c_f],
     'gp_graphconv_bwd': [c_f, c_f, c_f, c_ll, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_f, c_f,
                          c_i, c_f],
+    'gp_graphconv_bwd_ws': [c_i, c_i, c_i, c_i, c_i],
     'gp_relu_bn_fwd': [c_f, c_f, c_ll, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f],
     'gp_relu_bn_fwd_ws': [c_i, c_i, c_i],
     'gp_relu_bn_fwd_x': [c_f, c_f, c_ll, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f, c_f],
@@ -117,7 +118,7 @@ _PROTOS = {
     'gp_fill_f32': [c_f, c_ll, C.c_float, c_f],
     'gp_axpy_f32': [c_f, c_f, c_ll, C.c_float, c_f],
 }
-_RESTYPES = {'gp_last_error': C.c_char_p, 'gp_launch_count': c_ll, 'gp_gcn_layer_bwd_ws': c_ll, 'gp_gcn_layer_bwd_ws_x': c_ll, 'gp_relu_bn_fwd_ws': c_ll, 'gp_launch_count_reset': None}
+_RESTYPES = {'gp_last_error': C.c_char_p, 'gp_launch_count': c_ll, 'gp_gcn_layer_bwd_ws': c_ll, 'gp_gcn_layer_bwd_ws_x': c_ll, 'gp_relu_bn_fwd_ws': c_ll, 'gp_graphconv_bwd_ws': c_ll, 'gp_launch_count_reset': None}
 
 EXPORTS = tuple(_PROTOS)
 _lib = None

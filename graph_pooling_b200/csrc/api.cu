@@ -13,6 +13,14 @@ int bias_normalize(float* v, const float* bias, float* rnorm, long long rows, in
 int colsum(const float* x, long long rows, int d, long long ld, float* out, int accumulate, float* ws,
            cudaStream_t st);
 
+bool small_gcn_eligible(int B, int N, int din, int dout, int add_self);
+int small_gcn_fwd(const float* x, long long ldx, const float* adj, const float* w, const float* bias, const int32_t* nb,
+                  int B, int N, int din, int dout, int normalize, float* u, float* y, long long ldy, float* rnorm,
+                  cudaStream_t st);
+int small_gcn_bwd(const float* dv, const float* u, const float* x, long long ldx, const float* adj, const float* w,
+                  const int32_t* nb, int B, int N, int din, int dout, float* dw, float* db, float* dx, float* dadj,
+                  float* ws, cudaStream_t st);
+
 static gp_gemm mk(const float* A, const float* B, float* C, int M, int N, int K, int batch) {
   gp_gemm g;
   g.A = A; g.B = B; g.C = C; g.M = M; g.N = N; g.K = K; g.batch = batch;
@@ -49,6 +57,9 @@ extern "C" int gp_graphconv_fwd(const float* x, long long ldx, const float* adj,
   GP_REQUIRE(!normalize || rnorm, "graphconv_fwd: normalize needs rnorm");
   cudaStream_t st = S(stream);
   (void)precision;
+  // ENZYMES-sized graphs: one CTA per graph runs the whole layer out of shared memory (small_gcn.cu)
+  if (small_gcn_eligible(B, N, din, dout, add_self))
+    return small_gcn_fwd(x, ldx, adj, w, bias, nb, B, N, din, dout, normalize, u, y, ldy, rnorm, st);
   // U = A.X (+X)
   if (add_self)
     GP_CUDA(cudaMemcpy2DAsync(u, (size_t)din * 4, x, (size_t)ldx * 4, (size_t)din * 4, (size_t)B * N,
@@ -80,6 +91,10 @@ extern "C" int gp_graphconv_bwd(const float* dv, const float* u, const float* x,
   GP_REQUIRE(!dadj || x, "graphconv_bwd: dadj needs x");
   cudaStream_t st = S(stream);
   (void)precision;
+  if (small_gcn_eligible(B, N, din, dout, add_self)) {       // ws: gp_graphconv_bwd_ws floats
+    GP_REQUIRE(ws && x && adj, "graphconv_bwd: the per-graph fused path needs ws, x and adj");
+    return small_gcn_bwd(dv, u, x, ldx, adj, w, nb, B, N, din, dout, dw, db, dx, dadj, ws, st);
+  }
   const long long rows = (long long)B * N;
   if (db != nullptr) {
     GP_REQUIRE(ws, "graphconv_bwd: db needs ws");

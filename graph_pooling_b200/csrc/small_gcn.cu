@@ -1,0 +1,360 @@
+// Per-graph fused GraphConv for SMALL graphs (ENZYMES-sized: N <= 128, feature widths <= 128), fp32.
+//
+// At these sizes a whole graph's working set -- the real n_b x n_b adjacency block, X, U, W -- fits in one SM's
+// shared memory, and the generic path (three or more launches per layer, each a latency-bound chain of
+// global -> shared round trips over a handful of CTAs) is bound by launch and memory latency, not by FLOPs or
+// bandwidth.  Here ONE CTA per graph stages its operands once and runs the whole layer:
+//   forward   U = A.X ;  V = U.W + b ;  Y = V / max(||V||_2, 1e-12)            (encoders.py:315-328)
+//   backward  dU = dV.W^T ;  dX = A^T.dU ;  dA += dU.X^T ;  per-graph partials of dW = U^T.dV and db = colsum(dV)
+//             (reduced over the batch by the deterministic column-sum kernels)
+// Only the real n_b rows / columns are staged and multiplied (padding-aware); pad rows get their analytic values
+// (U = 0, Y = normalize(b)).  The in-shared-memory products use 4 x 4 register tiles.
+#include "common.cuh"
+
+namespace gp {
+
+constexpr float kEpsNormS = 1e-12f;
+constexpr int kSmallMaxSmem = 200 * 1024;
+
+int colsum(const float* x, long long rows, int d, long long ld, float* out, int accumulate, float* ws, cudaStream_t st);
+
+__host__ __device__ inline int r4i(int v) { return (v + 3) & ~3; }
+
+// C[M x Nc] (+)= A[M x K] . B[K x Nc], all in shared memory, row-major with leading dimensions lda / ldb / ldc
+// (ldb, ldc multiples of 4; A zero-filled up to r4(M) rows, B zero-filled up to r4(Nc) columns).
+__device__ __forceinline__ void smem_gemm(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int ldb,
+                                          int M, int Nc, int K, float* __restrict__ C, int ldc, const float* bias) {
+  const int ntn = (Nc + 3) >> 2, ntm = (M + 3) >> 2;
+  for (int t = threadIdx.x; t < ntm * ntn; t += blockDim.x) {
+    const int tm = t / ntn, tn = t - tm * ntn;
+    const int i0 = tm * 4, c0 = tn * 4;
+    float acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[r][e] = 0.f;
+    const float* a0 = A + i0 * lda;
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+      const float4 b4 = *reinterpret_cast<const float4*>(Bm + k * ldb + c0);
+      const float av[4] = {a0[k], a0[lda + k], a0[2 * lda + k], a0[3 * lda + k]};
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        acc[r][0] = fmaf(av[r], b4.x, acc[r][0]); acc[r][1] = fmaf(av[r], b4.y, acc[r][1]);
+        acc[r][2] = fmaf(av[r], b4.z, acc[r][2]); acc[r][3] = fmaf(av[r], b4.w, acc[r][3]);
+      }
+    }
+    float bs[4] = {0.f, 0.f, 0.f, 0.f};
+    if (bias != nullptr) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) bs[e] = c0 + e < Nc ? bias[c0 + e] : 0.f;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      *reinterpret_cast<float4*>(C + (i0 + r) * ldc + c0) =
+          make_float4(acc[r][0] + bs[0], acc[r][1] + bs[1], acc[r][2] + bs[2], acc[r][3] + bs[3]);
+  }
+}
+
+struct SmallFwd {
+  const float* x; long long ldx; const float* adj; const float* w; const float* bias; const int32_t* nb;
+  int B, N, din, dout, normalize;
+  float* u; float* y; long long ldy; float* rnorm;
+};
+
+// shared-memory floats of the forward kernel for max node count N
+__host__ __device__ inline size_t small_fwd_floats(int N, int din, int dout) {
+  const int n4 = r4i(N), dp = r4i(din), op = r4i(dout);
+  const int wide = dp > op ? dp : op;
+  return (size_t)n4 * (N + 1) + (size_t)n4 * wide + (size_t)n4 * dp + (size_t)din * op + op;
+}
+
+__global__ void __launch_bounds__(256) gconv_small_fwd_kernel(const SmallFwd p) {
+  extern __shared__ __align__(16) float sm[];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = p.N, din = p.din, dout = p.dout;
+  const int n = p.nb != nullptr ? min(max(p.nb[b], 0), N) : N;
+  const int n4 = r4i(n), dp = r4i(din), op = r4i(dout), lda = N + 1;
+  const int wide = dp > op ? dp : op;
+  float* As = sm;                                        // [r4(N)][N+1]   real block, rows zero-filled to n4
+  float* XV = As + (size_t)r4i(N) * lda;                 // [r4(N)][wide]  X (phase 1), then V (phase 2)
+  float* Us = XV + (size_t)r4i(N) * wide;                // [r4(N)][dp]
+  float* Ws = Us + (size_t)r4i(N) * dp;                  // [din][op]
+  float* bs = Ws + (size_t)din * op;                     // [op]
+  const float* ab = p.adj + (long long)b * N * N;
+  const float* xb = p.x + (long long)b * N * p.ldx;
+  // ---- stage A (real block), X (real rows), W, bias ----
+  for (int e = tid; e < n4 * n; e += 256) {
+    const int i = e / n, j = e - i * n;
+    As[i * lda + j] = i < n ? ab[(long long)i * N + j] : 0.f;
+  }
+  for (int e = tid; e < n * dp; e += 256) {
+    const int j = e / dp, c = e - j * dp;
+    XV[j * wide + c] = c < din ? xb[(long long)j * p.ldx + c] : 0.f;
+  }
+  for (int e = tid; e < din * op; e += 256) {
+    const int k = e / op, c = e - k * op;
+    Ws[k * op + c] = c < dout ? p.w[(long long)k * dout + c] : 0.f;
+  }
+  for (int c = tid; c < op; c += 256) bs[c] = (p.bias != nullptr && c < dout) ? p.bias[c] : 0.f;
+  __syncthreads();
+  // ---- U = A.X (rows < n), kept in shared memory and written out; pad rows of u are zero ----
+  smem_gemm(As, lda, XV, wide, n, din, n, Us, dp, nullptr);
+  __syncthreads();
+  float* ub = p.u + (long long)b * N * din;
+  for (int e = tid; e < N * din; e += 256) {
+    const int i = e / din, c = e - i * din;
+    ub[e] = i < n ? Us[i * dp + c] : 0.f;
+  }
+  // ---- V = U.W + b (rows < n) into XV ----
+  smem_gemm(Us, dp, Ws, op, n, dout, din, XV, wide, bs);
+  __syncthreads();
+  // ---- Y = V / max(||V||, eps); pad rows carry V = b; one warp per row ----
+  float* yb = p.y + (long long)b * N * p.ldy;
+  for (int i = warp; i < N; i += 8) {
+    const float* v = i < n ? XV + i * wide : bs;
+    float ss = 0.f;
+    for (int c = lane; c < dout; c += 32) ss = fmaf(v[c], v[c], ss);
+    ss = warp_sum(ss);
+    float r = 1.f;
+    if (p.normalize) {
+      r = fmaxf(sqrtf(ss), kEpsNormS);
+      if (lane == 0) p.rnorm[(long long)b * N + i] = r;
+    }
+    const float inv = 1.f / r;
+    for (int c = lane; c < dout; c += 32) yb[(long long)i * p.ldy + c] = p.normalize ? v[c] * inv : v[c];
+  }
+}
+
+struct SmallBwd {
+  const float* dv; const float* u; const float* x; long long ldx; const float* adj; const float* w;
+  const int32_t* nb; int B, N, din, dout;
+  float* part;            // [B][din*dout + dout]: per-graph dW and db partials
+  float* dx;              // [B,N,din] or NULL
+  float* dadj;            // [B,N,N] (+=) or NULL
+};
+
+__host__ __device__ inline size_t small_bwd_floats(int N, int din, int dout, int need_dx, int need_da) {
+  const int n4 = r4i(N), dp = r4i(din), op = r4i(dout);
+  size_t f = (size_t)n4 * op            // dVs   [n4][op]
+             + (size_t)r4i(din) * r4i(N) // Ut    [dp][r4(N)]   (U transposed: dW = U^T dV)
+             + op;                       // column sums
+  if (need_dx || need_da) f += (size_t)dout * dp + (size_t)n4 * dp;          // Wt [dout][dp], dUs [n4][dp]
+  if (need_dx) f += (size_t)n4 * (N + 4);                                    // At [n4][r4(N)+..] (A transposed)
+  if (need_da) f += (size_t)din * r4i(N);                                    // Xt [din][r4(N)]
+  return f;
+}
+
+__global__ void __launch_bounds__(256) gconv_small_bwd_kernel(const SmallBwd p, int need_dx, int need_da) {
+  extern __shared__ __align__(16) float sm[];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int N = p.N, din = p.din, dout = p.dout;
+  const int n = p.nb != nullptr ? min(max(p.nb[b], 0), N) : N;
+  const int n4 = r4i(n), N4 = r4i(N), dp = r4i(din), op = r4i(dout);
+  float* dVs = sm;                                       // [r4(N)][op]   rows < n (zero-filled to n4)
+  float* Ut = dVs + (size_t)N4 * op;                     // [dp][N4]      Ut[c][i] = U[i][c]
+  float* cs = Ut + (size_t)dp * N4;                      // [op]
+  float* Wt = cs + op;                                   // [dout][dp]    Wt[o][c] = W[c][o]
+  float* dUs = Wt + ((need_dx || need_da) ? (size_t)dout * dp : 0);           // [N4][dp]
+  float* At = dUs + ((need_dx || need_da) ? (size_t)N4 * dp : 0);             // [N4][N+4]  At[j][i] = A[i][j]
+  float* Xt = At + (need_dx ? (size_t)N4 * (N + 4) : 0);                      // [din][N4]  Xt[c][j] = X[j][c]
+  const int ldat = N + 4;
+  const float* dvb = p.dv + (long long)b * N * dout;
+  const float* ub = p.u + (long long)b * N * din;
+  // ---- db partial: column sums of dV over ALL N rows (pad rows carry gradient through the BatchNorm) ----
+  for (int c = tid; c < op; c += 256) cs[c] = 0.f;
+  for (int e = tid; e < n4 * op; e += 256) {
+    const int i = e / op, c = e - i * op;
+    dVs[e] = (i < n && c < dout) ? dvb[(long long)i * dout + c] : 0.f;
+  }
+  for (int e = tid; e < dp * N4; e += 256) {
+    const int c = e / N4, i = e - c * N4;
+    Ut[e] = (c < din && i < n) ? ub[(long long)i * din + c] : 0.f;
+  }
+  if (need_dx || need_da) {
+    for (int e = tid; e < dout * dp; e += 256) {
+      const int o = e / dp, c = e - o * dp;
+      Wt[e] = c < din ? p.w[(long long)c * dout + o] : 0.f;
+    }
+  }
+  if (need_dx) {
+    const float* ab = p.adj + (long long)b * N * N;
+    for (int e = tid; e < n4 * n; e += 256) {            // coalesced read of row i, transposed store
+      const int i = e % n, j = e / n;                    // j: output row (column of A)
+      At[j * ldat + i] = j < n ? ab[(long long)i * N + j] : 0.f;
+    }
+    // NOTE: the read above walks a column of A (stride N) -- n <= 128, the block is L1/L2 resident
+  }
+  if (need_da) {
+    const float* xb = p.x + (long long)b * N * p.ldx;
+    for (int e = tid; e < din * N4; e += 256) {
+      const int c = e / N4, j = e - c * N4;
+      Xt[e] = j < n ? xb[(long long)j * p.ldx + c] : 0.f;
+    }
+  }
+  __syncthreads();
+  float* part = p.part + (long long)b * ((long long)din * dout + dout);
+  {   // db: one thread per column over all N rows (coalesced across the warp)
+    for (int c = tid; c < dout; c += 256) {
+      float s = 0.f;
+      for (int i = 0; i < N; ++i) s += dvb[(long long)i * dout + c];
+      part[(long long)din * dout + c] = s;
+    }
+  }
+  // ---- dW partial = U^T dV : [din x dout] = Ut [dp x n] . dVs [n x op]; tiles written straight to global ----
+  {
+    const int ntn = op >> 2, ntm = dp >> 2;
+    for (int t = tid; t < ntm * ntn; t += 256) {
+      const int tm = t / ntn, tn = t - tm * ntn, i0 = tm * 4, c0 = tn * 4;
+      float acc[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[r][e] = 0.f;
+      for (int k = 0; k < n; ++k) {
+        const float4 b4 = *reinterpret_cast<const float4*>(dVs + k * op + c0);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float a = Ut[(i0 + r) * N4 + k];
+          acc[r][0] = fmaf(a, b4.x, acc[r][0]); acc[r][1] = fmaf(a, b4.y, acc[r][1]);
+          acc[r][2] = fmaf(a, b4.z, acc[r][2]); acc[r][3] = fmaf(a, b4.w, acc[r][3]);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (i0 + r < din && c0 + e < dout) part[(long long)(i0 + r) * dout + c0 + e] = acc[r][e];
+    }
+  }
+  if (!need_dx && !need_da) return;
+  // ---- dU = dV.W^T (rows < n) ----
+  smem_gemm(dVs, op, Wt, dp, n, din, dout, dUs, dp, nullptr);
+  __syncthreads();
+  if (need_dx) {          // dX = A^T.dU : rows j < n ; pad rows of dx are zero (A's pad columns are zero)
+    float* dxb = p.dx + (long long)b * N * din;
+    const int ntn = dp >> 2, ntm = n4 >> 2;
+    for (int t = tid; t < ntm * ntn; t += 256) {
+      const int tm = t / ntn, tn = t - tm * ntn, j0 = tm * 4, c0 = tn * 4;
+      float acc[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[r][e] = 0.f;
+      for (int i = 0; i < n; ++i) {
+        const float4 b4 = *reinterpret_cast<const float4*>(dUs + i * dp + c0);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float a = At[(j0 + r) * ldat + i];
+          acc[r][0] = fmaf(a, b4.x, acc[r][0]); acc[r][1] = fmaf(a, b4.y, acc[r][1]);
+          acc[r][2] = fmaf(a, b4.z, acc[r][2]); acc[r][3] = fmaf(a, b4.w, acc[r][3]);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (j0 + r < n && c0 + e < din) dxb[(long long)(j0 + r) * din + c0 + e] = acc[r][e];
+    }
+    for (int e = tid + n * din; e < N * din; e += 256) dxb[e] = 0.f;
+  }
+  if (need_da) {          // dA += dU.X^T : [n x n] += dUs [n x din] . Xt [din x n]
+    float* dab = p.dadj + (long long)b * N * N;
+    const int ntn = N4 >> 2, ntm = n4 >> 2;
+    for (int t = tid; t < ntm * ntn; t += 256) {
+      const int tm = t / ntn, tn = t - tm * ntn, i0 = tm * 4, j0 = tn * 4;
+      if (j0 >= n) continue;
+      float acc[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[r][e] = 0.f;
+      for (int c = 0; c < din; ++c) {
+        const float4 b4 = *reinterpret_cast<const float4*>(Xt + c * N4 + j0);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float a = dUs[(i0 + r) * dp + c];
+          acc[r][0] = fmaf(a, b4.x, acc[r][0]); acc[r][1] = fmaf(a, b4.y, acc[r][1]);
+          acc[r][2] = fmaf(a, b4.z, acc[r][2]); acc[r][3] = fmaf(a, b4.w, acc[r][3]);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (i0 + r < n && j0 + e < n) dab[(long long)(i0 + r) * N + j0 + e] += acc[r][e];
+    }
+  }
+}
+
+static bool small_enabled() {
+  static int en = -1;
+  if (en < 0) { const char* e = getenv("GP_NO_SMALL_GCN"); en = (e != nullptr && atoi(e) != 0) ? 0 : 1; }
+  return en != 0;
+}
+
+// true if the fused per-graph kernels take this shape (forward and backward must agree)
+bool small_gcn_eligible(int B, int N, int din, int dout, int add_self) {
+  if (!small_enabled() || add_self || N > 128 || din > 128 || dout > 128 || B > 65535) return false;
+  if (small_fwd_floats(N, din, dout) * 4 > (size_t)kSmallMaxSmem) return false;
+  if (small_bwd_floats(N, din, dout, 1, 1) * 4 > (size_t)kSmallMaxSmem) return false;
+  return true;
+}
+
+int small_gcn_fwd(const float* x, long long ldx, const float* adj, const float* w, const float* bias, const int32_t* nb,
+                  int B, int N, int din, int dout, int normalize, float* u, float* y, long long ldy, float* rnorm,
+                  cudaStream_t st) {
+  static bool cfgd = false;
+  if (!cfgd) {
+    GP_CUDA(cudaFuncSetAttribute(gconv_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallMaxSmem));
+    GP_CUDA(cudaFuncSetAttribute(gconv_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallMaxSmem));
+    cfgd = true;
+  }
+  SmallFwd p;
+  p.x = x; p.ldx = ldx; p.adj = adj; p.w = w; p.bias = bias; p.nb = nb;
+  p.B = B; p.N = N; p.din = din; p.dout = dout; p.normalize = normalize;
+  p.u = u; p.y = y; p.ldy = ldy; p.rnorm = rnorm;
+  gconv_small_fwd_kernel<<<B, 256, small_fwd_floats(N, din, dout) * 4, st>>>(p);
+  GP_LAUNCHED();
+  return GP_OK;
+}
+
+// ws: B * (din*dout + dout) partial floats followed by the column-sum scratch (256 * (din*dout + dout) floats)
+long long small_gcn_bwd_ws(int B, int din, int dout) {
+  const long long w = (long long)din * dout + dout;
+  return (long long)B * w + 256 * w;
+}
+
+int small_gcn_bwd(const float* dv, const float* u, const float* x, long long ldx, const float* adj, const float* w,
+                  const int32_t* nb, int B, int N, int din, int dout, float* dw, float* db, float* dx, float* dadj,
+                  float* ws, cudaStream_t st) {
+  static bool cfgd = false;
+  if (!cfgd) {
+    GP_CUDA(cudaFuncSetAttribute(gconv_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallMaxSmem));
+    GP_CUDA(cudaFuncSetAttribute(gconv_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallMaxSmem));
+    cfgd = true;
+  }
+  SmallBwd p;
+  p.dv = dv; p.u = u; p.x = x; p.ldx = ldx; p.adj = adj; p.w = w; p.nb = nb;
+  p.B = B; p.N = N; p.din = din; p.dout = dout; p.part = ws; p.dx = dx; p.dadj = dadj;
+  const int need_dx = dx != nullptr, need_da = dadj != nullptr;
+  gconv_small_bwd_kernel<<<B, 256, small_bwd_floats(N, din, dout, need_dx, need_da) * 4, st>>>(p, need_dx, need_da);
+  GP_LAUNCHED();
+  const int wdt = din * dout + dout;
+  float* tmp = ws + (long long)B * wdt;
+  // reduce the per-graph partials over the batch (two-stage, deterministic); dW and db are contiguous slices
+  GP_TRY(colsum(ws, B, din * dout, wdt, dw, 0, tmp, st));
+  if (db != nullptr) GP_TRY(colsum(ws + (long long)din * dout, B, dout, wdt, db, 0, tmp, st));
+  return GP_OK;
+}
+
+}  // namespace gp
+
+extern "C" long long gp_graphconv_bwd_ws(int B, int N, int din, int dout, int add_self) {
+  long long f = 256LL * dout;                                        // column sums of the generic path
+  if (gp::small_gcn_eligible(B, N, din, dout, add_self)) {
+    const long long s = gp::small_gcn_bwd_ws(B, din, dout);
+    if (s > f) f = s;
+  }
+  return f;
+}

@@ -521,7 +521,7 @@ class _GraphConvFn(torch.autograd.Function):
         du = ws.f(B, N, din) if (need_dx or need_da) else None
         dx = ws.f(B, N, din) if need_dx else None
         da = ws.z(B, N, N) if need_da else None
-        cs = ws.f(256 * dout)
+        cs = ws.f(int(T.load().gp_graphconv_bwd_ws(B, N, din, dout, int(add_self))))
         call('gp_graphconv_bwd', dv.data_ptr(), u.data_ptr(), x.data_ptr(), din, adj.data_ptr(), w.data_ptr(), None,
              B, N, din, dout, int(add_self), dw.data_ptr(), E._p(db), E._p(du), E._p(dx), E._p(da), cs.data_ptr(),
              E.F32, E._stream())

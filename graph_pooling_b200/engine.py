@@ -137,7 +137,6 @@ def stack_backward(ws, ctx, dz_ptr, lddz, dout_ptr, arg_ptr, ldo, need_dx, dadj,
     grads = [None] * L
     dxn = None
     zp = ctx.zcat.data_ptr()
-    cs = ws.f(256 * max(ctx.douts))
     for l in reversed(range(L)):
         x_ptr, ldx, din, dout, off, u, y, rnorm, mean, invstd = ctx.layers[l]
         last = l == L - 1
@@ -164,6 +163,7 @@ def stack_backward(ws, ctx, dz_ptr, lddz, dout_ptr, arg_ptr, ldo, need_dx, dadj,
         db = ws.f(dout) if ctx.biases[l] is not None else None
         du = ws.f(B, N, din) if (need_dx_l or dadj is not None) else None
         dx = ws.f(B, N, din) if need_dx_l else None
+        cs = ws.f(int(_lib.load().gp_graphconv_bwd_ws(B, N, din, dout, int(ctx.add_self))))
         call('gp_graphconv_bwd', _p(dv), _p(u), x_ptr, ldx, _p(ctx.adj), _p(w), _p(ctx.nb), B, N, din, dout,
              int(ctx.add_self), _p(dw), _p(db), _p(du), _p(dx), _p(dadj), _p(cs), prec, st)
         grads[l] = (dw, db)

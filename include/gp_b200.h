@@ -181,7 +181,11 @@ int gp_graphconv_fwd(const float* x, long long ldx, const float* adj, const floa
 
 /* backward of GraphConv given dV (gradient w.r.t. the pre-normalisation V, see gp_gcn_layer_bwd):
  *   dW = sum_b U^T dV ; db = colsum dV ; dU = dV W^T ; dX = A^T dU (+dU) ; dA += dU X^T
- *   dx / dadj may be NULL (not needed).  du: workspace [B,N,din].  ws: >= 256*dout floats. */
+ *   dx / dadj may be NULL (not needed).  du: workspace [B,N,din].  ws: gp_graphconv_bwd_ws(...) floats.
+ * ENZYMES-sized shapes (N, din, dout <= 128, add_self == 0, operands fitting one SM's shared memory) run as ONE
+ * CTA per graph that stages the real n_b x n_b adjacency block, X, U, W once and computes the whole layer
+ * (forward) / all four gradient products (backward; per-graph dW / db partials reduced deterministically). */
+long long gp_graphconv_bwd_ws(int B, int N, int din, int dout, int add_self);
 int gp_graphconv_bwd(const float* dv, const float* u, const float* x, long long ldx, const float* adj,
                      const float* w, const int32_t* nb, int B, int N, int din, int dout, int add_self,
                      float* dw, float* db, float* du, float* dx, float* dadj, float* ws,
