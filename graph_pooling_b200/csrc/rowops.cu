@@ -520,9 +520,24 @@ int bias_normalize(float* v, const float* bias, float* rnorm, long long rows, in
   return GP_OK;
 }
 
+// few rows (per-graph partials of an ENZYMES-sized batch, ...): one pass, a thread per column
+__global__ void colsum_small_kernel(const float* __restrict__ x, int rows, int d, long long ld, float* __restrict__ out,
+                                    int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  float s = 0.f;
+  for (int r = 0; r < rows; ++r) s += x[(long long)r * ld + c];
+  out[c] = accumulate ? out[c] + s : s;
+}
+
 int colsum(const float* x, long long rows, int d, long long ld, float* out, int accumulate, float* ws,
            cudaStream_t st) {
   GP_REQUIRE(x && out && ws && d > 0, "colsum: bad args");
+  if (rows <= 64) {
+    colsum_small_kernel<<<(d + 127) / 128, 128, 0, st>>>(x, (int)rows, d, ld, out, accumulate);
+    GP_LAUNCHED();
+    return GP_OK;
+  }
   int R = (int)((rows + 63) / 64);
   if (R > 256) R = 256;
   if (R < 1) R = 1;

@@ -20,6 +20,44 @@ int colsum(const float* x, long long rows, int d, long long ld, float* out, int 
 
 __host__ __device__ inline int r4i(int v) { return (v + 3) & ~3; }
 
+// Staging: one warp per row, 4-byte cp.async per element -- every load of a CTA is in flight at once and nothing is
+// held in registers, so the whole staging phase costs one memory latency instead of a chain of them.
+__device__ __forceinline__ void cpa4(float* dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cpa_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+// dst[r][c] (row stride ldd) <- src[r][c] (row stride lds) for r < rows, c < cols; zero for r < rows_pad, c < cols_pad
+__device__ __forceinline__ void stage_rows(float* dst, int ldd, const float* src, long long lds, int rows, int cols,
+                                           int rows_pad, int cols_pad) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int r = warp; r < rows_pad; r += nw) {
+    float* d = dst + r * ldd;
+    if (r < rows) {
+      const float* sp = src + (long long)r * lds;
+      for (int c = lane; c < cols; c += 32) cpa4(d + c, sp + c);
+      for (int c = cols + lane; c < cols_pad; c += 32) d[c] = 0.f;
+    } else {
+      for (int c = lane; c < cols_pad; c += 32) d[c] = 0.f;
+    }
+  }
+}
+// dst[c][r] (row stride ldd) <- src[r][c]: transposed staging (reads stay coalesced along c)
+__device__ __forceinline__ void stage_rows_t(float* dst, int ldd, const float* src, long long lds, int rows, int cols,
+                                             int rows_pad, int cols_pad) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int r = warp; r < rows_pad; r += nw) {
+    if (r < rows) {
+      const float* sp = src + (long long)r * lds;
+      for (int c = lane; c < cols; c += 32) cpa4(dst + c * ldd + r, sp + c);
+      for (int c = cols + lane; c < cols_pad; c += 32) dst[c * ldd + r] = 0.f;
+    } else {
+      for (int c = lane; c < cols_pad; c += 32) dst[c * ldd + r] = 0.f;
+    }
+  }
+}
+
 // C[M x Nc] (+)= A[M x K] . B[K x Nc], all in shared memory, row-major with leading dimensions lda / ldb / ldc
 // (ldb, ldc multiples of 4; A zero-filled up to r4(M) rows, B zero-filled up to r4(Nc) columns).
 __device__ __forceinline__ void smem_gemm(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int ldb,
@@ -84,19 +122,11 @@ __global__ void __launch_bounds__(256) gconv_small_fwd_kernel(const SmallFwd p) 
   const float* ab = p.adj + (long long)b * N * N;
   const float* xb = p.x + (long long)b * N * p.ldx;
   // ---- stage A (real block), X (real rows), W, bias ----
-  for (int e = tid; e < n4 * n; e += 256) {
-    const int i = e / n, j = e - i * n;
-    As[i * lda + j] = i < n ? ab[(long long)i * N + j] : 0.f;
-  }
-  for (int e = tid; e < n * dp; e += 256) {
-    const int j = e / dp, c = e - j * dp;
-    XV[j * wide + c] = c < din ? xb[(long long)j * p.ldx + c] : 0.f;
-  }
-  for (int e = tid; e < din * op; e += 256) {
-    const int k = e / op, c = e - k * op;
-    Ws[k * op + c] = c < dout ? p.w[(long long)k * dout + c] : 0.f;
-  }
+  stage_rows(As, lda, ab, N, n, n, n4, n);
+  stage_rows(XV, wide, xb, p.ldx, n, din, n, dp);
+  stage_rows(Ws, op, p.w, dout, din, dout, din, op);
   for (int c = tid; c < op; c += 256) bs[c] = (p.bias != nullptr && c < dout) ? p.bias[c] : 0.f;
+  cpa_wait_all();
   __syncthreads();
   // ---- U = A.X (rows < n), kept in shared memory and written out; pad rows of u are zero ----
   smem_gemm(As, lda, XV, wide, n, din, n, Us, dp, nullptr);
@@ -162,36 +192,12 @@ __global__ void __launch_bounds__(256) gconv_small_bwd_kernel(const SmallBwd p, 
   const float* dvb = p.dv + (long long)b * N * dout;
   const float* ub = p.u + (long long)b * N * din;
   // ---- db partial: column sums of dV over ALL N rows (pad rows carry gradient through the BatchNorm) ----
-  for (int c = tid; c < op; c += 256) cs[c] = 0.f;
-  for (int e = tid; e < n4 * op; e += 256) {
-    const int i = e / op, c = e - i * op;
-    dVs[e] = (i < n && c < dout) ? dvb[(long long)i * dout + c] : 0.f;
-  }
-  for (int e = tid; e < dp * N4; e += 256) {
-    const int c = e / N4, i = e - c * N4;
-    Ut[e] = (c < din && i < n) ? ub[(long long)i * din + c] : 0.f;
-  }
-  if (need_dx || need_da) {
-    for (int e = tid; e < dout * dp; e += 256) {
-      const int o = e / dp, c = e - o * dp;
-      Wt[e] = c < din ? p.w[(long long)c * dout + o] : 0.f;
-    }
-  }
-  if (need_dx) {
-    const float* ab = p.adj + (long long)b * N * N;
-    for (int e = tid; e < n4 * n; e += 256) {            // coalesced read of row i, transposed store
-      const int i = e % n, j = e / n;                    // j: output row (column of A)
-      At[j * ldat + i] = j < n ? ab[(long long)i * N + j] : 0.f;
-    }
-    // NOTE: the read above walks a column of A (stride N) -- n <= 128, the block is L1/L2 resident
-  }
-  if (need_da) {
-    const float* xb = p.x + (long long)b * N * p.ldx;
-    for (int e = tid; e < din * N4; e += 256) {
-      const int c = e / N4, j = e - c * N4;
-      Xt[e] = j < n ? xb[(long long)j * p.ldx + c] : 0.f;
-    }
-  }
+  stage_rows(dVs, op, dvb, dout, n, dout, n4, op);
+  stage_rows_t(Ut, N4, ub, din, n, din, n, dp);            // Ut[c][i] = U[i][c] (i < n), zero rows for c >= din
+  if (need_dx || need_da) stage_rows_t(Wt, dp, p.w, dout, din, dout, dp, dout);   // Wt[o][c] = W[c][o]
+  if (need_dx) stage_rows_t(At, ldat, p.adj + (long long)b * N * N, N, n, n, n, n4);   // At[j][i] = A[i][j]
+  if (need_da) stage_rows_t(Xt, N4, p.x + (long long)b * N * p.ldx, p.ldx, n, din, N4, din);   // Xt[c][j] = X[j][c]
+  cpa_wait_all();
   __syncthreads();
   float* part = p.part + (long long)b * ((long long)din * dout + dout);
   {   // db: one thread per column over all N rows (coalesced across the warp)
@@ -343,8 +349,12 @@ int small_gcn_bwd(const float* dv, const float* u, const float* x, long long ldx
   const int wdt = din * dout + dout;
   float* tmp = ws + (long long)B * wdt;
   // reduce the per-graph partials over the batch (two-stage, deterministic); dW and db are contiguous slices
-  GP_TRY(colsum(ws, B, din * dout, wdt, dw, 0, tmp, st));
-  if (db != nullptr) GP_TRY(colsum(ws + (long long)din * dout, B, dout, wdt, db, 0, tmp, st));
+  if (db == dw + (long long)din * dout) {                // the caller laid dW | db out contiguously: one reduction
+    GP_TRY(colsum(ws, B, wdt, wdt, dw, 0, tmp, st));
+  } else {
+    GP_TRY(colsum(ws, B, din * dout, wdt, dw, 0, tmp, st));
+    if (db != nullptr) GP_TRY(colsum(ws + (long long)din * dout, B, dout, wdt, db, 0, tmp, st));
+  }
   return GP_OK;
 }
 

@@ -159,8 +159,11 @@ def stack_backward(ws, ctx, dz_ptr, lddz, dout_ptr, arg_ptr, ldo, need_dx, dadj,
         call('gp_gcn_layer_bwd_x', C.byref(q), st)
         need_dx_l = need_dx or l > 0
         w = ctx.weights[l]
-        dw = ws.f(din, dout)
-        db = ws.f(dout) if ctx.biases[l] is not None else None
+        if ctx.biases[l] is not None:       # dW | db contiguous: the per-graph fused path reduces both in one pass
+            dwdb = ws.f(din * dout + dout)
+            dw, db = dwdb[:din * dout].view(din, dout), dwdb[din * dout:]
+        else:
+            dw, db = ws.f(din, dout), None
         du = ws.f(B, N, din) if (need_dx_l or dadj is not None) else None
         dx = ws.f(B, N, din) if need_dx_l else None
         cs = ws.f(int(_lib.load().gp_graphconv_bwd_ws(B, N, din, dout, int(ctx.add_self))))
