@@ -63,7 +63,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '20'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -77,23 +77,33 @@ class ClockSampler:
     def stop(self, t0, t1):
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.06)                                  # let the sample that covers the end of the region arrive
         self.proc.terminate()
-        sm, smax, reasons = [], None, set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for t, line in self.rows:
-            if t < t0 or t > t1 + 0.15:
-                continue
-            f = [x.strip() for x in line.split(',')]
-            try:
-                sm.append(float(f[0]))
-                smax = float(f[1])
-            except Exception:
-                continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith('active'):
-                    reasons.add(n)
+
+        def collect(lo, hi):
+            sm, smax, reasons = [], None, set()
+            for t, line in self.rows:
+                if t < lo or t > hi:
+                    continue
+                f = [x.strip() for x in line.split(',')]
+                try:
+                    sm.append(float(f[0]))
+                    smax = float(f[1])
+                except Exception:
+                    continue
+                for n, v in zip(names, f[3:7]):
+                    if v.lower().startswith('active'):
+                        reasons.add(n)
+            return sm, smax, reasons
+
+        sm, smax, reasons = collect(t0, t1 + 0.15)
+        window = 'timed region'
+        if not sm:       # a region shorter than the sampling period: fall back to warm-up + region (same load)
+            sm, smax, reasons = collect(0.0, t1 + 0.15)
+            window = 'warm-up + timed region (region shorter than the sampling period)'
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': smax, 'reasons': sorted(reasons),
-                'samples': len(sm)}
+                'samples': len(sm), 'window': window}
 
 
 def peaks():
@@ -231,12 +241,12 @@ def main():
         return ms
 
     # ---- device-resident timing ---------------------------------------------------------------
+    sampler = ClockSampler(local) if rank == 0 else None      # started early: already streaming when timing begins
     for _ in range(args.warmup):
         step(x, adj, label)
     lib.gp_launch_count_reset()
     if gstep is not None:
         gstep.replayed_launches = 0
-    sampler = ClockSampler(local) if rank == 0 else None
     t0 = time.time()
     if os.environ.get('GP_PROFILE'):            # ncu --profile-from-start off: capture the timed steps only
         torch.cuda.cudart().cudaProfilerStart()

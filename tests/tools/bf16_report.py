@@ -1,7 +1,7 @@
 """Error of the GP_BF16 (tensor-core) mode vs the fp64 oracle on seeded batches (GPU)."""
 import copy, os, sys
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 from helpers import rel_l2, synth_batch
 from graph_pooling_b200 import encoders

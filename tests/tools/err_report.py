@@ -1,7 +1,7 @@
 """Per-tensor error report: candidate (GPU) and fp32 oracle vs the fp64 golden vectors."""
 import os, sys
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 from helpers import GOLDEN, golden_inputs, golden_model, load_golden, rel_l2
 from graph_pooling_b200 import encoders
