@@ -141,3 +141,45 @@ def test_dual_stack_matches_separate_stacks(monkeypatch):
         a, b = res[('dual', same_x)], res[('sep', same_x)]
         assert np.array_equal(a[0], b[0]) and a[1] == b[1]
         assert rel_l2(a[2], b[2]) < 1e-5
+
+
+@pytest.mark.parametrize('B,N,H,ratio,n_min', [(2, 2048, 128, 0.25, 2048), (2, 2048, 128, 0.25, 700), (1, 5000, 64, 0.25, 3000)])
+def test_bf16_mode_against_fp32_mode_at_full_size(B, N, H, ratio, n_min):
+    """BASELINE.json's full sizes (2048-node dense graphs, K = 512; a 5000-node ragged graph, K = 1250) are beyond what
+    the CPU oracle finishes in seconds: there the tensor-core mode is checked against this library's own fp32 mode
+    (itself pinned to the oracle at small sizes) on the same inputs and weights -- every tile boundary, the
+    upper-band link-loss schedule, the symmetric shortcuts and the padding-aware skips at their real extents."""
+    from graph_pooling_b200 import encoders
+    D, C = H, 2
+    torch.manual_seed(N + B)
+    m = encoders.SoftPoolingGcnEncoder(N, D, H, H, C, 3, H, assign_ratio=ratio).cuda()
+    with torch.no_grad():
+        for k, p in m.named_parameters():
+            if k.endswith('bias'):
+                p.normal_(0, 0.2)
+    g = torch.Generator(device='cuda').manual_seed(1)
+    nb = np.random.RandomState(N).randint(n_min, N + 1, size=B).astype(np.int32)
+    real = torch.arange(N, device='cuda')[None, :] < torch.as_tensor(nb.astype(np.int64), device='cuda')[:, None]
+    u = torch.triu(torch.rand(B, N, N, device='cuda', generator=g) < 8.0 / N, diagonal=1)
+    u = u & real[:, None, :] & real[:, :, None]
+    adj = (u | u.transpose(1, 2)).float()
+    x = torch.randn(B, N, D, device='cuda', generator=g) * real[:, :, None].float()
+    label = torch.randint(0, C, (B,), device='cuda', generator=g)
+    out = {}
+    for prec in (0, 1):
+        m.precision = prec
+        m.zero_grad()
+        yp = m(x, adj, nb, assign_x=x)
+        loss = m.loss(yp, label, adj, nb)
+        loss.backward()
+        torch.cuda.synchronize()
+        out[prec] = (yp.detach().float().cpu().numpy(), loss.item(), m.link_loss.item(),
+                     m.assign_tensor.detach().cpu().numpy(),
+                     np.concatenate([p.grad.cpu().numpy().ravel() for p in m.parameters()]).astype(np.float64))
+        del yp, loss
+    y0, l0, k0, s0, g0 = out[0]
+    y1, l1, k1, s1, g1 = out[1]
+    assert rel_l2(y1, y0) < 2e-2 and rel_l2(s1, s0) < 2e-2
+    assert abs(l1 - l0) < 5e-3 * abs(l0) and abs(k1 - k0) < 5e-3 * abs(k0)
+    cos = float(g1 @ g0 / (np.linalg.norm(g1) * np.linalg.norm(g0)))
+    assert rel_l2(g1, g0) < 0.15 and cos > 0.99, (rel_l2(g1, g0), cos)
