@@ -14,7 +14,8 @@ FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std
 
 
 def sources():
-    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith('.cu'))
+    # .cu: device + C-ABI code (nvcc, sm_100a); .cpp: host-only helpers of the feed (compiled by the host compiler)
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cu', '.cpp')))
 
 
 def _stale(out, deps):
@@ -30,13 +31,17 @@ def build_native(force=False, verbose=False):
     hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cuh', '.h'))]
     hdrs.append(os.path.join(os.path.dirname(HERE), 'include', 'gp_b200.h'))
     srcs = sources()
-    objs = [os.path.join(HERE, 'build', os.path.basename(s)[:-3] + '.o') for s in srcs]
+    objs = [os.path.join(HERE, 'build', os.path.splitext(os.path.basename(s))[0] + '.o') for s in srcs]
 
     def compile_one(so):
         s, o = so
         if not force and not _stale(o, [s] + hdrs):
             return ''
-        r = subprocess.run([NVCC] + FLAGS + ['-c', s, '-o', o], capture_output=True, text=True)
+        if s.endswith('.cpp'):
+            cmd = [NVCC, '-O3', '-std=c++17', '-Xcompiler', '-fPIC,-pthread', '-c', s, '-o', o]
+        else:
+            cmd = [NVCC] + FLAGS + ['-c', s, '-o', o]
+        r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError('nvcc failed for %s:\n%s\n%s' % (s, r.stdout, r.stderr))
         return r.stderr
@@ -49,7 +54,8 @@ def build_native(force=False, verbose=False):
     with open(os.path.join(HERE, 'build', 'ptxas.log'), 'a') as f:
         f.write(''.join(logs))
     if force or _stale(LIB, objs):
-        r = subprocess.run([NVCC, '-shared', '-o', LIB] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a'],
+        r = subprocess.run([NVCC, '-shared', '-o', LIB] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a',
+                                                                    '-Xcompiler', '-pthread'],
                            capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError('link failed:\n%s\n%s' % (r.stdout, r.stderr))

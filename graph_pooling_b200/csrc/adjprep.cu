@@ -8,6 +8,7 @@
 // memory.  Tiles beyond a graph's node count are all-zero by the feed contract (graph_sampler.py:97-109):
 // they are written as zeros without being read (padding-aware schedule).
 #include <cuda_bf16.h>
+#include <type_traits>
 #include "common.cuh"
 
 namespace gp {
@@ -28,16 +29,29 @@ template <> struct Ld4<uint8_t> {
   }
 };
 
+// bit-packed adjacency (gp_host_pack_adj_bits): bit (c & 7) of byte c >> 3 of the row; c is a multiple of 4 here
+struct BitRow {};
+template <> struct Ld4<BitRow> {
+  static __device__ __forceinline__ void ld(const uint8_t* row, int c, int nvalid, float (&v)[4]) {
+    const uint32_t byte = row[c >> 3] >> (c & 7);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[e] = (e < nvalid && ((byte >> e) & 1u)) ? 1.f : 0.f;
+  }
+};
+
 __device__ __forceinline__ uint32_t pk2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
 // loads tile rows r0.., cols c0.. of graph b into regs (4 passes of 16 rows, one float4 per thread), writes bf16
+template <typename T> struct InPtr { using type = const T*; };
+template <> struct InPtr<BitRow> { using type = const uint8_t*; };
+
 template <typename T>
-__device__ __forceinline__ void tile_io(const T* __restrict__ ab, __nv_bfloat16* __restrict__ ob, int N, long long ld,
-                                        int r0, int c0, int nreal, bool vec_in, bool vec_out, float (&v)[4][4],
-                                        int* non01) {
+__device__ __forceinline__ void tile_io(typename InPtr<T>::type ab, long long ldin, __nv_bfloat16* __restrict__ ob,
+                                        int N, long long ld, int r0, int c0, int nreal, bool vec_in, bool vec_out,
+                                        float (&v)[4][4], int* non01) {
   const int tr = threadIdx.x >> 4, tc = (threadIdx.x & 15) * 4;
   const bool live = r0 < nreal && c0 < nreal;           // otherwise all-zero by contract: do not read
 #pragma unroll
@@ -45,7 +59,10 @@ __device__ __forceinline__ void tile_io(const T* __restrict__ ab, __nv_bfloat16*
     const int r = r0 + tr + 16 * i, c = c0 + tc;
 #pragma unroll
     for (int e = 0; e < 4; ++e) v[i][e] = 0.f;
-    if (live && r < N && c < N) Ld4<T>::ld(ab + (long long)r * N + c, vec_in && c + 4 <= N, N - c, v[i]);
+    if (live && r < N && c < N) {
+      if constexpr (std::is_same<T, BitRow>::value) Ld4<T>::ld(ab + (long long)r * ldin, c, N - c, v[i]);
+      else Ld4<T>::ld(ab + (long long)r * ldin + c, vec_in && c + 4 <= N, N - c, v[i]);
+    }
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -66,8 +83,9 @@ __device__ __forceinline__ void tile_io(const T* __restrict__ ab, __nv_bfloat16*
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-adj_prepare_kernel(const T* __restrict__ adj, const int32_t* __restrict__ nb, int N, __nv_bfloat16* __restrict__ out,
-                   long long ld, int tiles, int* __restrict__ flags, bool vec_in, bool vec_out) {
+adj_prepare_kernel(typename InPtr<T>::type adj, long long ldin, const int32_t* __restrict__ nb, int N,
+                   __nv_bfloat16* __restrict__ out, long long ld, int tiles, int* __restrict__ flags, bool vec_in,
+                   bool vec_out) {
   __shared__ float X[AT][AT + 1];
   // blockIdx.x enumerates pairs (ti <= tj) row by row
   int ti = 0, rem = blockIdx.x;
@@ -75,12 +93,12 @@ adj_prepare_kernel(const T* __restrict__ adj, const int32_t* __restrict__ nb, in
   const int tj = ti + rem;
   const int b = blockIdx.y;
   const int nreal = nb != nullptr ? min(nb[b], N) : N;
-  const T* ab = adj + (long long)b * N * N;
+  typename InPtr<T>::type ab = adj + (long long)b * N * ldin;
   __nv_bfloat16* ob = out + (long long)b * N * ld;
   const int tr = threadIdx.x >> 4, tc = (threadIdx.x & 15) * 4;
   int non01 = 0, asym = 0;
   float v[4][4];
-  tile_io<T>(ab, ob, N, ld, ti * AT, tj * AT, nreal, vec_in, vec_out, v, &non01);
+  tile_io<T>(ab, ldin, ob, N, ld, ti * AT, tj * AT, nreal, vec_in, vec_out, v, &non01);
   // the last tile column also owns the zero fill of the operand's padding columns [tiles*64, ld) -- none here:
   // ld - N < 8 < 64, so they fall inside tile tj == tiles-1 and tile_io's `c < ld` bound covers them.
 #pragma unroll
@@ -89,7 +107,7 @@ adj_prepare_kernel(const T* __restrict__ adj, const int32_t* __restrict__ nb, in
     for (int e = 0; e < 4; ++e) X[tr + 16 * i][tc + e] = v[i][e];
   __syncthreads();
   if (tj != ti) {
-    tile_io<T>(ab, ob, N, ld, tj * AT, ti * AT, nreal, vec_in, vec_out, v, &non01);
+    tile_io<T>(ab, ldin, ob, N, ld, tj * AT, ti * AT, nreal, vec_in, vec_out, v, &non01);
   }
   // compare (tj,ti)[r][c] with (ti,tj)[c][r]; on the diagonal the tile is compared with its own transpose
 #pragma unroll
@@ -150,23 +168,35 @@ extern "C" int gp_sym_select_bf16(const float* x, long long ldx, int B, int K, c
 
 extern "C" int gp_adj_prepare(const void* adj, int adj_dtype, const int32_t* nb, int B, int N, void* adj_bf16,
                               long long ld, int32_t* flags, gp_stream_t stream) {
+  return gp_adj_prepare_x(adj, adj_dtype, 0, nb, B, N, adj_bf16, ld, flags, 0, stream);
+}
+
+extern "C" int gp_adj_prepare_x(const void* adj, int adj_dtype, long long ld_in, const int32_t* nb, int B, int N,
+                                void* adj_bf16, long long ld, int32_t* flags, int accumulate_flags,
+                                gp_stream_t stream) {
   GP_REQUIRE(adj && adj_bf16 && B > 0 && N > 0 && ld >= N && ld - N < 8, "adj_prepare: bad args (need N <= ld < N+8)");
-  GP_REQUIRE(adj_dtype == 0 || adj_dtype == 1, "adj_prepare: adj_dtype must be 0 (fp32) or 1 (uint8)");
+  GP_REQUIRE(adj_dtype >= 0 && adj_dtype <= 2, "adj_prepare: adj_dtype must be 0 (fp32), 1 (uint8) or 2 (bit-packed)");
   GP_REQUIRE(B <= 65535, "adj_prepare: B too large");
+  if (ld_in <= 0) ld_in = adj_dtype == 2 ? (N + 7) / 8 : N;
+  GP_REQUIRE(ld_in >= (adj_dtype == 2 ? (N + 7) / 8 : N), "adj_prepare: input row stride too small");
   const int tiles = (N + AT - 1) / AT;
   const long long pairs = (long long)tiles * (tiles + 1) / 2;
   GP_REQUIRE(pairs < (1LL << 31), "adj_prepare: N too large");
-  if (flags != nullptr) GP_CUDA(cudaMemsetAsync(flags, 0, 2 * sizeof(int32_t), S(stream)));
+  if (flags != nullptr && !accumulate_flags) GP_CUDA(cudaMemsetAsync(flags, 0, 2 * sizeof(int32_t), S(stream)));
   dim3 grid((unsigned)pairs, (unsigned)B);
   const bool vec_out = (reinterpret_cast<uintptr_t>(adj_bf16) & 7) == 0 && ld % 4 == 0;
+  __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(adj_bf16);
   if (adj_dtype == 0) {
-    const bool vec_in = (reinterpret_cast<uintptr_t>(adj) & 15) == 0 && N % 4 == 0;
-    adj_prepare_kernel<float><<<grid, 256, 0, S(stream)>>>(reinterpret_cast<const float*>(adj), nb, N,
-        reinterpret_cast<__nv_bfloat16*>(adj_bf16), ld, tiles, flags, vec_in, vec_out);
+    const bool vec_in = (reinterpret_cast<uintptr_t>(adj) & 15) == 0 && N % 4 == 0 && ld_in % 4 == 0;
+    adj_prepare_kernel<float><<<grid, 256, 0, S(stream)>>>(reinterpret_cast<const float*>(adj), ld_in, nb, N, ob, ld,
+                                                          tiles, flags, vec_in, vec_out);
+  } else if (adj_dtype == 1) {
+    const bool vec_in = (reinterpret_cast<uintptr_t>(adj) & 3) == 0 && N % 4 == 0 && ld_in % 4 == 0;
+    adj_prepare_kernel<uint8_t><<<grid, 256, 0, S(stream)>>>(reinterpret_cast<const uint8_t*>(adj), ld_in, nb, N, ob, ld,
+                                                            tiles, flags, vec_in, vec_out);
   } else {
-    const bool vec_in = (reinterpret_cast<uintptr_t>(adj) & 3) == 0 && N % 4 == 0;
-    adj_prepare_kernel<uint8_t><<<grid, 256, 0, S(stream)>>>(reinterpret_cast<const uint8_t*>(adj), nb, N,
-        reinterpret_cast<__nv_bfloat16*>(adj_bf16), ld, tiles, flags, vec_in, vec_out);
+    adj_prepare_kernel<BitRow><<<grid, 256, 0, S(stream)>>>(reinterpret_cast<const uint8_t*>(adj), ld_in, nb, N, ob, ld,
+                                                           tiles, flags, false, vec_out);
   }
   GP_LAUNCHED();
   return GP_OK;

@@ -50,7 +50,10 @@ def _fwd_tc(ctx, plan, x, adj, assign_x, params):
     P, Fw = plan.num_pooling, plan.F
     ldo = Fw * (P + 1)
     out, arg = ws.f(B, ldo), ws.i(B, ldo)
-    adjb, aflags = T.adj_prepare(ws, adj, nb, B, N)       # bf16 operand + [not symmetric, not {0,1}] device flags
+    if isinstance(adj, T.PreparedAdjacency):
+        adjb, aflags = adj.op, adj.flags
+    else:
+        adjb, aflags = T.adj_prepare(ws, adj, nb, B, N)   # bf16 operand + [not symmetric, not {0,1}] device flags
     xb = T.cvt(ws, x.data_ptr(), D, B * N, D, B=B)
     w0, b0 = conv(plan.emb)
     xab, xa_d, pre_as = xb, D, None
@@ -622,8 +625,15 @@ class GcnEncoderGraph(nn.Module):
         return pairs
 
     def _base_plan(self, x, adj, batch_num_nodes):
-        x, adj = E._chk(x, 'x'), E._chk_adj(adj, self.precision == T.BF16 and self.concat)
-        if x.dim() != 3 or adj.dim() != 3 or adj.shape[1] != adj.shape[2] or adj.shape[:2] != x.shape[:2]:
+        x = E._chk(x, 'x')
+        if isinstance(adj, T.PreparedAdjacency):             # bf16 operand built by the feed (tensor-core mode only)
+            if not (self.precision == T.BF16 and self.concat):
+                raise ValueError('a PreparedAdjacency needs the tensor-core mode (model.precision = 1)')
+        else:
+            adj = E._chk_adj(adj, self.precision == T.BF16 and self.concat)
+        if len(adj.shape) != 3:
+            raise ValueError('adj must be [B,N,N]')
+        if x.dim() != 3 or adj.shape[1] != adj.shape[2] or tuple(adj.shape[:2]) != tuple(x.shape[:2]):
             raise ValueError('expected x [B,N,D] and adj [B,N,N], got %s and %s' % (tuple(x.shape), tuple(adj.shape)))
         if x.shape[2] != self.conv_first.weight.shape[0]:
             raise ValueError('input feature dim %d != conv_first input dim %d'
@@ -801,7 +811,8 @@ class SoftPoolingGcnEncoder(GcnEncoderGraph):
             raise NotImplementedError('gp_b200: entropy_weight with device-resident batch_num_nodes')
         lp.num_real_rows = S0.shape[0] * N0 if nb_host is None else max(int(np.sum(nb_host.astype(np.int64))), 1)
         if self.linkpred:
-            adj = E._chk_adj(adj, lp.sb0 is not None)
+            if not isinstance(adj, T.PreparedAdjacency):
+                adj = E._chk_adj(adj, lp.sb0 is not None)
             if dev_only:
                 st = torch.empty(2, device=S0.device, dtype=torch.float32)
                 call('gp_nb_stats', lp.nb_dev.data_ptr(), S0.shape[0], st.data_ptr(), E._stream())
@@ -814,7 +825,7 @@ class SoftPoolingGcnEncoder(GcnEncoderGraph):
                 lp.num_entries = int(np.sum(n64 * n64))
             if self._entries_override is not None:
                 lp.num_entries = self._entries_override
-        outs = _LossFn.apply(lp, pred, label, S0, adj if self.linkpred else None)
+        outs = _LossFn.apply(lp, pred, label, S0, adj if self.linkpred else None)   # adj: tensor or PreparedAdjacency
         k = 1
         if self.linkpred:
             self.link_loss = outs[k]

@@ -53,6 +53,38 @@ def adj_prepare(ws, adj, nb, B, N):
     return out, flags
 
 
+class PreparedAdjacency:
+    """The bf16 adjacency operand of a batch, built by the FEED instead of by the module: accepted wherever the
+    encoders (tensor-core mode) take `adj`.  A batch may be assembled from parts that reached the device in different
+    encodings -- fp32 (the reference feed, train.py:197), uint8, or bit-packed rows (gp_host_pack_adj_bits) -- each
+    expanded by gp_adj_prepare_x into its slice of the operand; the symmetry / {0,1} flags accumulate over the parts."""
+    KINDS = {'f32': 0, 'u8': 1, 'bits': 2}
+
+    def __init__(self, B, N, device):
+        self.shape = (B, N, N)
+        self.device = torch.device(device)
+        self.op = bfbuf(E.Workspace(self.device), B, N, N)
+        self.flags = torch.zeros(2, device=self.device, dtype=torch.int32)
+        self._fresh = True
+
+    def reset(self):
+        self._fresh = True
+
+    def add(self, src, b0, nb=None, kind='f32'):
+        """Graphs [b0, b0 + src.shape[0]) from `src`: [cnt,N,N] fp32 / uint8, or [cnt,N,ldb] uint8 bit rows."""
+        B, N, _ = self.shape
+        cnt = int(src.shape[0])
+        if not src.is_cuda or not src.is_contiguous() or b0 < 0 or b0 + cnt > B:
+            raise ValueError('PreparedAdjacency.add: need a contiguous CUDA tensor inside the batch')
+        code = self.KINDS[kind]
+        ld_in = int(src.shape[2])
+        nbp = None if nb is None else nb.data_ptr() + 4 * b0
+        call('gp_adj_prepare_x', src.data_ptr(), code, C.c_longlong(ld_in), nbp, cnt, N,
+             self.op.ptr + 2 * b0 * self.op.sb, self.op.ld, self.flags.data_ptr(), 0 if self._fresh else 1, E._stream())
+        self._fresh = False
+        return self
+
+
 _USE_V1 = bool(os.environ.get('GP_TC_V1'))     # debug: single-tile-per-CTA kernel of gemm_tc.cu
 
 

@@ -162,6 +162,17 @@ int gp_softmax_mask_bwd_x(const float* s, const float* ds, const int32_t* nb, in
  * zeros without being read (feed contract graph_sampler.py:97-109). */
 int gp_adj_prepare(const void* adj, int adj_dtype, const int32_t* nb, int B, int N, void* adj_bf16, long long ld,
                    int32_t* flags, gp_stream_t stream);
+/* Extended form: adj_dtype 2 = bit-packed rows from gp_host_pack_adj_bits (bit c & 7 of byte c >> 3); ld_in = input
+ * row stride in elements (bytes for dtype 2; 0 = dense); accumulate_flags = 1 ORs into `flags` instead of
+ * resetting them, so a batch may be prepared in several calls (e.g. one part fed as bits, one as fp32). */
+int gp_adj_prepare_x(const void* adj, int adj_dtype, long long ld_in, const int32_t* nb, int B, int N,
+                     void* adj_bf16, long long ld, int32_t* flags, int accumulate_flags, gp_stream_t stream);
+/* HOST function (no CUDA): packs `rows` rows of N fp32 entries (a dense {0,1} adjacency in host memory, the
+ * reference's feed, train.py:197) into bits, `ldb` bytes per row, on `threads` host threads (AVX2 when available).
+ * *non01 = 1 if any entry is outside {0,1} (the caller must then feed those rows as fp32).  Shrinks the PCIe
+ * transfer 32x; 16 threads pack ~87 GB/s on the B200 box (PCIe moves the raw floats at ~65 GB/s). */
+int gp_host_pack_adj_bits(const float* adj_host, long long rows, int N, void* out_host, long long ldb, int threads,
+                          int* non01);
 /* out[b] = bf16((cond && *cond == 0) ? x[b] + x[b]^T : x[b]), x [B,K,K] fp32 with row stride ldx, out row stride
  * ld (zero padded). */
 int gp_sym_select_bf16(const float* x, long long ldx, int B, int K, const int32_t* cond, void* out_bf16,

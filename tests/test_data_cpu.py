@@ -95,3 +95,24 @@ def test_reader_awkward_cases(tmp_path):
             assert {(min(u, v), max(u, v)) for u, v in g.edges()} == \
                 {tuple(r) for r in gs.edges[gs.eptr[gi_]:gs.eptr[gi_ + 1]]}
             off += gs.n[gi_]
+
+
+@pytest.mark.parametrize('rows,N,threads', [(37, 100, 1), (64, 2048, 4), (5, 13, 3), (200, 64, 16)])
+def test_host_bit_packer_matches_numpy(rows, N, threads):
+    """gp_host_pack_adj_bits (host code of the feed, no GPU needed): bit c & 7 of byte c >> 3, zero padding to the row
+    stride, and the 'entry outside {0,1}' report."""
+    import ctypes as C
+    from graph_pooling_b200 import _lib
+    lib = _lib.load()
+    rs = np.random.RandomState(rows + N)
+    a = (rs.rand(rows, N) < 0.3).astype(np.float32)
+    ldb = (N + 7) // 8 + 3
+    out = np.full((rows, ldb), 0xAB, np.uint8)
+    bad = C.c_int(-1)
+    rc = lib.gp_host_pack_adj_bits(a.ctypes.data, rows, N, out.ctypes.data, ldb, threads, C.addressof(bad))
+    assert rc == 0 and bad.value == 0
+    ref = np.packbits(a.astype(np.uint8), axis=1, bitorder='little')
+    assert np.array_equal(out[:, :ref.shape[1]], ref) and not out[:, ref.shape[1]:].any()
+    a[rows // 2, N // 3] = 0.5
+    lib.gp_host_pack_adj_bits(a.ctypes.data, rows, N, out.ctypes.data, ldb, threads, C.addressof(bad))
+    assert bad.value == 1

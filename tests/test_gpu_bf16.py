@@ -183,3 +183,40 @@ def test_bf16_mode_against_fp32_mode_at_full_size(B, N, H, ratio, n_min):
     assert abs(l1 - l0) < 5e-3 * abs(l0) and abs(k1 - k0) < 5e-3 * abs(k0)
     cos = float(g1 @ g0 / (np.linalg.norm(g1) * np.linalg.norm(g0)))
     assert rel_l2(g1, g0) < 0.15 and cos > 0.99, (rel_l2(g1, g0), cos)
+
+
+@pytest.mark.parametrize('B,N,sym', [(4, 200, 1), (3, 130, 0), (5, 64, 1)])
+def test_prepared_adjacency_from_bits_and_fp32_parts(B, N, sym):
+    """Feed-side adjacency: part of the batch bit-packed on the host (gp_host_pack_adj_bits), part as fp32, both
+    expanded by gp_adj_prepare_x into one bf16 operand -- identical operand, flags and model outputs as the plain
+    fp32 adjacency."""
+    import ctypes as C
+    from graph_pooling_b200 import _lib, encoders, engine as E, engine_tc as T
+    x, adj, nb, label = synth_batch(N + B, B, N, 6, N // 2, N, 3, 0.1, symmetric=bool(sym))
+    ldb = (N + 7) // 8
+    bits = np.zeros((B, N, ldb), np.uint8)
+    bad = C.c_int(0)
+    _lib.load().gp_host_pack_adj_bits(adj.ctypes.data, B * N, N, bits.ctypes.data, ldb, 4, C.addressof(bad))
+    assert bad.value == 0
+    nbd = torch.tensor(nb).cuda()
+    ref_op, ref_flags = T.adj_prepare(E.Workspace(torch.device('cuda')), torch.tensor(adj).cuda(), nbd, B, N)
+    h = B // 2
+    pa = T.PreparedAdjacency(B, N, 'cuda')
+    pa.add(torch.tensor(bits[:h]).cuda(), 0, nbd, 'bits')
+    pa.add(torch.tensor(adj[h:]).cuda(), h, nbd, 'f32')
+    torch.cuda.synchronize()
+    assert torch.equal(pa.op.t, ref_op.t) and pa.flags.tolist() == ref_flags.tolist() == [int(not sym), 0]
+    torch.manual_seed(0)
+    m = encoders.SoftPoolingGcnEncoder(N, 6, 32, 32, 3, 3, 32, assign_ratio=0.25).cuda()
+    m.precision = 1
+    xc, lc = torch.tensor(x).cuda(), torch.tensor(label).cuda()
+    res = []
+    for a in (torch.tensor(adj).cuda(), pa):
+        m.zero_grad()
+        yp = m(xc, a, nb, assign_x=xc)
+        loss = m.loss(yp, lc, a, nb)
+        loss.backward()
+        torch.cuda.synchronize()
+        res.append((yp.detach().cpu().numpy(), loss.item()))
+        del yp, loss
+    assert np.array_equal(res[0][0], res[1][0]) and res[0][1] == res[1][1]
