@@ -220,3 +220,33 @@ def test_prepared_adjacency_from_bits_and_fp32_parts(B, N, sym):
         res.append((yp.detach().cpu().numpy(), loss.item()))
         del yp, loss
     assert np.array_equal(res[0][0], res[1][0]) and res[0][1] == res[1][1]
+
+
+def test_host_adjacency_feed_pipeline():
+    """feed.HostAdjacencyFeed: fp32 adjacencies in pinned host memory, a different one per step, go through the
+    pack / copy / prepare pipeline and arrive as exactly the operand gp_adj_prepare builds from the fp32 tensor."""
+    from graph_pooling_b200 import engine as E, engine_tc as T, feed
+    B, N = 6, 150
+    batches = [synth_batch(70 + i, B, N, 4, 40, N, 2, 0.1) for i in range(4)]
+    host = [torch.tensor(b[1]).pin_memory() for b in batches]
+    fd = feed.HostAdjacencyFeed(B, N, 'cuda', packed_graphs=4, threads=3)
+    fd.submit(host[0], 0)
+    fd.copy(0)
+    fd.submit(host[1], 1)
+    for i in range(4):
+        cur, nxt = i & 1, (i + 1) & 1
+        if i + 1 < 4:
+            fd.copy(nxt)
+        if i + 2 < 4:
+            fd.submit(host[i + 2], cur)
+        nbd = torch.tensor(batches[i][2]).cuda()
+        pa = fd.prepared(cur, nbd)
+        ref, rflags = T.adj_prepare(E.Workspace(torch.device('cuda')), host[i].cuda(), nbd, B, N)
+        torch.cuda.synchronize()
+        assert torch.equal(pa.op.t, ref.t) and pa.flags.tolist() == rflags.tolist(), i
+    bad = host[0].clone().pin_memory()
+    bad[1, 3, 4] = 0.25
+    fd.submit(bad, 0)
+    with pytest.raises(ValueError):
+        fd.copy(0)
+    fd.close()
