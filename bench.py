@@ -191,17 +191,17 @@ def main():
     model = synth.build_model(encoders, cfg).to(dev)
     prec = args.precision if args.precision != 'auto' else ('bf16' if cfg['N'] >= 512 else 'f32')
     model.precision = 1 if prec == 'bf16' else 0
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
     params = [p for p in model.parameters()]
     x, adj, nb, label = batch['x'], batch['adj'], batch['nb'], batch['label']
     B = x.shape[0]
 
     # gradients live in ONE flat buffer (dp.FlatGradients): the all-reduce and the clip need no gather copies
     from graph_pooling_b200 import dp
-    flat = dp.FlatGradients(params)
-
     use_graph = (args.graph == 'on' or (args.graph == 'auto' and adj.numel() * 4 <= 256e6)) and world == 1
     gstep = None
+    if not use_graph:
+        opt = dp.FlatAdam(params, lr=1e-3, clip=2.0)     # clip_grad_norm + Adam: two kernels of this library
+        flat = opt.grads
     if use_graph:
         from graph_pooling_b200 import graphed
         gstep = graphed.GraphedTrainStep(model, lr=1e-3, clip=2.0)
@@ -216,8 +216,7 @@ def main():
         loss = model.loss(yp, ld, ad, nb) if soft else model.loss(yp, ld)
         loss.backward()
         flat.all_reduce(average=True)                # one NCCL all-reduce per step (no-op at world == 1)
-        flat.clip_(2.0)                              # train.py:209
-        opt.step()
+        opt.step()                                   # train.py:209-210: clip_grad_norm(2.0) folded into Adam
         return loss
 
     def barrier():

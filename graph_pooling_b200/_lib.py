@@ -107,6 +107,8 @@ _PROTOS = {
     'gp_entropy_partials': [c_i, c_i],
     'gp_entropy_fwd': [c_f, c_f, c_i, c_i, c_i, c_f, c_f],
     'gp_entropy_bwd': [c_f, c_f, c_i, c_i, c_i, c_f, C.c_float, c_f, c_i, c_f],
+    'gp_sumsq_f32': [c_f, c_ll, c_f, c_f, c_f],
+    'gp_adam_step_f32': [c_f, c_f, c_f, c_f, c_ll, C.c_float, C.c_float, C.c_float, C.c_float, c_f, c_f, C.c_float, c_f],
     'gp_nb_stats': [c_f, c_i, c_f, c_f],
     'gp_mul_add_dev': [c_f, c_f, c_f, c_f, c_f, c_f],
     'gp_add_scaled': [c_f, c_f, C.c_float, c_f, c_f],

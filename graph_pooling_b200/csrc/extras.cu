@@ -312,3 +312,77 @@ extern "C" int gp_mul_add_dev(const float* a, const float* b, const float* c, fl
   GP_LAUNCHED();
   return GP_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Optimiser step of train.py:209-210 over FLAT buffers: clip_grad_norm(max_norm) folded into Adam (lr, betas, eps;
+// no weight decay, no amsgrad -- torch.optim.Adam's defaults, train.py:173).  Deterministic two-stage norm, the step
+// counter lives on the device (CUDA-graph friendly), one pass over p / g / m / v.
+// ---------------------------------------------------------------------------------------------------------
+namespace gp {
+__global__ void sumsq_stage1(const float* __restrict__ g, long long n, float* __restrict__ part) {
+  __shared__ double shd[256];
+  double s = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double v = g[i];
+    s += v * v;
+  }
+  shd[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) shd[threadIdx.x] += shd[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[blockIdx.x] = (float)shd[0];
+}
+__global__ void sumsq_stage2(const float* __restrict__ part, int nparts, float* __restrict__ out) {
+  __shared__ double shd[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x) s += (double)part[i];
+  shd[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) shd[threadIdx.x] += shd[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = (float)shd[0];
+}
+__global__ void adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                 float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
+                                 const float* __restrict__ step_dev, const float* __restrict__ sumsq, float max_norm) {
+  const float t = *step_dev + 1.f;
+  float coef = 1.f;
+  if (max_norm > 0.f && sumsq != nullptr) coef = fminf(1.f, max_norm / (sqrtf(*sumsq) + 1e-6f));
+  const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
+  const float step_size = lr / bc1, rs2 = rsqrtf(bc2);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * coef;
+    const float mi = m[i] + (gi - m[i]) * (1.f - b1);             // exp_avg.lerp_(grad, 1 - beta1)
+    const float vi = v[i] * b2 + gi * gi * (1.f - b2);
+    m[i] = mi; v[i] = vi;
+    p[i] -= step_size * mi / (sqrtf(vi) * rs2 + eps);
+  }
+}
+__global__ void bump_kernel(float* step_dev) { *step_dev += 1.f; }
+}  // namespace gp
+
+extern "C" int gp_sumsq_f32(const float* g, long long n, float* out, float* ws, gp_stream_t stream) {
+  GP_REQUIRE(g && out && ws && n > 0, "sumsq: bad args (ws: 1024 floats)");
+  const int blocks = grid_for(n, 256 * 8) > 1024 ? 1024 : grid_for(n, 256 * 8);
+  gp::sumsq_stage1<<<blocks, 256, 0, S(stream)>>>(g, n, ws);
+  GP_LAUNCHED();
+  gp::sumsq_stage2<<<1, 256, 0, S(stream)>>>(ws, blocks, out);
+  GP_LAUNCHED();
+  return GP_OK;
+}
+
+extern "C" int gp_adam_step_f32(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
+                                float beta2, float eps, float* step_dev, const float* sumsq_dev, float max_norm,
+                                gp_stream_t stream) {
+  GP_REQUIRE(p && g && m && v && step_dev && n > 0, "adam_step: bad args");
+  gp::adam_flat_kernel<<<grid_for(n, 256 * 4), 256, 0, S(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, step_dev,
+                                                                      sumsq_dev, max_norm);
+  GP_LAUNCHED();
+  gp::bump_kernel<<<1, 1, 0, S(stream)>>>(step_dev);
+  GP_LAUNCHED();
+  return GP_OK;
+}

@@ -75,6 +75,51 @@ class FlatGradients:
         return norm
 
 
+class FlatAdam:
+    """train.py:209-210 (clip_grad_norm + Adam.step) as TWO kernels of this library over flat buffers: parameters are
+    re-pointed to views of one flat tensor (state_dict / .parameters() keep working), gradients live in a
+    FlatGradients buffer, and gp_adam_step_f32 applies the clip coefficient and torch.optim.Adam's update (lr,
+    betas, eps; no weight decay / amsgrad -- train.py:173) in one pass.  The step counter is a device scalar, so the
+    whole optimiser step can sit inside a captured CUDA graph.  An all-reduce of `grads.flat` (data parallel) goes
+    between backward() and step()."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, clip=2.0, grads=None):
+        from ._lib import call
+        self._call = call
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params or not self.params[0].is_cuda:
+            raise ValueError('FlatAdam needs CUDA parameters')
+        self.lr, self.betas, self.eps, self.clip = float(lr), betas, float(eps), clip
+        dev = self.params[0].device
+        n = sum(p.numel() for p in self.params)
+        self.flat_p = torch.empty(n, device=dev, dtype=torch.float32)
+        off = 0
+        with torch.no_grad():
+            for p in self.params:
+                k = p.numel()
+                self.flat_p[off:off + k].copy_(p.data.reshape(-1))
+                p.data = self.flat_p[off:off + k].view_as(p)
+                off += k
+        self.grads = grads if grads is not None else FlatGradients(self.params)
+        self.m = torch.zeros(n, device=dev)
+        self.v = torch.zeros(n, device=dev)
+        self.step_dev = torch.zeros(1, device=dev)
+        self.sumsq = torch.zeros(1, device=dev)
+        self._ws = torch.empty(1024, device=dev)
+
+    def step(self):
+        import ctypes as C
+        st = torch.cuda.current_stream().cuda_stream
+        g = self.grads.flat
+        n = C.c_longlong(g.numel())
+        clip = float(self.clip) if self.clip is not None else 0.0
+        if clip > 0:
+            self._call('gp_sumsq_f32', g.data_ptr(), n, self.sumsq.data_ptr(), self._ws.data_ptr(), st)
+        self._call('gp_adam_step_f32', self.flat_p.data_ptr(), g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), n,
+                   C.c_float(self.lr), C.c_float(self.betas[0]), C.c_float(self.betas[1]), C.c_float(self.eps),
+                   self.step_dev.data_ptr(), self.sumsq.data_ptr() if clip > 0 else None, C.c_float(clip), st)
+
+
 class DataParallelTrainer:
     """Runs train.py:196-210 (zero_grad -> forward -> loss -> backward -> clip -> optimizer step) on this rank's
     shard and synchronises gradients with one all-reduce.  `model` is one of the drop-in encoders (or any module

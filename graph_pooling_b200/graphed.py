@@ -26,9 +26,10 @@ class GraphedTrainStep:
     def __init__(self, model, lr=1e-3, clip=2.0, linkpred=True, warmup=3):
         self.model, self.clip, self.linkpred, self.warmup = model, clip, linkpred, warmup
         self.params = [p for p in model.parameters() if p.requires_grad]
-        # capturable Adam keeps its step counter on the device (train.py:173: Adam, lr hard-coded 0.001)
-        self.optimizer = torch.optim.Adam(self.params, lr=lr, capturable=True)
-        self.grads = dp.FlatGradients(self.params)
+        # clip + Adam as two kernels of this library over flat buffers; the step counter lives on the device
+        # (train.py:173: Adam, lr hard-coded 0.001; train.py:209: clip_grad_norm)
+        self.optimizer = dp.FlatAdam(self.params, lr=lr, clip=clip)
+        self.grads = self.optimizer.grads
         self.soft = hasattr(model, 'num_pooling')
         self._graphs = {}
         self.replayed_launches = 0           # kernels of this library executed through graph replays
@@ -45,9 +46,7 @@ class GraphedTrainStep:
             yp = m(st['x'], st['adj'], st['nb'])
             loss = m.loss(yp, st['label'])
         loss.backward()
-        if self.clip is not None:
-            self.grads.clip_(self.clip)
-        self.optimizer.step()
+        self.optimizer.step()                    # clip_grad_norm folded into the Adam kernel
         return yp, loss
 
     def _capture(self, key, x, adj, label, assign_x):
@@ -81,12 +80,9 @@ class GraphedTrainStep:
         with torch.no_grad():
             for p, s in zip(self.params, snapshot):
                 p.copy_(s)
-        for p in self.params:
-            stt = self.optimizer.state.get(p)
-            if stt:
-                stt['step'].zero_()
-                stt['exp_avg'].zero_()
-                stt['exp_avg_sq'].zero_()
+        self.optimizer.m.zero_()
+        self.optimizer.v.zero_()
+        self.optimizer.step_dev.zero_()
         from ._lib import load
         g = torch.cuda.CUDAGraph()
         n0 = int(load().gp_launch_count())

@@ -353,6 +353,14 @@ int gp_add_scaled(const float* base, const float* term, float w, float* total, g
  *   gp_nb_stats     out[0] = 1 / sum_b nb[b]^2 (encoders.py:1326) ; out[1] = 1 / sum_b nb[b]
  *   gp_mul_add_dev  prod = (*a) * (*b) ; total = (c ? *c : 0) + prod      (all device scalars; outputs optional) */
 int gp_nb_stats(const int32_t* nb, int B, float* out, gp_stream_t stream);
+/* Optimiser step of train.py:209-210 over flat buffers (dp.FlatAdam):
+ *   gp_sumsq_f32      *out = sum_i g[i]^2 (deterministic two-stage; ws: 1024 floats)
+ *   gp_adam_step_f32  clip_grad_norm folded into Adam: g' = g * min(1, max_norm / (sqrt(*sumsq) + 1e-6)) (skipped when
+ *                     max_norm <= 0 or sumsq == NULL); torch.optim.Adam's update with t = *step_dev + 1 (no weight
+ *                     decay, no amsgrad); then *step_dev += 1.  step_dev: device float counter (CUDA-graph friendly). */
+int gp_sumsq_f32(const float* g, long long n, float* out, float* ws, gp_stream_t stream);
+int gp_adam_step_f32(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                     float eps, float* step_dev, const float* sumsq_dev, float max_norm, gp_stream_t stream);
 int gp_mul_add_dev(const float* a, const float* b, const float* c, float* total, float* prod, gp_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------

@@ -48,3 +48,29 @@ def test_global_norm_shard_loss_and_flat_gradients():
     for p in tr.grads.params:
         assert p.grad.data_ptr() == tr.grads.flat.data_ptr() + off * 4
         off += p.numel()
+
+
+def test_flat_adam_matches_torch_adam_with_clipping():
+    """dp.FlatAdam (gp_sumsq_f32 + gp_adam_step_f32 over flat buffers) == clip_grad_norm_(2.0) + torch.optim.Adam."""
+    import copy
+    import torch
+    from graph_pooling_b200 import dp
+    torch.manual_seed(0)
+    shapes = [(30, 17), (17,), (5, 5, 3), (1,)]
+    pa = [torch.nn.Parameter(torch.randn(s, device='cuda')) for s in shapes]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    ref = torch.optim.Adam(pb, lr=1e-2)
+    opt = dp.FlatAdam(pa, lr=1e-2, clip=2.0)
+    for it in range(6):
+        gs = [torch.randn(s, device='cuda') * (3.0 if it % 2 else 0.05) for s in shapes]   # clipped / not clipped
+        opt.grads.zero()
+        for p, q, g in zip(pa, pb, gs):
+            p.grad.copy_(g)
+            q.grad = g.clone()
+        torch.nn.utils.clip_grad_norm_(pb, 2.0)
+        ref.step()
+        opt.step()
+        torch.cuda.synchronize()
+        for p, q in zip(pa, pb):
+            assert torch.allclose(p, q, rtol=2e-5, atol=2e-6), it
+    assert float(opt.step_dev.item()) == 6.0
