@@ -52,6 +52,7 @@ struct Params {
   float* rnorm; float2* rowstat; int stat_relu;                        // EPI == 2
   const int32_t* cond; int cond_npairs; float cond_alpha;              // device-side switch (see gp_gemm_bf16x)
   const int32_t* adj_flags; long long sym_total; int sym_per_graph;    // EPI == 1: gp_adj_prepare flags, upper-band tiles
+  const int32_t* order;                                                // batch permutation (heaviest graph first) or NULL
 };
 
 struct Work {
@@ -168,6 +169,9 @@ __device__ __forceinline__ Work get_work(const Params& p, long long w, int npair
     z = (int)(r / p.tiles_m);
   }
   k.b = z / split; k.ks = z % split;
+  // ragged batches: walk the graphs from the largest to the smallest (order[] = argsort(-n_b)), so the static
+  // round-robin over persistent CTAs deals every CTA the same mix of long and short tiles (longest-first schedule)
+  if (p.order != nullptr) k.b = p.order[k.b];
   k.m0 = mt * BM; k.n0 = nt;        // n0 scaled by BN by the caller
   int l = 0x7fffffff;
   if (p.lim != nullptr) l = p.lim[k.b];
@@ -892,6 +896,7 @@ int run(const gp_gemm_bf16x* g, cudaStream_t st) {
   p.rnorm = nullptr; p.rowstat = nullptr; p.stat_relu = 0;
   p.cond = g->cond; p.cond_npairs = g->cond_npairs; p.cond_alpha = g->cond_alpha;
   p.adj_flags = nullptr; p.sym_total = 0; p.sym_per_graph = 0;
+  p.order = g->order;
   GP_REQUIRE(g->cond == nullptr || (g->cond_npairs >= 0 && g->cond_npairs <= g->npairs), "bgemm_bf16x: bad cond_npairs");
   if (split > 1 && p.beta != 1.f) {
     const long long total = (long long)g->batch * g->M * g->N;
@@ -935,7 +940,7 @@ int run_norm(const gp_gemm_bf16x* g, float* rnorm, float* rowstat, int stat_relu
   p.adjb = nullptr; p.ldadj = p.sadjb = 0; p.partial = nullptr; p.link_mode = 0;
   p.rnorm = rnorm; p.rowstat = reinterpret_cast<float2*>(rowstat); p.stat_relu = stat_relu;
   p.cond = nullptr; p.cond_npairs = 0; p.cond_alpha = 1.f;
-  p.adj_flags = nullptr; p.sym_total = 0; p.sym_per_graph = 0;
+  p.adj_flags = nullptr; p.sym_total = 0; p.sym_per_graph = 0; p.order = nullptr;
   if (BN == 512) return launch<512, 2, 2, 4>(maps, p, st);
   if (BN == 256) return launch<256, 3, 2, 4>(maps, p, st);
   return launch<128, 4, 2, 4>(maps, p, st);
@@ -962,7 +967,7 @@ int run_linkloss(const void* s_bf16, long long lds, const void* adj_bf16, long l
   p.partial = partial; p.link_mode = mode;
   p.rnorm = nullptr; p.rowstat = nullptr; p.stat_relu = 0;
   p.cond = nullptr; p.cond_npairs = 0; p.cond_alpha = 1.f;
-  p.adj_flags = adj_flags;
+  p.adj_flags = adj_flags; p.order = nullptr;
   {
     const int tm = (N + BM - 1) / BM, tn = (N + 255) / 256;
     int per = 0;

@@ -258,5 +258,13 @@ def prep_nb(batch_num_nodes, N, device):
         raise ValueError('batch_num_nodes must be 1-D')
     if host.size and (host.min() < 0 or host.max() > N):
         raise ValueError('batch_num_nodes out of range [0, %d]' % N)
-    dev = torch.from_numpy(host).pin_memory().to(device, non_blocking=True)
+    # one small pinned transfer: [n_b | argsort(-n_b)] -- the second half lets the persistent GEMMs walk ragged
+    # batches from the largest graph to the smallest (balanced static schedule)
+    both = np.concatenate([host, np.argsort(-host.astype(np.int64), kind='stable').astype(np.int32)])
+    both_dev = torch.from_numpy(both).pin_memory().to(device, non_blocking=True)
+    dev, order = both_dev[:host.size], both_dev[host.size:]
+    if host.size and int(host.min()) != int(host.max()):
+        from . import engine_tc
+        engine_tc.register_order(dev, order)
+        dev._gp_order = order                       # keep the permutation alive as long as the node counts
     return dev, host

@@ -53,6 +53,19 @@ def adj_prepare(ws, adj, nb, B, N):
     return out, flags
 
 
+# device pointer of a node-count vector -> (argsort(-n_b) on the device, batch size), registered by engine.prep_nb for
+# host-side node counts.  The entry holds the permutation tensor -- which shares its storage with the node counts --
+# so the key address cannot be reused while the entry exists.  Batched contractions clipped by that vector walk the
+# graphs longest-first; any permutation is a valid schedule, so a stale entry of the same length is harmless.
+_ORDER = {}
+
+
+def register_order(nb_dev, order_dev):
+    if len(_ORDER) > 64:
+        _ORDER.clear()
+    _ORDER[nb_dev.data_ptr()] = (order_dev, int(order_dev.numel()))
+
+
 class PreparedAdjacency:
     """The bf16 adjacency operand of a batch, built by the FEED instead of by the module: accepted wherever the
     encoders (tensor-core mode) take `adj`.  A batch may be assembled from parts that reached the device in different
@@ -109,6 +122,8 @@ def tcgemm_multi(pairs, M, N, batch, Cf=None, Cb=None, lim=None, lim_m=0, lim_n=
     g.alpha, g.beta, g.alpha_dev = alpha, beta, alpha_dev
     g.bias, g.relu, g.split_k = bias, relu, split_k
     g.cond, g.cond_npairs, g.cond_alpha = cond, cond_npairs, cond_alpha
+    ent = _ORDER.get(lim) if lim is not None else None
+    g.order = ent[0].data_ptr() if (ent is not None and ent[1] == batch) else None   # longest-first walk (ragged)
     call('gp_bgemm_bf16x', C.byref(g), E._stream())
 
 
@@ -155,6 +170,7 @@ def _norm_gemm(A, Bo, M, N, K, bias, Cf, Cb, rnorm, rowstat, stat_relu):
     g.alpha, g.beta, g.alpha_dev = 1.0, 0.0, None
     g.bias, g.relu, g.split_k = bias, 0, 0
     g.cond, g.cond_npairs, g.cond_alpha = None, 0, 1.0
+    g.order = None
     call('gp_bgemm_bf16_norm', C.byref(g), rnorm, rowstat, int(stat_relu), E._stream())
 
 

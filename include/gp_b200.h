@@ -131,6 +131,9 @@ typedef struct gp_gemm_bf16x {
    * no-op (C untouched).  The DiffPool backward passes gp_adj_prepare's "adjacency is not symmetric" flag: for a
    * symmetric A, (G + G^T).S = 2 G.S and T^T dA' + A.(S dA'^T) = T^T (dA' + dA'^T). */
   const int32_t* cond; int cond_npairs; float cond_alpha;
+  /* optional device permutation of the batch index (e.g. argsort(-nb)): ragged batches are walked from the largest
+   * graph to the smallest, so the static round-robin over persistent CTAs stays balanced (longest-first). */
+  const int32_t* order;
 } gp_gemm_bf16x;
 int gp_bgemm_bf16x(const gp_gemm_bf16x* g, gp_stream_t stream);
 /* Fused GraphConv tail on tensor cores (encoders.py:322-326): one operand pair, batch == 1, N <= 256:
