@@ -41,8 +41,9 @@ enum gp_status {
 /* precision of the dense contractions */
 enum gp_precision {
   GP_F32 = 0,    /* fp32 FFMA everywhere (parity anchor, <=1e-5 relative)                       */
-  GP_BF16 = 1,   /* bf16 operands on tcgen05 tensor cores, fp32 accumulation in TMEM             */
-  GP_BF16X2 = 2  /* {0,1} adjacency exact in bf16; real operand split hi+lo (2 MMAs) ~ fp32     */
+  GP_BF16 = 1    /* bf16 operands on tcgen05 tensor cores, fp32 accumulation in TMEM             */
+  /* (a split-operand mode -- {0,1} adjacency exact in bf16, real operands as hi+lo pairs accumulated through the
+   * multi-pair GEMM for ~fp32 accuracy on tensor cores -- is NOT implemented in this round) */
 };
 
 int gp_version(void);
