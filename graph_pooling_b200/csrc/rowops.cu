@@ -349,8 +349,10 @@ __global__ void layer_bwd_split_apply_kernel(const LbG a, int bs, const float* _
 // ---------------------------------------------------------------------------------------------
 // Max readout over nodes: block = 32 feature lanes x 8 row groups.
 // ---------------------------------------------------------------------------------------------
+// N = rows scanned per graph, pitch = rows between consecutive graphs in memory (>= N; rows [N, pitch) do not exist
+// for the readout: dead clusters of a padded assignment width, gp_readout_max_fwd_x).
 __global__ void readout_max_kernel(const float* __restrict__ z, long long ldz, const int32_t* __restrict__ nb,
-                                   int N, int F, float* __restrict__ out, int32_t* __restrict__ argidx,
+                                   int N, int pitch, int F, float* __restrict__ out, int32_t* __restrict__ argidx,
                                    long long ldo) {
   __shared__ float sv[8][33];
   __shared__ int si[8][33];
@@ -360,7 +362,7 @@ __global__ void readout_max_kernel(const float* __restrict__ z, long long ldz, c
   float best = -INFINITY;
   int bi = -1;
   if (f < F) {
-    const float* p = z + (long long)b * N * ldz + f;
+    const float* p = z + (long long)b * pitch * ldz + f;
     for (int n = threadIdx.y; n < nreal; n += 8) {
       const float v = p[(long long)n * ldz];
       if (v > best) { best = v; bi = n; }      // strict: lowest index kept within this thread
@@ -499,6 +501,23 @@ __global__ void relu_mask_bwd_kernel(const float* __restrict__ dy, const float* 
 __global__ void fill_kernel(float* __restrict__ x, long long n, float v) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     x[i] = v;
+}
+__global__ void fill_i32_kernel(int32_t* __restrict__ x, long long n, int32_t v) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    x[i] = v;
+}
+// dst [rows_dst, cols_dst] (row stride ld_dst) = src [rows, cols] (row stride ld_src) in the top-left corner, `fill`
+// elsewhere
+__global__ void pad_copy_kernel(const float* __restrict__ src, long long ld_src, long long rows, int cols,
+                                float* __restrict__ dst, long long ld_dst, long long rows_dst, int cols_dst,
+                                float fill) {
+  const long long total = rows_dst * cols_dst;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols_dst;
+    const int c = (int)(i - r * cols_dst);
+    dst[r * ld_dst + c] = (r < rows && c < cols) ? src[r * ld_src + c] : fill;
+  }
 }
 __global__ void axpy_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float a) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -673,7 +692,17 @@ extern "C" int gp_readout_max_fwd(const float* z, long long ldz, const int32_t* 
   GP_REQUIRE(z && out && argidx && B > 0 && N > 0 && F > 0, "readout_max_fwd: bad args");
   GP_REQUIRE(B <= 65535, "readout_max_fwd: B too large");
   dim3 grid((F + 31) / 32, B), block(32, 8);
-  readout_max_kernel<<<grid, block, 0, S(stream)>>>(z, ldz, nb, N, F, out, argidx, ldo);
+  readout_max_kernel<<<grid, block, 0, S(stream)>>>(z, ldz, nb, N, N, F, out, argidx, ldo);
+  GP_LAUNCHED();
+  return GP_OK;
+}
+
+extern "C" int gp_readout_max_fwd_x(const float* z, long long ldz, int pitch, const int32_t* nb, int B, int N, int F,
+                                    float* out, int32_t* argidx, long long ldo, gp_stream_t stream) {
+  GP_REQUIRE(z && out && argidx && B > 0 && N > 0 && F > 0 && pitch >= N, "readout_max_fwd_x: bad args");
+  GP_REQUIRE(B <= 65535, "readout_max_fwd_x: B too large");
+  dim3 grid((F + 31) / 32, B), block(32, 8);
+  readout_max_kernel<<<grid, block, 0, S(stream)>>>(z, ldz, nb, N, pitch, F, out, argidx, ldo);
   GP_LAUNCHED();
   return GP_OK;
 }
@@ -739,6 +768,26 @@ extern "C" int gp_fill_f32(float* x, long long n, float v, gp_stream_t stream) {
   long long blocks = (n + 255) / 256;
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
   fill_kernel<<<(int)blocks, 256, 0, S(stream)>>>(x, n, v);
+  GP_LAUNCHED();
+  return GP_OK;
+}
+
+extern "C" int gp_fill_i32(int32_t* x, long long n, int32_t v, gp_stream_t stream) {
+  GP_REQUIRE(x && n > 0, "fill_i32: bad args");
+  long long blocks = (n + 255) / 256;
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  fill_i32_kernel<<<(int)blocks, 256, 0, S(stream)>>>(x, n, v);
+  GP_LAUNCHED();
+  return GP_OK;
+}
+
+extern "C" int gp_pad_copy_f32(const float* src, long long ld_src, long long rows, int cols, float* dst,
+                               long long ld_dst, long long rows_dst, int cols_dst, float fill, gp_stream_t stream) {
+  GP_REQUIRE(src && dst && rows > 0 && cols > 0 && rows_dst >= rows && cols_dst >= cols && ld_src >= cols &&
+             ld_dst >= cols_dst, "pad_copy: bad args");
+  long long blocks = (rows_dst * cols_dst + 255) / 256;
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  pad_copy_kernel<<<(int)blocks, 256, 0, S(stream)>>>(src, ld_src, rows, cols, dst, ld_dst, rows_dst, cols_dst, fill);
   GP_LAUNCHED();
   return GP_OK;
 }

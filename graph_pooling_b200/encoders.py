@@ -40,6 +40,14 @@ def _wb(params, pair):
     return params[iw], (None if ib is None else params[ib])
 
 
+def _kpad(K):
+    """Cluster count the tensor-core schedule runs a pooling level at: K rounded up to a multiple of 8 so that every
+    row of S / the assignment concat / A' is 16-byte aligned (TMA and vector paths).  The extra clusters are DEAD: zero
+    weights, logit bias -1e30 => probability exactly 0, zero rows / columns of X' and A', excluded from the next
+    level's readout and masked like pad nodes in its assignment.  GP_NO_KPAD=1 disables it (debug)."""
+    return K if os.environ.get('GP_NO_KPAD') else T.r8(K)
+
+
 def _fwd_tc(ctx, plan, x, adj, assign_x, params):
     """GP_BF16 forward: same schedule as _EncoderFn.forward with the contractions on tcgen05."""
     st = E._stream()
@@ -65,42 +73,57 @@ def _fwd_tc(ctx, plan, x, adj, assign_x, params):
         wa0, ba0 = conv(plan.assign[0])
         dual = T.dual_ok(w0, wa0) and not os.environ.get('GP_NO_DUAL')
     if dual:        # embedding + level-0 assignment GCN in lock-step: one pass over A per layer for both
+        K0 = plan.assign_dims[0]
         (z, zb, c_emb), pre_as = T.dual_stack_forward(ws, xb, D, xab, xa_d, adjb, nb, B, N, w0, b0, plan.bn, wa0, ba0,
-                                                      True)
+                                                      True, pad_lastA=_kpad(K0) if _kpad(K0) != K0 else 0)
     else:
         z, zb, c_emb = T.stack_forward(ws, xb, D, adjb, nb, B, N, w0, b0, plan.bn)
     call('gp_readout_max_fwd', z.data_ptr(), Fw, E._p(nb) if plan.soft else None, B, N, Fw,
          out.data_ptr(), arg.data_ptr(), ldo, st)
     levels, S0 = [], None
-    plan.adjb, plan.sb0, plan.asym, plan.adj_flags = adjb, None, aflags[0:1], aflags
+    plan.adjb, plan.sb0, plan.asym, plan.adj_flags, plan.S0_full = adjb, None, aflags[0:1], aflags, None
+    vis_S = []
     if plan.soft:
-        cur_adjb, cur_nb, cur_N, cur_zb = adjb, nb, N, zb
+        # cur_N rows are allocated per graph at this level, of which cur_Nr exist (cur_N > cur_Nr: dead clusters of a
+        # padded level above, masked through cur_nb like pad nodes)
+        cur_adjb, cur_nb, cur_N, cur_Nr, cur_zb = adjb, nb, N, N, zb
         for i in range(P):
-            K = plan.assign_dims[i]
+            Kr = plan.assign_dims[i]
+            K = _kpad(Kr)                                # width this level runs at (dead clusters beyond Kr)
+            pad = K if K != Kr else 0
             wa, ba = conv(plan.assign[i])
             if i == 0 and pre_as is not None:
                 za, zab, c_as = pre_as
             else:
                 # level 0 with assign_x == x: both GCNs start from the same U = A.x -- compute it once
                 u0 = c_emb.layers[0][4] if (i == 0 and xab is xb) else None
-                za, zab, c_as = T.stack_forward(ws, xab, xa_d, cur_adjb, cur_nb, B, cur_N, wa, ba, True, u0=u0)
+                za, zab, c_as = T.stack_forward(ws, xab, xa_d, cur_adjb, cur_nb, B, cur_N, wa, ba, True, u0=u0,
+                                                pad_last=pad)
             Fa = za.shape[2]
             wp, bp = _wb(params, plan.assign_pred[i])
-            Tl, wpb = T.assign_linear_fwd(ws, zab, Fa, B * cur_N, wp, bp)
+            Tl, wpb = T.assign_linear_fwd(ws, zab, Fa, B * cur_N, wp, bp, Kp=pad)
             S = Tl.view(B, cur_N, K)
             sb = T.softmax_forward(ws, S, cur_nb, B, cur_N, K)
             sb, xp, xpb, tb, ap, apb = T.pool_forward(ws, sb, cur_zb, cur_adjb, cur_nb, B, cur_N, K, Fw)
             wq, bq = conv(plan.post[i])
-            z2, z2b, c_post = T.stack_forward(ws, xpb, Fw, apb, None, B, K, wq, bq, plan.bn_post)
-            call('gp_readout_max_fwd', z2.data_ptr(), Fw, None, B, K, Fw, out.data_ptr() + (i + 1) * Fw * 4,
+            nbk = None
+            if pad:                                      # "node counts" of the pooled level: Kr real clusters of K
+                nbk = ws.i(B)
+                call('gp_fill_i32', nbk.data_ptr(), C.c_longlong(B), Kr, st)
+            z2, z2b, c_post = T.stack_forward(ws, xpb, Fw, apb, nbk, B, K, wq, bq, plan.bn_post)
+            # the reference's max over the pooled level's clusters (encoders.py:1287): the Kr real rows only
+            call('gp_readout_max_fwd_x', z2.data_ptr(), Fw, K, None, B, Kr, Fw, out.data_ptr() + (i + 1) * Fw * 4,
                  arg.data_ptr() + (i + 1) * Fw * 4, ldo, st)
-            levels.append(dict(K=K, N=cur_N, nb=cur_nb, adjb=cur_adjb, zb=cur_zb, S=S.detach(), sb=sb, zab=zab, Fa=Fa,
-                               c_as=c_as, tb=tb, c_post=c_post, wpb=wpb, has_bp=bp is not None,
-                               asym=plan.asym if i == 0 else None))
+            levels.append(dict(K=K, Kr=Kr, N=cur_N, nb=cur_nb, adjb=cur_adjb, zb=cur_zb, S=S.detach(), sb=sb, zab=zab,
+                               Fa=Fa, Fa_r=int(wp.shape[1]), c_as=c_as, tb=tb, c_post=c_post, wpb=wpb,
+                               has_bp=bp is not None, asym=plan.asym if i == 0 else None))
+            Sv = S if (K == Kr and cur_N == cur_Nr) else S[:, :cur_Nr, :Kr]     # what the caller sees: real rows / clusters
+            vis_S.append(Sv)
             if i == 0:
-                S0, plan.sb0 = S, sb
+                S0, plan.sb0 = Sv, sb
+                plan.S0_full = S.detach() if pad else None
             xab, xa_d = xpb, Fw
-            cur_adjb, cur_nb, cur_N, cur_zb = apb, None, K, z2b
+            cur_adjb, cur_nb, cur_N, cur_Nr, cur_zb = apb, nbk, K, Kr, z2b
     lin = [_wb(params, p) for p in plan.pred]
     ypred, acts = E.mlp_fwd(ws, out.data_ptr(), ldo, B, lin)
     ctx.tape = dict(plan=plan, params=params, B=B, N=N, emb=c_emb, levels=levels, out=out, arg=arg, ldo=ldo,
@@ -108,9 +131,24 @@ def _fwd_tc(ctx, plan, x, adj, assign_x, params):
     if plan.soft:
         # detached aliases: the tape holds `plan` and the returned S0 gets this node as grad_fn; storing S0
         # itself would close a reference cycle through the autograd node that only backward() breaks
-        plan.all_S = [lv['S'].detach() for lv in levels]
+        plan.all_S = [v.detach() for v in vis_S]
         return ypred, S0
     return ypred
+
+
+def _padded_grad(ws, plan, dS0, B, N, Kr, K):
+    """Gradient of the visible S0 [B,N,Kr] as a [B,N,K] buffer (K = padded width).  _LossFn hands back a narrowed view
+    of its own padded buffer (tagged in plan.ds_tag): that buffer is used in place; anything else is copied."""
+    if K == Kr:
+        return E._chk(dS0, 'grad of assign_tensor')
+    if dS0.is_cuda and dS0.dtype == torch.float32 and dS0.data_ptr() == getattr(plan, 'ds_tag', None) \
+            and tuple(dS0.stride()) == (N * K, K, 1):
+        return torch.as_strided(dS0, (B, N, K), (N * K, K, 1))
+    src = E._chk(dS0, 'grad of assign_tensor')
+    out = ws.f(B, N, K)
+    call('gp_pad_copy_f32', src.data_ptr(), C.c_longlong(Kr), C.c_longlong(B * N), Kr, out.data_ptr(),
+         C.c_longlong(K), C.c_longlong(B * N), K, C.c_float(0.0), E._stream())
+    return out
 
 
 def _bwd_tc(ctx, tape, dypred, dS0):
@@ -151,13 +189,13 @@ def _bwd_tc(ctx, tape, dypred, dS0):
                 call('gp_axpy_f32', dxp_extra[i].data_ptr(), dxp.data_ptr(), C.c_longlong(dxp.numel()),
                      C.c_float(1.0), st)
             if i == 0 and dS0 is not None:
-                ds, acc_ds = E._chk(dS0, 'grad of assign_tensor'), 1
+                ds, acc_ds = _padded_grad(ws, plan, dS0, B, Ni, lv['Kr'], K), 1
             else:
                 ds, acc_ds = ws.f(B, Ni, K), 0
             dz = T.pool_backward(ws, dxp, d_ap[i], lv['sb'], lv['zb'], lv['adjb'], lv['tb'], lv['nb'], B, Ni, K, Fw,
                                  ds, acc_ds, None if i == 0 else d_ap[i - 1], asym=lv['asym'])
             dwp, dbp, dza = T.assign_head_bwd(ws, lv['S'], ds, lv['nb'], B, Ni, lv['zab'], lv['Fa'], lv['wpb'], K,
-                                              lv['has_bp'])
+                                              lv['has_bp'], Kreal=lv['Kr'], Fa_real=lv['Fa_r'])
             iw, ib = plan.assign_pred[i]
             grads[iw] = dwp
             if ib is not None:
@@ -358,8 +396,14 @@ class _LossFn(torch.autograd.Function):
         if S is None or (link_kind is None and ent_w == 0.0):
             ctx.link_kind, ctx.ent_w = None, 0.0
             return (ce.view(()),)
+        # tensor-core mode with a padded cluster count: the kernels see the full [B,N,Kp] buffer (dead columns are 0),
+        # the caller's S is its first K columns
+        ctx.Kvis = S.shape[2]
+        if getattr(plan, 'S_full', None) is not None:
+            S = plan.S_full
         Bn, N, K = S.shape
         need_grad = ctx.needs_input_grad[3]
+        ctx.enc_plan = getattr(plan, 'enc_plan', None)
         ctx.sb = getattr(plan, 'sb0', None)
         ctx.asym = getattr(plan, 'asym', None)
         ctx.S, ctx.nb, ctx.gsym = S, plan.nb_dev, None
@@ -461,6 +505,10 @@ class _LossFn(torch.autograd.Function):
                 dS = ws.f(Bn, N, K)
             call('gp_entropy_bwd', S.data_ptr(), E._p(ctx.nb), Bn, N, K, g.data_ptr(), C.c_float(ctx.ent_scale),
                  dS.data_ptr(), int(acc), st)
+        if dS is not None and dS.shape[2] != ctx.Kvis:
+            if ctx.enc_plan is not None:
+                ctx.enc_plan.ds_tag = dS.data_ptr()      # _padded_grad recognises the buffer and uses it in place
+            dS = dS[:, :, :ctx.Kvis]
         return None, dy, None, dS, None
 
 
@@ -797,6 +845,8 @@ class SoftPoolingGcnEncoder(GcnEncoderGraph):
         lp.adjb = getattr(plan, 'adjb', None)
         lp.asym = getattr(plan, 'asym', None)
         lp.adj_flags = getattr(plan, 'adj_flags', None)
+        lp.S_full = getattr(plan, 'S0_full', None)
+        lp.enc_plan = plan
         lp.ce_scale = self._ce_scale
         lp.ent_w = ent_w
         lp.link_kind = self.link_loss_kind if self.linkpred else None

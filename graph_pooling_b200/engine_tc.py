@@ -174,12 +174,19 @@ def _norm_gemm(A, Bo, M, N, K, bias, Cf, Cb, rnorm, rowstat, stat_relu):
     call('gp_bgemm_bf16_norm', C.byref(g), rnorm, rowstat, int(stat_relu), E._stream())
 
 
-def _stack_begin(ws, xb, din, adjb, nb, B, N, weights, biases, bn):
+def _stack_begin(ws, xb, din, adjb, nb, B, N, weights, biases, bn, pad_last=0):
+    """pad_last: run the LAST layer at this width (> its weight's column count): the extra output columns have zero
+    weights and zero bias, so they are exact zeros everywhere (V = 0, Y = 0/||V|| = 0, dV = 0) and every buffer of the
+    stack keeps 16-byte-aligned rows.  Used for assignment GCNs whose cluster count K is not a multiple of 8."""
     L = len(weights)
-    douts = [int(w.shape[1]) for w in weights]
+    wcols = [int(w.shape[1]) for w in weights]
+    douts = list(wcols)
+    if pad_last:
+        douts[-1] = int(pad_last)
     Fw = sum(douts)
     ctx = StackCtxTC()
     ctx.B, ctx.N, ctx.douts, ctx.F, ctx.adjb, ctx.nb, ctx.bn = B, N, douts, Fw, adjb, nb, bn
+    ctx.wcols = wcols
     ctx.weights, ctx.biases, ctx.layers = weights, biases, []
     ctx.zcat = ws.f(B, N, Fw)
     ctx.zb = bfbuf(ws, B, N, Fw)
@@ -202,7 +209,14 @@ def _layer_forward(ws, ctx, l, ub, hb2=None):
     w = ctx.weights[l]
     rows = B * N
     zp = ctx.zcat.data_ptr()
-    wb = cvt(ws, w.data_ptr(), dout, cur_d, dout)                                   # [din, r8(dout)]
+    wc = ctx.wcols[l]
+    wb = cvt(ws, w.data_ptr(), wc, cur_d, wc)                                       # [din, r8(wc)], zero pad columns
+    bias_p = E._p(ctx.biases[l])
+    if wc != dout and bias_p is not None:                                           # padded last layer: zero bias beyond wc
+        bpad = ws.f(dout)
+        call('gp_pad_copy_f32', bias_p, C.c_longlong(wc), C.c_longlong(1), wc, bpad.data_ptr(), C.c_longlong(dout),
+             C.c_longlong(1), dout, C.c_float(0.0), st)
+        bias_p = bpad.data_ptr()
     slot = zp + off * 4
     # bf16 operand copy of this layer's output: a column slot of zb when 16-byte aligned, else its own buffer
     hb = Op(zb.ptr + off * 2, zb.ld, zb.sb, zb.t) if ctx.aligned else bfbuf(ws, B, N, dout)
@@ -218,7 +232,7 @@ def _layer_forward(ws, ctx, l, ub, hb2=None):
     mean = invstd = None
     if dout <= 512:                                      # rows up to 512 wide stay in TMEM for the fused tail
         rowstat = ws.f(rows, 2) if use_bn else None
-        _norm_gemm(uflat, wflat, rows, dout, cur_d, E._p(ctx.biases[l]), (y_ptr, ldy, 0), hb_flat if last else None,
+        _norm_gemm(uflat, wflat, rows, dout, cur_d, bias_p, (y_ptr, ldy, 0), hb_flat if last else None,
                    rnorm.data_ptr(), E._p(rowstat), 1)
         if use_bn:
             mean, invstd = ws.f(N), ws.f(N)
@@ -228,7 +242,7 @@ def _layer_forward(ws, ctx, l, ub, hb2=None):
                  hb.ptr, hb.ld, None if hb2 is None else hb2.ptr, 0 if hb2 is None else hb2.ld, st)
     else:
         # wide layer (e.g. the assignment GCN's last layer, dout = K): plain GEMM, then one normalize pass
-        tcgemm(uflat, KM, wflat, MN, rows, dout, cur_d, 1, Cf=(y_ptr, ldy, 0), bias=E._p(ctx.biases[l]))
+        tcgemm(uflat, KM, wflat, MN, rows, dout, cur_d, 1, Cf=(y_ptr, ldy, 0), bias=bias_p)
         yb_ok = dout % 4 == 0 and dout <= 1024 and ldy % 4 == 0
         call('gp_bias_normalize_x', y_ptr, None, rnorm.data_ptr(), C.c_longlong(rows), dout, ldy, 1,
              hb.ptr if (last and yb_ok) else None, hb.ld, st)
@@ -251,12 +265,12 @@ def _stack_end(ws, ctx):
     return ctx.zcat, ctx.zb, ctx
 
 
-def stack_forward(ws, xb, din, adjb, nb, B, N, weights, biases, bn, u0=None):
+def stack_forward(ws, xb, din, adjb, nb, B, N, weights, biases, bn, u0=None, pad_last=0):
     """TC version of engine.stack_forward (add_self unsupported).  xb/adjb: bf16 operands.
     Per layer:  U = A.X (tcgen05)  ->  _layer_forward.
     u0: optional precomputed U of the first layer (shared with another stack that has the same A and X).
     Returns (zcat fp32 [B,N,F], zb bf16 operand of the same concat, ctx)."""
-    ctx = _stack_begin(ws, xb, din, adjb, nb, B, N, weights, biases, bn)
+    ctx = _stack_begin(ws, xb, din, adjb, nb, B, N, weights, biases, bn, pad_last)
     nbp, lim = E._p(nb), int(nb is not None)
     for l in range(len(weights)):
         if l == 0 and u0 is not None:
@@ -281,12 +295,12 @@ def dual_ok(wE, wA):
     return True
 
 
-def dual_stack_forward(ws, xb, din, xab, dina, adjb, nb, B, N, wE, bE, bnE, wA, bA, bnA):
+def dual_stack_forward(ws, xb, din, xab, dina, adjb, nb, B, N, wE, bE, bnE, wA, bA, bnA, pad_lastA=0):
     """Embedding GCN and assignment GCN of one level in lock-step: both multiply the SAME
     adjacency, so layer l's two inputs sit side by side in one [B,N,He+Ha] operand and ONE pass over A produces
     both U's (A.X at 128 columns is HBM-bound on reading A: sharing the pass halves that traffic)."""
     cE = _stack_begin(ws, xb, din, adjb, nb, B, N, wE, bE, bnE)
-    cA = _stack_begin(ws, xab, dina, adjb, nb, B, N, wA, bA, bnA)
+    cA = _stack_begin(ws, xab, dina, adjb, nb, B, N, wA, bA, bnA, pad_lastA)
     nbp, lim = E._p(nb), int(nb is not None)
     L = len(wE)
     hcat = None
@@ -327,6 +341,7 @@ def _layer_backward_head(ws, ctx, l, dz_ptr, lddz, dxn, lddxn, dout_ptr, arg_ptr
     rows = B * N
     slot = ctx.zcat.data_ptr() + off * 4
     dvb = bfbuf(ws, 1, rows, dout)
+    wc = ctx.wcols[l]                                    # < dout for a padded last layer (its dV pad columns are 0)
     has_b = ctx.biases[l] is not None
     db = ws.f(dout) if has_b else None
     q = GpLayerBwd()
@@ -348,9 +363,11 @@ def _layer_backward_head(ws, ctx, l, dz_ptr, lddz, dxn, lddxn, dout_ptr, arg_ptr
     q.ws = E._p(wsf)
     call('gp_gcn_layer_bwd_x', C.byref(q), st)
     # dW = U^T dV : U stored [rows, din] = M-major A ; dV N-major B ; split-K over the rows
-    dw = ws.f(din, dout)
-    tcgemm(Op(ub.ptr, ub.ld, 0), MN, Op(dvb.ptr, dvb.ld, 0), MN, din, dout, rows, 1, Cf=(dw.data_ptr(), dout, 0),
-           split_k=pick_split(din, dout, rows))
+    dw = ws.f(din, wc)
+    tcgemm(Op(ub.ptr, ub.ld, 0), MN, Op(dvb.ptr, dvb.ld, 0), MN, din, wc, rows, 1, Cf=(dw.data_ptr(), wc, 0),
+           split_k=pick_split(din, wc, rows))
+    if has_b and wc != dout:
+        db = db[:wc]
     return dvb, dw, db
 
 
@@ -469,18 +486,39 @@ def pool_backward(ws, dxp, dap, sb, zb, adjb, tb, nb, B, N, K, Fw, ds, acc_ds, d
     return dz
 
 
-def assign_linear_fwd(ws, zab, Fa, rows, wp, bp):
-    K = int(wp.shape[0])
-    wpb = cvt(ws, wp.data_ptr(), Fa, K, Fa)                                             # [K, r8(Fa)]
-    T = ws.f(rows, K)
-    tcgemm(Op(zab.ptr, zab.ld, 0), KM, Op(wpb.ptr, wpb.ld, 0), KM, rows, K, Fa, 1, Cf=(T.data_ptr(), K, 0),
-           bias=E._p(bp))
+def assign_linear_fwd(ws, zab, Fa, rows, wp, bp, Kp=0):
+    """T = za.Wp^T + bp.  Kp > K (padded cluster count): Fa is the padded concat width; the extra rows / columns of
+    the bf16 weight are zero and the extra logits get a bias of -1e30, i.e. probability exactly 0 after the softmax
+    (dead clusters: S, X' = S^T Z and A' = S^T A S only gain zero columns / rows)."""
+    K, Fr = int(wp.shape[0]), int(wp.shape[1])
+    if not Kp or Kp == K:
+        wpb = cvt(ws, wp.data_ptr(), Fa, K, Fa)                                         # [K, r8(Fa)]
+        T = ws.f(rows, K)
+        tcgemm(Op(zab.ptr, zab.ld, 0), KM, Op(wpb.ptr, wpb.ld, 0), KM, rows, K, Fa, 1, Cf=(T.data_ptr(), K, 0),
+               bias=E._p(bp))
+        return T, wpb
+    st = E._stream()
+    wpb = bfbuf(ws, 1, Kp, Fa)
+    call('gp_fill_f32', wpb.ptr, C.c_longlong(Kp * wpb.ld // 2), C.c_float(0.0), st)    # bf16 zeros, two per float
+    cvt(ws, wp.data_ptr(), Fr, K, Fr, out=wpb)
+    bpad = ws.f(Kp)
+    if bp is None:
+        call('gp_fill_f32', bpad.data_ptr(), C.c_longlong(K), C.c_float(0.0), st)
+        call('gp_fill_f32', bpad.data_ptr() + 4 * K, C.c_longlong(Kp - K), C.c_float(-1e30), st)
+    else:
+        call('gp_pad_copy_f32', bp.data_ptr(), C.c_longlong(K), C.c_longlong(1), K, bpad.data_ptr(),
+             C.c_longlong(Kp), C.c_longlong(1), Kp, C.c_float(-1e30), st)
+    T = ws.f(rows, Kp)
+    tcgemm(Op(zab.ptr, zab.ld, 0), KM, Op(wpb.ptr, wpb.ld, 0), KM, rows, Kp, Fa, 1, Cf=(T.data_ptr(), Kp, 0),
+           bias=bpad.data_ptr())
     return T, wpb
 
 
-def assign_head_bwd(ws, S, ds, nb, B, N, zab, Fa, wpb, K, has_bias):
+def assign_head_bwd(ws, S, ds, nb, B, N, zab, Fa, wpb, K, has_bias, Kreal=0, Fa_real=0):
     """Backward of S = softmax(assign_pred(za)) * mask: dT (bf16 operand + bias gradient in one pass), then
-    dWp = dT^T za (split-K) and dza = dT Wp."""
+    dWp = dT^T za (split-K) and dza = dT Wp.  K / Fa may be the padded widths; the parameter gradients are produced
+    at the real ones (Kreal x Fa_real: the real clusters / concat columns come first)."""
+    Kreal, Fa_real = Kreal or K, Fa_real or Fa
     st = E._stream()
     rows = B * N
     dtb = bfbuf(ws, 1, rows, K)
@@ -496,9 +534,11 @@ def assign_head_bwd(ws, S, ds, nb, B, N, zab, Fa, wpb, K, has_bias):
         if has_bias:
             cs = ws.f(256 * K)
             call('gp_colsum_f32', E._p(dt), C.c_longlong(rows), K, C.c_longlong(K), E._p(dbp), 0, E._p(cs), st)
-    dwp = ws.f(K, Fa)
-    tcgemm(Op(dtb.ptr, dtb.ld, 0), MN, Op(zab.ptr, zab.ld, 0), MN, K, Fa, rows, 1, Cf=(dwp.data_ptr(), Fa, 0),
-           split_k=pick_split(K, Fa, rows))
+    dwp = ws.f(Kreal, Fa_real)
+    tcgemm(Op(dtb.ptr, dtb.ld, 0), MN, Op(zab.ptr, zab.ld, 0), MN, Kreal, Fa_real, rows, 1,
+           Cf=(dwp.data_ptr(), Fa_real, 0), split_k=pick_split(Kreal, Fa_real, rows))
+    if has_bias and Kreal != K:
+        dbp = dbp[:Kreal]
     dza = ws.f(rows, Fa)
     tcgemm(Op(dtb.ptr, dtb.ld, 0), KM, Op(wpb.ptr, wpb.ld, 0), MN, rows, Fa, K, 1, Cf=(dza.data_ptr(), Fa, 0))
     return dwp, dbp, dza

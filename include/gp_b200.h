@@ -266,6 +266,10 @@ long long gp_gcn_layer_bwd_ws_x(const gp_layer_bwd* q);
  * ------------------------------------------------------------------------------------------- */
 int gp_readout_max_fwd(const float* z, long long ldz, const int32_t* nb, int B, int N, int F,
                        float* out, int32_t* argidx, long long ldo, gp_stream_t stream);
+/* Same over the first N rows of graphs stored `pitch` rows apart (pitch >= N): rows [N, pitch) are not part of the
+ * readout at all.  Used for pooled levels whose cluster count was padded to a multiple of 8 (dead clusters). */
+int gp_readout_max_fwd_x(const float* z, long long ldz, int pitch, const int32_t* nb, int B, int N, int F,
+                         float* out, int32_t* argidx, long long ldo, gp_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Assignment softmax (encoders.py:1273-1275): in place, S = softmax(T) on rows n < nb[b], 0 on
@@ -386,6 +390,11 @@ int gp_bias_normalize_f32(float* v, const float* bias, float* rnorm, long long r
 /* x[i] = v ;  y[i] += a*x[i]  (buffer initialisation / gradient accumulation for num_pooling >= 2) */
 int gp_fill_f32(float* x, long long n, float v, gp_stream_t stream);
 int gp_axpy_f32(const float* x, float* y, long long n, float a, gp_stream_t stream);
+int gp_fill_i32(int32_t* x, long long n, int32_t v, gp_stream_t stream);
+/* dst [rows_dst, cols_dst] = src [rows, cols] in the top-left corner, `fill` elsewhere (padded parameter / gradient
+ * copies when the assignment width is padded to a multiple of 8) */
+int gp_pad_copy_f32(const float* src, long long ld_src, long long rows, int cols, float* dst, long long ld_dst,
+                    long long rows_dst, int cols_dst, float fill, gp_stream_t stream);
 
 #ifdef __cplusplus
 }

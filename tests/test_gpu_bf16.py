@@ -54,6 +54,54 @@ def test_bf16_mode_bounds(N, D, H, C, B, ratio, P, n_min, density):
     assert rel_l2(gc, go) < 0.15 and cos > 0.99, (rel_l2(gc, go), cos)
 
 
+@pytest.mark.parametrize('N,H,ratio,P,extra', [(200, 24, 0.25, 2, 0), (120, 64, 0.25, 2, 1), (600, 32, 0.25, 1, 1),
+                                               (100, 30, 0.1, 1, 0)])
+def test_padded_cluster_count_is_exact(monkeypatch, N, H, ratio, P, extra):
+    """Cluster counts that are not multiples of 8 (cfg3: K = 250 / 62, cfg5: K = 1250) run at r8(K) with DEAD
+    clusters (zero weights, logit bias -1e30).  The dead clusters must change nothing: the padded schedule is compared
+    with the unpadded one (GP_NO_KPAD=1, same bf16 operands) -- outputs, S (shape and values), losses and every
+    parameter gradient.  extra=1 adds a user loss on the level-0 assignment tensor (its gradient reaches the encoder through
+    the padded-copy path instead of the link loss's own padded buffer)."""
+    from graph_pooling_b200 import encoders
+    D, C, B = 12, 3, 3
+    torch.manual_seed(7 * N)
+    m = encoders.SoftPoolingGcnEncoder(N, D, H, H, C, 3, H, assign_ratio=ratio, num_pooling=P).cuda()
+    with torch.no_grad():
+        for k, p in m.named_parameters():
+            if k.endswith('bias'):
+                p.copy_(0.2 * torch.randn(p.shape, device='cuda'))
+    m.precision = 1
+    assert any(k % 8 for k in m.assign_dims)
+    x, adj, nb, label = synth_batch(N + 3, B, N, D, max(N // 4, 2), N, C, 0.05)
+    xc, ac, lc = torch.tensor(x).cuda(), torch.tensor(adj).cuda(), torch.tensor(label).cuda()
+    res = []
+    for nopad in (0, 1):
+        if nopad:
+            monkeypatch.setenv('GP_NO_KPAD', '1')
+        m.zero_grad(set_to_none=True)
+        yp = m(xc, ac, nb, assign_x=xc)
+        loss = m.loss(yp, lc, ac, nb)
+        tot = loss + (0.01 * (m.assign_tensors[0] ** 2).sum() if extra else 0.0)
+        tot.backward()
+        torch.cuda.synchronize()
+        assert [tuple(t.shape[1:]) for t in m.assign_tensors] == \
+            [(N if i == 0 else m.assign_dims[i - 1], m.assign_dims[i]) for i in range(P)]
+        res.append((yp.detach().cpu().numpy(), [t.detach().cpu().numpy() for t in m.assign_tensors], loss.item(),
+                    m.link_loss.item(), {k: p.grad.cpu().numpy().copy() for k, p in m.named_parameters()}))
+    (y0, s0, l0, ll0, g0), (y1, s1, l1, ll1, g1) = res
+    # same arithmetic on the real clusters; only the order of a few fp32 reductions (vector vs scalar row kernels,
+    # split-K shapes) differs, plus the bf16 roundings that those last-bit differences can flip
+    assert rel_l2(y0, y1) < 2e-3
+    for a, b in zip(s0, s1):
+        assert rel_l2(a, b) < 2e-3
+    assert abs(l0 - l1) < 1e-4 * abs(l1) and abs(ll0 - ll1) < 1e-4 * abs(ll1)
+    f0 = np.concatenate([g0[k].ravel() for k in sorted(g0)]).astype(np.float64)
+    f1 = np.concatenate([g1[k].ravel() for k in sorted(g1)]).astype(np.float64)
+    assert rel_l2(f0, f1) < 2e-2, rel_l2(f0, f1)
+    for k in g0:
+        assert g0[k].shape == g1[k].shape and np.isfinite(g0[k]).all(), k
+
+
 @pytest.mark.parametrize('B,N,sym,weighted,use_nb,u8', [(3, 200, 1, 0, 1, 0), (2, 130, 0, 0, 1, 0), (2, 64, 1, 1, 0, 0),
                                                        (3, 257, 1, 0, 1, 1), (2, 96, 0, 0, 0, 1)])
 def test_adj_prepare_flags_and_values(B, N, sym, weighted, use_nb, u8):

@@ -149,6 +149,35 @@ def test_readout_max_ties_and_mask():
     assert torch.equal(out.cpu(), torch.max(torch.tensor(z), dim=1)[0])
 
 
+def test_readout_max_row_limit_and_pad_helpers():
+    """gp_readout_max_fwd_x scans the first N rows of graphs stored `pitch` rows apart (dead clusters of a padded
+    assignment width are not part of the readout); gp_pad_copy_f32 / gp_fill_i32 build the padded parameter copies."""
+    from graph_pooling_b200._lib import call
+    B, N, pitch, F = 3, 10, 16, 40
+    rs = np.random.RandomState(5)
+    z = rs.randn(B, pitch, F).astype(np.float32)
+    z[:, N:, :] = 50.0                          # rows beyond N must never win
+    z[1, :N, 7] = -2.0                          # all real rows negative: the max stays negative (no zero pad row)
+    zc = dev(z)
+    out = torch.empty(B, F, device='cuda')
+    arg = torch.empty(B, F, device='cuda', dtype=torch.int32)
+    call('gp_readout_max_fwd_x', zc.data_ptr(), F, pitch, None, B, N, F, out.data_ptr(), arg.data_ptr(), F, st())
+    ref, idx = torch.max(torch.tensor(z[:, :N]), dim=1)
+    assert torch.equal(out.cpu(), ref) and out[1, 7].item() == -2.0
+    assert np.array_equal(arg.cpu().numpy(), idx.numpy().astype(np.int32))
+    src = dev(rs.randn(5, 9).astype(np.float32))
+    dst = torch.full((8, 12), 3.0, device='cuda')
+    call('gp_pad_copy_f32', src.data_ptr(), C.c_longlong(9), C.c_longlong(5), 7, dst.data_ptr(), C.c_longlong(12),
+         C.c_longlong(6), 10, C.c_float(-1.5), st())
+    d = dst.cpu().numpy()
+    assert np.array_equal(d[:5, :7], src.cpu().numpy()[:, :7])
+    assert (d[5, :10] == -1.5).all() and (d[:5, 7:10] == -1.5).all()
+    assert (d[6:] == 3.0).all() and (d[:, 10:] == 3.0).all()      # outside [rows_dst, cols_dst]: untouched
+    iv = torch.zeros(11, device='cuda', dtype=torch.int32)
+    call('gp_fill_i32', iv.data_ptr(), C.c_longlong(10), 250, st())
+    assert iv.cpu().tolist() == [250] * 10 + [0]
+
+
 @pytest.mark.parametrize('K', [1, 10, 33, 512])
 def test_softmax_mask_fwd_bwd(K):
     from graph_pooling_b200._lib import call
