@@ -562,11 +562,81 @@ __global__ void __launch_bounds__(256) layer_bwd_row_kernel(const LbArgs a, long
   }
 }
 
+// Rows wider than 512 floats (the assignment GCN's last layer at K = 1250 -> 1256 / 1280 clusters): the row no longer
+// fits the registers twice over, so the dot product is taken in a first pass and the operands are read again (L1 / L2
+// hits: a row is a few KB) for the update.  4 warps per block; VPL float4 per lane hold the column sums only.
+template <int VPL>
+__global__ void __launch_bounds__(128) layer_bwd_row_wide_kernel(const LbArgs a, long long rows) {
+  __shared__ __align__(16) float colacc[4][VPL * 128];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int d4 = a.d >> 2;
+  const long long gw = (long long)blockIdx.x * 4 + warp, nw = (long long)gridDim.x * 4;
+  float4 cs[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) cs[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long row = gw; row < rows; row += nw) {
+    const int b = (int)(row / a.N), n = (int)(row - (long long)b * a.N);
+    const float r = a.normalize ? a.rnorm[row] : 1.f;
+    float dot = 0.f;
+    if (a.normalize) {
+#pragma unroll 4
+      for (int k = 0; k < VPL; ++k) {
+        const int c4 = lane + 32 * k;
+        if (c4 < d4) {
+          float4 g = load_g(a, b, n, row, c4 * 4);
+          const float4 yv = ld4(a.y + row * a.ldy + c4 * 4);
+          if (a.relu) {
+            if (!(yv.x > 0.f)) g.x = 0.f;
+            if (!(yv.y > 0.f)) g.y = 0.f;
+            if (!(yv.z > 0.f)) g.z = 0.f;
+            if (!(yv.w > 0.f)) g.w = 0.f;
+          }
+          dot = fmaf(g.x, yv.x, fmaf(g.y, yv.y, fmaf(g.z, yv.z, fmaf(g.w, yv.w, dot))));
+        }
+      }
+      dot = warp_sum(dot);
+    }
+    const bool clamped = !(r > kEpsNormB);
+    const float ir = clamped ? 1.f / kEpsNormB : 1.f / r;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int c4 = lane + 32 * k;
+      if (c4 < d4) {
+        float4 g = load_g(a, b, n, row, c4 * 4);
+        const float4 yv = ld4(a.y + row * a.ldy + c4 * 4);
+        if (a.relu) {
+          if (!(yv.x > 0.f)) g.x = 0.f;
+          if (!(yv.y > 0.f)) g.y = 0.f;
+          if (!(yv.z > 0.f)) g.z = 0.f;
+          if (!(yv.w > 0.f)) g.w = 0.f;
+        }
+        if (a.normalize) {
+          if (clamped) {
+            g.x /= kEpsNormB; g.y /= kEpsNormB; g.z /= kEpsNormB; g.w /= kEpsNormB;
+          } else {
+            g.x = (g.x - yv.x * dot) * ir; g.y = (g.y - yv.y * dot) * ir;
+            g.z = (g.z - yv.z * dot) * ir; g.w = (g.w - yv.w * dot) * ir;
+          }
+        }
+        store_dv(a, row, c4 * 4, g);
+        cs[k].x += g.x; cs[k].y += g.y; cs[k].z += g.z; cs[k].w += g.w;
+      }
+    }
+  }
+  if (a.part != nullptr) {
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) *reinterpret_cast<float4*>(&colacc[warp][(lane + 32 * k) * 4]) = cs[k];
+    __syncthreads();
+    for (int cidx = threadIdx.x; cidx < a.d; cidx += blockDim.x)
+      a.part[(long long)blockIdx.x * a.d + cidx] = (colacc[0][cidx] + colacc[1][cidx]) + (colacc[2][cidx] + colacc[3][cidx]);
+  }
+}
+
 static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // shape-level eligibility for the vectorised kernels (pointer alignment is checked per call)
 static bool shape_fast(int B, int d, int bn, int* CS_out) {
-  if (d % 4 != 0 || d > 512) return false;
+  if (d % 4 != 0 || d > (bn ? 512 : 2048)) return false;
   if (!bn) return true;
   const int d4 = d / 4;
   if (d4 > 32 || (d4 & (d4 - 1)) != 0) return false;     // a row must fit a power-of-two slice of one warp
@@ -741,7 +811,9 @@ int layer_bwd_fast(const gp_layer_bwd* q, cudaStream_t st, bool* handled) {
     const int d4 = d / 4;
     if (d4 <= 32) layer_bwd_row_kernel<1><<<(int)blocks, 256, 0, st>>>(a, rows);
     else if (d4 <= 64) layer_bwd_row_kernel<2><<<(int)blocks, 256, 0, st>>>(a, rows);
-    else layer_bwd_row_kernel<4><<<(int)blocks, 256, 0, st>>>(a, rows);
+    else if (d4 <= 128) layer_bwd_row_kernel<4><<<(int)blocks, 256, 0, st>>>(a, rows);
+    else if (d4 <= 256) layer_bwd_row_wide_kernel<8><<<(int)blocks, 128, 0, st>>>(a, rows);
+    else layer_bwd_row_wide_kernel<16><<<(int)blocks, 128, 0, st>>>(a, rows);
     GP_LAUNCHED();
     part_rows = blocks;
   }

@@ -222,6 +222,61 @@ __global__ void softmax_bwd_x_kernel(const float* __restrict__ s, const float* _
   }
 }
 
+// K up to 2048 (VPL = 8 / 16): the dot product in a first pass, S and dS read again (L1 / L2 hits) for the update;
+// 4 warps per block, the lanes keep the column sums only
+template <int VPL>
+__global__ void __launch_bounds__(128) softmax_bwd_wide_kernel(const float* __restrict__ s, const float* __restrict__ ds,
+                                                               const int32_t* __restrict__ nb, long long rows, int N,
+                                                               int K, float* __restrict__ dt,
+                                                               __nv_bfloat16* __restrict__ dtb, long long lddtb,
+                                                               float* __restrict__ part) {
+  __shared__ __align__(16) float colacc[4][VPL * 128];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long gw = (long long)blockIdx.x * 4 + warp, nw = (long long)gridDim.x * 4;
+  float4 cs[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) cs[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long r = gw; r < rows; r += nw) {
+    const int b = (int)(r / N), n = (int)(r - (long long)b * N);
+    const bool pad = nb != nullptr && n >= nb[b];
+    float dot = 0.f;
+    if (!pad) {
+#pragma unroll 4
+      for (int k = 0; k < VPL; ++k) {
+        const int c = (lane + 32 * k) * 4;
+        if (c < K) {
+          const float4 sv = *reinterpret_cast<const float4*>(s + r * K + c);
+          const float4 gv = *reinterpret_cast<const float4*>(ds + r * K + c);
+          dot = fmaf(sv.x, gv.x, fmaf(sv.y, gv.y, fmaf(sv.z, gv.z, fmaf(sv.w, gv.w, dot))));
+        }
+      }
+      dot = warp_sum(dot);
+    }
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int c = (lane + 32 * k) * 4;
+      if (c < K) {
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!pad) {
+          const float4 sv = *reinterpret_cast<const float4*>(s + r * K + c);
+          const float4 gv = *reinterpret_cast<const float4*>(ds + r * K + c);
+          o = make_float4(sv.x * (gv.x - dot), sv.y * (gv.y - dot), sv.z * (gv.z - dot), sv.w * (gv.w - dot));
+        }
+        if (dt != nullptr) *reinterpret_cast<float4*>(dt + r * K + c) = o;
+        if (dtb != nullptr) *reinterpret_cast<uint2*>(dtb + r * lddtb + c) = make_uint2(packx(o.x, o.y), packx(o.z, o.w));
+        cs[k].x += o.x; cs[k].y += o.y; cs[k].z += o.z; cs[k].w += o.w;
+      }
+    }
+  }
+  if (part != nullptr) {
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) *reinterpret_cast<float4*>(&colacc[warp][(lane + 32 * k) * 4]) = cs[k];
+    __syncthreads();
+    for (int c = threadIdx.x; c < K; c += blockDim.x)
+      part[(long long)blockIdx.x * K + c] = (colacc[0][c] + colacc[1][c]) + (colacc[2][c] + colacc[3][c]);
+  }
+}
+
 int colsum(const float* x, long long rows, int d, long long ld, float* out, int accumulate, float* ws,
            cudaStream_t st);
 int bias_normalize(float* v, const float* bias, float* rnorm, long long rows, int d, long long ld, int normalize,
@@ -261,15 +316,16 @@ extern "C" int gp_bias_normalize_x(float* v, const float* bias, float* rnorm, lo
   GP_REQUIRE(v && rows > 0 && d > 0 && ld >= d, "bias_normalize_x: bad args");
   GP_REQUIRE(!normalize || rnorm, "bias_normalize_x: normalize needs rnorm");
   __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(y_bf16);
-  const bool vec = d % 4 == 0 && d <= 1024 && al16x(v) && ld % 4 == 0 && (!bias || al16x(bias)) &&
+  const bool vec = d % 4 == 0 && d <= 2048 && al16x(v) && ld % 4 == 0 && (!bias || al16x(bias)) &&
                    (!yb || (al8x(yb) && ldyb % 4 == 0));
-  GP_REQUIRE(vec || yb == nullptr, "bias_normalize_x: the bf16 copy needs d %% 4 == 0, d <= 1024 and 16-byte aligned rows");
+  GP_REQUIRE(vec || yb == nullptr, "bias_normalize_x: the bf16 copy needs d %% 4 == 0, d <= 2048 and 16-byte aligned rows");
   if (!vec) return bias_normalize(v, bias, rnorm, rows, d, ld, normalize, S(stream));
   const int g = row_grid(rows);
   if (d <= 128)      bias_normalize_x_kernel<1><<<g, 256, 0, S(stream)>>>(v, bias, rnorm, rows, d, ld, normalize, yb, ldyb);
   else if (d <= 256) bias_normalize_x_kernel<2><<<g, 256, 0, S(stream)>>>(v, bias, rnorm, rows, d, ld, normalize, yb, ldyb);
   else if (d <= 512) bias_normalize_x_kernel<4><<<g, 256, 0, S(stream)>>>(v, bias, rnorm, rows, d, ld, normalize, yb, ldyb);
-  else               bias_normalize_x_kernel<8><<<g, 256, 0, S(stream)>>>(v, bias, rnorm, rows, d, ld, normalize, yb, ldyb);
+  else if (d <= 1024) bias_normalize_x_kernel<8><<<g, 256, 0, S(stream)>>>(v, bias, rnorm, rows, d, ld, normalize, yb, ldyb);
+  else               bias_normalize_x_kernel<16><<<g, 256, 0, S(stream)>>>(v, bias, rnorm, rows, d, ld, normalize, yb, ldyb);
   GP_LAUNCHED();
   return GP_OK;
 }
@@ -278,9 +334,9 @@ extern "C" int gp_softmax_mask_fwd_x(float* t, const int32_t* nb, int B, int N, 
                                      gp_stream_t stream) {
   GP_REQUIRE(t && B > 0 && N > 0 && K > 0, "softmax_mask_fwd_x: bad args");
   __nv_bfloat16* sb = reinterpret_cast<__nv_bfloat16*>(s_bf16);
-  const bool vec = K % 4 == 0 && K <= 1024 && al16x(t) && (!sb || (al8x(sb) && ldsb % 4 == 0));
+  const bool vec = K % 4 == 0 && K <= 2048 && al16x(t) && (!sb || (al8x(sb) && ldsb % 4 == 0));
   if (!vec) {
-    GP_REQUIRE(sb == nullptr, "softmax_mask_fwd_x: the bf16 copy needs K %% 4 == 0 and K <= 1024");
+    GP_REQUIRE(sb == nullptr, "softmax_mask_fwd_x: the bf16 copy needs K %% 4 == 0 and K <= 2048");
     return gp_softmax_mask_fwd(t, nb, B, N, K, stream);
   }
   const long long rows = (long long)B * N;
@@ -288,7 +344,8 @@ extern "C" int gp_softmax_mask_fwd_x(float* t, const int32_t* nb, int B, int N, 
   if (K <= 128)      softmax_fwd_x_kernel<1><<<g, 256, 0, S(stream)>>>(t, nb, rows, N, K, sb, ldsb);
   else if (K <= 256) softmax_fwd_x_kernel<2><<<g, 256, 0, S(stream)>>>(t, nb, rows, N, K, sb, ldsb);
   else if (K <= 512) softmax_fwd_x_kernel<4><<<g, 256, 0, S(stream)>>>(t, nb, rows, N, K, sb, ldsb);
-  else               softmax_fwd_x_kernel<8><<<g, 256, 0, S(stream)>>>(t, nb, rows, N, K, sb, ldsb);
+  else if (K <= 1024) softmax_fwd_x_kernel<8><<<g, 256, 0, S(stream)>>>(t, nb, rows, N, K, sb, ldsb);
+  else               softmax_fwd_x_kernel<16><<<g, 256, 0, S(stream)>>>(t, nb, rows, N, K, sb, ldsb);
   GP_LAUNCHED();
   return GP_OK;
 }
@@ -300,11 +357,11 @@ extern "C" int gp_softmax_mask_bwd_x(const float* s, const float* ds, const int3
   GP_REQUIRE(s && ds && (dt || dt_bf16) && B > 0 && N > 0 && K > 0, "softmax_mask_bwd_x: bad args");
   GP_REQUIRE(!dcol || ws, "softmax_mask_bwd_x: dcol needs ws");
   __nv_bfloat16* dtb = reinterpret_cast<__nv_bfloat16*>(dt_bf16);
-  const bool vec = K % 4 == 0 && K <= 512 && al16x(s) && al16x(ds) && (!dt || al16x(dt)) &&
+  const bool vec = K % 4 == 0 && K <= 2048 && al16x(s) && al16x(ds) && (!dt || al16x(dt)) &&
                    (!dtb || (al8x(dtb) && lddtb % 4 == 0));
   const long long rows = (long long)B * N;
   if (!vec) {
-    GP_REQUIRE(dtb == nullptr && dt != nullptr, "softmax_mask_bwd_x: the bf16 copy needs K %% 4 == 0 and K <= 512");
+    GP_REQUIRE(dtb == nullptr && dt != nullptr, "softmax_mask_bwd_x: the bf16 copy needs K %% 4 == 0 and K <= 2048");
     GP_TRY(gp_softmax_mask_bwd(s, ds, nb, B, N, K, dt, stream));
     if (dcol) GP_TRY(colsum(dt, rows, K, K, dcol, 0, ws, S(stream)));
     return GP_OK;
@@ -313,7 +370,9 @@ extern "C" int gp_softmax_mask_bwd_x(const float* s, const float* ds, const int3
   float* part = dcol ? ws : nullptr;
   if (K <= 128)      softmax_bwd_x_kernel<1><<<g, 256, 0, S(stream)>>>(s, ds, nb, rows, N, K, dt, dtb, lddtb, part);
   else if (K <= 256) softmax_bwd_x_kernel<2><<<g, 256, 0, S(stream)>>>(s, ds, nb, rows, N, K, dt, dtb, lddtb, part);
-  else               softmax_bwd_x_kernel<4><<<g, 256, 0, S(stream)>>>(s, ds, nb, rows, N, K, dt, dtb, lddtb, part);
+  else if (K <= 512) softmax_bwd_x_kernel<4><<<g, 256, 0, S(stream)>>>(s, ds, nb, rows, N, K, dt, dtb, lddtb, part);
+  else if (K <= 1024) softmax_bwd_wide_kernel<8><<<g, 128, 0, S(stream)>>>(s, ds, nb, rows, N, K, dt, dtb, lddtb, part);
+  else               softmax_bwd_wide_kernel<16><<<g, 128, 0, S(stream)>>>(s, ds, nb, rows, N, K, dt, dtb, lddtb, part);
   GP_LAUNCHED();
   if (dcol) GP_TRY(colsum(ws, g, K, K, dcol, 0, ws + (long long)g * K, S(stream)));
   return GP_OK;

@@ -243,7 +243,7 @@ def _layer_forward(ws, ctx, l, ub, hb2=None):
     else:
         # wide layer (e.g. the assignment GCN's last layer, dout = K): plain GEMM, then one normalize pass
         tcgemm(uflat, KM, wflat, MN, rows, dout, cur_d, 1, Cf=(y_ptr, ldy, 0), bias=bias_p)
-        yb_ok = dout % 4 == 0 and dout <= 1024 and ldy % 4 == 0
+        yb_ok = dout % 4 == 0 and dout <= 2048 and ldy % 4 == 0
         call('gp_bias_normalize_x', y_ptr, None, rnorm.data_ptr(), C.c_longlong(rows), dout, ldy, 1,
              hb.ptr if (last and yb_ok) else None, hb.ld, st)
         if last and not yb_ok:
@@ -439,7 +439,7 @@ def dual_stack_backward(ws, cE, cA, dzE_ptr, lddzE, doutE_ptr, argE_ptr, ldo, dz
 def softmax_forward(ws, S, nb, B, N, K):
     """In-place masked softmax (encoders.py:1273-1275) that also emits the bf16 operand copy of S."""
     sb = bfbuf(ws, B, N, K)
-    if K % 4 == 0 and K <= 1024:
+    if K % 4 == 0 and K <= 2048:
         call('gp_softmax_mask_fwd_x', S.data_ptr(), E._p(nb), B, N, K, sb.ptr, sb.ld, E._stream())
     else:
         call('gp_softmax_mask_fwd', S.data_ptr(), E._p(nb), B, N, K, E._stream())
@@ -523,7 +523,7 @@ def assign_head_bwd(ws, S, ds, nb, B, N, zab, Fa, wpb, K, has_bias, Kreal=0, Fa_
     rows = B * N
     dtb = bfbuf(ws, 1, rows, K)
     dbp = ws.f(K) if has_bias else None
-    if K % 4 == 0 and K <= 512:
+    if K % 4 == 0 and K <= 2048:
         wsb = ws.f((148 * 16 + 256) * K) if has_bias else None
         call('gp_softmax_mask_bwd_x', S.data_ptr(), ds.data_ptr(), E._p(nb), B, N, K, None, dtb.ptr, dtb.ld,
              E._p(dbp), E._p(wsb), st)

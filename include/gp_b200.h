@@ -153,7 +153,7 @@ int gp_bn_apply(const float* y, long long ldy, const float* mean, const float* i
                 long long ldhb2, gp_stream_t stream);
 /* gp_bias_normalize_f32 / gp_softmax_mask_fwd / _bwd with the bf16 operand copy written in the same pass;
  * softmax backward can also return dcol = colsum(dT) (the assign_pred bias gradient, encoders.py:1273);
- * ws >= (148*16 + 256) * K floats. */
+ * ws >= (148*16 + 256) * K floats.  The bf16 copies need 16-byte aligned rows, width % 4 == 0 and <= 2048. */
 int gp_bias_normalize_x(float* v, const float* bias, float* rnorm, long long rows, int d, long long ld,
                         int normalize, void* y_bf16, long long ldyb, gp_stream_t stream);
 int gp_softmax_mask_fwd_x(float* t, const int32_t* nb, int B, int N, int K, void* s_bf16, long long ldsb,
@@ -238,7 +238,7 @@ int gp_gcn_layer_bwd(const float* dz, long long lddz, const float* dxn, const fl
 /* Extended form (the one the engines use): optional bf16 copy of dV (the operand of the tensor-core dW / dU
  * contractions), the bias gradient db = colsum(dV) produced in the same pass, and Hhat recomputed from Y and
  * the saved statistics (h == NULL, mean != NULL) so the BN output need not be re-read.  16-byte aligned
- * inputs with d in {32, 64, 128} (bn) or d % 4 == 0, d <= 512 (no bn) take a single-pass vectorised kernel
+ * inputs with d in {32, 64, 128} (bn) or d % 4 == 0, d <= 2048 (no bn; two passes over a row beyond 512) take a vectorised kernel
  * (a thread-block cluster per node index, batch means reduced through distributed shared memory).
  * ws: gp_gcn_layer_bwd_ws_x(q) floats, needed when db != NULL (gp_gcn_layer_bwd_ws(B, N, d, bn) is the
  * shape-only bound, valid when every operand meets the alignment above or dv != NULL); optional otherwise --

@@ -26,6 +26,10 @@ def st():
     (7, 30, 128, 0, 0, 1, 1, 1, 0),       # last layer: no relu / bn -> row kernel
     (5, 21, 512, 0, 0, 1, 0, 0, 0),       # row kernel, 4 float4 per lane
     (6, 11, 256, 1, 0, 1, 1, 1, 0),       # row kernel with relu, 2 float4 per lane
+    (3, 37, 1256, 0, 0, 1, 0, 0, 0),      # wide row kernel (two passes, 4 warps per block), 16 float4 slots per lane
+    (4, 13, 768, 0, 0, 1, 1, 0, 0),       # wide row kernel, 8 slots
+    (2, 150, 1280, 1, 0, 1, 1, 1, 0),     # wide row kernel, 16 slots, relu + readout scatter
+    (2, 9, 2048, 0, 0, 1, 1, 0, 0),       # widest vectorised row
     (20, 100, 30, 1, 1, 1, 1, 1, 1),      # generic (d % 4 != 0), stored h
     (20, 40, 30, 1, 1, 1, 0, 1, 0),       # generic, recomputed Hhat
     (4, 6, 256, 1, 1, 1, 0, 0, 0),        # bn with d4 = 64 -> generic
