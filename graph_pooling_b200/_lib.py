@@ -123,6 +123,8 @@ _PROTOS = {
     'gp_fill_f32': [c_f, c_ll, C.c_float, c_f],
     'gp_axpy_f32': [c_f, c_f, c_ll, C.c_float, c_f],
     'gp_fill_i32': [c_f, c_ll, c_i, c_f],
+    'gp_set2set_fwd': [c_f, c_ll, c_f, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f],
+    'gp_set2set_bwd': [c_f, c_ll, c_f, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_f, c_f, c_ll, c_f, c_f, c_f, c_f],
     'gp_pad_copy_f32': [c_f, c_ll, c_ll, c_i, c_f, c_ll, c_ll, c_i, C.c_float, c_f],
 }
 _RESTYPES = {'gp_last_error': C.c_char_p, 'gp_launch_count': c_ll, 'gp_gcn_layer_bwd_ws': c_ll, 'gp_gcn_layer_bwd_ws_x': c_ll, 'gp_relu_bn_fwd_ws': c_ll, 'gp_graphconv_bwd_ws': c_ll, 'gp_launch_count_reset': None}

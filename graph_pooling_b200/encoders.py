@@ -21,7 +21,7 @@ from . import engine as E
 from . import engine_tc as T
 from ._lib import call
 
-__all__ = ['GraphConv', 'GcnEncoderGraph', 'GcnSet2SetEncoder', 'SoftPoolingGcnEncoder']
+__all__ = ['GraphConv', 'GcnEncoderGraph', 'GcnSet2SetEncoder', 'Set2Set', 'SoftPoolingGcnEncoder']
 
 # precision new encoders start with: 0 = fp32 FFMA (parity anchor), 1 = bf16 tensor cores; `model.precision` overrides
 DEFAULT_PRECISION = E.F32
@@ -725,17 +725,199 @@ class GcnEncoderGraph(nn.Module):
         self._entries_override = None if num_entries is None else int(num_entries)
 
 
+class Set2Set(nn.Module):
+    """set2set.py:8-57.  Holds the reference's parameters under the reference's names (``lstm.weight_ih_l0`` ...,
+    ``pred.weight``); the nn.LSTM / nn.Linear objects are parameter containers only -- the n sequential LSTM +
+    attention steps run in gp_set2set_fwd / gp_set2set_bwd (one CTA per graph), the projection on the library's GEMM."""
+
+    def __init__(self, input_dim, hidden_dim, act_fn=nn.ReLU, num_layers=1):
+        super().__init__()
+        if num_layers != 1:
+            raise NotImplementedError('gp_b200: Set2Set with num_layers != 1 (the reference always uses 1)')
+        if act_fn is not nn.ReLU:
+            raise NotImplementedError('gp_b200: Set2Set supports act_fn=nn.ReLU (the reference default)')
+        self.input_dim = input_dim
+        self.hidden_dim = hidden_dim
+        self.num_layers = num_layers
+        if hidden_dim <= input_dim:
+            print('ERROR: Set2Set output_dim should be larger than input_dim')
+        self.lstm_output_dim = hidden_dim - input_dim
+        if hidden_dim != 2 * input_dim:
+            # q* = [q, r] has lstm_output_dim + input_dim entries and e = E q^T needs lstm_output_dim == input_dim
+            raise ValueError('Set2Set needs hidden_dim == 2 * input_dim (set2set.py:51,55)')
+        self.lstm = nn.LSTM(hidden_dim, input_dim, num_layers=num_layers, batch_first=True)
+        self.pred = nn.Linear(hidden_dim, input_dim)
+        self.act = act_fn()
+
+    def _params(self):
+        l = self.lstm
+        return [l.weight_ih_l0, l.weight_hh_l0, l.bias_ih_l0, l.bias_hh_l0]
+
+    def forward(self, embedding, batch_num_nodes=None):
+        """[B,n,d] -> [B,d].  batch_num_nodes (an extension): rows beyond a graph's node count are treated as zero rows."""
+        emb = E._chk(embedding, 'embedding')
+        nb_dev, _ = E.prep_nb(batch_num_nodes, emb.shape[1], emb.device)
+        return _Set2SetFn.apply(emb, nb_dev, self.pred.weight, self.pred.bias, *self._params())
+
+
+def _s2s_forward(ws, e_ptr, lde, nb, B, N, d, lstm_params):
+    wih, whh, bih, bhh = lstm_params
+    qs, gates = ws.f(B, N + 1, 2 * d), ws.f(B, N, 4 * d)
+    cells, att = ws.f(B, N, d), ws.f(B, N, N)
+    call('gp_set2set_fwd', e_ptr, C.c_longlong(lde), E._p(nb), B, N, d, wih.data_ptr(), whh.data_ptr(), E._p(bih),
+         E._p(bhh), qs.data_ptr(), gates.data_ptr(), cells.data_ptr(), att.data_ptr(), E._stream())
+    return qs, gates, cells, att
+
+
+def _s2s_backward(ws, e_ptr, lde, nb, B, N, d, lstm_params, saved, dqs):
+    """BPTT kernel + the batched contractions that turn its per-step gradients into parameter / embedding gradients.
+    Returns (dW_ih, dW_hh, db_ih, db_hh, dE [B,N,d])."""
+    st = E._stream()
+    wih, whh, bih, bhh = lstm_params
+    qs, gates, cells, att = saved
+    dz, dr, de = ws.f(B, N + 1, 4 * d), ws.f(B, N, d), ws.f(B, N, N)
+    call('gp_set2set_bwd', e_ptr, C.c_longlong(lde), E._p(nb), B, N, d, wih.data_ptr(), whh.data_ptr(),
+         gates.data_ptr(), cells.data_ptr(), att.data_ptr(), dqs.data_ptr(), C.c_longlong(2 * d), dz.data_ptr(),
+         dr.data_ptr(), de.data_ptr(), st)
+    rows = B * (N + 1)
+    split = max(1, min(64, rows // 1024))
+    dwih, dwhh = ws.f(4 * d, 2 * d), ws.f(4 * d, d)
+    # dW_ih = DZ^T QS ;  dW_hh = DZ^T QS[:, :d]  (h_{t-1} is the first half of q*_{t-1})
+    E.bgemm(dz.data_ptr(), qs.data_ptr(), dwih.data_ptr(), 4 * d, 2 * d, rows, 1, (0, 1, 4 * d), (0, 2 * d, 1),
+            (0, 2 * d, 1), split_k=split)
+    E.bgemm(dz.data_ptr(), qs.data_ptr(), dwhh.data_ptr(), 4 * d, d, rows, 1, (0, 1, 4 * d), (0, 2 * d, 1),
+            (0, d, 1), split_k=split)
+    dbs = []
+    for b_ in (bih, bhh):                     # the two bias vectors enter the gates as a sum: same gradient, own buffer
+        if b_ is None:
+            dbs.append(None)
+            continue
+        db, cs = ws.f(4 * d), ws.f(256 * 4 * d)
+        call('gp_colsum_f32', dz.data_ptr(), C.c_longlong(rows), 4 * d, C.c_longlong(4 * d), db.data_ptr(), 0,
+             cs.data_ptr(), st)
+        dbs.append(db)
+    # dE_b = AT_b^T DR_b + DE_b^T Q_b, rows beyond n_b stay zero (the mask of encoders.py:1080)
+    dE = ws.f(B, N, d)
+    lim = int(nb is not None)
+    E.bgemm(att.data_ptr(), dr.data_ptr(), dE.data_ptr(), N, d, N, B, (N * N, 1, N), (N * d, d, 1), (N * d, d, 1),
+            lim=E._p(nb), lim_m=lim)
+    E.bgemm(de.data_ptr(), qs.data_ptr() + 2 * d * 4, dE.data_ptr(), N, d, N, B, (N * N, 1, N),
+            ((N + 1) * 2 * d, 2 * d, 1), (N * d, d, 1), lim=E._p(nb), lim_m=lim, beta=1.0)
+    return dwih, dwhh, dbs[0], dbs[1], dE
+
+
+class _Set2SetFn(torch.autograd.Function):
+    """Stand-alone Set2Set module: out = relu(pred(q*_n))."""
+
+    @staticmethod
+    def forward(ctx, emb, nb, wp, bp, wih, whh, bih, bhh):
+        ws = E.Workspace(emb.device)
+        B, N, d = emb.shape
+        saved = _s2s_forward(ws, emb.data_ptr(), d, nb, B, N, d, (wih, whh, bih, bhh))
+        qs = saved[0]
+        out = E.linear_fwd(ws, qs.data_ptr() + N * 2 * d * 4, (N + 1) * 2 * d, B, wp, bp, relu=True)
+        ctx.tape = (emb, nb, wp, bp is not None, (wih, whh, bih, bhh), saved, out.detach())
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        emb, nb, wp, has_bp, lstm_params, saved, out = ctx.tape
+        ctx.tape = None
+        ws = E.Workspace(emb.device)
+        B, N, d = emb.shape
+        dout = E._chk(dout, 'grad of the Set2Set output')
+        g = ws.f(B, d)
+        call('gp_relu_mask_bwd', dout.data_ptr(), out.data_ptr(), C.c_longlong(g.numel()), g.data_ptr(), E._stream())
+        qs = saved[0]
+        dwp, dbp, dqs = E.linear_bwd(ws, g, qs.data_ptr() + N * 2 * d * 4, (N + 1) * 2 * d, B, wp, has_bp, True)
+        dwih, dwhh, dbih, dbhh, dE = _s2s_backward(ws, emb.data_ptr(), d, nb, B, N, d, lstm_params, saved, dqs)
+        return dE, None, dwp, dbp, dwih, dwhh, dbih, dbhh
+
+
+class _S2SEncoderFn(torch.autograd.Function):
+    """GcnSet2SetEncoder.forward (encoders.py:1144-1157) as one autograd node: GCN stack (fp32 schedule) -> masked
+    concat -> Set2Set -> relu(s2s.pred) -> pred_model."""
+
+    @staticmethod
+    def forward(ctx, plan, x, adj, *params):
+        ws = E.Workspace(x.device)
+        B, N, D = x.shape
+        nb = plan.nb_dev
+        w0 = [_wb(params, p)[0] for p in plan.emb]
+        b0 = [_wb(params, p)[1] for p in plan.emb]
+        z, c_emb = E.stack_forward(ws, x.data_ptr(), D, D, adj, nb, B, N, w0, b0, plan.add_self, plan.bn, E.F32)
+        d = plan.F
+        lstm_params = tuple(None if i is None else params[i] for i in plan.lstm)
+        saved = _s2s_forward(ws, z.data_ptr(), d, nb, B, N, d, lstm_params)
+        lin = [_wb(params, p) for p in plan.pred]         # [s2s.pred (ReLU after it), pred_model ...]
+        ypred, acts = E.mlp_fwd(ws, saved[0].data_ptr() + N * 2 * d * 4, (N + 1) * 2 * d, B, lin)
+        ctx.tape = dict(plan=plan, params=params, B=B, N=N, emb=c_emb, z=z, saved=saved, acts=acts, lin=lin,
+                        lstm=lstm_params)
+        return ypred
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dypred):
+        tape = ctx.tape
+        if tape is None:
+            raise RuntimeError('gp_b200: backward called twice (buffers were freed)')
+        ctx.tape = None
+        plan, params, B, N = tape['plan'], tape['params'], tape['B'], tape['N']
+        ws = E.Workspace(tape['z'].device)
+        d = plan.F
+        grads = [None] * len(params)
+        dypred = E._chk(dypred, 'grad of ypred')
+        dqs = ws.f(B, 2 * d)
+        gl = E.mlp_bwd(ws, dypred, B, tape['acts'], tape['lin'], dqs.data_ptr(), 2 * d)
+        for (iw, ib), (dw, db) in zip(plan.pred, gl):
+            grads[iw] = dw
+            if ib is not None:
+                grads[ib] = db
+        dwih, dwhh, dbih, dbhh, dE = _s2s_backward(ws, tape['z'].data_ptr(), d, plan.nb_dev, B, N, d, tape['lstm'],
+                                                   tape['saved'], dqs)
+        for i, gq in zip(plan.lstm, (dwih, dwhh, dbih, dbhh)):
+            if i is not None:
+                grads[i] = gq
+        gl, _ = E.stack_backward(ws, tape['emb'], dE.data_ptr(), d, None, None, 0, False, None, E.F32)
+        for (iw, ib), (dw, db) in zip(plan.emb, gl):
+            grads[iw] = dw
+            if ib is not None:
+                grads[ib] = db
+        return (None, None, None) + tuple(grads)
+
+
 class GcnSet2SetEncoder(GcnEncoderGraph):
-    """encoders.py:1137-1157 (method=base-set2set) -- outside the north-star path.
-    Constructible for import compatibility; forward is not implemented on the CUDA path yet."""
+    """encoders.py:1137-1157 (method=base-set2set): GCN stack, masked concat, Set2Set readout (set2set.py), pred_model.
+    Outside the north-star path: runs on the fp32 schedule whatever `precision` says."""
 
     def __init__(self, input_dim, hidden_dim, embedding_dim, label_dim, num_layers,
                  pred_hidden_dims=[], concat=True, bn=True, dropout=0.0, args=None):
         super().__init__(input_dim, hidden_dim, embedding_dim, label_dim, num_layers, pred_hidden_dims, concat,
                          bn, dropout, args=args)
+        if not concat:
+            # gcn_forward always concatenates (encoders.py:1078) while Set2Set is sized for pred_input_dim =
+            # embedding_dim when concat=False (:1141): the reference cannot run that combination either
+            raise NotImplementedError('gp_b200: GcnSet2SetEncoder requires concat=True (as the reference does)')
+        self.s2s = Set2Set(self.pred_input_dim, self.pred_input_dim * 2)
 
     def forward(self, x, adj, batch_num_nodes=None, **kwargs):
-        raise NotImplementedError('gp_b200: GcnSet2SetEncoder (Set2Set readout) is out of the hot-path scope')
+        if isinstance(adj, T.PreparedAdjacency):
+            raise ValueError('GcnSet2SetEncoder runs on the fp32 schedule: pass the fp32 adjacency')
+        prec, self.precision = self.precision, E.F32
+        try:
+            plan, params, x, adj = self._base_plan(x, adj, batch_num_nodes)
+        finally:
+            self.precision = prec
+        plan.precision = E.F32
+        plan.soft, plan.num_pooling = False, 0
+        plan.lstm = []
+        for p in self.s2s._params():
+            params.append(p)
+            plan.lstm.append(len(params) - 1)
+        plan.pred = self._pred_pairs(params, self.s2s.pred) + self._pred_pairs(params, self.pred_model)
+        self._plan = plan
+        return _S2SEncoderFn.apply(plan, x, adj, *params)
 
 
 class SoftPoolingGcnEncoder(GcnEncoderGraph):

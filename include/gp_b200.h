@@ -387,6 +387,24 @@ int gp_relu_mask_bwd(const float* dy, const float* y, long long n, float* dx, gp
 /* in place: v (+bias) -> v / max(||v||_2, 1e-12) per row (encoders.py:323-326); rnorm[r] = the divisor */
 int gp_bias_normalize_f32(float* v, const float* bias, float* rnorm, long long rows, int d, long long ld,
                           int normalize, gp_stream_t stream);
+/* ---------------------------------------------------------------------------------------------
+ * Set2Set readout of GcnSet2SetEncoder (set2set.py:33-57, called from encoders.py:1144-1157).
+ * E [B,N,ldE] node embeddings (d columns; rows n >= nb[b] count as zero rows, the mask of encoders.py:1080),
+ * one-layer LSTM weights in torch.nn.LSTM layout (w_ih [4d,2d], w_hh [4d,d], biases [4d] or NULL, gates i f g o).
+ * One CTA per graph runs the N sequential steps.  Forward outputs (all saved for the backward):
+ *   qs [B,N+1,2d] q*_t (row 0 zeros, row N = the readout), gates [B,N,4d], cells [B,N,d], att [B,N,N].
+ * Backward: dout = gradient of qs[:,N,:] (row stride lddout); emits dz [B,N+1,4d] (gate pre-activation gradients,
+ * row N zero), dr [B,N,d], de [B,N,N]; the caller forms dW_ih = dz^T qs, dW_hh = dz^T qs[:, :d],
+ * db = colsum(dz) and dE_b = att_b^T dr_b + de_b^T qs_b[1:, :d] with gp_bgemm_f32 / gp_colsum_f32.
+ * Needs (N + 16 d + 64) floats of shared memory (<= 200 KB).
+ * ------------------------------------------------------------------------------------------- */
+int gp_set2set_fwd(const float* E, long long ldE, const int32_t* nb, int B, int N, int d, const float* w_ih,
+                   const float* w_hh, const float* b_ih, const float* b_hh, float* qs, float* gates, float* cells,
+                   float* att, gp_stream_t stream);
+int gp_set2set_bwd(const float* E, long long ldE, const int32_t* nb, int B, int N, int d, const float* w_ih,
+                   const float* w_hh, const float* gates, const float* cells, const float* att, const float* dout,
+                   long long lddout, float* dz, float* dr, float* de, gp_stream_t stream);
+
 /* x[i] = v ;  y[i] += a*x[i]  (buffer initialisation / gradient accumulation for num_pooling >= 2) */
 int gp_fill_f32(float* x, long long n, float v, gp_stream_t stream);
 int gp_axpy_f32(const float* x, float* y, long long n, float a, gp_stream_t stream);

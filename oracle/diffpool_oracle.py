@@ -2,7 +2,8 @@
 
 This file is a plain-PyTorch restatement of the reference's algorithm
 (JiaxuanYou/graph-pooling, ``encoders.py:976-1334`` plus the commented-out DiffPool
-``GraphConv`` at ``encoders.py:296-328`` == ``:945-974``).  It exists so that the CUDA
+``GraphConv`` at ``encoders.py:296-328`` == ``:945-974``, and ``set2set.py:8-57`` for the
+base-set2set readout).  It exists so that the CUDA
 path in ``graph_pooling_b200`` can be checked against it; it is NOT part of the product:
 only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
 ``--impl reference`` leg may import it, and only as the checker / the CPU baseline.
@@ -271,6 +272,54 @@ class GcnEncoderGraph(nn.Module):
             onehot = torch.zeros(pred.size(0), self.label_dim, dtype=torch.long, device=pred.device)
             onehot.scatter_(1, label.view(-1, 1), 1)
             return torch.nn.MultiLabelMarginLoss()(pred, onehot)
+
+
+class Set2Set(nn.Module):
+    """set2set.py:8-57 (R2: the zero states follow the input's device / dtype instead of .cuda())."""
+
+    def __init__(self, input_dim, hidden_dim, act_fn=nn.ReLU, num_layers=1):
+        super().__init__()
+        self.input_dim = input_dim
+        self.hidden_dim = hidden_dim
+        self.num_layers = num_layers
+        if hidden_dim <= input_dim:
+            print('ERROR: Set2Set output_dim should be larger than input_dim')
+        self.lstm_output_dim = hidden_dim - input_dim
+        self.lstm = nn.LSTM(hidden_dim, input_dim, num_layers=num_layers, batch_first=True)
+        self.pred = nn.Linear(hidden_dim, input_dim)
+        self.act = act_fn()
+
+    def forward(self, embedding):
+        batch_size, n = embedding.size(0), embedding.size(1)
+        z = lambda *shape: torch.zeros(*shape, dtype=embedding.dtype, device=embedding.device)
+        hidden = (z(self.num_layers, batch_size, self.lstm_output_dim),
+                  z(self.num_layers, batch_size, self.lstm_output_dim))
+        q_star = z(batch_size, 1, self.hidden_dim)
+        for _ in range(n):                                                    # set2set.py:47-55
+            q, hidden = self.lstm(q_star, hidden)
+            e = embedding @ torch.transpose(q, 1, 2)
+            a = torch.softmax(e, dim=1)
+            r = torch.sum(a * embedding, dim=1, keepdim=True)
+            q_star = torch.cat((q, r), dim=2)
+        q_star = torch.squeeze(q_star, dim=1)
+        return self.act(self.pred(q_star))
+
+
+class GcnSet2SetEncoder(GcnEncoderGraph):
+    """encoders.py:1137-1157 (method=base-set2set): masked GCN concat -> Set2Set readout -> pred_model."""
+
+    def __init__(self, input_dim, hidden_dim, embedding_dim, label_dim, num_layers,
+                 pred_hidden_dims=[], concat=True, bn=True, dropout=0.0, args=None):
+        super().__init__(input_dim, hidden_dim, embedding_dim, label_dim, num_layers, pred_hidden_dims, concat,
+                         bn, dropout, args=args)
+        self.s2s = Set2Set(self.pred_input_dim, self.pred_input_dim * 2)
+
+    def forward(self, x, adj, batch_num_nodes=None, **kwargs):
+        mask = None
+        if batch_num_nodes is not None:
+            mask = self.construct_mask(adj.size(1), batch_num_nodes, x)
+        emb = self.gcn_forward(x, adj, self.conv_first, self.conv_block, self.conv_last, mask)
+        return self.pred_model(self.s2s(emb))
 
 
 class SoftPoolingGcnEncoder(GcnEncoderGraph):

@@ -106,6 +106,10 @@ def run_case(ref, name, kind, seed, B, N, D, H, E, C, L, ratio, n_min, n_max, de
     if kind == 'soft':
         model = ref.SoftPoolingGcnEncoder(N, D, H, E, C, L, H, assign_ratio=ratio, num_pooling=1,
                                           bn=True, linkpred=True, assign_input_dim=D)
+    elif kind == 's2s':
+        # method=base-set2set (train.py:352-354): the reference's own GcnSet2SetEncoder + set2set.Set2Set; their
+        # .cuda() calls are the no-ops installed by load_reference (R2), torch.zeros follows the default dtype
+        model = ref.GcnSet2SetEncoder(D, H, E, C, L, bn=True)
     else:
         model = ref.GcnEncoderGraph(D, H, E, C, L, bn=True)
     # non-zero biases so that pad rows are non-trivial (they are normalize(b))
@@ -155,3 +159,4 @@ if __name__ == '__main__':
     run_case(ref, 'soft_l2',      'soft', 2, 3, 24, 5, 12, 12, 3, 2, 0.25, 1, 24, 0.20, 0.1)
     run_case(ref, 'base_small',   'base', 3, 5, 48, 7, 20, 20, 2, 3, 0.0, 3, 48, 0.10, 0.3)
     run_case(ref, 'base_l4',      'base', 4, 4, 32, 4, 10, 14, 4, 4, 0.0, 2, 32, 0.15, 0.2)
+    run_case(ref, 's2s_small',    's2s',  5, 4, 20, 5, 8, 8, 3, 3, 0.0, 2, 20, 0.20, 0.2)

@@ -21,6 +21,8 @@ def golden_model(g, mod, dtype=torch.float32, device='cpu'):
     if str(g['kind']) == 'soft':
         m = mod.SoftPoolingGcnEncoder(N, D, H, E, C, L, H, assign_ratio=float(g['ratio']), num_pooling=1,
                                       bn=True, linkpred=True, assign_input_dim=D)
+    elif str(g['kind']) == 's2s':
+        m = mod.GcnSet2SetEncoder(D, H, E, C, L, bn=True)
     else:
         m = mod.GcnEncoderGraph(D, H, E, C, L, bn=True)
     sd = {k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith('sd.')}

@@ -156,6 +156,37 @@ def test_base_with_pred_hidden_and_dd_like_dims():
     oracle_vs_candidate(make, 30, 3, 150, 89, 2, soft=False, density=0.03)
 
 
+@pytest.mark.parametrize('nb_mode,hidden,bn', [('rand', [], True), ('none', [10], True), ('tiny', [], False)])
+def test_set2set_encoder(nb_mode, hidden, bn):
+    """method=base-set2set (encoders.py:1137-1157 + set2set.py): GCN concat, mask, n LSTM/attention steps, pred_model --
+    forward, loss and every gradient (LSTM weights included) against the oracle; SURVEY 8(f) N4."""
+    make = lambda mod: mod.GcnSet2SetEncoder(6, 10, 12, 3, 3, pred_hidden_dims=hidden, bn=bn)
+    oracle_vs_candidate(make, 40 + len(hidden), 5, 30, 6, 3, nb_mode=nb_mode, soft=False)
+
+
+def test_set2set_module_standalone_and_wide_features():
+    """The Set2Set module on its own (d = 96: several feature chunks per lane, n = 70 steps) against the oracle's."""
+    torch.manual_seed(5)
+    B, n, d = 3, 70, 96
+    so = orc.Set2Set(d, 2 * d).double()
+    sc = enc().Set2Set(d, 2 * d)
+    sc.load_state_dict({k: v.float() for k, v in so.state_dict().items()})
+    sc = sc.cuda()
+    emb = 0.5 * torch.randn(B, n, d, dtype=torch.float64)
+    eo = emb.clone().requires_grad_()
+    oo = so(eo)
+    g = torch.randn_like(oo)
+    (oo * g).sum().backward()
+    ec = emb.float().cuda().requires_grad_()
+    oc = sc(ec)
+    (oc * g.float().cuda()).sum().backward()
+    torch.cuda.synchronize()
+    assert rel_l2(oc.detach().cpu().numpy(), oo.detach().numpy()) < 1e-5
+    assert rel_l2(ec.grad.cpu().numpy(), eo.grad.numpy()) < 1e-4
+    for (k, pc), (_, po) in zip(sc.named_parameters(), so.named_parameters()):
+        assert rel_l2(pc.grad.cpu().numpy(), po.grad.numpy()) < 1e-4, k
+
+
 def test_padding_invariance_and_pad_row_features_ignored():
     """SURVEY 8(a) probes: re-padding to a larger N (K fixed) and garbage in pad rows of x leave ypred unchanged."""
     e = enc()
