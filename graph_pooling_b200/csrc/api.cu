@@ -14,6 +14,12 @@ int colsum(const float* x, long long rows, int d, long long ld, float* out, int 
            cudaStream_t st);
 
 bool small_gcn_eligible(int B, int N, int din, int dout, int add_self);
+bool small_pool_eligible(int B, int N, int K, int F);
+int small_pool_fwd(const float* s, const float* z, long long ldz, const float* adj, const int32_t* nb, int B, int N,
+                   int K, int F, float* xp, float* t, float* ap, cudaStream_t st);
+int small_pool_bwd(const float* dxp, const float* dap, const float* s, const float* z, long long ldz, const float* adj,
+                   const float* t, const int32_t* nb, int B, int N, int K, int F, float* dz, long long lddz, int acc_dz,
+                   float* ds, int acc_ds, cudaStream_t st);
 int small_gcn_fwd(const float* x, long long ldx, const float* adj, const float* w, const float* bias, const int32_t* nb,
                   int B, int N, int din, int dout, int normalize, float* u, float* y, long long ldy, float* rnorm,
                   cudaStream_t st);
@@ -143,6 +149,8 @@ extern "C" int gp_pool_fwd(const float* s, const float* z, long long ldz, const 
   GP_REQUIRE(B > 0 && N > 0 && K > 0 && F > 0 && ldz >= F, "pool_fwd: bad dims");
   cudaStream_t st = S(stream);
   (void)precision;
+  // ENZYMES-sized graphs: one CTA per graph chains S^T Z, S^T A and (S^T A) S out of shared memory (small_gcn.cu)
+  if (small_pool_eligible(B, N, K, F)) return small_pool_fwd(s, z, ldz, adj, nb, B, N, K, F, xp, t, ap, st);
   const int lim = nb != nullptr;
   {   // X' = S^T Z
     gp_gemm g = mk(s, z, xp, K, F, N, B);
@@ -179,6 +187,8 @@ extern "C" int gp_pool_bwd(const float* dxp, const float* dap, const float* s, c
   GP_REQUIRE(B > 0 && N > 0 && K > 0 && F > 0 && ldz >= F && lddz >= F, "pool_bwd: bad dims");
   cudaStream_t st = S(stream);
   (void)precision;
+  if (dadj == nullptr && small_pool_eligible(B, N, K, F))
+    return small_pool_bwd(dxp, dap, s, z, ldz, adj, t, nb, B, N, K, F, dz, lddz, accumulate_dz, ds, accumulate_ds, st);
   const int lim = nb != nullptr;
   {   // dZ (+)= S dX'
     gp_gemm g = mk(s, dxp, dz, N, F, K, B);

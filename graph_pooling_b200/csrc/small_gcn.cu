@@ -60,6 +60,7 @@ __device__ __forceinline__ void stage_rows_t(float* dst, int ldd, const float* s
 
 // C[M x Nc] (+)= A[M x K] . B[K x Nc], all in shared memory, row-major with leading dimensions lda / ldb / ldc
 // (ldb, ldc multiples of 4; A zero-filled up to r4(M) rows, B zero-filled up to r4(Nc) columns).
+template <bool ACC = false>
 __device__ __forceinline__ void smem_gemm(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int ldb,
                                           int M, int Nc, int K, float* __restrict__ C, int ldc, const float* bias) {
   const int ntn = (Nc + 3) >> 2, ntm = (M + 3) >> 2;
@@ -88,9 +89,12 @@ __device__ __forceinline__ void smem_gemm(const float* __restrict__ A, int lda, 
       for (int e = 0; e < 4; ++e) bs[e] = c0 + e < Nc ? bias[c0 + e] : 0.f;
     }
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
-      *reinterpret_cast<float4*>(C + (i0 + r) * ldc + c0) =
-          make_float4(acc[r][0] + bs[0], acc[r][1] + bs[1], acc[r][2] + bs[2], acc[r][3] + bs[3]);
+    for (int r = 0; r < 4; ++r) {
+      float4 o = make_float4(acc[r][0] + bs[0], acc[r][1] + bs[1], acc[r][2] + bs[2], acc[r][3] + bs[3]);
+      float4* cp = reinterpret_cast<float4*>(C + (i0 + r) * ldc + c0);
+      if (ACC) { const float4 old = *cp; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+      *cp = o;
+    }
   }
 }
 
@@ -355,6 +359,166 @@ int small_gcn_bwd(const float* dv, const float* u, const float* x, long long ldx
     GP_TRY(colsum(ws, B, din * dout, wdt, dw, 0, tmp, st));
     if (db != nullptr) GP_TRY(colsum(ws + (long long)din * dout, B, dout, wdt, db, 0, tmp, st));
   }
+  return GP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Per-graph fused POOLING for small graphs (encoders.py:1278-1279): X' = S^T Z, T = S^T A, A' = T S as ONE kernel,
+// one CTA per graph, with S, Z, the real n_b x n_b adjacency block and the intermediate T = S^T A all in shared
+// memory (T is chained straight into the second product; it is also written out because the backward API takes
+// it).  Backward (no dA: level 0, or any level when the caller passes dadj == NULL):
+//     dZ (+)= S dX'        dS (+)= Z dX'^T + T^T dA' + A (S dA'^T)
+// again one kernel, every operand staged once.  Replaces 3 (forward) and 5 (backward) batched-GEMM launches that are
+// latency-bound at these sizes.  S rows beyond n_b are zero by construction (masked softmax), so only the real rows
+// are staged; pad rows / columns of the outputs are written as zeros (or left alone when accumulating).
+// ---------------------------------------------------------------------------------------------------------
+struct SmallPool {
+  const float* s; const float* z; long long ldz; const float* adj; const int32_t* nb;
+  int B, N, K, F;
+  float* xp; float* t; float* ap;                                     // forward outputs
+  const float* dxp; const float* dap; const float* tin;               // backward inputs
+  float* dz; long long lddz; int acc_dz; float* ds; int acc_ds;       // backward outputs
+};
+
+__host__ __device__ inline size_t small_pool_fwd_floats(int N, int K, int F) {
+  const size_t n4 = r4i(N), k4 = r4i(K), f4 = r4i(F);
+  const size_t wide = f4 > k4 ? f4 : k4;
+  return n4 * k4 + k4 * n4 + n4 * f4 + n4 * n4 + k4 * n4 + k4 * wide;
+}
+__host__ __device__ inline size_t small_pool_bwd_floats(int N, int K, int F) {
+  const size_t n4 = r4i(N), k4 = r4i(K), f4 = r4i(F);
+  return 4 * n4 * k4 + 2 * n4 * f4 + n4 * n4 + 2 * k4 * f4 + 2 * k4 * k4;
+}
+
+__global__ void __launch_bounds__(256) pool_small_fwd_kernel(const SmallPool p) {
+  extern __shared__ __align__(16) float sm[];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int N = p.N, K = p.K, F = p.F;
+  const int n = p.nb != nullptr ? min(max(p.nb[b], 0), N) : N;
+  const int n4 = r4i(n), k4 = r4i(K), f4 = r4i(F);
+  const int N4 = r4i(N);
+  const int wide = f4 > k4 ? f4 : k4;
+  float* Ss = sm;                                   // [N4][k4]  S (real rows)
+  float* St = Ss + (size_t)N4 * k4;                 // [k4][N4]  S^T
+  float* Zs = St + (size_t)k4 * N4;                 // [N4][f4]
+  float* As = Zs + (size_t)N4 * f4;                 // [N4][N4]  real adjacency block
+  float* Ts = As + (size_t)N4 * N4;                 // [k4][N4]  T = S^T A  (stays on chip for A' = T S)
+  float* Cs = Ts + (size_t)k4 * N4;                 // [k4][wide] output staging
+  const float* sb = p.s + (long long)b * N * K;
+  stage_rows(Ss, k4, sb, K, n, K, n4, k4);
+  stage_rows_t(St, n4, sb, K, n, K, n4, k4);
+  stage_rows(Zs, f4, p.z + (long long)b * N * p.ldz, p.ldz, n, F, n4, f4);
+  stage_rows(As, n4, p.adj + (long long)b * N * N, N, n, n, n4, n4);
+  cpa_wait_all();
+  __syncthreads();
+  smem_gemm(St, n4, Zs, f4, K, F, n, Cs, wide, nullptr);            // X' = S^T Z
+  __syncthreads();
+  float* xpb = p.xp + (long long)b * K * F;
+  for (int e = tid; e < K * F; e += 256) { const int k = e / F, c = e - k * F; xpb[e] = Cs[k * wide + c]; }
+  smem_gemm(St, n4, As, n4, K, n, n, Ts, n4, nullptr);              // T = S^T A
+  __syncthreads();
+  float* tb = p.t + (long long)b * K * N;
+  for (int e = tid; e < K * N; e += 256) { const int k = e / N, j = e - k * N; tb[e] = j < n ? Ts[k * n4 + j] : 0.f; }
+  smem_gemm(Ts, n4, Ss, k4, K, K, n, Cs, wide, nullptr);            // A' = T S   (Cs: X' was copied out above)
+  __syncthreads();
+  float* apb = p.ap + (long long)b * K * K;
+  for (int e = tid; e < K * K; e += 256) { const int k = e / K, c = e - k * K; apb[e] = Cs[k * wide + c]; }
+}
+
+__global__ void __launch_bounds__(256) pool_small_bwd_kernel(const SmallPool p) {
+  extern __shared__ __align__(16) float sm[];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int N = p.N, K = p.K, F = p.F;
+  const int n = p.nb != nullptr ? min(max(p.nb[b], 0), N) : N;
+  const int n4 = r4i(n), k4 = r4i(K), f4 = r4i(F);
+  const int N4 = r4i(N);
+  float* Ss = sm;                                   // [N4][k4]
+  float* Tt = Ss + (size_t)N4 * k4;                 // [N4][k4]  T^T
+  float* Wv = Tt + (size_t)N4 * k4;                 // [N4][k4]  W = S dA'^T
+  float* dSs = Wv + (size_t)N4 * k4;                // [N4][k4]
+  float* Zs = dSs + (size_t)N4 * k4;                // [N4][f4]
+  float* dZs = Zs + (size_t)N4 * f4;                // [N4][f4]
+  float* As = dZs + (size_t)N4 * f4;                // [N4][N4]
+  float* dXs = As + (size_t)N4 * N4;                // [k4][f4]  dX'
+  float* dXt = dXs + (size_t)k4 * f4;               // [f4][k4]  dX'^T
+  float* dAs = dXt + (size_t)k4 * f4;               // [k4][k4]  dA'
+  float* dAt = dAs + (size_t)k4 * k4;               // [k4][k4]  dA'^T
+  const float* dxb = p.dxp + (long long)b * K * F;
+  const float* dab = p.dap + (long long)b * K * K;
+  stage_rows(Ss, k4, p.s + (long long)b * N * K, K, n, K, n4, k4);
+  stage_rows_t(Tt, k4, p.tin + (long long)b * K * N, N, K, n, k4, n4);
+  stage_rows(Zs, f4, p.z + (long long)b * N * p.ldz, p.ldz, n, F, n4, f4);
+  stage_rows(As, n4, p.adj + (long long)b * N * N, N, n, n, n4, n4);
+  stage_rows(dXs, f4, dxb, F, K, F, k4, f4);
+  stage_rows_t(dXt, k4, dxb, F, K, F, k4, f4);
+  stage_rows(dAs, k4, dab, K, K, K, k4, k4);
+  stage_rows_t(dAt, k4, dab, K, K, K, k4, k4);
+  cpa_wait_all();
+  __syncthreads();
+  smem_gemm(Ss, k4, dXs, f4, n, F, K, dZs, f4, nullptr);            // dZ = S dX'
+  smem_gemm(Zs, f4, dXt, k4, n, K, F, dSs, k4, nullptr);            // dS = Z dX'^T
+  smem_gemm(Ss, k4, dAt, k4, n, K, K, Wv, k4, nullptr);             // W = S dA'^T
+  __syncthreads();
+  smem_gemm<true>(Tt, k4, dAs, k4, n, K, K, dSs, k4, nullptr);      // dS += T^T dA'
+  __syncthreads();
+  smem_gemm<true>(As, n4, Wv, k4, n, K, n, dSs, k4, nullptr);       // dS += A W
+  __syncthreads();
+  float* dzb = p.dz + (long long)b * N * p.lddz;
+  for (int e = tid; e < N * F; e += 256) {
+    const int i = e / F, c = e - i * F;
+    const float v = i < n ? dZs[i * f4 + c] : 0.f;
+    float* o = dzb + (long long)i * p.lddz + c;
+    if (p.acc_dz) { if (i < n) *o += v; } else *o = v;
+  }
+  float* dsb = p.ds + (long long)b * N * K;
+  for (int e = tid; e < N * K; e += 256) {
+    const int i = e / K, c = e - i * K;
+    const float v = i < n ? dSs[i * k4 + c] : 0.f;
+    if (p.acc_ds) { if (i < n) dsb[e] += v; } else dsb[e] = v;
+  }
+}
+
+static bool small_pool_enabled() {
+  static int en = -1;
+  if (en < 0) { const char* e = getenv("GP_NO_SMALL_POOL"); en = (e != nullptr && atoi(e) != 0) ? 0 : 1; }
+  return en != 0;
+}
+
+bool small_pool_eligible(int B, int N, int K, int F) {
+  if (!small_pool_enabled() || N > 128 || K > 64 || F > 512 || B > 2147483647 / 2) return false;
+  return small_pool_fwd_floats(N, K, F) * 4 <= (size_t)kSmallMaxSmem && small_pool_bwd_floats(N, K, F) * 4 <= (size_t)kSmallMaxSmem;
+}
+
+static int small_pool_cfg() {
+  static bool cfgd = false;
+  if (!cfgd) {
+    GP_CUDA(cudaFuncSetAttribute(pool_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallMaxSmem));
+    GP_CUDA(cudaFuncSetAttribute(pool_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallMaxSmem));
+    cfgd = true;
+  }
+  return GP_OK;
+}
+
+int small_pool_fwd(const float* s, const float* z, long long ldz, const float* adj, const int32_t* nb, int B, int N,
+                   int K, int F, float* xp, float* t, float* ap, cudaStream_t st) {
+  GP_TRY(small_pool_cfg());
+  SmallPool p = {};
+  p.s = s; p.z = z; p.ldz = ldz; p.adj = adj; p.nb = nb; p.B = B; p.N = N; p.K = K; p.F = F;
+  p.xp = xp; p.t = t; p.ap = ap;
+  pool_small_fwd_kernel<<<B, 256, small_pool_fwd_floats(N, K, F) * 4, st>>>(p);
+  GP_LAUNCHED();
+  return GP_OK;
+}
+
+int small_pool_bwd(const float* dxp, const float* dap, const float* s, const float* z, long long ldz, const float* adj,
+                   const float* t, const int32_t* nb, int B, int N, int K, int F, float* dz, long long lddz, int acc_dz,
+                   float* ds, int acc_ds, cudaStream_t st) {
+  GP_TRY(small_pool_cfg());
+  SmallPool p = {};
+  p.s = s; p.z = z; p.ldz = ldz; p.adj = adj; p.nb = nb; p.B = B; p.N = N; p.K = K; p.F = F;
+  p.dxp = dxp; p.dap = dap; p.tin = t; p.dz = dz; p.lddz = lddz; p.acc_dz = acc_dz; p.ds = ds; p.acc_ds = acc_ds;
+  pool_small_bwd_kernel<<<B, 256, small_pool_bwd_floats(N, K, F) * 4, st>>>(p);
+  GP_LAUNCHED();
   return GP_OK;
 }
 

@@ -199,7 +199,8 @@ def test_softmax_mask_fwd_bwd(K):
     assert rel_l2(dt.cpu().numpy(), tt.grad.numpy()) < TOL
 
 
-@pytest.mark.parametrize('B,N,K,F,use_nb,sym', [(3, 50, 12, 20, 1, 0), (2, 130, 32, 90, 1, 1), (2, 24, 6, 8, 0, 0)])
+@pytest.mark.parametrize('B,N,K,F,use_nb,sym', [(3, 50, 12, 20, 1, 0), (2, 130, 32, 90, 1, 1), (2, 24, 6, 8, 0, 0),
+                                                   (20, 100, 10, 90, 1, 1), (5, 33, 7, 13, 1, 0), (3, 128, 32, 96, 0, 1)])
 def test_pool_fwd_bwd(B, N, K, F, use_nb, sym):
     from graph_pooling_b200._lib import call
     _, adj, nb, _ = synth_batch(3, B, N, 2, 2, N, 2, density=0.2, symmetric=bool(sym))
@@ -234,6 +235,16 @@ def test_pool_fwd_bwd(B, N, K, F, use_nb, sym):
     assert rel_l2(dz.cpu().numpy(), z_t.grad.numpy()) < TOL
     mm = m.numpy()
     assert rel_l2(dsb.cpu().numpy() * mm, s_t.grad.numpy() * mm) < TOL     # pad rows of dS are masked downstream
+    # T = S^T A is an output of the forward (the backward reads it); pad columns are zero
+    t_ref = torch.tensor(s_np, dtype=torch.float64).transpose(1, 2) @ torch.tensor(adj, dtype=torch.float64)
+    assert rel_l2(t.cpu().numpy(), t_ref.numpy()) < TOL
+    # accumulate flags: dZ / dS are added to what the buffers hold (real rows; pad rows are left alone)
+    dz2, ds2 = torch.ones_like(dz), torch.ones_like(dsb)
+    call('gp_pool_bwd', gxc.data_ptr(), gac.data_ptr(), sc.data_ptr(), zc.data_ptr(), F, ac.data_ptr(),
+         t.data_ptr(), nbp, B, N, K, F, dz2.data_ptr(), F, 1, ds2.data_ptr(), 1, None, ws.data_ptr(), 0, st())
+    torch.cuda.synchronize()
+    assert rel_l2((dz2 - 1).cpu().numpy(), dz.cpu().numpy()) < 1e-5
+    assert rel_l2((ds2 - 1).cpu().numpy() * mm, dsb.cpu().numpy() * mm) < 1e-5
 
 
 @pytest.mark.parametrize('B,N,K,use_nb,sym', [(3, 70, 10, 1, 1), (2, 130, 33, 1, 0), (2, 20, 4, 0, 1)])
