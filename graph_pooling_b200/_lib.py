@@ -123,6 +123,7 @@ _PROTOS = {
     'gp_fill_f32': [c_f, c_ll, C.c_float, c_f],
     'gp_axpy_f32': [c_f, c_f, c_ll, C.c_float, c_f],
     'gp_fill_i32': [c_f, c_ll, c_i, c_f],
+    'gp_dropout_f32': [c_f, c_ll, c_ll, c_i, C.c_float, C.c_ulonglong, c_f, c_ll, c_f, c_ll, c_f],
     'gp_set2set_fwd': [c_f, c_ll, c_f, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f],
     'gp_set2set_bwd': [c_f, c_ll, c_f, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_f, c_f, c_ll, c_f, c_f, c_f, c_f],
     'gp_pad_copy_f32': [c_f, c_ll, c_ll, c_i, c_f, c_ll, c_ll, c_i, C.c_float, c_f],

@@ -519,6 +519,30 @@ __global__ void pad_copy_kernel(const float* __restrict__ src, long long ld_src,
     dst[r * ld_dst + c] = (r < rows && c < cols) ? src[r * ld_src + c] : fill;
   }
 }
+// Dropout of a GraphConv input (encoders.py:316-317, nn.Dropout in training mode): y = keep ? x / (1 - p) : 0 with
+// keep decided by a counter-based hash of (seed, row * d + column) -- the same call with the same seed reproduces
+// the mask, which is how the backward applies it to the input gradient (in place: y == x).
+__device__ __forceinline__ bool dropout_keep(unsigned long long seed, unsigned long long idx, float p) {
+  unsigned long long z = seed + (idx + 1ull) * 0x9E3779B97F4A7C15ull;              // splitmix64 finaliser
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (float)(unsigned)(z >> 40) * (1.f / 16777216.f) >= p;                   // 24 uniform bits
+}
+__global__ void dropout_kernel(const float* __restrict__ x, long long ldx, long long rows, int d, float p,
+                               unsigned long long seed, float* __restrict__ y, long long ldy,
+                               __nv_bfloat16* __restrict__ yb, long long ldyb) {
+  const float scale = 1.f / (1.f - p);
+  const long long total = rows * d;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / d;
+    const int c = (int)(i - r * d);
+    const float v = dropout_keep(seed, (unsigned long long)i, p) ? x[r * ldx + c] * scale : 0.f;
+    if (y != nullptr) y[r * ldy + c] = v;
+    if (yb != nullptr) yb[r * ldyb + c] = __float2bfloat16_rn(v);
+  }
+}
 __global__ void axpy_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float a) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] = fmaf(a, x[i], y[i]);
@@ -788,6 +812,18 @@ extern "C" int gp_pad_copy_f32(const float* src, long long ld_src, long long row
   long long blocks = (rows_dst * cols_dst + 255) / 256;
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
   pad_copy_kernel<<<(int)blocks, 256, 0, S(stream)>>>(src, ld_src, rows, cols, dst, ld_dst, rows_dst, cols_dst, fill);
+  GP_LAUNCHED();
+  return GP_OK;
+}
+
+extern "C" int gp_dropout_f32(const float* x, long long ldx, long long rows, int d, float p, unsigned long long seed,
+                              float* y, long long ldy, void* y_bf16, long long ldyb, gp_stream_t stream) {
+  GP_REQUIRE(x && (y || y_bf16) && rows > 0 && d > 0 && ldx >= d && p >= 0.f && p < 1.f, "dropout: bad args");
+  GP_REQUIRE((!y || ldy >= d) && (!y_bf16 || ldyb >= d), "dropout: bad output strides");
+  long long blocks = (rows * d + 255) / 256;
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  dropout_kernel<<<(int)blocks, 256, 0, S(stream)>>>(x, ldx, rows, d, p, seed, y, ldy,
+                                                    reinterpret_cast<__nv_bfloat16*>(y_bf16), ldyb);
   GP_LAUNCHED();
   return GP_OK;
 }

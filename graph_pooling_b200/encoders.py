@@ -71,13 +71,13 @@ def _fwd_tc(ctx, plan, x, adj, assign_x, params):
     dual = False
     if plan.soft:
         wa0, ba0 = conv(plan.assign[0])
-        dual = T.dual_ok(w0, wa0) and not os.environ.get('GP_NO_DUAL')
+        dual = T.dual_ok(w0, wa0) and not os.environ.get('GP_NO_DUAL') and not any(plan.emb_drop)
     if dual:        # embedding + level-0 assignment GCN in lock-step: one pass over A per layer for both
         K0 = plan.assign_dims[0]
         (z, zb, c_emb), pre_as = T.dual_stack_forward(ws, xb, D, xab, xa_d, adjb, nb, B, N, w0, b0, plan.bn, wa0, ba0,
                                                       True, pad_lastA=_kpad(K0) if _kpad(K0) != K0 else 0)
     else:
-        z, zb, c_emb = T.stack_forward(ws, xb, D, adjb, nb, B, N, w0, b0, plan.bn)
+        z, zb, c_emb = T.stack_forward(ws, xb, D, adjb, nb, B, N, w0, b0, plan.bn, drops=plan.emb_drop, seed=plan.seed)
     call('gp_readout_max_fwd', z.data_ptr(), Fw, E._p(nb) if plan.soft else None, B, N, Fw,
          out.data_ptr(), arg.data_ptr(), ldo, st)
     levels, S0 = [], None
@@ -110,7 +110,8 @@ def _fwd_tc(ctx, plan, x, adj, assign_x, params):
             if pad:                                      # "node counts" of the pooled level: Kr real clusters of K
                 nbk = ws.i(B)
                 call('gp_fill_i32', nbk.data_ptr(), C.c_longlong(B), Kr, st)
-            z2, z2b, c_post = T.stack_forward(ws, xpb, Fw, apb, nbk, B, K, wq, bq, plan.bn_post)
+            z2, z2b, c_post = T.stack_forward(ws, xpb, Fw, apb, nbk, B, K, wq, bq, plan.bn_post,
+                                              drops=plan.post_drop[i], seed=plan.seed + 4096 * (i + 1))
             # the reference's max over the pooled level's clusters (encoders.py:1287): the Kr real rows only
             call('gp_readout_max_fwd_x', z2.data_ptr(), Fw, K, None, B, Kr, Fw, out.data_ptr() + (i + 1) * Fw * 4,
                  arg.data_ptr() + (i + 1) * Fw * 4, ldo, st)
@@ -240,7 +241,8 @@ class _EncoderFn(torch.autograd.Function):
         ldo = Fw * (P + 1)
 
         w0, b0 = conv(plan.emb)
-        z, c_emb = E.stack_forward(ws, x.data_ptr(), D, D, adj, nb, B, N, w0, b0, plan.add_self, plan.bn, prec)
+        z, c_emb = E.stack_forward(ws, x.data_ptr(), D, D, adj, nb, B, N, w0, b0, plan.add_self, plan.bn, prec,
+                                   drops=plan.emb_drop, seed=plan.seed)
         # base path: no mask ever (encoders.py:1087 builds it, nothing uses it); soft: mask of :1078
         call('gp_readout_max_fwd', z.data_ptr(), Fw, E._p(nb) if plan.soft else None, B, N, Fw,
              out.data_ptr(), arg.data_ptr(), ldo, st)
@@ -265,7 +267,7 @@ class _EncoderFn(torch.autograd.Function):
                      K, Fw, xp.data_ptr(), t.data_ptr(), ap.data_ptr(), prec, st)
                 wq, bq = conv(plan.post[i])
                 z2, c_post = E.stack_forward(ws, xp.data_ptr(), Fw, Fw, ap, None, B, K, wq, bq, plan.add_self,
-                                             plan.bn_post, prec)
+                                             plan.bn_post, prec, drops=plan.post_drop[i], seed=plan.seed + 4096 * (i + 1))
                 call('gp_readout_max_fwd', z2.data_ptr(), Fw, None, B, K, Fw, out.data_ptr() + (i + 1) * Fw * 4,
                      arg.data_ptr() + (i + 1) * Fw * 4, ldo, st)
                 levels.append(dict(K=K, N=cur_N, nb=cur_nb, adj=cur_adj, z=cur_z, S=S.detach(), za=za, Fa=Fa, c_as=c_as,
@@ -536,7 +538,35 @@ class GraphConv(nn.Module):
             self.bias = None
 
     def forward(self, x, adj):
+        if self.dropout > 0.001 and self.training:                            # encoders.py:316-317
+            x = _DropoutFn.apply(E._chk(x, 'x'), float(self.dropout), _draw_seed())
         return _GraphConvFn.apply(x, adj, self.weight, self.bias, self.add_self, self.normalize_embedding)
+
+
+def _draw_seed():
+    """Base seed of one forward call's dropout masks, from torch's CPU generator (torch.manual_seed reproduces it)."""
+    if torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
+        raise NotImplementedError('gp_b200: dropout inside a captured CUDA graph would replay one fixed mask')
+    return int(torch.randint(0, 1 << 62, (1,)).item())
+
+
+class _DropoutFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p, seed):
+        y = torch.empty_like(x)
+        d = x.shape[-1]
+        E.dropout(x.data_ptr(), d, x.numel() // d, d, p, seed, y.data_ptr(), d)
+        ctx.ps = (p, seed)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        dy = E._chk(dy, 'dy')
+        dx = torch.empty_like(dy)
+        d = dy.shape[-1]
+        E.dropout(dy.data_ptr(), d, dy.numel() // d, d, ctx.ps[0], ctx.ps[1], dx.data_ptr(), d)
+        return dx, None, None
 
 
 class _GraphConvFn(torch.autograd.Function):
@@ -595,9 +625,6 @@ class GcnEncoderGraph(nn.Module):
         self.bias = True
         if args is not None:
             self.bias = args.bias
-        if dropout > 0.001:
-            # only conv_block layers would use it (encoders.py:1015); callers default to 0.0
-            raise NotImplementedError('gp_b200: dropout > 0 is not implemented on the CUDA path')
         self.conv_first, self.conv_block, self.conv_last = self.build_conv_layers(
             input_dim, hidden_dim, embedding_dim, num_layers, add_self, normalize=True, dropout=dropout)
         self.act = nn.ReLU()
@@ -659,6 +686,12 @@ class GcnEncoderGraph(nn.Module):
             pairs.append((iw, ib))
         return pairs
 
+    def _drops(self, block):
+        """Dropout probability per layer of a stack: only conv_block layers have one (encoders.py:1015), and only in
+        training mode (nn.Dropout)."""
+        mid = [float(m.dropout) if (self.training and m.dropout > 0.001) else 0.0 for m in block]
+        return [0.0] + mid + [0.0]
+
     def _pred_pairs(self, params, model):
         mods = [model] if isinstance(model, nn.Linear) else [m for m in model if isinstance(m, nn.Linear)]
         pairs = []
@@ -699,6 +732,9 @@ class GcnEncoderGraph(nn.Module):
         plan.label_dim = self.label_dim
         params = []
         plan.emb = self._conv_pairs(params, self.conv_first, self.conv_block, self.conv_last)
+        plan.emb_drop = self._drops(self.conv_block)
+        plan.post_drop = []
+        plan.seed = _draw_seed() if any(plan.emb_drop) else 0
         plan.F = sum(params[iw].shape[1] for iw, _ in plan.emb)
         plan.douts_last = self.conv_last.weight.shape[1]
         return plan, params, x, adj
@@ -780,7 +816,7 @@ def _s2s_backward(ws, e_ptr, lde, nb, B, N, d, lstm_params, saved, dqs):
          gates.data_ptr(), cells.data_ptr(), att.data_ptr(), dqs.data_ptr(), C.c_longlong(2 * d), dz.data_ptr(),
          dr.data_ptr(), de.data_ptr(), st)
     rows = B * (N + 1)
-    split = max(1, min(64, rows // 1024))
+    split = max(1, min(512, rows // 1024))     # split-K over the rows: enough CTAs to stream them at HBM rate
     dwih, dwhh = ws.f(4 * d, 2 * d), ws.f(4 * d, d)
     # dW_ih = DZ^T QS ;  dW_hh = DZ^T QS[:, :d]  (h_{t-1} is the first half of q*_{t-1})
     E.bgemm(dz.data_ptr(), qs.data_ptr(), dwih.data_ptr(), 4 * d, 2 * d, rows, 1, (0, 1, 4 * d), (0, 2 * d, 1),
@@ -846,7 +882,8 @@ class _S2SEncoderFn(torch.autograd.Function):
         nb = plan.nb_dev
         w0 = [_wb(params, p)[0] for p in plan.emb]
         b0 = [_wb(params, p)[1] for p in plan.emb]
-        z, c_emb = E.stack_forward(ws, x.data_ptr(), D, D, adj, nb, B, N, w0, b0, plan.add_self, plan.bn, E.F32)
+        z, c_emb = E.stack_forward(ws, x.data_ptr(), D, D, adj, nb, B, N, w0, b0, plan.add_self, plan.bn, E.F32,
+                                   drops=plan.emb_drop, seed=plan.seed)
         d = plan.F
         lstm_params = tuple(None if i is None else params[i] for i in plan.lstm)
         saved = _s2s_forward(ws, z.data_ptr(), d, nb, B, N, d, lstm_params)
@@ -936,8 +973,6 @@ class SoftPoolingGcnEncoder(GcnEncoderGraph):
             # the reference's gcn_forward always concatenates (encoders.py:1078) while the post-pool
             # GCN is sized for embedding_dim only (:1185-1186): concat=False cannot run there either.
             raise NotImplementedError('gp_b200: SoftPoolingGcnEncoder requires concat=True (as the reference does)')
-        if dropout > 0.001:
-            raise NotImplementedError('gp_b200: dropout > 0 is not implemented on the CUDA path')
         add_self = not concat
         self.num_pooling = num_pooling
         self.linkpred = linkpred
@@ -1000,11 +1035,14 @@ class SoftPoolingGcnEncoder(GcnEncoderGraph):
         for i in range(self.num_pooling):
             plan.post.append(self._conv_pairs(params, self.conv_first_after_pool[i], self.conv_block_after_pool[i],
                                               self.conv_last_after_pool[i]))
+            plan.post_drop.append(self._drops(self.conv_block_after_pool[i]))
             plan.assign.append(self._conv_pairs(params, self.assign_conv_first_modules[i],
                                                 self.assign_conv_block_modules[i],
                                                 self.assign_conv_last_modules[i]))
             plan.assign_pred.append(self._pred_pairs(params, self.assign_pred_modules[i])[0])
         plan.pred = self._pred_pairs(params, self.pred_model)
+        if any(any(d) for d in plan.post_drop) and not plan.seed:
+            plan.seed = _draw_seed()
         self._plan = plan
         ypred, S0 = _EncoderFn.apply(plan, x, adj, x_a, *params)
         self.assign_tensors = [S0] + plan.all_S[1:]

@@ -82,10 +82,21 @@ def bgemm(A, B, Cp, M, N, K, batch, sA, sB, sC, lim=None, lim_m=0, lim_n=0, lim_
 # ------------------------------------------------------------------------------------------
 class StackCtx:
     __slots__ = ('B', 'N', 'din', 'douts', 'F', 'x_ptr', 'ldx', 'adj', 'nb', 'weights', 'biases', 'add_self',
-                 'bn', 'zcat', 'layers', 'keep')
+                 'bn', 'zcat', 'layers', 'keep', 'drops')
 
 
-def stack_forward(ws, x_ptr, ldx, din, adj, nb, B, N, weights, biases, add_self, bn, prec, keep=()):
+def layer_seed(seed, l):
+    """Per-layer dropout seed derived from the forward call's base seed (also used by the tests to rebuild a mask)."""
+    return (int(seed) + 0x632BE5AB * (l + 1)) & ((1 << 62) - 1)
+
+
+def dropout(x_ptr, ldx, rows, d, p, seed, y_ptr, ldy, yb_ptr=None, ldyb=0):
+    call('gp_dropout_f32', x_ptr, C.c_longlong(ldx), C.c_longlong(rows), d, C.c_float(p), C.c_ulonglong(seed),
+         y_ptr, C.c_longlong(ldy), yb_ptr, C.c_longlong(ldyb), _stream())
+
+
+def stack_forward(ws, x_ptr, ldx, din, adj, nb, B, N, weights, biases, add_self, bn, prec, keep=(), drops=None,
+                  seed=0):
     """Runs L GraphConv layers (+ReLU+BN between) and returns the UNMASKED concat buffer
     zcat [B,N,F]; the mask of encoders.py:1078-1080 is applied by the consumers (readout treats
     pad rows as 0; pooling multiplies by S whose pad rows are 0)."""
@@ -98,12 +109,19 @@ def stack_forward(ws, x_ptr, ldx, din, adj, nb, B, N, weights, biases, add_self,
     ctx.B, ctx.N, ctx.din, ctx.douts, ctx.F = B, N, din, douts, Fw
     ctx.x_ptr, ctx.ldx, ctx.adj, ctx.nb = x_ptr, ldx, adj, nb
     ctx.weights, ctx.biases, ctx.add_self, ctx.bn = weights, biases, add_self, bn
-    ctx.zcat, ctx.layers, ctx.keep = zcat, [], keep
+    ctx.zcat, ctx.layers, ctx.keep = zcat, [], list(keep)
+    ctx.drops = [None] * L
     cur_ptr, cur_ld, cur_d, off = x_ptr, ldx, din, 0
     zp = zcat.data_ptr()
     for l in range(L):
         last = l == L - 1
         dout = douts[l]
+        if drops is not None and drops[l] > 0.0:          # nn.Dropout on this layer's input (encoders.py:316-317)
+            xd = ws.f(B, N, cur_d)
+            ctx.drops[l] = (float(drops[l]), layer_seed(seed, l))
+            dropout(cur_ptr, cur_ld, B * N, cur_d, ctx.drops[l][0], ctx.drops[l][1], xd.data_ptr(), cur_d)
+            ctx.keep.append(xd)
+            cur_ptr, cur_ld = xd.data_ptr(), cur_d
         u = ws.f(B, N, cur_d)
         rnorm = ws.f(B, N)
         slot = zp + off * 4
@@ -170,6 +188,9 @@ def stack_backward(ws, ctx, dz_ptr, lddz, dout_ptr, arg_ptr, ldo, need_dx, dadj,
         call('gp_graphconv_bwd', _p(dv), _p(u), x_ptr, ldx, _p(ctx.adj), _p(w), _p(ctx.nb), B, N, din, dout,
              int(ctx.add_self), _p(dw), _p(db), _p(du), _p(dx), _p(dadj), _p(cs), prec, st)
         grads[l] = (dw, db)
+        if dx is not None and ctx.drops[l] is not None:   # gradient of the dropped input -> gradient of the input
+            pd, sd = ctx.drops[l]
+            dropout(dx.data_ptr(), din, B * N, din, pd, sd, dx.data_ptr(), din)
         dxn = dx
     return grads, dxn
 
@@ -189,7 +210,7 @@ def linear_bwd(ws, dy, x_ptr, ldx, rows, w, has_bias, need_dx, dx_ptr=None, lddx
     """Returns (dW, db, dx); with dx_ptr the input gradient is written there (row stride lddx)."""
     out_f, in_f = int(w.shape[0]), int(w.shape[1])
     dw = ws.f(out_f, in_f)
-    split = max(1, min(64, rows // 1024))
+    split = max(1, min(512, rows // 1024))     # split-K over the rows: enough CTAs to stream them at HBM rate
     bgemm(_p(dy), x_ptr, _p(dw), out_f, in_f, rows, 1, (0, 1, out_f), (0, ldx, 1), (0, in_f, 1), split_k=split)
     db = None
     if has_bias:

@@ -265,14 +265,23 @@ def _stack_end(ws, ctx):
     return ctx.zcat, ctx.zb, ctx
 
 
-def stack_forward(ws, xb, din, adjb, nb, B, N, weights, biases, bn, u0=None, pad_last=0):
+def stack_forward(ws, xb, din, adjb, nb, B, N, weights, biases, bn, u0=None, pad_last=0, drops=None, seed=0):
     """TC version of engine.stack_forward (add_self unsupported).  xb/adjb: bf16 operands.
     Per layer:  U = A.X (tcgen05)  ->  _layer_forward.
     u0: optional precomputed U of the first layer (shared with another stack that has the same A and X).
     Returns (zcat fp32 [B,N,F], zb bf16 operand of the same concat, ctx)."""
     ctx = _stack_begin(ws, xb, din, adjb, nb, B, N, weights, biases, bn, pad_last)
     nbp, lim = E._p(nb), int(nb is not None)
+    ctx.drops = [None] * len(weights)
     for l in range(len(weights)):
+        if drops is not None and drops[l] > 0.0 and l > 0:
+            # nn.Dropout on this layer's input (encoders.py:316-317): the dropped bf16 operand is made from the fp32
+            # concat slot of the previous layer; the backward re-applies the mask to dX from the same seed
+            ctx.drops[l] = (float(drops[l]), E.layer_seed(seed, l))
+            xdb = bfbuf(ws, B, N, ctx.cur_d)
+            E.dropout(ctx.zcat.data_ptr() + ctx.offs[l - 1] * 4, ctx.F, B * N, ctx.cur_d, ctx.drops[l][0],
+                      ctx.drops[l][1], None, 0, xdb.ptr, xdb.ld)
+            ctx.cur = xdb
         if l == 0 and u0 is not None:
             ub = u0
         else:
@@ -399,6 +408,9 @@ def stack_backward(ws, ctx, dz_ptr, lddz, dout_ptr, arg_ptr, ldo, need_dx, dadj)
                 dx = ws.f(B, N, din)
                 tcgemm(ctx.adjb, MN, dub, MN, N, din, N, B, Cf=(dx.data_ptr(), din, N * din), lim=nbp, lim_m=lim,
                        lim_k=lim)
+                if getattr(ctx, 'drops', None) is not None and ctx.drops[l] is not None:
+                    pd, sd = ctx.drops[l]
+                    E.dropout(dx.data_ptr(), din, B * N, din, pd, sd, dx.data_ptr(), din)
             if dadj is not None:
                 # dA += dU X^T : dU K-major ; B[n=node, k=din] = X stored [node rows, din cols] = K-major
                 tcgemm(dub, KM, xb, KM, N, N, din, B, Cf=(dadj.data_ptr(), dadj.shape[2], N * dadj.shape[2]), beta=1.0)

@@ -409,6 +409,12 @@ int gp_set2set_bwd(const float* E, long long ldE, const int32_t* nb, int B, int 
 int gp_fill_f32(float* x, long long n, float v, gp_stream_t stream);
 int gp_axpy_f32(const float* x, float* y, long long n, float a, gp_stream_t stream);
 int gp_fill_i32(int32_t* x, long long n, int32_t v, gp_stream_t stream);
+/* Dropout of a GraphConv input (encoders.py:316-317; conv_block layers, training mode): y = keep ? x/(1-p) : 0,
+ * fp32 and/or bf16 output, keep = hash(seed, row*d + col) >= p.  Reproducible from the seed: the backward calls it
+ * in place on the input gradient (x == y) with the forward's seed.  The mask stream is this library's own -- it
+ * cannot reproduce torch's generator, only nn.Dropout's distribution. */
+int gp_dropout_f32(const float* x, long long ldx, long long rows, int d, float p, unsigned long long seed,
+                   float* y, long long ldy, void* y_bf16, long long ldyb, gp_stream_t stream);
 /* dst [rows_dst, cols_dst] = src [rows, cols] in the top-left corner, `fill` elsewhere (padded parameter / gradient
  * copies when the assignment width is padded to a multiple of 8) */
 int gp_pad_copy_f32(const float* src, long long ld_src, long long rows, int cols, float* dst, long long ld_dst,

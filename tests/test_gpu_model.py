@@ -187,6 +187,90 @@ def test_set2set_module_standalone_and_wide_features():
         assert rel_l2(pc.grad.cpu().numpy(), po.grad.numpy()) < 1e-4, k
 
 
+@pytest.mark.parametrize('kind,prec', [('base', 0), ('soft', 0), ('base', 1), ('soft', 1), ('s2s', 0)])
+def test_dropout_matches_oracle_with_the_same_masks(kind, prec):
+    """dropout > 0 (conv_block layers only, training mode only: encoders.py:316-317,1015,1187).  The library draws its
+    own masks (counter-based hash of a seed taken from torch's generator), so parity is checked with the SAME masks:
+    they are rebuilt from the forward's seed and injected into the oracle's nn.Dropout slots."""
+    from graph_pooling_b200 import engine as E_
+    e, p = enc(), 0.3
+    N, D, H, C, B, L, K = 40, 6, 16, 3, 5, 4, 10          # L = 4: two conv_block layers per stack
+    soft = kind == 'soft'
+    if kind == 'base':
+        make = lambda mod: mod.GcnEncoderGraph(D, H, H, C, L, dropout=p)
+    elif kind == 's2s':
+        make = lambda mod: mod.GcnSet2SetEncoder(D, H, H, C, L, dropout=p)
+    else:
+        make = lambda mod: mod.SoftPoolingGcnEncoder(N, D, H, H, C, L, H, assign_ratio=0.25, dropout=p)
+    torch.manual_seed(77)
+    mo = make(orc)
+    g = torch.Generator().manual_seed(78)
+    with torch.no_grad():
+        for k, q in mo.named_parameters():
+            if k.endswith('bias'):
+                q.copy_(0.2 * torch.randn(q.shape, generator=g))
+    mc = make(e)
+    mc.load_state_dict(mo.state_dict(), strict=True)
+    mc = mc.cuda()
+    mc.precision = prec
+    x, adj, nb, label = synth_batch(79, B, N, D, 5, N, C, 0.12)
+    # eval mode: nn.Dropout is the identity -> identical to a model built without dropout
+    mc.eval()
+    m0 = (e.GcnEncoderGraph(D, H, H, C, L) if kind == 'base' else e.GcnSet2SetEncoder(D, H, H, C, L) if kind == 's2s'
+          else e.SoftPoolingGcnEncoder(N, D, H, H, C, L, H, assign_ratio=0.25)).cuda()
+    m0.load_state_dict(mc.state_dict())
+    m0.precision = prec
+    xc, ac = torch.tensor(x).cuda(), torch.tensor(adj).cuda()
+    with torch.no_grad():
+        assert torch.equal(mc(xc, ac, nb, assign_x=xc), m0(xc, ac, nb, assign_x=xc))
+    mc.train()
+    yp, loss = run_candidate(mc, x, adj, nb, label, soft)
+    plan = mc._plan
+    assert plan.seed != 0
+    y_again, _ = run_candidate(mc, x, adj, nb, label, soft)
+    assert not torch.equal(yp, y_again)                   # a fresh mask per forward call
+    yp, loss = run_candidate(mc, x, adj, nb, label, soft)
+    plan = mc._plan
+
+    def mask(seed, l, Bn, rows):
+        ones = torch.ones(Bn * rows, H, device='cuda')
+        out = torch.empty_like(ones)
+        E_.dropout(ones.data_ptr(), H, Bn * rows, H, p, E_.layer_seed(seed, l), out.data_ptr(), H)
+        torch.cuda.synchronize()
+        return out.view(Bn, rows, H).cpu()
+
+    def inject(m):
+        blocks, seed, rows = (m.conv_block_after_pool[0], plan.seed + 4096, K) if soft else (m.conv_block, plan.seed, N)
+        for i, blk in enumerate(blocks):
+            # the tensor-core schedule runs the pooled level at r8(K) rows per graph (dead clusters): same mask stream
+            alloc = (rows + 7) // 8 * 8 if (soft and prec == 1) else rows
+            mk = mask(seed, i + 1, B, alloc)[:, :rows].contiguous()
+            keep = float((mk > 0).float().mean())
+            assert abs(keep - (1 - p)) < 0.06
+            assert bool(((mk == 0) | ((mk - 1 / (1 - p)).abs() < 1e-5)).all())
+            del blk.dropout_layer
+            object.__setattr__(blk, 'dropout_layer', (lambda mk: lambda t: t * mk.to(t.dtype))(mk))
+        return m
+
+    res = {}
+    for tag, dt in (('f32', torch.float32), ('f64', torch.float64)):
+        m = inject(copy.deepcopy(mo).to(dt).train())
+        yo, lo = orc.train_step(m, torch.tensor(x, dtype=dt), torch.tensor(adj, dtype=dt), torch.tensor(label), nb)
+        res[tag] = (yo.detach().numpy(), lo.item(), {k: q.grad.numpy() for k, q in m.named_parameters()})
+    y64, l64, g64 = res['f64']
+    cand = {k: q.grad.cpu().numpy() for k, q in mc.named_parameters()}
+    if prec == 0:
+        assert rel_l2(yp.detach().cpu().numpy(), y64) < OUT_TOL
+        assert abs(loss.item() - l64) < OUT_TOL * max(1.0, abs(l64))
+        grade_grads(cand, res['f32'][2], g64)
+    else:
+        assert rel_l2(yp.detach().cpu().numpy(), y64) < 2e-2
+        assert abs(loss.item() - l64) < 5e-3 * abs(l64)
+        gc = np.concatenate([cand[k].ravel() for k in sorted(cand)]).astype(np.float64)
+        go = np.concatenate([g64[k].ravel() for k in sorted(g64)])
+        assert rel_l2(gc, go) < 0.15 and float(gc @ go / (np.linalg.norm(gc) * np.linalg.norm(go))) > 0.99
+
+
 def test_padding_invariance_and_pad_row_features_ignored():
     """SURVEY 8(a) probes: re-padding to a larger N (K fixed) and garbage in pad rows of x leave ypred unchanged."""
     e = enc()
