@@ -98,6 +98,41 @@ __device__ __forceinline__ void smem_gemm(const float* __restrict__ A, int lda, 
   }
 }
 
+// Same product written straight to GLOBAL memory: C[i][c] (+)= ... for i < M, c < Nc (row stride ldc, any alignment)
+template <bool ACC>
+__device__ __forceinline__ void smem_gemm_to_global(const float* __restrict__ A, int lda, const float* __restrict__ Bm,
+                                                    int ldb, int M, int Nc, int K, float* __restrict__ C, long long ldc) {
+  const int ntn = (Nc + 3) >> 2, ntm = (M + 3) >> 2;
+  for (int t = threadIdx.x; t < ntm * ntn; t += blockDim.x) {
+    const int tm = t / ntn, tn = t - tm * ntn;
+    const int i0 = tm * 4, c0 = tn * 4;
+    float acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[r][e] = 0.f;
+    const float* a0 = A + i0 * lda;
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+      const float4 b4 = *reinterpret_cast<const float4*>(Bm + k * ldb + c0);
+      const float av[4] = {a0[k], a0[lda + k], a0[2 * lda + k], a0[3 * lda + k]};
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        acc[r][0] = fmaf(av[r], b4.x, acc[r][0]); acc[r][1] = fmaf(av[r], b4.y, acc[r][1]);
+        acc[r][2] = fmaf(av[r], b4.z, acc[r][2]); acc[r][3] = fmaf(av[r], b4.w, acc[r][3]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (i0 + r < M && c0 + e < Nc) {
+          float* o = C + (long long)(i0 + r) * ldc + c0 + e;
+          *o = ACC ? *o + acc[r][e] : acc[r][e];
+        }
+  }
+}
+
 struct SmallFwd {
   const float* x; long long ldx; const float* adj; const float* w; const float* bias; const int32_t* nb;
   int B, N, din, dout, normalize;
@@ -387,7 +422,7 @@ __host__ __device__ inline size_t small_pool_fwd_floats(int N, int K, int F) {
 }
 __host__ __device__ inline size_t small_pool_bwd_floats(int N, int K, int F) {
   const size_t n4 = r4i(N), k4 = r4i(K), f4 = r4i(F);
-  return 4 * n4 * k4 + 2 * n4 * f4 + n4 * n4 + 2 * k4 * f4 + 2 * k4 * k4;
+  return 4 * n4 * k4 + n4 * f4 + n4 * n4 + 2 * k4 * f4 + 2 * k4 * k4;
 }
 
 __global__ void __launch_bounds__(256) pool_small_fwd_kernel(const SmallPool p) {
@@ -437,8 +472,7 @@ __global__ void __launch_bounds__(256) pool_small_bwd_kernel(const SmallPool p) 
   float* Wv = Tt + (size_t)N4 * k4;                 // [N4][k4]  W = S dA'^T
   float* dSs = Wv + (size_t)N4 * k4;                // [N4][k4]
   float* Zs = dSs + (size_t)N4 * k4;                // [N4][f4]
-  float* dZs = Zs + (size_t)N4 * f4;                // [N4][f4]
-  float* As = dZs + (size_t)N4 * f4;                // [N4][N4]
+  float* As = Zs + (size_t)N4 * f4;                 // [N4][N4]
   float* dXs = As + (size_t)N4 * N4;                // [k4][f4]  dX'
   float* dXt = dXs + (size_t)k4 * f4;               // [f4][k4]  dX'^T
   float* dAs = dXt + (size_t)k4 * f4;               // [k4][k4]  dA'
@@ -455,7 +489,11 @@ __global__ void __launch_bounds__(256) pool_small_bwd_kernel(const SmallPool p) 
   stage_rows_t(dAt, k4, dab, K, K, K, k4, k4);
   cpa_wait_all();
   __syncthreads();
-  smem_gemm(Ss, k4, dXs, f4, n, F, K, dZs, f4, nullptr);            // dZ = S dX'
+  float* dzb = p.dz + (long long)b * N * p.lddz;
+  if (p.acc_dz) smem_gemm_to_global<true>(Ss, k4, dXs, f4, n, F, K, dzb, p.lddz);      // dZ (+)= S dX' (real rows)
+  else          smem_gemm_to_global<false>(Ss, k4, dXs, f4, n, F, K, dzb, p.lddz);
+  if (!p.acc_dz)                                                     // pad rows of dZ are zero
+    for (int e = tid; e < (N - n) * F; e += 256) { const int i = n + e / F, c = e % F; dzb[(long long)i * p.lddz + c] = 0.f; }
   smem_gemm(Zs, f4, dXt, k4, n, K, F, dSs, k4, nullptr);            // dS = Z dX'^T
   smem_gemm(Ss, k4, dAt, k4, n, K, K, Wv, k4, nullptr);             // W = S dA'^T
   __syncthreads();
@@ -463,13 +501,6 @@ __global__ void __launch_bounds__(256) pool_small_bwd_kernel(const SmallPool p) 
   __syncthreads();
   smem_gemm<true>(As, n4, Wv, k4, n, K, n, dSs, k4, nullptr);       // dS += A W
   __syncthreads();
-  float* dzb = p.dz + (long long)b * N * p.lddz;
-  for (int e = tid; e < N * F; e += 256) {
-    const int i = e / F, c = e - i * F;
-    const float v = i < n ? dZs[i * f4 + c] : 0.f;
-    float* o = dzb + (long long)i * p.lddz + c;
-    if (p.acc_dz) { if (i < n) *o += v; } else *o = v;
-  }
   float* dsb = p.ds + (long long)b * N * K;
   for (int e = tid; e < N * K; e += 256) {
     const int i = e / K, c = e - i * K;
