@@ -309,6 +309,116 @@ __global__ void __launch_bounds__(1024, 1) layer_bwd_bn_cta_kernel(const LbArgs 
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Two-CTAs-per-SM BN variant (bf16-only output, i.e. the tensor-core schedule).  ncu on the kernel above
+// (profiles/r1_ncu_layer_bwd_bn_cta_n2048.md): DRAM 39 % busy, one CTA resident per SM, so the load phase of one node
+// never overlaps the reduce / finish / store phase of another.  Here a node is one 512-thread CTA with twice the rows
+// per thread; the combined upstream gradient g is stashed between the two phases as PACKED BF16 (2 registers per
+// float4 instead of 4), which brings a thread under the 64-register line needed for two resident CTAs.  The batch sums
+// s1 = sum g, s2 = sum g.hhat are taken from the fp32 values BEFORE the stash; only the per-element use of g in phase 2
+// sees the rounding, of the same size as the bf16 rounding of the dV it produces (this variant is used only when no
+// fp32 dV is requested).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+template <int VPT>
+__global__ void __launch_bounds__(512, 2) layer_bwd_bn_cta2_kernel(const LbArgs a) {
+  constexpr int T = 512;
+  __shared__ float red[2][T / 32];
+  __shared__ float tot[2];
+  __shared__ __align__(16) float colacc[T * 4];
+  const int n = blockIdx.x;
+  const int d4 = a.d >> 2;
+  const int lg4 = 31 - __clz(d4);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c = (tid & (d4 - 1)) * 4;
+  const int rstep = T >> lg4;
+  const int r0 = tid >> lg4;
+  const float mu = a.mean[n], is = a.invstd[n];
+  auto hhat4 = [&](const float4 y) -> float4 {
+    return make_float4(((a.relu ? fmaxf(y.x, 0.f) : y.x) - mu) * is, ((a.relu ? fmaxf(y.y, 0.f) : y.y) - mu) * is,
+                       ((a.relu ? fmaxf(y.z, 0.f) : y.z) - mu) * is, ((a.relu ? fmaxf(y.w, 0.f) : y.w) - mu) * is);
+  };
+  uint2 gs[VPT];                                         // g as 4 x bf16
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) {
+    const int b = r0 + j * rstep;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f), yv = g;
+    if (b < a.B) {
+      const long long row = (long long)b * a.N + n;
+      g = load_g<true>(a, b, n, row, c);
+      yv = ld4(a.y + row * a.ldy + c);
+    }
+    const float4 hj = hhat4(yv);                         // rows beyond B have g == 0: they add nothing
+    s1 += (g.x + g.y) + (g.z + g.w);
+    s2 = fmaf(g.x, hj.x, s2); s2 = fmaf(g.y, hj.y, s2);
+    s2 = fmaf(g.z, hj.z, s2); s2 = fmaf(g.w, hj.w, s2);
+    gs[j] = make_uint2(pack2(g.x, g.y), pack2(g.z, g.w));
+  }
+  s1 = warp_sum(s1); s2 = warp_sum(s2);
+  if (lane == 0) { red[0][warp] = s1; red[1][warp] = s2; }
+  __syncthreads();
+  if (warp == 0) {
+    float t1 = lane < T / 32 ? red[0][lane] : 0.f, t2 = lane < T / 32 ? red[1][lane] : 0.f;
+    t1 = warp_sum(t1); t2 = warp_sum(t2);
+    if (lane == 0) { tot[0] = t1; tot[1] = t2; }
+  }
+  __syncthreads();
+  const float inv_cnt = 1.f / ((float)a.B * (float)a.d);
+  const float m1 = tot[0] * inv_cnt, m2 = tot[1] * inv_cnt;
+  float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) {
+    const int b = r0 + j * rstep;
+    const bool live = b < a.B;
+    const long long row = (long long)(live ? b : 0) * a.N + n;
+    float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+    float r = 1.f;
+    if (live) {
+      y = ld4(a.y + row * a.ldy + c);                    // second read of Y: L2 (this CTA just read it)
+      if (a.normalize) r = a.rnorm[row];
+    }
+    const float4 hj = hhat4(y);
+    const float4 g = make_float4(bf_lo(gs[j].x), bf_hi(gs[j].x), bf_lo(gs[j].y), bf_hi(gs[j].y));
+    float4 v;
+    v.x = (g.x - m1 - hj.x * m2) * is; v.y = (g.y - m1 - hj.y * m2) * is;
+    v.z = (g.z - m1 - hj.z * m2) * is; v.w = (g.w - m1 - hj.w * m2) * is;
+    if (a.relu) {
+      if (!(y.x > 0.f)) v.x = 0.f;
+      if (!(y.y > 0.f)) v.y = 0.f;
+      if (!(y.z > 0.f)) v.z = 0.f;
+      if (!(y.w > 0.f)) v.w = 0.f;
+    }
+    if (a.normalize) {
+      float dot = fmaf(v.x, y.x, fmaf(v.y, y.y, fmaf(v.z, y.z, v.w * y.w)));
+      for (int o = d4 >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      if (!(r > kEpsNormB)) {
+        v.x /= kEpsNormB; v.y /= kEpsNormB; v.z /= kEpsNormB; v.w /= kEpsNormB;
+      } else {
+        const float ir = 1.f / r;
+        v.x = (v.x - y.x * dot) * ir; v.y = (v.y - y.y * dot) * ir;
+        v.z = (v.z - y.z * dot) * ir; v.w = (v.w - y.w * dot) * ir;
+      }
+    }
+    if (live) {
+      *reinterpret_cast<uint2*>(a.dvb + row * a.lddvb + c) = make_uint2(pack2(v.x, v.y), pack2(v.z, v.w));
+      cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
+    }
+  }
+  if (a.part != nullptr) {                               // deterministic per-CTA column sums
+    *reinterpret_cast<float4*>(&colacc[tid * 4]) = cs;
+    __syncthreads();
+    if (tid < a.d) {
+      const int q = tid >> 2, e = tid & 3;
+      float t = 0.f;
+      for (int rr = q; rr < T; rr += d4) t += colacc[rr * 4 + e];
+      a.part[(long long)blockIdx.x * a.d + tid] = t;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Pipelined BN variant: PERSISTENT clusters.  The one-node-per-cluster kernel above spends most of a CTA's life
 // outside its load phase (cluster syncs, reduction, launch of the next cluster), so HBM idles: measured 2.5 TB/s.
 // Here a cluster of CS CTAs walks nodes n = cluster, cluster + G, ...; the rows of node i+1 stream into the other
@@ -717,6 +827,21 @@ int layer_bwd_fast(const gp_layer_bwd* q, cudaStream_t st, bool* handled) {
   if (use_cta < 0) { const char* e = getenv("GP_LBWD_CTA"); use_cta = (e == nullptr || atoi(e) != 0) ? 1 : 0; }
   if (q->bn && use_cta && q->h == nullptr && q->mean != nullptr) {
     const int d4 = d / 4;
+    // bf16-only output, d >= 64 (column sums need tid < d <= 512): two 512-thread CTAs per SM with a bf16 stash
+    static int use_cta2 = -1;
+    if (use_cta2 < 0) { const char* e = getenv("GP_LBWD_CTA2"); use_cta2 = (e != nullptr && atoi(e) == 0) ? 0 : 1; }
+    const int rstep2 = 512 / d4;
+    const int vpt2 = (q->B + rstep2 - 1) / rstep2;
+    if (use_cta2 && a.dv == nullptr && a.dvb != nullptr && vpt2 > 4 && vpt2 <= 16 && d <= 512) {
+      if (vpt2 <= 8) layer_bwd_bn_cta2_kernel<8><<<q->N, 512, 0, st>>>(a);
+      else layer_bwd_bn_cta2_kernel<16><<<q->N, 512, 0, st>>>(a);
+      GP_LAUNCHED();
+      part_rows = q->N;
+      if (q->db != nullptr)
+        GP_TRY(colsum(q->ws, part_rows, d, d, q->db, 0, q->ws + part_rows * d, st));
+      *handled = true;
+      return GP_OK;
+    }
     const int rstep = 1024 / d4;
     const int vpt = (q->B + rstep - 1) / rstep;
     if (vpt <= 8) {

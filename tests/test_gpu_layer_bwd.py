@@ -112,5 +112,8 @@ def test_layer_bwd_x(B, N, d, relu, bn, use_dz, use_dxn, use_readout, stored_h):
         q.dv_bf16, q.db = dvb2.data_ptr(), db2.data_ptr()
         call('gp_gcn_layer_bwd_x', C.byref(q), st())
         torch.cuda.synchronize()
-        assert torch.equal(dvb2[:, :, :d], dvb[:, :, :d])
-        assert rel_l2(db2.cpu().numpy(), db.cpu().numpy()) < 1e-5
+        # (BN layers with many rows per thread take the two-CTAs-per-SM kernel, which stashes the upstream gradient as
+        # bf16 between its two phases: same bound as the bf16 output itself, not bit-identical to the fp32-dV run)
+        gb2 = dvb2[:, :, :d].float().cpu().numpy()
+        assert rel_l2(gb2[mask], dv_ref[mask]) < 8e-3
+        assert rel_l2(db2.cpu().numpy(), db.cpu().numpy()) < 2e-3
