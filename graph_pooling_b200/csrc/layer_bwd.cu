@@ -607,8 +607,8 @@ layer_bwd_bn_pipe_kernel(const LbArgs a, int CS, int rows_per_cta, int nclusters
 // ---------------------------------------------------------------------------------------------------------
 // No BN: one warp per row, lane owns float4 columns lane, lane+32, ... (VPL of them).
 // ---------------------------------------------------------------------------------------------------------
-template <int VPL>
-__global__ void __launch_bounds__(256) layer_bwd_row_kernel(const LbArgs a, long long rows) {
+template <int VPL, int MINB = 1>
+__global__ void __launch_bounds__(256, MINB) layer_bwd_row_kernel(const LbArgs a, long long rows) {
   __shared__ __align__(16) float colacc[8][VPL * 128];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int d4 = a.d >> 2;
@@ -624,8 +624,8 @@ __global__ void __launch_bounds__(256) layer_bwd_row_kernel(const LbArgs a, long
       const int c4 = lane + 32 * k;
       g[k] = yv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (c4 < d4) {
-        g[k] = load_g(a, b, n, row, c4 * 4);
-        yv[k] = ld4(a.y + row * a.ldy + c4 * 4);
+        g[k] = load_g<true>(a, b, n, row, c4 * 4);       // every operand of a row is read exactly once: streaming
+        yv[k] = ld4s(a.y + row * a.ldy + c4 * 4);
       }
     }
     const float r = a.normalize ? a.rnorm[row] : 1.f;
@@ -942,9 +942,19 @@ int layer_bwd_fast(const gp_layer_bwd* q, cudaStream_t st, bool* handled) {
     long long blocks = (rows + 7) / 8;
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
     const int d4 = d / 4;
+    // four 256-thread blocks per SM (64 registers) is the measured optimum for every row width: wider rows are capped
+    // there with launch bounds (d = 256: 0.329 -> 0.262 ms; d = 512: 0.741 -> 0.535 ms at [B*N = 524288] rows)
     if (d4 <= 32) layer_bwd_row_kernel<1><<<(int)blocks, 256, 0, st>>>(a, rows);
-    else if (d4 <= 64) layer_bwd_row_kernel<2><<<(int)blocks, 256, 0, st>>>(a, rows);
-    else if (d4 <= 128) layer_bwd_row_kernel<4><<<(int)blocks, 256, 0, st>>>(a, rows);
+    else if (d4 <= 64) layer_bwd_row_kernel<2, 4><<<(int)blocks, 256, 0, st>>>(a, rows);
+    else if (d4 <= 128) {
+      // 16 floats x 2 operands per lane: left alone the compiler takes 106 registers (2 blocks per SM, 0.74 ms at
+      // [B*N, 512]); capped at 64 registers four blocks are resident and the pass runs at 5.0 TB/s (0.535 ms).
+      // Measured: 3 blocks 0.66 ms, 5 blocks (48 registers, spills) 0.64 ms, 6 blocks 0.75 ms.
+      static int minb = -1;
+      if (minb < 0) { const char* e = getenv("GP_LBWD_ROW_MINB"); minb = e != nullptr ? atoi(e) : 4; }
+      if (minb >= 4) layer_bwd_row_kernel<4, 4><<<(int)blocks, 256, 0, st>>>(a, rows);
+      else layer_bwd_row_kernel<4><<<(int)blocks, 256, 0, st>>>(a, rows);
+    }
     else if (d4 <= 256) layer_bwd_row_wide_kernel<8><<<(int)blocks, 128, 0, st>>>(a, rows);
     else layer_bwd_row_wide_kernel<16><<<(int)blocks, 128, 0, st>>>(a, rows);
     GP_LAUNCHED();
