@@ -679,8 +679,8 @@ __global__ void __launch_bounds__(256, MINB) layer_bwd_row_kernel(const LbArgs a
 // Rows wider than 512 floats (the assignment GCN's last layer at K = 1250 -> 1256 / 1280 clusters): the row no longer
 // fits the registers twice over, so the dot product is taken in a first pass and the operands are read again (L1 / L2
 // hits: a row is a few KB) for the update.  4 warps per block; VPL float4 per lane hold the column sums only.
-template <int VPL>
-__global__ void __launch_bounds__(128) layer_bwd_row_wide_kernel(const LbArgs a, long long rows) {
+template <int VPL, int MINB = 1>
+__global__ void __launch_bounds__(128, MINB) layer_bwd_row_wide_kernel(const LbArgs a, long long rows) {
   __shared__ __align__(16) float colacc[4][VPL * 128];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int d4 = a.d >> 2;
@@ -956,7 +956,12 @@ int layer_bwd_fast(const gp_layer_bwd* q, cudaStream_t st, bool* handled) {
       else layer_bwd_row_kernel<4><<<(int)blocks, 256, 0, st>>>(a, rows);
     }
     else if (d4 <= 256) layer_bwd_row_wide_kernel<8><<<(int)blocks, 128, 0, st>>>(a, rows);
-    else layer_bwd_row_wide_kernel<16><<<(int)blocks, 128, 0, st>>>(a, rows);
+    else {
+      static int wminb = -1;
+      if (wminb < 0) { const char* e = getenv("GP_WIDE_MINB"); wminb = e != nullptr ? atoi(e) : 1; }   /* 80 registers: six / three blocks per SM, measured 2.31 -> 1.95 ms at cfg5 */
+      if (wminb) layer_bwd_row_wide_kernel<16, 6><<<(int)blocks, 128, 0, st>>>(a, rows);
+      else layer_bwd_row_wide_kernel<16><<<(int)blocks, 128, 0, st>>>(a, rows);
+    }
     GP_LAUNCHED();
     part_rows = blocks;
   }

@@ -81,8 +81,8 @@ __global__ void bn_apply_kernel(const float* __restrict__ y, long long ldy, cons
 }
 
 // V (+bias) -> Y = V / max(||V||, eps) in place, rnorm, optional bf16 copy; the row stays in registers (d <= 1024)
-template <int VPL>
-__global__ void bias_normalize_x_kernel(float* __restrict__ v, const float* __restrict__ bias, float* __restrict__ rnorm,
+template <int VPL, int MINB = 1>
+__global__ void __launch_bounds__(256, MINB) bias_normalize_x_kernel(float* __restrict__ v, const float* __restrict__ bias, float* __restrict__ rnorm,
                                         long long rows, int d, long long ld, int normalize,
                                         __nv_bfloat16* __restrict__ yb, long long ldyb) {
   const int lane = threadIdx.x & 31;
@@ -325,7 +325,12 @@ extern "C" int gp_bias_normalize_x(float* v, const float* bias, float* rnorm, lo
   else if (d <= 256) bias_normalize_x_kernel<2><<<g, 256, 0, S(stream)>>>(v, bias, rnorm, rows, d, ld, normalize, yb, ldyb);
   else if (d <= 512) bias_normalize_x_kernel<4><<<g, 256, 0, S(stream)>>>(v, bias, rnorm, rows, d, ld, normalize, yb, ldyb);
   else if (d <= 1024) bias_normalize_x_kernel<8><<<g, 256, 0, S(stream)>>>(v, bias, rnorm, rows, d, ld, normalize, yb, ldyb);
-  else               bias_normalize_x_kernel<16><<<g, 256, 0, S(stream)>>>(v, bias, rnorm, rows, d, ld, normalize, yb, ldyb);
+  else {
+    static int wminb = -1;
+    if (wminb < 0) { const char* e = getenv("GP_WIDE_MINB"); wminb = e != nullptr ? atoi(e) : 1; }   /* 80 registers: six / three blocks per SM, measured 2.31 -> 1.95 ms at cfg5 */
+    if (wminb) bias_normalize_x_kernel<16, 3><<<g, 256, 0, S(stream)>>>(v, bias, rnorm, rows, d, ld, normalize, yb, ldyb);
+    else       bias_normalize_x_kernel<16><<<g, 256, 0, S(stream)>>>(v, bias, rnorm, rows, d, ld, normalize, yb, ldyb);
+  }
   GP_LAUNCHED();
   return GP_OK;
 }
