@@ -59,3 +59,27 @@ def test_state_dict_keys_match_oracle():
     a = encoders.GcnEncoderGraph(7, 20, 20, 2, 3)
     b = orc.GcnEncoderGraph(7, 20, 20, 2, 3)
     assert list(a.state_dict().keys()) == list(b.state_dict().keys())
+    a = encoders.GcnSet2SetEncoder(7, 20, 20, 2, 3)
+    b = orc.GcnSet2SetEncoder(7, 20, 20, 2, 3)
+    assert [(k, tuple(v.shape)) for k, v in a.state_dict().items()] == \
+           [(k, tuple(v.shape)) for k, v in b.state_dict().items()]
+
+
+def test_host_side_plan_logic(monkeypatch):
+    """Host logic that needs no GPU: dead-cluster padding of the cluster count, per-layer dropout seeds, and the
+    dropout schedule of a stack (conv_block layers only, training mode only: encoders.py:1015, nn.Dropout)."""
+    from graph_pooling_b200 import encoders, engine
+    assert [encoders._kpad(k) for k in (8, 10, 62, 250, 512, 1250)] == [8, 16, 64, 256, 512, 1256]
+    monkeypatch.setenv('GP_NO_KPAD', '1')
+    assert encoders._kpad(250) == 250
+    seeds = {engine.layer_seed(12345, l) for l in range(8)}
+    assert len(seeds) == 8 and all(0 <= s < (1 << 62) for s in seeds)
+    m = encoders.GcnEncoderGraph(7, 20, 20, 2, 4, dropout=0.25)
+    assert m._drops(m.conv_block) == [0.0, 0.25, 0.25, 0.0]
+    m.eval()
+    assert m._drops(m.conv_block) == [0.0, 0.0, 0.0, 0.0]
+    s = encoders.SoftPoolingGcnEncoder(40, 3, 16, 16, 2, 4, 16, dropout=0.5)
+    assert s._drops(s.conv_block) == [0.0] * 4                      # R8: the first GCN ignores dropout (:1172-1173)
+    assert s._drops(s.conv_block_after_pool[0]) == [0.0, 0.5, 0.5, 0.0]
+    with pytest.raises(ValueError):
+        encoders.Set2Set(10, 15)                                    # hidden_dim must be 2 * input_dim
