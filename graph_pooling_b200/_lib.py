@@ -57,7 +57,8 @@ class GpLayerBwd(C.Structure):
                 ('h', c_f), ('ldh', c_ll), ('y', c_f), ('ldy', c_ll),
                 ('rnorm', c_f), ('mean', c_f), ('invstd', c_f),
                 ('B', c_i), ('N', c_i), ('d', c_i), ('relu', c_i), ('bn', c_i), ('normalize', c_i),
-                ('dv', c_f), ('dv_bf16', c_f), ('lddvb', c_ll), ('db', c_f), ('ws', c_f), ('lddxn', c_ll)]
+                ('dv', c_f), ('dv_bf16', c_f), ('lddvb', c_ll), ('db', c_f), ('ws', c_f), ('lddxn', c_ll),
+                ('nb_zero', c_f)]
 
 
 # name -> argtypes (restype is int unless listed in _RESTYPES)

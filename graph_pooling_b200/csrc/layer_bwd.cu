@@ -36,6 +36,7 @@ struct LbArgs {
   int B, N, d, relu, bn, normalize;
   float* dv; __nv_bfloat16* dvb; long long lddvb;
   float* part;          // [blocks][d] partial column sums or NULL
+  const int32_t* nbz;   // rows n >= nbz[b] have zero upstream gradient (row kernels: dV = 0 written without reading)
 };
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -618,6 +619,14 @@ __global__ void __launch_bounds__(256, MINB) layer_bwd_row_kernel(const LbArgs a
   for (int k = 0; k < VPL; ++k) cs[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (long long row = gw; row < rows; row += nw) {
     const int b = (int)(row / a.N), n = (int)(row - (long long)b * a.N);
+    if (a.nbz != nullptr && n >= a.nbz[b]) {             // pad row of a masked level: dV = 0, nothing to read
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        const int c4 = lane + 32 * k;
+        if (c4 < d4) store_dv(a, row, c4 * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+      }
+      continue;
+    }
     float4 g[VPL], yv[VPL];
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
@@ -690,6 +699,14 @@ __global__ void __launch_bounds__(128, MINB) layer_bwd_row_wide_kernel(const LbA
   for (int k = 0; k < VPL; ++k) cs[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (long long row = gw; row < rows; row += nw) {
     const int b = (int)(row / a.N), n = (int)(row - (long long)b * a.N);
+    if (a.nbz != nullptr && n >= a.nbz[b]) {             // pad row of a masked level: dV = 0, nothing to read
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        const int c4 = lane + 32 * k;
+        if (c4 < d4) store_dv(a, row, c4 * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+      }
+      continue;
+    }
     const float r = a.normalize ? a.rnorm[row] : 1.f;
     float dot = 0.f;
     if (a.normalize) {
@@ -822,6 +839,7 @@ int layer_bwd_fast(const gp_layer_bwd* q, cudaStream_t st, bool* handled) {
   a.B = q->B; a.N = q->N; a.d = d; a.relu = q->relu; a.bn = q->bn; a.normalize = q->normalize;
   a.dv = q->dv; a.dvb = reinterpret_cast<__nv_bfloat16*>(q->dv_bf16); a.lddvb = q->lddvb;
   a.part = q->db != nullptr ? q->ws : nullptr;
+  a.nbz = q->bn ? nullptr : q->nb_zero;
   long long part_rows = 0;
   static int use_cta = -1;
   if (use_cta < 0) { const char* e = getenv("GP_LBWD_CTA"); use_cta = (e == nullptr || atoi(e) != 0) ? 1 : 0; }

@@ -707,7 +707,7 @@ extern "C" int gp_gcn_layer_bwd(const float* dz, long long lddz, const float* dx
   q.dz = dz; q.lddz = lddz; q.dxn = dxn; q.dout = dout; q.argidx = argidx; q.ldo = ldo;
   q.h = h; q.ldh = ldh; q.y = y; q.ldy = ldy; q.rnorm = rnorm; q.mean = nullptr; q.invstd = invstd;
   q.B = B; q.N = N; q.d = d; q.relu = relu; q.bn = bn; q.normalize = normalize;
-  q.dv = dv; q.dv_bf16 = nullptr; q.lddvb = 0; q.db = nullptr; q.ws = nullptr; q.lddxn = 0;
+  q.dv = dv; q.dv_bf16 = nullptr; q.lddvb = 0; q.db = nullptr; q.ws = nullptr; q.lddxn = 0; q.nb_zero = nullptr;
   return gp_gcn_layer_bwd_x(&q, stream);
 }
 

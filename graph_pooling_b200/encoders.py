@@ -99,6 +99,7 @@ def _fwd_tc(ctx, plan, x, adj, assign_x, params):
                 u0 = c_emb.layers[0][4] if (i == 0 and xab is xb) else None
                 za, zab, c_as = T.stack_forward(ws, xab, xa_d, cur_adjb, cur_nb, B, cur_N, wa, ba, True, u0=u0,
                                                 pad_last=pad)
+            c_as.pad_grad_zero = True                   # S's pad rows are masked: no gradient reaches this stack's pad rows
             Fa = za.shape[2]
             wp, bp = _wb(params, plan.assign_pred[i])
             Tl, wpb = T.assign_linear_fwd(ws, zab, Fa, B * cur_N, wp, bp, Kp=pad)

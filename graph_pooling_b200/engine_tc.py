@@ -368,6 +368,10 @@ def _layer_backward_head(ws, ctx, l, dz_ptr, lddz, dxn, lddxn, dout_ptr, arg_ptr
     q.dv, q.dv_bf16, q.lddvb = None, dvb.ptr, dvb.ld
     q.db = E._p(db)
     q.ws = None
+    # padding-aware row pass: the last layer of a masked assignment stack gets its only upstream gradient from
+    # dza = dT.Wp, whose pad rows are exactly zero (masked softmax backward): those rows are written as zeros unread
+    if last and getattr(ctx, 'pad_grad_zero', False) and ctx.nb is not None and dxn is None and dout_ptr is None:
+        q.nb_zero = E._p(ctx.nb)
     wsf = ws.f(int(load().gp_gcn_layer_bwd_ws_x(C.byref(q)))) if has_b else None
     q.ws = E._p(wsf)
     call('gp_gcn_layer_bwd_x', C.byref(q), st)

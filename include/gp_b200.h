@@ -254,6 +254,9 @@ typedef struct gp_layer_bwd {
   float* dv; void* dv_bf16; long long lddvb;
   float* db; float* ws;
   long long lddxn;           /* row stride of dxn in elements; 0 = contiguous (d) */
+  const int32_t* nb_zero;    /* optional, layers without BN only: the caller guarantees that rows n >= nb_zero[b] receive
+                                no upstream gradient (masked level: encoders.py:1080, 1275) -- their dV is written as
+                                zero without reading the operands (padding-aware row pass) */
 } gp_layer_bwd;
 int gp_gcn_layer_bwd_x(const gp_layer_bwd* q, gp_stream_t stream);
 long long gp_gcn_layer_bwd_ws(int B, int N, int d, int bn);

@@ -117,3 +117,39 @@ def test_layer_bwd_x(B, N, d, relu, bn, use_dz, use_dxn, use_readout, stored_h):
         gb2 = dvb2[:, :, :d].float().cpu().numpy()
         assert rel_l2(gb2[mask], dv_ref[mask]) < 8e-3
         assert rel_l2(db2.cpu().numpy(), db.cpu().numpy()) < 2e-3
+
+
+@pytest.mark.parametrize('B,N,d', [(3, 40, 128), (2, 33, 512), (2, 25, 1256)])
+def test_layer_bwd_row_nb_zero_hint(B, N, d):
+    """nb_zero (layers without BN): rows n >= nb_zero[b] are declared gradient-free by the caller -- their dV is written
+    as zero without reading the operands.  With an upstream gradient that IS zero there, the result must equal the
+    unhinted run bit for bit (row kernels of every width: 1 / 4 slots per lane and the two-pass wide kernel)."""
+    from graph_pooling_b200._lib import GpLayerBwd, call, load
+    rs = np.random.RandomState(d)
+    nb = rs.randint(1, N + 1, size=B).astype(np.int32)
+    dz = rs.randn(B, N, d).astype(np.float32)
+    for b in range(B):
+        dz[b, nb[b]:] = 0.0
+    y = rs.randn(B, N, d).astype(np.float32)
+    y /= np.linalg.norm(y, axis=2, keepdims=True)
+    dev = lambda a, dt=torch.float32: torch.tensor(np.ascontiguousarray(a), dtype=dt, device='cuda')
+    dzc, yc, rn, nbc = dev(dz), dev(y), dev(rs.rand(B, N) + 0.5), dev(nb, torch.int32)
+    outs = []
+    for hint in (0, 1):
+        ldb = (d + 7) // 8 * 8
+        dvb = torch.full((B, N, ldb), 7.0, device='cuda', dtype=torch.bfloat16)
+        db = torch.empty(d, device='cuda')
+        q = GpLayerBwd()
+        q.dz, q.lddz, q.y, q.ldy, q.rnorm = dzc.data_ptr(), d, yc.data_ptr(), d, rn.data_ptr()
+        q.B, q.N, q.d, q.relu, q.bn, q.normalize = B, N, d, 0, 0, 1
+        q.dv, q.dv_bf16, q.lddvb, q.db = None, dvb.data_ptr(), ldb, db.data_ptr()
+        q.nb_zero = nbc.data_ptr() if hint else None
+        w = torch.empty(int(load().gp_gcn_layer_bwd_ws_x(C.byref(q))), device='cuda')
+        q.ws = w.data_ptr()
+        call('gp_gcn_layer_bwd_x', C.byref(q), st())
+        torch.cuda.synchronize()
+        outs.append((dvb[:, :, :d].clone(), db.clone()))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert rel_l2(outs[1][1].cpu().numpy(), outs[0][1].cpu().numpy()) < 1e-6
+    for b in range(B):
+        assert float(outs[1][0][b, nb[b]:].float().abs().sum()) == 0.0
