@@ -153,6 +153,42 @@ sym_select_kernel(const float* __restrict__ x, long long ldx, int K, const int32
   }
 }
 
+// Same, 64x64 tiles with 16-byte loads and 8-byte bf16 stores (needs K, ldx, ld multiples of 4 and aligned bases):
+// the 32x32 scalar version moved its 0.4 GB at 1.8 TB/s.
+__global__ void __launch_bounds__(256)
+sym_select_vec_kernel(const float* __restrict__ x, long long ldx, int K, const int32_t* __restrict__ cond,
+                      __nv_bfloat16* __restrict__ out, long long ld) {
+  __shared__ float Tt[64][65];
+  const bool sym = cond != nullptr && *cond == 0;
+  const float* xb = x + (long long)blockIdx.z * K * ldx;
+  __nv_bfloat16* ob = out + (long long)blockIdx.z * K * ld;
+  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+  const int q = threadIdx.x & 15, rr = threadIdx.x >> 4;     // 16 float4 per tile row, 16 rows per pass
+  if (sym) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {                            // mirrored tile: rows c0.., cols r0..
+      const int r = rr + 16 * i, gr = c0 + r, gc = r0 + q * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gr < K && gc < K) v = *reinterpret_cast<const float4*>(xb + (long long)gr * ldx + gc);
+      Tt[r][q * 4] = v.x; Tt[r][q * 4 + 1] = v.y; Tt[r][q * 4 + 2] = v.z; Tt[r][q * 4 + 3] = v.w;
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = rr + 16 * i, gr = r0 + r, gc = c0 + q * 4;
+    if (gr >= K || gc >= ld) continue;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gc < K) {
+      v = *reinterpret_cast<const float4*>(xb + (long long)gr * ldx + gc);
+      if (sym) { v.x += Tt[q * 4][r]; v.y += Tt[q * 4 + 1][r]; v.z += Tt[q * 4 + 2][r]; v.w += Tt[q * 4 + 3][r]; }
+    }
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    *reinterpret_cast<uint2*>(ob + (long long)gr * ld + gc) =
+        make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+  }
+}
+
 }  // namespace gp
 
 using namespace gp;
@@ -160,8 +196,14 @@ using namespace gp;
 extern "C" int gp_sym_select_bf16(const float* x, long long ldx, int B, int K, const int32_t* cond, void* out_bf16,
                                   long long ld, gp_stream_t stream) {
   GP_REQUIRE(x && out_bf16 && B > 0 && K > 0 && ld >= K && ldx >= K && B <= 65535, "sym_select_bf16: bad args");
-  sym_select_kernel<<<dim3((unsigned)((ld + 31) / 32), (unsigned)((K + 31) / 32), (unsigned)B), 256, 0, S(stream)>>>(
-      x, ldx, K, cond, reinterpret_cast<__nv_bfloat16*>(out_bf16), ld);
+  const bool vec = K % 4 == 0 && ldx % 4 == 0 && ld % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(out_bf16) & 7) == 0;
+  if (vec)
+    sym_select_vec_kernel<<<dim3((unsigned)((ld + 63) / 64), (unsigned)((K + 63) / 64), (unsigned)B), 256, 0, S(stream)>>>(
+        x, ldx, K, cond, reinterpret_cast<__nv_bfloat16*>(out_bf16), ld);
+  else
+    sym_select_kernel<<<dim3((unsigned)((ld + 31) / 32), (unsigned)((K + 31) / 32), (unsigned)B), 256, 0, S(stream)>>>(
+        x, ldx, K, cond, reinterpret_cast<__nv_bfloat16*>(out_bf16), ld);
   GP_LAUNCHED();
   return GP_OK;
 }
