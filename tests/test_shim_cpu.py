@@ -29,9 +29,9 @@ torch.Tensor.cuda = lambda self, *a, **k: self
 torch.nn.Module.cuda = lambda self, *a, **k: self
 import os
 os.makedirs('results', exist_ok=True)
-sys.argv = ['train.py', '--bmname=ENZYMES', '--datadir=%(ref)s/data', '--method=soft-assign', '--max-nodes=100',
+sys.argv = ['train.py', '--bmname=ENZYMES', '--datadir=%(ref)s/data', '--method=%(method)s', '--max-nodes=100',
             '--num-classes=6', '--hidden-dim=30', '--output-dim=30', '--assign-ratio=0.1', '--num-pool=1',
-            '--linkpred', '--epochs=1', '--num_workers=0', '--cuda=0']
+            '--epochs=1', '--num_workers=0', '--cuda=0'] + %(extra)r
 import train
 train.log_assignment = lambda *a, **k: None
 train.log_graph = lambda *a, **k: None
@@ -53,9 +53,10 @@ print('SHIM_OK', sorted(stubbed))
 
 
 @pytest.mark.skipif(not os.path.isfile(os.path.join(REF, 'train.py')), reason='reference checkout not present')
-def test_reference_train_py_runs_one_epoch_under_the_shim(tmp_path):
-    r = subprocess.run([sys.executable, '-c', SCRIPT % {'root': ROOT, 'ref': REF}], cwd=str(tmp_path),
-                       capture_output=True, text=True, timeout=600)
+@pytest.mark.parametrize('method,extra', [('soft-assign', ['--linkpred']), ('base-set2set', ['--dropout=0.1'])])
+def test_reference_train_py_runs_one_epoch_under_the_shim(tmp_path, method, extra):
+    r = subprocess.run([sys.executable, '-c', SCRIPT % {'root': ROOT, 'ref': REF, 'method': method, 'extra': extra}],
+                       cwd=str(tmp_path), capture_output=True, text=True, timeout=900)
     assert 'SHIM_OK' in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
     assert 'Validation  accuracy' in r.stdout
 
