@@ -160,3 +160,4 @@ if __name__ == '__main__':
     run_case(ref, 'base_small',   'base', 3, 5, 48, 7, 20, 20, 2, 3, 0.0, 3, 48, 0.10, 0.3)
     run_case(ref, 'base_l4',      'base', 4, 4, 32, 4, 10, 14, 4, 4, 0.0, 2, 32, 0.15, 0.2)
     run_case(ref, 's2s_small',    's2s',  5, 4, 20, 5, 8, 8, 3, 3, 0.0, 2, 20, 0.20, 0.2)
+    run_case(ref, 's2s_l4',       's2s',  6, 3, 33, 4, 8, 6, 4, 4, 0.0, 1, 33, 0.15, 0.3)
