@@ -101,7 +101,8 @@ def synth_batch(seed, B, N, D, n_min, n_max, C, density):
     return x, adj, nb, label
 
 
-def run_case(ref, name, kind, seed, B, N, D, H, E, C, L, ratio, n_min, n_max, density, bias_scale):
+def run_case(ref, name, kind, seed, B, N, D, H, E, C, L, ratio, n_min, n_max, density, bias_scale, bn=True,
+             concat=True):
     torch.manual_seed(seed)
     if kind == 'soft':
         model = ref.SoftPoolingGcnEncoder(N, D, H, E, C, L, H, assign_ratio=ratio, num_pooling=1,
@@ -111,7 +112,7 @@ def run_case(ref, name, kind, seed, B, N, D, H, E, C, L, ratio, n_min, n_max, de
         # .cuda() calls are the no-ops installed by load_reference (R2), torch.zeros follows the default dtype
         model = ref.GcnSet2SetEncoder(D, H, E, C, L, bn=True)
     else:
-        model = ref.GcnEncoderGraph(D, H, E, C, L, bn=True)
+        model = ref.GcnEncoderGraph(D, H, E, C, L, bn=bn, concat=concat)      # --nobn / concat=False (add_self) variants
     # non-zero biases so that pad rows are non-trivial (they are normalize(b))
     g = torch.Generator().manual_seed(seed + 1)
     with torch.no_grad():
@@ -121,7 +122,7 @@ def run_case(ref, name, kind, seed, B, N, D, H, E, C, L, ratio, n_min, n_max, de
     x, adj, nb, label = synth_batch(seed, B, N, D, n_min, n_max, C, density)
     out = {'x': x, 'adj_u8': adj.astype(np.uint8), 'nb': nb, 'label': label,
            'meta': np.array([B, N, D, H, E, C, L], np.int64), 'ratio': np.array(ratio),
-           'kind': np.array(kind)}
+           'kind': np.array(kind), 'bn': np.array(bool(bn)), 'concat': np.array(bool(concat))}
     for k, v in model.state_dict().items():
         out['sd.' + k] = v.detach().numpy().copy()
     for tag, dt in (('f32', torch.float32), ('f64', torch.float64)):
@@ -161,3 +162,5 @@ if __name__ == '__main__':
     run_case(ref, 'base_l4',      'base', 4, 4, 32, 4, 10, 14, 4, 4, 0.0, 2, 32, 0.15, 0.2)
     run_case(ref, 's2s_small',    's2s',  5, 4, 20, 5, 8, 8, 3, 3, 0.0, 2, 20, 0.20, 0.2)
     run_case(ref, 's2s_l4',       's2s',  6, 3, 33, 4, 8, 6, 4, 4, 0.0, 1, 33, 0.15, 0.3)
+    run_case(ref, 'base_nobn',    'base', 7, 4, 36, 6, 12, 12, 3, 3, 0.0, 2, 36, 0.15, 0.3, bn=False)
+    run_case(ref, 'base_addself', 'base', 8, 4, 28, 5, 10, 10, 3, 3, 0.0, 2, 28, 0.20, 0.3, concat=False)

@@ -24,7 +24,8 @@ def golden_model(g, mod, dtype=torch.float32, device='cpu'):
     elif str(g['kind']) == 's2s':
         m = mod.GcnSet2SetEncoder(D, H, E, C, L, bn=True)
     else:
-        m = mod.GcnEncoderGraph(D, H, E, C, L, bn=True)
+        m = mod.GcnEncoderGraph(D, H, E, C, L, bn=bool(g['bn']) if 'bn' in g else True,
+                                concat=bool(g['concat']) if 'concat' in g else True)
     sd = {k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith('sd.')}
     m.load_state_dict(sd, strict=True)
     return m.to(device=device, dtype=dtype)
