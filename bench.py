@@ -201,7 +201,7 @@ def main():
     gstep = None
     if not use_graph:
         opt = dp.FlatAdam(params, lr=1e-3, clip=2.0)     # clip_grad_norm + Adam: two kernels of this library
-        flat = opt.grads
+        flat = opt.grads.attach(model)                   # the backward adds all parameter gradients in ONE launch
     if use_graph:
         from graph_pooling_b200 import graphed
         gstep = graphed.GraphedTrainStep(model, lr=1e-3, clip=2.0)
@@ -333,7 +333,9 @@ def main():
                 fd.copy(nxt, [(st['xd'][nxt], hx), (st['ld'][nxt], hl)])     # H2D of step i+1
                 fd.submit(ha, cur)                                              # host pack of step i+2
                 pa = fd.prepared(cur, nbd_)
-                return float(step(st['xd'][cur], pa, st['ld'][cur]).item())    # compute of step i + D2H read-back
+                loss = step(st['xd'][cur], pa, st['ld'][cur])
+                fd.consumed(cur)                                                # next copy into this slot waits for the step
+                return float(loss.item())                                       # compute of step i + D2H read-back
 
             best = None
             for f in sorted({min(1.0, max(0.0, f0 + df)) for df in (-0.12, 0.0, 0.12, 0.24)}):
@@ -388,10 +390,30 @@ def main():
             else:
                 e2e['hybrid_host_pack'] = hyb
 
+    # ---- data-parallel correctness on the NCCL path (outside every timed region) ---------------------------
+    dp_check = None
     if world > 1:
+        # (1) one step's reduced gradient == mean of the shard gradients gathered from every rank
+        flat.zero()
+        yp = model(x, adj, nb, assign_x=x) if soft else model(x, adj, nb)
+        (model.loss(yp, label, adj, nb) if soft else model.loss(yp, label)).backward()
+        mine = flat.flat.clone()
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        mean = torch.stack(parts).double().mean(0)
+        flat.all_reduce(average=True)
+        flat.apply_pending_scale()
+        err = float((flat.flat.double() - mean).norm() / mean.norm().clamp_min(1e-30))
+        # (2) the replicas are bit-identical after all the steps above: MAX - MIN over ranks of every parameter == 0
+        pmax, pmin = opt.flat_p.clone(), opt.flat_p.clone()
+        dist.all_reduce(pmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(pmin, op=dist.ReduceOp.MIN)
+        spread = float((pmax - pmin).abs().max())
+        dp_check = {'reduced_grad_vs_mean_of_shard_grads_rel_l2': err, 'replica_param_max_minus_min': spread,
+                    'replicas_bit_identical': spread == 0.0, 'ranks': world}
+        assert err < 1e-5 and spread == 0.0, dp_check
         dist.barrier()
         dist.destroy_process_group()
-        world_done = True
     if rank != 0:
         return
 
@@ -567,7 +589,8 @@ def main():
                       if adj.numel() * 4 > 126e6 else 'inputs smaller than L2; not flushed',
                       'cuda_graph': bool(use_graph),
                       'parallelism': 'dp%d' % world},
-           'clocks': clocks, 'e2e': e2e, 'e2e_u8_feed': e2e_u8, 'gpu_launches': launches, 'roofline': roof, 'cpu_baseline': cpu}
+           'clocks': clocks, 'e2e': e2e, 'e2e_u8_feed': e2e_u8, 'gpu_launches': launches, 'roofline': roof, 'cpu_baseline': cpu,
+           'dp_check': dp_check}
     print(json.dumps(out), flush=True)
 
 

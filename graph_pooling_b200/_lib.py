@@ -52,6 +52,10 @@ class GpGemmBf16x(C.Structure):
                 ('cond', c_f), ('cond_npairs', c_i), ('cond_alpha', C.c_float), ('order', c_f)]
 
 
+class GpAxpyEntry(C.Structure):
+    _fields_ = [('src', c_f), ('dst', c_f), ('n', c_ll)]
+
+
 class GpLayerBwd(C.Structure):
     _fields_ = [('dz', c_f), ('lddz', c_ll), ('dxn', c_f), ('dout', c_f), ('argidx', c_f), ('ldo', c_ll),
                 ('h', c_f), ('ldh', c_ll), ('y', c_f), ('ldy', c_ll),
@@ -110,12 +114,16 @@ _PROTOS = {
     'gp_entropy_fwd': [c_f, c_f, c_i, c_i, c_i, c_f, c_f],
     'gp_entropy_bwd': [c_f, c_f, c_i, c_i, c_i, c_f, C.c_float, c_f, c_i, c_f],
     'gp_sumsq_f32': [c_f, c_ll, c_f, c_f, c_f],
-    'gp_adam_step_f32': [c_f, c_f, c_f, c_f, c_ll, C.c_float, C.c_float, C.c_float, C.c_float, c_f, c_f, C.c_float, c_f],
+    'gp_adam_step_f32': [c_f, c_f, c_f, c_f, c_ll, C.c_float, C.c_float, C.c_float, C.c_float, c_f, c_f, C.c_float,
+                         C.c_float, c_f],
+    'gp_clip_scale_f32': [c_f, c_ll, c_f, C.c_float, C.c_float, c_f],
+    'gp_multi_axpy_f32': [c_f, c_i, C.c_float, c_f],
     'gp_nb_stats': [c_f, c_i, c_f, c_f],
     'gp_mul_add_dev': [c_f, c_f, c_f, c_f, c_f, c_f],
     'gp_add_scaled': [c_f, c_f, C.c_float, c_f, c_f],
     'gp_linkloss_tc_partials': [c_i, c_i],
-    'gp_linkloss_from_p': [c_f, c_f, c_f, c_i, c_i, c_ll, c_f, c_f, c_f],
+    'gp_linkloss_from_q_partials': [c_i, c_i],
+    'gp_linkloss_from_q': [c_f, c_f, c_f, c_i, c_i, c_f, c_f, c_f],
     'gp_ce_fwd': [c_f, c_f, c_i, c_i, c_f, c_f, c_f],
     'gp_ce_bwd': [c_f, c_f, c_f, c_i, c_i, c_f, c_f],
     'gp_colsum_f32': [c_f, c_ll, c_i, c_ll, c_f, c_i, c_f, c_f],

@@ -55,6 +55,26 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {
   return sh[32];
 }
 
-constexpr int kNumSMs = 148;   // B200
+constexpr int kNumSMs = 148;   // B200 (grid sizing only: a device with another SM count runs the same kernels correctly)
+
+// "Configure once per DEVICE": cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device / context, so the
+// done-flag is one bit per device ordinal.  The attribute is set BEFORE the bit is published: a concurrent first call
+// from another thread at worst sets it twice (harmless), and a process that moves to a second GPU configures it there.
+struct DeviceOnce {
+  std::atomic<unsigned long long> done{0};
+  bool pending(unsigned long long* bit) {
+    int d = 0;
+    cudaGetDevice(&d);
+    *bit = 1ull << (d & 63);
+    return !(done.load(std::memory_order_acquire) & *bit);
+  }
+  void mark(unsigned long long bit) { done.fetch_or(bit, std::memory_order_release); }
+};
+#define GP_CONFIG_ONCE(...)                                   \
+  do {                                                        \
+    static gp::DeviceOnce once_;                              \
+    unsigned long long bit_;                                  \
+    if (once_.pending(&bit_)) { __VA_ARGS__; once_.mark(bit_); } \
+  } while (0)
 
 }  // namespace gp

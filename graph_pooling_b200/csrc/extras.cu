@@ -348,10 +348,12 @@ __global__ void sumsq_stage2(const float* __restrict__ part, int nparts, float* 
 }
 __global__ void adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                  float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
-                                 const float* __restrict__ step_dev, const float* __restrict__ sumsq, float max_norm) {
+                                 const float* __restrict__ step_dev, const float* __restrict__ sumsq, float max_norm,
+                                 float grad_scale) {
   const float t = *step_dev + 1.f;
-  float coef = 1.f;
-  if (max_norm > 0.f && sumsq != nullptr) coef = fminf(1.f, max_norm / (sqrtf(*sumsq) + 1e-6f));
+  // g' = grad_scale * g (data parallel: 1 / world after a SUM all-reduce), then clip_grad_norm on ||g'||
+  float coef = grad_scale;
+  if (max_norm > 0.f && sumsq != nullptr) coef *= fminf(1.f, max_norm / (grad_scale * sqrtf(*sumsq) + 1e-6f));
   const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
   const float step_size = lr / bc1, rs2 = rsqrtf(bc2);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -363,6 +365,27 @@ __global__ void adam_flat_kernel(float* __restrict__ p, const float* __restrict_
   }
 }
 __global__ void bump_kernel(float* step_dev) { *step_dev += 1.f; }
+// g *= pre_scale * min(1, max_norm / (pre_scale * sqrt(sumsq) + 1e-6)): clip_grad_norm_ on a flat buffer whose sum of
+// squares was taken BEFORE the pre-scale (max_norm <= 0 or sumsq == NULL: pre-scale only)
+__global__ void clip_scale_kernel(float* __restrict__ g, long long n, const float* __restrict__ sumsq, float max_norm,
+                                  float pre_scale) {
+  float coef = pre_scale;
+  if (max_norm > 0.f && sumsq != nullptr) coef *= fminf(1.f, max_norm / (pre_scale * sqrtf(*sumsq) + 1e-6f));
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    g[i] *= coef;
+}
+// dst_e[i] += alpha * src_e[i] for up to 64 (src, dst, n) entries per launch: every parameter gradient of a backward
+// pass is added into its slot of the flat gradient buffer by ONE launch (instead of one autograd AccumulateGrad add
+// per parameter).  blockIdx.y = entry.
+struct AxpyTable { const float* src[64]; float* dst[64]; long long n[64]; };
+__global__ void multi_axpy_kernel(const __grid_constant__ AxpyTable t, float alpha) {
+  const int e = blockIdx.y;
+  const float* __restrict__ s = t.src[e];
+  float* __restrict__ d = t.dst[e];
+  const long long n = t.n[e];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    d[i] = fmaf(alpha, s[i], d[i]);
+}
 }  // namespace gp
 
 extern "C" int gp_sumsq_f32(const float* g, long long n, float* out, float* ws, gp_stream_t stream) {
@@ -377,12 +400,41 @@ extern "C" int gp_sumsq_f32(const float* g, long long n, float* out, float* ws, 
 
 extern "C" int gp_adam_step_f32(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
                                 float beta2, float eps, float* step_dev, const float* sumsq_dev, float max_norm,
-                                gp_stream_t stream) {
-  GP_REQUIRE(p && g && m && v && step_dev && n > 0, "adam_step: bad args");
+                                float grad_scale, gp_stream_t stream) {
+  GP_REQUIRE(p && g && m && v && step_dev && n > 0 && grad_scale > 0.f, "adam_step: bad args");
   gp::adam_flat_kernel<<<grid_for(n, 256 * 4), 256, 0, S(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, step_dev,
-                                                                      sumsq_dev, max_norm);
+                                                                      sumsq_dev, max_norm, grad_scale);
   GP_LAUNCHED();
   gp::bump_kernel<<<1, 1, 0, S(stream)>>>(step_dev);
   GP_LAUNCHED();
+  return GP_OK;
+}
+
+extern "C" int gp_clip_scale_f32(float* g, long long n, const float* sumsq_dev, float max_norm, float pre_scale,
+                                 gp_stream_t stream) {
+  GP_REQUIRE(g && n > 0 && pre_scale > 0.f, "clip_scale: bad args");
+  gp::clip_scale_kernel<<<grid_for(n, 256 * 4), 256, 0, S(stream)>>>(g, n, sumsq_dev, max_norm, pre_scale);
+  GP_LAUNCHED();
+  return GP_OK;
+}
+
+extern "C" int gp_multi_axpy_f32(const gp_axpy_entry* entries, int count, float alpha, gp_stream_t stream) {
+  GP_REQUIRE(entries != nullptr && count > 0, "multi_axpy: bad args");
+  for (int e0 = 0; e0 < count; e0 += 64) {
+    gp::AxpyTable t;
+    const int c = count - e0 < 64 ? count - e0 : 64;
+    long long nmax = 0;
+    for (int i = 0; i < 64; ++i) {
+      const gp_axpy_entry& q = entries[e0 + (i < c ? i : 0)];
+      GP_REQUIRE(q.src && q.dst && q.n >= 0, "multi_axpy: entry %d: null pointer or negative length", e0 + i);
+      t.src[i] = q.src; t.dst[i] = q.dst; t.n[i] = i < c ? q.n : 0;
+      if (i < c && q.n > nmax) nmax = q.n;
+    }
+    if (nmax == 0) continue;
+    int bx = (int)((nmax + 256 * 4 - 1) / (256 * 4));
+    if (bx > 64) bx = 64;
+    gp::multi_axpy_kernel<<<dim3(bx, c), 256, 0, S(stream)>>>(t, alpha);
+    GP_LAUNCHED();
+  }
   return GP_OK;
 }

@@ -21,6 +21,7 @@
 //   the per-row sums of relu(Y) and relu(Y)^2 that the following BatchNorm-per-node needs (encoders.py:1062).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <string.h>
 #include "common.cuh"
 
 namespace gp {
@@ -118,7 +119,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
       : "r"(taddr) : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-// UMMA smem descriptor, SWIZZLE_128B (see gemm_tc.cu)
+// UMMA shared-memory descriptor for a SWIZZLE_128B tile: start address >> 4 (14 bits), leading-dimension byte offset
+// >> 4 at bit 16, stride-dimension byte offset >> 4 at bit 32 (the 1024-byte pitch of an 8-row swizzle atom), descriptor
+// version 1 at bit 46, layout type 2 (= 128-byte swizzle) at bit 61
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
@@ -829,11 +832,7 @@ template <int BN, int STAGES, int EPI, int EW>
 static int launch(const Maps& maps, Params& p, cudaStream_t st) {
   using L = Smem<BN, STAGES, EW>;
   auto kern = tc_gemm2_kernel<BN, STAGES, EPI, EW>;
-  static bool configured = false;
-  if (!configured) {
-    GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes));
-    configured = true;
-  }
+  GP_CONFIG_ONCE(GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes)));
   const int split = p.split_k > 1 ? p.split_k : 1;
   p.tiles_m = (p.M + BM - 1) / BM;
   p.tiles_n = (p.N + BN - 1) / BN;
@@ -987,6 +986,25 @@ extern "C" int gp_bgemm_bf16_norm(const gp_gemm_bf16x* g, float* rnorm, float* r
 
 extern "C" int gp_bgemm_bf16x(const gp_gemm_bf16x* g, gp_stream_t stream) {
   return gp::v2::run(g, gp::S(stream));
+}
+
+// single-product form of the same ABI: one operand pair of the persistent kernel
+extern "C" int gp_bgemm_bf16(const gp_gemm_bf16* g, gp_stream_t stream) {
+  GP_REQUIRE(g != nullptr, "bgemm_bf16: null descriptor");
+  gp_gemm_bf16x x;
+  memset(&x, 0, sizeof(x));
+  x.npairs = 1;
+  x.pair[0].A = g->A; x.pair[0].B = g->B; x.pair[0].K = g->K;
+  x.pair[0].ldA = g->ldA; x.pair[0].sAb = g->sAb; x.pair[0].a_major = g->a_major;
+  x.pair[0].ldB = g->ldB; x.pair[0].sBb = g->sBb; x.pair[0].b_major = g->b_major;
+  x.pair[0].lim_k = g->lim_k;
+  x.C = g->C; x.Cb = g->Cb; x.M = g->M; x.N = g->N; x.batch = g->batch;
+  x.ldC = g->ldC; x.sCb = g->sCb; x.ldCb = g->ldCb; x.sCbb = g->sCbb;
+  x.lim = g->lim; x.lim_m = g->lim_m; x.lim_n = g->lim_n;
+  x.alpha = g->alpha; x.beta = g->beta; x.alpha_dev = g->alpha_dev;
+  x.bias = g->bias; x.relu = g->relu; x.split_k = g->split_k;
+  x.cond = nullptr; x.cond_npairs = 0; x.cond_alpha = 1.f; x.order = nullptr;
+  return gp::v2::run(&x, gp::S(stream));
 }
 
 // n_partial = batch * ceil(N/128) * ceil(N/256) * (epilogue warps)

@@ -916,8 +916,7 @@ int layer_bwd_fast(const gp_layer_bwd* q, cudaStream_t st, bool* handled) {
       GP_PIPE_SEL(512, 2) GP_PIPE_SEL(512, 3) GP_PIPE_SEL(512, 4)
       GP_PIPE_SEL(1024, 2) GP_PIPE_SEL(1024, 3) GP_PIPE_SEL(1024, 4)
 #undef GP_PIPE_SEL
-      static bool cfgd = false;
-      if (!cfgd) { GP_CUDA(cudaFuncSetAttribute(pipe_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); cfgd = true; }
+      GP_CUDA(cudaFuncSetAttribute(pipe_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));   // one site, several variants
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3((unsigned)(ncl * PCS));
       cfg.blockDim = dim3(pipe_threads);

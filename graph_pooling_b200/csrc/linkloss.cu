@@ -138,48 +138,37 @@ __global__ void loss_finalize_kernel(const float* __restrict__ partial, int n_pa
 }
 
 // ---------------------------------------------------------------------------------------------
-// Tensor-core path: P = S S^T comes from gp_bgemm_bf16 (fp32, [B,N,N]); this pass fuses the masked
-// BCE reduction with the write of the symmetrised gradient as the bf16 operand of the backward GEMM.
-// 32x32 tiles; the transposed adjacency tile is staged through shared memory.
+// adj_hop > 1 (encoders.py:1312-1317): the predicted adjacency is Q = sum_{h=1..hop} (S S^T)^h, materialised by the
+// caller's GEMM chain; this pass does the clamp (R3: min(Q, 1)), the masked BCE reduction and writes G = dl/dQ
+// (fp32, NOT symmetrised: the backward pushes it through the powers of P first), zero where the clamp is active
+// or outside the n_b x n_b block.  One partial per 32-row x 256-column strip.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-linkloss_from_p_kernel(const float* __restrict__ P, const float* __restrict__ adj, const int32_t* __restrict__ nb,
-                       int N, long long ldg, float* __restrict__ partial, __nv_bfloat16* __restrict__ gsym) {
-  __shared__ float At[32][33];
+linkloss_from_q_kernel(const float* __restrict__ Q, const float* __restrict__ adj, const int32_t* __restrict__ nb,
+                       int N, float* __restrict__ partial, float* __restrict__ G) {
   __shared__ float sh[33];
-  const int b = blockIdx.z, i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
-  const int T = gridDim.x;
+  const int b = blockIdx.z, i0 = blockIdx.y * 32, j0 = blockIdx.x * 256;
   const int nreal = nb != nullptr ? min(nb[b], N) : N;
-  const int nfill = min(N, (nreal + 63) / 64 * 64);      // gsym must be finite up to the next 64 multiple
-  const long long pidx = ((long long)b * T + blockIdx.y) * T + blockIdx.x;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  if (i0 >= nfill || j0 >= nfill) {
-    if (threadIdx.x == 0) partial[pidx] = 0.f;
-    return;
-  }
+  const long long pidx = ((long long)b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
   const float* ab = adj + (long long)b * N * N;
-  const float* pb = P + (long long)b * N * N;
-  for (int r = ty; r < 32; r += 8) {
-    const int gr = j0 + r, gc = i0 + tx;
-    At[r][tx] = (gr < nreal && gc < nreal) ? ab[(long long)gr * N + gc] : 0.f;
-  }
-  __syncthreads();
+  const float* qb = Q + (long long)b * N * N;
   float lsum = 0.f;
-  for (int r = ty; r < 32; r += 8) {
-    const int m = i0 + r, n = j0 + tx;
-    if (m >= N || n >= N) continue;
-    float g = 0.f;
-    if (m < nreal && n < nreal) {
-      float p = pb[(long long)m * N + n];
-      const bool over = p > 1.f;
-      if (over) p = 1.f;
-      float l, g1, l2, g2;
-      bce(ab[(long long)m * N + n], p, over, l, g1);
-      bce(At[tx][r], p, over, l2, g2);
-      lsum += l;
-      g = g1 + g2;
+  const int n = j0 + threadIdx.x;
+  if (n < N) {
+    for (int r = 0; r < 32; ++r) {
+      const int m = i0 + r;
+      if (m >= N) break;
+      float g = 0.f;
+      if (m < nreal && n < nreal) {
+        float q = qb[(long long)m * N + n];
+        const bool over = q > 1.f;
+        if (over) q = 1.f;
+        float l;
+        bce(ab[(long long)m * N + n], q, over, l, g);
+        lsum += l;
+      }
+      if (G != nullptr) G[((long long)b * N + m) * N + n] = g;
     }
-    if (gsym != nullptr && m < nfill && n < nfill) gsym[((long long)b * N + m) * ldg + n] = __float2bfloat16_rn(g);
   }
   const float tot = block_sum(lsum, sh);
   if (threadIdx.x == 0) partial[pidx] = tot;
@@ -189,14 +178,14 @@ linkloss_from_p_kernel(const float* __restrict__ P, const float* __restrict__ ad
 
 using namespace gp;
 
-extern "C" int gp_linkloss_from_p(const float* P, const float* adj, const int32_t* nb, int B, int N, long long ldg,
-                                  float* partial, void* gsym_bf16, gp_stream_t stream) {
-  GP_REQUIRE(P && adj && partial && B > 0 && N > 0 && ldg >= N, "linkloss_from_p: bad args");
-  const int T = (N + 31) / 32;
-  GP_REQUIRE(B <= 65535 && T <= 65535, "linkloss_from_p: grid too large");
-  dim3 grid(T, T, B);
-  linkloss_from_p_kernel<<<grid, 256, 0, S(stream)>>>(P, adj, nb, N, ldg, partial,
-                                                       reinterpret_cast<__nv_bfloat16*>(gsym_bf16));
+extern "C" int gp_linkloss_from_q_partials(int B, int N) { return B * ((N + 31) / 32) * ((N + 255) / 256); }
+extern "C" int gp_linkloss_from_q(const float* Q, const float* adj, const int32_t* nb, int B, int N, float* partial,
+                                  float* G, gp_stream_t stream) {
+  GP_REQUIRE(Q && adj && partial && B > 0 && N > 0, "linkloss_from_q: bad args");
+  const int Ty = (N + 31) / 32, Tx = (N + 255) / 256;
+  GP_REQUIRE(B <= 65535 && Ty <= 65535, "linkloss_from_q: grid too large");
+  dim3 grid(Tx, Ty, B);
+  linkloss_from_q_kernel<<<grid, 256, 0, S(stream)>>>(Q, adj, nb, N, partial, G);
   GP_LAUNCHED();
   return GP_OK;
 }

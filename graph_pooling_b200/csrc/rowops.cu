@@ -625,8 +625,7 @@ extern "C" int gp_relu_bn_fwd(const float* y, float* h, long long ldh, float* me
   const size_t cache_bytes = (size_t)total * sizeof(float);
   if (bn && cache_bytes > 16 * 1024 && cache_bytes <= kNodeCacheMax) {
     auto kern = relu_bn_fwd_kernel<true>;
-    static bool cfgd = false;
-    if (!cfgd) { GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNodeCacheMax)); cfgd = true; }
+    GP_CONFIG_ONCE(GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNodeCacheMax)));
     kern<<<N, 1024, cache_bytes, S(stream)>>>(y, h, ldh, mean, invstd, B, N, d, relu, bn);
   } else {
     const int threads = total >= 4096 ? 512 : (total >= 512 ? 256 : 128);
@@ -680,8 +679,7 @@ int layer_bwd_generic(const gp_layer_bwd* q, cudaStream_t st) {
   do {                                                                                                     \
     auto kern = gcn_layer_bwd_kernel<C_, E_>;                                                              \
     if (C_) {                                                                                              \
-      static bool cfgd = false;                                                                            \
-      if (!cfgd) { GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNodeCacheMax)); cfgd = true; } \
+      GP_CONFIG_ONCE(GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNodeCacheMax))); \
     }                                                                                                      \
     kern<<<N, threads, C_ ? cache_bytes : 0, st>>>(a);                                                     \
   } while (0)

@@ -349,12 +349,9 @@ bool small_gcn_eligible(int B, int N, int din, int dout, int add_self) {
 int small_gcn_fwd(const float* x, long long ldx, const float* adj, const float* w, const float* bias, const int32_t* nb,
                   int B, int N, int din, int dout, int normalize, float* u, float* y, long long ldy, float* rnorm,
                   cudaStream_t st) {
-  static bool cfgd = false;
-  if (!cfgd) {
-    GP_CUDA(cudaFuncSetAttribute(gconv_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallMaxSmem));
-    GP_CUDA(cudaFuncSetAttribute(gconv_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallMaxSmem));
-    cfgd = true;
-  }
+  GP_CONFIG_ONCE(
+      GP_CUDA(cudaFuncSetAttribute(gconv_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallMaxSmem));
+      GP_CUDA(cudaFuncSetAttribute(gconv_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallMaxSmem)));
   SmallFwd p;
   p.x = x; p.ldx = ldx; p.adj = adj; p.w = w; p.bias = bias; p.nb = nb;
   p.B = B; p.N = N; p.din = din; p.dout = dout; p.normalize = normalize;
@@ -373,12 +370,9 @@ long long small_gcn_bwd_ws(int B, int din, int dout) {
 int small_gcn_bwd(const float* dv, const float* u, const float* x, long long ldx, const float* adj, const float* w,
                   const int32_t* nb, int B, int N, int din, int dout, float* dw, float* db, float* dx, float* dadj,
                   float* ws, cudaStream_t st) {
-  static bool cfgd = false;
-  if (!cfgd) {
-    GP_CUDA(cudaFuncSetAttribute(gconv_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallMaxSmem));
-    GP_CUDA(cudaFuncSetAttribute(gconv_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallMaxSmem));
-    cfgd = true;
-  }
+  GP_CONFIG_ONCE(
+      GP_CUDA(cudaFuncSetAttribute(gconv_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallMaxSmem));
+      GP_CUDA(cudaFuncSetAttribute(gconv_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallMaxSmem)));
   SmallBwd p;
   p.dv = dv; p.u = u; p.x = x; p.ldx = ldx; p.adj = adj; p.w = w; p.nb = nb;
   p.B = B; p.N = N; p.din = din; p.dout = dout; p.part = ws; p.dx = dx; p.dadj = dadj;
@@ -521,12 +515,9 @@ bool small_pool_eligible(int B, int N, int K, int F) {
 }
 
 static int small_pool_cfg() {
-  static bool cfgd = false;
-  if (!cfgd) {
-    GP_CUDA(cudaFuncSetAttribute(pool_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallMaxSmem));
-    GP_CUDA(cudaFuncSetAttribute(pool_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallMaxSmem));
-    cfgd = true;
-  }
+  GP_CONFIG_ONCE(
+      GP_CUDA(cudaFuncSetAttribute(pool_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallMaxSmem));
+      GP_CUDA(cudaFuncSetAttribute(pool_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallMaxSmem)));
   return GP_OK;
 }
 

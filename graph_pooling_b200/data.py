@@ -80,18 +80,24 @@ class GraphSet:
         idx = torch.as_tensor(idx, device=dev, dtype=torch.long)
         B, N = int(idx.numel()), int(max_nodes)
         nb = d['n'][idx]
-        # position of each selected graph inside the batch (graphs not selected -> -1)
-        slot = torch.full((len(self.n),), -1, device=dev, dtype=torch.long)
-        slot[idx] = torch.arange(B, device=dev)
+        # gather per BATCH POSITION (a graph id may occur several times: sampling with replacement, oversampled
+        # cross-validation folds): position p owns the edge range eptr[idx[p]] .. eptr[idx[p]+1] and the node range
+        # nptr[idx[p]] .. nptr[idx[p]+1], expanded with repeat_interleave
+        def expand(ptr):
+            start = ptr[idx]
+            cnt = ptr[idx + 1] - start
+            pos = torch.repeat_interleave(torch.arange(B, device=dev), cnt)
+            first = torch.cumsum(cnt, 0) - cnt                             # offset of each position's first item
+            item = torch.arange(int(pos.numel()), device=dev) - first[pos] + start[pos]
+            return pos, item
+
         adj = torch.zeros(B, N, N, device=dev, dtype=adj_dtype)
-        es = slot[d['egraph']]
-        keep = es >= 0
-        eb, eu, ev = es[keep], d['edges'][keep, 0], d['edges'][keep, 1]
+        eb, ei = expand(d['eptr'])
+        eu, ev = d['edges'][ei, 0], d['edges'][ei, 1]
         adj[eb, eu, ev] = 1
         adj[eb, ev, eu] = 1
-        ns = slot[d['ngraph']]
-        nk = ns >= 0
-        nbi, nli = ns[nk], d['nlocal'][nk]
+        nbi, nk = expand(d['nptr'])
+        nli = d['nlocal'][nk]
         if features == 'node-label' and 'nlabel' in d:                     # train.py:477-481
             x = torch.zeros(B, N, self.num_node_labels, device=dev)
             x[nbi, nli, d['nlabel'][nk]] = 1.0
@@ -141,7 +147,6 @@ def read_tu_dataset(datadir, name, max_nodes=None):
     starts = np.concatenate([[0], np.cumsum(counts)])
     local = np.arange(len(unode)) - starts[ugraph]
     # global (graph, node) -> local id lookup for the edges
-    lut = dict()                                                            # only needed if a node spans graphs
     node_local = np.full(len(gind) + 1, -1, np.int64)
     node_local[unode] = local                                               # well-formed: one graph per node
     keep_g = np.ones(G, bool) if max_nodes is None else counts <= max_nodes

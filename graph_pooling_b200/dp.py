@@ -37,7 +37,13 @@ def shard_batch(rank, world, x, adj, batch_num_nodes, label, assign_x=None):
 
 
 class FlatGradients:
-    """One contiguous fp32 buffer holding every parameter's gradient (p.grad are views into it)."""
+    """One contiguous fp32 buffer holding every parameter's gradient (p.grad are views into it).
+
+    On CUDA nothing here is an ATen op: zero() is gp_fill_f32, the averaging after the SUM all-reduce is a factor
+    (`pending_scale`) that FlatAdam folds into gp_adam_step_f32 (or gp_clip_scale_f32 applies), clip_() is
+    gp_sumsq_f32 + gp_clip_scale_f32, and -- once attach()ed to a drop-in encoder -- the backward pass adds all its
+    parameter gradients into the buffer with ONE gp_multi_axpy_f32 launch instead of one autograd AccumulateGrad add
+    per parameter.  CPU tensors (the gloo tests run the oracle through this class) take the plain torch ops."""
 
     def __init__(self, params):
         self.params = [p for p in params if p.requires_grad]
@@ -46,33 +52,101 @@ class FlatGradients:
         dev, dt = self.params[0].device, self.params[0].dtype
         n = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(n, device=dev, dtype=dt)
+        self.cuda = self.flat.is_cuda and dt == torch.float32
+        self.pending_scale = 1.0            # factor still to be applied to `flat` (1 / world after a SUM all-reduce)
+        self._sumsq = self._ws = None
+        self._offset = {}
         off = 0
         for p in self.params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
+            self._offset[id(p)] = off
             off += p.numel()
 
+    def attach(self, model):
+        """Let `model`'s backward (graph_pooling_b200.encoders) deliver its parameter gradients straight into this
+        buffer (accumulating, like autograd would)."""
+        if self.cuda:
+            model._grad_sink = self
+        return self
+
     def zero(self):
-        self.flat.zero_()
+        if self.cuda:
+            import ctypes as C
+            from ._lib import call
+            call('gp_fill_f32', self.flat.data_ptr(), C.c_longlong(self.flat.numel()), C.c_float(0.0),
+                 torch.cuda.current_stream().cuda_stream)
+        else:
+            self.flat.zero_()
+        self.pending_scale = 1.0
         off = 0
         for p in self.params:                       # re-attach if someone replaced / dropped p.grad
             if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + off * self.flat.element_size():
                 p.grad = self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
 
+    def accumulate(self, params, grads):
+        """Called by the encoders' backward: adds every gradient whose parameter lives in this buffer with one
+        gp_multi_axpy_f32 launch per 64 parameters and returns the list with those entries replaced by None (autograd
+        then has nothing left to accumulate for them)."""
+        import ctypes as C
+        from ._lib import GpAxpyEntry, call
+        out, ent = list(grads), []
+        base, esz = self.flat.data_ptr(), self.flat.element_size()
+        for i, (p, g) in enumerate(zip(params, grads)):
+            off = self._offset.get(id(p))
+            if g is None or off is None or p.grad is None or p.grad.data_ptr() != base + off * esz:
+                continue
+            if not (g.is_cuda and g.dtype == torch.float32 and g.is_contiguous() and g.numel() == p.numel()):
+                continue
+            ent.append((g.data_ptr(), base + off * esz, g.numel()))
+            out[i] = None
+        if ent:
+            tab = (GpAxpyEntry * len(ent))(*[GpAxpyEntry(a, b, n) for a, b, n in ent])
+            call('gp_multi_axpy_f32', C.cast(tab, C.c_void_p), len(ent), C.c_float(1.0),
+                 torch.cuda.current_stream().cuda_stream)
+        return out
+
     def all_reduce(self, group=None, average=True):
         world = dist.get_world_size(group) if dist.is_initialized() else 1
         if world > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
             if average:
-                self.flat.div_(world)
+                if self.cuda:
+                    self.pending_scale = 1.0 / world      # folded into the optimiser / clip kernel
+                else:
+                    self.flat.div_(world)
+        return self.flat
+
+    def apply_pending_scale(self):
+        """Materialise the averaging factor in the buffer (callers that read `flat` directly)."""
+        if self.pending_scale != 1.0:
+            import ctypes as C
+            from ._lib import call
+            call('gp_clip_scale_f32', self.flat.data_ptr(), C.c_longlong(self.flat.numel()), None, C.c_float(0.0),
+                 C.c_float(self.pending_scale), torch.cuda.current_stream().cuda_stream)
+            self.pending_scale = 1.0
         return self.flat
 
     def clip_(self, max_norm):
         """torch.nn.utils.clip_grad_norm_ semantics on the (already reduced) flat buffer; returns the norm."""
-        norm = self.flat.norm(2)
-        coef = torch.clamp(max_norm / (norm + 1e-6), max=1.0)
-        self.flat.mul_(coef)
-        return norm
+        if not self.cuda:
+            norm = self.flat.norm(2)
+            coef = torch.clamp(max_norm / (norm + 1e-6), max=1.0)
+            self.flat.mul_(coef)
+            return norm
+        import ctypes as C
+        from ._lib import call
+        st = torch.cuda.current_stream().cuda_stream
+        if self._sumsq is None:
+            self._sumsq = torch.zeros(1, device=self.flat.device)
+            self._ws = torch.empty(1024, device=self.flat.device)
+        n = C.c_longlong(self.flat.numel())
+        scale = self.pending_scale
+        call('gp_sumsq_f32', self.flat.data_ptr(), n, self._sumsq.data_ptr(), self._ws.data_ptr(), st)
+        call('gp_clip_scale_f32', self.flat.data_ptr(), n, self._sumsq.data_ptr(), C.c_float(float(max_norm)),
+             C.c_float(scale), st)
+        self.pending_scale = 1.0
+        return self._sumsq.sqrt() * scale           # diagnostic only (not on the training path)
 
 
 class FlatAdam:
@@ -117,7 +191,9 @@ class FlatAdam:
             self._call('gp_sumsq_f32', g.data_ptr(), n, self.sumsq.data_ptr(), self._ws.data_ptr(), st)
         self._call('gp_adam_step_f32', self.flat_p.data_ptr(), g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), n,
                    C.c_float(self.lr), C.c_float(self.betas[0]), C.c_float(self.betas[1]), C.c_float(self.eps),
-                   self.step_dev.data_ptr(), self.sumsq.data_ptr() if clip > 0 else None, C.c_float(clip), st)
+                   self.step_dev.data_ptr(), self.sumsq.data_ptr() if clip > 0 else None, C.c_float(clip),
+                   C.c_float(self.grads.pending_scale), st)
+        self.grads.pending_scale = 1.0
 
 
 class DataParallelTrainer:
@@ -130,7 +206,7 @@ class DataParallelTrainer:
             raise ValueError("mode must be 'shard_mean' or 'global_norm'")
         self.model, self.optimizer, self.clip, self.mode, self.group = model, optimizer, clip, mode, group
         self.linkpred = linkpred
-        self.grads = FlatGradients(model.parameters())
+        self.grads = FlatGradients(model.parameters()).attach(model)
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
 
@@ -171,8 +247,14 @@ class DataParallelTrainer:
         loss = self._loss(ypred, label, adj, batch_num_nodes, global_num_nodes, global_batch)
         loss.backward()
         self.grads.all_reduce(self.group, average=(self.mode == 'shard_mean'))
+        if isinstance(self.optimizer, FlatAdam) and self.optimizer.grads is self.grads:
+            self.optimizer.clip = self.clip            # averaging factor + clip folded into the Adam kernel
+            self.optimizer.step()
+            return ypred, loss
         if self.clip is not None:
             self.grads.clip_(self.clip)
+        else:
+            self.grads.apply_pending_scale() if self.grads.cuda else None
         if self.optimizer is not None:
             self.optimizer.step()
         return ypred, loss

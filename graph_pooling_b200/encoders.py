@@ -208,7 +208,7 @@ def _bwd_tc(ctx, tape, dypred, dS0):
                                                dza.data_ptr(), lv['Fa'])
                 put(plan.emb, gE)
                 put(plan.assign[0], gA)
-                return (None, None, None, None) + tuple(grads)
+                return (None, None, None, None) + tuple(_deliver(plan, params, grads))
             gl, dxa = T.stack_backward(ws, lv['c_as'], dza.data_ptr(), lv['Fa'], None, None, 0, i > 0,
                                        None if i == 0 else d_ap[i - 1])
             put(plan.assign[i], gl)
@@ -219,7 +219,14 @@ def _bwd_tc(ctx, tape, dypred, dS0):
     gl, _ = T.stack_backward(ws, tape['emb'], None if dz_dense is None else dz_dense.data_ptr(), Fw, dout_p, arg_p,
                              ldo, False, None)
     put(plan.emb, gl)
-    return (None, None, None, None) + tuple(grads)
+    return (None, None, None, None) + tuple(_deliver(plan, params, grads))
+
+
+def _deliver(plan, params, grads):
+    """Hand the parameter gradients of a backward pass to autograd -- or, when a dp.FlatGradients buffer is attached
+    to the model (`model._grad_sink`), add them into it with one gp_multi_axpy_f32 launch and return None for them."""
+    sink = getattr(plan, 'grad_sink', None)
+    return grads if sink is None else sink.accumulate(params, grads)
 
 
 class _EncoderFn(torch.autograd.Function):
@@ -372,7 +379,7 @@ class _EncoderFn(torch.autograd.Function):
         gl, _ = E.stack_backward(ws, tape['emb'], None if dz_dense is None else dz_dense.data_ptr(), Fw, dout_p,
                                  arg_p, ldo, False, None, prec)
         put(plan.emb, gl)
-        return (None, None, None, None) + tuple(grads)
+        return (None, None, None, None) + tuple(_deliver(plan, params, grads))
 
 
 class _LossFn(torch.autograd.Function):
@@ -513,6 +520,81 @@ class _LossFn(torch.autograd.Function):
                 ctx.enc_plan.ds_tag = dS.data_ptr()      # _padded_grad recognises the buffer and uses it in place
             dS = dS[:, :, :ctx.Kvis]
         return None, dy, None, dS, None
+
+
+class _LinkHopFn(torch.autograd.Function):
+    """Link-prediction loss with adj_hop > 1 (encoders.py:1312-1317): the predicted adjacency is
+    Q = sum_{h=1..hop} P^h with P = S S^T, clamped at 1 (R3).  Never passed by the reference's callers, so it runs on
+    the fp32 FFMA schedule in either precision mode: the powers of P are materialised ([B,N,N] fp32 each, like the
+    reference does) by the library's batched GEMM, gp_linkloss_from_q does clamp + masked BCE + G = dl/dQ, and the
+    backward pushes G through the powers:  D_1 = G,  D_h = P D_{h-1} + G P^{h-1},  dP = sum_h D_h,
+    dS = (dP + dP^T) S.  forward returns (base + link, link); `base` is the CE (+ entropy) scalar."""
+
+    @staticmethod
+    def forward(ctx, S, base, adj, nb_dev, inv, hop):
+        st = E._stream()
+        ws = E.Workspace(S.device)
+        S = E._chk(S, 'assign_tensor')
+        B, N, K = S.shape
+        nbp, lim = E._p(nb_dev), int(nb_dev is not None)
+        sNN, sNK = (N * N, N, 1), (N * K, K, 1)
+        P1 = ws.f(B, N, N)
+        E.bgemm(S.data_ptr(), S.data_ptr(), P1.data_ptr(), N, N, K, B, sNK, (N * K, 1, K), sNN, lim=nbp, lim_m=lim,
+                lim_n=lim)
+        pows = [P1]
+        Q = ws.f(B, N, N)
+        call('gp_pad_copy_f32', P1.data_ptr(), C.c_longlong(N), C.c_longlong(B * N), N, Q.data_ptr(),
+             C.c_longlong(N), C.c_longlong(B * N), N, C.c_float(0.0), st)
+        for _ in range(hop - 1):
+            Th = ws.f(B, N, N)
+            E.bgemm(pows[-1].data_ptr(), P1.data_ptr(), Th.data_ptr(), N, N, N, B, sNN, sNN, sNN, lim=nbp, lim_m=lim,
+                    lim_n=lim, lim_k=lim)
+            call('gp_axpy_f32', Th.data_ptr(), Q.data_ptr(), C.c_longlong(Q.numel()), C.c_float(1.0), st)
+            pows.append(Th)
+        need_grad = ctx.needs_input_grad[0]
+        npart = int(T.load().gp_linkloss_from_q_partials(B, N))
+        partial = ws.f(npart + 256)
+        G = ws.f(B, N, N) if need_grad else None
+        call('gp_linkloss_from_q', Q.data_ptr(), adj.data_ptr(), nbp, B, N, partial.data_ptr(), E._p(G), st)
+        total, link = ws.f(1), ws.f(1)
+        call('gp_loss_finalize', partial.data_ptr(), npart, C.c_double(inv), base.data_ptr(), total.data_ptr(),
+             link.data_ptr(), st)
+        ctx.tape = (S, pows[:-1], G, nb_dev, float(inv), int(hop))
+        link = link.view(())
+        ctx.mark_non_differentiable(link)
+        return total.view(()), link
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g, _unused=None):
+        S, pows, G, nb_dev, inv, hop = ctx.tape
+        ctx.tape = None
+        st = E._stream()
+        ws = E.Workspace(S.device)
+        g = E._chk(g, 'grad of loss')
+        dS = None
+        if G is not None:
+            B, N, K = S.shape
+            nbp, lim = E._p(nb_dev), int(nb_dev is not None)
+            sNN, sNK = (N * N, N, 1), (N * K, K, 1)
+            kw = dict(lim=nbp, lim_m=lim, lim_n=lim, lim_k=lim)
+            D, tot = G, G
+            if hop > 1:
+                tot = ws.f(B, N, N)
+                call('gp_pad_copy_f32', G.data_ptr(), C.c_longlong(N), C.c_longlong(B * N), N, tot.data_ptr(),
+                     C.c_longlong(N), C.c_longlong(B * N), N, C.c_float(0.0), st)
+            for h in range(2, hop + 1):
+                Dn = ws.f(B, N, N)
+                E.bgemm(pows[0].data_ptr(), D.data_ptr(), Dn.data_ptr(), N, N, N, B, sNN, sNN, sNN, **kw)
+                E.bgemm(G.data_ptr(), pows[h - 2].data_ptr(), Dn.data_ptr(), N, N, N, B, sNN, sNN, sNN, beta=1.0, **kw)
+                call('gp_axpy_f32', Dn.data_ptr(), tot.data_ptr(), C.c_longlong(tot.numel()), C.c_float(1.0), st)
+                D = Dn
+            dS = ws.f(B, N, K)
+            E.bgemm(tot.data_ptr(), S.data_ptr(), dS.data_ptr(), N, K, N, B, sNN, sNK, sNK, lim=nbp, lim_m=lim,
+                    lim_k=lim, alpha=inv, alpha_dev=g.data_ptr())
+            E.bgemm(tot.data_ptr(), S.data_ptr(), dS.data_ptr(), N, K, N, B, (N * N, 1, N), sNK, sNK, lim=nbp,
+                    lim_m=lim, lim_k=lim, alpha=inv, alpha_dev=g.data_ptr(), beta=1.0)
+        return dS, g, None, None, None, None
 
 
 # ------------------------------------------------------------------------------------------
@@ -722,6 +804,7 @@ class GcnEncoderGraph(nn.Module):
                              % (x.shape[2], self.conv_first.weight.shape[0]))
         plan = _Plan()
         plan.precision = self.precision
+        plan.grad_sink = getattr(self, '_grad_sink', None)
         plan.nb_dev, plan.nb_host = E.prep_nb(batch_num_nodes, adj.shape[1], x.device)
         if plan.nb_host is not None and len(plan.nb_host) != x.shape[0]:
             raise ValueError('batch_num_nodes has %d entries for a batch of %d' % (len(plan.nb_host), x.shape[0]))
@@ -1058,8 +1141,9 @@ class SoftPoolingGcnEncoder(GcnEncoderGraph):
             lp0 = _Plan()
             lp0.ce_scale = self._ce_scale
             return _LossFn.apply(lp0, pred, label, None, None)[0]
-        if adj_hop != 1:
-            raise NotImplementedError('gp_b200: adj_hop > 1 is not implemented (callers never pass it)')
+        adj_hop = int(adj_hop)
+        if adj_hop < 1:
+            raise ValueError('adj_hop must be >= 1')
         S0 = self._S0                                                        # R7: level-0 S with level-0 adj
         lp = _Plan()
         lp.sb0 = getattr(plan, 'sb0', None)
@@ -1096,6 +1180,21 @@ class SoftPoolingGcnEncoder(GcnEncoderGraph):
                 lp.num_entries = int(np.sum(n64 * n64))
             if self._entries_override is not None:
                 lp.num_entries = self._entries_override
+                if dev_only:        # the override (dp.py, mode='global_norm') replaces the device-side 1 / sum n_b^2 too
+                    call('gp_fill_f32', lp.inv_dev.data_ptr(), C.c_longlong(1), C.c_float(1.0 / float(lp.num_entries)),
+                         E._stream())
+        if self.linkpred and adj_hop > 1:
+            # encoders.py:1312-1317, never passed by the reference's callers: fp32 FFMA schedule, fp32 dense adjacency
+            if self.link_loss_kind != 'bce' or dev_only or isinstance(adj, T.PreparedAdjacency) or \
+                    adj.dtype != torch.float32:
+                raise NotImplementedError('gp_b200: adj_hop > 1 needs the BCE link loss, a float32 adjacency tensor and '
+                                          'host-side batch_num_nodes')
+            lp.link_kind = None
+            outs = _LossFn.apply(lp, pred, label, S0, None)
+            total, self.link_loss = _LinkHopFn.apply(S0, outs[0], adj, lp.nb_dev, 1.0 / float(lp.num_entries), adj_hop)
+            if ent_w != 0.0:
+                self.entropy_loss = outs[1]
+            return total
         outs = _LossFn.apply(lp, pred, label, S0, adj if self.linkpred else None)   # adj: tensor or PreparedAdjacency
         k = 1
         if self.linkpred:

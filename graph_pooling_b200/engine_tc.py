@@ -12,7 +12,7 @@ import os
 import torch
 
 from . import engine as E
-from ._lib import GpGemmBf16, GpGemmBf16x, GpLayerBwd, call, load
+from ._lib import GpGemmBf16x, GpLayerBwd, call, load
 
 BF16 = 1
 KM, MN = 0, 1        # operand major-ness (see include/gp_b200.h)
@@ -98,9 +98,6 @@ class PreparedAdjacency:
         return self
 
 
-_USE_V1 = bool(os.environ.get('GP_TC_V1'))     # debug: single-tile-per-CTA kernel of gemm_tc.cu
-
-
 def tcgemm_multi(pairs, M, N, batch, Cf=None, Cb=None, lim=None, lim_m=0, lim_n=0, alpha=1.0, beta=0.0,
                  alpha_dev=None, bias=None, relu=0, split_k=0, cond=None, cond_npairs=0, cond_alpha=1.0):
     """One persistent tcgen05 launch accumulating sum_q A_q.B_q (gp_bgemm_bf16x).
@@ -130,15 +127,8 @@ def tcgemm_multi(pairs, M, N, batch, Cf=None, Cb=None, lim=None, lim_m=0, lim_n=
 def tcgemm(A, a_major, Bo, b_major, M, N, K, batch, Cf=None, Cb=None, lim=None, lim_m=0, lim_n=0, lim_k=0,
            alpha=1.0, beta=0.0, alpha_dev=None, bias=None, relu=0, split_k=0, cond=None, cond_npairs=0):
     """Single product on tensor cores.  Cf = (ptr, ld, sb) fp32 output, Cb = Op bf16 output."""
-    if not _USE_V1:
-        return tcgemm_multi([(A, a_major, Bo, b_major, K, lim_k)], M, N, batch, Cf, Cb, lim, lim_m, lim_n, alpha,
-                            beta, alpha_dev, bias, relu, split_k, cond, cond_npairs)
-    cp, cld, csb = Cf if Cf is not None else (None, 0, 0)
-    g = GpGemmBf16(A.ptr, Bo.ptr, cp, None if Cb is None else Cb.ptr, M, N, K, batch,
-                   A.ld, A.sb, a_major, Bo.ld, Bo.sb, b_major, cld, csb,
-                   0 if Cb is None else Cb.ld, 0 if Cb is None else Cb.sb,
-                   lim, lim_m, lim_n, lim_k, alpha, beta, alpha_dev, bias, relu, split_k)
-    call('gp_bgemm_bf16', C.byref(g), E._stream())
+    return tcgemm_multi([(A, a_major, Bo, b_major, K, lim_k)], M, N, batch, Cf, Cb, lim, lim_m, lim_n, alpha,
+                        beta, alpha_dev, bias, relu, split_k, cond, cond_npairs)
 
 
 def pick_split(M, N, K):

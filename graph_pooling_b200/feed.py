@@ -42,7 +42,11 @@ class HostAdjacencyFeed:
         self.dtail = [torch.empty(max(B - Bp, 1), N, N, device=dev) for _ in range(2)]
         self.pa = [T.PreparedAdjacency(B, N, dev) for _ in range(2)]
         self.ready = [torch.cuda.Event(), torch.cuda.Event()]
-        for e in self.ready:
+        # freed[slot]: the last CONSUMER of the slot's device staging buffers (gp_adj_prepare_x in prepared(), and the
+        # step that read the caller's extra destinations -- consumed()) has finished; copy() waits for it before
+        # overwriting them (write-after-read across the copy and compute streams)
+        self.freed = [torch.cuda.Event(), torch.cuda.Event()]
+        for e in self.ready + self.freed:
             e.record(torch.cuda.current_stream(dev))
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.pool = ThreadPoolExecutor(1)
@@ -71,11 +75,14 @@ class HostAdjacencyFeed:
 
     def copy(self, slot, extra=()):
         """Stage 2 (copy stream, asynchronous): H2D of the packed bits and of the fp32 tail of the batch submitted to
-        `slot`; `extra` = [(dst_device_tensor, src_pinned_tensor)] rides along (features, labels)."""
+        `slot`; `extra` = [(dst_device_tensor, src_pinned_tensor)] rides along (features, labels).  The copies wait
+        for the slot's previous consumer: prepared() marks the staging buffers as consumed by itself; a caller whose
+        step reads `extra` destinations without a host synchronisation must call consumed(slot) after that step."""
         if self.fut[slot] is not None:
             self.fut[slot].result()
         adj_host = self._src[slot]
         with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.freed[slot])
             for dst, src in extra:
                 dst.copy_(src, non_blocking=True)
             if self.Bp:
@@ -94,7 +101,13 @@ class HostAdjacencyFeed:
             pa.add(self.dbits[slot], 0, nb_dev, 'bits')
         if self.Bp < self.B:
             pa.add(self.dtail[slot][:self.B - self.Bp], self.Bp, nb_dev, 'f32')
+        self.freed[slot].record(torch.cuda.current_stream(self.dev))
         return pa
+
+    def consumed(self, slot):
+        """Call on the compute stream after the step that read the slot's `extra` destinations (and the prepared
+        operand): the next copy() into this slot is ordered behind it."""
+        self.freed[slot].record(torch.cuda.current_stream(self.dev))
 
     # ---- choosing the packed fraction ---------------------------------------------------------------------------
     @staticmethod

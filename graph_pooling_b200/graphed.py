@@ -29,7 +29,7 @@ class GraphedTrainStep:
         # clip + Adam as two kernels of this library over flat buffers; the step counter lives on the device
         # (train.py:173: Adam, lr hard-coded 0.001; train.py:209: clip_grad_norm)
         self.optimizer = dp.FlatAdam(self.params, lr=lr, clip=clip)
-        self.grads = self.optimizer.grads
+        self.grads = self.optimizer.grads.attach(model)   # the backward adds its gradients in one launch
         self.soft = hasattr(model, 'num_pooling')
         self._graphs = {}
         self.replayed_launches = 0           # kernels of this library executed through graph replays
@@ -71,6 +71,10 @@ class GraphedTrainStep:
         except AttributeError:
             pass
         snapshot = [p.detach().clone() for p in self.params]
+        # a new batch shape can show up mid-training (the smaller last batch of an epoch: the reference's DataLoader
+        # does not drop it): the warm-up steps must leave the accumulated Adam moments and step count untouched too
+        opt = self.optimizer
+        opt_state = [t.detach().clone() for t in (opt.m, opt.v, opt.step_dev)]
         with torch.cuda.stream(side):
             for _ in range(self.warmup):
                 self._eager(st)
@@ -80,9 +84,8 @@ class GraphedTrainStep:
         with torch.no_grad():
             for p, s in zip(self.params, snapshot):
                 p.copy_(s)
-        self.optimizer.m.zero_()
-        self.optimizer.v.zero_()
-        self.optimizer.step_dev.zero_()
+            for t, s in zip((opt.m, opt.v, opt.step_dev), opt_state):
+                t.copy_(s)
         from ._lib import load
         g = torch.cuda.CUDAGraph()
         n0 = int(load().gp_launch_count())

@@ -309,9 +309,6 @@ int gp_linkloss_fwd(const float* s, const float* adj, const int32_t* nb, int B, 
                     float* partial, float* gsym, gp_stream_t stream);
 int gp_loss_finalize(const float* partial, int n_partial, double inv_entries, const float* ce,
                      float* total, float* link, gp_stream_t stream);
-/* Tensor-core path: P = S S^T [B,N,N] fp32 from gp_bgemm_bf16; this pass does the masked BCE
- * reduction (n_partial = B * ceil(N/32)^2) and writes gsym as the bf16 operand (row stride ldg) of
- * the backward GEMM, zero-filled up to the next multiple of 64 beyond nb[b]. */
 /* Fused tensor-core form: S (bf16, row stride lds) -> P = S S^T tiles in TMEM -> masked BCE against
  * the bf16 adjacency in the epilogue; G = dl/dP evaluated with a[m,n] (bf16, row stride ldg, may be
  * NULL; the backward is dS = (G + G^T) S = two operand pairs of gp_bgemm_bf16x) and one partial per
@@ -329,8 +326,12 @@ int gp_linkloss_tc_partials(int B, int N);
 int gp_linkloss_tc(const void* s_bf16, long long lds, const void* adj_bf16, long long ldadj,
                    const int32_t* nb, int B, int N, int K, float* partial, void* gsym_bf16, long long ldg,
                    int mode, const int32_t* adj_flags, gp_stream_t stream);
-int gp_linkloss_from_p(const float* P, const float* adj, const int32_t* nb, int B, int N, long long ldg,
-                       float* partial, void* gsym_bf16, gp_stream_t stream);
+/* adj_hop > 1 (encoders.py:1312-1317): Q = sum_{h=1..hop} (S S^T)^h [B,N,N] fp32 is formed by the caller's GEMM chain;
+ * this pass clamps (min(Q,1), R3), reduces the masked BCE against fp32 `adj` into gp_linkloss_from_q_partials(B,N)
+ * partial sums and writes G = dl/dQ (fp32 [B,N,N], zero where clamped or outside the n_b x n_b block; may be NULL). */
+int gp_linkloss_from_q_partials(int B, int N);
+int gp_linkloss_from_q(const float* Q, const float* adj, const int32_t* nb, int B, int N, float* partial, float* G,
+                       gp_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * North-star loss options that the reference does NOT contain (oracle: the DiffPool paper's definitions,
@@ -366,12 +367,22 @@ int gp_add_scaled(const float* base, const float* term, float w, float* total, g
 int gp_nb_stats(const int32_t* nb, int B, float* out, gp_stream_t stream);
 /* Optimiser step of train.py:209-210 over flat buffers (dp.FlatAdam):
  *   gp_sumsq_f32      *out = sum_i g[i]^2 (deterministic two-stage; ws: 1024 floats)
- *   gp_adam_step_f32  clip_grad_norm folded into Adam: g' = g * min(1, max_norm / (sqrt(*sumsq) + 1e-6)) (skipped when
- *                     max_norm <= 0 or sumsq == NULL); torch.optim.Adam's update with t = *step_dev + 1 (no weight
- *                     decay, no amsgrad); then *step_dev += 1.  step_dev: device float counter (CUDA-graph friendly). */
+ *   gp_adam_step_f32  g' = grad_scale * g (data parallel: 1 / world after the SUM all-reduce, else 1), then
+ *                     clip_grad_norm folded into Adam: g'' = g' * min(1, max_norm / (grad_scale * sqrt(*sumsq) + 1e-6))
+ *                     (skipped when max_norm <= 0 or sumsq == NULL; *sumsq is the sum of squares of the UNSCALED g);
+ *                     torch.optim.Adam's update with t = *step_dev + 1 (no weight decay, no amsgrad); then
+ *                     *step_dev += 1.  step_dev: device float counter (CUDA-graph friendly).
+ *   gp_clip_scale_f32 the same scaling applied to g in place (for optimisers other than FlatAdam)
+ *   gp_multi_axpy_f32 dst_e[i] += alpha * src_e[i] for `count` entries (host array) in ceil(count/64) launches: all
+ *                     parameter gradients of one backward pass are added into the flat gradient buffer at once. */
+typedef struct gp_axpy_entry { const float* src; float* dst; long long n; } gp_axpy_entry;
 int gp_sumsq_f32(const float* g, long long n, float* out, float* ws, gp_stream_t stream);
 int gp_adam_step_f32(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
-                     float eps, float* step_dev, const float* sumsq_dev, float max_norm, gp_stream_t stream);
+                     float eps, float* step_dev, const float* sumsq_dev, float max_norm, float grad_scale,
+                     gp_stream_t stream);
+int gp_clip_scale_f32(float* g, long long n, const float* sumsq_dev, float max_norm, float pre_scale,
+                      gp_stream_t stream);
+int gp_multi_axpy_f32(const gp_axpy_entry* entries, int count, float alpha, gp_stream_t stream);
 int gp_mul_add_dev(const float* a, const float* b, const float* c, float* total, float* prod, gp_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------

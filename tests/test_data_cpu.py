@@ -26,7 +26,7 @@ def fixture_graphset():
 def test_batch_feed_matches_padded_arrays():
     x, adj, nb, label = load_enzymes()
     gs = fixture_graphset().to('cpu')
-    idx = np.array([5, 0, 17, 596, 300, 42])
+    idx = np.array([5, 0, 17, 596, 300, 42, 17, 5, 5])        # with repeats: sampling with replacement / oversampled folds
     bx, badj, bnb, bl = gs.batch(idx, 100, adj_dtype=torch.float32)
     assert np.array_equal(bx.numpy(), x[idx]) and np.array_equal(badj.numpy(), adj[idx])
     assert np.array_equal(bnb.numpy(), nb[idx]) and np.array_equal(bl.numpy(), label[idx])

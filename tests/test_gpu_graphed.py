@@ -73,3 +73,33 @@ def test_graphed_base_encoder_and_no_mask():
         opt.step()
         _, lgr = gs.step(xc, ac, None, lc)
         assert abs(lgr.item() - loss.item()) < 2e-5 * abs(loss.item())
+
+
+def test_second_shape_captured_mid_training_keeps_adam_state():
+    """A new batch shape first seen after some training steps (the smaller last batch of an epoch) is captured
+    then: its warm-up steps must not disturb the parameters, the Adam moments or the step count.  Steps
+    [full, full, full, small, full] against eager clip_grad_norm + Adam on the same batches."""
+    from graph_pooling_b200 import encoders, graphed
+    N, H, D, C = 48, 16, 5, 3
+    torch.manual_seed(5)
+    m0 = encoders.SoftPoolingGcnEncoder(N, D, H, H, C, 3, H, assign_ratio=0.25).cuda()
+    me, mg = copy.deepcopy(m0), copy.deepcopy(m0)
+    sizes = [6, 6, 6, 3, 6]
+    batches = [synth_batch(60 + i, b, N, D, 4, N, C, 0.1) for i, b in enumerate(sizes)]
+    opt = torch.optim.Adam(me.parameters(), lr=1e-3)
+    gs = graphed.GraphedTrainStep(mg, lr=1e-3, clip=2.0)
+    for x, adj, nb, label in batches:
+        xc, ac, lc = torch.tensor(x).cuda(), torch.tensor(adj).cuda(), torch.tensor(label).cuda()
+        me.zero_grad()
+        yp = me(xc, ac, nb, assign_x=xc)
+        loss = me.loss(yp, lc, ac, nb)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(me.parameters(), 2.0)
+        opt.step()
+        del yp
+        _, lg = gs.step(xc, ac, nb, lc)
+        assert abs(lg.item() - loss.item()) <= 1e-4 * abs(loss.item())
+        del loss
+    assert len(gs._graphs) == 2 and float(gs.optimizer.step_dev.item()) == float(len(sizes))
+    for (k, p), (_, q) in zip(mg.named_parameters(), me.named_parameters()):
+        assert rel_l2(p.detach().cpu().numpy(), q.detach().cpu().numpy()) < 1e-3, k

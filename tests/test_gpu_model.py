@@ -341,3 +341,43 @@ def test_forward_without_backward_does_not_leak():
         gc.collect()
         torch.cuda.synchronize()
         assert torch.cuda.memory_allocated() <= base + (1 << 20), (prec, torch.cuda.memory_allocated() - base)
+
+
+@pytest.mark.parametrize('hop,precision,nb_mode', [(2, 0, 'rand'), (3, 0, 'rand'), (2, 0, 'none'), (2, 1, 'rand')])
+def test_link_loss_adj_hop(hop, precision, nb_mode):
+    """loss(..., adj_hop > 1) (encoders.py:1312-1317, never passed by the reference's callers): the predicted adjacency
+    is sum_h (S S^T)^h clamped at 1 (R3) -- the clamp is ACTIVE here, unlike adj_hop = 1.  fp32 rule in fp32 mode; in
+    the tensor-core mode the encoder is bf16 and this loss branch runs on the fp32 schedule (bf16 bound)."""
+    N, D, H, C, B = 40, 5, 16, 3, 5
+    torch.manual_seed(20 + hop)
+    mo = orc.SoftPoolingGcnEncoder(N, D, H, H, C, 3, H, assign_ratio=0.25)
+    mc = enc().SoftPoolingGcnEncoder(N, D, H, H, C, 3, H, assign_ratio=0.25)
+    mc.load_state_dict(mo.state_dict(), strict=True)
+    mc = mc.cuda()
+    mc.precision = precision
+    x, adj, nb, label = synth_batch(21, B, N, D, 3, N, C, 0.15)
+    nbo = None if nb_mode == 'none' else nb
+    res = {}
+    for tag, dt in (('f32', torch.float32), ('f64', torch.float64)):
+        m = copy.deepcopy(mo).to(dt)
+        xt, at = torch.tensor(x, dtype=dt), torch.tensor(adj, dtype=dt)
+        yp = m(xt, at, nbo, assign_x=xt)
+        loss = m.loss(yp, torch.tensor(label), at, nbo, adj_hop=hop)
+        loss.backward()
+        res[tag] = (loss.item(), float(m.link_loss), {k: p.grad.numpy() for k, p in m.named_parameters()})
+    xc, ac, lc = torch.tensor(x).cuda(), torch.tensor(adj).cuda(), torch.tensor(label).cuda()
+    yp = mc(xc, ac, nbo, assign_x=xc)
+    loss = mc.loss(yp, lc, ac, nbo, adj_hop=hop)
+    loss.backward()
+    torch.cuda.synchronize()
+    l64, k64, g64 = res['f64']
+    cand = {k: p.grad.cpu().numpy() for k, p in mc.named_parameters()}
+    if precision == 0:
+        assert abs(loss.item() - l64) < OUT_TOL * max(1.0, abs(l64))
+        assert abs(mc.link_loss.item() - k64) < OUT_TOL * max(1.0, abs(k64))
+        grade_grads(cand, res['f32'][2], g64)
+    else:
+        assert abs(loss.item() - l64) < 5e-3 * abs(l64)
+        fc = np.concatenate([cand[k].ravel() for k in sorted(cand)]).astype(np.float64)
+        fo = np.concatenate([g64[k].ravel() for k in sorted(g64)])
+        assert rel_l2(fc, fo) < 0.1 and float(fc @ fo / (np.linalg.norm(fc) * np.linalg.norm(fo))) > 0.995
