@@ -137,30 +137,79 @@ def reference_arm(args, rank, world):
 
 
 def default_cpu_sample(cfg):
-    # ~10-30 s of CPU work in total: scale the per-step sample with the per-graph cost
+    # ~10-30 s of CPU work in total: scale the per-step sample with the per-graph cost; never fewer than 8 graphs
+    # (BatchNorm couples the graphs of a batch: a 2-graph sample is not the same computation per graph)
     cost = cfg['N'] * cfg['N'] * (cfg['H'] * 6 + int(cfg['N'] * cfg['ratio']) * 6)
-    return int(max(2, min(cfg['B'], 2e10 / max(cost, 1))))
+    return int(min(cfg['B'], max(8, 1.6e11 / max(cost, 1))))
+
+
+def time_oracle(workload, sample, steps, warmup, seed, device='cpu', with_optimizer=True):
+    """The oracle restatement of the reference (plain torch ops + autograd) on `device`: 'cpu' = the reference's CPU
+    path on the host cores; a CUDA device = the "ATen-on-B200" comparator (torch eager: cuBLAS / ATen kernels)."""
+    from graph_pooling_b200 import synth
+    from oracle import diffpool_oracle as orc
+    batch = synth.make_batch(workload, seed=seed, device=device, B=sample)
+    cfg = batch['cfg']
+    torch.manual_seed(seed)
+    model = synth.build_model(orc, cfg).to(device)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3) if with_optimizer else None
+    x, adj, nb, label = batch['x'], batch['adj'], batch['nb'], batch['label']
+    soft = cfg['kind'] == 'soft'
+    cuda = torch.device(device).type == 'cuda'
+    ts = []
+    for i in range(warmup + steps):
+        if cuda:
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        _, loss = orc.train_step(model, x, adj, label, nb, assign_x=x if soft else None, optimizer=opt)
+        if cuda:
+            float(loss.item())
+            torch.cuda.synchronize()
+        ts.append(time.perf_counter() - t0)
+    t = float(np.mean(ts[warmup:]))
+    desc = ('%d graphs/step of %s (same shapes), %d warm-up + %d timed steps, %s, torch %s %s fp32%s'
+            % (sample, workload, warmup, steps, 'zero_grad+fwd+loss+bwd+clip+Adam' if with_optimizer else
+               'zero_grad+fwd+loss+bwd only', torch.__version__,
+               'eager on the GPU (cuBLAS/ATen kernels)' if cuda else 'CPU',
+               '' if cuda else ', %d threads' % torch.get_num_threads()))
+    return sample / t, t * 1e3, desc
 
 
 def time_cpu_oracle(workload, sample, steps, warmup, seed):
-    from graph_pooling_b200 import synth
-    from oracle import diffpool_oracle as orc
-    batch = synth.make_batch(workload, seed=seed, device='cpu', B=sample)
+    return time_oracle(workload, sample, steps, warmup, seed, 'cpu', True)
+
+
+def enzymes_regime_point(dev, hbm, B=4096, reps=20):
+    """The small-graph half of BASELINE.json's metric inside the driver-run record: cfg1 (ENZYMES-like) shapes at
+    B = 4096 graphs, fp32 schedule, whole train step replayed from a CUDA graph, batch resident; algorithmic bytes
+    (roofline.step_bytes, fp32) / time against the measured HBM peak."""
+    from graph_pooling_b200 import encoders, graphed, roofline, synth
+    batch = synth.make_batch('cfg1_enzymes_like', seed=0, device=dev, B=B)
     cfg = batch['cfg']
-    torch.manual_seed(seed)
-    model = synth.build_model(orc, cfg)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
-    x, adj, nb, label = batch['x'], batch['adj'], batch['nb'], batch['label']
-    soft = cfg['kind'] == 'soft'
-    ts = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        orc.train_step(model, x, adj, label, nb, assign_x=x if soft else None, optimizer=opt)
-        ts.append(time.perf_counter() - t0)
-    t = float(np.mean(ts[warmup:]))
-    desc = ('%d graphs/step of %s (same shapes), %d warm-up + %d timed steps, torch %s CPU fp32, %d threads'
-            % (sample, workload, warmup, steps, torch.__version__, torch.get_num_threads()))
-    return sample / t, t * 1e3, desc
+    torch.manual_seed(0)
+    model = synth.build_model(encoders, cfg).to(dev)
+    model.precision = 0
+    gs = graphed.GraphedTrainStep(model, lr=1e-3, clip=2.0)
+    nbd = torch.from_numpy(np.ascontiguousarray(batch['nb'].astype(np.int32))).to(dev)
+    x, adj, label = batch['x'], batch['adj'], batch['label']
+    for _ in range(3):
+        gs.step(x, adj, nbd, label)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        gs.step(x, adj, nbd, label)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    gb = roofline.step_bytes(batch['nb'], cfg) / 1e9
+    st = next(iter(gs._graphs.values()))
+    return {'workload': 'cfg1_enzymes_like', 'graphs_per_step': B, 'precision': 'f32', 'cuda_graph': True,
+            'ms_per_step': ms, 'graphs_per_s': B / (ms * 1e-3), 'launches_per_step': st['launches'],
+            'algorithmic_gb_per_step': gb, 'achieved_gbs': gb / (ms * 1e-3), 'peak_gbs': hbm,
+            'frac_of_hbm_peak': gb / (ms * 1e-3) / hbm,
+            'note': 'bytes counted at fp32 over the real n_b x n_b blocks and real rows (SURVEY 8(d)); inputs resident, '
+                    'smaller than L2 per graph but %.0f MB per batch' % (adj.numel() * 4 / 1e6)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -427,8 +476,28 @@ def main():
         torch.cuda.synchronize()
         return e0.elapsed_time(e1)
 
-    # ---- roofline of the dominant kernel: the batched A.X contraction -------------------------
     hbm, tf_sus, tf_burst, src = peaks()
+    # ---- per-call table of ONE extra (untimed) step: every C-ABI call bracketed by CUDA events -----------------
+    from graph_pooling_b200 import profile as gprof
+    FFMA_TF = 148 * 128 * 2 * 1.965e9 / 1e12            # fp32 FMA peak of the SIMT pipe (fp32 schedule's compute roof)
+    kernels_tab, prof_ms = None, None
+    try:
+        with gprof.CallProfiler() as cp:
+            if gstep is not None:
+                gstep._eager(next(iter(gstep._graphs.values())))
+            else:
+                step(x, adj, label)
+        rows_, prof_ms = cp.table(hbm, tf_burst if prec == 'bf16' else FFMA_TF)
+        kernels_tab = [{k: (round(v, 6) if isinstance(v, float) else v) for k, v in r.items()
+                        if k in ('entry', 'shape', 'launches', 'ms', 'ms_per_launch', 'share', 'bound', 'achieved',
+                                 'peak', 'unit', 'frac', 'flops', 'bytes', 'counted_at')} for r in rows_]
+        for r in kernels_tab:
+            if r.get('bound') == 'tensor' and prec != 'bf16':
+                r['bound'] = 'ffma'
+    except Exception as ex:                    # the table is diagnostic: it must never cost the bench line
+        kernels_tab = [{'error': str(ex)[:200]}]
+
+    # ---- the dominant kernel timed alone: the batched A.X contraction -------------------------
     H = cfg['H']
     xin = torch.randn(B, cfg['N'], H, device=dev)
     u = torch.empty(B, cfg['N'], H, device=dev)
@@ -514,13 +583,23 @@ def main():
         roof = {'bound': 'hbm', 'achieved': kby / (kms_dom * 1e-3) / 1e9, 'peak': hbm, 'unit': 'GB/s'}
     roof['frac'] = roof['achieved'] / roof['peak']
     traffic = None
-    tpath = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
+    # ncu --set full captures of this shape (profiles/): valid only for the kernel source they were taken on --
+    # the file records the sha256 of csrc/gemm_tc2.cu at capture time; a different source => traffic is null
+    tpath = os.path.join(ROOT, 'profiles', 'r2_traffic.json')
+    if not os.path.exists(tpath):
+        tpath = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
     tj = json.load(open(tpath)) if os.path.exists(tpath) else {}
+    import hashlib
+    ksrc = os.path.join(ROOT, 'graph_pooling_b200', 'csrc', 'gemm_tc2.cu')
+    ksha = hashlib.sha256(open(ksrc, 'rb').read()).hexdigest()[:16] if os.path.exists(ksrc) else None
+    same_rev = tj.get('kernel_source_sha256_16') == ksha
     tkey = 'ax2_gemm' if dual else 'ax_gemm'
-    if prec == 'bf16' and args.workload == 'cfg4_diffpool_256x2048' and B == 256 and tkey in tj:
+    if prec == 'bf16' and args.workload == 'cfg4_diffpool_256x2048' and B == 256 and tkey in tj and same_rev:
         traffic = tj[tkey]['dram_bytes_per_launch']               # ncu --set full, same shape (profiles/)
         roof['ncu_tensor_pipe_active_pct'] = tj[tkey].get('tensor_pipe_active_pct')
     roof['traffic'] = traffic
+    roof['traffic_source'] = (os.path.basename(tpath) + (' (same kernel source)' if same_rev else
+                                                         ' is from another revision of the kernel: not reported'))
     roof['algorithmic_bytes_per_launch'] = kby
     roof['algorithmic_flops_per_launch'] = kfl
     roof['arithmetic_intensity_flop_per_byte'] = ai
@@ -564,18 +643,56 @@ def main():
             'kernel': 'gp::v2::tc_gemm2_kernel<256,4,0,8> (T = S^T.A, K=%d, N=%d, batch=%d)' % (K0, N, B),
             'bound': 'tensor', 'achieved': tfl / (tms * 1e-3) / 1e12, 'peak': tf_burst, 'unit': 'TFLOP/s',
             'frac': tfl / (tms * 1e-3) / 1e12 / tf_burst, 'ms_per_launch': tms,
-            'traffic': tj.get('tsa_gemm', {}).get('dram_bytes_per_launch') if (B == 256 and N == 2048) else None,
+            'traffic': tj.get('tsa_gemm', {}).get('dram_bytes_per_launch') if (B == 256 and N == 2048 and same_rev) else None,
             'ncu_tensor_pipe_active_pct': tj.get('tsa_gemm', {}).get('tensor_pipe_active_pct')}
         del sprob, tbuf
 
-    # ---- CPU baseline (oracle port) on this box's host cores -----------------------------------
+    # ---- the step against ITS roof (top-level `roofline`); the kernel timed alone above is `dominant_kernel` ------
+    if prec == 'bf16':        # model AI >> ridge: the step is tensor-bound; sustained peak (kernels inside a long step)
+        step_roof = {'bound': 'tensor', 'achieved': roof['step_tflops'], 'peak': tf_sus, 'unit': 'TFLOP/s',
+                     'frac': roof['step_tflops'] / tf_sus,
+                     'what': 'whole train step: algorithmic TFLOP (roofline.py: real n_b blocks, reference association, '
+                             'fwd+bwd) / device time, against the SUSTAINED bf16 peak'}
+    else:                     # ENZYMES / DD-base sized work: HBM-bound (AI ~ 35 flop/B); bytes counted at fp32
+        step_roof = {'bound': 'hbm', 'achieved': roof['step_gbs'], 'peak': hbm, 'unit': 'GB/s',
+                     'frac': roof['step_gbs'] / hbm,
+                     'what': 'whole train step: compulsory bytes (roofline.py, fp32: adjacency read fwd + bwd, saved '
+                             'activations written once and read once) / device time'}
+    step_roof['traffic'] = None
+    step_roof['traffic_note'] = 'step level; the ncu dram bytes of the dominant launch are under dominant_kernel.traffic'
+    step_roof['peak_source'] = src + ' (MEASURED_PEAKS.json)'
+    step_roof['kernels'] = kernels_tab
+    step_roof['kernels_note'] = ('one extra untimed step, every C-ABI call bracketed by CUDA events (profile.py); rows = '
+                                 '(entry point, shape) groups with >= 3 %% of the %.3f ms of calls; flops / bytes are '
+                                 'algorithmic (dense extents) at the dtype each call reads and writes'
+                                 % (prof_ms if prof_ms else 0.0))
+    step_roof['dominant_kernel'] = roof
+
+    # ---- comparators ------------------------------------------------------------------------------
     cpu = None
+    aten = None
     if not args.no_cpu_baseline and world == 1:       # rank 0 at N = 1 only (other ranks would contend for the cores)
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
         sample = args.cpu_sample or default_cpu_sample(cfg)
-        v, cms, desc = time_cpu_oracle(args.workload, sample, 2, 1, args.seed)
+        v, cms, desc = time_oracle(args.workload, sample, 2, 1, args.seed, 'cpu', True)
         cpu = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': desc, 'ms_per_step': cms}
+        v2, cms2, desc2 = time_oracle(args.workload, sample, 2, 1, args.seed, 'cpu', False)
+        cpu['fwd_bwd_only'] = {'value': v2, 'ms_per_step': cms2, 'sample': desc2}
+        try:                  # the same oracle in torch eager ON THE B200 (cuBLAS / ATen kernels): "ATen-on-B200"
+            del xin, u
+            torch.cuda.empty_cache()
+            gs_ = int(min(B, 32 if cfg['N'] >= 1024 else 4096))
+            v3, ams, desc3 = time_oracle(args.workload, gs_, 3, 2, args.seed, dev, True)
+            aten = {'value': v3, 'unit': UNIT, 'ms_per_step': ams, 'sample': desc3}
+        except Exception as ex:
+            aten = {'error': str(ex)[:200]}
+    enz = None
+    if world == 1 and args.workload == 'cfg4_diffpool_256x2048' and not os.environ.get('GP_BENCH_NO_ENZ'):
+        try:
+            enz = enzymes_regime_point(dev, hbm)
+        except Exception as ex:
+            enz = {'error': str(ex)[:200]}
 
     out = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
            'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
@@ -589,8 +706,8 @@ def main():
                       if adj.numel() * 4 > 126e6 else 'inputs smaller than L2; not flushed',
                       'cuda_graph': bool(use_graph),
                       'parallelism': 'dp%d' % world},
-           'clocks': clocks, 'e2e': e2e, 'e2e_u8_feed': e2e_u8, 'gpu_launches': launches, 'roofline': roof, 'cpu_baseline': cpu,
-           'dp_check': dp_check}
+           'clocks': clocks, 'e2e': e2e, 'e2e_u8_feed': e2e_u8, 'gpu_launches': launches, 'roofline': step_roof,
+           'cpu_baseline': cpu, 'aten_on_b200': aten, 'enzymes_regime': enz, 'dp_check': dp_check}
     print(json.dumps(out), flush=True)
 
 

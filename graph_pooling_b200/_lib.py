@@ -169,5 +169,18 @@ def check(status, what):
         raise GpError('%s failed (%d): %s' % (what, status, load().gp_last_error().decode()))
 
 
+_hook = None     # profile.CallProfiler while a profiled step runs (bench.py); None on the product path
+
+
+def set_hook(h):
+    global _hook
+    _hook = h
+
+
 def call(name, *args):
+    if _hook is None:
+        check(getattr(load(), name)(*args), name)
+        return
+    tok = _hook.begin(name, args)
     check(getattr(load(), name)(*args), name)
+    _hook.end(tok)

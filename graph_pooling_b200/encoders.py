@@ -208,7 +208,7 @@ def _bwd_tc(ctx, tape, dypred, dS0):
                                                dza.data_ptr(), lv['Fa'])
                 put(plan.emb, gE)
                 put(plan.assign[0], gA)
-                return (None, None, None, None) + tuple(_deliver(plan, params, grads))
+                return (None, None, None, None, None) + tuple(_deliver(plan, params, grads))
             gl, dxa = T.stack_backward(ws, lv['c_as'], dza.data_ptr(), lv['Fa'], None, None, 0, i > 0,
                                        None if i == 0 else d_ap[i - 1])
             put(plan.assign[i], gl)
@@ -219,19 +219,39 @@ def _bwd_tc(ctx, tape, dypred, dS0):
     gl, _ = T.stack_backward(ws, tape['emb'], None if dz_dense is None else dz_dense.data_ptr(), Fw, dout_p, arg_p,
                              ldo, False, None)
     put(plan.emb, gl)
-    return (None, None, None, None) + tuple(_deliver(plan, params, grads))
+    return (None, None, None, None, None) + tuple(_deliver(plan, params, grads))
 
 
 def _deliver(plan, params, grads):
-    """Hand the parameter gradients of a backward pass to autograd -- or, when a dp.FlatGradients buffer is attached
-    to the model (`model._grad_sink`), add them into it with one gp_multi_axpy_f32 launch and return None for them."""
-    sink = getattr(plan, 'grad_sink', None)
-    return grads if sink is None else sink.accumulate(params, grads)
+    """Hand the parameter gradients of a backward pass to autograd -- or, in sink mode (_apply_encoder), add them
+    into the attached dp.FlatGradients buffer with one gp_multi_axpy_f32 launch; autograd then sees no parameter at all."""
+    real = getattr(plan, 'sink_params', None)
+    if real is None:
+        return grads
+    left = plan.grad_sink.accumulate(real, grads)
+    for p, g in zip(real, left):               # a parameter outside the buffer (not expected): plain accumulation
+        if g is not None:
+            p.grad = g if p.grad is None else p.grad + g
+    return [None] * len(grads)
+
+
+def _apply_encoder(plan, x, adj, x_a, params):
+    """_EncoderFn.apply.  With a gradient sink attached (dp.FlatGradients.attach) the parameters enter the autograd
+    node DETACHED and a fresh empty `anchor` tensor carries requires_grad instead: the backward then delivers the
+    parameter gradients itself (one launch) and autograd runs no AccumulateGrad node for them -- an AccumulateGrad
+    node that receives an undefined gradient would still register its own (creation-time) stream for the engine's
+    final synchronisation, which breaks CUDA-graph capture of the step."""
+    if plan.grad_sink is not None and torch.is_grad_enabled() and any(p.requires_grad for p in params):
+        plan.sink_params = list(params)
+        anchor = torch.empty(0, device=x.device, requires_grad=True)
+        return _EncoderFn.apply(plan, x, adj, x_a, anchor, *[p.detach() for p in params])
+    plan.sink_params = None
+    return _EncoderFn.apply(plan, x, adj, x_a, None, *params)
 
 
 class _EncoderFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, plan, x, adj, assign_x, *params):
+    def forward(ctx, plan, x, adj, assign_x, anchor, *params):
         ctx.set_materialize_grads(False)
         if plan.precision == T.BF16:
             return _fwd_tc(ctx, plan, x, adj, assign_x, params)
@@ -379,7 +399,7 @@ class _EncoderFn(torch.autograd.Function):
         gl, _ = E.stack_backward(ws, tape['emb'], None if dz_dense is None else dz_dense.data_ptr(), Fw, dout_p,
                                  arg_p, ldo, False, None, prec)
         put(plan.emb, gl)
-        return (None, None, None, None) + tuple(_deliver(plan, params, grads))
+        return (None, None, None, None, None) + tuple(_deliver(plan, params, grads))
 
 
 class _LossFn(torch.autograd.Function):
@@ -829,7 +849,7 @@ class GcnEncoderGraph(nn.Module):
         plan.num_pooling = 0
         plan.pred = self._pred_pairs(params, self.pred_model)
         self._plan = plan
-        return _EncoderFn.apply(plan, x, adj, None, *params)
+        return _apply_encoder(plan, x, adj, None, params)
 
     def loss(self, pred, label, type='softmax'):
         if type != 'softmax':
@@ -1128,7 +1148,7 @@ class SoftPoolingGcnEncoder(GcnEncoderGraph):
         if any(any(d) for d in plan.post_drop) and not plan.seed:
             plan.seed = _draw_seed()
         self._plan = plan
-        ypred, S0 = _EncoderFn.apply(plan, x, adj, x_a, *params)
+        ypred, S0 = _apply_encoder(plan, x, adj, x_a, params)
         self.assign_tensors = [S0] + plan.all_S[1:]
         self.assign_tensor = plan.all_S[-1] if self.num_pooling > 1 else S0   # last level's S (:1269,1273)
         self._S0 = S0

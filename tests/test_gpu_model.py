@@ -41,14 +41,16 @@ def run_candidate(m, x, adj, nb, label, soft, assign_x=None, linkpred=True):
     return yp, loss
 
 
-def grade_grads(cand, g32, g64):
-    """cand/g32/g64: dict name -> numpy grad."""
+def grade_grads(cand, g32, g64, floor=1e-7):
+    """cand/g32/g64: dict name -> numpy grad.  Per parameter: error <= max(1e-5, 4 x the fp32 oracle's own error)
+    relative to that parameter's gradient, plus `floor` x the largest parameter gradient (cancellation-dominated
+    gradients -- a bias behind an L2 normalise -- are tiny sums of large terms)."""
     G = max(np.linalg.norm(v) for v in g64.values())
     for k in g64:
         scale = max(np.linalg.norm(g64[k]), 1e-30)
         a_c = np.linalg.norm(cand[k].astype(np.float64) - g64[k])
         e_o = np.linalg.norm(g32[k].astype(np.float64) - g64[k]) / scale
-        assert a_c <= max(1e-5, 4 * e_o) * scale + 1e-7 * G, \
+        assert a_c <= max(1e-5, 4 * e_o) * scale + floor * G, \
             '%s: cand err %.3g, fp32-oracle err %.3g' % (k, a_c / scale, e_o)
 
 
@@ -355,7 +357,7 @@ def test_link_loss_adj_hop(hop, precision, nb_mode):
     mc.load_state_dict(mo.state_dict(), strict=True)
     mc = mc.cuda()
     mc.precision = precision
-    x, adj, nb, label = synth_batch(21, B, N, D, 3, N, C, 0.15)
+    x, adj, nb, label = synth_batch(21, B, N, D, N if nb_mode == 'none' else 3, N, C, 0.15)
     nbo = None if nb_mode == 'none' else nb
     res = {}
     for tag, dt in (('f32', torch.float32), ('f64', torch.float64)):
