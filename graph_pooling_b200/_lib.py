@@ -65,6 +65,57 @@ class GpLayerBwd(C.Structure):
                 ('nb_zero', c_f)]
 
 
+# ---- packed small-graph schedule (include/gp_b200.h "PACKED schedule") ---------------------------------------------
+PK_MAX_LAYERS = 6
+
+
+class GpPkTiling(C.Structure):
+    _fields_ = [('rowptr', c_f), ('tile_g0', c_f), ('ntiles', c_f), ('B', c_i), ('nfix', c_i), ('gpt', c_i),
+                ('max_rows', c_i)]
+
+
+class GpPkAdj(C.Structure):
+    _fields_ = [('info', c_f), ('entries', c_f), ('dense', c_f), ('transposed', c_i)]
+
+
+class GpPkSrc(C.Structure):
+    _fields_ = [('y', c_f), ('ld', c_ll), ('d', c_i), ('padded', c_i), ('sums', c_f), ('bias', c_f)]
+
+
+class GpPkGrad(C.Structure):
+    _fields_ = [('dense', c_f), ('ld', c_ll), ('coff', c_i), ('dout', c_f), ('arg', c_f), ('ldo', c_ll), ('ooff', c_i)]
+
+
+class GpPkStackFwd(C.Structure):
+    _fields_ = [('inp', GpPkSrc), ('W', c_f), ('b', c_f), ('dout', c_i), ('y', c_f), ('rnorm', c_f), ('sums_out', c_f)]
+
+
+class GpPkLayerFwdArgs(C.Structure):
+    _fields_ = [('tl', GpPkTiling), ('adj', GpPkAdj), ('cnt_pad', c_f), ('N', c_i), ('ns', c_i), ('s', GpPkStackFwd * 2)]
+
+
+class GpPkStackBwd(C.Structure):
+    _fields_ = [('inp', GpPkSrc), ('out', GpPkSrc), ('rnorm', c_f), ('msums', c_f), ('gl', GpPkGrad),
+                ('W', c_f), ('b', c_f), ('dout', c_i), ('dW', c_f), ('db', c_f), ('need_dx', c_i),
+                ('gz_prev', GpPkGrad), ('gl_prev', c_f), ('msums_prev', c_f), ('dadj', c_f), ('dadj_acc', c_i)]
+
+
+class GpPkLayerBwdArgs(C.Structure):
+    _fields_ = [('tl', GpPkTiling), ('adj', GpPkAdj), ('adj_in', GpPkAdj), ('cnt_pad', c_f), ('N', c_i), ('ns', c_i),
+                ('s', GpPkStackBwd * 2)]
+
+
+class GpPkConcat(C.Structure):
+    _fields_ = [('L', c_i), ('F', c_i), ('slot', GpPkSrc * PK_MAX_LAYERS)]
+
+
+class GpPkPoolArgs(C.Structure):
+    _fields_ = [('tl', GpPkTiling), ('adj', GpPkAdj), ('adj_in', GpPkAdj), ('cnt_pad', c_f), ('nb', c_f), ('N', c_i),
+                ('K', c_i), ('z', GpPkConcat), ('za', GpPkConcat), ('Wp', c_f), ('bp', c_f), ('S', c_f), ('xp', c_f),
+                ('ap', c_f), ('out', c_f), ('arg', c_f), ('ldo', c_ll), ('dxp', c_f), ('dap', c_f), ('dS_ext', c_f),
+                ('dout', c_f), ('gz', c_f), ('gza', c_f), ('dWp', c_f), ('dbp', c_f)]
+
+
 # name -> argtypes (restype is int unless listed in _RESTYPES)
 _PROTOS = {
     'gp_bgemm_bf16x': [C.POINTER(GpGemmBf16x), c_f],
@@ -135,6 +186,16 @@ _PROTOS = {
     'gp_dropout_f32': [c_f, c_ll, c_ll, c_i, C.c_float, C.c_ulonglong, c_f, c_ll, c_f, c_ll, c_f],
     'gp_set2set_fwd': [c_f, c_ll, c_f, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f],
     'gp_set2set_bwd': [c_f, c_ll, c_f, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_f, c_f, c_ll, c_f, c_f, c_f, c_f],
+    'gp_pk_prepare': [c_f, c_i, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_f, c_f],
+    'gp_pk_build_lists': [c_f, c_f, c_f, c_i, c_i, c_f, c_f, c_f, c_f, c_f, c_ll, c_f],
+    'gp_pk_layer_fwd': [C.POINTER(GpPkLayerFwdArgs), c_f],
+    'gp_pk_layer_bwd': [C.POINTER(GpPkLayerBwdArgs), c_f],
+    'gp_pk_pool_fwd': [C.POINTER(GpPkPoolArgs), c_f],
+    'gp_pk_pool_bwd': [C.POINTER(GpPkPoolArgs), c_f],
+    'gp_pk_readout': [C.POINTER(GpPkTiling), C.POINTER(GpPkConcat), c_f, c_f, c_i, c_f, c_f, c_ll, c_i, c_f],
+    'gp_pk_link_fwd': [c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f],
+    'gp_pk_link_bwd': [c_f, c_f, c_f, c_i, c_i, c_i, C.c_float, c_f, c_f, c_f, c_f],
+    'gp_pk_link_finalize': [c_f, C.c_double, c_f, c_f, c_f, c_f, c_f],
     'gp_pad_copy_f32': [c_f, c_ll, c_ll, c_i, c_f, c_ll, c_ll, c_i, C.c_float, c_f],
 }
 _RESTYPES = {'gp_last_error': C.c_char_p, 'gp_launch_count': c_ll, 'gp_gcn_layer_bwd_ws': c_ll, 'gp_gcn_layer_bwd_ws_x': c_ll, 'gp_relu_bn_fwd_ws': c_ll, 'gp_graphconv_bwd_ws': c_ll, 'gp_launch_count_reset': None}

@@ -18,6 +18,7 @@ import torch.nn as nn
 from torch.autograd.function import once_differentiable
 
 from . import engine as E
+from . import engine_pk as PK
 from . import engine_tc as T
 from ._lib import call
 
@@ -255,6 +256,12 @@ class _EncoderFn(torch.autograd.Function):
         ctx.set_materialize_grads(False)
         if plan.precision == T.BF16:
             return _fwd_tc(ctx, plan, x, adj, assign_x, params)
+        if getattr(plan, 'packed', False):            # ENZYMES-sized graphs: packed rows, one launch per phase
+            ypred, S0, tape = PK.forward(plan, x, adj, assign_x, params, _wb)
+            tape.update(plan=plan, params=params, packed=True)
+            ctx.tape = tape
+            plan.all_S = [S0.detach()]
+            return ypred, S0
         st = E._stream()
         ws = E.Workspace(x.device)
         B, N, D = x.shape
@@ -327,6 +334,9 @@ class _EncoderFn(torch.autograd.Function):
         if tape['plan'].precision == T.BF16:
             return _bwd_tc(ctx, tape, dypred, dS0)
         plan, params = tape['plan'], tape['params']
+        if tape.get('packed'):
+            grads = PK.backward(plan, tape, params, dypred, dS0)
+            return (None, None, None, None, None) + tuple(_deliver(plan, params, grads))
         B, N = tape['B'], tape['N']
         st = E._stream()
         ws = E.Workspace(tape['x'].device)
@@ -441,7 +451,17 @@ class _LossFn(torch.autograd.Function):
         if link_kind is not None:
             frob = link_kind == 'frobenius'
             total, link = ws.f(1), ws.f(1)
-            if ctx.sb is not None:                      # GP_BF16: P = S S^T on tensor cores, loss in the epilogue
+            ctx.pk = None
+            if getattr(plan, 'packed', False) and not frob and ctx.sb is None:
+                # packed schedule: the real n_b x n_b blocks only, P and dl/dP never leave shared memory
+                if getattr(plan, 'inv_dev', None) is not None:
+                    inv, inv_dev = 1.0, plan.inv_dev
+                else:
+                    inv, inv_dev = 1.0 / float(plan.num_entries), None
+                total, link = PK.link_forward(ws, S, adj, plan.nb_dev, inv, inv_dev, ce)
+                ctx.pk = (adj, inv, inv_dev) if need_grad else None
+                npart = 0
+            elif ctx.sb is not None:                    # GP_BF16: P = S S^T on tensor cores, loss in the epilogue
                 partial, npart, gsym = T.linkloss_forward(ws, ctx.sb, plan.adjb, plan.nb_dev, Bn, N, K, need_grad,
                                                           mode=int(frob), adj_flags=getattr(plan, 'adj_flags', None))
             else:
@@ -451,7 +471,9 @@ class _LossFn(torch.autograd.Function):
                 gsym = ws.f(Bn, N, N) if need_grad else None
                 call('gp_frob_link_fwd' if frob else 'gp_linkloss_fwd', S.data_ptr(), adj.data_ptr(),
                      E._p(plan.nb_dev), Bn, N, K, partial.data_ptr(), E._p(gsym), st)
-            if frob:
+            if npart == 0:
+                gsym = None
+            elif frob:
                 ctx.coef = ws.f(Bn)
                 call('gp_frob_finalize', partial.data_ptr(), npart // Bn, Bn, ce.data_ptr(), total.data_ptr(),
                      link.data_ptr(), ws.f(Bn).data_ptr(), ctx.coef.data_ptr(), st)
@@ -495,6 +517,10 @@ class _LossFn(torch.autograd.Function):
         if ctx.ce_scale != 1.0:
             call('gp_axpy_f32', dy.data_ptr(), dy.data_ptr(), C.c_longlong(dy.numel()), C.c_float(ctx.ce_scale - 1.0), st)
         dS = None
+        if ctx.link_kind is not None and getattr(ctx, 'pk', None) is not None:
+            adj_, inv_, inv_dev_ = ctx.pk
+            dS = PK.link_backward(ws, ctx.S, adj_, ctx.nb, inv_, inv_dev_, g)
+            ctx.pk = None
         if ctx.link_kind is not None and ctx.gsym is not None:
             S = ctx.S
             Bn, N, K = S.shape
@@ -1147,6 +1173,7 @@ class SoftPoolingGcnEncoder(GcnEncoderGraph):
         plan.pred = self._pred_pairs(params, self.pred_model)
         if any(any(d) for d in plan.post_drop) and not plan.seed:
             plan.seed = _draw_seed()
+        plan.packed = PK.supported(plan, x, adj, x_a, params)
         self._plan = plan
         ypred, S0 = _apply_encoder(plan, x, adj, x_a, params)
         self.assign_tensors = [S0] + plan.all_S[1:]
@@ -1175,6 +1202,7 @@ class SoftPoolingGcnEncoder(GcnEncoderGraph):
         lp.ce_scale = self._ce_scale
         lp.ent_w = ent_w
         lp.link_kind = self.link_loss_kind if self.linkpred else None
+        lp.packed = bool(getattr(plan, 'packed', False)) and torch.is_tensor(adj) and adj.dtype == torch.float32
         N0 = S0.shape[1]
         if batch_num_nodes is None and adj is None:
             lp.nb_dev, nb_host = plan.nb_dev, plan.nb_host                   # 2-argument call: the forward's n_b

@@ -434,6 +434,121 @@ int gp_dropout_f32(const float* x, long long ldx, long long rows, int d, float p
 int gp_pad_copy_f32(const float* src, long long ld_src, long long rows, int cols, float* dst, long long ld_dst,
                     long long rows_dst, int cols_dst, float fill, gp_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * PACKED schedule for ENZYMES-sized graphs (N <= 128; SURVEY 8(d) small-graph regime, encoders.py:1054-1081,
+ * 1231-1300 with num_pooling == 1).  Only the real n_b rows of every graph exist ("packed rows": graph g owns
+ * rows rowptr[g] .. rowptr[g+1]); a pad row of a layer is the one vector normalize(bias) and enters the BatchNorm
+ * statistics and the bias gradient analytically through cnt_pad[n] = #graphs with n_b <= n
+ * (tests/test_pad_row_math_cpu.py, tests/packed_blueprint.py).  The level-0 adjacency is read ONCE per step and
+ * kept as per-row neighbour lists (out: A row i, in: A column i), the pooled level keeps its dense [K,K] A'.
+ * A launch = one phase for ALL graphs; CTAs walk "tiles" (groups of whole graphs, ~64 packed rows) so that every
+ * graph-structured product (A.H, S^T Z, S^T A S, A^T dU) is local to a CTA's shared memory and the dense products
+ * (U.W, dV.W^T, U^T dV) run over all rows of the tile at once.  The only cross-graph coupling, BatchNorm per node
+ * index (encoders.py:1048-1052), is a sum per node index that a phase accumulates and the next phase consumes:
+ * the launch boundary is the grid-wide dependency.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct gp_pk_tiling {
+  const int32_t* rowptr;   /* [B+1] first packed row of each graph; NULL: every graph has `nfix` rows */
+  const int32_t* tile_g0;  /* [ntiles+1] first graph of each tile; NULL: `gpt` graphs per tile */
+  const int32_t* ntiles;   /* device scalar; NULL: ceil(B / gpt) */
+  int B, nfix, gpt, max_rows;   /* max_rows: upper bound of the rows of one tile (sizes the shared memory) */
+} gp_pk_tiling;
+
+typedef struct gp_pk_adj {
+  const int32_t* info;     /* [R][2] {first entry, degree} of every packed row; NULL: dense */
+  const int32_t* entries;  /* [nnz][2] {node index within the graph, value as float bits} */
+  const float* dense;      /* [B, nfix, nfix] when info == NULL */
+  int transposed;          /* dense only: row i of the operator is column i of `dense` */
+} gp_pk_adj;
+
+/* rows of one layer's normalised output Y (or of the caller's input) and the ReLU + BatchNorm applied on read */
+typedef struct gp_pk_src {
+  const float* y; long long ld; int d;
+  int padded;              /* 1: the caller's [B, N, d] tensor, row (g, i) at y + (g*N + i)*ld; 0: packed rows */
+  const double* sums;      /* [2N] sum relu(y), sum relu(y)^2 per node index over the REAL rows; NULL: rows as they are */
+  const float* bias;       /* bias of the producing layer (its pad rows are normalize(bias)); NULL: zero pad rows */
+} gp_pk_src;
+
+/* upstream gradient of a layer's output: dense packed rows and/or the max-readout scatter */
+typedef struct gp_pk_grad {
+  const float* dense; long long ld; int coff;     /* dense[r*ld + coff + c]; NULL: none */
+  const float* dout; const int32_t* arg; long long ldo; int ooff;
+                           /* dout[g*ldo + ooff + c] lands on node arg[g*ldo + ooff + c] of graph g; NULL: none */
+} gp_pk_grad;
+
+typedef struct gp_pk_stack_fwd {
+  gp_pk_src in;
+  const float* W; const float* b; int dout;     /* W [din, dout] row-major (GraphConv.weight), b [dout] or NULL */
+  float* y; float* rnorm;                       /* [R, dout], [R]: Y = V / max(||V||, 1e-12), the clamped norm */
+  double* sums_out;                             /* [2N] accumulated (zero on entry); NULL: last layer of the stack */
+} gp_pk_stack_fwd;
+typedef struct gp_pk_layer_fwd_args {
+  gp_pk_tiling tl; gp_pk_adj adj; const float* cnt_pad; int N; int ns; gp_pk_stack_fwd s[2];
+} gp_pk_layer_fwd_args;
+
+typedef struct gp_pk_stack_bwd {
+  gp_pk_src in;            /* the layer's input, as in the forward */
+  gp_pk_src out;           /* this layer's Y with ITS BatchNorm sums (sums NULL: last layer) */
+  const float* rnorm;
+  const double* msums;     /* [2N] sum gl, sum gl*H of this layer over the real rows (NULL with the last layer) */
+  gp_pk_grad gl;           /* upstream gradient of this layer's output */
+  const float* W; const float* b; int dout;
+  float* dW; float* db;    /* [din, dout], [dout]: ACCUMULATED with atomics (zero on entry); db may be NULL */
+  int need_dx;             /* gl_prev = gz_prev + A^T (dV W^T) */
+  gp_pk_grad gz_prev; float* gl_prev;           /* [R, din] */
+  double* msums_prev;      /* [2N] accumulated sum gl_prev, sum gl_prev*Hin; NULL: the input has no BatchNorm */
+  float* dadj; int dadj_acc;                    /* dense level only: dA[g] (+)= dU Hin^T, [B, nfix, nfix] */
+} gp_pk_stack_bwd;
+typedef struct gp_pk_layer_bwd_args {
+  gp_pk_tiling tl; gp_pk_adj adj; gp_pk_adj adj_in; const float* cnt_pad; int N; int ns; gp_pk_stack_bwd s[2];
+} gp_pk_layer_bwd_args;
+
+#define GP_PK_MAX_LAYERS 6
+typedef struct gp_pk_concat { int L; int F; gp_pk_src slot[GP_PK_MAX_LAYERS]; } gp_pk_concat;
+
+typedef struct gp_pk_pool_args {
+  gp_pk_tiling tl; gp_pk_adj adj; gp_pk_adj adj_in; const float* cnt_pad; const int32_t* nb; int N; int K;
+  gp_pk_concat z, za;                       /* embedding / assignment concat (encoders.py:1078) */
+  const float* Wp; const float* bp;         /* assign_pred: Linear [K, Fa], [K] or NULL (encoders.py:1272) */
+  float* S;                                 /* [B, N, K] dense, pad rows zero (encoders.py:1273-1275) */
+  float* xp; float* ap;                     /* X' = S^T Z [B,K,F], A' = S^T A S [B,K,K] (encoders.py:1278-1279) */
+  float* out; int32_t* arg; long long ldo;  /* level-0 max readout (encoders.py:1257): [B, ldo], first F columns */
+  /* backward only */
+  const float* dxp; const float* dap;       /* [B,K,F], [B,K,K] */
+  const float* dS_ext;                      /* [B,N,K] gradient of S from the losses, or NULL */
+  const float* dout;                        /* [B, ldo] gradient of the readout */
+  float* gz; float* gza;                    /* [R, F], [R, Fa]: gradients of the two concats */
+  float* dWp; float* dbp;                   /* accumulated with atomics (zero on entry) */
+} gp_pk_pool_args;
+
+/* nb [B] -> rowptr [B+1], cnt_pad [N], two tilings (window `w_layer` / `w_pool` packed rows: tile t holds the graphs
+ * whose first row lies in [t*w, (t+1)*w), at most w - 1 + N rows), meta = {R, ntiles_layer, ntiles_pool, 0 (list
+ * cursor)}.  nb == NULL: every graph has N nodes.  tiles_*: [ceil(B*N / w) + 2] ints. */
+int gp_pk_prepare(const int32_t* nb, int B, int N, int w_layer, int w_pool, int32_t* rowptr, float* cnt_pad,
+                  int32_t* tiles_layer, int32_t* tiles_pool, int32_t* meta, gp_stream_t stream);
+/* dense fp32 adjacency [B,N,N] -> neighbour lists of the n_b x n_b blocks (out: rows, in: columns); `cursor` is a
+ * zeroed device int (bump allocator), `capacity` entries per list */
+int gp_pk_build_lists(const float* adj, const int32_t* nb, const int32_t* rowptr, int B, int N, int32_t* info_out,
+                      int32_t* ent_out, int32_t* info_in, int32_t* ent_in, int32_t* cursor, long long capacity,
+                      gp_stream_t stream);
+int gp_pk_layer_fwd(const gp_pk_layer_fwd_args* a, gp_stream_t stream);
+int gp_pk_layer_bwd(const gp_pk_layer_bwd_args* a, gp_stream_t stream);
+int gp_pk_pool_fwd(const gp_pk_pool_args* a, gp_stream_t stream);
+int gp_pk_pool_bwd(const gp_pk_pool_args* a, gp_stream_t stream);
+/* max readout of a packed concat over each graph's rows (pooled level: encoders.py:1287) */
+int gp_pk_readout(const gp_pk_tiling* tl, const gp_pk_concat* z, const float* cnt_pad, const int32_t* nb, int N,
+                  float* out, int32_t* arg, long long ldo, int ooff, gp_stream_t stream);
+/* link-prediction loss over the real n_b x n_b blocks without materialising P or dl/dP (encoders.py:1311-1331):
+ * fwd adds sum -[a log(P+eps) + (1-a) log(1-P+eps)] into the zeroed double *sum; bwd writes
+ * dS = alpha * alpha_dev[0] * alpha_dev2[0] * (G + G^T) S (device scalars optional), pad rows zero */
+int gp_pk_link_fwd(const float* S, const float* adj, const int32_t* nb, int B, int N, int K, double* sum,
+                   gp_stream_t stream);
+int gp_pk_link_bwd(const float* S, const float* adj, const int32_t* nb, int B, int N, int K, float alpha,
+                   const float* alpha_dev, const float* alpha_dev2, float* dS, gp_stream_t stream);
+/* total [1] = base[0] (or 0) + scale * scale_dev[0] (or 1) * sum[0]; link [1] = the second term */
+int gp_pk_link_finalize(const double* sum, double scale, const float* scale_dev, const float* base, float* total,
+                        float* link, gp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
