@@ -386,408 +386,687 @@ build_lists_kernel(const float* __restrict__ adj, const int32_t* __restrict__ nb
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// GCN layer forward, one or two stacks in lock-step
+// shared pieces of the layer / pooling kernels
 // ------------------------------------------------------------------------------------------------------------------
-struct FwdDims {
-  int ldi[2], ldo[2], ldbuf;        // padded widths
-};
-__host__ __device__ inline FwdDims fwd_dims(const gp_pk_layer_fwd_args& p) {
-  FwdDims d;
-  d.ldbuf = 4;
-  for (int s = 0; s < p.ns; ++s) {
-    d.ldi[s] = r4(p.s[s].in.d);
-    d.ldo[s] = r4(p.s[s].dout);
-    d.ldbuf = d.ldbuf > d.ldi[s] ? d.ldbuf : d.ldi[s];
-    d.ldbuf = d.ldbuf > d.ldo[s] ? d.ldbuf : d.ldo[s];
-  }
-  return d;
+// A window tile can hold up to w - 1 + N rows; the CTA walks it in runs of whole graphs with at most max_rows rows
+// (max_rows >= N, so one graph always fits): shared memory is sized for max_rows, not for the worst window.
+__device__ __forceinline__ int sub_end(const gp_pk_tiling& t, int g, int G1) {
+  if (t.rowptr == nullptr) return G1;
+  const int r = t.rowptr[g];
+  int ge = g + 1;
+  while (ge < G1 && t.rowptr[ge + 1] - r <= t.max_rows) ++ge;
+  return ge;
 }
-template <class C>
-inline void fwd_carve(const gp_pk_layer_fwd_args& p, const FwdDims& d, C& c) {
-  c.take(p.tl.max_rows * d.ldbuf);   // buf0
-  c.take(p.tl.max_rows * d.ldbuf);   // buf1
-  c.take(p.tl.max_rows);             // gs
-  c.take(p.tl.max_rows);             // gid
-  for (int s = 0; s < p.ns; ++s) {
-    c.take(d.ldi[s] * d.ldo[s]);     // W
-    c.take(d.ldo[s]);                // b
-    c.take(2 * p.N);                 // mean / istd of the input
-    c.take(2 * p.N);                 // partial sums
+__host__ __device__ __forceinline__ int pow2_ge(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// sum_e a(i, e) * src[gs + col_e][4q .. 4q+3]
+__device__ __forceinline__ float4 gather_row4(const gp_pk_adj& a, int nfix, int r0, int i, int gs, int gid,
+                                              const float* src, int ld, int q) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int ni = i - gs;
+  const float* sp = src + (size_t)gs * ld + 4 * q;
+  if (a.info) {
+    const int2 inf = __ldg(reinterpret_cast<const int2*>(a.info) + r0 + i);
+    const int2* en = reinterpret_cast<const int2*>(a.entries) + inf.x;
+    for (int e = 0; e < inf.y; ++e) {
+      const int2 x = __ldg(en + e);
+      const float v = __int_as_float(x.y);
+      const float4 s = *reinterpret_cast<const float4*>(sp + (size_t)x.x * ld);
+      acc.x = fmaf(v, s.x, acc.x); acc.y = fmaf(v, s.y, acc.y); acc.z = fmaf(v, s.z, acc.z); acc.w = fmaf(v, s.w, acc.w);
+    }
+  } else {
+    const float* dn = a.dense + (long long)gid * nfix * nfix;
+    for (int e = 0; e < nfix; ++e) {
+      const float v = a.transposed ? __ldg(dn + e * nfix + ni) : __ldg(dn + ni * nfix + e);
+      const float4 s = *reinterpret_cast<const float4*>(sp + (size_t)e * ld);
+      acc.x = fmaf(v, s.x, acc.x); acc.y = fmaf(v, s.y, acc.y); acc.z = fmaf(v, s.z, acc.z); acc.w = fmaf(v, s.w, acc.w);
+    }
   }
+  return acc;
+}
+// dst = A src over a sub-tile, one thread per (row, 4-column chunk): every thread has its own neighbour list in
+// flight, the 8 threads of a row share the list loads (broadcast) and read 128 contiguous bytes of the source row
+__device__ void gather4(const gp_pk_adj& a, int nfix, int r0, int nt, const int* s_gs, const int* s_gid,
+                        const float* src, int ld, float* dst) {
+  const int C4 = ld >> 2;
+  for (int item = threadIdx.x; item < nt * C4; item += blockDim.x) {
+    const int i = item / C4, q = item - i * C4;
+    const float4 acc = gather_row4(a, nfix, r0, i, s_gs[i], s_gid[i], src, ld, q);
+    *reinterpret_cast<float4*>(dst + (size_t)i * ld + 4 * q) = acc;
+  }
+}
+
+
+// Deterministic per-node-index accumulation of per-row statistics: s_rs[i], s_rs[mr + i] hold the two values of local
+// row i; thread n adds the rows with node index n graph by graph (fixed order), so a forward pass is bit-reproducible
+// (shared-memory atomics would add them in scheduling order).
+__device__ __forceinline__ void reduce_row_stats(const gp_pk_tiling& tl, int g0, int g1, int r0, int N, int mr,
+                                                 const float* s_rs, float* s_st) {
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    float a1 = 0.f, a2 = 0.f;
+    for (int g = g0; g < g1; ++g) {
+      const int gs = t_row0(tl, g) - r0, ng = t_row0(tl, g + 1) - r0 - gs;
+      if (n < ng) {
+        a1 += s_rs[gs + n];
+        a2 += s_rs[mr + gs + n];
+      }
+    }
+    s_st[n] += a1;
+    s_st[N + n] += a2;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// GCN layer forward: blockIdx.y = stack (embedding / assignment GCN in lock-step), persistent over the window tiles
+// ------------------------------------------------------------------------------------------------------------------
+static size_t fwd_smem(const gp_pk_layer_fwd_args& p) {
+  size_t best = 0;
+  for (int s = 0; s < p.ns; ++s) {
+    Count c;
+    const int ldi = r4(p.s[s].in.d), ldo = r4(p.s[s].dout), mr = p.tl.max_rows;
+    c.take(mr * ldi); c.take(mr * ldi); c.take(ldi * ldo); c.take(ldo); c.take(2 * p.N); c.take(2 * p.N);
+    c.take(mr); c.take(mr); c.take(2 * mr);
+    best = best > c.n ? best : c.n;
+  }
+  return best * sizeof(float);
 }
 
 __global__ void __launch_bounds__(kThreads)
 layer_fwd_kernel(const gp_pk_layer_fwd_args p) {
   extern __shared__ __align__(16) float sm[];
-  const FwdDims dm = fwd_dims(p);
+  const gp_pk_stack_fwd& st = p.s[blockIdx.y];
+  const int N = p.N, din = st.in.d, dout = st.dout, ldi = r4(din), ldo = r4(dout), mr = p.tl.max_rows;
   Carve cv{sm};
-  float* buf0 = cv.take(p.tl.max_rows * dm.ldbuf);
-  float* buf1 = cv.take(p.tl.max_rows * dm.ldbuf);
-  int* s_gs = reinterpret_cast<int*>(cv.take(p.tl.max_rows));
-  int* s_gid = reinterpret_cast<int*>(cv.take(p.tl.max_rows));
-  float *s_w[2], *s_b[2], *s_bn[2], *s_st[2];
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
-  const int N = p.N;
-  for (int s = 0; s < p.ns; ++s) {
-    s_w[s] = cv.take(dm.ldi[s] * dm.ldo[s]);
-    s_b[s] = cv.take(dm.ldo[s]);
-    s_bn[s] = cv.take(2 * N);
-    s_st[s] = cv.take(2 * N);
-    const gp_pk_stack_fwd& st = p.s[s];
-    const int din = st.in.d, dout = st.dout, ldo = dm.ldo[s];
-    for (int idx = tid; idx < dm.ldi[s] * ldo; idx += blockDim.x) {
-      const int k = idx / ldo, n = idx - k * ldo;
-      s_w[s][idx] = (k < din && n < dout) ? st.W[(long long)k * dout + n] : 0.f;
-    }
-    for (int n = tid; n < ldo; n += blockDim.x) s_b[s][n] = (st.b && n < dout) ? st.b[n] : 0.f;
-    for (int n = tid; n < 2 * N; n += blockDim.x) s_st[s][n] = 0.f;
-    bn_stats(st.in, p.cnt_pad, N, p.tl.B, s_bn[s], s_bn[s] + N);
+  float* bH = cv.take(mr * ldi);
+  float* bU = cv.take(mr * ldi);
+  float* s_w = cv.take(ldi * ldo);
+  float* s_b = cv.take(ldo);
+  float* s_bn = cv.take(2 * N);
+  float* s_st = cv.take(2 * N);
+  int* s_gs = reinterpret_cast<int*>(cv.take(mr));
+  int* s_gid = reinterpret_cast<int*>(cv.take(mr));
+  float* s_rs = cv.take(2 * mr);
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < ldi * ldo; idx += blockDim.x) {
+    const int k = idx / ldo, n = idx - k * ldo;
+    s_w[idx] = (k < din && n < dout) ? st.W[(long long)k * dout + n] : 0.f;
   }
-  __syncthreads();
+  for (int n = tid; n < ldo; n += blockDim.x) s_b[n] = (st.b && n < dout) ? st.b[n] : 0.f;
+  for (int n = tid; n < 2 * N; n += blockDim.x) s_st[n] = 0.f;
+  bn_stats(st.in, p.cnt_pad, N, p.tl.B, s_bn, s_bn + N);
+  const int N4 = ldo >> 2, N4p = pow2_ge(N4), K4 = ldi >> 2;
+  const bool stats = st.sums_out != nullptr;
   const int ntiles = t_count(p.tl);
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    int g0, g1;
-    t_graphs(p.tl, tile, g0, g1);
-    const int r0 = t_row0(p.tl, g0);
-    const int nt = (g1 > g0 ? t_row0(p.tl, g1) : r0) - r0;
-    if (nt <= 0) continue;
-    __syncthreads();
-    row_map(p.tl, g0, g1, r0, nt, s_gs, s_gid);
-    __syncthreads();
-    for (int s = 0; s < p.ns; ++s) {
-      const gp_pk_stack_fwd& st = p.s[s];
-      const int ldi = dm.ldi[s], ldo = dm.ldo[s], dout = st.dout;
-      load_rows(st.in, N, r0, nt, s_gs, s_gid, s_bn[s], s_bn[s] + N, buf0, ldi, 0, ldi);
-      __syncthreads();
-      gather(p.adj, p.tl.nfix, r0, nt, s_gs, s_gid, buf0, ldi, buf1);
-      __syncthreads();
-      {
-        float* v = buf0;
-        const float* bb = s_b[s];
-        gemm_nn(buf1, ldi, s_w[s], ldo, nt, ldo >> 2, ldi >> 2,
-                [=](int m, int n, float a) { v[m * ldo + n] = a + bb[n]; });
-      }
-      __syncthreads();
-      for (int i = wid; i < nt; i += nw) {
-        const float* v = buf0 + i * ldo;
-        float ss = 0.f;
-        for (int c = lane; c < dout; c += 32) ss = fmaf(v[c], v[c], ss);
-        ss = warp_sum(ss);
-        const float r = fmaxf(sqrtf(ss), kEpsNorm);
-        float a1 = 0.f, a2 = 0.f;
-        float* yo = st.y + (long long)(r0 + i) * dout;
-        for (int c = lane; c < dout; c += 32) {
-          const float y = v[c] / r;
-          yo[c] = y;
-          const float q = fmaxf(y, 0.f);
-          a1 += q;
-          a2 = fmaf(q, q, a2);
-        }
-        if (lane == 0) st.rnorm[r0 + i] = r;
-        if (st.sums_out) {
-          a1 = warp_sum(a1);
-          a2 = warp_sum(a2);
-          if (lane == 0) {
-            const int ni = i - s_gs[i];
-            atomicAdd(&s_st[s][ni], a1);
-            atomicAdd(&s_st[s][N + ni], a2);
+    int G0, G1;
+    t_graphs(p.tl, tile, G0, G1);
+    for (int g0 = G0; g0 < G1;) {
+      const int g1 = sub_end(p.tl, g0, G1);
+      const int r0 = t_row0(p.tl, g0), nt = t_row0(p.tl, g1) - r0;
+      if (nt > 0) {
+        __syncthreads();
+        row_map(p.tl, g0, g1, r0, nt, s_gs, s_gid);
+        __syncthreads();
+        load_rows(st.in, N, r0, nt, s_gs, s_gid, s_bn, s_bn + N, bH, ldi, 0, ldi);
+        __syncthreads();
+        gather4(p.adj, p.tl.nfix, r0, nt, s_gs, s_gid, bH, ldi, bU);
+        __syncthreads();
+        // V = U W + b, Y = V / max(||V||, eps), ReLU statistics: a row lives in the N4p lanes of one aligned group
+        const int total = ((nt + 3) >> 2) * N4p;
+        for (int base = 0; base < total; base += blockDim.x) {
+          const bool act = base + tid < total;
+          const int item = act ? base + tid : total - 1;
+          const int i = item / N4p, j = item - i * N4p;
+          const bool cols = j < N4;
+          const int mrem = nt - 4 * i;
+          float acc[4][4];
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+          if (cols) {
+            const float* a0 = bU + (size_t)(4 * i) * ldi;
+            const float* a1 = a0 + (mrem > 1 ? ldi : 0);
+            const float* a2 = a0 + (mrem > 2 ? 2 * ldi : 0);
+            const float* a3 = a0 + (mrem > 3 ? 3 * ldi : 0);
+            const float* b = s_w + 4 * j;
+            for (int k4 = 0; k4 < K4; ++k4) {
+              const float4 x0 = *reinterpret_cast<const float4*>(a0 + 4 * k4);
+              const float4 x1 = *reinterpret_cast<const float4*>(a1 + 4 * k4);
+              const float4 x2 = *reinterpret_cast<const float4*>(a2 + 4 * k4);
+              const float4 x3 = *reinterpret_cast<const float4*>(a3 + 4 * k4);
+              const float xs[4][4] = {{x0.x, x0.y, x0.z, x0.w}, {x1.x, x1.y, x1.z, x1.w}, {x2.x, x2.y, x2.z, x2.w},
+                                      {x3.x, x3.y, x3.z, x3.w}};
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                const float4 wv = *reinterpret_cast<const float4*>(b + (size_t)(4 * k4 + kk) * ldo);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                  acc[r][0] = fmaf(xs[r][kk], wv.x, acc[r][0]);
+                  acc[r][1] = fmaf(xs[r][kk], wv.y, acc[r][1]);
+                  acc[r][2] = fmaf(xs[r][kk], wv.z, acc[r][2]);
+                  acc[r][3] = fmaf(xs[r][kk], wv.w, acc[r][3]);
+                }
+              }
+            }
+            const float4 bv = *reinterpret_cast<const float4*>(s_b + 4 * j);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) { acc[r][0] += bv.x; acc[r][1] += bv.y; acc[r][2] += bv.z; acc[r][3] += bv.w; }
+          }
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            float ss = acc[r][0] * acc[r][0];
+            ss = fmaf(acc[r][1], acc[r][1], ss);
+            ss = fmaf(acc[r][2], acc[r][2], ss);
+            ss = fmaf(acc[r][3], acc[r][3], ss);
+            for (int o = N4p >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            const float rn = fmaxf(sqrtf(ss), kEpsNorm);
+            float a1 = 0.f, a2 = 0.f;
+            const bool rowok = act && r < mrem;
+            float* yo = st.y + (long long)(r0 + 4 * i + r) * dout + 4 * j;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float y = acc[r][c] / rn;
+              if (rowok && cols && 4 * j + c < dout) yo[c] = y;
+              const float q = fmaxf(y, 0.f);
+              a1 += q;
+              a2 = fmaf(q, q, a2);
+            }
+            if (stats) {
+              for (int o = N4p >> 1; o > 0; o >>= 1) {
+                a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+                a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+              }
+            }
+            if (rowok && j == 0) {
+              st.rnorm[r0 + 4 * i + r] = rn;
+              s_rs[4 * i + r] = a1;
+              s_rs[mr + 4 * i + r] = a2;
+            }
           }
         }
+        if (stats) {
+          __syncthreads();
+          reduce_row_stats(p.tl, g0, g1, r0, N, mr, s_rs, s_st);
+        }
       }
-      __syncthreads();
+      g0 = g1;
     }
   }
   __syncthreads();
-  for (int s = 0; s < p.ns; ++s)
-    if (p.s[s].sums_out)
-      for (int n = tid; n < 2 * N; n += blockDim.x)
-        if (s_st[s][n] != 0.f) atomicAdd(&p.s[s].sums_out[n], (double)s_st[s][n]);
+  if (stats)
+    for (int n = tid; n < 2 * N; n += blockDim.x)
+      if (s_st[n] != 0.f) atomicAdd(&st.sums_out[n], (double)s_st[n]);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// GCN layer backward
+// GCN layer backward (blockIdx.y = stack)
 // ------------------------------------------------------------------------------------------------------------------
-struct BwdDims {
-  int ldi[2], ldo[2], ldbuf, dwcap;
-};
-__host__ __device__ inline BwdDims bwd_dims(const gp_pk_layer_bwd_args& p) {
-  BwdDims d;
-  d.ldbuf = 4;
-  d.dwcap = 0;
-  for (int s = 0; s < p.ns; ++s) {
-    d.ldi[s] = r4(p.s[s].in.d);
-    d.ldo[s] = r4(p.s[s].dout);
-    d.ldbuf = d.ldbuf > d.ldi[s] ? d.ldbuf : d.ldi[s];
-    d.ldbuf = d.ldbuf > d.ldo[s] ? d.ldbuf : d.ldo[s];
-    const int one = d.ldi[s] * d.ldo[s];
-    int groups = kThreads / ((d.ldi[s] >> 2) * (d.ldo[s] >> 2));
-    groups = groups < 1 ? 1 : (groups > 4 ? 4 : groups);
-    d.dwcap = d.dwcap > one * groups ? d.dwcap : one * groups;
-  }
-  return d;
+__host__ __device__ inline int bwd_groups(int ldi, int ldo) {
+  int g = kThreads / ((ldi >> 2) * (ldo >> 2));
+  return g < 1 ? 1 : (g > 2 ? 2 : g);
 }
-template <class C>
-inline void bwd_carve(const gp_pk_layer_bwd_args& p, const BwdDims& d, C& c) {
-  for (int i = 0; i < 4; ++i) c.take(p.tl.max_rows * d.ldbuf);
-  c.take(p.tl.max_rows);
-  c.take(p.tl.max_rows);
+static size_t bwd_smem(const gp_pk_layer_bwd_args& p) {
+  size_t best = 0;
   for (int s = 0; s < p.ns; ++s) {
-    c.take(d.ldi[s] * d.ldo[s]);     // W   [din x ldo]
-    c.take(d.ldo[s] * d.ldi[s]);     // W^T [dout x ldi]
-    c.take(d.dwcap);                 // dW accumulators (groups)
-    c.take(d.ldo[s]);                // db accumulator
-    c.take(2 * p.N);                 // mean / istd of the input
-    c.take(2 * p.N);                 // mean / istd of the output
-    c.take(2 * p.N);                 // m1 / m2 of the output
-    c.take(2 * p.N);                 // partial sums for msums_prev
+    Count c;
+    const int ldi = r4(p.s[s].in.d), ldo = r4(p.s[s].dout), mr = p.tl.max_rows;
+    c.take(mr * ldo); c.take(mr * ldi); c.take(mr * ldi);
+    c.take(ldi * ldo); c.take(ldo * ldi); c.take(bwd_groups(ldi, ldo) * ldi * ldo); c.take(ldo);
+    for (int i = 0; i < 4; ++i) c.take(2 * p.N);
+    c.take(p.N); c.take(mr); c.take(mr);
+    best = best > c.n ? best : c.n;
   }
-  c.take(p.N);                       // scratch (pad rows)
+  return best * sizeof(float);
 }
 
 __global__ void __launch_bounds__(kThreads)
 layer_bwd_kernel(const gp_pk_layer_bwd_args p) {
   extern __shared__ __align__(16) float sm[];
-  const BwdDims dm = bwd_dims(p);
+  const gp_pk_stack_bwd& st = p.s[blockIdx.y];
+  const int N = p.N, B = p.tl.B, din = st.in.d, dout = st.dout, ldi = r4(din), ldo = r4(dout), mr = p.tl.max_rows;
+  const int groups = bwd_groups(ldi, ldo);
   Carve cv{sm};
-  float* bG = cv.take(p.tl.max_rows * dm.ldbuf);    // gl -> dV
-  float* bY = cv.take(p.tl.max_rows * dm.ldbuf);    // Y  -> dX
-  float* bH = cv.take(p.tl.max_rows * dm.ldbuf);    // Hin
-  float* bU = cv.take(p.tl.max_rows * dm.ldbuf);    // U  -> dU
-  int* s_gs = reinterpret_cast<int*>(cv.take(p.tl.max_rows));
-  int* s_gid = reinterpret_cast<int*>(cv.take(p.tl.max_rows));
-  float *s_w[2], *s_wt[2], *s_dw[2], *s_db[2], *s_bni[2], *s_bno[2], *s_m[2], *s_mp[2];
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
-  const int N = p.N, B = p.tl.B;
-  int groups[2];
-  for (int s = 0; s < p.ns; ++s) {
-    const gp_pk_stack_bwd& st = p.s[s];
-    const int din = st.in.d, dout = st.dout, ldi = dm.ldi[s], ldo = dm.ldo[s];
-    s_w[s] = cv.take(ldi * ldo);
-    s_wt[s] = cv.take(ldo * ldi);
-    s_dw[s] = cv.take(dm.dwcap);
-    s_db[s] = cv.take(ldo);
-    s_bni[s] = cv.take(2 * N);
-    s_bno[s] = cv.take(2 * N);
-    s_m[s] = cv.take(2 * N);
-    s_mp[s] = cv.take(2 * N);
-    groups[s] = tn_groups(ldi >> 2, ldo >> 2, dm.dwcap, ldo);
-    for (int idx = tid; idx < ldi * ldo; idx += blockDim.x) {
-      const int k = idx / ldo, n = idx - k * ldo;
-      s_w[s][idx] = (k < din && n < dout) ? st.W[(long long)k * dout + n] : 0.f;
-    }
-    for (int idx = tid; idx < ldo * ldi; idx += blockDim.x) {
-      const int n = idx / ldi, k = idx - n * ldi;
-      s_wt[s][idx] = (k < din && n < dout) ? st.W[(long long)k * dout + n] : 0.f;
-    }
-    for (int idx = tid; idx < dm.dwcap; idx += blockDim.x) s_dw[s][idx] = 0.f;
-    for (int n = tid; n < ldo; n += blockDim.x) s_db[s][n] = 0.f;
-    for (int n = tid; n < 2 * N; n += blockDim.x) s_mp[s][n] = 0.f;
-    bn_stats(st.in, p.cnt_pad, N, B, s_bni[s], s_bni[s] + N);
-    bn_stats(st.out, p.cnt_pad, N, B, s_bno[s], s_bno[s] + N);
-    if (st.msums) {
-      const double cnt = (double)B * (double)dout;
-      for (int n = tid; n < 2 * N; n += blockDim.x) s_m[s][n] = (float)(st.msums[n] / cnt);
-    }
-  }
+  float* bV = cv.take(mr * ldo);      // dV
+  float* bH = cv.take(mr * ldi);      // Hin
+  float* bU = cv.take(mr * ldi);      // U = A Hin, then dU = dV W^T
+  float* s_w = cv.take(ldi * ldo);
+  float* s_wt = cv.take(ldo * ldi);
+  float* s_dw = cv.take(groups * ldi * ldo);
+  float* s_db = cv.take(ldo);
+  float* s_bni = cv.take(2 * N);
+  float* s_bno = cv.take(2 * N);
+  float* s_m = cv.take(2 * N);
+  float* s_mp = cv.take(2 * N);
   float* s_scr = cv.take(N);
+  int* s_gs = reinterpret_cast<int*>(cv.take(mr));
+  int* s_gid = reinterpret_cast<int*>(cv.take(mr));
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+  for (int idx = tid; idx < ldi * ldo; idx += blockDim.x) {
+    const int k = idx / ldo, n = idx - k * ldo;
+    s_w[idx] = (k < din && n < dout) ? st.W[(long long)k * dout + n] : 0.f;
+  }
+  for (int idx = tid; idx < ldo * ldi; idx += blockDim.x) {
+    const int n = idx / ldi, k = idx - n * ldi;
+    s_wt[idx] = (k < din && n < dout) ? st.W[(long long)k * dout + n] : 0.f;
+  }
+  for (int idx = tid; idx < groups * ldi * ldo; idx += blockDim.x) s_dw[idx] = 0.f;
+  for (int n = tid; n < ldo; n += blockDim.x) s_db[n] = 0.f;
+  for (int n = tid; n < 2 * N; n += blockDim.x) s_mp[n] = 0.f;
+  bn_stats(st.in, p.cnt_pad, N, B, s_bni, s_bni + N);
+  bn_stats(st.out, p.cnt_pad, N, B, s_bno, s_bno + N);
+  const bool bn = st.out.sums != nullptr;
+  if (bn) {
+    const double cnt = (double)B * (double)dout;
+    for (int n = tid; n < 2 * N; n += blockDim.x) s_m[n] = (float)(st.msums[n] / cnt);
+  }
   __syncthreads();
 
   // pad rows of a BatchNorm'd layer with a bias: no upstream gradient, but the batch means reach them; cnt_pad[n]
   // copies of one vector per node index feed the bias gradient (packed_blueprint.stack_backward)
-  if (blockIdx.x == 0) {
-    for (int s = 0; s < p.ns; ++s) {
-      const gp_pk_stack_bwd& st = p.s[s];
-      if (!(st.out.sums && st.b && st.db && p.cnt_pad)) continue;
-      const int dout = st.dout;
-      float nn = 0.f;
-      for (int c = 0; c < dout; ++c) nn = fmaf(st.b[c], st.b[c], nn);
-      const float rp = fmaxf(sqrtf(nn), kEpsNorm);
-      const float *mean = s_bno[s], *istd = s_bno[s] + N, *m1 = s_m[s], *m2 = s_m[s] + N;
-      for (int n = tid; n < N; n += blockDim.x) {        // proj[n] = sum_c yp[c] * dYp[n][c]
-        float pr = 0.f;
-        for (int c = 0; c < dout; ++c) {
-          const float yp = st.b[c] / rp;
-          const float hp = (fmaxf(yp, 0.f) - mean[n]) * istd[n];
-          const float dy = yp > 0.f ? (-m1[n] - hp * m2[n]) * istd[n] : 0.f;
-          pr = fmaf(yp, dy, pr);
-        }
-        s_scr[n] = pr;
-      }
-      __syncthreads();
-      for (int c = tid; c < dout; c += blockDim.x) {
+  if (blockIdx.x == 0 && bn && st.b && st.db && p.cnt_pad) {
+    float nn = 0.f;
+    for (int c = 0; c < dout; ++c) nn = fmaf(st.b[c], st.b[c], nn);
+    const float rp = fmaxf(sqrtf(nn), kEpsNorm);
+    const float *mean = s_bno, *istd = s_bno + N, *m1 = s_m, *m2 = s_m + N;
+    for (int n = tid; n < N; n += blockDim.x) {        // proj[n] = sum_c yp[c] * dYp[n][c]
+      float pr = 0.f;
+      for (int c = 0; c < dout; ++c) {
         const float yp = st.b[c] / rp;
-        float acc = 0.f;
-        for (int n = 0; n < N; ++n) {
-          const float cp = p.cnt_pad[n];
-          if (cp == 0.f) continue;
-          const float hp = (fmaxf(yp, 0.f) - mean[n]) * istd[n];
-          const float dy = yp > 0.f ? (-m1[n] - hp * m2[n]) * istd[n] : 0.f;
-          const float dv = rp > kEpsNorm ? (dy - yp * s_scr[n]) / rp : dy / kEpsNorm;
-          acc = fmaf(cp, dv, acc);
-        }
-        s_db[s][c] += acc;
+        const float hp = (fmaxf(yp, 0.f) - mean[n]) * istd[n];
+        const float dy = yp > 0.f ? (-m1[n] - hp * m2[n]) * istd[n] : 0.f;
+        pr = fmaf(yp, dy, pr);
       }
-      __syncthreads();
+      s_scr[n] = pr;
     }
+    __syncthreads();
+    for (int c = tid; c < dout; c += blockDim.x) {
+      const float yp = st.b[c] / rp;
+      float acc = 0.f;
+      for (int n = 0; n < N; ++n) {
+        const float cp = p.cnt_pad[n];
+        if (cp == 0.f) continue;
+        const float hp = (fmaxf(yp, 0.f) - mean[n]) * istd[n];
+        const float dy = yp > 0.f ? (-m1[n] - hp * m2[n]) * istd[n] : 0.f;
+        const float dv = rp > kEpsNorm ? (dy - yp * s_scr[n]) / rp : dy / kEpsNorm;
+        acc = fmaf(cp, dv, acc);
+      }
+      s_db[c] += acc;
+    }
+    __syncthreads();
   }
 
+  float dbacc[4] = {0.f, 0.f, 0.f, 0.f};               // bias gradient: columns lane, lane+32, ... of this warp's rows
+  const int C4 = ldi >> 2, C4p = pow2_ge(C4);
   const int ntiles = t_count(p.tl);
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    int g0, g1;
-    t_graphs(p.tl, tile, g0, g1);
-    const int r0 = t_row0(p.tl, g0);
-    const int nt = (g1 > g0 ? t_row0(p.tl, g1) : r0) - r0;
-    if (nt <= 0) continue;
-    __syncthreads();
-    row_map(p.tl, g0, g1, r0, nt, s_gs, s_gid);
-    __syncthreads();
-    for (int s = 0; s < p.ns; ++s) {
-      const gp_pk_stack_bwd& st = p.s[s];
-      const int din = st.in.d, dout = st.dout, ldi = dm.ldi[s], ldo = dm.ldo[s];
-      // ---- dV = d normalize . d(ReLU + BatchNorm) . gl
-      for (int idx = tid; idx < nt * ldo; idx += blockDim.x) {
-        const int i = idx / ldo, c = idx - i * ldo;
-        float g = 0.f, y = 0.f;
-        if (c < dout) {
-          g = grad_at(st.gl, r0, i, s_gid[i], i - s_gs[i], c);
-          y = st.out.y[(long long)(r0 + i) * st.out.ld + c];
-        }
-        bG[idx] = g;
-        bY[idx] = y;
-      }
-      __syncthreads();
-      const bool bn = st.out.sums != nullptr;
-      for (int i = wid; i < nt; i += nw) {
-        const int ni = i - s_gs[i];
-        const float r = st.rnorm[r0 + i];
-        float mean = 0.f, istd = 1.f, m1 = 0.f, m2 = 0.f;
-        if (bn) { mean = s_bno[s][ni]; istd = s_bno[s][N + ni]; m1 = s_m[s][ni]; m2 = s_m[s][N + ni]; }
-        float* g = bG + i * ldo;
-        const float* y = bY + i * ldo;
-        float pr = 0.f;
-        for (int c = lane; c < dout; c += 32) {
-          float dy = g[c];
-          if (bn) {
-            const float h = (fmaxf(y[c], 0.f) - mean) * istd;
-            dy = y[c] > 0.f ? (dy - m1 - h * m2) * istd : 0.f;
+    int G0, G1;
+    t_graphs(p.tl, tile, G0, G1);
+    for (int g0 = G0; g0 < G1;) {
+      const int g1 = sub_end(p.tl, g0, G1);
+      const int r0 = t_row0(p.tl, g0), nt = t_row0(p.tl, g1) - r0;
+      if (nt > 0) {
+        __syncthreads();
+        row_map(p.tl, g0, g1, r0, nt, s_gs, s_gid);
+        __syncthreads();
+        // ---- dV = d normalize . d(ReLU + BatchNorm) . gl, straight from global memory (one warp per row)
+        for (int i = wid; i < nt; i += nw) {
+          const int ni = i - s_gs[i], gid = s_gid[i];
+          const float r = st.rnorm[r0 + i];
+          float mean = 0.f, istd = 1.f, m1 = 0.f, m2 = 0.f;
+          if (bn) { mean = s_bno[ni]; istd = s_bno[N + ni]; m1 = s_m[ni]; m2 = s_m[N + ni]; }
+          float gv[4], yv[4];
+          float pr = 0.f;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int c = lane + 32 * t;
+            gv[t] = 0.f;
+            yv[t] = 0.f;
+            if (c < dout) {
+              float dy = grad_at(st.gl, r0, i, gid, ni, c);
+              const float y = st.out.y[(long long)(r0 + i) * st.out.ld + c];
+              if (bn) {
+                const float h = (fmaxf(y, 0.f) - mean) * istd;
+                dy = y > 0.f ? (dy - m1 - h * m2) * istd : 0.f;
+              }
+              gv[t] = dy;
+              yv[t] = y;
+              pr = fmaf(y, dy, pr);
+            }
           }
-          g[c] = dy;
-          pr = fmaf(y[c], dy, pr);
-        }
-        pr = warp_sum(pr);
-        for (int c = lane; c < dout; c += 32)
-          g[c] = r > kEpsNorm ? (g[c] - y[c] * pr) / r : g[c] / kEpsNorm;
-      }
-      __syncthreads();
-      if (st.db)
-        for (int c = tid; c < dout; c += blockDim.x) {
-          float acc = 0.f;
-          for (int i = 0; i < nt; ++i) acc += bG[i * ldo + c];
-          s_db[s][c] += acc;
-        }
-      // ---- U = A Hin (recomputed), dW += U^T dV
-      load_rows(st.in, N, r0, nt, s_gs, s_gid, s_bni[s], s_bni[s] + N, bH, ldi, 0, ldi);
-      __syncthreads();
-      gather(p.adj, p.tl.nfix, r0, nt, s_gs, s_gid, bH, ldi, bU);
-      __syncthreads();
-      gemm_tn_acc(bU, ldi, bG, ldo, ldi >> 2, ldo >> 2, 0, nt, s_dw[s], ldo, groups[s]);
-      __syncthreads();
-      if (!st.need_dx) continue;
-      // ---- dU = dV W^T, dA (dense level), dX = A^T dU
-      {
-        float* du = bU;
-        gemm_nn(bG, ldo, s_wt[s], ldi, nt, ldi >> 2, ldo >> 2, [=](int m, int n, float a) { du[m * ldi + n] = a; });
-      }
-      __syncthreads();
-      if (st.dadj) {
-        const int nf = p.tl.nfix;
-        for (int idx = tid; idx < nt * nf; idx += blockDim.x) {
-          const int i = idx / nf, j = idx - i * nf;                 // dA[g][ni][j] = <dU[i], Hin[gs + j]>
-          const float* a = bU + i * ldi;
-          const float* h = bH + (s_gs[i] + j) * ldi;
-          float acc = 0.f;
-          for (int c = 0; c < din; ++c) acc = fmaf(a[c], h[c], acc);
-          float* o = st.dadj + ((long long)s_gid[i] * nf + (i - s_gs[i])) * nf + j;
-          *o = st.dadj_acc ? *o + acc : acc;
-        }
-      }
-      gather(p.adj_in, p.tl.nfix, r0, nt, s_gs, s_gid, bU, ldi, bY);
-      __syncthreads();
-      for (int i = wid; i < nt; i += nw) {
-        const int ni = i - s_gs[i], gid = s_gid[i];
-        float a1 = 0.f, a2 = 0.f;
-        for (int c = lane; c < din; c += 32) {
-          const float g = bY[i * ldi + c] + grad_at(st.gz_prev, r0, i, gid, ni, c);
-          st.gl_prev[(long long)(r0 + i) * din + c] = g;
-          a1 += g;
-          a2 = fmaf(g, bH[i * ldi + c], a2);
-        }
-        if (st.msums_prev) {
-          a1 = warp_sum(a1);
-          a2 = warp_sum(a2);
-          if (lane == 0) {
-            atomicAdd(&s_mp[s][ni], a1);
-            atomicAdd(&s_mp[s][N + ni], a2);
+          pr = warp_sum(pr);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int c = lane + 32 * t;
+            if (c < ldo) {
+              const float dv = c < dout ? (r > kEpsNorm ? (gv[t] - yv[t] * pr) / r : gv[t] / kEpsNorm) : 0.f;
+              bV[i * ldo + c] = dv;
+              dbacc[t] += dv;
+            }
           }
         }
+        load_rows(st.in, N, r0, nt, s_gs, s_gid, s_bni, s_bni + N, bH, ldi, 0, ldi);
+        __syncthreads();
+        gather4(p.adj, p.tl.nfix, r0, nt, s_gs, s_gid, bH, ldi, bU);
+        __syncthreads();
+        gemm_tn_acc(bU, ldi, bV, ldo, ldi >> 2, ldo >> 2, 0, nt, s_dw, ldo, groups);
+        if (st.need_dx) {
+          __syncthreads();
+          {
+            float* du = bU;
+            gemm_nn(bV, ldo, s_wt, ldi, nt, ldi >> 2, ldo >> 2, [=](int m, int n, float a) { du[m * ldi + n] = a; });
+          }
+          __syncthreads();
+          if (st.dadj) {
+            const int nf = p.tl.nfix;
+            for (int idx = tid; idx < nt * nf; idx += blockDim.x) {
+              const int i = idx / nf, j = idx - i * nf;               // dA[g][ni][j] = <dU[i], Hin[gs + j]>
+              const float* a = bU + i * ldi;
+              const float* h = bH + (s_gs[i] + j) * ldi;
+              float acc = 0.f;
+              for (int c = 0; c < ldi; c += 4) {
+                const float4 x = *reinterpret_cast<const float4*>(a + c);
+                const float4 y = *reinterpret_cast<const float4*>(h + c);
+                acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+              }
+              float* o = st.dadj + ((long long)s_gid[i] * nf + (i - s_gs[i])) * nf + j;
+              *o = st.dadj_acc ? *o + acc : acc;
+            }
+          }
+          // gl_prev = gz_prev + A^T dU, and its two batch sums per node index
+          const int total = nt * C4p;
+          for (int base = 0; base < total; base += blockDim.x) {
+            const bool act = base + tid < total;
+            const int item = act ? base + tid : total - 1;
+            const int i = item / C4p, q = item - i * C4p;
+            const int gs = s_gs[i], gid = s_gid[i], ni = i - gs;
+            float a1 = 0.f, a2 = 0.f;
+            if (q < C4) {
+              const float4 d4 = gather_row4(p.adj_in, p.tl.nfix, r0, i, gs, gid, bU, ldi, q);
+              const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+              for (int cc = 0; cc < 4; ++cc) {
+                const int c = 4 * q + cc;
+                if (c < din) {
+                  const float g = dv[cc] + grad_at(st.gz_prev, r0, i, gid, ni, c);
+                  if (act) st.gl_prev[(long long)(r0 + i) * din + c] = g;
+                  a1 += g;
+                  a2 = fmaf(g, bH[i * ldi + c], a2);
+                }
+              }
+            }
+            if (st.msums_prev) {
+              for (int o = C4p >> 1; o > 0; o >>= 1) {
+                a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+                a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+              }
+              if (act && q == 0) {
+                atomicAdd(&s_mp[ni], a1);
+                atomicAdd(&s_mp[N + ni], a2);
+              }
+            }
+          }
+        }
       }
-      __syncthreads();
+      g0 = g1;
+    }
+  }
+  if (st.db) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int c = lane + 32 * t;
+      if (c < dout && dbacc[t] != 0.f) atomicAdd(&s_db[c], dbacc[t]);
     }
   }
   __syncthreads();
-  for (int s = 0; s < p.ns; ++s) {
-    const gp_pk_stack_bwd& st = p.s[s];
-    const int din = st.in.d, dout = st.dout, ldi = dm.ldi[s], ldo = dm.ldo[s];
-    const int gstride = ldi * ldo;
-    for (int idx = tid; idx < din * dout; idx += blockDim.x) {
-      const int k = idx / dout, n = idx - k * dout;
-      float acc = 0.f;
-      for (int g = 0; g < groups[s]; ++g) acc += s_dw[s][g * gstride + k * ldo + n];
-      if (acc != 0.f) atomicAdd(&st.dW[idx], acc);
-    }
-    if (st.db)
-      for (int c = tid; c < dout; c += blockDim.x)
-        if (s_db[s][c] != 0.f) atomicAdd(&st.db[c], s_db[s][c]);
-    if (st.msums_prev)
-      for (int n = tid; n < 2 * N; n += blockDim.x)
-        if (s_mp[s][n] != 0.f) atomicAdd(&st.msums_prev[n], (double)s_mp[s][n]);
+  for (int idx = tid; idx < din * dout; idx += blockDim.x) {
+    const int k = idx / dout, n = idx - k * dout;
+    float acc = 0.f;
+    for (int g = 0; g < groups; ++g) acc += s_dw[g * ldi * ldo + k * ldo + n];
+    if (acc != 0.f) atomicAdd(&st.dW[idx], acc);
   }
+  if (st.db)
+    for (int c = tid; c < dout; c += blockDim.x)
+      if (s_db[c] != 0.f) atomicAdd(&st.db[c], s_db[c]);
+  if (st.msums_prev)
+    for (int n = tid; n < 2 * N; n += blockDim.x)
+      if (s_mp[n] != 0.f) atomicAdd(&st.msums_prev[n], (double)s_mp[n]);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Fast path of the layer kernels for din <= 32 and dout <= 32 (every level-0 layer at ENZYMES shapes, the pooled
+// level's layers after its first): ONE WARP PER ROW, lane = column.  The weight column W[:, lane] (forward) or the
+// weight row W[lane, :] plus the dW column (backward) live in registers; the only shared-memory traffic per row is the
+// neighbour rows of the gather and a 128-byte broadcast buffer.  ~80 warp instructions per row and stack instead of
+// ~380 for the 4x4-tiled kernels (ncu, profiles/r2_ncu_packed.md): no index arithmetic, no staging of V.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kDegCap = 8;      // neighbour-list entries per row kept in shared memory (longer lists: the rest from L2)
+
+// Neighbour lists (or the dense blocks of the pooled level) of a sub-tile -> shared memory, all rows in parallel: the
+// two dependent global accesses (list header, entries) are paid once per sub-tile instead of once per row and warp.
+__device__ __forceinline__ void stage_lists(const gp_pk_adj& a, const gp_pk_tiling& tl, int g0, int g1, int r0, int nt,
+                                            int2* s_info, int2* s_ent) {
+  if (a.info) {
+    for (int i = threadIdx.x; i < nt; i += blockDim.x) {
+      const int2 inf = __ldg(reinterpret_cast<const int2*>(a.info) + r0 + i);
+      s_info[i] = inf;
+      const int2* en = reinterpret_cast<const int2*>(a.entries) + inf.x;
+      const int m = min(inf.y, kDegCap);
+      for (int e = 0; e < m; ++e) s_ent[i * kDegCap + e] = __ldg(en + e);
+    }
+  } else {
+    const int nf = tl.nfix, per = nf * nf;
+    if ((g1 - g0) * per <= 2 * tl.max_rows * kDegCap) {           // dense blocks fit: stage them
+      float* d = reinterpret_cast<float*>(s_ent);
+      const float* src = a.dense + (long long)g0 * per;
+      for (int idx = threadIdx.x; idx < (g1 - g0) * per; idx += blockDim.x) d[idx] = __ldg(src + idx);
+    }
+  }
+}
+
+__device__ __forceinline__ float gather_lane(const gp_pk_adj& a, const gp_pk_tiling& tl, int g0, int g1, int i, int gs,
+                                             int gid, int ni, const int2* s_info, const int2* s_ent, const float* rows,
+                                             int ld, int lane) {
+  float u = 0.f;
+  const float* sp = rows + (size_t)gs * ld + lane;
+  if (a.info) {
+    const int2 inf = s_info[i];
+    if (lane < ld) {
+      const int m = min(inf.y, kDegCap);
+      for (int e = 0; e < m; ++e) {
+        const int2 x = s_ent[i * kDegCap + e];
+        u = fmaf(__int_as_float(x.y), sp[(size_t)x.x * ld], u);
+      }
+      const int2* en = reinterpret_cast<const int2*>(a.entries) + inf.x;
+      for (int e = kDegCap; e < inf.y; ++e) {
+        const int2 x = __ldg(en + e);
+        u = fmaf(__int_as_float(x.y), sp[(size_t)x.x * ld], u);
+      }
+    }
+  } else {
+    const int nf = tl.nfix, per = nf * nf;
+    const bool staged = (g1 - g0) * per <= 2 * tl.max_rows * kDegCap;
+    const float* dn = staged ? reinterpret_cast<const float*>(s_ent) + (gid - g0) * per : a.dense + (long long)gid * per;
+    if (lane < ld)
+      for (int e = 0; e < nf; ++e) {
+        const float v = a.transposed ? dn[e * nf + ni] : dn[ni * nf + e];
+        u = fmaf(v, sp[(size_t)e * ld], u);
+      }
+  }
+  return u;
+}
+
+// rows of the sub-tile -> shared memory, one warp per row (ld <= 32), four rows in flight per warp
+__device__ __forceinline__ void load_rows_warp(const gp_pk_src& src, int N, int r0, int nt, const int* s_gs,
+                                               const int* s_gid, const float* s_mean, const float* s_istd, float* dst,
+                                               int ld) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const bool bn = src.sums != nullptr;
+  if (lane >= ld) return;
+#pragma unroll 4
+  for (int i = wid; i < nt; i += nw) {
+    float v = 0.f;
+    if (lane < src.d) {
+      const int ni = i - s_gs[i];
+      const long long row = src.padded ? ((long long)s_gid[i] * N + ni) : (long long)(r0 + i);
+      v = __ldg(src.y + row * src.ld + lane);
+      if (bn) v = (fmaxf(v, 0.f) - s_mean[ni]) * s_istd[ni];
+    }
+    dst[i * ld + lane] = v;
+  }
+}
+
+static size_t fwd_row_smem(const gp_pk_layer_fwd_args& p) {
+  size_t best = 0;
+  for (int s = 0; s < p.ns; ++s) {
+    Count c;
+    const int ldi = r4(p.s[s].in.d), mr = p.tl.max_rows;
+    c.take(mr * ldi); c.take((kThreads / 32) * 64); c.take(2 * p.N); c.take(2 * p.N); c.take(mr); c.take(mr);
+    c.take(2 * mr); c.take(2 * mr * kDegCap); c.take(2 * mr);
+    best = best > c.n ? best : c.n;
+  }
+  return best * sizeof(float);
+}
+
+__global__ void __launch_bounds__(kThreads, 3)
+layer_fwd_row_kernel(const gp_pk_layer_fwd_args p) {
+  extern __shared__ __align__(16) float sm[];
+  const gp_pk_stack_fwd& st = p.s[blockIdx.y];
+  const int N = p.N, din = st.in.d, dout = st.dout, ldi = r4(din), mr = p.tl.max_rows;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+  Carve cv{sm};
+  float* bH = cv.take(mr * ldi);
+  float* su = cv.take((kThreads / 32) * 64) + wid * 64;
+  float* s_bn = cv.take(2 * N);
+  float* s_st = cv.take(2 * N);
+  int* s_gs = reinterpret_cast<int*>(cv.take(mr));
+  int* s_gid = reinterpret_cast<int*>(cv.take(mr));
+  int2* s_info = reinterpret_cast<int2*>(cv.take(2 * mr));
+  int2* s_ent = reinterpret_cast<int2*>(cv.take(2 * mr * kDegCap));
+  float* s_rs = cv.take(2 * mr);
+  float wreg[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) wreg[k] = (k < din && lane < dout) ? __ldg(st.W + (long long)k * dout + lane) : 0.f;
+  const float bias = (st.b && lane < dout) ? __ldg(st.b + lane) : 0.f;
+  for (int n = tid; n < 2 * N; n += blockDim.x) s_st[n] = 0.f;
+  bn_stats(st.in, p.cnt_pad, N, p.tl.B, s_bn, s_bn + N);
+  const bool stats = st.sums_out != nullptr;
+  const int ntiles = t_count(p.tl);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int G0, G1;
+    t_graphs(p.tl, tile, G0, G1);
+    for (int g0 = G0; g0 < G1;) {
+      const int g1 = sub_end(p.tl, g0, G1);
+      const int r0 = t_row0(p.tl, g0), nt = t_row0(p.tl, g1) - r0;
+      if (nt > 0) {
+        __syncthreads();
+        row_map(p.tl, g0, g1, r0, nt, s_gs, s_gid);
+        stage_lists(p.adj, p.tl, g0, g1, r0, nt, s_info, s_ent);
+        __syncthreads();
+        load_rows_warp(st.in, N, r0, nt, s_gs, s_gid, s_bn, s_bn + N, bH, ldi);
+        __syncthreads();
+        for (int ib = wid; ib < nt; ib += 2 * nw) {        // two rows per iteration: their chains interleave
+          int ii[2], nis[2];
+          float vv[2];
+          const bool two = ib + nw < nt;
+          ii[0] = ib;
+          ii[1] = two ? ib + nw : ib;
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const int i = ii[r], gs = s_gs[i];
+            nis[r] = i - gs;
+            su[r * 32 + lane] = gather_lane(p.adj, p.tl, g0, g1, i, gs, s_gid[i], nis[r], s_info, s_ent, bH, ldi, lane);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            float a0 = bias, a1 = 0.f;
+#pragma unroll
+            for (int k4 = 0; k4 < 8; ++k4)
+              if (4 * k4 < ldi) {
+                const float4 uu = *reinterpret_cast<const float4*>(su + r * 32 + 4 * k4);
+                a0 = fmaf(uu.x, wreg[4 * k4], a0);
+                a1 = fmaf(uu.y, wreg[4 * k4 + 1], a1);
+                a0 = fmaf(uu.z, wreg[4 * k4 + 2], a0);
+                a1 = fmaf(uu.w, wreg[4 * k4 + 3], a1);
+              }
+            vv[r] = a0 + a1;                               // lanes >= dout: 0
+          }
+          __syncwarp();
+          float ss[2], s1[2], s2[2];
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const float q = fmaxf(vv[r], 0.f);
+            ss[r] = vv[r] * vv[r];
+            s1[r] = q;
+            s2[r] = q * q;
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+              ss[r] += __shfl_xor_sync(0xffffffffu, ss[r], o);
+              s1[r] += __shfl_xor_sync(0xffffffffu, s1[r], o);
+              s2[r] += __shfl_xor_sync(0xffffffffu, s2[r], o);
+            }
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            if (r == 1 && !two) break;
+            const int i = ii[r];
+            const float rn = fmaxf(sqrtf(ss[r]), kEpsNorm);
+            if (lane < dout) st.y[(long long)(r0 + i) * dout + lane] = vv[r] / rn;
+            if (lane == 0) {
+              st.rnorm[r0 + i] = rn;
+              const float inv = 1.f / rn;                 // sum relu(y) = sum relu(v) / rn (rn > 0)
+              s_rs[i] = s1[r] * inv;
+              s_rs[mr + i] = s2[r] * inv * inv;
+            }
+          }
+        }
+        if (stats) {
+          __syncthreads();
+          reduce_row_stats(p.tl, g0, g1, r0, N, mr, s_rs, s_st);
+        }
+      }
+      g0 = g1;
+    }
+  }
+  __syncthreads();
+  if (stats)
+    for (int n = tid; n < 2 * N; n += blockDim.x)
+      if (s_st[n] != 0.f) atomicAdd(&st.sums_out[n], (double)s_st[n]);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
 // pooling forward / backward
 // ------------------------------------------------------------------------------------------------------------------
+constexpr int kPoolThreads = 512;
 struct PoolDims {
-  int ldF, ldFa, ldK, Fa, F, K;
+  int ldF, ldFa, ldK, Fa, F, K, gw;
 };
 __host__ __device__ inline PoolDims pool_dims(const gp_pk_pool_args& p) {
   PoolDims d;
   d.F = p.z.F; d.Fa = p.za.F; d.K = p.K;
   d.ldF = r4(d.F); d.ldFa = r4(d.Fa); d.ldK = r4(d.K);
+  int g = kPoolThreads / ((d.ldK >> 2) * (d.ldFa >> 2));
+  d.gw = g < 1 ? 1 : (g > 4 ? 4 : g);
   return d;
 }
-template <class C>
-inline void pool_carve(const gp_pk_pool_args& p, const PoolDims& d, bool bwd, C& c) {
+static size_t pool_smem(const gp_pk_pool_args& p, const PoolDims& d, bool bwd) {
+  Count c;
   const int mr = p.tl.max_rows;
-  c.take(mr * d.ldF);        // Z
-  c.take(mr * d.ldFa);       // Za
-  c.take(mr * d.ldK);        // S
-  c.take(mr * d.ldK);        // A^T S   (fwd: T^T; bwd)
-  c.take(mr);                // gs
-  c.take(mr);                // gid
-  c.take((p.z.L + p.za.L) * 2 * p.N);   // BatchNorm of every slot
+  c.take(mr * d.ldF); c.take(mr * d.ldFa); c.take(mr * d.ldK); c.take(mr * d.ldK); c.take(mr); c.take(mr);
+  c.take((p.z.L + p.za.L) * 2 * p.N);
   if (!bwd) {
-    c.take(d.ldFa * d.ldK);  // Wp^T [Fa x ldK]
-    c.take(d.ldK);           // bp
+    c.take(d.ldFa * d.ldK); c.take(d.ldK);
   } else {
-    c.take(mr * d.ldK);      // A S
-    c.take(mr * d.ldK);      // dS -> dT
-    c.take(d.ldK * d.ldFa);  // Wp [K x ldFa]
-    c.take(d.ldK * d.ldF);   // dX' of the current graph
-    c.take(d.ldK * d.ldK);   // dA' of the current graph
-    c.take(d.ldK * d.ldFa);  // dWp accumulator
-    c.take(d.ldK);           // dbp accumulator
+    c.take(mr * d.ldK); c.take(mr * d.ldK); c.take(d.ldK * d.ldFa); c.take(d.gw * d.ldK * d.ldFa); c.take(d.ldK);
   }
+  return c.n * sizeof(float);
 }
 
 __device__ void concat_stats(const gp_pk_concat& z, const float* cnt_pad, int N, int B, float* s_bn) {
@@ -804,7 +1083,7 @@ __device__ void concat_load(const gp_pk_concat& z, int N, int r0, int nt, const 
   }
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kPoolThreads)
 pool_fwd_kernel(const gp_pk_pool_args p) {
   extern __shared__ __align__(16) float sm[];
   const PoolDims dm = pool_dims(p);
@@ -828,114 +1107,115 @@ pool_fwd_kernel(const gp_pk_pool_args p) {
   for (int k = tid; k < ldK; k += blockDim.x) s_bp[k] = (p.bp && k < K) ? p.bp[k] : 0.f;
   concat_stats(p.z, p.cnt_pad, N, p.tl.B, s_bn);
   concat_stats(p.za, p.cnt_pad, N, p.tl.B, s_bna);
-  __syncthreads();
   const int ntiles = t_count(p.tl);
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    int g0, g1;
-    t_graphs(p.tl, tile, g0, g1);
-    const int r0 = t_row0(p.tl, g0);
-    const int nt = (g1 > g0 ? t_row0(p.tl, g1) : r0) - r0;
-    __syncthreads();
-    // graphs of the tile without rows still own their (all-zero) outputs
-    if (nt > 0) row_map(p.tl, g0, g1, r0, nt, s_gs, s_gid);
-    __syncthreads();
-    if (nt > 0) {
-      concat_load(p.z, N, r0, nt, s_gs, s_gid, s_bn, bZ, ldF);
-      concat_load(p.za, N, r0, nt, s_gs, s_gid, s_bna, bZa, ldFa);
-    }
-    __syncthreads();
-    if (nt > 0) {
-      float* sp = bS;
-      const float* bb = s_bp;
-      gemm_nn(bZa, ldFa, s_wpt, ldK, nt, ldK >> 2, ldFa >> 2, [=](int m, int n, float a) { sp[m * ldK + n] = a + bb[n]; });
-    }
-    __syncthreads();
-    for (int i = wid; i < nt; i += nw) {                       // softmax over the K clusters
-      float* s = bS + i * ldK;
-      float mx = -INFINITY;
-      for (int k = lane; k < K; k += 32) mx = fmaxf(mx, s[k]);
-      mx = warp_max(mx);
-      float sum = 0.f;
-      for (int k = lane; k < K; k += 32) {
-        const float e = expf(s[k] - mx);
-        s[k] = e;
-        sum += e;
+    int G0, G1;
+    t_graphs(p.tl, tile, G0, G1);
+    for (int g0 = G0; g0 < G1;) {
+      const int g1 = sub_end(p.tl, g0, G1);
+      const int r0 = t_row0(p.tl, g0), nt = t_row0(p.tl, g1) - r0;
+      __syncthreads();
+      if (nt > 0) row_map(p.tl, g0, g1, r0, nt, s_gs, s_gid);      // graphs without rows still own (all-zero) outputs
+      __syncthreads();
+      if (nt > 0) {
+        concat_load(p.z, N, r0, nt, s_gs, s_gid, s_bn, bZ, ldF);
+        concat_load(p.za, N, r0, nt, s_gs, s_gid, s_bna, bZa, ldFa);
       }
-      sum = warp_sum(sum);
-      float* so = p.S + ((long long)s_gid[i] * N + (i - s_gs[i])) * K;
-      for (int k = lane; k < ldK; k += 32) {
-        const float v = k < K ? s[k] / sum : 0.f;
-        s[k] = v;
-        if (k < K) so[k] = v;
+      __syncthreads();
+      if (nt > 0) {
+        float* sp = bS;
+        const float* bb = s_bp;
+        gemm_nn(bZa, ldFa, s_wpt, ldK, nt, ldK >> 2, ldFa >> 2, [=](int m, int n, float a) { sp[m * ldK + n] = a + bb[n]; });
       }
-    }
-    for (int g = g0; g < g1; ++g) {                            // S rows of pad nodes are zero (mask, :1275)
-      const int n = t_row0(p.tl, g + 1) - t_row0(p.tl, g);
-      float* so = p.S + ((long long)g * N + n) * K;
-      for (int idx = tid; idx < (N - n) * K; idx += blockDim.x) so[idx] = 0.f;
-    }
-    __syncthreads();
-    if (nt > 0) gather(p.adj_in, p.tl.nfix, r0, nt, s_gs, s_gid, bS, ldK, bT);    // (A^T S)[j][k] = T[k][j]
-    // max readout over the graph's rows; with pad rows (zeros after the mask) a negative maximum loses to 0
-    const int ng = g1 - g0;
-    for (int idx = tid; idx < ng * F; idx += blockDim.x) {
-      const int gl = idx / F, f = idx - gl * F, g = g0 + gl;
-      const int rs = t_row0(p.tl, g) - r0, n = t_row0(p.tl, g + 1) - r0 - rs;
-      float best = -INFINITY;
-      int arg = -1;
-      for (int i = 0; i < n; ++i) {
-        const float v = bZ[(rs + i) * ldF + f];
-        if (v > best) { best = v; arg = i; }
-      }
-      if (n < N && !(best >= 0.f)) { best = 0.f; arg = -1; }
-      p.out[(long long)g * p.ldo + f] = best;
-      p.arg[(long long)g * p.ldo + f] = arg;
-    }
-    __syncthreads();
-    // X'[g] = S^T Z  and  A'[g] = (A^T S)^T S, 4x4 blocks over (graph, k, f)
-    {
-      const int K4 = ldK >> 2, F4 = ldF >> 2;
-      const int per = K4 * (F4 + K4);
-      for (int item = tid; item < ng * per; item += blockDim.x) {
-        const int gl = item / per, blk = item - gl * per, g = g0 + gl;
-        const int rs = t_row0(p.tl, g) - r0, re = t_row0(p.tl, g + 1) - r0;
-        const bool isx = blk < K4 * F4;
-        const int b2 = isx ? blk : blk - K4 * F4;
-        const int nb4 = isx ? F4 : K4;
-        const int i = b2 / nb4, j = b2 - i * nb4;
-        const float* A = isx ? bS : bT;
-        const float* Bm = isx ? bZ : bS;
-        const int ldb = isx ? ldF : ldK;
-        float acc[4][4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
-        for (int r = rs; r < re; ++r) {
-          const float4 a = *reinterpret_cast<const float4*>(A + r * ldK + 4 * i);
-          const float4 b = *reinterpret_cast<const float4*>(Bm + r * ldb + 4 * j);
-          const float av[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-          for (int rr = 0; rr < 4; ++rr) {
-            acc[rr][0] = fmaf(av[rr], b.x, acc[rr][0]);
-            acc[rr][1] = fmaf(av[rr], b.y, acc[rr][1]);
-            acc[rr][2] = fmaf(av[rr], b.z, acc[rr][2]);
-            acc[rr][3] = fmaf(av[rr], b.w, acc[rr][3]);
-          }
+      __syncthreads();
+      for (int i = wid; i < nt; i += nw) {                       // softmax over the K clusters
+        float* s = bS + i * ldK;
+        float mx = -INFINITY;
+        for (int k = lane; k < K; k += 32) mx = fmaxf(mx, s[k]);
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int k = lane; k < K; k += 32) {
+          const float e = expf(s[k] - mx);
+          s[k] = e;
+          sum += e;
         }
-        const int ncol = isx ? F : K;
-        float* o = isx ? p.xp + (long long)g * K * F : p.ap + (long long)g * K * K;
-#pragma unroll
-        for (int rr = 0; rr < 4; ++rr)
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc)
-            if (4 * i + rr < K && 4 * j + cc < ncol) o[(4 * i + rr) * ncol + 4 * j + cc] = acc[rr][cc];
+        sum = warp_sum(sum);
+        float* so = p.S + ((long long)s_gid[i] * N + (i - s_gs[i])) * K;
+        for (int k = lane; k < ldK; k += 32) {
+          const float v = k < K ? s[k] / sum : 0.f;
+          s[k] = v;
+          if (k < K) so[k] = v;
+        }
       }
+      for (int g = g0; g < g1; ++g) {                            // S rows of pad nodes are zero (mask, :1275)
+        const int n = t_row0(p.tl, g + 1) - t_row0(p.tl, g);
+        float* so = p.S + ((long long)g * N + n) * K;
+        for (int idx = tid; idx < (N - n) * K; idx += blockDim.x) so[idx] = 0.f;
+      }
+      __syncthreads();
+      if (nt > 0) gather4(p.adj_in, p.tl.nfix, r0, nt, s_gs, s_gid, bS, ldK, bT);    // (A^T S)[j][k] = T[k][j]
+      // max readout over the graph's rows; with pad rows (zeros after the mask) a negative maximum loses to 0
+      const int ng = g1 - g0;
+      for (int idx = tid; idx < ng * F; idx += blockDim.x) {
+        const int gl = idx / F, f = idx - gl * F, g = g0 + gl;
+        const int rs = t_row0(p.tl, g) - r0, n = t_row0(p.tl, g + 1) - r0 - rs;
+        float best = -INFINITY;
+        int arg = -1;
+        for (int i = 0; i < n; ++i) {
+          const float v = bZ[(rs + i) * ldF + f];
+          if (v > best) { best = v; arg = i; }
+        }
+        if (n < N && !(best >= 0.f)) { best = 0.f; arg = -1; }
+        p.out[(long long)g * p.ldo + f] = best;
+        p.arg[(long long)g * p.ldo + f] = arg;
+      }
+      __syncthreads();
+      // X'[g] = S^T Z  and  A'[g] = (A^T S)^T S, 4x4 blocks over (graph, k, f)
+      {
+        const int K4 = ldK >> 2, F4 = ldF >> 2;
+        const int per = K4 * (F4 + K4);
+        for (int item = tid; item < ng * per; item += blockDim.x) {
+          const int gl = item / per, blk = item - gl * per, g = g0 + gl;
+          const int rs = t_row0(p.tl, g) - r0, re = t_row0(p.tl, g + 1) - r0;
+          const bool isx = blk < K4 * F4;
+          const int b2 = isx ? blk : blk - K4 * F4;
+          const int nb4 = isx ? F4 : K4;
+          const int i = b2 / nb4, j = b2 - i * nb4;
+          const float* A = isx ? bS : bT;
+          const float* Bm = isx ? bZ : bS;
+          const int ldb = isx ? ldF : ldK;
+          float acc[4][4];
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+          for (int r = rs; r < re; ++r) {
+            const float4 a = *reinterpret_cast<const float4*>(A + r * ldK + 4 * i);
+            const float4 b = *reinterpret_cast<const float4*>(Bm + r * ldb + 4 * j);
+            const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+              acc[rr][0] = fmaf(av[rr], b.x, acc[rr][0]);
+              acc[rr][1] = fmaf(av[rr], b.y, acc[rr][1]);
+              acc[rr][2] = fmaf(av[rr], b.z, acc[rr][2]);
+              acc[rr][3] = fmaf(av[rr], b.w, acc[rr][3]);
+            }
+          }
+          const int ncol = isx ? F : K;
+          float* o = isx ? p.xp + (long long)g * K * F : p.ap + (long long)g * K * K;
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc)
+              if (4 * i + rr < K && 4 * j + cc < ncol) o[(4 * i + rr) * ncol + 4 * j + cc] = acc[rr][cc];
+        }
+      }
+      g0 = g1;
     }
   }
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kPoolThreads)
 pool_bwd_kernel(const gp_pk_pool_args p) {
   extern __shared__ __align__(16) float sm[];
   const PoolDims dm = pool_dims(p);
@@ -952,113 +1232,112 @@ pool_bwd_kernel(const gp_pk_pool_args p) {
   float* bAS = cv.take(mr * ldK);
   float* bD = cv.take(mr * ldK);
   float* s_wp = cv.take(ldK * ldFa);
-  float* s_dxp = cv.take(ldK * ldF);
-  float* s_dap = cv.take(ldK * ldK);
-  float* s_dwp = cv.take(ldK * ldFa);
+  float* s_dwp = cv.take(dm.gw * ldK * ldFa);
   float* s_dbp = cv.take(ldK);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
   for (int idx = tid; idx < ldK * ldFa; idx += blockDim.x) {
     const int k = idx / ldFa, f = idx - k * ldFa;
     s_wp[idx] = (k < K && f < Fa) ? p.Wp[(long long)k * Fa + f] : 0.f;
-    s_dwp[idx] = 0.f;
   }
+  for (int idx = tid; idx < dm.gw * ldK * ldFa; idx += blockDim.x) s_dwp[idx] = 0.f;
   for (int k = tid; k < ldK; k += blockDim.x) s_dbp[k] = 0.f;
   concat_stats(p.z, p.cnt_pad, N, p.tl.B, s_bn);
   concat_stats(p.za, p.cnt_pad, N, p.tl.B, s_bna);
-  __syncthreads();
+  float dbacc[4] = {0.f, 0.f, 0.f, 0.f};
   const int ntiles = t_count(p.tl);
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    int g0, g1;
-    t_graphs(p.tl, tile, g0, g1);
-    const int r0 = t_row0(p.tl, g0);
-    const int nt = (g1 > g0 ? t_row0(p.tl, g1) : r0) - r0;
-    if (nt <= 0) continue;
-    __syncthreads();
-    row_map(p.tl, g0, g1, r0, nt, s_gs, s_gid);
-    __syncthreads();
-    concat_load(p.z, N, r0, nt, s_gs, s_gid, s_bn, bZ, ldF);
-    concat_load(p.za, N, r0, nt, s_gs, s_gid, s_bna, bZa, ldFa);
-    for (int idx = tid; idx < nt * ldK; idx += blockDim.x) {
-      const int i = idx / ldK, k = idx - i * ldK;
-      bS[idx] = k < K ? p.S[((long long)s_gid[i] * N + (i - s_gs[i])) * K + k] : 0.f;
-    }
-    __syncthreads();
-    gather(p.adj, p.tl.nfix, r0, nt, s_gs, s_gid, bS, ldK, bAS);
-    gather(p.adj_in, p.tl.nfix, r0, nt, s_gs, s_gid, bS, ldK, bAtS);
-    for (int g = g0; g < g1; ++g) {
-      const int rs = t_row0(p.tl, g) - r0, n = t_row0(p.tl, g + 1) - r0 - rs;
-      if (n <= 0) continue;
-      __syncthreads();
-      for (int idx = tid; idx < ldK * ldF; idx += blockDim.x) {
-        const int k = idx / ldF, f = idx - k * ldF;
-        s_dxp[idx] = (k < K && f < F) ? p.dxp[((long long)g * K + k) * F + f] : 0.f;
-      }
-      for (int idx = tid; idx < ldK * ldK; idx += blockDim.x) {
-        const int k = idx / ldK, k2 = idx - k * ldK;
-        s_dap[idx] = (k < K && k2 < K) ? p.dap[((long long)g * K + k) * K + k2] : 0.f;
-      }
-      __syncthreads();
-      // dS[i][k] = <Z[i], dX'[k]> + <AS[i], dA'[k]> + sum_k2 AtS[i][k2] dA'[k2][k] + dS_ext
-      for (int idx = tid; idx < n * ldK; idx += blockDim.x) {
-        const int il = idx / ldK, k = idx - il * ldK, i = rs + il;
-        float acc = 0.f;
-        if (k < K) {
-          const float* z = bZ + i * ldF;
-          const float* dx = s_dxp + k * ldF;
-          for (int f = 0; f < ldF; f += 4) {
-            const float4 a = *reinterpret_cast<const float4*>(z + f);
-            const float4 b = *reinterpret_cast<const float4*>(dx + f);
-            acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
-          }
-          const float* as = bAS + i * ldK;
-          const float* ats = bAtS + i * ldK;
-          for (int k2 = 0; k2 < K; ++k2) {
-            acc = fmaf(as[k2], s_dap[k * ldK + k2], acc);
-            acc = fmaf(ats[k2], s_dap[k2 * ldK + k], acc);
-          }
-          if (p.dS_ext) acc += p.dS_ext[((long long)g * N + il) * K + k];
+    int G0, G1;
+    t_graphs(p.tl, tile, G0, G1);
+    for (int g0 = G0; g0 < G1;) {
+      const int g1 = sub_end(p.tl, g0, G1);
+      const int r0 = t_row0(p.tl, g0), nt = t_row0(p.tl, g1) - r0;
+      if (nt > 0) {
+        __syncthreads();
+        row_map(p.tl, g0, g1, r0, nt, s_gs, s_gid);
+        __syncthreads();
+        concat_load(p.z, N, r0, nt, s_gs, s_gid, s_bn, bZ, ldF);
+        concat_load(p.za, N, r0, nt, s_gs, s_gid, s_bna, bZa, ldFa);
+        for (int idx = tid; idx < nt * ldK; idx += blockDim.x) {
+          const int i = idx / ldK, k = idx - i * ldK;
+          bS[idx] = k < K ? p.S[((long long)s_gid[i] * N + (i - s_gs[i])) * K + k] : 0.f;
         }
-        bD[i * ldK + k] = acc;
+        __syncthreads();
+        gather4(p.adj, p.tl.nfix, r0, nt, s_gs, s_gid, bS, ldK, bAS);
+        gather4(p.adj_in, p.tl.nfix, r0, nt, s_gs, s_gid, bS, ldK, bAtS);
+        // gz[i][f] = sum_k S[i][k] dX'[g][k][f] + readout scatter   (dX' read through L1: each element serves n_g rows)
+        for (int idx = tid; idx < nt * F; idx += blockDim.x) {
+          const int i = idx / F, f = idx - i * F;
+          const int g = s_gid[i], il = i - s_gs[i];
+          const float* s = bS + i * ldK;
+          const float* dx = p.dxp + (long long)g * K * F + f;
+          float acc = 0.f;
+          for (int k = 0; k < K; ++k) acc = fmaf(s[k], __ldg(dx + (long long)k * F), acc);
+          const long long o = (long long)g * p.ldo + f;
+          if (p.arg[o] == il) acc += p.dout[o];
+          p.gz[(long long)(r0 + i) * F + f] = acc;
+        }
+        __syncthreads();
+        // dS[i][k] = <Z[i], dX'[k]> + <AS[i], dA'[k]> + sum_k2 AtS[i][k2] dA'[k2][k] + dS_ext
+        for (int idx = tid; idx < nt * ldK; idx += blockDim.x) {
+          const int i = idx / ldK, k = idx - i * ldK;
+          float acc = 0.f;
+          if (k < K) {
+            const int g = s_gid[i], il = i - s_gs[i];
+            const float* z = bZ + i * ldF;
+            const float* dx = p.dxp + ((long long)g * K + k) * F;
+            for (int f = 0; f < F; ++f) acc = fmaf(z[f], __ldg(dx + f), acc);
+            const float* as = bAS + i * ldK;
+            const float* ats = bAtS + i * ldK;
+            const float* da = p.dap + (long long)g * K * K;
+            for (int k2 = 0; k2 < K; ++k2) {
+              acc = fmaf(as[k2], __ldg(da + k * K + k2), acc);
+              acc = fmaf(ats[k2], __ldg(da + k2 * K + k), acc);
+            }
+            if (p.dS_ext) acc += p.dS_ext[((long long)g * N + il) * K + k];
+          }
+          bD[idx] = acc;
+        }
+        __syncthreads();
+        for (int i = wid; i < nt; i += nw) {                      // softmax backward: dT = s (dS - <dS, s>)
+          float* d = bD + i * ldK;
+          const float* s = bS + i * ldK;
+          float pr = 0.f;
+          for (int k = lane; k < K; k += 32) pr = fmaf(d[k], s[k], pr);
+          pr = warp_sum(pr);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int k = lane + 32 * t;
+            if (k < ldK) {
+              const float v = k < K ? s[k] * (d[k] - pr) : 0.f;
+              d[k] = v;
+              dbacc[t] += v;
+            }
+          }
+        }
+        __syncthreads();
+        gemm_tn_acc(bD, ldK, bZa, ldFa, ldK >> 2, ldFa >> 2, 0, nt, s_dwp, ldFa, dm.gw);
+        {
+          float* gza = p.gza;
+          gemm_nn(bD, ldK, s_wp, ldFa, nt, ldFa >> 2, ldK >> 2, [=](int m, int n, float a) {
+            if (n < Fa) gza[(long long)(r0 + m) * Fa + n] = a;
+          });
+        }
       }
-      // gz[i][f] = sum_k S[i][k] dX'[k][f] + readout scatter
-      for (int idx = tid; idx < n * F; idx += blockDim.x) {
-        const int il = idx / F, f = idx - il * F, i = rs + il;
-        const float* s = bS + i * ldK;
-        float acc = 0.f;
-        for (int k = 0; k < K; ++k) acc = fmaf(s[k], s_dxp[k * ldF + f], acc);
-        const long long o = (long long)g * p.ldo + f;
-        if (p.arg[o] == il) acc += p.dout[o];
-        p.gz[(long long)(r0 + i) * F + f] = acc;
-      }
+      g0 = g1;
     }
-    __syncthreads();
-    for (int i = wid; i < nt; i += nw) {                        // softmax backward: dT = s (dS - <dS, s>)
-      float* d = bD + i * ldK;
-      const float* s = bS + i * ldK;
-      float pr = 0.f;
-      for (int k = lane; k < K; k += 32) pr = fmaf(d[k], s[k], pr);
-      pr = warp_sum(pr);
-      for (int k = lane; k < ldK; k += 32) d[k] = k < K ? s[k] * (d[k] - pr) : 0.f;
-    }
-    __syncthreads();
-    gemm_tn_acc(bD, ldK, bZa, ldFa, ldK >> 2, ldFa >> 2, 0, nt, s_dwp, ldFa, 1);
-    if (p.dbp)
-      for (int k = tid; k < K; k += blockDim.x) {
-        float acc = 0.f;
-        for (int i = 0; i < nt; ++i) acc += bD[i * ldK + k];
-        s_dbp[k] += acc;
-      }
-    {
-      float* gza = p.gza;
-      gemm_nn(bD, ldK, s_wp, ldFa, nt, ldFa >> 2, ldK >> 2, [=](int m, int n, float a) {
-        if (n < Fa) gza[(long long)(r0 + m) * Fa + n] = a;
-      });
+  }
+  if (p.dbp) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int k = lane + 32 * t;
+      if (k < K && dbacc[t] != 0.f) atomicAdd(&s_dbp[k], dbacc[t]);
     }
   }
   __syncthreads();
   for (int idx = tid; idx < K * Fa; idx += blockDim.x) {
     const int k = idx / Fa, f = idx - k * Fa;
-    const float v = s_dwp[k * ldFa + f];
+    float v = 0.f;
+    for (int g = 0; g < dm.gw; ++g) v += s_dwp[g * ldK * ldFa + k * ldFa + f];
     if (v != 0.f) atomicAdd(&p.dWp[idx], v);
   }
   if (p.dbp)
@@ -1199,12 +1478,14 @@ __global__ void link_finalize_kernel(const double* sum, double scale, const floa
   if (total) *total = (float)((base ? (double)*base : 0.0) + l);
 }
 
-static int grid_for(int smem_bytes, int want) {
-  // persistent CTAs: as many as fit per SM (228 KB of shared memory per SM, 1 KB reserved per CTA), at most `want`
+static int grid_for(int smem_bytes, int want, int ny = 1, int reg_limit = 8) {
+  // persistent CTAs, ONE wave: as many as fit per SM (228 KB of shared memory per SM, 1 KB reserved per CTA; at most
+  // `reg_limit` by registers), shared between the `ny` slices of the grid's y dimension, at most `want`
   int per_sm = (int)(228 * 1024 / (smem_bytes + 1024));
-  per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
-  const int g = kNumSMs * per_sm;
-  return g < want ? g : (want < 1 ? 1 : want);
+  per_sm = per_sm < 1 ? 1 : (per_sm > reg_limit ? reg_limit : per_sm);
+  int g = (kNumSMs * per_sm) / ny;
+  g = g < want ? g : want;
+  return g < 1 ? 1 : g;
 }
 
 // dynamic shared memory opt-in, once per device and kernel (not a stream operation: safe under graph capture too)
@@ -1255,6 +1536,7 @@ static int check_tiling(const gp_pk_tiling& t, int N) {
   GP_REQUIRE((t.rowptr != nullptr) == (t.tile_g0 != nullptr) && (t.rowptr != nullptr) == (t.ntiles != nullptr),
              "pk: ragged tiling needs rowptr, tile_g0 and ntiles");
   GP_REQUIRE(t.rowptr != nullptr || (t.nfix > 0 && t.nfix <= N && t.gpt * t.nfix <= t.max_rows), "pk: uniform tiling");
+  GP_REQUIRE(t.rowptr == nullptr || t.max_rows >= N, "pk: max_rows must hold one whole graph");
   GP_REQUIRE(N > 0 && N <= kMaxN, "pk: N = %d (<= %d)", N, kMaxN);
   return GP_OK;
 }
@@ -1273,12 +1555,19 @@ extern "C" int gp_pk_layer_fwd(const gp_pk_layer_fwd_args* a, gp_stream_t stream
     GP_REQUIRE(st.in.y && st.W && st.y && st.rnorm && st.in.d > 0 && st.dout > 0 && st.in.d <= 512 && st.dout <= 512,
                "pk_layer_fwd: stack %d", s);
   }
-  const FwdDims dm = fwd_dims(*a);
-  Count c;
-  fwd_carve(*a, dm, c);
-  const size_t smem = c.n * sizeof(float);
+  bool narrow = true;                       // every stack at most 32 wide: one warp per row, weights in registers
+  for (int s = 0; s < a->ns; ++s) narrow = narrow && a->s[s].in.d <= 32 && a->s[s].dout <= 32;
+  if (narrow) {
+    const size_t smem = fwd_row_smem(*a);
+    GP_PK_SMEM(layer_fwd_row_kernel, smem);
+    const int g = grid_for((int)smem, tiles_upper(a->tl), a->ns, 3);
+    layer_fwd_row_kernel<<<dim3(g, a->ns), kThreads, smem, S(stream)>>>(*a);
+    GP_LAUNCHED();
+    return GP_OK;
+  }
+  const size_t smem = fwd_smem(*a);
   GP_PK_SMEM(layer_fwd_kernel, smem);
-  layer_fwd_kernel<<<grid_for((int)smem, tiles_upper(a->tl)), kThreads, smem, S(stream)>>>(*a);
+  layer_fwd_kernel<<<dim3(grid_for((int)smem, tiles_upper(a->tl), a->ns, 3), a->ns), kThreads, smem, S(stream)>>>(*a);
   GP_LAUNCHED();
   return GP_OK;
 }
@@ -1300,12 +1589,9 @@ extern "C" int gp_pk_layer_bwd(const gp_pk_layer_bwd_args* a, gp_stream_t stream
     }
     GP_REQUIRE(st.dadj == nullptr || a->tl.rowptr == nullptr, "pk_layer_bwd: dadj needs the dense level");
   }
-  const BwdDims dm = bwd_dims(*a);
-  Count c;
-  bwd_carve(*a, dm, c);
-  const size_t smem = c.n * sizeof(float);
+  const size_t smem = bwd_smem(*a);
   GP_PK_SMEM(layer_bwd_kernel, smem);
-  layer_bwd_kernel<<<grid_for((int)smem, tiles_upper(a->tl)), kThreads, smem, S(stream)>>>(*a);
+  layer_bwd_kernel<<<dim3(grid_for((int)smem, tiles_upper(a->tl), a->ns, 3), a->ns), kThreads, smem, S(stream)>>>(*a);
   GP_LAUNCHED();
   return GP_OK;
 }
@@ -1330,11 +1616,9 @@ static int check_pool(const gp_pk_pool_args* a, bool bwd) {
 extern "C" int gp_pk_pool_fwd(const gp_pk_pool_args* a, gp_stream_t stream) {
   GP_TRY(check_pool(a, false));
   const PoolDims dm = pool_dims(*a);
-  Count c;
-  pool_carve(*a, dm, false, c);
-  const size_t smem = c.n * sizeof(float);
+  const size_t smem = pool_smem(*a, dm, false);
   GP_PK_SMEM(pool_fwd_kernel, smem);
-  pool_fwd_kernel<<<grid_for((int)smem, tiles_upper(a->tl)), kThreads, smem, S(stream)>>>(*a);
+  pool_fwd_kernel<<<grid_for((int)smem, tiles_upper(a->tl), 1, 1), kPoolThreads, smem, S(stream)>>>(*a);
   GP_LAUNCHED();
   return GP_OK;
 }
@@ -1342,11 +1626,9 @@ extern "C" int gp_pk_pool_fwd(const gp_pk_pool_args* a, gp_stream_t stream) {
 extern "C" int gp_pk_pool_bwd(const gp_pk_pool_args* a, gp_stream_t stream) {
   GP_TRY(check_pool(a, true));
   const PoolDims dm = pool_dims(*a);
-  Count c;
-  pool_carve(*a, dm, true, c);
-  const size_t smem = c.n * sizeof(float);
+  const size_t smem = pool_smem(*a, dm, true);
   GP_PK_SMEM(pool_bwd_kernel, smem);
-  pool_bwd_kernel<<<grid_for((int)smem, tiles_upper(a->tl)), kThreads, smem, S(stream)>>>(*a);
+  pool_bwd_kernel<<<grid_for((int)smem, tiles_upper(a->tl), 1, 1), kPoolThreads, smem, S(stream)>>>(*a);
   GP_LAUNCHED();
   return GP_OK;
 }

@@ -19,8 +19,8 @@ from ._lib import (GpPkAdj, GpPkConcat, GpPkGrad, GpPkLayerBwdArgs, GpPkLayerFwd
                    GpPkTiling, PK_MAX_LAYERS, call)
 
 MAX_N = 128           # kMaxN in packed.cu
-W_LAYER = 64          # packed rows per tile window of the layer kernels (a tile holds at most W - 1 + N rows)
-W_POOL = 32           # ... of the pooling kernels (they keep both concats of a tile in shared memory)
+W_LAYER = 96          # packed rows per tile WINDOW (graphs whose first row falls into it); the kernels walk a window in
+W_POOL = 96           # runs of whole graphs of at most max(N, W) rows, which is what sizes their shared memory
 POST_ROWS = 64        # rows per tile at the pooled level (whole graphs of K rows)
 
 
@@ -165,8 +165,8 @@ def forward(plan, x, adj, assign_x, params, wb):
          info[1].data_ptr(), ent[1].data_ptr(), meta.data_ptr() + 12, C.c_longlong(cap), st)
     a_out = GpPkAdj(info[0].data_ptr(), ent[0].data_ptr(), None, 0)
     a_in = GpPkAdj(info[1].data_ptr(), ent[1].data_ptr(), None, 0)
-    tl1 = GpPkTiling(rowptr.data_ptr(), tiles1.data_ptr(), meta.data_ptr() + 4, B, N, t1max, W_LAYER - 1 + N)
-    tl2 = GpPkTiling(rowptr.data_ptr(), tiles2.data_ptr(), meta.data_ptr() + 8, B, N, t2max, W_POOL - 1 + N)
+    tl1 = GpPkTiling(rowptr.data_ptr(), tiles1.data_ptr(), meta.data_ptr() + 4, B, N, t1max, max(N, W_LAYER))
+    tl2 = GpPkTiling(rowptr.data_ptr(), tiles2.data_ptr(), meta.data_ptr() + 8, B, N, t2max, max(N, W_POOL))
 
     # ---- level 0: embedding and assignment GCN in lock-step
     se = _Stack(ws, rows, we, be, _src(x.data_ptr(), D, D, 1), dbl, 0, N)
