@@ -313,6 +313,7 @@ def main():
     # and every step's loss is read back inside the timed region.
     e2e = None
     e2e_u8 = None
+    e2e_edges = None
     if not args.no_e2e:
         def run_e2e(adj_host_dtype):
             hx, hl = x.cpu().pin_memory(), label.cpu().pin_memory()
@@ -417,6 +418,49 @@ def main():
                             'cross PCIe as fp32; pack of step i+2, H2D of step i+1 and compute of step i overlap'
                             % (Bp, B, threads)}
 
+        def run_e2e_edges():
+            """feed.EdgeListFeed (the plugin's own feed API): every step the host hands over the batch's
+            edge lists (pinned int32) and features; gp_adj_from_edges builds the bf16 operand on the device."""
+            from graph_pooling_b200 import feed
+            Nn = cfg['N']
+            au = torch.triu(adj, diagonal=1)
+            eptr_l, chunks = [0], []
+            for b in range(B):                                   # per graph: bounded temporaries
+                nz = au[b].nonzero().to(torch.int32)
+                chunks.append(nz)
+                eptr_l.append(eptr_l[-1] + int(nz.shape[0]))
+            del au
+            he = torch.cat(chunks).cpu().contiguous().pin_memory()
+            hp = torch.tensor(eptr_l, dtype=torch.int32).pin_memory()
+            maxdeg = int(max(np.diff(np.asarray(eptr_l)))) if B else 1
+            hx, hl = x.cpu().pin_memory(), label.cpu().pin_memory()
+            fd = feed.EdgeListFeed(B, Nn, dev, max_edges=max(int(he.shape[0]), 1))
+            xd = [torch.empty_like(x) for _ in range(2)]
+            ld_ = [torch.empty_like(label) for _ in range(2)]
+            st = {'i': 0}
+            fd.copy(0, he, hp, maxdeg, [(xd[0], hx), (ld_[0], hl)])
+
+            def estep():
+                i = st['i']
+                st['i'] += 1
+                cur, nxt = i & 1, (i + 1) & 1
+                fd.copy(nxt, he, hp, maxdeg, [(xd[nxt], hx), (ld_[nxt], hl)])     # H2D of step i+1
+                pa = fd.prepared(cur)
+                loss = step(xd[cur], pa, ld_[cur])
+                fd.consumed(cur)
+                return float(loss.item())
+
+            for _ in range(min(args.warmup, 3)):
+                estep()
+            ems = timed(estep, args.steps) / args.steps
+            torch.cuda.synchronize()
+            h2d = hx.numel() * 4 + hl.numel() * 8 + nb.nbytes + he.numel() * 4 + hp.numel() * 4
+            return {'value': world * B / (ems * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
+                    'd2h_bytes_per_step': 4, 'ms_per_step': ems, 'edges_per_step': int(he.shape[0]),
+                    'strategy': 'feed.EdgeListFeed: pinned int32 edge lists + fp32 features -> H2D -> gp_adj_from_edges',
+                    'note': 'the plugin\'s own feed API (SURVEY 8(f) N2): the adjacency crosses PCIe as 8 bytes per '
+                            'undirected edge instead of 4 N^2 bytes per graph; same step, same loss read-back'}
+
         e2e = run_e2e(torch.float32)
         e2e['note'] = ('dense fp32 adjacency from pinned host memory every step (the reference feed contract, '
                        'train.py:197-201); H2D of step i+1 overlaps step i on a copy stream')
@@ -433,6 +477,10 @@ def main():
                 hyb = run_e2e_hybrid()
             except Exception as ex:            # e.g. entries outside {0,1}: the direct copy stays the answer
                 hyb = {'error': str(ex)[:200]}
+            try:
+                e2e_edges = run_e2e_edges()
+            except Exception as ex:
+                e2e_edges = {'error': str(ex)[:200]}
             if 'value' in hyb and hyb['value'] > e2e['value']:
                 hyb['direct_fp32_copy'] = {k: e2e[k] for k in ('value', 'ms_per_step', 'h2d_bytes_per_step')}
                 e2e = hyb
@@ -706,7 +754,7 @@ def main():
                       if adj.numel() * 4 > 126e6 else 'inputs smaller than L2; not flushed',
                       'cuda_graph': bool(use_graph),
                       'parallelism': 'dp%d' % world},
-           'clocks': clocks, 'e2e': e2e, 'e2e_u8_feed': e2e_u8, 'gpu_launches': launches, 'roofline': step_roof,
+           'clocks': clocks, 'e2e': e2e, 'e2e_u8_feed': e2e_u8, 'e2e_edge_feed': e2e_edges, 'gpu_launches': launches, 'roofline': step_roof,
            'cpu_baseline': cpu, 'aten_on_b200': aten, 'enzymes_regime': enz, 'dp_check': dp_check}
     print(json.dumps(out), flush=True)
 

@@ -97,6 +97,19 @@ class PreparedAdjacency:
         self._fresh = False
         return self
 
+    def from_edges(self, edges, eptr, max_edges_per_graph, undirected=True):
+        """The whole batch from its edge lists (device int32 tensors: edges [E,2] graph-local ids, eptr [B+1]): the
+        adjacency never exists as fp32 / uint8 anywhere (gp_adj_from_edges)."""
+        B, N, _ = self.shape
+        if edges.dtype != torch.int32 or eptr.dtype != torch.int32 or not edges.is_cuda or not eptr.is_cuda:
+            raise ValueError('PreparedAdjacency.from_edges: need CUDA int32 tensors')
+        if eptr.numel() != B + 1 or not edges.is_contiguous():
+            raise ValueError('PreparedAdjacency.from_edges: eptr must have B + 1 entries, edges must be contiguous')
+        call('gp_adj_from_edges', edges.data_ptr(), eptr.data_ptr(), B, N, int(max_edges_per_graph), int(undirected),
+             self.op.ptr, self.op.ld, self.flags.data_ptr(), 0, E._stream())
+        self._fresh = False
+        return self
+
 
 def tcgemm_multi(pairs, M, N, batch, Cf=None, Cb=None, lim=None, lim_m=0, lim_n=0, alpha=1.0, beta=0.0,
                  alpha_dev=None, bias=None, relu=0, split_k=0, cond=None, cond_npairs=0, cond_alpha=1.0):
