@@ -239,6 +239,24 @@ def set_hook(h):
     _hook = h
 
 
+class _NvtxHook:
+    """GP_NVTX=1: every C-ABI call (= one fused op of the hot path) becomes an NVTX range named after its entry point,
+    so Nsight timelines / `ncu --nvtx --nvtx-include` can address the ops by name.  Off by default (no overhead)."""
+
+    def begin(self, name, args):
+        import torch
+        torch.cuda.nvtx.range_push(name)
+        return name
+
+    def end(self, tok):
+        import torch
+        torch.cuda.nvtx.range_pop()
+
+
+if os.environ.get('GP_NVTX'):
+    _hook = _NvtxHook()
+
+
 def call(name, *args):
     if _hook is None:
         check(getattr(load(), name)(*args), name)
