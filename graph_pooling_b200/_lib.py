@@ -69,17 +69,20 @@ class GpLayerBwd(C.Structure):
 PK_MAX_LAYERS = 6
 
 
+PK_ELL = 8
+
+
 class GpPkTiling(C.Structure):
-    _fields_ = [('rowptr', c_f), ('tile_g0', c_f), ('ntiles', c_f), ('B', c_i), ('nfix', c_i), ('gpt', c_i),
-                ('max_rows', c_i)]
+    _fields_ = [('rowptr', c_f), ('subs', c_f), ('nsub', c_f), ('rowmeta', c_f), ('B', c_i), ('nfix', c_i),
+                ('gpt', c_i), ('max_rows', c_i)]
 
 
 class GpPkAdj(C.Structure):
-    _fields_ = [('info', c_f), ('entries', c_f), ('dense', c_f), ('transposed', c_i)]
+    _fields_ = [('info', c_f), ('ell', c_f), ('entries', c_f), ('dense', c_f), ('transposed', c_i)]
 
 
 class GpPkSrc(C.Structure):
-    _fields_ = [('y', c_f), ('ld', c_ll), ('d', c_i), ('padded', c_i), ('sums', c_f), ('bias', c_f)]
+    _fields_ = [('y', c_f), ('ld', c_ll), ('d', c_i), ('sums', c_f), ('bias', c_f)]
 
 
 class GpPkGrad(C.Structure):
@@ -187,8 +190,9 @@ _PROTOS = {
     'gp_dropout_f32': [c_f, c_ll, c_ll, c_i, C.c_float, C.c_ulonglong, c_f, c_ll, c_f, c_ll, c_f],
     'gp_set2set_fwd': [c_f, c_ll, c_f, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f],
     'gp_set2set_bwd': [c_f, c_ll, c_f, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_f, c_f, c_ll, c_f, c_f, c_f, c_f],
-    'gp_pk_prepare': [c_f, c_i, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_f, c_f],
-    'gp_pk_build_lists': [c_f, c_f, c_f, c_i, c_i, c_f, c_f, c_f, c_f, c_f, c_ll, c_f],
+    'gp_pk_prepare': [c_f, c_i, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_f],
+    'gp_pk_build_lists': [c_f, c_f, c_f, c_i, c_i, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_ll, c_f, c_f, c_i, c_f, c_ll, c_f,
+                          c_i, c_f, c_ll, c_f],
     'gp_pk_layer_fwd': [C.POINTER(GpPkLayerFwdArgs), c_f],
     'gp_pk_layer_bwd': [C.POINTER(GpPkLayerBwdArgs), c_f],
     'gp_pk_pool_fwd': [C.POINTER(GpPkPoolArgs), c_f],

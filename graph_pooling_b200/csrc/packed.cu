@@ -26,44 +26,43 @@ constexpr int kThreads = 256;
 __host__ __device__ __forceinline__ int r4(int v) { return (v + 3) & ~3; }
 
 // ------------------------------------------------------------------------------------------------------------------
-// tiling helpers
+// runs ("sub-tiles"): groups of whole graphs with at most max_rows packed rows; one CTA processes a run at a time
 // ------------------------------------------------------------------------------------------------------------------
+struct Sub { int r0, nt, g0, g1; };
 __device__ __forceinline__ int t_row0(const gp_pk_tiling& t, int g) { return t.rowptr ? t.rowptr[g] : g * t.nfix; }
-__device__ __forceinline__ int t_count(const gp_pk_tiling& t) {
-  return t.ntiles ? *t.ntiles : (t.B + t.gpt - 1) / t.gpt;
+__device__ __forceinline__ int sub_count(const gp_pk_tiling& t) {
+  return t.subs ? *t.nsub : (t.B + t.gpt - 1) / t.gpt;
 }
-__device__ __forceinline__ void t_graphs(const gp_pk_tiling& t, int tile, int& g0, int& g1) {
-  if (t.tile_g0) {
-    g0 = t.tile_g0[tile];
-    g1 = t.tile_g0[tile + 1];
+__device__ __forceinline__ Sub sub_get(const gp_pk_tiling& t, int s) {
+  Sub r;
+  if (t.subs) {
+    const int4 v = __ldg(reinterpret_cast<const int4*>(t.subs) + s);
+    r.r0 = v.x; r.nt = v.y; r.g0 = v.z; r.g1 = v.w;
   } else {
-    g0 = tile * t.gpt;
-    g1 = min(t.B, g0 + t.gpt);
+    r.g0 = s * t.gpt;
+    r.g1 = min(t.B, r.g0 + t.gpt);
+    r.r0 = r.g0 * t.nfix;
+    r.nt = (r.g1 - r.g0) * t.nfix;
   }
+  return r;
 }
-
-// per-row maps of a tile: s_gs[i] = local row of the first row of i's graph, s_gid[i] = its graph
-__device__ __forceinline__ void row_map(const gp_pk_tiling& t, int g0, int g1, int r0, int nt, int* s_gs, int* s_gid) {
-  for (int i = threadIdx.x; i < nt; i += blockDim.x) {
-    int g;
-    if (t.rowptr) {
-      int lo = g0, hi = g1;                       // last g in [g0, g1) with rowptr[g] <= r0 + i
-      const int r = r0 + i;
-      while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (t.rowptr[mid] <= r) lo = mid; else hi = mid;
-      }
-      g = lo;
-      // graphs with zero rows share a start: take the LAST graph starting at or before r that is non-empty
-      s_gs[i] = t.rowptr[g] - r0;
+// per-row maps of a run: s_gs[i] = local row of the first row of i's graph, s_gid[i] = its graph
+__device__ __forceinline__ void load_meta(const gp_pk_tiling& t, const Sub& sb, int* s_gs, int* s_gid) {
+  for (int i = threadIdx.x; i < sb.nt; i += blockDim.x) {
+    int ni, gid;
+    if (t.rowmeta) {
+      const int2 m = __ldg(reinterpret_cast<const int2*>(t.rowmeta) + sb.r0 + i);
+      ni = m.x;
+      gid = m.y;
     } else {
-      g = g0 + i / t.nfix;
-      s_gs[i] = (g - g0) * t.nfix;
+      const int q = i / t.nfix;
+      ni = i - q * t.nfix;
+      gid = sb.g0 + q;
     }
-    s_gid[i] = g;
+    s_gs[i] = i - ni;
+    s_gid[i] = gid;
   }
 }
-
 struct Carve {
   float* p;
   __device__ float* take(int nfloats) { float* r = p; p += (nfloats + 3) & ~3; return r; }
@@ -103,54 +102,33 @@ __device__ void bn_stats(const gp_pk_src& src, const float* __restrict__ cnt_pad
 
 // rows [r0, r0+nt) of a source -> dst[i*ldd + coff + c], c < d, ReLU + BatchNorm applied when the source has sums.
 // Columns [d, dz) are written as zeros (dz = d rounded up when the slot is the last one of the destination).
-__device__ void load_rows(const gp_pk_src& src, int N, int r0, int nt, const int* s_gs, const int* s_gid,
-                          const float* s_mean, const float* s_istd, float* dst, int ldd, int coff, int dz) {
+// Four elements per thread are in flight at a time.
+__device__ void load_rows(const gp_pk_src& src, int r0, int nt, const int* s_gs, const float* s_mean,
+                          const float* s_istd, float* dst, int ldd, int coff, int dz) {
   const int d = src.d;
   const bool bn = src.sums != nullptr;
-  for (int idx = threadIdx.x; idx < nt * dz; idx += blockDim.x) {
-    const int i = idx / dz, c = idx - i * dz;
-    float v = 0.f;
-    if (c < d) {
-      const int ni = i - s_gs[i];
-      const long long row = src.padded ? ((long long)s_gid[i] * N + ni) : (long long)(r0 + i);
-      v = src.y[row * src.ld + c];
-      if (bn) v = (fmaxf(v, 0.f) - s_mean[ni]) * s_istd[ni];
+  const int total = nt * dz;
+  for (int base = threadIdx.x; base < total; base += 4 * blockDim.x) {
+    float v[4];
+    int ii[4], cc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int idx = base + j * blockDim.x;
+      ii[j] = idx / dz;
+      cc[j] = idx - ii[j] * dz;
+      v[j] = (idx < total && cc[j] < d) ? __ldg(src.y + (long long)(r0 + ii[j]) * src.ld + cc[j]) : 0.f;
     }
-    dst[i * ldd + coff + c] = v;
-  }
-}
-
-// dst[i][c] = sum_e a(i, e) * src[gs(i) + col_e][c]   (one warp per row; c < ld)
-__device__ void gather(const gp_pk_adj& a, int nfix, int r0, int nt, const int* s_gs, const int* s_gid,
-                       const float* src, int ld, float* dst) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int i = w; i < nt; i += nw) {
-    const int gs = s_gs[i], ni = i - gs;
-    int start = 0, deg = nfix;
-    const float* dn = nullptr;
-    if (a.info) {
-      const int2 inf = reinterpret_cast<const int2*>(a.info)[r0 + i];
-      start = inf.x;
-      deg = inf.y;
-    } else {
-      dn = a.dense + (long long)s_gid[i] * nfix * nfix;
-    }
-    for (int c = lane; c < ld; c += 32) {
-      float acc = 0.f;
-      for (int e = 0; e < deg; ++e) {
-        int col;
-        float val;
-        if (a.info) {
-          const int2 en = reinterpret_cast<const int2*>(a.entries)[start + e];
-          col = en.x;
-          val = __int_as_float(en.y);
-        } else {
-          col = e;
-          val = a.transposed ? dn[e * nfix + ni] : dn[ni * nfix + e];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int idx = base + j * blockDim.x;
+      if (idx < total) {
+        float x = v[j];
+        if (bn && cc[j] < d) {
+          const int ni = ii[j] - s_gs[ii[j]];
+          x = (fmaxf(x, 0.f) - s_mean[ni]) * s_istd[ni];
         }
-        acc = fmaf(val, src[(gs + col) * ld + c], acc);
+        dst[ii[j] * ldd + coff + cc[j]] = x;
       }
-      dst[i * ld + c] = acc;
     }
   }
 }
@@ -255,12 +233,35 @@ __device__ __forceinline__ float grad_at(const gp_pk_grad& g, int r0, int i, int
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// prepare: scan of the node counts, pad counts per node index, the two tilings
+// prepare: scan of the node counts, pad counts per node index, the run table
 // ------------------------------------------------------------------------------------------------------------------
+// first graph whose first row is >= target
+__device__ __forceinline__ int first_graph_at(const int32_t* rowptr, int B, int target) {
+  int lo = 0, hi = B;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (rowptr[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+// greedy split of the graphs [G0, G1) of one window into runs of at most `cap` rows; returns the number of runs and,
+// with out != nullptr, writes them
+__device__ __forceinline__ int split_window(const int32_t* rowptr, int G0, int G1, int cap, int4* out) {
+  int cnt = 0;
+  for (int g = G0; g < G1;) {
+    const int r = rowptr[g];
+    int ge = g + 1;
+    while (ge < G1 && rowptr[ge + 1] - r <= cap) ++ge;
+    if (out) out[cnt] = make_int4(r, rowptr[ge] - r, g, ge);
+    ++cnt;
+    g = ge;
+  }
+  return cnt;
+}
+
 __global__ void __launch_bounds__(1024)
-prepare_kernel(const int32_t* __restrict__ nb, int B, int N, int w1, int w2, int32_t* __restrict__ rowptr,
-               float* __restrict__ cnt_pad, int32_t* __restrict__ tiles1, int32_t* __restrict__ tiles2,
-               int32_t* __restrict__ meta) {
+prepare_kernel(const int32_t* __restrict__ nb, int B, int N, int w, int cap, int32_t* __restrict__ rowptr,
+               float* __restrict__ cnt_pad, int32_t* __restrict__ subs, int32_t* __restrict__ meta) {
   __shared__ int s_part[1024];
   __shared__ int s_hist[kMaxN + 2];
   const int tid = threadIdx.x, nth = blockDim.x;
@@ -289,8 +290,7 @@ prepare_kernel(const int32_t* __restrict__ nb, int B, int N, int w1, int w2, int
   }
   const int R = s_part[nth - 1];
   if (tid == 0) rowptr[B] = R;
-  // cnt_pad[n] = #graphs with n_b <= n
-  if (tid == 0) {
+  if (tid == 0) {                               // cnt_pad[n] = #graphs with n_b <= n
     int c = 0;
     for (int n = 0; n < N; ++n) {
       c += s_hist[n];
@@ -299,38 +299,52 @@ prepare_kernel(const int32_t* __restrict__ nb, int B, int N, int w1, int w2, int
   }
   __threadfence_block();
   __syncthreads();
-  // tile t = graphs whose first row is in [t*w, (t+1)*w): tiles[t] = lower_bound(rowptr[0..B), t*w)
-  for (int pass = 0; pass < 2; ++pass) {
-    const int w = pass ? w2 : w1;
-    int32_t* tiles = pass ? tiles2 : tiles1;
-    const int nt = (R + w - 1) / w;
-    for (int t = tid; t <= nt; t += nth) {
-      if (t == nt) { tiles[t] = B; continue; }
-      const int target = t * w;
-      int lo = 0, hi = B;                       // first g with rowptr[g] >= target
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (rowptr[mid] < target) lo = mid + 1; else hi = mid;
-      }
-      tiles[t] = lo;
-    }
-    if (tid == 0) meta[1 + pass] = nt;
+  // windows of w packed rows -> runs; two passes (count, scan, write) so that the table is dense
+  const int nwin = (R + w - 1) / w;
+  const int wper = (nwin + nth - 1) / nth;
+  const int w0 = min(nwin, tid * wper), w1 = min(nwin, w0 + wper);
+  int mine = 0;
+  for (int t = w0; t < w1; ++t) {
+    const int G0 = first_graph_at(rowptr, B, t * w);
+    const int G1 = t + 1 < nwin ? first_graph_at(rowptr, B, (t + 1) * w) : B;
+    mine += split_window(rowptr, G0, G1, cap, nullptr);
   }
-  if (tid == 0) { meta[0] = R; meta[3] = 0; }
+  __syncthreads();
+  s_part[tid] = mine;
+  __syncthreads();
+  for (int o = 1; o < nth; o <<= 1) {
+    const int v = tid >= o ? s_part[tid - o] : 0;
+    __syncthreads();
+    s_part[tid] += v;
+    __syncthreads();
+  }
+  int at = tid ? s_part[tid - 1] : 0;
+  for (int t = w0; t < w1; ++t) {
+    const int G0 = first_graph_at(rowptr, B, t * w);
+    const int G1 = t + 1 < nwin ? first_graph_at(rowptr, B, (t + 1) * w) : B;
+    at += split_window(rowptr, G0, G1, cap, reinterpret_cast<int4*>(subs) + at);
+  }
+  if (tid == 0) { meta[0] = R; meta[1] = s_part[nth - 1]; meta[2] = 0; meta[3] = 0; }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// neighbour lists of the dense level-0 adjacency (one CTA per graph at a time)
+// neighbour lists of the dense level-0 adjacency (one CTA per graph at a time): ELL part (first kEll entries of every
+// row at a fixed position, zero padded: loadable without knowing the degree) + overflow; rowmeta; packed inputs
 // ------------------------------------------------------------------------------------------------------------------
+constexpr int kEll = GP_PK_ELL;
+
 __global__ void __launch_bounds__(128)
 build_lists_kernel(const float* __restrict__ adj, const int32_t* __restrict__ nb, const int32_t* __restrict__ rowptr,
-                   int B, int N, int2* __restrict__ info_out, int2* __restrict__ ent_out, int2* __restrict__ info_in,
-                   int2* __restrict__ ent_in, int32_t* __restrict__ cursor, long long capacity) {
+                   int B, int N, int2* __restrict__ info_out, int2* __restrict__ ell_out, int2* __restrict__ ovf_out,
+                   int2* __restrict__ info_in, int2* __restrict__ ell_in, int2* __restrict__ ovf_in,
+                   int32_t* __restrict__ cursors, long long capacity, int2* __restrict__ rowmeta,
+                   const float* __restrict__ x, int D, float* __restrict__ xpack, long long ldxp,
+                   const float* __restrict__ ax, int Da, float* __restrict__ axpack, long long ldaxp) {
   extern __shared__ __align__(16) float sm[];
-  float* s_a = sm;                                   // [n][n+1]
-  int* s_do = reinterpret_cast<int*>(sm + N * (N + 1));   // out degree / offset [N+1]
-  int* s_di = s_do + N + 1;                          // in degree / offset
-  __shared__ int s_base;
+  float* s_a = sm;                                           // [n][n+1]
+  int* s_do = reinterpret_cast<int*>(sm + N * (N + 1));      // out degree, then overflow offset [N+1]
+  int* s_di = s_do + N + 1;                                  // in degree, then overflow offset
+  __shared__ int s_base[2];
   const int tid = threadIdx.x;
   for (int g = blockIdx.x; g < B; g += gridDim.x) {
     const int n = nb ? min(max(nb[g], 0), N) : N;
@@ -342,6 +356,18 @@ build_lists_kernel(const float* __restrict__ adj, const int32_t* __restrict__ nb
       const int i = idx / n, j = idx - i * n;
       s_a[i * ld + j] = ag[(long long)i * N + j];
     }
+    // packed copies of the inputs and the row map
+    for (int i = tid; i < n; i += blockDim.x) rowmeta[r0 + i] = make_int2(i, g);
+    if (xpack)
+      for (int idx = tid; idx < n * (int)ldxp; idx += blockDim.x) {
+        const int i = idx / (int)ldxp, c = idx - i * (int)ldxp;
+        xpack[(long long)(r0 + i) * ldxp + c] = c < D ? x[((long long)g * N + i) * D + c] : 0.f;
+      }
+    if (axpack)
+      for (int idx = tid; idx < n * (int)ldaxp; idx += blockDim.x) {
+        const int i = idx / (int)ldaxp, c = idx - i * (int)ldaxp;
+        axpack[(long long)(r0 + i) * ldaxp + c] = c < Da ? ax[((long long)g * N + i) * Da + c] : 0.f;
+      }
     __syncthreads();
     for (int i = tid; i < n; i += blockDim.x) {
       int co = 0, ci = 0;
@@ -353,34 +379,49 @@ build_lists_kernel(const float* __restrict__ adj, const int32_t* __restrict__ nb
       s_di[i] = ci;
     }
     __syncthreads();
-    if (tid == 0) {
+    if (tid == 0) {                                          // overflow offsets (entries beyond the ELL part)
       int ro = 0, ri = 0;
       for (int i = 0; i < n; ++i) {
+        ro += max(s_do[i] - kEll, 0);
+        ri += max(s_di[i] - kEll, 0);
+      }
+      s_base[0] = ro > 0 ? atomicAdd(cursors, ro) : 0;
+      s_base[1] = ri > 0 ? atomicAdd(cursors + 1, ri) : 0;
+      ro = s_base[0];
+      ri = s_base[1];
+      for (int i = 0; i < n; ++i) {
         const int a = s_do[i], b = s_di[i];
+        // degree in the low half, overflow position kept in the info record
         s_do[i] = ro;
         s_di[i] = ri;
-        ro += a;
-        ri += b;
+        ro += max(a - kEll, 0);
+        ri += max(b - kEll, 0);
+        info_out[r0 + i] = make_int2(s_do[i], (long long)ro <= capacity ? a : min(a, kEll));
+        info_in[r0 + i] = make_int2(s_di[i], (long long)ri <= capacity ? b : min(b, kEll));
       }
-      s_do[n] = ro;
-      s_di[n] = ri;
-      s_base = ro > 0 ? atomicAdd(cursor, ro) : 0;     // both lists hold the same number of entries
     }
     __syncthreads();
-    const long long base = s_base;
-    const bool ok = base + s_do[n] <= capacity;        // cannot fail when capacity >= sum n_b^2
     for (int i = tid; i < n; i += blockDim.x) {
-      const int so = s_do[i], si = s_di[i];
-      info_out[r0 + i] = make_int2((int)(base + so), ok ? s_do[i + 1] - so : 0);
-      info_in[r0 + i] = make_int2((int)(base + si), ok ? s_di[i + 1] - si : 0);
-      if (!ok) continue;
       int po = 0, pi = 0;
+      const int degs_o = info_out[r0 + i].y, degs_i = info_in[r0 + i].y;
+      int2* eo = ell_out + (long long)(r0 + i) * kEll;
+      int2* ei = ell_in + (long long)(r0 + i) * kEll;
       for (int j = 0; j < n; ++j) {
         const float vo = s_a[i * ld + j];
-        if (vo != 0.f) ent_out[base + so + po++] = make_int2(j, __float_as_int(vo));
+        if (vo != 0.f && po < degs_o) {
+          if (po < kEll) eo[po] = make_int2(j, __float_as_int(vo));
+          else ovf_out[s_do[i] + po - kEll] = make_int2(j, __float_as_int(vo));
+          ++po;
+        }
         const float vi = s_a[j * ld + i];
-        if (vi != 0.f) ent_in[base + si + pi++] = make_int2(j, __float_as_int(vi));
+        if (vi != 0.f && pi < degs_i) {
+          if (pi < kEll) ei[pi] = make_int2(j, __float_as_int(vi));
+          else ovf_in[s_di[i] + pi - kEll] = make_int2(j, __float_as_int(vi));
+          ++pi;
+        }
       }
+      for (; po < kEll; ++po) eo[po] = make_int2(0, 0);
+      for (; pi < kEll; ++pi) ei[pi] = make_int2(0, 0);
     }
   }
 }
@@ -388,68 +429,151 @@ build_lists_kernel(const float* __restrict__ adj, const int32_t* __restrict__ nb
 // ------------------------------------------------------------------------------------------------------------------
 // shared pieces of the layer / pooling kernels
 // ------------------------------------------------------------------------------------------------------------------
-// A window tile can hold up to w - 1 + N rows; the CTA walks it in runs of whole graphs with at most max_rows rows
-// (max_rows >= N, so one graph always fits): shared memory is sized for max_rows, not for the worst window.
-__device__ __forceinline__ int sub_end(const gp_pk_tiling& t, int g, int G1) {
-  if (t.rowptr == nullptr) return G1;
-  const int r = t.rowptr[g];
-  int ge = g + 1;
-  while (ge < G1 && t.rowptr[ge + 1] - r <= t.max_rows) ++ge;
-  return ge;
-}
 __host__ __device__ __forceinline__ int pow2_ge(int v) {
   int p = 1;
   while (p < v) p <<= 1;
   return p;
 }
 
+// Neighbour lists (or the dense blocks of the pooled level) of a run -> shared memory.  Every load is independent of
+// every other (the ELL part sits at a fixed position per row), so the whole run's lists are in flight at once: one
+// global round trip per run instead of two dependent ones per row.   s_info [mr] int2, s_ell [mr * kEll] int2.
+__device__ __forceinline__ bool dense_fits(const gp_pk_tiling& tl, const Sub& sb) {
+  return (sb.g1 - sb.g0) * tl.nfix * tl.nfix <= 2 * tl.max_rows * kEll;
+}
+__device__ __forceinline__ void stage_lists(const gp_pk_adj& a, const gp_pk_tiling& tl, const Sub& sb, int2* s_info,
+                                            int2* s_ell) {
+  if (a.info) {
+    const int2* gi = reinterpret_cast<const int2*>(a.info) + sb.r0;
+    for (int i = threadIdx.x; i < sb.nt; i += blockDim.x) s_info[i] = __ldg(gi + i);
+    const int4* ge = reinterpret_cast<const int4*>(a.ell) + (size_t)sb.r0 * (kEll / 2);
+    int4* se = reinterpret_cast<int4*>(s_ell);
+    const int total = sb.nt * (kEll / 2);
+    for (int base = threadIdx.x; base < total; base += 4 * blockDim.x) {
+      int4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (base + j * blockDim.x < total) v[j] = __ldg(ge + base + j * blockDim.x);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (base + j * blockDim.x < total) se[base + j * blockDim.x] = v[j];
+    }
+  } else if (dense_fits(tl, sb)) {
+    const int per = tl.nfix * tl.nfix;
+    float* d = reinterpret_cast<float*>(s_ell);
+    const float* src = a.dense + (long long)sb.g0 * per;
+    for (int idx = threadIdx.x; idx < (sb.g1 - sb.g0) * per; idx += blockDim.x) d[idx] = __ldg(src + idx);
+  }
+}
+
+// u = sum_e a(i, e) * rows[gs + col_e][lane]        (one warp per row, lane = column, ld <= 32)
+__device__ __forceinline__ float gather_lane(const gp_pk_adj& a, const gp_pk_tiling& tl, const Sub& sb, int i, int gs,
+                                             int gid, int ni, const int2* s_info, const int2* s_ell,
+                                             const float* rows, int ld, int lane) {
+  float u = 0.f;
+  const float* sp = rows + (size_t)gs * ld + lane;
+  if (a.info) {
+    const int2 inf = s_info[i];
+    if (lane < ld) {
+      const int m = min(inf.y, kEll);
+      for (int e = 0; e < m; ++e) {
+        const int2 x = s_ell[i * kEll + e];
+        u = fmaf(__int_as_float(x.y), sp[(size_t)x.x * ld], u);
+      }
+      const int2* en = reinterpret_cast<const int2*>(a.entries) + inf.x;
+      for (int e = kEll; e < inf.y; ++e) {
+        const int2 x = __ldg(en + e - kEll);
+        u = fmaf(__int_as_float(x.y), sp[(size_t)x.x * ld], u);
+      }
+    }
+  } else {
+    const int nf = tl.nfix, per = nf * nf;
+    const float* dn = dense_fits(tl, sb) ? reinterpret_cast<const float*>(s_ell) + (gid - sb.g0) * per
+                                         : a.dense + (long long)gid * per;
+    if (lane < ld)
+      for (int e = 0; e < nf; ++e) {
+        const float v = a.transposed ? dn[e * nf + ni] : dn[ni * nf + e];
+        u = fmaf(v, sp[(size_t)e * ld], u);
+      }
+  }
+  return u;
+}
+
 // sum_e a(i, e) * src[gs + col_e][4q .. 4q+3]
-__device__ __forceinline__ float4 gather_row4(const gp_pk_adj& a, int nfix, int r0, int i, int gs, int gid,
-                                              const float* src, int ld, int q) {
+__device__ __forceinline__ float4 gather_row4(const gp_pk_adj& a, const gp_pk_tiling& tl, const Sub& sb, int i, int gs,
+                                              int gid, const int2* s_info, const int2* s_ell, const float* src, int ld,
+                                              int q) {
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   const int ni = i - gs;
   const float* sp = src + (size_t)gs * ld + 4 * q;
   if (a.info) {
-    const int2 inf = __ldg(reinterpret_cast<const int2*>(a.info) + r0 + i);
-    const int2* en = reinterpret_cast<const int2*>(a.entries) + inf.x;
-    for (int e = 0; e < inf.y; ++e) {
-      const int2 x = __ldg(en + e);
+    const int2 inf = s_info[i];
+    const int m = min(inf.y, kEll);
+    for (int e = 0; e < m; ++e) {
+      const int2 x = s_ell[i * kEll + e];
       const float v = __int_as_float(x.y);
-      const float4 s = *reinterpret_cast<const float4*>(sp + (size_t)x.x * ld);
-      acc.x = fmaf(v, s.x, acc.x); acc.y = fmaf(v, s.y, acc.y); acc.z = fmaf(v, s.z, acc.z); acc.w = fmaf(v, s.w, acc.w);
+      const float4 t = *reinterpret_cast<const float4*>(sp + (size_t)x.x * ld);
+      acc.x = fmaf(v, t.x, acc.x); acc.y = fmaf(v, t.y, acc.y); acc.z = fmaf(v, t.z, acc.z); acc.w = fmaf(v, t.w, acc.w);
+    }
+    const int2* en = reinterpret_cast<const int2*>(a.entries) + inf.x;
+    for (int e = kEll; e < inf.y; ++e) {
+      const int2 x = __ldg(en + e - kEll);
+      const float v = __int_as_float(x.y);
+      const float4 t = *reinterpret_cast<const float4*>(sp + (size_t)x.x * ld);
+      acc.x = fmaf(v, t.x, acc.x); acc.y = fmaf(v, t.y, acc.y); acc.z = fmaf(v, t.z, acc.z); acc.w = fmaf(v, t.w, acc.w);
     }
   } else {
-    const float* dn = a.dense + (long long)gid * nfix * nfix;
-    for (int e = 0; e < nfix; ++e) {
-      const float v = a.transposed ? __ldg(dn + e * nfix + ni) : __ldg(dn + ni * nfix + e);
-      const float4 s = *reinterpret_cast<const float4*>(sp + (size_t)e * ld);
-      acc.x = fmaf(v, s.x, acc.x); acc.y = fmaf(v, s.y, acc.y); acc.z = fmaf(v, s.z, acc.z); acc.w = fmaf(v, s.w, acc.w);
+    const int nf = tl.nfix, per = nf * nf;
+    const float* dn = dense_fits(tl, sb) ? reinterpret_cast<const float*>(s_ell) + (gid - sb.g0) * per
+                                         : a.dense + (long long)gid * per;
+    for (int e = 0; e < nf; ++e) {
+      const float v = a.transposed ? dn[e * nf + ni] : dn[ni * nf + e];
+      const float4 t = *reinterpret_cast<const float4*>(sp + (size_t)e * ld);
+      acc.x = fmaf(v, t.x, acc.x); acc.y = fmaf(v, t.y, acc.y); acc.z = fmaf(v, t.z, acc.z); acc.w = fmaf(v, t.w, acc.w);
     }
   }
   return acc;
 }
-// dst = A src over a sub-tile, one thread per (row, 4-column chunk): every thread has its own neighbour list in
-// flight, the 8 threads of a row share the list loads (broadcast) and read 128 contiguous bytes of the source row
-__device__ void gather4(const gp_pk_adj& a, int nfix, int r0, int nt, const int* s_gs, const int* s_gid,
-                        const float* src, int ld, float* dst) {
+// dst = A src over a run, one thread per (row, 4-column chunk)
+__device__ void gather4(const gp_pk_adj& a, const gp_pk_tiling& tl, const Sub& sb, const int* s_gs, const int* s_gid,
+                        const int2* s_info, const int2* s_ell, const float* src, int ld, float* dst) {
   const int C4 = ld >> 2;
-  for (int item = threadIdx.x; item < nt * C4; item += blockDim.x) {
+  for (int item = threadIdx.x; item < sb.nt * C4; item += blockDim.x) {
     const int i = item / C4, q = item - i * C4;
-    const float4 acc = gather_row4(a, nfix, r0, i, s_gs[i], s_gid[i], src, ld, q);
+    const float4 acc = gather_row4(a, tl, sb, i, s_gs[i], s_gid[i], s_info, s_ell, src, ld, q);
     *reinterpret_cast<float4*>(dst + (size_t)i * ld + 4 * q) = acc;
   }
 }
 
+// rows of the run -> shared memory, one warp per row (ld <= 32), four rows in flight per warp
+__device__ __forceinline__ void load_rows_warp(const gp_pk_src& src, const Sub& sb, const int* s_gs,
+                                               const float* s_mean, const float* s_istd, float* dst, int ld) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const bool bn = src.sums != nullptr;
+  if (lane >= ld) return;
+#pragma unroll 4
+  for (int i = wid; i < sb.nt; i += nw) {
+    float v = 0.f;
+    if (lane < src.d) {
+      v = __ldg(src.y + (long long)(sb.r0 + i) * src.ld + lane);
+      if (bn) {
+        const int ni = i - s_gs[i];
+        v = (fmaxf(v, 0.f) - s_mean[ni]) * s_istd[ni];
+      }
+    }
+    dst[i * ld + lane] = v;
+  }
+}
 
 // Deterministic per-node-index accumulation of per-row statistics: s_rs[i], s_rs[mr + i] hold the two values of local
 // row i; thread n adds the rows with node index n graph by graph (fixed order), so a forward pass is bit-reproducible
 // (shared-memory atomics would add them in scheduling order).
-__device__ __forceinline__ void reduce_row_stats(const gp_pk_tiling& tl, int g0, int g1, int r0, int N, int mr,
+__device__ __forceinline__ void reduce_row_stats(const gp_pk_tiling& tl, const Sub& sb, int N, int mr,
                                                  const float* s_rs, float* s_st) {
   for (int n = threadIdx.x; n < N; n += blockDim.x) {
     float a1 = 0.f, a2 = 0.f;
-    for (int g = g0; g < g1; ++g) {
-      const int gs = t_row0(tl, g) - r0, ng = t_row0(tl, g + 1) - r0 - gs;
+    for (int g = sb.g0; g < sb.g1; ++g) {
+      const int gs = t_row0(tl, g) - sb.r0, ng = t_row0(tl, g + 1) - sb.r0 - gs;
       if (n < ng) {
         a1 += s_rs[gs + n];
         a2 += s_rs[mr + gs + n];
@@ -469,13 +593,13 @@ static size_t fwd_smem(const gp_pk_layer_fwd_args& p) {
     Count c;
     const int ldi = r4(p.s[s].in.d), ldo = r4(p.s[s].dout), mr = p.tl.max_rows;
     c.take(mr * ldi); c.take(mr * ldi); c.take(ldi * ldo); c.take(ldo); c.take(2 * p.N); c.take(2 * p.N);
-    c.take(mr); c.take(mr); c.take(2 * mr);
+    c.take(mr); c.take(mr); c.take(2 * mr); c.take(2 * mr); c.take(2 * mr * kEll);
     best = best > c.n ? best : c.n;
   }
   return best * sizeof(float);
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
 layer_fwd_kernel(const gp_pk_layer_fwd_args p) {
   extern __shared__ __align__(16) float sm[];
   const gp_pk_stack_fwd& st = p.s[blockIdx.y];
@@ -490,6 +614,8 @@ layer_fwd_kernel(const gp_pk_layer_fwd_args p) {
   int* s_gs = reinterpret_cast<int*>(cv.take(mr));
   int* s_gid = reinterpret_cast<int*>(cv.take(mr));
   float* s_rs = cv.take(2 * mr);
+  int2* s_info = reinterpret_cast<int2*>(cv.take(2 * mr));
+  int2* s_ell = reinterpret_cast<int2*>(cv.take(2 * mr * kEll));
   const int tid = threadIdx.x;
   for (int idx = tid; idx < ldi * ldo; idx += blockDim.x) {
     const int k = idx / ldo, n = idx - k * ldo;
@@ -500,20 +626,20 @@ layer_fwd_kernel(const gp_pk_layer_fwd_args p) {
   bn_stats(st.in, p.cnt_pad, N, p.tl.B, s_bn, s_bn + N);
   const int N4 = ldo >> 2, N4p = pow2_ge(N4), K4 = ldi >> 2;
   const bool stats = st.sums_out != nullptr;
-  const int ntiles = t_count(p.tl);
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    int G0, G1;
-    t_graphs(p.tl, tile, G0, G1);
-    for (int g0 = G0; g0 < G1;) {
-      const int g1 = sub_end(p.tl, g0, G1);
-      const int r0 = t_row0(p.tl, g0), nt = t_row0(p.tl, g1) - r0;
+  const int nsub = sub_count(p.tl);
+  for (int run = blockIdx.x; run < nsub; run += gridDim.x) {
+    {
+      const Sub sb = sub_get(p.tl, run);
+      const int r0 = sb.r0, nt = sb.nt, g0 = sb.g0, g1 = sb.g1;
+      (void)g0; (void)g1;
       if (nt > 0) {
         __syncthreads();
-        row_map(p.tl, g0, g1, r0, nt, s_gs, s_gid);
+        load_meta(p.tl, sb, s_gs, s_gid);
+        stage_lists(p.adj, p.tl, sb, s_info, s_ell);
         __syncthreads();
-        load_rows(st.in, N, r0, nt, s_gs, s_gid, s_bn, s_bn + N, bH, ldi, 0, ldi);
+        load_rows(st.in, r0, nt, s_gs, s_bn, s_bn + N, bH, ldi, 0, ldi);
         __syncthreads();
-        gather4(p.adj, p.tl.nfix, r0, nt, s_gs, s_gid, bH, ldi, bU);
+        gather4(p.adj, p.tl, sb, s_gs, s_gid, s_info, s_ell, bH, ldi, bU);
         __syncthreads();
         // V = U W + b, Y = V / max(||V||, eps), ReLU statistics: a row lives in the N4p lanes of one aligned group
         const int total = ((nt + 3) >> 2) * N4p;
@@ -591,10 +717,9 @@ layer_fwd_kernel(const gp_pk_layer_fwd_args p) {
         }
         if (stats) {
           __syncthreads();
-          reduce_row_stats(p.tl, g0, g1, r0, N, mr, s_rs, s_st);
+          reduce_row_stats(p.tl, sb, N, mr, s_rs, s_st);
         }
       }
-      g0 = g1;
     }
   }
   __syncthreads();
@@ -619,12 +744,13 @@ static size_t bwd_smem(const gp_pk_layer_bwd_args& p) {
     c.take(ldi * ldo); c.take(ldo * ldi); c.take(bwd_groups(ldi, ldo) * ldi * ldo); c.take(ldo);
     for (int i = 0; i < 4; ++i) c.take(2 * p.N);
     c.take(p.N); c.take(mr); c.take(mr);
+    for (int i = 0; i < 2; ++i) { c.take(2 * mr); c.take(2 * mr * kEll); }
     best = best > c.n ? best : c.n;
   }
   return best * sizeof(float);
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
 layer_bwd_kernel(const gp_pk_layer_bwd_args p) {
   extern __shared__ __align__(16) float sm[];
   const gp_pk_stack_bwd& st = p.s[blockIdx.y];
@@ -645,6 +771,10 @@ layer_bwd_kernel(const gp_pk_layer_bwd_args p) {
   float* s_scr = cv.take(N);
   int* s_gs = reinterpret_cast<int*>(cv.take(mr));
   int* s_gid = reinterpret_cast<int*>(cv.take(mr));
+  int2* s_info = reinterpret_cast<int2*>(cv.take(2 * mr));
+  int2* s_ell = reinterpret_cast<int2*>(cv.take(2 * mr * kEll));
+  int2* s_info_in = reinterpret_cast<int2*>(cv.take(2 * mr));
+  int2* s_ell_in = reinterpret_cast<int2*>(cv.take(2 * mr * kEll));
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
   for (int idx = tid; idx < ldi * ldo; idx += blockDim.x) {
     const int k = idx / ldo, n = idx - k * ldo;
@@ -702,16 +832,17 @@ layer_bwd_kernel(const gp_pk_layer_bwd_args p) {
 
   float dbacc[4] = {0.f, 0.f, 0.f, 0.f};               // bias gradient: columns lane, lane+32, ... of this warp's rows
   const int C4 = ldi >> 2, C4p = pow2_ge(C4);
-  const int ntiles = t_count(p.tl);
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    int G0, G1;
-    t_graphs(p.tl, tile, G0, G1);
-    for (int g0 = G0; g0 < G1;) {
-      const int g1 = sub_end(p.tl, g0, G1);
-      const int r0 = t_row0(p.tl, g0), nt = t_row0(p.tl, g1) - r0;
+  const int nsub = sub_count(p.tl);
+  for (int run = blockIdx.x; run < nsub; run += gridDim.x) {
+    {
+      const Sub sb = sub_get(p.tl, run);
+      const int r0 = sb.r0, nt = sb.nt, g0 = sb.g0, g1 = sb.g1;
+      (void)g0; (void)g1;
       if (nt > 0) {
         __syncthreads();
-        row_map(p.tl, g0, g1, r0, nt, s_gs, s_gid);
+        load_meta(p.tl, sb, s_gs, s_gid);
+        stage_lists(p.adj, p.tl, sb, s_info, s_ell);
+        if (st.need_dx && p.adj_in.info) stage_lists(p.adj_in, p.tl, sb, s_info_in, s_ell_in);
         __syncthreads();
         // ---- dV = d normalize . d(ReLU + BatchNorm) . gl, straight from global memory (one warp per row)
         for (int i = wid; i < nt; i += nw) {
@@ -749,9 +880,9 @@ layer_bwd_kernel(const gp_pk_layer_bwd_args p) {
             }
           }
         }
-        load_rows(st.in, N, r0, nt, s_gs, s_gid, s_bni, s_bni + N, bH, ldi, 0, ldi);
+        load_rows(st.in, r0, nt, s_gs, s_bni, s_bni + N, bH, ldi, 0, ldi);
         __syncthreads();
-        gather4(p.adj, p.tl.nfix, r0, nt, s_gs, s_gid, bH, ldi, bU);
+        gather4(p.adj, p.tl, sb, s_gs, s_gid, s_info, s_ell, bH, ldi, bU);
         __syncthreads();
         gemm_tn_acc(bU, ldi, bV, ldo, ldi >> 2, ldo >> 2, 0, nt, s_dw, ldo, groups);
         if (st.need_dx) {
@@ -786,7 +917,8 @@ layer_bwd_kernel(const gp_pk_layer_bwd_args p) {
             const int gs = s_gs[i], gid = s_gid[i], ni = i - gs;
             float a1 = 0.f, a2 = 0.f;
             if (q < C4) {
-              const float4 d4 = gather_row4(p.adj_in, p.tl.nfix, r0, i, gs, gid, bU, ldi, q);
+              const float4 d4 = gather_row4(p.adj_in, p.tl, sb, i, gs, gid, s_info_in,
+                                            p.adj_in.info ? s_ell_in : s_ell, bU, ldi, q);
               const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
               for (int cc = 0; cc < 4; ++cc) {
@@ -812,7 +944,6 @@ layer_bwd_kernel(const gp_pk_layer_bwd_args p) {
           }
         }
       }
-      g0 = g1;
     }
   }
   if (st.db) {
@@ -844,89 +975,13 @@ layer_bwd_kernel(const gp_pk_layer_bwd_args p) {
 // neighbour rows of the gather and a 128-byte broadcast buffer.  ~80 warp instructions per row and stack instead of
 // ~380 for the 4x4-tiled kernels (ncu, profiles/r2_ncu_packed.md): no index arithmetic, no staging of V.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kDegCap = 8;      // neighbour-list entries per row kept in shared memory (longer lists: the rest from L2)
-
-// Neighbour lists (or the dense blocks of the pooled level) of a sub-tile -> shared memory, all rows in parallel: the
-// two dependent global accesses (list header, entries) are paid once per sub-tile instead of once per row and warp.
-__device__ __forceinline__ void stage_lists(const gp_pk_adj& a, const gp_pk_tiling& tl, int g0, int g1, int r0, int nt,
-                                            int2* s_info, int2* s_ent) {
-  if (a.info) {
-    for (int i = threadIdx.x; i < nt; i += blockDim.x) {
-      const int2 inf = __ldg(reinterpret_cast<const int2*>(a.info) + r0 + i);
-      s_info[i] = inf;
-      const int2* en = reinterpret_cast<const int2*>(a.entries) + inf.x;
-      const int m = min(inf.y, kDegCap);
-      for (int e = 0; e < m; ++e) s_ent[i * kDegCap + e] = __ldg(en + e);
-    }
-  } else {
-    const int nf = tl.nfix, per = nf * nf;
-    if ((g1 - g0) * per <= 2 * tl.max_rows * kDegCap) {           // dense blocks fit: stage them
-      float* d = reinterpret_cast<float*>(s_ent);
-      const float* src = a.dense + (long long)g0 * per;
-      for (int idx = threadIdx.x; idx < (g1 - g0) * per; idx += blockDim.x) d[idx] = __ldg(src + idx);
-    }
-  }
-}
-
-__device__ __forceinline__ float gather_lane(const gp_pk_adj& a, const gp_pk_tiling& tl, int g0, int g1, int i, int gs,
-                                             int gid, int ni, const int2* s_info, const int2* s_ent, const float* rows,
-                                             int ld, int lane) {
-  float u = 0.f;
-  const float* sp = rows + (size_t)gs * ld + lane;
-  if (a.info) {
-    const int2 inf = s_info[i];
-    if (lane < ld) {
-      const int m = min(inf.y, kDegCap);
-      for (int e = 0; e < m; ++e) {
-        const int2 x = s_ent[i * kDegCap + e];
-        u = fmaf(__int_as_float(x.y), sp[(size_t)x.x * ld], u);
-      }
-      const int2* en = reinterpret_cast<const int2*>(a.entries) + inf.x;
-      for (int e = kDegCap; e < inf.y; ++e) {
-        const int2 x = __ldg(en + e);
-        u = fmaf(__int_as_float(x.y), sp[(size_t)x.x * ld], u);
-      }
-    }
-  } else {
-    const int nf = tl.nfix, per = nf * nf;
-    const bool staged = (g1 - g0) * per <= 2 * tl.max_rows * kDegCap;
-    const float* dn = staged ? reinterpret_cast<const float*>(s_ent) + (gid - g0) * per : a.dense + (long long)gid * per;
-    if (lane < ld)
-      for (int e = 0; e < nf; ++e) {
-        const float v = a.transposed ? dn[e * nf + ni] : dn[ni * nf + e];
-        u = fmaf(v, sp[(size_t)e * ld], u);
-      }
-  }
-  return u;
-}
-
-// rows of the sub-tile -> shared memory, one warp per row (ld <= 32), four rows in flight per warp
-__device__ __forceinline__ void load_rows_warp(const gp_pk_src& src, int N, int r0, int nt, const int* s_gs,
-                                               const int* s_gid, const float* s_mean, const float* s_istd, float* dst,
-                                               int ld) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const bool bn = src.sums != nullptr;
-  if (lane >= ld) return;
-#pragma unroll 4
-  for (int i = wid; i < nt; i += nw) {
-    float v = 0.f;
-    if (lane < src.d) {
-      const int ni = i - s_gs[i];
-      const long long row = src.padded ? ((long long)s_gid[i] * N + ni) : (long long)(r0 + i);
-      v = __ldg(src.y + row * src.ld + lane);
-      if (bn) v = (fmaxf(v, 0.f) - s_mean[ni]) * s_istd[ni];
-    }
-    dst[i * ld + lane] = v;
-  }
-}
-
 static size_t fwd_row_smem(const gp_pk_layer_fwd_args& p) {
   size_t best = 0;
   for (int s = 0; s < p.ns; ++s) {
     Count c;
     const int ldi = r4(p.s[s].in.d), mr = p.tl.max_rows;
     c.take(mr * ldi); c.take((kThreads / 32) * 64); c.take(2 * p.N); c.take(2 * p.N); c.take(mr); c.take(mr);
-    c.take(2 * mr); c.take(2 * mr * kDegCap); c.take(2 * mr);
+    c.take(2 * mr); c.take(2 * mr * kEll); c.take(2 * mr);
     best = best > c.n ? best : c.n;
   }
   return best * sizeof(float);
@@ -946,7 +1001,7 @@ layer_fwd_row_kernel(const gp_pk_layer_fwd_args p) {
   int* s_gs = reinterpret_cast<int*>(cv.take(mr));
   int* s_gid = reinterpret_cast<int*>(cv.take(mr));
   int2* s_info = reinterpret_cast<int2*>(cv.take(2 * mr));
-  int2* s_ent = reinterpret_cast<int2*>(cv.take(2 * mr * kDegCap));
+  int2* s_ent = reinterpret_cast<int2*>(cv.take(2 * mr * kEll));
   float* s_rs = cv.take(2 * mr);
   float wreg[32];
 #pragma unroll
@@ -955,19 +1010,18 @@ layer_fwd_row_kernel(const gp_pk_layer_fwd_args p) {
   for (int n = tid; n < 2 * N; n += blockDim.x) s_st[n] = 0.f;
   bn_stats(st.in, p.cnt_pad, N, p.tl.B, s_bn, s_bn + N);
   const bool stats = st.sums_out != nullptr;
-  const int ntiles = t_count(p.tl);
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    int G0, G1;
-    t_graphs(p.tl, tile, G0, G1);
-    for (int g0 = G0; g0 < G1;) {
-      const int g1 = sub_end(p.tl, g0, G1);
-      const int r0 = t_row0(p.tl, g0), nt = t_row0(p.tl, g1) - r0;
+  const int nsub = sub_count(p.tl);
+  for (int run = blockIdx.x; run < nsub; run += gridDim.x) {
+    {
+      const Sub sb = sub_get(p.tl, run);
+      const int r0 = sb.r0, nt = sb.nt, g0 = sb.g0, g1 = sb.g1;
+      (void)g0; (void)g1;
       if (nt > 0) {
         __syncthreads();
-        row_map(p.tl, g0, g1, r0, nt, s_gs, s_gid);
-        stage_lists(p.adj, p.tl, g0, g1, r0, nt, s_info, s_ent);
+        load_meta(p.tl, sb, s_gs, s_gid);
+        stage_lists(p.adj, p.tl, sb, s_info, s_ent);
         __syncthreads();
-        load_rows_warp(st.in, N, r0, nt, s_gs, s_gid, s_bn, s_bn + N, bH, ldi);
+        load_rows_warp(st.in, sb, s_gs, s_bn, s_bn + N, bH, ldi);
         __syncthreads();
         for (int ib = wid; ib < nt; ib += 2 * nw) {        // two rows per iteration: their chains interleave
           int ii[2], nis[2];
@@ -979,7 +1033,7 @@ layer_fwd_row_kernel(const gp_pk_layer_fwd_args p) {
           for (int r = 0; r < 2; ++r) {
             const int i = ii[r], gs = s_gs[i];
             nis[r] = i - gs;
-            su[r * 32 + lane] = gather_lane(p.adj, p.tl, g0, g1, i, gs, s_gid[i], nis[r], s_info, s_ent, bH, ldi, lane);
+            su[r * 32 + lane] = gather_lane(p.adj, p.tl, sb, i, gs, s_gid[i], nis[r], s_info, s_ent, bH, ldi, lane);
           }
           __syncwarp();
 #pragma unroll
@@ -1029,10 +1083,9 @@ layer_fwd_row_kernel(const gp_pk_layer_fwd_args p) {
         }
         if (stats) {
           __syncthreads();
-          reduce_row_stats(p.tl, g0, g1, r0, N, mr, s_rs, s_st);
+          reduce_row_stats(p.tl, sb, N, mr, s_rs, s_st);
         }
       }
-      g0 = g1;
     }
   }
   __syncthreads();
@@ -1061,6 +1114,7 @@ static size_t pool_smem(const gp_pk_pool_args& p, const PoolDims& d, bool bwd) {
   const int mr = p.tl.max_rows;
   c.take(mr * d.ldF); c.take(mr * d.ldFa); c.take(mr * d.ldK); c.take(mr * d.ldK); c.take(mr); c.take(mr);
   c.take((p.z.L + p.za.L) * 2 * p.N);
+  for (int i = 0; i < (bwd ? 2 : 1); ++i) { c.take(2 * mr); c.take(2 * mr * kEll); }
   if (!bwd) {
     c.take(d.ldFa * d.ldK); c.take(d.ldK);
   } else {
@@ -1072,13 +1126,13 @@ static size_t pool_smem(const gp_pk_pool_args& p, const PoolDims& d, bool bwd) {
 __device__ void concat_stats(const gp_pk_concat& z, const float* cnt_pad, int N, int B, float* s_bn) {
   for (int l = 0; l < z.L; ++l) bn_stats(z.slot[l], cnt_pad, N, B, s_bn + l * 2 * N, s_bn + l * 2 * N + N);
 }
-__device__ void concat_load(const gp_pk_concat& z, int N, int r0, int nt, const int* s_gs, const int* s_gid,
-                            const float* s_bn, float* dst, int ldd) {
+__device__ void concat_load(const gp_pk_concat& z, int N, int r0, int nt, const int* s_gs, const float* s_bn,
+                            float* dst, int ldd) {
   int off = 0;
   for (int l = 0; l < z.L; ++l) {
     const int d = z.slot[l].d;
     const int dz = (l == z.L - 1) ? ldd - off : d;
-    load_rows(z.slot[l], N, r0, nt, s_gs, s_gid, s_bn + l * 2 * N, s_bn + l * 2 * N + N, dst, ldd, off, dz);
+    load_rows(z.slot[l], r0, nt, s_gs, s_bn + l * 2 * N, s_bn + l * 2 * N + N, dst, ldd, off, dz);
     off += d;
   }
 }
@@ -1097,6 +1151,8 @@ pool_fwd_kernel(const gp_pk_pool_args p) {
   int* s_gid = reinterpret_cast<int*>(cv.take(mr));
   float* s_bn = cv.take((p.z.L + p.za.L) * 2 * N);
   float* s_bna = s_bn + p.z.L * 2 * N;
+  int2* s_info_in = reinterpret_cast<int2*>(cv.take(2 * mr));
+  int2* s_ell_in = reinterpret_cast<int2*>(cv.take(2 * mr * kEll));
   float* s_wpt = cv.take(ldFa * ldK);
   float* s_bp = cv.take(ldK);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
@@ -1107,19 +1163,21 @@ pool_fwd_kernel(const gp_pk_pool_args p) {
   for (int k = tid; k < ldK; k += blockDim.x) s_bp[k] = (p.bp && k < K) ? p.bp[k] : 0.f;
   concat_stats(p.z, p.cnt_pad, N, p.tl.B, s_bn);
   concat_stats(p.za, p.cnt_pad, N, p.tl.B, s_bna);
-  const int ntiles = t_count(p.tl);
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    int G0, G1;
-    t_graphs(p.tl, tile, G0, G1);
-    for (int g0 = G0; g0 < G1;) {
-      const int g1 = sub_end(p.tl, g0, G1);
-      const int r0 = t_row0(p.tl, g0), nt = t_row0(p.tl, g1) - r0;
+  const int nsub = sub_count(p.tl);
+  for (int run = blockIdx.x; run < nsub; run += gridDim.x) {
+    {
+      const Sub sb = sub_get(p.tl, run);
+      const int r0 = sb.r0, nt = sb.nt, g0 = sb.g0, g1 = sb.g1;
+      (void)g0; (void)g1;
       __syncthreads();
-      if (nt > 0) row_map(p.tl, g0, g1, r0, nt, s_gs, s_gid);      // graphs without rows still own (all-zero) outputs
+      if (nt > 0) {                                   // graphs without rows still own (all-zero) outputs
+        load_meta(p.tl, sb, s_gs, s_gid);
+        stage_lists(p.adj_in, p.tl, sb, s_info_in, s_ell_in);
+      }
       __syncthreads();
       if (nt > 0) {
-        concat_load(p.z, N, r0, nt, s_gs, s_gid, s_bn, bZ, ldF);
-        concat_load(p.za, N, r0, nt, s_gs, s_gid, s_bna, bZa, ldFa);
+        concat_load(p.z, N, r0, nt, s_gs, s_bn, bZ, ldF);
+        concat_load(p.za, N, r0, nt, s_gs, s_bna, bZa, ldFa);
       }
       __syncthreads();
       if (nt > 0) {
@@ -1153,7 +1211,7 @@ pool_fwd_kernel(const gp_pk_pool_args p) {
         for (int idx = tid; idx < (N - n) * K; idx += blockDim.x) so[idx] = 0.f;
       }
       __syncthreads();
-      if (nt > 0) gather4(p.adj_in, p.tl.nfix, r0, nt, s_gs, s_gid, bS, ldK, bT);    // (A^T S)[j][k] = T[k][j]
+      if (nt > 0) gather4(p.adj_in, p.tl, sb, s_gs, s_gid, s_info_in, s_ell_in, bS, ldK, bT);    // (A^T S)[j][k] = T[k][j]
       // max readout over the graph's rows; with pad rows (zeros after the mask) a negative maximum loses to 0
       const int ng = g1 - g0;
       for (int idx = tid; idx < ng * F; idx += blockDim.x) {
@@ -1210,7 +1268,6 @@ pool_fwd_kernel(const gp_pk_pool_args p) {
               if (4 * i + rr < K && 4 * j + cc < ncol) o[(4 * i + rr) * ncol + 4 * j + cc] = acc[rr][cc];
         }
       }
-      g0 = g1;
     }
   }
 }
@@ -1229,6 +1286,10 @@ pool_bwd_kernel(const gp_pk_pool_args p) {
   int* s_gid = reinterpret_cast<int*>(cv.take(mr));
   float* s_bn = cv.take((p.z.L + p.za.L) * 2 * N);
   float* s_bna = s_bn + p.z.L * 2 * N;
+  int2* s_info = reinterpret_cast<int2*>(cv.take(2 * mr));
+  int2* s_ell = reinterpret_cast<int2*>(cv.take(2 * mr * kEll));
+  int2* s_info_in = reinterpret_cast<int2*>(cv.take(2 * mr));
+  int2* s_ell_in = reinterpret_cast<int2*>(cv.take(2 * mr * kEll));
   float* bAS = cv.take(mr * ldK);
   float* bD = cv.take(mr * ldK);
   float* s_wp = cv.take(ldK * ldFa);
@@ -1244,26 +1305,27 @@ pool_bwd_kernel(const gp_pk_pool_args p) {
   concat_stats(p.z, p.cnt_pad, N, p.tl.B, s_bn);
   concat_stats(p.za, p.cnt_pad, N, p.tl.B, s_bna);
   float dbacc[4] = {0.f, 0.f, 0.f, 0.f};
-  const int ntiles = t_count(p.tl);
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    int G0, G1;
-    t_graphs(p.tl, tile, G0, G1);
-    for (int g0 = G0; g0 < G1;) {
-      const int g1 = sub_end(p.tl, g0, G1);
-      const int r0 = t_row0(p.tl, g0), nt = t_row0(p.tl, g1) - r0;
+  const int nsub = sub_count(p.tl);
+  for (int run = blockIdx.x; run < nsub; run += gridDim.x) {
+    {
+      const Sub sb = sub_get(p.tl, run);
+      const int r0 = sb.r0, nt = sb.nt, g0 = sb.g0, g1 = sb.g1;
+      (void)g0; (void)g1;
       if (nt > 0) {
         __syncthreads();
-        row_map(p.tl, g0, g1, r0, nt, s_gs, s_gid);
+        load_meta(p.tl, sb, s_gs, s_gid);
+        stage_lists(p.adj, p.tl, sb, s_info, s_ell);
+        stage_lists(p.adj_in, p.tl, sb, s_info_in, s_ell_in);
         __syncthreads();
-        concat_load(p.z, N, r0, nt, s_gs, s_gid, s_bn, bZ, ldF);
-        concat_load(p.za, N, r0, nt, s_gs, s_gid, s_bna, bZa, ldFa);
+        concat_load(p.z, N, r0, nt, s_gs, s_bn, bZ, ldF);
+        concat_load(p.za, N, r0, nt, s_gs, s_bna, bZa, ldFa);
         for (int idx = tid; idx < nt * ldK; idx += blockDim.x) {
           const int i = idx / ldK, k = idx - i * ldK;
           bS[idx] = k < K ? p.S[((long long)s_gid[i] * N + (i - s_gs[i])) * K + k] : 0.f;
         }
         __syncthreads();
-        gather4(p.adj, p.tl.nfix, r0, nt, s_gs, s_gid, bS, ldK, bAS);
-        gather4(p.adj_in, p.tl.nfix, r0, nt, s_gs, s_gid, bS, ldK, bAtS);
+        gather4(p.adj, p.tl, sb, s_gs, s_gid, s_info, s_ell, bS, ldK, bAS);
+        gather4(p.adj_in, p.tl, sb, s_gs, s_gid, s_info_in, s_ell_in, bS, ldK, bAtS);
         // gz[i][f] = sum_k S[i][k] dX'[g][k][f] + readout scatter   (dX' read through L1: each element serves n_g rows)
         for (int idx = tid; idx < nt * F; idx += blockDim.x) {
           const int i = idx / F, f = idx - i * F;
@@ -1323,7 +1385,6 @@ pool_bwd_kernel(const gp_pk_pool_args p) {
           });
         }
       }
-      g0 = g1;
     }
   }
   if (p.dbp) {
@@ -1497,8 +1558,8 @@ static int grid_for(int smem_bytes, int want, int ny = 1, int reg_limit = 8) {
   } while (0)
 
 static int tiles_upper(const gp_pk_tiling& t) {
-  if (t.tile_g0 == nullptr) return (t.B + t.gpt - 1) / t.gpt;
-  return t.gpt;            // ragged tiling: the caller passes an upper bound of the tile count in gpt
+  if (t.subs == nullptr) return (t.B + t.gpt - 1) / t.gpt;
+  return t.gpt;            // ragged level: the caller passes an upper bound of the run count in gpt
 }
 
 }  // namespace pk
@@ -1507,41 +1568,53 @@ static int tiles_upper(const gp_pk_tiling& t) {
 using namespace gp;
 using namespace gp::pk;
 
-extern "C" int gp_pk_prepare(const int32_t* nb, int B, int N, int w_layer, int w_pool, int32_t* rowptr, float* cnt_pad,
-                             int32_t* tiles_layer, int32_t* tiles_pool, int32_t* meta, gp_stream_t stream) {
-  GP_REQUIRE(rowptr && cnt_pad && tiles_layer && tiles_pool && meta, "pk_prepare: null pointer");
-  GP_REQUIRE(B > 0 && N > 0 && N <= kMaxN && w_layer > 0 && w_pool > 0, "pk_prepare: B=%d N=%d (N <= %d)", B, N, kMaxN);
-  prepare_kernel<<<1, 1024, 0, S(stream)>>>(nb, B, N, w_layer, w_pool, rowptr, cnt_pad, tiles_layer, tiles_pool, meta);
+extern "C" int gp_pk_prepare(const int32_t* nb, int B, int N, int window, int max_rows, int32_t* rowptr, float* cnt_pad,
+                             int32_t* subs, int32_t* meta, gp_stream_t stream) {
+  GP_REQUIRE(rowptr && cnt_pad && subs && meta, "pk_prepare: null pointer");
+  GP_REQUIRE(B > 0 && N > 0 && N <= kMaxN && window > 0 && max_rows >= N && max_rows >= window,
+             "pk_prepare: B=%d N=%d (N <= %d), max_rows >= max(N, window)", B, N, kMaxN);
+  GP_REQUIRE((reinterpret_cast<uintptr_t>(subs) & 15) == 0, "pk_prepare: subs must be 16-byte aligned");
+  prepare_kernel<<<1, 1024, 0, S(stream)>>>(nb, B, N, window, max_rows, rowptr, cnt_pad, subs, meta);
   GP_LAUNCHED();
   return GP_OK;
 }
 
 extern "C" int gp_pk_build_lists(const float* adj, const int32_t* nb, const int32_t* rowptr, int B, int N,
-                                 int32_t* info_out, int32_t* ent_out, int32_t* info_in, int32_t* ent_in,
-                                 int32_t* cursor, long long capacity, gp_stream_t stream) {
-  GP_REQUIRE(adj && rowptr && info_out && ent_out && info_in && ent_in && cursor, "pk_build_lists: null pointer");
+                                 int32_t* info_out, int32_t* ell_out, int32_t* ovf_out, int32_t* info_in,
+                                 int32_t* ell_in, int32_t* ovf_in, int32_t* cursors, long long capacity,
+                                 int32_t* rowmeta, const float* x, int D, float* xpack, long long ldxp, const float* ax,
+                                 int Da, float* axpack, long long ldaxp, gp_stream_t stream) {
+  GP_REQUIRE(adj && rowptr && info_out && ell_out && ovf_out && info_in && ell_in && ovf_in && cursors && rowmeta,
+             "pk_build_lists: null pointer");
   GP_REQUIRE(B > 0 && N > 0 && N <= kMaxN && capacity > 0 && capacity < (1ll << 31), "pk_build_lists: bad sizes");
+  GP_REQUIRE((xpack == nullptr) || (x && D > 0 && ldxp >= D), "pk_build_lists: x / xpack");
+  GP_REQUIRE((axpack == nullptr) || (ax && Da > 0 && ldaxp >= Da), "pk_build_lists: ax / axpack");
+  GP_REQUIRE(((reinterpret_cast<uintptr_t>(ell_out) | reinterpret_cast<uintptr_t>(ell_in)) & 15) == 0,
+             "pk_build_lists: ell arrays must be 16-byte aligned");
   const size_t smem = (size_t)(N * (N + 1) + 2 * (N + 1)) * sizeof(float);
   GP_PK_SMEM(build_lists_kernel, smem);
   const int grid = grid_for((int)smem, B);
-  build_lists_kernel<<<grid, 128, smem, S(stream)>>>(adj, nb, rowptr, B, N, reinterpret_cast<int2*>(info_out),
-                                                     reinterpret_cast<int2*>(ent_out), reinterpret_cast<int2*>(info_in),
-                                                     reinterpret_cast<int2*>(ent_in), cursor, capacity);
+  build_lists_kernel<<<grid, 128, smem, S(stream)>>>(
+      adj, nb, rowptr, B, N, reinterpret_cast<int2*>(info_out), reinterpret_cast<int2*>(ell_out),
+      reinterpret_cast<int2*>(ovf_out), reinterpret_cast<int2*>(info_in), reinterpret_cast<int2*>(ell_in),
+      reinterpret_cast<int2*>(ovf_in), cursors, capacity, reinterpret_cast<int2*>(rowmeta), x, D, xpack, ldxp, ax, Da,
+      axpack, ldaxp);
   GP_LAUNCHED();
   return GP_OK;
 }
 
 static int check_tiling(const gp_pk_tiling& t, int N) {
   GP_REQUIRE(t.B > 0 && t.max_rows > 0 && t.gpt > 0, "pk: bad tiling");
-  GP_REQUIRE((t.rowptr != nullptr) == (t.tile_g0 != nullptr) && (t.rowptr != nullptr) == (t.ntiles != nullptr),
-             "pk: ragged tiling needs rowptr, tile_g0 and ntiles");
+  GP_REQUIRE((t.rowptr != nullptr) == (t.subs != nullptr) && (t.rowptr != nullptr) == (t.nsub != nullptr) &&
+             (t.rowptr != nullptr) == (t.rowmeta != nullptr), "pk: the ragged level needs rowptr, subs, nsub and rowmeta");
   GP_REQUIRE(t.rowptr != nullptr || (t.nfix > 0 && t.nfix <= N && t.gpt * t.nfix <= t.max_rows), "pk: uniform tiling");
   GP_REQUIRE(t.rowptr == nullptr || t.max_rows >= N, "pk: max_rows must hold one whole graph");
   GP_REQUIRE(N > 0 && N <= kMaxN, "pk: N = %d (<= %d)", N, kMaxN);
   return GP_OK;
 }
 static int check_adj(const gp_pk_adj& a, const gp_pk_tiling& t) {
-  GP_REQUIRE((a.info && a.entries) || (a.dense && t.rowptr == nullptr), "pk: adjacency (lists, or dense with a uniform tiling)");
+  GP_REQUIRE((a.info && a.ell && a.entries) || (a.dense && t.rowptr == nullptr),
+             "pk: adjacency (lists, or dense with a uniform tiling)");
   return GP_OK;
 }
 

@@ -16,12 +16,12 @@ import torch
 
 from . import engine as E
 from ._lib import (GpPkAdj, GpPkConcat, GpPkGrad, GpPkLayerBwdArgs, GpPkLayerFwdArgs, GpPkPoolArgs, GpPkSrc,
-                   GpPkTiling, PK_MAX_LAYERS, call)
+                   GpPkTiling, PK_ELL, PK_MAX_LAYERS, call)
 
 MAX_N = 128           # kMaxN in packed.cu
-W_LAYER = 96          # packed rows per tile WINDOW (graphs whose first row falls into it); the kernels walk a window in
-W_POOL = 96           # runs of whole graphs of at most max(N, W) rows, which is what sizes their shared memory
-POST_ROWS = 64        # rows per tile at the pooled level (whole graphs of K rows)
+WINDOW = 96           # packed rows per window (the graphs whose first row falls into it); gp_pk_prepare splits every
+                      # window into runs of whole graphs of at most max(N, WINDOW) rows: the unit a CTA works on
+POST_ROWS = 64        # rows per run at the pooled level (whole graphs of K rows)
 
 
 def _stream():
@@ -59,8 +59,12 @@ def supported(plan, x, adj, assign_x, params):
     return True
 
 
-def _src(y_ptr, ld, d, padded=0, sums=None, bias=None):
-    return GpPkSrc(y_ptr, ld, d, padded, sums, bias)
+def _src(y_ptr, ld, d, sums=None, bias=None):
+    return GpPkSrc(y_ptr, ld, d, sums, bias)
+
+
+def _r4(v):
+    return (int(v) + 3) & ~3
 
 
 class _Stack:
@@ -90,10 +94,10 @@ class _Stack:
     def src_in(self, l):
         if l == 0:
             return self.in_src
-        return _src(self.Y[l - 1].data_ptr(), self.d[l - 1], self.d[l - 1], 0, self.sums[l - 1], _p(self.b[l - 1]))
+        return _src(self.Y[l - 1].data_ptr(), self.d[l - 1], self.d[l - 1], self.sums[l - 1], _p(self.b[l - 1]))
 
     def src_out(self, l):
-        return _src(self.Y[l].data_ptr(), self.d[l], self.d[l], 0, self.sums[l], _p(self.b[l]))
+        return _src(self.Y[l].data_ptr(), self.d[l], self.d[l], self.sums[l], _p(self.b[l]))
 
     def concat(self):
         c = GpPkConcat()
@@ -139,9 +143,10 @@ def forward(plan, x, adj, assign_x, params, wb):
     rows = int(host.astype(np.int64).sum()) if host is not None else B * N
     cap = int((host.astype(np.int64) ** 2).sum()) if host is not None else B * N * N
     rows, cap = max(rows, 1), max(cap, 1)
-    t1max, t2max = (rows + W_LAYER - 1) // W_LAYER, (rows + W_POOL - 1) // W_POOL
+    max_rows = max(N, WINDOW)
+    nsub_max = 4 * ((rows + WINDOW - 1) // WINDOW + 1)
 
-    # ---- one zeroed blob: BatchNorm sums (doubles) | link-loss sum | parameter gradients (floats)
+    # ---- one zeroed blob: BatchNorm sums (doubles) | parameter gradients (floats)
     nd_e, nd_a, nd_q = _Stack.doubles(Le, N), _Stack.doubles(La, N), _Stack.doubles(Lq, K)
     nd = nd_e + nd_a + nd_q
     shapes = [tuple(p.shape) for p in params]
@@ -151,26 +156,35 @@ def forward(plan, x, adj, assign_x, params, wb):
     call('gp_fill_f32', dbl.data_ptr(), C.c_longlong(2 * dbl.numel()), C.c_float(0.0), st)
     gflat = dbl[nd:].view(torch.float32)
 
-    imeta = ws.i(B + 1 + 4 + (t1max + 2) + (t2max + 2))
-    rowptr = imeta[:B + 1]
-    meta = imeta[B + 1:B + 5]
-    tiles1 = imeta[B + 5:B + 5 + t1max + 2]
-    tiles2 = imeta[B + 5 + t1max + 2:]
+    # ---- rows, runs, neighbour lists, packed inputs
+    subs = ws.i(nsub_max, 4)                          # 16-byte aligned (fresh allocation)
+    imeta = ws.i(B + 1 + 4)
+    rowptr, meta = imeta[:B + 1], imeta[B + 1:]
     cnt_pad = ws.f(N)
-    call('gp_pk_prepare', _p(nb), B, N, W_LAYER, W_POOL, rowptr.data_ptr(), cnt_pad.data_ptr(), tiles1.data_ptr(),
-         tiles2.data_ptr(), meta.data_ptr(), st)
+    call('gp_pk_prepare', _p(nb), B, N, WINDOW, max_rows, rowptr.data_ptr(), cnt_pad.data_ptr(), subs.data_ptr(),
+         meta.data_ptr(), st)
+    Da = int(assign_x.shape[2])
+    own_ax = assign_x.data_ptr() != x.data_ptr()
     info = ws.i(2, rows, 2)
-    ent = ws.i(2, cap, 2)
-    call('gp_pk_build_lists', adj.data_ptr(), _p(nb), rowptr.data_ptr(), B, N, info[0].data_ptr(), ent[0].data_ptr(),
-         info[1].data_ptr(), ent[1].data_ptr(), meta.data_ptr() + 12, C.c_longlong(cap), st)
-    a_out = GpPkAdj(info[0].data_ptr(), ent[0].data_ptr(), None, 0)
-    a_in = GpPkAdj(info[1].data_ptr(), ent[1].data_ptr(), None, 0)
-    tl1 = GpPkTiling(rowptr.data_ptr(), tiles1.data_ptr(), meta.data_ptr() + 4, B, N, t1max, max(N, W_LAYER))
-    tl2 = GpPkTiling(rowptr.data_ptr(), tiles2.data_ptr(), meta.data_ptr() + 8, B, N, t2max, max(N, W_POOL))
+    ell = ws.i(2, rows, PK_ELL, 2)
+    ovf = ws.i(2, cap, 2)
+    rowmeta = ws.i(rows, 2)
+    xpack = ws.f(rows, _r4(D))
+    axpack = ws.f(rows, _r4(Da)) if own_ax else None
+    call('gp_pk_build_lists', adj.data_ptr(), _p(nb), rowptr.data_ptr(), B, N, info[0].data_ptr(), ell[0].data_ptr(),
+         ovf[0].data_ptr(), info[1].data_ptr(), ell[1].data_ptr(), ovf[1].data_ptr(), meta.data_ptr() + 8,
+         C.c_longlong(cap), rowmeta.data_ptr(), x.data_ptr(), D, xpack.data_ptr(), C.c_longlong(_r4(D)),
+         assign_x.data_ptr() if own_ax else None, Da, _p(axpack), C.c_longlong(_r4(Da)), st)
+    a_out = GpPkAdj(info[0].data_ptr(), ell[0].data_ptr(), ovf[0].data_ptr(), None, 0)
+    a_in = GpPkAdj(info[1].data_ptr(), ell[1].data_ptr(), ovf[1].data_ptr(), None, 0)
+    tl1 = GpPkTiling(rowptr.data_ptr(), subs.data_ptr(), meta.data_ptr() + 4, rowmeta.data_ptr(), B, N, nsub_max,
+                     max_rows)
+    tl2 = tl1
 
     # ---- level 0: embedding and assignment GCN in lock-step
-    se = _Stack(ws, rows, we, be, _src(x.data_ptr(), D, D, 1), dbl, 0, N)
-    sa = _Stack(ws, rows, wa, ba, _src(assign_x.data_ptr(), assign_x.shape[2], assign_x.shape[2], 1), dbl, nd_e, N)
+    se = _Stack(ws, rows, we, be, _src(xpack.data_ptr(), _r4(D), D), dbl, 0, N)
+    sa = _Stack(ws, rows, wa, ba, _src(axpack.data_ptr(), _r4(Da), Da) if own_ax else _src(xpack.data_ptr(), _r4(D), D),
+                dbl, nd_e, N)
     for l in range(max(Le, La)):
         _layer_fwd(tl1, a_out, cnt_pad.data_ptr(), N, [se, sa], l)
 
@@ -190,10 +204,10 @@ def forward(plan, x, adj, assign_x, params, wb):
 
     # ---- pooled level: K rows per graph, dense A'
     gpt = max(1, POST_ROWS // K)
-    tlq = GpPkTiling(None, None, None, B, K, gpt, gpt * K)
-    q_out = GpPkAdj(None, None, ap.data_ptr(), 0)
-    q_in = GpPkAdj(None, None, ap.data_ptr(), 1)
-    sq = _Stack(ws, B * K, wq, bq, _src(xp.data_ptr(), F, F, 0), dbl, nd_e + nd_a, K)
+    tlq = GpPkTiling(None, None, None, None, B, K, gpt, gpt * K)
+    q_out = GpPkAdj(None, None, None, ap.data_ptr(), 0)
+    q_in = GpPkAdj(None, None, None, ap.data_ptr(), 1)
+    sq = _Stack(ws, B * K, wq, bq, _src(xp.data_ptr(), F, F), dbl, nd_e + nd_a, K)
     for l in range(Lq):
         _layer_fwd(tlq, q_out, None, K, [sq], l)
     zq = sq.concat()
@@ -201,7 +215,8 @@ def forward(plan, x, adj, assign_x, params, wb):
          C.c_longlong(ldo), F, st)
     ypred, acts = E.mlp_fwd(ws, out.data_ptr(), ldo, B, lin)
     tape = dict(B=B, N=N, K=K, rows=rows, F=F, Fa=Fa, ldo=ldo, dbl=dbl, gflat=gflat, goff=goff, shapes=shapes,
-                imeta=imeta, cnt_pad=cnt_pad, info=info, ent=ent, tl1=tl1, tl2=tl2, tlq=tlq, a_out=a_out, a_in=a_in,
+                imeta=imeta, subs=subs, cnt_pad=cnt_pad, info=info, ell=ell, ovf=ovf, rowmeta=rowmeta, xpack=xpack,
+                axpack=axpack, tl1=tl1, tl2=tl2, tlq=tlq, a_out=a_out, a_in=a_in,
                 q_out=q_out, q_in=q_in, se=se, sa=sa, sq=sq, pa=pa, S=S, xp=xp, ap=ap, out=out, arg=arg, acts=acts,
                 lin=lin, x=x, adj=adj, assign_x=assign_x, nb=nb)
     return ypred, S, tape

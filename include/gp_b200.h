@@ -454,24 +454,28 @@ int gp_pad_copy_f32(const float* src, long long ld_src, long long rows, int cols
  * index (encoders.py:1048-1052), is a sum per node index that a phase accumulates and the next phase consumes:
  * the launch boundary is the grid-wide dependency.
  * ------------------------------------------------------------------------------------------- */
+#define GP_PK_ELL 8        /* neighbour-list entries per row kept at a fixed position (longer lists overflow) */
 typedef struct gp_pk_tiling {
   const int32_t* rowptr;   /* [B+1] first packed row of each graph; NULL: every graph has `nfix` rows */
-  const int32_t* tile_g0;  /* [ntiles+1] first graph of each tile; NULL: `gpt` graphs per tile */
-  const int32_t* ntiles;   /* device scalar; NULL: ceil(B / gpt) */
-  int B, nfix, gpt, max_rows;   /* max_rows: upper bound of the rows of one tile (sizes the shared memory) */
+  const int32_t* subs;     /* [nsub][4] {first packed row, rows, first graph, end graph}: runs of whole graphs with at
+                              most max_rows rows, built by gp_pk_prepare; NULL: `gpt` graphs per run */
+  const int32_t* nsub;     /* device scalar; NULL: ceil(B / gpt) */
+  const int32_t* rowmeta;  /* [R][2] {node index, graph} of every packed row; NULL: computed from nfix */
+  int B, nfix, gpt, max_rows;   /* max_rows: upper bound of the rows of one run (sizes the shared memory) */
 } gp_pk_tiling;
 
 typedef struct gp_pk_adj {
-  const int32_t* info;     /* [R][2] {first entry, degree} of every packed row; NULL: dense */
-  const int32_t* entries;  /* [nnz][2] {node index within the graph, value as float bits} */
+  const int32_t* info;     /* [R][2] {first overflow entry, degree} of every packed row; NULL: dense */
+  const int32_t* ell;      /* [R][GP_PK_ELL][2] first entries of every row {node index within the graph, value as
+                              float bits}, zero padded */
+  const int32_t* entries;  /* overflow entries of rows with more than GP_PK_ELL neighbours */
   const float* dense;      /* [B, nfix, nfix] when info == NULL */
   int transposed;          /* dense only: row i of the operator is column i of `dense` */
 } gp_pk_adj;
 
-/* rows of one layer's normalised output Y (or of the caller's input) and the ReLU + BatchNorm applied on read */
+/* packed rows of one layer's normalised output Y (or of the packed input) and the ReLU + BatchNorm applied on read */
 typedef struct gp_pk_src {
   const float* y; long long ld; int d;
-  int padded;              /* 1: the caller's [B, N, d] tensor, row (g, i) at y + (g*N + i)*ld; 0: packed rows */
   const double* sums;      /* [2N] sum relu(y), sum relu(y)^2 per node index over the REAL rows; NULL: rows as they are */
   const float* bias;       /* bias of the producing layer (its pad rows are normalize(bias)); NULL: zero pad rows */
 } gp_pk_src;
@@ -528,16 +532,20 @@ typedef struct gp_pk_pool_args {
   float* dWp; float* dbp;                   /* accumulated with atomics (zero on entry) */
 } gp_pk_pool_args;
 
-/* nb [B] -> rowptr [B+1], cnt_pad [N], two tilings (window `w_layer` / `w_pool` packed rows: tile t holds the graphs
- * whose first row lies in [t*w, (t+1)*w), at most w - 1 + N rows), meta = {R, ntiles_layer, ntiles_pool, 0 (list
- * cursor)}.  nb == NULL: every graph has N nodes.  tiles_*: [ceil(B*N / w) + 2] ints. */
-int gp_pk_prepare(const int32_t* nb, int B, int N, int w_layer, int w_pool, int32_t* rowptr, float* cnt_pad,
-                  int32_t* tiles_layer, int32_t* tiles_pool, int32_t* meta, gp_stream_t stream);
-/* dense fp32 adjacency [B,N,N] -> neighbour lists of the n_b x n_b blocks (out: rows, in: columns); `cursor` is a
- * zeroed device int (bump allocator), `capacity` entries per list */
+/* nb [B] -> rowptr [B+1], cnt_pad [N], the run table subs (graphs are grouped by windows of `window` packed rows --
+ * the graphs whose first row falls into a window -- and every window is split greedily into runs of whole graphs with
+ * at most max_rows >= max(N, window) rows; at most 4 runs per window), meta = {R, nsub, 0, 0} (meta[2], meta[3]: the
+ * overflow cursors of gp_pk_build_lists).  nb == NULL: every graph has N nodes.  subs: [4 * (B*N / window + 2)][4]. */
+int gp_pk_prepare(const int32_t* nb, int B, int N, int window, int max_rows, int32_t* rowptr, float* cnt_pad,
+                  int32_t* subs, int32_t* meta, gp_stream_t stream);
+/* dense fp32 adjacency [B,N,N] -> neighbour lists of the n_b x n_b blocks (out: rows, in: columns) in ELL + overflow
+ * form, rowmeta [R][2], and the packed copies of the inputs: xpack [R, ldxp] <- x [B,N,D] (and axpack <- ax when the
+ * assignment GCN has its own features; NULL otherwise).  cursors: two zeroed device ints, `capacity` overflow entries
+ * per direction (sum max(deg - GP_PK_ELL, 0) <= sum n_b^2). */
 int gp_pk_build_lists(const float* adj, const int32_t* nb, const int32_t* rowptr, int B, int N, int32_t* info_out,
-                      int32_t* ent_out, int32_t* info_in, int32_t* ent_in, int32_t* cursor, long long capacity,
-                      gp_stream_t stream);
+                      int32_t* ell_out, int32_t* ovf_out, int32_t* info_in, int32_t* ell_in, int32_t* ovf_in,
+                      int32_t* cursors, long long capacity, int32_t* rowmeta, const float* x, int D, float* xpack,
+                      long long ldxp, const float* ax, int Da, float* axpack, long long ldaxp, gp_stream_t stream);
 int gp_pk_layer_fwd(const gp_pk_layer_fwd_args* a, gp_stream_t stream);
 int gp_pk_layer_bwd(const gp_pk_layer_bwd_args* a, gp_stream_t stream);
 int gp_pk_pool_fwd(const gp_pk_pool_args* a, gp_stream_t stream);

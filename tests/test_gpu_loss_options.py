@@ -58,7 +58,10 @@ def build(N, D, H, C, ratio, link, ent_w, seed, linkpred=True):
 def test_fp32_loss_options(link, ent_w, use_nb, sym):
     N, D, H, C, B = 70, 5, 24, 4, 6
     mo, mc = build(N, D, H, C, 0.2, link, ent_w, 3, linkpred=link is not None)
-    x, adj, nb, label = synth_batch(11, B, N, D, 5, N, C, 0.15, symmetric=bool(sym))
+    # seed 12: with seed 11 the pooled level has two clusters whose maxima differ by 2 ulp (1.97006226 vs 1.97006261);
+    # the fp32 schedules then disagree with the fp64 oracle on WHICH row wins the max readout -- a legitimate fp32
+    # artefact of a non-differentiable point, not an error -- and every gradient downstream moves by ~1e-4
+    x, adj, nb, label = synth_batch(12, B, N, D, 5, N, C, 0.15, symmetric=bool(sym))
     nbo = nb if use_nb else None
     m64 = copy.deepcopy(mo).double()
     yo, lo, parts = oracle_step(m64, x, adj, nbo, label, link, ent_w)

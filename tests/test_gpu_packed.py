@@ -61,3 +61,31 @@ def test_packed_agrees_with_dense_schedule_and_device_node_counts():
     S = res['packed'][2]
     for b in range(B):
         assert not S[b, nb[b]:].any()
+
+
+def test_packed_step_under_graph_replay_tracks_eager_training():
+    """graphed.GraphedTrainStep captures the packed schedule (node counts on the device only: rows, runs and lists are
+    all derived there) and its replays track eager clip_grad_norm + Adam training on the same batches."""
+    import copy
+    from graph_pooling_b200 import graphed
+    N, D, H, C, B = 100, 3, 30, 6, 24
+    torch.manual_seed(8)
+    m0 = soft_factory(N, D, H, H, C, ratio=0.1)(enc()).cuda()
+    me, mg = copy.deepcopy(m0), copy.deepcopy(m0)
+    opt = torch.optim.Adam(me.parameters(), lr=1e-3)
+    gs = graphed.GraphedTrainStep(mg, lr=1e-3, clip=2.0)
+    for i in range(4):
+        x, adj, nb, label = synth_batch(90 + i, B, N, D, 2, N, C, 0.05)
+        xc, ac, lc = torch.tensor(x).cuda(), torch.tensor(adj).cuda(), torch.tensor(label).cuda()
+        me.zero_grad()
+        yp = me(xc, ac, nb, assign_x=xc)
+        loss = me.loss(yp, lc, ac, nb)
+        assert me._plan.packed
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(me.parameters(), 2.0)
+        opt.step()
+        del yp
+        _, lg = gs.step(xc, ac, nb, lc)
+        assert abs(lg.item() - loss.item()) <= 2e-4 * abs(loss.item()), (i, lg.item(), loss.item())
+        del loss
+    assert mg._plan.packed
