@@ -19,9 +19,9 @@ from ._lib import (GpPkAdj, GpPkConcat, GpPkGrad, GpPkLayerBwdArgs, GpPkLayerFwd
                    GpPkTiling, PK_ELL, PK_MAX_LAYERS, call)
 
 MAX_N = 128           # kMaxN in packed.cu
-WINDOW = 96           # packed rows per window (the graphs whose first row falls into it); gp_pk_prepare splits every
+WINDOW = int(os.environ.get('GP_PK_WINDOW', 96))           # packed rows per window (the graphs whose first row falls into it); gp_pk_prepare splits every
                       # window into runs of whole graphs of at most max(N, WINDOW) rows: the unit a CTA works on
-POST_ROWS = 64        # rows per run at the pooled level (whole graphs of K rows)
+POST_ROWS = int(os.environ.get('GP_PK_POST_ROWS', 64))        # rows per run at the pooled level (whole graphs of K rows)
 
 
 def _stream():

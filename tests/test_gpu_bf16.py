@@ -2,10 +2,17 @@
 
 Stated bound of this mode (bf16 operands, fp32 accumulation; BASELINE.json north_star "bf16
 tensor-core path with its own stated bound"):
-  ypred, S: rel-L2 <= 2e-2;  loss: relative <= 5e-3;
-  full flattened parameter gradient: rel-L2 <= 0.15 and cosine similarity >= 0.99.
+  ypred: rel-L2 <= 1.5e-2;  S: rel-L2 <= 5e-3;  loss: relative <= 2.5e-3;
+  full flattened parameter gradient: rel-L2 <= 0.09 and cosine similarity >= 0.995
+-- about twice the worst value measured over the cases of this file on a B200 (ypred 7.2e-3, S 2.4e-3, loss 1.0e-3,
+gradient 0.044 / cosine 0.999: profiles/r2_bf16_errors.md; round 1 tested 0.15 / 0.99 without recording them).
+At the BASELINE shapes the bound is tighter still (tests/test_gpu_baseline_shapes.py).
 (The fp32 mode's bound is 1e-5, tests/test_gpu_model.py.)"""
+
+BF16_OUT, BF16_S, BF16_LOSS, BF16_GRAD, BF16_COS = 1.5e-2, 5e-3, 2.5e-3, 0.09, 0.995
 import copy
+import json
+import os
 
 import numpy as np
 import pytest
@@ -15,6 +22,17 @@ from helpers import rel_l2, synth_batch
 from oracle import diffpool_oracle as orc
 
 pytestmark = pytest.mark.gpu
+
+
+def _record(**kw):
+    """Measured errors of the small-shape cases -> gpurun_out/r2_bf16_small_errors.jsonl (profiles/r2_bf16_errors.md)."""
+    try:
+        d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, 'r2_bf16_small_errors.jsonl'), 'a') as f:
+            f.write(json.dumps(kw) + '\n')
+    except OSError:
+        pass
 
 
 @pytest.mark.parametrize('N,D,H,C,B,ratio,P,n_min,density', [
@@ -45,13 +63,16 @@ def test_bf16_mode_bounds(N, D, H, C, B, ratio, P, n_min, density):
     loss = mc.loss(yp, torch.tensor(label).cuda(), ac, nb)
     loss.backward()
     torch.cuda.synchronize()
-    assert rel_l2(yp.detach().cpu().numpy(), yo.detach().numpy()) < 2e-2
-    assert rel_l2(mc.assign_tensors[0].detach().cpu().numpy(), m64.assign_tensors[0].detach().numpy()) < 2e-2
-    assert abs(loss.item() - lo.item()) < 5e-3 * abs(lo.item())
+    assert rel_l2(yp.detach().cpu().numpy(), yo.detach().numpy()) < BF16_OUT
+    assert rel_l2(mc.assign_tensors[0].detach().cpu().numpy(), m64.assign_tensors[0].detach().numpy()) < BF16_S
+    assert abs(loss.item() - lo.item()) < BF16_LOSS * abs(lo.item())
     gc = np.concatenate([p.grad.cpu().numpy().ravel() for p in mc.parameters()]).astype(np.float64)
     go = np.concatenate([p.grad.numpy().ravel() for p in m64.parameters()])
     cos = float(gc @ go / (np.linalg.norm(gc) * np.linalg.norm(go)))
-    assert rel_l2(gc, go) < 0.15 and cos > 0.99, (rel_l2(gc, go), cos)
+    _record(case='small N=%d D=%d H=%d B=%d P=%d' % (N, D, H, B, P), ypred=rel_l2(yp.detach().cpu().numpy(), yo.detach().numpy()),
+            S=rel_l2(mc.assign_tensors[0].detach().cpu().numpy(), m64.assign_tensors[0].detach().numpy()),
+            loss=abs(loss.item() - lo.item()) / abs(lo.item()), grad_flat=rel_l2(gc, go), grad_cos=cos)
+    assert rel_l2(gc, go) < BF16_GRAD and cos > BF16_COS, (rel_l2(gc, go), cos)
 
 
 @pytest.mark.parametrize('N,H,ratio,P,extra', [(200, 24, 0.25, 2, 0), (120, 64, 0.25, 2, 1), (600, 32, 0.25, 1, 1),
