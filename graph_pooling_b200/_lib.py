@@ -131,7 +131,7 @@ _PROTOS = {
     'gp_softmax_mask_bwd_x': [c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f, c_ll, c_f, c_f, c_f],
     'gp_adj_prepare': [c_f, c_i, c_f, c_i, c_i, c_f, c_ll, c_f, c_f],
     'gp_adj_prepare_x': [c_f, c_i, c_ll, c_f, c_i, c_i, c_f, c_ll, c_f, c_i, c_f],
-    'gp_adj_from_edges': [c_f, c_f, c_i, c_i, c_i, c_i, c_f, c_ll, c_f, c_i, c_f],
+    'gp_adj_from_edges': [c_f, c_i, c_f, c_i, c_i, c_i, c_i, c_f, c_ll, c_f, c_i, c_f],
     'gp_host_pack_adj_bits': [c_f, c_ll, c_i, c_f, c_ll, c_i, c_f],
     'gp_sym_select_bf16': [c_f, c_ll, c_i, c_i, c_f, c_f, c_ll, c_f],
     'gp_cvt_f32_bf16': [c_f, c_ll, c_f, c_ll, c_ll, c_i, c_i, c_f],

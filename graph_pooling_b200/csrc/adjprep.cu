@@ -212,18 +212,20 @@ namespace gp {
 // Edge-list feed: the batch's adjacency never exists as fp32.  edges [E][2] are graph-local node ids,
 // graph b owns edges eptr[b] .. eptr[b+1]; the operand slice is zero-filled by the caller (cudaMemsetAsync) and every
 // edge writes 1.0 at (u, v) -- and at (v, u) for an undirected list.  Out-of-range ids are ignored.
+template <class E2>          // int2 (32-bit ids) or ushort2 (16-bit ids)
 __global__ void __launch_bounds__(256)
-adj_from_edges_kernel(const int32_t* __restrict__ edges, const int32_t* __restrict__ eptr, int N,
+adj_from_edges_kernel(const E2* __restrict__ edges, const int32_t* __restrict__ eptr, int N,
                       __nv_bfloat16* __restrict__ out, long long ld, int undirected) {
   const int b = blockIdx.y;
   const int e0 = eptr[b], e1 = eptr[b + 1];
   __nv_bfloat16* ob = out + (long long)b * N * ld;
   const __nv_bfloat16 one = __float2bfloat16(1.0f);
   for (int e = e0 + blockIdx.x * blockDim.x + threadIdx.x; e < e1; e += gridDim.x * blockDim.x) {
-    const int2 uv = reinterpret_cast<const int2*>(edges)[e];
-    if ((unsigned)uv.x >= (unsigned)N || (unsigned)uv.y >= (unsigned)N) continue;
-    ob[(long long)uv.x * ld + uv.y] = one;
-    if (undirected) ob[(long long)uv.y * ld + uv.x] = one;
+    const E2 uv = edges[e];
+    const int u = (int)uv.x, v = (int)uv.y;
+    if ((unsigned)u >= (unsigned)N || (unsigned)v >= (unsigned)N) continue;
+    ob[(long long)u * ld + v] = one;
+    if (undirected) ob[(long long)v * ld + u] = one;
   }
 }
 __global__ void set_flags_kernel(int32_t* flags, int not_sym, int accumulate) {
@@ -231,17 +233,22 @@ __global__ void set_flags_kernel(int32_t* flags, int not_sym, int accumulate) {
 }
 }  // namespace gp
 
-extern "C" int gp_adj_from_edges(const int32_t* edges, const int32_t* eptr, int B, int N, int max_edges_per_graph,
-                                 int undirected, void* adj_bf16, long long ld, int32_t* flags, int accumulate_flags,
-                                 gp_stream_t stream) {
+extern "C" int gp_adj_from_edges(const void* edges, int id_bytes, const int32_t* eptr, int B, int N,
+                                 int max_edges_per_graph, int undirected, void* adj_bf16, long long ld, int32_t* flags,
+                                 int accumulate_flags, gp_stream_t stream) {
   GP_REQUIRE(edges && eptr && adj_bf16 && B > 0 && N > 0 && ld >= N && ld - N < 8 && B <= 65535,
              "adj_from_edges: bad args (need N <= ld < N+8)");
-  GP_REQUIRE((reinterpret_cast<uintptr_t>(edges) & 7) == 0, "adj_from_edges: edges must be 8-byte aligned");
+  GP_REQUIRE(id_bytes == 4 || (id_bytes == 2 && N <= 65536), "adj_from_edges: node ids are 4 or 2 bytes (2: N <= 65536)");
+  GP_REQUIRE((reinterpret_cast<uintptr_t>(edges) & (uintptr_t)(2 * id_bytes - 1)) == 0, "adj_from_edges: edge alignment");
   GP_CUDA(cudaMemsetAsync(adj_bf16, 0, (size_t)B * N * ld * sizeof(__nv_bfloat16), S(stream)));
   int gx = (max_edges_per_graph + 255) / 256;
   gx = gx < 1 ? 1 : (gx > 64 ? 64 : gx);
-  adj_from_edges_kernel<<<dim3((unsigned)gx, (unsigned)B), 256, 0, S(stream)>>>(
-      edges, eptr, N, reinterpret_cast<__nv_bfloat16*>(adj_bf16), ld, undirected);
+  if (id_bytes == 4)
+    adj_from_edges_kernel<int2><<<dim3((unsigned)gx, (unsigned)B), 256, 0, S(stream)>>>(
+        reinterpret_cast<const int2*>(edges), eptr, N, reinterpret_cast<__nv_bfloat16*>(adj_bf16), ld, undirected);
+  else
+    adj_from_edges_kernel<ushort2><<<dim3((unsigned)gx, (unsigned)B), 256, 0, S(stream)>>>(
+        reinterpret_cast<const ushort2*>(edges), eptr, N, reinterpret_cast<__nv_bfloat16*>(adj_bf16), ld, undirected);
   GP_LAUNCHED();
   if (flags != nullptr) {
     set_flags_kernel<<<1, 1, 0, S(stream)>>>(flags, undirected ? 0 : 1, accumulate_flags);

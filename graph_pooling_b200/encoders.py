@@ -63,7 +63,10 @@ def _fwd_tc(ctx, plan, x, adj, assign_x, params):
         adjb, aflags = adj.op, adj.flags
     else:
         adjb, aflags = T.adj_prepare(ws, adj, nb, B, N)   # bf16 operand + [not symmetric, not {0,1}] device flags
-    xb = T.cvt(ws, x.data_ptr(), D, B * N, D, B=B)
+    if x.dtype == torch.bfloat16:          # features already in the operand precision (compact feed): used as they are
+        xb = T.Op(x.data_ptr(), D, N * D, x)
+    else:
+        xb = T.cvt(ws, x.data_ptr(), D, B * N, D, B=B)
     w0, b0 = conv(plan.emb)
     xab, xa_d, pre_as = xb, D, None
     if plan.soft and assign_x is not x:
@@ -835,7 +838,14 @@ class GcnEncoderGraph(nn.Module):
         return pairs
 
     def _base_plan(self, x, adj, batch_num_nodes):
-        x = E._chk(x, 'x')
+        if torch.is_tensor(x) and x.dtype == torch.bfloat16:
+            # compact feed (tensor-core mode only): bf16 features are what the contractions read anyway; the row must
+            # satisfy TMA's 16-byte rule
+            if not (self.precision == T.BF16 and self.concat and x.is_cuda and x.is_contiguous() and x.dim() == 3
+                    and x.shape[2] % 8 == 0):
+                raise ValueError('bfloat16 features need the tensor-core mode, a contiguous CUDA tensor and D % 8 == 0')
+        else:
+            x = E._chk(x, 'x')
         if isinstance(adj, T.PreparedAdjacency):             # bf16 operand built by the feed (tensor-core mode only)
             if not (self.precision == T.BF16 and self.concat):
                 raise ValueError('a PreparedAdjacency needs the tensor-core mode (model.precision = 1)')
@@ -1152,8 +1162,10 @@ class SoftPoolingGcnEncoder(GcnEncoderGraph):
         self._reinit()
 
     def forward(self, x, adj, batch_num_nodes, **kwargs):
+        ax_in = kwargs.get('assign_x')
+        same_ax = ax_in is None or ax_in is x
         plan, params, x, adj = self._base_plan(x, adj, batch_num_nodes)
-        x_a = E._chk(kwargs['assign_x'], 'assign_x') if 'assign_x' in kwargs else x
+        x_a = x if same_ax else E._chk(ax_in, 'assign_x')
         if x_a.shape[:2] != x.shape[:2]:
             raise ValueError('assign_x batch/node dims differ from x')
         plan.soft = True

@@ -98,15 +98,16 @@ class PreparedAdjacency:
         return self
 
     def from_edges(self, edges, eptr, max_edges_per_graph, undirected=True):
-        """The whole batch from its edge lists (device int32 tensors: edges [E,2] graph-local ids, eptr [B+1]): the
+        """The whole batch from its edge lists (device tensors: edges [E,2] graph-local ids, int32 or 16-bit; eptr [B+1] int32): the
         adjacency never exists as fp32 / uint8 anywhere (gp_adj_from_edges)."""
         B, N, _ = self.shape
-        if edges.dtype != torch.int32 or eptr.dtype != torch.int32 or not edges.is_cuda or not eptr.is_cuda:
-            raise ValueError('PreparedAdjacency.from_edges: need CUDA int32 tensors')
+        if edges.dtype not in (torch.int32, torch.int16, torch.uint16) or eptr.dtype != torch.int32 or \
+                not edges.is_cuda or not eptr.is_cuda:
+            raise ValueError('PreparedAdjacency.from_edges: need CUDA tensors, edges int32 or 16-bit, eptr int32')
         if eptr.numel() != B + 1 or not edges.is_contiguous():
             raise ValueError('PreparedAdjacency.from_edges: eptr must have B + 1 entries, edges must be contiguous')
-        call('gp_adj_from_edges', edges.data_ptr(), eptr.data_ptr(), B, N, int(max_edges_per_graph), int(undirected),
-             self.op.ptr, self.op.ld, self.flags.data_ptr(), 0, E._stream())
+        call('gp_adj_from_edges', edges.data_ptr(), int(edges.element_size()), eptr.data_ptr(), B, N,
+             int(max_edges_per_graph), int(undirected), self.op.ptr, self.op.ld, self.flags.data_ptr(), 0, E._stream())
         self._fresh = False
         return self
 

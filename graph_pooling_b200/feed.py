@@ -130,14 +130,17 @@ class HostAdjacencyFeed:
 
 class EdgeListFeed:
     """The plugin's own feed: per step the host hands over the batch's EDGE LISTS (pinned int32
-    [E,2] graph-local ids + eptr [B+1]) and the features; 8 bytes per edge cross PCIe instead of 4 N^2 bytes per graph,
+    [E,2] graph-local ids + eptr [B+1]) and the features; 8 (int32 ids) or 4 (int16 ids) bytes per edge cross PCIe instead of 4 N^2 bytes per graph,
     and gp_adj_from_edges writes the bf16 operand on the device.  Double-buffered like HostAdjacencyFeed: H2D of
     step i+1 on a copy stream while step i computes; copy() waits for the slot's previous consumer."""
 
-    def __init__(self, B, N, device, max_edges):
+    def __init__(self, B, N, device, max_edges, edge_dtype=torch.int32):
         self.B, self.N, self.dev = int(B), int(N), torch.device(device)
         self.max_edges = int(max_edges)
-        self.dedges = [torch.empty(self.max_edges, 2, device=self.dev, dtype=torch.int32) for _ in range(2)]
+        if edge_dtype not in (torch.int32, torch.int16) or (edge_dtype == torch.int16 and self.N > 32768):
+            raise ValueError('edge_dtype: torch.int32, or torch.int16 for N <= 32768')
+        self.edge_dtype = edge_dtype
+        self.dedges = [torch.empty(self.max_edges, 2, device=self.dev, dtype=edge_dtype) for _ in range(2)]
         self.deptr = [torch.empty(self.B + 1, device=self.dev, dtype=torch.int32) for _ in range(2)]
         self.pa = [T.PreparedAdjacency(B, N, self.dev) for _ in range(2)]
         self.ready = [torch.cuda.Event(), torch.cuda.Event()]
@@ -151,8 +154,8 @@ class EdgeListFeed:
     def copy(self, slot, edges_host, eptr_host, max_edges_per_graph, extra=()):
         """H2D (copy stream) of one batch's edge lists; `extra` = [(dst_device_tensor, src_pinned_tensor)]."""
         E_ = int(edges_host.shape[0])
-        if edges_host.dtype != torch.int32 or eptr_host.dtype != torch.int32 or E_ > self.max_edges:
-            raise ValueError('EdgeListFeed.copy: int32 edge lists of at most max_edges edges')
+        if edges_host.dtype != self.edge_dtype or eptr_host.dtype != torch.int32 or E_ > self.max_edges:
+            raise ValueError('EdgeListFeed.copy: edge lists of the feed\'s edge_dtype, at most max_edges edges')
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self.freed[slot])
             for dst, src in extra:

@@ -167,10 +167,11 @@ int gp_softmax_mask_bwd_x(const float* s, const float* ds, const int32_t* nb, in
 int gp_adj_prepare(const void* adj, int adj_dtype, const int32_t* nb, int B, int N, void* adj_bf16, long long ld,
                    int32_t* flags, gp_stream_t stream);
 /* Edge-list feed: the bf16 operand [B,N,ld] straight from the batch's edge lists -- edges [E][2]
- * graph-local node ids (int32, 8-byte aligned), graph b owns edges eptr[b] .. eptr[b+1]; undirected = 1 writes both
- * (u,v) and (v,u).  flags as gp_adj_prepare: [0] = 0 for an undirected list (symmetric by construction), [1] = 0.
- * What graph_sampler.py:97-109 + train.py:197-201 ship as B*N*N*4 bytes becomes 8 bytes per edge. */
-int gp_adj_from_edges(const int32_t* edges, const int32_t* eptr, int B, int N, int max_edges_per_graph,
+ * graph-local node ids of id_bytes = 4 (int32) or 2 (uint16, N <= 65536) bytes each, graph b owns edges
+ * eptr[b] .. eptr[b+1]; undirected = 1 writes both (u,v) and (v,u).  flags as gp_adj_prepare: [0] = 0 for an
+ * undirected list (symmetric by construction), [1] = 0.  What graph_sampler.py:97-109 + train.py:197-201 ship as
+ * B*N*N*4 bytes becomes 4 or 8 bytes per edge. */
+int gp_adj_from_edges(const void* edges, int id_bytes, const int32_t* eptr, int B, int N, int max_edges_per_graph,
                       int undirected, void* adj_bf16, long long ld, int32_t* flags, int accumulate_flags,
                       gp_stream_t stream);
 /* Extended form: adj_dtype 2 = bit-packed rows from gp_host_pack_adj_bits (bit c & 7 of byte c >> 3); ld_in = input

@@ -65,3 +65,26 @@ def test_train_step_through_the_edge_list_feed():
     assert res[0][1] == res[1][1] and res[0][2] == res[1][2]
     # split-K reductions accumulate with atomics: the gradients agree to the last few bits, not bitwise
     assert float((res[0][3] - res[1][3]).norm() / res[0][3].norm()) < 1e-5
+
+
+def test_bf16_features_and_16bit_edges_change_nothing():
+    """The tensor-core schedule rounds the features to bf16 itself: feeding them as bf16 (and the edge ids as int16)
+    gives the bit-identical forward."""
+    from graph_pooling_b200 import encoders, feed
+    B, N, D = 3, 128, 16
+    x, adj, nb, label = synth_batch(4, B, N, D, 20, N, 2, 0.05)
+    e, eptr = _edges(adj, nb)
+    torch.manual_seed(2)
+    m = encoders.SoftPoolingGcnEncoder(N, D, 16, 16, 2, 3, 16, assign_ratio=0.25).cuda()
+    m.precision = 1
+    xc, ac = torch.tensor(x).cuda(), torch.tensor(adj).cuda()
+    with torch.no_grad():
+        y0 = m(xc, ac, nb, assign_x=xc)
+        fd = feed.EdgeListFeed(B, N, 'cuda', max_edges=len(e), edge_dtype=torch.int16)
+        fd.copy(0, torch.tensor(e.astype(np.int16)).pin_memory(), torch.tensor(eptr).pin_memory(), int(np.diff(eptr).max()))
+        xb = xc.to(torch.bfloat16)
+        y1 = m(xb, fd.prepared(0), nb, assign_x=xb)
+    assert torch.equal(y0, y1)
+    m.precision = 0
+    with pytest.raises(ValueError):
+        m(xb, ac, nb, assign_x=xb)
