@@ -102,32 +102,33 @@ __device__ void bn_stats(const gp_pk_src& src, const float* __restrict__ cnt_pad
 
 // rows [r0, r0+nt) of a source -> dst[i*ldd + coff + c], c < d, ReLU + BatchNorm applied when the source has sums.
 // Columns [d, dz) are written as zeros (dz = d rounded up when the slot is the last one of the destination).
-// Four elements per thread are in flight at a time.
+// One warp per row, lane = column (no index arithmetic per element), four rows in flight per warp.
 __device__ void load_rows(const gp_pk_src& src, int r0, int nt, const int* s_gs, const float* s_mean,
                           const float* s_istd, float* dst, int ldd, int coff, int dz) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int d = src.d;
   const bool bn = src.sums != nullptr;
-  const int total = nt * dz;
-  for (int base = threadIdx.x; base < total; base += 4 * blockDim.x) {
-    float v[4];
-    int ii[4], cc[4];
+  const float* base = src.y + (long long)r0 * src.ld;
+  const int ld = (int)src.ld;
+  for (int i0 = wid; i0 < nt; i0 += 4 * nw) {
+    for (int c = lane; c < dz; c += 32) {
+      float v[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int idx = base + j * blockDim.x;
-      ii[j] = idx / dz;
-      cc[j] = idx - ii[j] * dz;
-      v[j] = (idx < total && cc[j] < d) ? __ldg(src.y + (long long)(r0 + ii[j]) * src.ld + cc[j]) : 0.f;
-    }
+      for (int j = 0; j < 4; ++j) {
+        const int i = i0 + j * nw;
+        v[j] = (i < nt && c < d) ? __ldg(base + i * ld + c) : 0.f;
+      }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int idx = base + j * blockDim.x;
-      if (idx < total) {
-        float x = v[j];
-        if (bn && cc[j] < d) {
-          const int ni = ii[j] - s_gs[ii[j]];
-          x = (fmaxf(x, 0.f) - s_mean[ni]) * s_istd[ni];
+      for (int j = 0; j < 4; ++j) {
+        const int i = i0 + j * nw;
+        if (i < nt) {
+          float x = v[j];
+          if (bn && c < d) {
+            const int ni = i - s_gs[i];
+            x = (fmaxf(x, 0.f) - s_mean[ni]) * s_istd[ni];
+          }
+          dst[i * ldd + coff + c] = x;
         }
-        dst[ii[j] * ldd + coff + cc[j]] = x;
       }
     }
   }
@@ -1326,17 +1327,32 @@ pool_bwd_kernel(const gp_pk_pool_args p) {
         __syncthreads();
         gather4(p.adj, p.tl, sb, s_gs, s_gid, s_info, s_ell, bS, ldK, bAS);
         gather4(p.adj_in, p.tl, sb, s_gs, s_gid, s_info_in, s_ell_in, bS, ldK, bAtS);
-        // gz[i][f] = sum_k S[i][k] dX'[g][k][f] + readout scatter   (dX' read through L1: each element serves n_g rows)
-        for (int idx = tid; idx < nt * F; idx += blockDim.x) {
-          const int i = idx / F, f = idx - i * F;
-          const int g = s_gid[i], il = i - s_gs[i];
-          const float* s = bS + i * ldK;
-          const float* dx = p.dxp + (long long)g * K * F + f;
-          float acc = 0.f;
-          for (int k = 0; k < K; ++k) acc = fmaf(s[k], __ldg(dx + (long long)k * F), acc);
-          const long long o = (long long)g * p.ldo + f;
-          if (p.arg[o] == il) acc += p.dout[o];
-          p.gz[(long long)(r0 + i) * F + f] = acc;
+        // gz[i][f] = sum_k S[i][k] dX'[g][k][f] + readout scatter   (dX' read through L1: each element serves n_g rows;
+        // one warp per row, lane = column, two rows in flight)
+        for (int i0 = wid; i0 < nt; i0 += 2 * nw) {
+          const int i1 = i0 + nw < nt ? i0 + nw : i0;
+          const int ga = s_gid[i0], gb2 = s_gid[i1];
+          const float* sa = bS + i0 * ldK;
+          const float* sb2 = bS + i1 * ldK;
+          for (int f = lane; f < F; f += 32) {
+            const float* da = p.dxp + (long long)ga * K * F + f;
+            const float* db = p.dxp + (long long)gb2 * K * F + f;
+            float acc0 = 0.f, acc1 = 0.f;
+            for (int k = 0; k < K; ++k) {
+              acc0 = fmaf(sa[k], __ldg(da), acc0);
+              acc1 = fmaf(sb2[k], __ldg(db), acc1);
+              da += F;
+              db += F;
+            }
+            const long long o0 = (long long)ga * p.ldo + f;
+            if (p.arg[o0] == i0 - s_gs[i0]) acc0 += p.dout[o0];
+            p.gz[(long long)(r0 + i0) * F + f] = acc0;
+            if (i1 != i0) {
+              const long long o1 = (long long)gb2 * p.ldo + f;
+              if (p.arg[o1] == i1 - s_gs[i1]) acc1 += p.dout[o1];
+              p.gz[(long long)(r0 + i1) * F + f] = acc1;
+            }
+          }
         }
         __syncthreads();
         // dS[i][k] = <Z[i], dX'[k]> + <AS[i], dA'[k]> + sum_k2 AtS[i][k2] dA'[k2][k] + dS_ext
