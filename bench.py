@@ -746,8 +746,10 @@ def main():
                      'frac': roof['step_gbs'] / hbm,
                      'what': 'whole train step: compulsory bytes (roofline.py, fp32: adjacency read fwd + bwd, saved '
                              'activations written once and read once) / device time'}
-    step_roof['traffic'] = None
-    step_roof['traffic_note'] = 'step level; the ncu dram bytes of the dominant launch are under dominant_kernel.traffic'
+    step_roof['traffic'] = roof.get('traffic')
+    step_roof['traffic_note'] = ('dram__bytes_read + dram__bytes_write of ONE launch of the dominant kernel '
+                                 '(dominant_kernel: its algorithmic bytes are algorithmic_bytes_per_launch there), from '
+                                 'ncu --set full on the same kernel source (profiles/r2_traffic.json); not a step total')
     step_roof['peak_source'] = src + ' (MEASURED_PEAKS.json)'
     step_roof['kernels'] = kernels_tab
     step_roof['kernels_note'] = ('one extra untimed step, every C-ABI call bracketed by CUDA events (profile.py); rows = '

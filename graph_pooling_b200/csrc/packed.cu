@@ -214,14 +214,6 @@ __device__ __forceinline__ void gemm_tn_acc(const float* __restrict__ A, int lda
   }
 }
 
-__device__ __forceinline__ int tn_groups(int M4, int N4, int cap_floats, int ldc) {
-  const int nblk = M4 * N4;
-  int g = blockDim.x / max(nblk, 1);
-  g = max(1, min(g, 4));
-  while (g > 1 && g * 4 * M4 * ldc > cap_floats) --g;
-  return g;
-}
-
 // value of an upstream-gradient source at (local row i, column c)
 __device__ __forceinline__ float grad_at(const gp_pk_grad& g, int r0, int i, int gid, int ni, int c) {
   float v = 0.f;
