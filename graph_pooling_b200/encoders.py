@@ -109,7 +109,8 @@ def _fwd_tc(ctx, plan, x, adj, assign_x, params):
             Tl, wpb = T.assign_linear_fwd(ws, zab, Fa, B * cur_N, wp, bp, Kp=pad)
             S = Tl.view(B, cur_N, K)
             sb = T.softmax_forward(ws, S, cur_nb, B, cur_N, K)
-            sb, xp, xpb, tb, ap, apb = T.pool_forward(ws, sb, cur_zb, cur_adjb, cur_nb, B, cur_N, K, Fw)
+            sb, xp, xpb, tb, ap, apb = T.pool_forward(ws, sb, cur_zb, cur_adjb, cur_nb, B, cur_N, K, Fw,
+                                                      keep_t=any(ctx.needs_input_grad))
             wq, bq = conv(plan.post[i])
             nbk = None
             if pad:                                      # "node counts" of the pooled level: Kr real clusters of K

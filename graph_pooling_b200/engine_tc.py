@@ -467,13 +467,29 @@ def softmax_forward(ws, S, nb, B, N, K):
     return sb
 
 
-def pool_forward(ws, sb, zb, adjb, nb, B, N, K, Fw):
+def chain_ok(sb, adjb, N, K):
+    """The chained S^T A S kernel (gp_pool_chain_bf16) takes dense per-graph operands and at most 512 clusters."""
+    return K <= 512 and sb.sb == N * sb.ld and adjb.sb == N * adjb.ld and not os.environ.get('GP_NO_CHAIN')
+
+
+def pool_forward(ws, sb, zb, adjb, nb, B, N, K, Fw, keep_t=True):
+    """X' = S^T Z, A' = S^T A S (encoders.py:1278-1279).  K <= 512: A' comes from ONE chained launch that keeps T = S^T A
+    on chip (TMEM -> bf16 shared-memory tile -> second tcgen05.mma); T is written to HBM (bf16, once) only when the
+    backward will need it (`keep_t`).  Larger K: T = S^T A and A' = T S as two launches."""
     nbp, lim = E._p(nb), int(nb is not None)
     xp, xpb = ws.f(B, K, Fw), bfbuf(ws, B, K, Fw)
     tcgemm(sb, MN, zb, MN, K, Fw, N, B, Cf=(xp.data_ptr(), Fw, K * Fw), Cb=xpb, lim=nbp, lim_k=lim)
+    ap, apb = ws.f(B, K, K), bfbuf(ws, B, K, K)
+    if chain_ok(sb, adjb, N, K):
+        tb = bfbuf(ws, B, K, N) if keep_t else None
+        ent = _ORDER.get(nbp) if nbp is not None else None
+        order = ent[0].data_ptr() if (ent is not None and ent[1] == B) else None
+        call('gp_pool_chain_bf16', sb.ptr, C.c_longlong(sb.ld), adjb.ptr, C.c_longlong(adjb.ld), nbp, order, B, N, K,
+             None if tb is None else tb.ptr, C.c_longlong(0 if tb is None else tb.ld), ap.data_ptr(), C.c_longlong(K),
+             apb.ptr, C.c_longlong(apb.ld), E._stream())
+        return sb, xp, xpb, tb, ap, apb
     tb = bfbuf(ws, B, K, N)
     tcgemm(sb, MN, adjb, MN, K, N, N, B, Cb=tb, lim=nbp, lim_k=lim, lim_n=lim)
-    ap, apb = ws.f(B, K, K), bfbuf(ws, B, K, K)
     tcgemm(tb, KM, sb, MN, K, K, N, B, Cf=(ap.data_ptr(), K, K * K), Cb=apb, lim=nbp, lim_k=lim)
     return sb, xp, xpb, tb, ap, apb
 

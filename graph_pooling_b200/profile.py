@@ -70,6 +70,14 @@ class CallProfiler:
                 has_g = bool(_ival(args[9]))
                 return ('linkloss fwd N=%d K=%d batch=%d' % (N, K, B), 2.0 * N * N * K * B,
                         2.0 * B * (N * K + N * N + (N * N if has_g else 0)), 'bf16 S, bf16 adjacency, bf16 G')
+            if name == 'gp_pool_chain_bf16':
+                B, N, K = _ival(args[6]), _ival(args[7]), _ival(args[8])
+                has_t = bool(_ival(args[9]))
+                by = B * (2.0 * N * K + 2.0 * N * N + (2.0 * K * N if has_t else 0.0) +
+                          (4.0 if _ival(args[11]) else 0.0) * K * K + (2.0 if _ival(args[13]) else 0.0) * K * K)
+                return ('chained S^T A S N=%d K=%d batch=%d%s' % (N, K, B, ' (+T store)' if has_t else ''),
+                        2.0 * B * (float(K) * N * N + float(K) * K * N), by,
+                        'bf16 S and adjacency in, fp32 + bf16 A\' out, T on chip' + (' and stored once as bf16' if has_t else ''))
             if name in ('gp_adj_prepare', 'gp_adj_prepare_x'):
                 off = 1 if name.endswith('_x') else 0
                 kind = _ival(args[1])

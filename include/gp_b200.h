@@ -291,6 +291,27 @@ int gp_softmax_mask_bwd(const float* s, const float* ds, const int32_t* nb, int 
                         float* dt, gp_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Chained pooling contraction on tensor cores (encoders.py:1279): A' = S^T A S in ONE launch, the
+ * intermediate T = S^T A staying ON CHIP: a T tile [128 clusters x 128 nodes] is accumulated in TMEM,
+ * converted to bf16 into shared memory in UMMA operand layout and is the A operand of a second
+ * tcgen05.mma that accumulates the A' row block [128 x K] in another TMEM region.  K <= 256: one CTA per
+ * row block.  256 < K <= 512 (the A' row block alone would fill the SM's 512 TMEM columns): a cluster of two
+ * CTAs shares a row block, each accumulates one column half of A', computes every second T tile and pushes
+ * it into the partner's shared memory (bulk DSMEM copy), so every T tile is still computed once.
+ *   s   [B,N,lds] bf16 (masked assignment, pad rows zero), adj [B,N,ldadj] bf16, nb (optional) node counts,
+ *   order (optional) batch permutation for ragged batches (longest first).
+ *   t   (optional, bf16 [B,K,ldt]): training keeps T for the backward (dS += T^T dA'); it is written once
+ *       from the shared-memory tile by a TMA store.  NULL (inference): T never exists in HBM.
+ *       Columns beyond ceil(nb/128)*128 are left untouched (never read: every consumer clips to nb).
+ *   ap  (optional fp32 [B,K,ldap]) / ap_bf16 (optional [B,K,ldapb]): A'.
+ * Strides in elements, operand strides multiples of 8, bases 16-byte aligned.  K <= 512.
+ * ------------------------------------------------------------------------------------------- */
+int gp_pool_chain_bf16(const void* s_bf16, long long lds, const void* adj_bf16, long long ldadj,
+                       const int32_t* nb, const int32_t* order, int B, int N, int K, void* t_bf16,
+                       long long ldt, float* ap, long long ldap, void* ap_bf16, long long ldapb,
+                       gp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Pooling (encoders.py:1278-1279):  X' = S^T Z ;  T = S^T A ;  A' = T S
  *   z row stride ldz (concat buffer, pad rows need no masking because S's pad rows are 0).
  *   t [B,K,N] is saved for backward.
