@@ -11,6 +11,15 @@
 //   chains over [B,N,K] buffers by one pass;
 // * epilogue: TMEM -> registers -> per-warp shared staging tile (transposed, conflict-free) -> fully
 //   coalesced 128-byte global stores (fp32), 64-byte (bf16);
+// * MC == 2 (plain GEMM epilogue, BN = 256): a CTA PAIR (two-CTA cluster, tcgen05 cta_group::2) computes a 256 x 256
+//   tile with ONE UMMA of M = 256 per k-step: CTA r holds rows m0 + 128 r of A and columns n0 + 128 r of B in its
+//   shared memory and rows 128 r .. of the accumulator in its TMEM; the leader CTA's elected thread issues the MMAs for
+//   both SMs.  Per SM and k-step the tensor core then reads 16 KB (A) + 16 KB (half of B) instead of 16 + 32 KB and TMA
+//   writes 32 instead of 48 KB: the single-CTA kernel's shared-memory port carries 96 B/clk of operand reads plus
+//   96 B/clk of TMA writes against 128 B/clk available -- that, not HBM or L2, is what holds it at ~63 % tensor-pipe
+//   activity (a TMA-multicast variant that halved only the L2 -> SM traffic measured no faster).  Both CTAs' TMA
+//   loads complete on the LEADER's `full` barrier; the leader's commits are multicast to both CTAs' `empty` /
+//   `tmem_full` barriers; the partner's epilogue warps arrive remotely on the leader's `tmem_empty`.
 // * EPI == 1: fused link-prediction loss (encoders.py:1311-1331).  The accumulator tile is P = S S^T;
 //   the epilogue does the masked BCE against the bf16 adjacency (coalesced), writes G = dl/dP (bf16) and
 //   one partial sum per epilogue warp; P never touches HBM.  {0,1} adjacency tiles (warp-uniform test)
@@ -54,6 +63,7 @@ struct Params {
   const int32_t* cond; int cond_npairs; float cond_alpha;              // device-side switch (see gp_gemm_bf16x)
   const int32_t* adj_flags; long long sym_total; int sym_per_graph;    // EPI == 1: gp_adj_prepare flags, upper-band tiles
   const int32_t* order;                                                // batch permutation (heaviest graph first) or NULL
+  int pair;                                                            // MC == 2: tiles_m counts 256-row blocks
 };
 
 struct Work {
@@ -95,6 +105,35 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// cta_group::2 forms (CTA pair).  The TMA load writes this CTA's shared memory but completes on `bar`, a shared::cluster
+// address that may name the LEADER CTA's mbarrier.
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t cta_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -175,7 +214,7 @@ __device__ __forceinline__ Work get_work(const Params& p, long long w, int npair
   // ragged batches: walk the graphs from the largest to the smallest (order[] = argsort(-n_b)), so the static
   // round-robin over persistent CTAs deals every CTA the same mix of long and short tiles (longest-first schedule)
   if (p.order != nullptr) k.b = p.order[k.b];
-  k.m0 = mt * BM; k.n0 = nt;        // n0 scaled by BN by the caller
+  k.m0 = mt * (p.pair ? 2 * BM : BM); k.n0 = nt;        // n0 scaled by BN by the caller
   int l = 0x7fffffff;
   if (p.lim != nullptr) l = p.lim[k.b];
   k.Me = p.lim_m ? min(p.M, l) : p.M;
@@ -286,11 +325,12 @@ __device__ __forceinline__ uint4 bce01_row8(const float (&pv)[8], const uint4 aw
 
 // ---- kernel -------------------------------------------------------------------------------------
 // EW epilogue warps (8 or 16): warps 0..EW-1 epilogue, EW = TMA producer, EW+1 = MMA issuer.
-template <int BN, int STAGES, int EPI, int EW>
+template <int BN, int STAGES, int EPI, int EW, int MC = 1>
 __global__ void __launch_bounds__((EW + 2) * 32, 1)
 tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
+  static_assert(MC == 1 || (MC == 2 && EPI == 0 && BN == 256), "the multicast pair exists for the plain BN = 256 GEMM");
   extern __shared__ uint8_t smem_raw[];
-  using L = Smem<BN, STAGES, EW>;
+  using L = Smem<BN / MC, STAGES, EW>;                   // MC == 2: each CTA stages half of the B tile
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));
   float* staging = reinterpret_cast<float*>(smem_gen + STAGES * L::kStage);
@@ -304,6 +344,9 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
       reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * L::kStage + L::kStaging + 8 * (2 * STAGES + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t rank = 0;                                     // MC == 2: this CTA's row block inside the pair, and its half of B
+  if (MC > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const long long w_first = blockIdx.x / MC, w_step = gridDim.x / MC;
   // BN <= 256: two accumulator buffers (the epilogue of tile i overlaps the MMAs of tile i+1).  BN == 512 (row-owning
   // epilogues over rows wider than 256: the assignment GCN's last layer): ONE buffer filling all 512 TMEM columns,
   // two N = 256 MMAs per k-step; MMA and epilogue of a CTA then alternate (the epilogue is HBM-write-bound).
@@ -314,11 +357,17 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
   constexpr int kProd = EW, kMma = EW + 1;
 
   if (warp == kMma) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (MC == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-      for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EW); }   // NACC == 1 uses a = 0
+      // MC == 2: the leader's tmem_empty collects the epilogue warps of BOTH CTAs
+      for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EW * MC); }   // NACC == 1 uses a = 0
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -331,6 +380,7 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
   }
   tc_fence_before();
   __syncthreads();
+  if (MC > 1) cluster_sync_all();                        // the partner's barriers exist before anything is multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
   // device-side switch: when *cond == 0 (e.g. "the adjacency is symmetric", adjprep.cu) only the first cond_npairs
@@ -361,18 +411,38 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
     // ===== TMA producer =====
     if (lane == 0) {
       uint32_t it = 0;                                   // running stage counter across tiles
-      for (long long w = blockIdx.x; w < total_work; w += gridDim.x) {
+      for (long long w = w_first; w < total_work; w += w_step) {
         Work k = get_work<BN>(p, w, npairs, sym_upper);
         finish_work<BN>(p, k, sym_upper);
+        if (MC > 1) k.m0 += (int)rank * BM;             // liveness / k-extent were decided for the pair: lock-step
         int pos = 0;
         for (int q = 0; q < npairs; ++q) {
           const int lo = max(k.kt0, pos), hi = min(k.kt1, pos + k.kt[q]);
           for (int g = lo; g < hi; ++g, ++it) {
             const int s = it % STAGES, ph = (it / STAGES) & 1;
             mbar_wait(empty_bar(s), ph ^ 1);
-            mbar_expect_tx(full_bar(s), L::kStage);
             const uint32_t sa = base + s * L::kStage, sb = sa + L::kA;
             const int k0 = (g - pos) * BK;
+            if (MC > 1) {
+              // both CTAs' boxes complete on the leader's barrier, which the leader arms for the bytes of both
+              if (rank == 0) mbar_expect_tx(full_bar(s), 2 * L::kStage);
+              const uint32_t lbar = map_to_rank(full_bar(s), 0);
+              if (p.a_mn[q]) {
+                tma_load_3d_2sm(sa, &maps.a[q], lbar, k.m0, k0, k.b);
+                tma_load_3d_2sm(sa + 8192, &maps.a[q], lbar, k.m0 + 64, k0, k.b);
+              } else {
+                tma_load_3d_2sm(sa, &maps.a[q], lbar, k0, k.m0, k.b);
+              }
+              const int nh0 = k.n0 + 128 * (int)rank;    // this CTA's half of the B tile
+              if (p.b_mn[q]) {
+                tma_load_3d_2sm(sb, &maps.b[q], lbar, nh0, k0, k.b);
+                tma_load_3d_2sm(sb + 8192, &maps.b[q], lbar, nh0 + 64, k0, k.b);
+              } else {
+                tma_load_3d_2sm(sb, &maps.b[q], lbar, k0, nh0, k.b);
+              }
+              continue;
+            }
+            mbar_expect_tx(full_bar(s), L::kStage);
             if (p.a_mn[q]) {
               tma_load_3d(sa, &maps.a[q], full_bar(s), k.m0, k0, k.b);
               tma_load_3d(sa + 8192, &maps.a[q], full_bar(s), k.m0 + 64, k0, k.b);
@@ -394,10 +464,10 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
       }
     }
   } else if (warp == kMma) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer (MC == 2: the leader CTA issues for the pair) =====
+    if (lane == 0 && (MC == 1 || rank == 0)) {
       uint32_t it = 0, nacc = 0;
-      for (long long w = blockIdx.x; w < total_work; w += gridDim.x) {
+      for (long long w = w_first; w < total_work; w += w_step) {
         Work k = get_work<BN>(p, w, npairs, sym_upper);
         finish_work<BN>(p, k, sym_upper);
         if (k.kt1 <= k.kt0) continue;
@@ -411,7 +481,7 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
           const int lo = max(k.kt0, pos), hi = min(k.kt1, pos + k.kt[q]);
           const bool amn = p.a_mn[q] != 0, bmn = p.b_mn[q] != 0;
           const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((amn ? 1u : 0u) << 15) |
-                                 ((bmn ? 1u : 0u) << 16) | ((uint32_t)(MMA_N >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                                 ((bmn ? 1u : 0u) << 16) | ((uint32_t)(MMA_N >> 3) << 17) | ((uint32_t)((BM * MC) >> 4) << 24);
           for (int g = lo; g < hi; ++g, ++it) {
             const int s = it % STAGES, ph = (it / STAGES) & 1;
             mbar_wait(full_bar(s), ph);
@@ -424,15 +494,16 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
               for (int h = 0; h < NHALF; ++h) {          // N-major B: 64-column groups 8 KB apart; K-major: rows 128 B
                 const uint32_t sbh = sb + (bmn ? h * (MMA_N / 64) * 8192 : h * MMA_N * 128);
                 const uint64_t bd = bmn ? umma_desc(sbh + kk * 2048, 8192, 1024) : umma_desc(sbh + kk * 32, 16, 1024);
-                tc_mma_bf16(tm + h * MMA_N, ad, bd, idesc, (first && kk == 0) ? 0u : 1u);
+                if (MC > 1) tc_mma_bf16_2sm(tm + h * MMA_N, ad, bd, idesc, (first && kk == 0) ? 0u : 1u);
+                else        tc_mma_bf16(tm + h * MMA_N, ad, bd, idesc, (first && kk == 0) ? 0u : 1u);
               }
             }
             first = false;
-            tc_commit(empty_bar(s));
+            if (MC > 1) tc_commit_2sm(empty_bar(s), (uint16_t)3); else tc_commit(empty_bar(s));
           }
           pos += k.kt[q];
         }
-        tc_commit(tfull_bar(a));
+        if (MC > 1) tc_commit_2sm(tfull_bar(a), (uint16_t)3); else tc_commit(tfull_bar(a));
         ++nacc;
       }
     }
@@ -455,9 +526,10 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
     const bool vecCb8 = p.Cb != nullptr && (reinterpret_cast<uintptr_t>(p.Cb) & 15) == 0 && (p.ldCb & 7) == 0 &&
                         (p.sCbb & 7) == 0;
     uint32_t nacc = 0;
-    for (long long w = blockIdx.x; w < total_work; w += gridDim.x) {
+    for (long long w = w_first; w < total_work; w += w_step) {
       Work k = get_work<BN>(p, w, npairs, sym_upper);
       finish_work<BN>(p, k, sym_upper);
+      if (MC > 1) k.m0 += (int)rank * BM;
       const bool has_acc = k.kt1 > k.kt0;
       const uint32_t a = NACC == 2 ? (nacc & 1) : 0u, aph = NACC == 2 ? ((nacc >> 1) & 1) : (nacc & 1);
       if (has_acc) {
@@ -780,17 +852,23 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
       if (has_acc) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(a));
+        if (lane == 0) {
+          if (MC > 1 && rank != 0) mbar_arrive_remote(map_to_rank(tempty_bar(a), 0));
+          else mbar_arrive(tempty_bar(a));
+        }
         ++nacc;
       }
     }
   }
 
+  __syncwarp();
   tc_fence_before();
   __syncthreads();
+  if (MC > 1) cluster_sync_all();                        // nobody exits while the partner may still multicast / arrive here
   if (warp == kMma) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if (MC == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -834,11 +912,48 @@ static int launch(const Maps& maps, Params& p, cudaStream_t st) {
   auto kern = tc_gemm2_kernel<BN, STAGES, EPI, EW>;
   GP_CONFIG_ONCE(GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes)));
   const int split = p.split_k > 1 ? p.split_k : 1;
+  p.pair = 0;
   p.tiles_m = (p.M + BM - 1) / BM;
   p.tiles_n = (p.N + BN - 1) / BN;
   p.total_work = (long long)p.tiles_m * p.tiles_n * p.batch * split;
   const int grid = (int)(p.total_work < kNumSMs ? p.total_work : kNumSMs);
   kern<<<grid, (EW + 2) * 32, L::kBytes, st>>>(maps, p);
+  GP_LAUNCHED();
+  return GP_OK;
+}
+
+// MC == 2: persistent two-CTA clusters, 256-row blocks per cluster
+static int launch_pair(const Maps& maps, Params& p, cudaStream_t st) {
+  using L = Smem<128, 6, 8>;                             // per CTA: 16 KB of A rows + 16 KB (half) of the B tile per stage
+  auto kern = tc_gemm2_kernel<256, 6, 0, 8, 2>;
+  GP_CONFIG_ONCE(GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes)));
+  p.pair = 1;
+  p.tiles_m = (p.M + 2 * BM - 1) / (2 * BM);
+  p.tiles_n = (p.N + 255) / 256;
+  p.total_work = (long long)p.tiles_m * p.tiles_n * p.batch;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.blockDim = dim3(10 * 32);
+  cfg.dynamicSmemBytes = L::kBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  static int max_clusters[64];                           // persistent clusters must all be co-resident
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (max_clusters[dev & 63] == 0) {
+    cfg.gridDim = dim3(kNumSMs / 2 * 2);
+    int mc = 0;
+    if (cudaOccupancyMaxActiveClusters(&mc, kern, &cfg) != cudaSuccess || mc <= 0) { mc = kNumSMs / 4; cudaGetLastError(); }
+    max_clusters[dev & 63] = mc;
+    if (getenv("GP_DEBUG")) fprintf(stderr, "[gp] tc_gemm2 cta pair: smem %d B -> max active clusters %d\n", L::kBytes, mc);
+  }
+  long long ncl = max_clusters[dev & 63];
+  if (ncl > p.total_work) ncl = p.total_work;
+  cfg.gridDim = dim3((unsigned)(ncl * 2));
+  GP_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, p));
   GP_LAUNCHED();
   return GP_OK;
 }
@@ -868,6 +983,11 @@ int run(const gp_gemm_bf16x* g, cudaStream_t st) {
   Maps maps;
   Params p;
   const int BN = pick_bn(g->N);
+  // CTA pair (cta_group::2, UMMA M = 256): plain epilogue, 256-column tiles, no split-K, and a row count whose last
+  // 256-row block is not mostly padding
+  static const bool no_pair = getenv("GP_NO_PAIR") != nullptr;
+  const int t128 = (g->M + BM - 1) / BM, t256 = (g->M + 2 * BM - 1) / (2 * BM);
+  const bool pair = !no_pair && BN == 256 && split == 1 && t128 >= 2 && 2 * t256 * 16 <= t128 * 17;
   for (int q = 0; q < g->npairs; ++q) {
     const gp_operand_pair& o = g->pair[q];
     GP_REQUIRE(o.A && o.B && o.K > 0, "bgemm_bf16x: pair %d: null operand or K <= 0", q);
@@ -877,7 +997,7 @@ int run(const gp_gemm_bf16x* g, cudaStream_t st) {
                "bgemm_bf16x: pair %d: operand base must be 16-byte aligned", q);
     if (o.a_major == 0) GP_TRY(make_map(&maps.a[q], o.A, o.K, g->M, g->batch, o.ldA, o.sAb, BM));
     else                GP_TRY(make_map(&maps.a[q], o.A, g->M, o.K, g->batch, o.ldA, o.sAb, BK));
-    if (o.b_major == 0) GP_TRY(make_map(&maps.b[q], o.B, o.K, g->N, g->batch, o.ldB, o.sBb, BN));
+    if (o.b_major == 0) GP_TRY(make_map(&maps.b[q], o.B, o.K, g->N, g->batch, o.ldB, o.sBb, pair ? 128 : BN));
     else                GP_TRY(make_map(&maps.b[q], o.B, g->N, o.K, g->batch, o.ldB, o.sBb, BK));
     p.K[q] = o.K; p.a_mn[q] = o.a_major; p.b_mn[q] = o.b_major; p.lim_k[q] = o.lim_k;
   }
@@ -905,6 +1025,7 @@ int run(const gp_gemm_bf16x* g, cudaStream_t st) {
     GP_LAUNCHED();
     p.beta = 1.f;
   }
+  if (pair) return launch_pair(maps, p, st);
   if (BN == 256) return launch<256, 4, 0, 8>(maps, p, st);
   if (BN == 128) return launch<128, 6, 0, 8>(maps, p, st);
   return launch<64, 6, 0, 8>(maps, p, st);

@@ -55,3 +55,22 @@ if which in ('all', 'link'):
     nb = torch.full((B,), N, device=dev, dtype=torch.int32)
     timeit('linkloss fused', lambda: T.linkloss_forward(ws, op(s), op(adj), nb, B, N, K, True), 2.0 * B * N * N * K, B * N * N * 4)
     timeit('linkloss fused nograd', lambda: T.linkloss_forward(ws, op(s), op(adj), nb, B, N, K, False), 2.0 * B * N * N * K, B * N * N * 2)
+if which in ('all', 'chain'):
+    # chained A' = S^T A S (gp_pool_chain_bf16) against the two launches it replaces (T = S^T A, A' = T S)
+    import ctypes as C
+    from graph_pooling_b200._lib import call
+    s_ = torch.softmax(torch.randn(B, N, K, device=dev), -1).bfloat16()
+    tb = T.bfbuf(ws, B, K, N)
+    ap = torch.empty(B, K, K, device=dev); apb = T.bfbuf(ws, B, K, K)
+    fl = 2.0 * B * (K * N * N + K * K * N)
+    by_t = B * (N * N + N * K + K * N) * 2 + B * K * K * 6
+    def chain(keep):
+        call('gp_pool_chain_bf16', s_.data_ptr(), C.c_longlong(K), adj.data_ptr(), C.c_longlong(N), None, None, B, N, K,
+             tb.ptr if keep else None, C.c_longlong(tb.ld if keep else 0), ap.data_ptr(), C.c_longlong(K), apb.ptr,
+             C.c_longlong(apb.ld), None)
+    def two():
+        T.tcgemm(op(s_), 1, op(adj), 1, K, N, N, B, Cb=tb)
+        T.tcgemm(tb, 0, op(s_), 1, K, K, N, B, Cf=(ap.data_ptr(), K, K * K), Cb=apb)
+    timeit('two launches T=S^T.A, A\'=T.S', two, fl, by_t + B * K * N * 2)
+    timeit('chained, T stored (training)', lambda: chain(True), fl, by_t)
+    timeit('chained, T on chip only', lambda: chain(False), fl, by_t - B * K * N * 2)

@@ -135,3 +135,41 @@ def test_fused_linkloss_tc(B, N, K, use_nb, sym, weighted, flag):
     mm = m.numpy()
     # G is rounded to bf16 before the backward GEMM: 2^-9 relative per entry
     assert rel_l2(dS.cpu().numpy() * mm, s_t.grad.numpy() * mm) < 4e-3
+
+
+@pytest.mark.parametrize('M,N,batch', [(2048, 512, 3), (1280, 300, 5), (256, 256, 40), (5000, 264, 2)])
+def test_multicast_pair_ragged_multi_pair(M, N, batch):
+    """Shapes that take the CTA-pair schedule (cta_group::2: 256-row blocks, each CTA staging half of every B tile):
+    a dS-style launch with three operand pairs of all major-ness combinations, per-graph limits on M and on one
+    contraction, beta = 1 and a bf16 copy; more work items than resident clusters at batch 40."""
+    rs = np.random.RandomState(M + N)
+    K1, K2 = 192, 136
+    lim_np = rs.randint(1, M + 1, size=batch).astype(np.int32)
+    lim_np[0] = M
+    A1, A1v = store(rs.randn(batch, M, K1), 0)
+    B1, B1v = store(rs.randn(batch, N, K1), 0)
+    A2, A2v = store(rs.randn(batch, M, K2), 1)
+    B2, B2v = store(rs.randn(batch, N, K2), 1)
+    A3h = rs.randn(batch, M, M) * 0.1
+    for b in range(batch):
+        A3h[b, :, lim_np[b]:] = 0
+    A3, A3v = store(A3h, 0)
+    B3, B3v = store(rs.randn(batch, N, M), 1)
+    C0 = torch.randn(batch, M, N, device='cuda')
+    out = C0.clone()
+    ob = torch.zeros(batch, M, r8(N), device='cuda', dtype=torch.bfloat16)
+    lim = torch.tensor(lim_np).cuda()
+    T().tcgemm_multi([(op(A1), 0, op(B1), 0, K1, 0), (op(A2), 1, op(B2), 1, K2, 0), (op(A3), 0, op(B3), 1, M, 1)],
+                     M, N, batch, Cf=(out.data_ptr(), N, M * N), Cb=op(ob), lim=lim.data_ptr(), lim_m=1, alpha=0.5,
+                     beta=1.0)
+    torch.cuda.synchronize()
+    ref = C0.cpu().double().numpy().copy()
+    full = 0.5 * (A1v @ np.swapaxes(B1v, 1, 2) + A2v @ np.swapaxes(B2v, 1, 2) + A3v @ np.swapaxes(B3v, 1, 2))
+    for b in range(batch):
+        ref[b, :lim_np[b]] += full[b, :lim_np[b]]
+    assert rel_l2(out.cpu().numpy(), ref) < 2e-5      # contractions up to 5000 terms long in fp32
+    assert rel_l2(ob.float().cpu().numpy()[:, :, :N], ref) < 4e-3
+
+
+def r8(n):
+    return (n + 7) & ~7
