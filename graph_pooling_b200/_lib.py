@@ -49,7 +49,7 @@ class GpGemmBf16x(C.Structure):
                 ('lim', c_f), ('lim_m', c_i), ('lim_n', c_i),
                 ('alpha', C.c_float), ('beta', C.c_float), ('alpha_dev', c_f),
                 ('bias', c_f), ('relu', c_i), ('split_k', c_i),
-                ('cond', c_f), ('cond_npairs', c_i), ('cond_alpha', C.c_float), ('order', c_f)]
+                ('cond', c_f), ('cond_npairs', c_i), ('cond_alpha', C.c_float), ('order', c_f), ('tri', c_i)]
 
 
 class GpAxpyEntry(C.Structure):

@@ -64,11 +64,14 @@ struct Params {
   const int32_t* adj_flags; long long sym_total; int sym_per_graph;    // EPI == 1: gp_adj_prepare flags, upper-band tiles
   const int32_t* order;                                                // batch permutation (heaviest graph first) or NULL
   int pair;                                                            // MC == 2: tiles_m counts 256-row blocks
+  int tri;                                                             // see gp_gemm_bf16x.tri
+  int upper_only;                                                      // EPI == 1: gp_linkloss_tc mode bit 1
 };
 
 struct Work {
   int b, ks, m0, n0, Me, Ne;
   int kt[kMaxPairs];     // k-tiles per pair (after clipping)
+  int kb[kMaxPairs];     // first k-tile of each pair (non-zero only in `tri` mode)
   int kt0, kt1;          // this split's range over the concatenated k-tile sequence
 };
 
@@ -181,7 +184,7 @@ struct Smem {
 };
 
 template <int BN>
-__device__ __forceinline__ Work get_work(const Params& p, long long w, int npairs, bool sym_upper) {
+__device__ __forceinline__ Work get_work(const Params& p, long long w, int npairs, bool sym_upper, bool tri = false) {
   Work k;
   const int split = p.split_k > 1 ? p.split_k : 1;
   int nt, mt, z;
@@ -191,7 +194,7 @@ __device__ __forceinline__ Work get_work(const Params& p, long long w, int npair
     if (w >= p.sym_total) {
       k.b = 0; k.ks = 0; k.m0 = 0; k.n0 = 0; k.Me = 0; k.Ne = 0;
 #pragma unroll
-      for (int q = 0; q < kMaxPairs; ++q) k.kt[q] = 0;
+      for (int q = 0; q < kMaxPairs; ++q) { k.kt[q] = 0; k.kb[q] = 0; }
       k.kt0 = k.kt1 = 0;
       return k;
     }
@@ -222,12 +225,20 @@ __device__ __forceinline__ Work get_work(const Params& p, long long w, int npair
   int tot = 0;
 #pragma unroll
   for (int q = 0; q < kMaxPairs; ++q) {
-    int t = 0;
+    int t = 0, kb = 0;
     if (q < npairs) {
       const int Ke = p.lim_k[q] ? min(p.K[q], l) : p.K[q];
       t = (Ke + BK - 1) / BK;
+      if (tri) {
+        // symmetric operand stored as its upper band only: pair 0 reads A[m, k] for k >= c0, pair 1 reads the
+        // transposed stripe A[k, m] for k < c0 (c0 = start of the 256-wide diagonal block of this row block)
+        const int c0t = (k.m0 / 256) * (256 / BK);
+        if (q == 0) { kb = min(c0t, t); t -= kb; }
+        else if (q == 1) t = min(c0t, t);
+      }
     }
     k.kt[q] = t;
+    k.kb[q] = kb;
     tot += t;
   }
   k.kt0 = tot; k.kt1 = tot;          // filled by finish_work once n0 is known
@@ -323,6 +334,42 @@ __device__ __forceinline__ uint4 bce01_row8(const float (&pv)[8], const uint4 aw
   return make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]), pack_bf16x2(g[6], g[7]));
 }
 
+__device__ __forceinline__ void ldg256_stream(const void* p, uint32_t (&v)[8]) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+// Row form of the {0,1} BCE (one lane owns 16 consecutive entries of ONE row: P values straight from TMEM, the
+// adjacency as 8 words of packed bf16): same arithmetic as bce01_row8.  MASK: entries e >= nvalid contribute nothing.
+template <bool MASK>
+__device__ __forceinline__ void bce01_row16(const uint32_t* pv, const uint32_t (&aw)[8], int nvalid, float* l2,
+                                            uint32_t (&gw)[8]) {
+  float acc = 0.f;
+#pragma unroll
+  for (int h = 0; h < 8; ++h) {
+    float g[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const uint32_t bits = e ? (aw[h] >> 16) : (aw[h] & 0xffffu);
+      const bool one = bits != 0u;
+      const float pval = __uint_as_float(pv[2 * h + e]);
+      const float s = one ? 1.f : -1.f;
+      const float x = fmaf(s, fminf(pval, 1.f), one ? kEpsLink : 1.f + kEpsLink);
+      float ll = lg2_approx(x);
+      float gg = -s * rcp_approx(x);
+      if (pval > 1.f) gg = 0.f;
+      if (MASK && 2 * h + e >= nvalid) { gg = 0.f; ll = 0.f; }
+      acc += ll;
+      g[e] = gg;
+    }
+    gw[h] = pack_bf16x2(g[0], g[1]);
+  }
+  *l2 += acc;
+}
+
 // ---- kernel -------------------------------------------------------------------------------------
 // EW epilogue warps (8 or 16): warps 0..EW-1 epilogue, EW = TMA producer, EW+1 = MMA issuer.
 template <int BN, int STAGES, int EPI, int EW, int MC = 1>
@@ -388,7 +435,7 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
   int npairs = p.npairs;
   float alpha_mul = 1.f;
   long long total_work = p.total_work;
-  bool sym_upper = false, adj01 = false;
+  bool sym_upper = false, adj01 = false, tri_on = false, row_mode = false;
   if (EPI == 1) {
     if (p.adj_flags != nullptr) {
       // link loss over a symmetric adjacency: compute the upper band only, mirror the rest (BCE mode: the
@@ -396,10 +443,12 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
       sym_upper = p.adj_flags[0] == 0 && p.link_mode == 0;
       adj01 = p.adj_flags[1] == 0;
     }
+    row_mode = sym_upper && adj01 && p.upper_only != 0;
   } else if (p.cond != nullptr && *p.cond == 0) {
     npairs = p.cond_npairs;
     alpha_mul = p.cond_alpha;
     if (npairs == 0) total_work = 0;
+    tri_on = p.tri != 0;
   }
   float* sbias = reinterpret_cast<float*>(smem_gen + STAGES * L::kStage + L::kStaging + 256);
   if (EPI == 2) {                                        // bias (zero beyond N) staged once per CTA
@@ -412,7 +461,7 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
     if (lane == 0) {
       uint32_t it = 0;                                   // running stage counter across tiles
       for (long long w = w_first; w < total_work; w += w_step) {
-        Work k = get_work<BN>(p, w, npairs, sym_upper);
+        Work k = get_work<BN>(p, w, npairs, sym_upper, tri_on);
         finish_work<BN>(p, k, sym_upper);
         if (MC > 1) k.m0 += (int)rank * BM;             // liveness / k-extent were decided for the pair: lock-step
         int pos = 0;
@@ -422,7 +471,7 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
             const int s = it % STAGES, ph = (it / STAGES) & 1;
             mbar_wait(empty_bar(s), ph ^ 1);
             const uint32_t sa = base + s * L::kStage, sb = sa + L::kA;
-            const int k0 = (g - pos) * BK;
+            const int k0 = (k.kb[q] + g - pos) * BK;
             if (MC > 1) {
               // both CTAs' boxes complete on the leader's barrier, which the leader arms for the bytes of both
               if (rank == 0) mbar_expect_tx(full_bar(s), 2 * L::kStage);
@@ -468,7 +517,7 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
     if (lane == 0 && (MC == 1 || rank == 0)) {
       uint32_t it = 0, nacc = 0;
       for (long long w = w_first; w < total_work; w += w_step) {
-        Work k = get_work<BN>(p, w, npairs, sym_upper);
+        Work k = get_work<BN>(p, w, npairs, sym_upper, tri_on);
         finish_work<BN>(p, k, sym_upper);
         if (k.kt1 <= k.kt0) continue;
         const uint32_t a = NACC == 2 ? (nacc & 1) : 0u, aph = NACC == 2 ? ((nacc >> 1) & 1) : (nacc & 1);
@@ -527,7 +576,7 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
                         (p.sCbb & 7) == 0;
     uint32_t nacc = 0;
     for (long long w = w_first; w < total_work; w += w_step) {
-      Work k = get_work<BN>(p, w, npairs, sym_upper);
+      Work k = get_work<BN>(p, w, npairs, sym_upper, tri_on);
       finish_work<BN>(p, k, sym_upper);
       if (MC > 1) k.m0 += (int)rank * BM;
       const bool has_acc = k.kt1 > k.kt0;
@@ -636,6 +685,42 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
         if (row0 >= p.M || nbase >= p.N) continue;       // warp-uniform
         if (EPI == 1 && !has_acc) continue;
         if (EPI == 0 && !has_acc && beta == 1.f && p.bias == nullptr && p.Cb == nullptr) continue;   // nothing to add
+        if (EPI == 1 && row_mode) {
+          // ---- symmetric {0,1} adjacency, G kept as its upper band only (mode bit 1): lane = row, no shared-memory
+          // staging and no mirrored chunks -- P straight from TMEM, 64 contiguous bytes of adjacency in, 64 bytes of G
+          // out per lane and chunk (two 32-byte accesses each); the consumer (gp_bgemm_bf16x.tri) reads the band twice
+          const int row = row0 + lane;                   // < p.M: N is a multiple of 32 in this mode
+          const __nv_bfloat16* arow = p.adjb + (long long)k.b * p.sadjb + (long long)row * p.ldadj + nbase;
+          __nv_bfloat16* grow = p.Cb != nullptr ? p.Cb + (long long)k.b * p.sCbb + (long long)row * p.ldCb + nbase : nullptr;
+          const bool interior = row0 + 32 <= k.Me && nbase + 32 <= k.Ne;   // warp-uniform
+          const bool mirror = (row0 / BN) * BN + BN <= (nbase / BM) * BM;  // the mirror image lies in a skipped tile
+          float l2 = 0.f;
+          if (interior) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              uint32_t aw[8], gw[8];
+              ldg256_stream(arow + 16 * hh, aw);
+              bce01_row16<false>(&v[16 * hh], aw, 16, &l2, gw);
+              if (grow != nullptr) stg256(grow + 16 * hh, gw);
+            }
+          } else {
+            const int nv = row < k.Me ? max(0, min(32, k.Ne - nbase)) : 0;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              uint32_t aw[8], gw[8];
+              if (nv > 16 * hh) ldg256_stream(arow + 16 * hh, aw);
+              else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) aw[e] = 0u;
+              }
+              bce01_row16<true>(&v[16 * hh], aw, nv - 16 * hh, &l2, gw);
+              if (grow != nullptr) stg256(grow + 16 * hh, gw);
+            }
+          }
+          if (mirror) l2 *= 2.f;                         // the mirrored entries' loss terms are identical
+          lsum = fmaf(l2, -0.69314718055994531f, lsum);
+          continue;
+        }
         // registers (lane = row) -> staging tile [32 rows][32], swizzled; float4 stores, conflict-free
 #pragma unroll
         for (int q = 0; q < 8; ++q)
@@ -1016,6 +1101,9 @@ int run(const gp_gemm_bf16x* g, cudaStream_t st) {
   p.cond = g->cond; p.cond_npairs = g->cond_npairs; p.cond_alpha = g->cond_alpha;
   p.adj_flags = nullptr; p.sym_total = 0; p.sym_per_graph = 0;
   p.order = g->order;
+  p.tri = g->tri; p.upper_only = 0;
+  GP_REQUIRE(g->tri == 0 || (g->npairs == 2 && g->cond != nullptr && g->cond_npairs == 2 && split == 1),
+             "bgemm_bf16x: tri needs exactly two operand pairs, a cond flag with cond_npairs == 2 and no split-K");
   GP_REQUIRE(g->cond == nullptr || (g->cond_npairs >= 0 && g->cond_npairs <= g->npairs), "bgemm_bf16x: bad cond_npairs");
   if (split > 1 && p.beta != 1.f) {
     const long long total = (long long)g->batch * g->M * g->N;
@@ -1060,7 +1148,7 @@ int run_norm(const gp_gemm_bf16x* g, float* rnorm, float* rowstat, int stat_relu
   p.adjb = nullptr; p.ldadj = p.sadjb = 0; p.partial = nullptr; p.link_mode = 0;
   p.rnorm = rnorm; p.rowstat = reinterpret_cast<float2*>(rowstat); p.stat_relu = stat_relu;
   p.cond = nullptr; p.cond_npairs = 0; p.cond_alpha = 1.f;
-  p.adj_flags = nullptr; p.sym_total = 0; p.sym_per_graph = 0; p.order = nullptr;
+  p.adj_flags = nullptr; p.sym_total = 0; p.sym_per_graph = 0; p.order = nullptr; p.tri = 0; p.upper_only = 0;
   if (BN == 512) return launch<512, 2, 2, 4>(maps, p, st);
   if (BN == 256) return launch<256, 3, 2, 4>(maps, p, st);
   return launch<128, 4, 2, 4>(maps, p, st);
@@ -1070,7 +1158,14 @@ int run_linkloss(const void* s_bf16, long long lds, const void* adj_bf16, long l
                  int B, int N, int K, float* partial, void* g_bf16, long long ldg, int mode, const int32_t* adj_flags,
                  cudaStream_t st) {
   GP_REQUIRE(s_bf16 && adj_bf16 && partial && B > 0 && N > 0 && K > 0, "linkloss_tc: bad args");
-  GP_REQUIRE(mode == 0 || mode == 1, "linkloss_tc: mode must be 0 (BCE) or 1 (Frobenius)");
+  GP_REQUIRE(mode == 0 || mode == 1 || mode == 2, "linkloss_tc: mode must be 0 (BCE), 1 (Frobenius) or 2 (BCE, upper-band G)");
+  const int upper_only = mode == 2;
+  if (upper_only) {
+    mode = 0;
+    GP_REQUIRE(adj_flags != nullptr && N % 32 == 0 && ldadj % 16 == 0 && (g_bf16 == nullptr || ldg % 16 == 0) &&
+                   (reinterpret_cast<uintptr_t>(adj_bf16) & 31) == 0 && (reinterpret_cast<uintptr_t>(g_bf16) & 31) == 0,
+               "linkloss_tc: mode 2 needs adj_flags, N % 32 == 0 and 32-byte aligned adjacency / G rows");
+  }
   GP_REQUIRE(lds % 8 == 0 && (g_bf16 == nullptr || ldg >= N), "linkloss_tc: bad strides");
   Maps maps;
   Params p;
@@ -1087,7 +1182,7 @@ int run_linkloss(const void* s_bf16, long long lds, const void* adj_bf16, long l
   p.partial = partial; p.link_mode = mode;
   p.rnorm = nullptr; p.rowstat = nullptr; p.stat_relu = 0;
   p.cond = nullptr; p.cond_npairs = 0; p.cond_alpha = 1.f;
-  p.adj_flags = adj_flags; p.order = nullptr;
+  p.adj_flags = adj_flags; p.order = nullptr; p.tri = 0; p.upper_only = upper_only;
   {
     const int tm = (N + BM - 1) / BM, tn = (N + 255) / 256;
     int per = 0;

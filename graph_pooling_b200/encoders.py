@@ -466,8 +466,9 @@ class _LossFn(torch.autograd.Function):
                 ctx.pk = (adj, inv, inv_dev) if need_grad else None
                 npart = 0
             elif ctx.sb is not None:                    # GP_BF16: P = S S^T on tensor cores, loss in the epilogue
-                partial, npart, gsym = T.linkloss_forward(ws, ctx.sb, plan.adjb, plan.nb_dev, Bn, N, K, need_grad,
-                                                          mode=int(frob), adj_flags=getattr(plan, 'adj_flags', None))
+                partial, npart, gsym, ctx.g_upper = T.linkloss_forward(ws, ctx.sb, plan.adjb, plan.nb_dev, Bn, N, K,
+                                                                       need_grad, mode=int(frob),
+                                                                       adj_flags=getattr(plan, 'adj_flags', None))
             else:
                 nt = (N + 63) // 64
                 npart = Bn * nt * nt
@@ -543,7 +544,8 @@ class _LossFn(torch.autograd.Function):
                          ssb.ptr, ssb.ld, ssb.ld, st)
                     dS = T.linkloss_backward(ws, ctx.gsym, ssb, ctx.nb, Bn, N, K, 1.0, None, asym=ctx.asym)
                 else:
-                    dS = T.linkloss_backward(ws, ctx.gsym, ctx.sb, ctx.nb, Bn, N, K, ctx.inv, g_link.data_ptr(), asym=ctx.asym)
+                    dS = T.linkloss_backward(ws, ctx.gsym, ctx.sb, ctx.nb, Bn, N, K, ctx.inv, g_link.data_ptr(), asym=ctx.asym,
+                                             upper=getattr(ctx, 'g_upper', False))
             else:
                 dS = ws.f(Bn, N, K)
                 if frob:

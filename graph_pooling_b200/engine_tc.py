@@ -113,7 +113,7 @@ class PreparedAdjacency:
 
 
 def tcgemm_multi(pairs, M, N, batch, Cf=None, Cb=None, lim=None, lim_m=0, lim_n=0, alpha=1.0, beta=0.0,
-                 alpha_dev=None, bias=None, relu=0, split_k=0, cond=None, cond_npairs=0, cond_alpha=1.0):
+                 alpha_dev=None, bias=None, relu=0, split_k=0, cond=None, cond_npairs=0, cond_alpha=1.0, tri=0):
     """One persistent tcgen05 launch accumulating sum_q A_q.B_q (gp_bgemm_bf16x).
     pairs: [(A Op, a_major, B Op, b_major, K, lim_k)]; Cf = (ptr, ld, sb) fp32 out, Cb = Op bf16 out."""
     g = GpGemmBf16x()
@@ -133,6 +133,7 @@ def tcgemm_multi(pairs, M, N, batch, Cf=None, Cb=None, lim=None, lim_m=0, lim_n=
     g.alpha, g.beta, g.alpha_dev = alpha, beta, alpha_dev
     g.bias, g.relu, g.split_k = bias, relu, split_k
     g.cond, g.cond_npairs, g.cond_alpha = cond, cond_npairs, cond_alpha
+    g.tri = tri
     ent = _ORDER.get(lim) if lim is not None else None
     g.order = ent[0].data_ptr() if (ent is not None and ent[1] == batch) else None   # longest-first walk (ragged)
     call('gp_bgemm_bf16x', C.byref(g), E._stream())
@@ -580,25 +581,37 @@ def assign_head_bwd(ws, S, ds, nb, B, N, zab, Fa, wpb, K, has_bias, Kreal=0, Fa_
     return dwp, dbp, dza
 
 
+def upper_band_ok(sb, adjb, N, mode, adj_flags):
+    """gp_linkloss_tc mode 2 / gp_gemm_bf16x.tri: for a symmetric {0,1} adjacency (decided on the device from the
+    gp_adj_prepare flags) G = dl/dP is written as its upper diagonal band only and the backward reads that band twice
+    (once transposed).  Needs the BCE loss, the flags, N a multiple of 32 and 32-byte aligned rows."""
+    return (mode == 0 and adj_flags is not None and N % 32 == 0 and adjb.ld % 16 == 0 and adjb.ptr % 32 == 0 and
+            not os.environ.get('GP_NO_UPPER_G'))
+
+
 def linkloss_forward(ws, sb, adjb, nb, B, N, K, need_grad, mode=0, adj_flags=None):
     """Fused tensor-core link loss: P = S S^T tiles stay in TMEM, the epilogue does the masked BCE
-    against the bf16 adjacency and writes gsym (bf16).  Returns (partial, n_partial, gsym op)."""
+    against the bf16 adjacency and writes gsym (bf16).  Returns (partial, n_partial, gsym op, upper)."""
     nbp = E._p(nb)
     npart = int(load().gp_linkloss_tc_partials(B, N))
     partial = ws.f(npart + 256)                      # +256: scratch of the two-stage finalisation
     gs = bfbuf(ws, B, N, N) if need_grad else None
+    upper = upper_band_ok(sb, adjb, N, mode, adj_flags) and (gs is None or (gs.ld % 16 == 0 and gs.ptr % 32 == 0))
     call('gp_linkloss_tc', sb.ptr, sb.ld, adjb.ptr, adjb.ld, nbp, B, N, K, partial.data_ptr(),
-         None if gs is None else gs.ptr, N if gs is None else gs.ld, mode, E._p(adj_flags), E._stream())
-    return partial, npart, gs
+         None if gs is None else gs.ptr, N if gs is None else gs.ld, 2 if upper else mode, E._p(adj_flags), E._stream())
+    return partial, npart, gs, upper
 
 
-def linkloss_backward(ws, gs, sb, nb, B, N, K, inv, g_ptr, dS=None, asym=None):
+def linkloss_backward(ws, gs, sb, nb, B, N, K, inv, g_ptr, dS=None, asym=None, upper=False):
     nbp, lim = E._p(nb), int(nb is not None)
     if dS is None:
         dS = ws.f(B, N, K)
     # dS = (G + G^T).S : G K-major, then the same buffer read M-major (= G^T), accumulated.  A symmetric adjacency
-    # makes G symmetric (P = S S^T is): the kernel then runs the first product only, with alpha doubled.
+    # makes G symmetric (P = S S^T is): the kernel then runs ONE full contraction with alpha doubled -- the first
+    # product only, or (`upper`: G holds its upper diagonal band only) the band read directly for k >= the row
+    # block's diagonal and transposed for k below it (gp_gemm_bf16x.tri).
     cf = (dS.data_ptr(), K, N * K)
     tcgemm_multi([(gs, KM, sb, MN, N, lim), (gs, MN, sb, MN, N, lim)], N, K, B, Cf=cf, alpha=inv, alpha_dev=g_ptr,
-                 lim=nbp, lim_m=lim, cond=E._p(asym), cond_npairs=1, cond_alpha=2.0)
+                 lim=nbp, lim_m=lim, cond=E._p(asym), cond_npairs=2 if upper else 1, cond_alpha=2.0,
+                 tri=1 if upper else 0)
     return dS

@@ -68,8 +68,13 @@ class CallProfiler:
             if name == 'gp_linkloss_tc':
                 B, N, K = _ival(args[5]), _ival(args[6]), _ival(args[7])
                 has_g = bool(_ival(args[9]))
-                return ('linkloss fwd N=%d K=%d batch=%d' % (N, K, B), 2.0 * N * N * K * B,
-                        2.0 * B * (N * K + N * N + (N * N if has_g else 0)), 'bf16 S, bf16 adjacency, bf16 G')
+                f, tag = 1.0, ''
+                if _ival(args[11]) == 2:        # symmetric {0,1} adjacency: only the upper diagonal band is computed / written
+                    tm, tn = (N + 127) // 128, (N + 255) // 256
+                    f = sum(max(0, tn - (mt * 128) // 256) for mt in range(tm)) / float(tm * tn)
+                    tag = ' upper band (%.0f %% of the tiles, if the batch is symmetric {0,1})' % (100 * f)
+                return ('linkloss fwd N=%d K=%d batch=%d%s' % (N, K, B, tag), 2.0 * N * N * K * B * f,
+                        2.0 * B * (N * K + f * N * N + (f * N * N if has_g else 0)), 'bf16 S, bf16 adjacency, bf16 G')
             if name == 'gp_pool_chain_bf16':
                 B, N, K = _ival(args[6]), _ival(args[7]), _ival(args[8])
                 has_t = bool(_ival(args[9]))

@@ -135,6 +135,12 @@ typedef struct gp_gemm_bf16x {
   /* optional device permutation of the batch index (e.g. argsort(-nb)): ragged batches are walked from the largest
    * graph to the smallest, so the static round-robin over persistent CTAs stays balanced (longest-first). */
   const int32_t* order;
+  /* tri = 1 (two pairs reading the SAME symmetric M x M operand, e.g. dS = (G + G^T) S with the link-loss gradient G;
+   * needs cond with cond_npairs == 2): when *cond == 0 the operand is taken to be stored as its upper diagonal band
+   * only (what gp_linkloss_tc writes in mode 2): for the row block starting at m0, pair 0 (A K-major) contracts over
+   * k >= c0 and pair 1 (the same buffer read M-major, i.e. transposed) over k < c0, with c0 = floor(m0 / 256) * 256 --
+   * together one full contraction, so cond_alpha carries the factor 2.  When *cond != 0 both pairs run in full. */
+  int tri;
 } gp_gemm_bf16x;
 int gp_bgemm_bf16x(const gp_gemm_bf16x* g, gp_stream_t stream);
 /* Fused GraphConv tail on tensor cores (encoders.py:322-326): one operand pair, batch == 1, N <= 256:

@@ -33,6 +33,7 @@ for name, asym in (('general', None), ('adjacency flags', flags)):
         out['r'] = T.linkloss_forward(ws, sb, adjb, None, B, N, K, True, adj_flags=asym)
     t = timeit(fwd)
     gs = out['r'][2]
-    tb = timeit(lambda: T.linkloss_backward(ws, gs, sb, None, B, N, K, 1e-6, one.data_ptr(), asym=None if asym is None else asym[0:1]))
+    up = out['r'][3]
+    tb = timeit(lambda: T.linkloss_backward(ws, gs, sb, None, B, N, K, 1e-6, one.data_ptr(), asym=None if asym is None else asym[0:1], upper=up))
     fl = 2.0 * B * N * N * K
     print('%-15s fwd %.3f ms (%.0f TFLOP/s of the full P)   bwd %.3f ms' % (name, t, fl / t / 1e9, tb))

@@ -101,7 +101,11 @@ def test_split_k_bias_relu():
 @pytest.mark.parametrize('B,N,K,use_nb,sym,weighted,flag', [
     (3, 300, 40, 1, 1, 0, 0), (2, 512, 128, 1, 0, 0, 0), (2, 260, 16, 0, 1, 0, 0), (2, 200, 24, 1, 0, 1, 0),
     # symmetric adjacency with the device flag: upper-band tiles only, mirrored G chunks, single-product backward
-    (3, 300, 40, 1, 1, 0, 1), (2, 768, 64, 1, 1, 0, 1), (2, 1024, 32, 0, 1, 0, 1), (2, 520, 24, 1, 1, 1, 1)])
+    (3, 300, 40, 1, 1, 0, 1), (2, 768, 64, 1, 1, 0, 1), (2, 1024, 32, 0, 1, 0, 1), (2, 520, 24, 1, 1, 1, 1),
+    # N a multiple of 32, symmetric {0,1}: G kept as its upper band only (mode 2), backward through gp_gemm_bf16x.tri;
+    # the weighted one keeps the mirrored writes but its backward still reads the band twice
+    (3, 288, 40, 1, 1, 0, 1), (2, 2048, 64, 1, 1, 0, 1), (4, 640, 24, 0, 1, 0, 1), (2, 544, 24, 1, 1, 1, 1),
+    (5, 1280, 136, 1, 1, 0, 1)])
 def test_fused_linkloss_tc(B, N, K, use_nb, sym, weighted, flag):
     """gp_linkloss_tc + the (G + G^T).S backward vs the fp64 oracle on bf16-rounded S / adjacency."""
     from graph_pooling_b200._lib import call
@@ -123,13 +127,15 @@ def test_fused_linkloss_tc(B, N, K, use_nb, sym, weighted, flag):
     nbc = torch.tensor(nb).cuda() if use_nb else None
     ws = __import__('graph_pooling_b200.engine', fromlist=['x']).Workspace(torch.device('cuda'))
     asym = torch.tensor([0, int(bool(weighted))], device='cuda', dtype=torch.int32) if flag else None   # gp_adj_prepare flags
-    partial, npart, gs = t.linkloss_forward(ws, op(sb), op(ab), nbc, B, N, K, True, adj_flags=asym)
+    partial, npart, gs, upper = t.linkloss_forward(ws, op(sb), op(ab), nbc, B, N, K, True, adj_flags=asym)
+    assert upper == bool(flag and N % 32 == 0)
     entries = float(np.sum(nb.astype(np.int64) ** 2)) if use_nb else float(B * N * N)
     total, link = torch.empty(1, device='cuda'), torch.empty(1, device='cuda')
     call('gp_loss_finalize', partial.data_ptr(), npart, C.c_double(1.0 / entries), None, total.data_ptr(),
          link.data_ptr(), torch.cuda.current_stream().cuda_stream)
     one = torch.ones(1, device='cuda')
-    dS = t.linkloss_backward(ws, gs, op(sb), nbc, B, N, K, 1.0 / entries, one.data_ptr(), asym=None if asym is None else asym[0:1])
+    dS = t.linkloss_backward(ws, gs, op(sb), nbc, B, N, K, 1.0 / entries, one.data_ptr(), asym=None if asym is None else asym[0:1],
+                             upper=upper)
     torch.cuda.synchronize()
     assert abs(link.item() - lo.item()) < 2e-5 * abs(lo.item())          # __logf + fp32 sums
     mm = m.numpy()
