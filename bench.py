@@ -692,7 +692,7 @@ def main():
     roof['algorithmic_flops_per_launch'] = kfl
     roof['arithmetic_intensity_flop_per_byte'] = ai
     roof['kernel'] = '%s (U = A.%s, N=%d, %d columns, batch=%d)' % (
-        ('gp::v2::tc_gemm2_kernel<%s,0,8> tcgen05+TMA persistent' % ('256,4' if cols > 128 else '128,6'))
+        ('gp::v2::tc_gemm2_kernel<%s> tcgen05+TMA persistent' % ('256,6,0,8,2 (cta_group::2 CTA pair, UMMA M=256)' if cols > 128 else '128,6,0,8'))
         if prec == 'bf16' else ('gp::gconv_small_fwd_kernel: fused per-graph GraphConv layer, V = (A.X).W + b, normalize;'
                                 if small_fused else 'gp::bgemm_kernel FFMA'), '[h|a]' if dual else 'X', N, cols, B)
     roof['tflops'] = kfl / (kms_dom * 1e-3) / 1e12
@@ -728,11 +728,43 @@ def main():
         nbf = np.asarray(nb, dtype=np.float64)
         tfl = float(np.sum(2.0 * K0 * nbf * nbf))
         roof['tensor_contraction'] = {
-            'kernel': 'gp::v2::tc_gemm2_kernel<256,4,0,8> (T = S^T.A, K=%d, N=%d, batch=%d)' % (K0, N, B),
+            'kernel': 'gp::v2::tc_gemm2_kernel<256,6,0,8,2> cta_group::2 CTA pair (T = S^T.A, K=%d, N=%d, batch=%d)' % (K0, N, B),
             'bound': 'tensor', 'achieved': tfl / (tms * 1e-3) / 1e12, 'peak': tf_burst, 'unit': 'TFLOP/s',
             'frac': tfl / (tms * 1e-3) / 1e12 / tf_burst, 'ms_per_launch': tms,
             'traffic': tj.get('tsa_gemm', {}).get('dram_bytes_per_launch') if (B == 256 and N == 2048 and same_rev) else None,
             'ncu_tensor_pipe_active_pct': tj.get('tsa_gemm', {}).get('tensor_pipe_active_pct')}
+        # the chained form of the same pooling step (gp_pool_chain_bf16: A' = S^T A S in one launch, T on chip) next to
+        # the two launches the step uses by default (T = S^T A with CTA pairs, A' = T S); DESIGN.md section 4 explains why
+        # the chain is the slower one at K = 512 (TMEM leaves it 128-column T tiles on single CTAs: shared-memory port)
+        if K0 <= 512 and K0 % 8 == 0:
+            import ctypes as C_
+            from graph_pooling_b200._lib import call as call_
+            apf = torch.empty(B, K0, K0, device=dev)
+            apb = T.bfbuf(wsb, B, K0, K0)
+
+            def chain(keep_t):
+                call_('gp_pool_chain_bf16', sop.ptr, C_.c_longlong(sop.ld), adjb.ptr, C_.c_longlong(adjb.ld),
+                      nbd.data_ptr(), None, B, N, K0, tbuf.ptr if keep_t else None,
+                      C_.c_longlong(tbuf.ld if keep_t else 0), apf.data_ptr(), C_.c_longlong(K0), apb.ptr,
+                      C_.c_longlong(apb.ld), None)
+
+            def two():
+                tsa()
+                T.tcgemm(tbuf, T.KM, sop, T.MN, K0, K0, N, B, Cf=(apf.data_ptr(), K0, K0 * K0), Cb=apb,
+                         lim=nbd.data_ptr(), lim_k=1)
+            for f_ in (lambda: chain(True), lambda: chain(False), two):
+                for _ in range(2):
+                    f_()
+            cfl = tfl + float(np.sum(2.0 * K0 * K0 * nbf))
+            c_t, c_n, c_2 = [timed_local(f_, reps) / reps for f_ in (lambda: chain(True), lambda: chain(False), two)]
+            roof['chained_pooling'] = {
+                'kernel': "gp::chain::pool_chain_kernel<%d> (A' = S^T A S, T = S^T A in TMEM -> bf16 shared tile -> second "
+                          "tcgen05.mma; %s)" % (2 if K0 > 256 else 1, 'two-CTA cluster, DSMEM exchange of T tiles'
+                                                if K0 > 256 else 'one CTA per row block'),
+                'flops': cfl, 'ms_chained_T_stored_once': c_t, 'ms_chained_T_on_chip_only': c_n,
+                'ms_two_launches_default': c_2, 'tflops_chained': cfl / (c_t * 1e-3) / 1e12,
+                'tflops_two_launches': cfl / (c_2 * 1e-3) / 1e12, 'default': 'two launches (GP_CHAIN=1 selects the chain)'}
+            del apf, apb
         del sprob, tbuf
 
     # ---- the step against ITS roof (top-level `roofline`); the kernel timed alone above is `dominant_kernel` ------

@@ -468,15 +468,22 @@ def softmax_forward(ws, S, nb, B, N, K):
     return sb
 
 
+CHAIN_POOLING = None     # None: decided by GP_CHAIN; True / False: set by the caller (tests, bench)
+
+
 def chain_ok(sb, adjb, N, K):
-    """The chained S^T A S kernel (gp_pool_chain_bf16) takes dense per-graph operands and at most 512 clusters."""
-    return K <= 512 and sb.sb == N * sb.ld and adjb.sb == N * adjb.ld and not os.environ.get('GP_NO_CHAIN')
+    """The chained S^T A S kernel (gp_pool_chain_bf16) takes dense per-graph operands and at most 512 clusters.  It is
+    OPT-IN (GP_CHAIN=1 or engine_tc.CHAIN_POOLING = True): measured on B200 at cfg4 (K = 512) it is slower than T = S^T A
+    on CTA pairs followed by A' = T S (1.5 vs 1.0 ms), although it moves 1 GB less through HBM."""
+    want = CHAIN_POOLING if CHAIN_POOLING is not None else bool(os.environ.get('GP_CHAIN'))
+    return want and K <= 512 and sb.sb == N * sb.ld and adjb.sb == N * adjb.ld
 
 
 def pool_forward(ws, sb, zb, adjb, nb, B, N, K, Fw, keep_t=True):
-    """X' = S^T Z, A' = S^T A S (encoders.py:1278-1279).  K <= 512: A' comes from ONE chained launch that keeps T = S^T A
-    on chip (TMEM -> bf16 shared-memory tile -> second tcgen05.mma); T is written to HBM (bf16, once) only when the
-    backward will need it (`keep_t`).  Larger K: T = S^T A and A' = T S as two launches."""
+    """X' = S^T Z, A' = S^T A S (encoders.py:1278-1279).  Default: T = S^T A and A' = T S as two launches (the first
+    on cta_group::2 CTA pairs).  With the chain selected (chain_ok) and K <= 512, A' comes from ONE launch that keeps T on
+    chip (TMEM -> bf16 shared-memory tile -> second tcgen05.mma); T is written to HBM (bf16, once) only when the backward
+    will need it (`keep_t`)."""
     nbp, lim = E._p(nb), int(nb is not None)
     xp, xpb = ws.f(B, K, Fw), bfbuf(ws, B, K, Fw)
     tcgemm(sb, MN, zb, MN, K, Fw, N, B, Cf=(xp.data_ptr(), Fw, K * Fw), Cb=xpb, lim=nbp, lim_k=lim)

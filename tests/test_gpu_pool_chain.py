@@ -129,11 +129,9 @@ def test_model_chain_equals_three_launch_schedule(monkeypatch):
     N, D, H, Cc, B = 300, 16, 32, 3, 4
     x, adj, nb, label = synth_batch(2, B, N, D, 40, N, Cc, 0.05)
     outs = []
+    from graph_pooling_b200 import engine_tc
     for no_chain in ('', '1'):
-        if no_chain:
-            monkeypatch.setenv('GP_NO_CHAIN', '1')
-        else:
-            monkeypatch.delenv('GP_NO_CHAIN', raising=False)
+        monkeypatch.setattr(engine_tc, 'CHAIN_POOLING', not no_chain)
         torch.manual_seed(0)
         m = enc.SoftPoolingGcnEncoder(N, D, H, H, Cc, 3, H, assign_ratio=0.25, num_pooling=2).cuda()
         m.precision = 1
