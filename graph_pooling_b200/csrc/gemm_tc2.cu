@@ -174,12 +174,12 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
-template <int BN, int STAGES, int EW>
+template <int BN, int STAGES, int EW, bool STG = true>
 struct Smem {
   static constexpr int kA = BM * BK * 2;
   static constexpr int kB = BN * BK * 2;
   static constexpr int kStage = kA + kB;
-  static constexpr int kStaging = EW * 32 * 32 * 4;
+  static constexpr int kStaging = STG ? EW * 32 * 32 * 4 : 0;   // EPI == 3 (row epilogue) has no staging tile
   static constexpr int kBytes = STAGES * kStage + kStaging + 1024 /*align slack*/ + 256 /*barriers*/ + (BN > 256 ? 2048 : 1024) /*bias*/;
 };
 
@@ -342,26 +342,65 @@ __device__ __forceinline__ void stg256(void* p, const uint32_t (&v)[8]) {
   asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
 }
-// Row form of the {0,1} BCE (one lane owns 16 consecutive entries of ONE row: P values straight from TMEM, the
-// adjacency as 8 words of packed bf16): same arithmetic as bce01_row8.  MASK: entries e >= nvalid contribute nothing.
-template <bool MASK>
-__device__ __forceinline__ void bce01_row16(const uint32_t* pv, const uint32_t (&aw)[8], int nvalid, float* l2,
-                                            uint32_t (&gw)[8]) {
+// Row form of the link-loss arithmetic: one lane owns 32 consecutive entries of ONE row -- P values straight from TMEM
+// (pv), the adjacency as 16 words of packed bf16 (aw) -- and produces G = dl/dP as 16 packed words.
+//
+// FAST path ({0,1} adjacency, whole chunk inside the n_b x n_b block), branch- and predicate-free per entry: with
+// a in {0.0f, 1.0f} taken from the bf16 bits,  x = a (2p - 1) + (1 - p) + eps  (= p + eps or 1 - p + eps, p = min(P, 1));
+// loss += log2 x;  G = (1 - 2a) / x, zeroed where P > 1 (R3 clamp, encoders.py:1317).
+__device__ __forceinline__ void link_row32_fast(const uint32_t (&pv)[32], const uint32_t (&aw)[16], float* l2,
+                                                uint32_t (&gw)[16]) {
+  float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+  for (int h = 0; h < 16; ++h) {
+    const float a0 = __uint_as_float(aw[h] << 16), a1 = __uint_as_float(aw[h] & 0xffff0000u);
+    const float q0 = __uint_as_float(pv[2 * h]), q1 = __uint_as_float(pv[2 * h + 1]);
+    const float p0 = fminf(q0, 1.f), p1 = fminf(q1, 1.f);
+    const float x0 = fmaf(a0, fmaf(2.f, p0, -1.f), (1.f + kEpsLink) - p0);
+    const float x1 = fmaf(a1, fmaf(2.f, p1, -1.f), (1.f + kEpsLink) - p1);
+    acc0 += lg2_approx(x0);
+    acc1 += lg2_approx(x1);
+    float g0 = rcp_approx(x0) * fmaf(-2.f, a0, 1.f);
+    float g1 = rcp_approx(x1) * fmaf(-2.f, a1, 1.f);
+    g0 = q0 > 1.f ? 0.f : g0;
+    g1 = q1 > 1.f ? 0.f : g1;
+    gw[h] = pack_bf16x2(g0, g1);
+  }
+  *l2 += acc0 + acc1;
+}
+// Every other case (real-valued adjacency, Frobenius option, chunks cut by n_b): run-time mode (warp-uniform branches),
+// one instance per chunk.  mode 0: general BCE, 1: {0,1} BCE, 2: Frobenius (as bce_row8).  Entries e >= nvalid
+// contribute nothing.  (Unrolled like the fast path: a rolled loop or a call would force the register arrays into
+// local memory for BOTH paths -- measured 1.45 vs 0.98 ms.)
+__device__ __forceinline__ void link_row32_any(const uint32_t (&pv)[32], const uint32_t (&aw)[16], int mode, int nvalid,
+                                            float* l2, uint32_t (&gw)[16]) {
   float acc = 0.f;
 #pragma unroll
-  for (int h = 0; h < 8; ++h) {
+  for (int h = 0; h < 16; ++h) {
     float g[2];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      const uint32_t bits = e ? (aw[h] >> 16) : (aw[h] & 0xffffu);
-      const bool one = bits != 0u;
+      const float a1 = __uint_as_float(e ? (aw[h] & 0xffff0000u) : (aw[h] << 16));
       const float pval = __uint_as_float(pv[2 * h + e]);
-      const float s = one ? 1.f : -1.f;
-      const float x = fmaf(s, fminf(pval, 1.f), one ? kEpsLink : 1.f + kEpsLink);
-      float ll = lg2_approx(x);
-      float gg = -s * rcp_approx(x);
-      if (pval > 1.f) gg = 0.f;
-      if (MASK && 2 * h + e >= nvalid) { gg = 0.f; ll = 0.f; }
+      const float pc = fminf(pval, 1.f);
+      float ll, gg;
+      if (mode == 2) {
+        const float d = a1 - pval;
+        ll = d * d;
+        gg = -d;
+      } else {
+        if (mode == 1) {
+          const float x = fmaf(a1, fmaf(2.f, pc, -1.f), (1.f + kEpsLink) - pc);
+          ll = lg2_approx(x);
+          gg = rcp_approx(x) * fmaf(-2.f, a1, 1.f);
+        } else {
+          const float pe = pc + kEpsLink, qe = 1.f - pc + kEpsLink;
+          ll = a1 * lg2_approx(pe) + (1.f - a1) * lg2_approx(qe);
+          gg = (1.f - a1) * rcp_approx(qe) - a1 * rcp_approx(pe);
+        }
+        if (pval > 1.f) gg = 0.f;
+      }
+      if (2 * h + e >= nvalid) { gg = 0.f; ll = 0.f; }
       acc += ll;
       g[e] = gg;
     }
@@ -377,7 +416,7 @@ __global__ void __launch_bounds__((EW + 2) * 32, 1)
 tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
   static_assert(MC == 1 || (MC == 2 && EPI == 0 && BN == 256), "the multicast pair exists for the plain BN = 256 GEMM");
   extern __shared__ uint8_t smem_raw[];
-  using L = Smem<BN / MC, STAGES, EW>;                   // MC == 2: each CTA stages half of the B tile
+  using L = Smem<BN / MC, STAGES, EW, EPI != 3>;         // MC == 2: each CTA stages half of the B tile
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));
   float* staging = reinterpret_cast<float*>(smem_gen + STAGES * L::kStage);
@@ -435,15 +474,17 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
   int npairs = p.npairs;
   float alpha_mul = 1.f;
   long long total_work = p.total_work;
-  bool sym_upper = false, adj01 = false, tri_on = false, row_mode = false;
-  if (EPI == 1) {
+  bool sym_upper = false, adj01 = false, tri_on = false;
+  if (EPI == 1 || EPI == 3) {
     if (p.adj_flags != nullptr) {
       // link loss over a symmetric adjacency: compute the upper band only, mirror the rest (BCE mode: the
       // Frobenius finalisation needs per-graph partial blocks, which the compact enumeration does not keep)
       sym_upper = p.adj_flags[0] == 0 && p.link_mode == 0;
       adj01 = p.adj_flags[1] == 0;
     }
-    row_mode = sym_upper && adj01 && p.upper_only != 0;
+    // EPI == 3 (row epilogue) never writes mirrored chunks: it may skip the lower tiles only if the consumer reads the
+    // band twice (gp_linkloss_tc mode 2 + gp_gemm_bf16x.tri); otherwise it computes every tile
+    if (EPI == 3) sym_upper = sym_upper && p.upper_only != 0;
   } else if (p.cond != nullptr && *p.cond == 0) {
     npairs = p.cond_npairs;
     alpha_mul = p.cond_alpha;
@@ -581,6 +622,86 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
       if (MC > 1) k.m0 += (int)rank * BM;
       const bool has_acc = k.kt1 > k.kt0;
       const uint32_t a = NACC == 2 ? (nacc & 1) : 0u, aph = NACC == 2 ? ((nacc >> 1) & 1) : (nacc & 1);
+      if (EPI == 3) {
+        // ---- link loss, row epilogue: lane = row, no shared-memory staging and no mirrored chunks -- P straight from
+        // TMEM, 64 contiguous bytes of adjacency in and 64 bytes of G out per lane and 32-column chunk (two 32-byte
+        // accesses each).  For a symmetric adjacency in mode 2 only the upper-band tiles are computed and written; the
+        // consumer (gp_bgemm_bf16x.tri) reads that band twice.  The adjacency does not depend on the accumulator: the
+        // first chunk's loads are issued BEFORE the wait for the tensor cores, the next chunk's before the current
+        // chunk's arithmetic.
+        constexpr int NCH = CPW / 32;
+        const int row0r = k.m0 + quarter * 32, row = row0r + lane;       // row < p.M: N is a multiple of 32 here
+        const bool frob = p.link_mode == 1;
+        float lsum = 0.f;
+        if (has_acc) {
+          const __nv_bfloat16* arow = p.adjb + (long long)k.b * p.sadjb + (long long)row * p.ldadj;
+          __nv_bfloat16* grow = p.Cb != nullptr ? p.Cb + (long long)k.b * p.sCbb + (long long)row * p.ldCb : nullptr;
+          const bool rows_ok = row0r < p.M;                              // warp-uniform
+          auto nvalid = [&](int nbase) { return row < k.Me ? max(0, min(32, k.Ne - nbase)) : 0; };
+          auto issue = [&](int c, uint32_t (&w)[16]) {
+            const int nbase = k.n0 + cgrp * CPW + c * 32;
+            const int nv = (rows_ok && nbase < p.N) ? nvalid(nbase) : 0;
+            uint32_t lo[8], hi[8];
+            if (nv > 0) ldg256_stream(arow + nbase, lo);
+            else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) lo[e] = 0u;
+            }
+            if (nv > 16) ldg256_stream(arow + nbase + 16, hi);
+            else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) hi[e] = 0u;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { w[e] = lo[e]; w[8 + e] = hi[e]; }
+          };
+          uint32_t aw[NCH][16];
+          issue(0, aw[0]);
+          mbar_wait(tfull_bar(a), aph);
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            if (c + 1 < NCH) issue(c + 1, aw[c + 1]);
+            const int col = cgrp * CPW + c * 32, nbase = k.n0 + col;
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * BN + col), v);
+            if (!rows_ok || nbase >= p.N) continue;                      // warp-uniform
+            const bool interior = row0r + 32 <= k.Me && nbase + 32 <= k.Ne;        // warp-uniform
+            // symmetric mode: does this chunk's mirror image fall into a skipped tile?
+            const bool mirror = sym_upper && ((row0r / BN) * BN + BN <= (nbase / BM) * BM);
+            bool fast = adj01;                                           // kernel-uniform flag from gp_adj_prepare, or ...
+            if (p.adj_flags == nullptr && !frob) {                       // ... a warp-uniform test of this chunk's entries
+              bool is01 = true;                                          // bf16 0.0 = 0x0000, 1.0 = 0x3f80
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                const uint32_t w0 = aw[c][e];
+                is01 = is01 && (w0 & ~0x3f803f80u) == 0u && ((w0 & 0xffffu) == 0u || (w0 & 0xffffu) == 0x3f80u) &&
+                       ((w0 >> 16) == 0u || (w0 >> 16) == 0x3f80u);
+              }
+              fast = __all_sync(0xffffffffu, is01);
+            }
+            float l2 = 0.f;
+            uint32_t gwd[16];
+            if (fast && interior && !frob) link_row32_fast(v, aw[c], &l2, gwd);
+            else link_row32_any(v, aw[c], frob ? 2 : (fast ? 1 : 0), interior ? 32 : nvalid(nbase), &l2, gwd);
+            uint32_t g0[8], g1[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { g0[e] = gwd[e]; g1[e] = gwd[8 + e]; }
+            if (grow != nullptr) { stg256(grow + nbase, g0); stg256(grow + nbase + 16, g1); }
+            if (mirror) l2 *= 2.f;                                       // the mirrored entries' loss terms are identical
+            lsum = frob ? lsum + l2 : fmaf(l2, -0.69314718055994531f, lsum);
+          }
+        }
+        lsum = warp_sum(lsum);
+        if (lane == 0) p.partial[w * EW + warp] = lsum;
+        if (has_acc) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(a));
+          ++nacc;
+        }
+        continue;
+      }
       if (has_acc) {
         mbar_wait(tfull_bar(a), aph);
         tc_fence_after();
@@ -685,42 +806,6 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
         if (row0 >= p.M || nbase >= p.N) continue;       // warp-uniform
         if (EPI == 1 && !has_acc) continue;
         if (EPI == 0 && !has_acc && beta == 1.f && p.bias == nullptr && p.Cb == nullptr) continue;   // nothing to add
-        if (EPI == 1 && row_mode) {
-          // ---- symmetric {0,1} adjacency, G kept as its upper band only (mode bit 1): lane = row, no shared-memory
-          // staging and no mirrored chunks -- P straight from TMEM, 64 contiguous bytes of adjacency in, 64 bytes of G
-          // out per lane and chunk (two 32-byte accesses each); the consumer (gp_bgemm_bf16x.tri) reads the band twice
-          const int row = row0 + lane;                   // < p.M: N is a multiple of 32 in this mode
-          const __nv_bfloat16* arow = p.adjb + (long long)k.b * p.sadjb + (long long)row * p.ldadj + nbase;
-          __nv_bfloat16* grow = p.Cb != nullptr ? p.Cb + (long long)k.b * p.sCbb + (long long)row * p.ldCb + nbase : nullptr;
-          const bool interior = row0 + 32 <= k.Me && nbase + 32 <= k.Ne;   // warp-uniform
-          const bool mirror = (row0 / BN) * BN + BN <= (nbase / BM) * BM;  // the mirror image lies in a skipped tile
-          float l2 = 0.f;
-          if (interior) {
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              uint32_t aw[8], gw[8];
-              ldg256_stream(arow + 16 * hh, aw);
-              bce01_row16<false>(&v[16 * hh], aw, 16, &l2, gw);
-              if (grow != nullptr) stg256(grow + 16 * hh, gw);
-            }
-          } else {
-            const int nv = row < k.Me ? max(0, min(32, k.Ne - nbase)) : 0;
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              uint32_t aw[8], gw[8];
-              if (nv > 16 * hh) ldg256_stream(arow + 16 * hh, aw);
-              else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) aw[e] = 0u;
-              }
-              bce01_row16<true>(&v[16 * hh], aw, nv - 16 * hh, &l2, gw);
-              if (grow != nullptr) stg256(grow + 16 * hh, gw);
-            }
-          }
-          if (mirror) l2 *= 2.f;                         // the mirrored entries' loss terms are identical
-          lsum = fmaf(l2, -0.69314718055994531f, lsum);
-          continue;
-        }
         // registers (lane = row) -> staging tile [32 rows][32], swizzled; float4 stores, conflict-free
 #pragma unroll
         for (int q = 0; q < 8; ++q)
@@ -993,7 +1078,7 @@ static int make_map(CUtensorMap* tm, const void* ptr, long long cols, long long 
 
 template <int BN, int STAGES, int EPI, int EW>
 static int launch(const Maps& maps, Params& p, cudaStream_t st) {
-  using L = Smem<BN, STAGES, EW>;
+  using L = Smem<BN, STAGES, EW, EPI != 3>;
   auto kern = tc_gemm2_kernel<BN, STAGES, EPI, EW>;
   GP_CONFIG_ONCE(GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes)));
   const int split = p.split_k > 1 ? p.split_k : 1;
@@ -1160,13 +1245,13 @@ int run_linkloss(const void* s_bf16, long long lds, const void* adj_bf16, long l
   GP_REQUIRE(s_bf16 && adj_bf16 && partial && B > 0 && N > 0 && K > 0, "linkloss_tc: bad args");
   GP_REQUIRE(mode == 0 || mode == 1 || mode == 2, "linkloss_tc: mode must be 0 (BCE), 1 (Frobenius) or 2 (BCE, upper-band G)");
   const int upper_only = mode == 2;
-  if (upper_only) {
-    mode = 0;
-    GP_REQUIRE(adj_flags != nullptr && N % 32 == 0 && ldadj % 16 == 0 && (g_bf16 == nullptr || ldg % 16 == 0) &&
-                   (reinterpret_cast<uintptr_t>(adj_bf16) & 31) == 0 && (reinterpret_cast<uintptr_t>(g_bf16) & 31) == 0,
-               "linkloss_tc: mode 2 needs adj_flags, N % 32 == 0 and 32-byte aligned adjacency / G rows");
-  }
-  GP_REQUIRE(lds % 8 == 0 && (g_bf16 == nullptr || ldg >= N), "linkloss_tc: bad strides");
+  if (upper_only) mode = 0;
+  // row epilogue (EPI == 3: one lane per row, 256-bit accesses, no staging tile -> a fourth pipeline stage)
+  const bool rows32 = N % 32 == 0 && ldadj % 16 == 0 && (g_bf16 == nullptr || ldg % 16 == 0) &&
+                      (reinterpret_cast<uintptr_t>(adj_bf16) & 31) == 0 && (reinterpret_cast<uintptr_t>(g_bf16) & 31) == 0;
+  GP_REQUIRE(!upper_only || (adj_flags != nullptr && rows32),
+             "linkloss_tc: mode 2 needs adj_flags, N % 32 == 0 and 32-byte aligned adjacency / G rows");
+  static const bool no_row = getenv("GP_LINK_NO_ROW") != nullptr;
   Maps maps;
   Params p;
   GP_TRY(make_map(&maps.a[0], s_bf16, K, N, B, lds, (long long)N * lds, BM));
@@ -1189,6 +1274,9 @@ int run_linkloss(const void* s_bf16, long long lds, const void* adj_bf16, long l
     for (int mt = 0; mt < tm; ++mt) { const int first = (mt * BM) / 256; per += tn > first ? tn - first : 0; }
     p.sym_per_graph = per; p.sym_total = (long long)per * B;
   }
+  static const bool four = getenv("GP_LINK_STAGES4") != nullptr;
+  // three stages measured faster than four (0.98 vs 1.10 ms at cfg4) although the staging tile's 64 KB are free
+  if (rows32 && (upper_only || !no_row)) return four ? launch<256, 4, 3, kLinkEW>(maps, p, st) : launch<256, 3, 3, kLinkEW>(maps, p, st);
   return launch<256, 3, 1, kLinkEW>(maps, p, st);
 }
 
