@@ -453,7 +453,9 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
       // MC == 2: the leader's tmem_empty collects the epilogue warps of BOTH CTAs
-      for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EW * MC); }   // NACC == 1 uses a = 0
+      // EPI == 2 with eight epilogue warps: two groups of four, group g drains accumulator buffer g (see the epilogue)
+      constexpr int kDrain = (EPI == 2 && EW == 8) ? 4 : EW * MC;
+      for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kDrain); }   // NACC == 1 uses a = 0
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -702,13 +704,20 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
         }
         continue;
       }
+      if (EPI == 2 && EW == 8) {
+        // a thread owns a whole output row, so a tile occupies four warps; with ONE warp per scheduler the TMEM-load /
+        // staging / store chain of a tile had nothing to overlap with (HBM at 0.55 of its peak).  Eight warps = two
+        // groups: group g drains the tiles that land in accumulator buffer g, so two tiles' epilogues are in flight.
+        static_assert(EPI != 2 || EW != 8 || NACC == 2, "needs the double-buffered accumulator");
+        if ((nacc & 1u) != (uint32_t)(warp >> 2)) { ++nacc; continue; }
+      }
       if (has_acc) {
         mbar_wait(tfull_bar(a), aph);
         tc_fence_after();
       }
       const int row0 = k.m0 + quarter * 32;
       if (EPI == 2) {
-        // ---- bias + L2 normalize + BN row statistics; EW == 4: this warp owns rows row0..row0+31 entirely ----
+        // ---- bias + L2 normalize + BN row statistics: this warp owns rows row0..row0+31 entirely ----
         const int row = row0 + lane;
         const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * BN);
         float ssp[4] = {0.f, 0.f, 0.f, 0.f};             // 4 independent chains
@@ -1235,8 +1244,10 @@ int run_norm(const gp_gemm_bf16x* g, float* rnorm, float* rowstat, int stat_relu
   p.cond = nullptr; p.cond_npairs = 0; p.cond_alpha = 1.f;
   p.adj_flags = nullptr; p.sym_total = 0; p.sym_per_graph = 0; p.order = nullptr; p.tri = 0; p.upper_only = 0;
   if (BN == 512) return launch<512, 2, 2, 4>(maps, p, st);
-  if (BN == 256) return launch<256, 3, 2, 4>(maps, p, st);
-  return launch<128, 4, 2, 4>(maps, p, st);
+  static const bool one_group = getenv("GP_TAIL_EW4") != nullptr;
+  if (one_group) return BN == 256 ? launch<256, 3, 2, 4>(maps, p, st) : launch<128, 4, 2, 4>(maps, p, st);
+  if (BN == 256) return launch<256, 3, 2, 8>(maps, p, st);
+  return launch<128, 4, 2, 8>(maps, p, st);
 }
 
 int run_linkloss(const void* s_bf16, long long lds, const void* adj_bf16, long long ldadj, const int32_t* nb,
