@@ -100,7 +100,7 @@ adj_prepare_kernel(typename InPtr<T>::type adj, long long ldin, const int32_t* _
   float v[4][4];
   tile_io<T>(ab, ldin, ob, N, ld, ti * AT, tj * AT, nreal, vec_in, vec_out, v, &non01);
   // the last tile column also owns the zero fill of the operand's padding columns [tiles*64, ld) -- none here:
-  // ld - N < 8 < 64, so they fall inside tile tj == tiles-1 and tile_io's `c < ld` bound covers them.
+  // ld <= round_up(N, 32) <= tiles * 64, so they fall inside tile tj == tiles-1 and tile_io's `c < ld` bound covers them.
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -236,8 +236,8 @@ __global__ void set_flags_kernel(int32_t* flags, int not_sym, int accumulate) {
 extern "C" int gp_adj_from_edges(const void* edges, int id_bytes, const int32_t* eptr, int B, int N,
                                  int max_edges_per_graph, int undirected, void* adj_bf16, long long ld, int32_t* flags,
                                  int accumulate_flags, gp_stream_t stream) {
-  GP_REQUIRE(edges && eptr && adj_bf16 && B > 0 && N > 0 && ld >= N && ld - N < 8 && B <= 65535,
-             "adj_from_edges: bad args (need N <= ld < N+8)");
+  GP_REQUIRE(edges && eptr && adj_bf16 && B > 0 && N > 0 && ld >= N && ld - N < 32 && B <= 65535,
+             "adj_from_edges: bad args (need N <= ld < N+32)");
   GP_REQUIRE(id_bytes == 4 || (id_bytes == 2 && N <= 65536), "adj_from_edges: node ids are 4 or 2 bytes (2: N <= 65536)");
   GP_REQUIRE((reinterpret_cast<uintptr_t>(edges) & (uintptr_t)(2 * id_bytes - 1)) == 0, "adj_from_edges: edge alignment");
   GP_CUDA(cudaMemsetAsync(adj_bf16, 0, (size_t)B * N * ld * sizeof(__nv_bfloat16), S(stream)));
@@ -265,7 +265,7 @@ extern "C" int gp_adj_prepare(const void* adj, int adj_dtype, const int32_t* nb,
 extern "C" int gp_adj_prepare_x(const void* adj, int adj_dtype, long long ld_in, const int32_t* nb, int B, int N,
                                 void* adj_bf16, long long ld, int32_t* flags, int accumulate_flags,
                                 gp_stream_t stream) {
-  GP_REQUIRE(adj && adj_bf16 && B > 0 && N > 0 && ld >= N && ld - N < 8, "adj_prepare: bad args (need N <= ld < N+8)");
+  GP_REQUIRE(adj && adj_bf16 && B > 0 && N > 0 && ld >= N && ld - N < 32, "adj_prepare: bad args (need N <= ld < N+32)");
   GP_REQUIRE(adj_dtype >= 0 && adj_dtype <= 2, "adj_prepare: adj_dtype must be 0 (fp32), 1 (uint8) or 2 (bit-packed)");
   GP_REQUIRE(B <= 65535, "adj_prepare: B too large");
   if (ld_in <= 0) ld_in = adj_dtype == 2 ? (N + 7) / 8 : N;

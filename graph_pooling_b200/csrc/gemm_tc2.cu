@@ -632,7 +632,7 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
         // first chunk's loads are issued BEFORE the wait for the tensor cores, the next chunk's before the current
         // chunk's arithmetic.
         constexpr int NCH = CPW / 32;
-        const int row0r = k.m0 + quarter * 32, row = row0r + lane;       // row < p.M: N is a multiple of 32 here
+        const int row0r = k.m0 + quarter * 32, row = row0r + lane;       // row may be >= p.M in the last 32-row group
         const bool frob = p.link_mode == 1;
         float lsum = 0.f;
         if (has_acc) {
@@ -689,7 +689,7 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
             uint32_t g0[8], g1[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) { g0[e] = gwd[e]; g1[e] = gwd[8 + e]; }
-            if (grow != nullptr) { stg256(grow + nbase, g0); stg256(grow + nbase + 16, g1); }
+            if (grow != nullptr && row < p.M) { stg256(grow + nbase, g0); stg256(grow + nbase + 16, g1); }
             if (mirror) l2 *= 2.f;                                       // the mirrored entries' loss terms are identical
             lsum = frob ? lsum + l2 : fmaf(l2, -0.69314718055994531f, lsum);
           }
@@ -1258,10 +1258,11 @@ int run_linkloss(const void* s_bf16, long long lds, const void* adj_bf16, long l
   const int upper_only = mode == 2;
   if (upper_only) mode = 0;
   // row epilogue (EPI == 3: one lane per row, 256-bit accesses, no staging tile -> a fourth pipeline stage)
-  const bool rows32 = N % 32 == 0 && ldadj % 16 == 0 && (g_bf16 == nullptr || ldg % 16 == 0) &&
+  const long long n32 = ((long long)N + 31) / 32 * 32;     // a lane reads / writes whole 32-column chunks of its row
+  const bool rows32 = ldadj % 16 == 0 && ldadj >= n32 && (g_bf16 == nullptr || (ldg % 16 == 0 && ldg >= n32)) &&
                       (reinterpret_cast<uintptr_t>(adj_bf16) & 31) == 0 && (reinterpret_cast<uintptr_t>(g_bf16) & 31) == 0;
   GP_REQUIRE(!upper_only || (adj_flags != nullptr && rows32),
-             "linkloss_tc: mode 2 needs adj_flags, N % 32 == 0 and 32-byte aligned adjacency / G rows");
+             "linkloss_tc: mode 2 needs adj_flags and 32-byte aligned adjacency / G rows of at least round_up(N, 32) elements");
   static const bool no_row = getenv("GP_LINK_NO_ROW") != nullptr;
   Maps maps;
   Params p;

@@ -30,9 +30,12 @@ class Op:
         self.ptr, self.ld, self.sb, self.t = ptr, ld, sb, t
 
 
-def bfbuf(ws, B, R, Ccols):
-    t = torch.empty(B, R, r8(Ccols), device=ws.device, dtype=torch.bfloat16)
-    return Op(t.data_ptr(), r8(Ccols), R * r8(Ccols), t)
+def bfbuf(ws, B, R, Ccols, pad=8):
+    """bf16 operand buffer [B, R, ld], ld = Ccols rounded up to `pad` elements (8: TMA's 16-byte rule; 32: adjacency-sized
+    operands whose rows the link-loss epilogue reads / writes in whole 32-column chunks with 256-bit accesses)."""
+    ld = (int(Ccols) + pad - 1) // pad * pad
+    t = torch.empty(B, R, ld, device=ws.device, dtype=torch.bfloat16)
+    return Op(t.data_ptr(), ld, R * ld, t)
 
 
 def cvt(ws, x_ptr, ldx, rows, cols, B=1, out=None):
@@ -46,7 +49,7 @@ def cvt(ws, x_ptr, ldx, rows, cols, B=1, out=None):
 
 def adj_prepare(ws, adj, nb, B, N):
     """adj [B,N,N] fp32 (or uint8) -> (bf16 operand, flags int32[2] on device: [not symmetric, not {0,1}])."""
-    out = bfbuf(ws, B, N, N)
+    out = bfbuf(ws, B, N, N, pad=32)
     flags = torch.empty(2, device=ws.device, dtype=torch.int32)
     call('gp_adj_prepare', adj.data_ptr(), 1 if adj.dtype == torch.uint8 else 0, E._p(nb), B, N, out.ptr, out.ld,
          flags.data_ptr(), E._stream())
@@ -76,7 +79,7 @@ class PreparedAdjacency:
     def __init__(self, B, N, device):
         self.shape = (B, N, N)
         self.device = torch.device(device)
-        self.op = bfbuf(E.Workspace(self.device), B, N, N)
+        self.op = bfbuf(E.Workspace(self.device), B, N, N, pad=32)
         self.flags = torch.zeros(2, device=self.device, dtype=torch.int32)
         self._fresh = True
 
@@ -591,8 +594,9 @@ def assign_head_bwd(ws, S, ds, nb, B, N, zab, Fa, wpb, K, has_bias, Kreal=0, Fa_
 def upper_band_ok(sb, adjb, N, mode, adj_flags):
     """gp_linkloss_tc mode 2 / gp_gemm_bf16x.tri: for a symmetric {0,1} adjacency (decided on the device from the
     gp_adj_prepare flags) G = dl/dP is written as its upper diagonal band only and the backward reads that band twice
-    (once transposed).  Needs the BCE loss, the flags, N a multiple of 32 and 32-byte aligned rows."""
-    return (mode == 0 and adj_flags is not None and N % 32 == 0 and adjb.ld % 16 == 0 and adjb.ptr % 32 == 0 and
+    (once transposed).  Needs the BCE loss, the flags and 32-byte aligned rows of at least round_up(N, 32) elements
+    (adjacency operands and G are allocated that way: bfbuf(..., pad=32))."""
+    return (mode == 0 and adj_flags is not None and adjb.ld % 16 == 0 and adjb.ld >= (N + 31) // 32 * 32 and adjb.ptr % 32 == 0 and
             not os.environ.get('GP_NO_UPPER_G'))
 
 
@@ -602,8 +606,9 @@ def linkloss_forward(ws, sb, adjb, nb, B, N, K, need_grad, mode=0, adj_flags=Non
     nbp = E._p(nb)
     npart = int(load().gp_linkloss_tc_partials(B, N))
     partial = ws.f(npart + 256)                      # +256: scratch of the two-stage finalisation
-    gs = bfbuf(ws, B, N, N) if need_grad else None
-    upper = upper_band_ok(sb, adjb, N, mode, adj_flags) and (gs is None or (gs.ld % 16 == 0 and gs.ptr % 32 == 0))
+    gs = bfbuf(ws, B, N, N, pad=32) if need_grad else None
+    upper = upper_band_ok(sb, adjb, N, mode, adj_flags) and (gs is None or (gs.ld % 16 == 0 and gs.ptr % 32 == 0 and
+                                                                      gs.ld >= (N + 31) // 32 * 32))
     call('gp_linkloss_tc', sb.ptr, sb.ld, adjb.ptr, adjb.ld, nbp, B, N, K, partial.data_ptr(),
          None if gs is None else gs.ptr, N if gs is None else gs.ld, 2 if upper else mode, E._p(adj_flags), E._stream())
     return partial, npart, gs, upper

@@ -167,7 +167,7 @@ int gp_softmax_mask_fwd_x(float* t, const int32_t* nb, int B, int N, int K, void
 int gp_softmax_mask_bwd_x(const float* s, const float* ds, const int32_t* nb, int B, int N, int K, float* dt,
                           void* dt_bf16, long long lddtb, float* dcol, float* ws, gp_stream_t stream);
 /* Adjacency preparation (one HBM pass): adj [B,N,N] fp32 (adj_dtype 0, train.py:197) or uint8 {0,1} (adj_dtype 1,
- * compact feed) -> bf16 operand [B,N,ld] (N <= ld < N+8, zero padded); flags[0] != 0 iff some graph's adjacency
+ * compact feed) -> bf16 operand [B,N,ld] (N <= ld < N+32, zero padded); flags[0] != 0 iff some graph's adjacency
  * is NOT symmetric, flags[1] != 0 iff some entry is outside {0,1}.  With nb, tiles beyond nb[b] are written as
  * zeros without being read (feed contract graph_sampler.py:97-109). */
 int gp_adj_prepare(const void* adj, int adj_dtype, const int32_t* nb, int B, int N, void* adj_bf16, long long ld,

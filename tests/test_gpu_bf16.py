@@ -136,7 +136,7 @@ def test_adj_prepare_flags_and_values(B, N, sym, weighted, use_nb, u8):
     op, flags = T.adj_prepare(E.Workspace(a.device), a, nbd, B, N)
     torch.cuda.synchronize()
     out = op.t.float().cpu().numpy()
-    assert out.shape == (B, N, (N + 7) // 8 * 8)
+    assert out.shape == (B, N, (N + 31) // 32 * 32)     # adjacency operands: rows padded to 32 elements (row epilogue)
     assert np.array_equal(out[:, :, :N], torch.tensor(adj).bfloat16().float().numpy()) and not out[:, :, N:].any()
     assert flags.cpu().tolist() == [int(not sym), int(bool(weighted))]
 

@@ -120,7 +120,7 @@ def test_fused_linkloss_tc(B, N, K, use_nb, sym, weighted, flag):
     s_t = sbt.double().requires_grad_()
     lo = orc.link_pred_loss(s_t, adjb_t.double(), nbo)
     lo.backward()
-    Kp, Np = -(-K // 8) * 8, -(-N // 8) * 8
+    Kp, Np = -(-K // 8) * 8, (-(-N // 32) * 32 if flag else -(-N // 8) * 8)   # with flags: rows padded for the row epilogue
     sb = torch.zeros(B, N, Kp, dtype=torch.bfloat16); sb[:, :, :K] = sbt
     ab = torch.zeros(B, N, Np, dtype=torch.bfloat16); ab[:, :, :N] = adjb_t
     sb, ab = sb.cuda(), ab.cuda()
@@ -128,7 +128,7 @@ def test_fused_linkloss_tc(B, N, K, use_nb, sym, weighted, flag):
     ws = __import__('graph_pooling_b200.engine', fromlist=['x']).Workspace(torch.device('cuda'))
     asym = torch.tensor([0, int(bool(weighted))], device='cuda', dtype=torch.int32) if flag else None   # gp_adj_prepare flags
     partial, npart, gs, upper = t.linkloss_forward(ws, op(sb), op(ab), nbc, B, N, K, True, adj_flags=asym)
-    assert upper == bool(flag and N % 32 == 0)
+    assert upper == bool(flag)
     entries = float(np.sum(nb.astype(np.int64) ** 2)) if use_nb else float(B * N * N)
     total, link = torch.empty(1, device='cuda'), torch.empty(1, device='cuda')
     call('gp_loss_finalize', partial.data_ptr(), npart, C.c_double(1.0 / entries), None, total.data_ptr(),
