@@ -1102,9 +1102,10 @@ static int launch(const Maps& maps, Params& p, cudaStream_t st) {
 }
 
 // MC == 2: persistent two-CTA clusters, 256-row blocks per cluster
+template <int STAGES, int EW>
 static int launch_pair(const Maps& maps, Params& p, cudaStream_t st) {
-  using L = Smem<128, 6, 8>;                             // per CTA: 16 KB of A rows + 16 KB (half) of the B tile per stage
-  auto kern = tc_gemm2_kernel<256, 6, 0, 8, 2>;
+  using L = Smem<128, STAGES, EW>;                       // per CTA: 16 KB of A rows + 16 KB (half) of the B tile per stage
+  auto kern = tc_gemm2_kernel<256, STAGES, 0, EW, 2>;
   GP_CONFIG_ONCE(GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes)));
   p.pair = 1;
   p.tiles_m = (p.M + 2 * BM - 1) / (2 * BM);
@@ -1112,7 +1113,7 @@ static int launch_pair(const Maps& maps, Params& p, cudaStream_t st) {
   p.total_work = (long long)p.tiles_m * p.tiles_n * p.batch;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.blockDim = dim3(10 * 32);
+  cfg.blockDim = dim3((EW + 2) * 32);
   cfg.dynamicSmemBytes = L::kBytes;
   cfg.stream = st;
   cudaLaunchAttribute at[1];
@@ -1207,8 +1208,14 @@ int run(const gp_gemm_bf16x* g, cudaStream_t st) {
     GP_LAUNCHED();
     p.beta = 1.f;
   }
-  if (pair) return launch_pair(maps, p, st);
+  // short contractions (U.W-sized products over B*N rows) are bound by their epilogue (TMEM load -> staging -> store
+  // chains of two warps per scheduler): sixteen epilogue warps for them (U.W fp32 out 0.108 -> 0.086 ms)
+  static const int ew16 = getenv("GP_GEMM_EW16") ? atoi(getenv("GP_GEMM_EW16")) : 3;    // bit 0: BN = 128, bit 1: CTA pairs
+  int ksum = 0;
+  for (int q = 0; q < g->npairs; ++q) ksum += g->pair[q].K;
+  if (pair) return ((ew16 & 2) && ksum <= 1024) ? launch_pair<4, 16>(maps, p, st) : launch_pair<6, 8>(maps, p, st);
   if (BN == 256) return launch<256, 4, 0, 8>(maps, p, st);
+  if (BN == 128 && (ew16 & 1) && ksum <= 256 && split == 1) return launch<128, 4, 0, 16>(maps, p, st);
   if (BN == 128) return launch<128, 6, 0, 8>(maps, p, st);
   return launch<64, 6, 0, 8>(maps, p, st);
 }
