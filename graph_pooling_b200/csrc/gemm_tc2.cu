@@ -180,7 +180,7 @@ struct Smem {
   static constexpr int kB = BN * BK * 2;
   static constexpr int kStage = kA + kB;
   static constexpr int kStaging = STG ? EW * 32 * 32 * 4 : 0;   // EPI == 3 (row epilogue) has no staging tile
-  static constexpr int kBytes = STAGES * kStage + kStaging + 1024 /*align slack*/ + 256 /*barriers*/ + (BN > 256 ? 2048 : 1024) /*bias*/;
+  static constexpr int kBytes = STAGES * kStage + kStaging + 1024 /*align slack*/ + 256 /*barriers*/ + (BN > 256 ? 2048 : 1024) /*bias*/ + (BN > 256 ? 3072 : 0) /*group exchange*/;
 };
 
 template <int BN>
@@ -454,7 +454,7 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
       for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
       // MC == 2: the leader's tmem_empty collects the epilogue warps of BOTH CTAs
       // EPI == 2 with eight epilogue warps: two groups of four, group g drains accumulator buffer g (see the epilogue)
-      constexpr int kDrain = (EPI == 2 && EW == 8) ? 4 : EW * MC;
+      constexpr int kDrain = (EPI == 2 && EW == 8 && NACC == 2) ? 4 : EW * MC;
       for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kDrain); }   // NACC == 1 uses a = 0
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -704,11 +704,10 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
         }
         continue;
       }
-      if (EPI == 2 && EW == 8) {
+      if (EPI == 2 && EW == 8 && NACC == 2) {
         // a thread owns a whole output row, so a tile occupies four warps; with ONE warp per scheduler the TMEM-load /
         // staging / store chain of a tile had nothing to overlap with (HBM at 0.55 of its peak).  Eight warps = two
         // groups: group g drains the tiles that land in accumulator buffer g, so two tiles' epilogues are in flight.
-        static_assert(EPI != 2 || EW != 8 || NACC == 2, "needs the double-buffered accumulator");
         if ((nacc & 1u) != (uint32_t)(warp >> 2)) { ++nacc; continue; }
       }
       if (has_acc) {
@@ -718,11 +717,18 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
       const int row0 = k.m0 + quarter * 32;
       if (EPI == 2) {
         // ---- bias + L2 normalize + BN row statistics: this warp owns rows row0..row0+31 entirely ----
+        // SPLIT (512-column rows, one accumulator buffer, eight warps): the two warp groups share a row block and take
+        // 256 columns each; the row's sum of squares and its BatchNorm sums are combined through shared memory at two
+        // named barriers per tile (HBM was at 0.54 of its peak with one warp per scheduler)
+        constexpr bool SPLIT = EW == 8 && NACC == 1;
+        const int grp = warp >> 2;
+        const int c_lo = SPLIT ? grp * (BN / 64) : 0, c_hi = SPLIT ? c_lo + BN / 64 : BN / 32;
+        float* xch = sbias + (BN > 256 ? 512 : 256);     // SPLIT: [256] sums of squares, [256] s1, [256] s2
         const int row = row0 + lane;
         const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * BN);
         float ssp[4] = {0.f, 0.f, 0.f, 0.f};             // 4 independent chains
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = c_lo; c < c_hi; ++c) {
           if (c * 32 >= p.N) break;
           uint32_t v[32];
           tmem_ld32(trow + c * 32, v);
@@ -732,13 +738,18 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
             ssp[j & 3] = fmaf(x, x, ssp[j & 3]);
           }
         }
-        const float ss = (ssp[0] + ssp[1]) + (ssp[2] + ssp[3]);
+        float ss = (ssp[0] + ssp[1]) + (ssp[2] + ssp[3]);
+        if (SPLIT) {
+          xch[warp * 32 + lane] = ss;
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          ss = xch[(warp & 3) * 32 + lane] + xch[(4 + (warp & 3)) * 32 + lane];     // same order in both groups
+        }
         const float nrm = fmaxf(sqrtf(ss), 1e-12f);
         const float inv = 1.f / nrm;
-        if (row < p.M && p.rnorm != nullptr) p.rnorm[row] = nrm;
+        if (row < p.M && p.rnorm != nullptr && (!SPLIT || grp == 0)) p.rnorm[row] = nrm;
         float s1p[2] = {0.f, 0.f}, s2p[2] = {0.f, 0.f};
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = c_lo; c < c_hi; ++c) {
           const int nbase = c * 32;
           if (nbase >= p.N) break;
           uint32_t v[32];
@@ -793,7 +804,14 @@ tc_gemm2_kernel(const __grid_constant__ Maps maps, const Params p) {
           }
           __syncwarp();
         }
-        if (row < p.M && p.rowstat != nullptr) p.rowstat[row] = make_float2(s1p[0] + s1p[1], s2p[0] + s2p[1]);
+        if (SPLIT) {
+          xch[256 + warp * 32 + lane] = s1p[0] + s1p[1];
+          xch[512 + warp * 32 + lane] = s2p[0] + s2p[1];
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+          if (grp == 0 && row < p.M && p.rowstat != nullptr)
+            p.rowstat[row] = make_float2(xch[256 + warp * 32 + lane] + xch[256 + (warp + 4) * 32 + lane],
+                                         xch[512 + warp * 32 + lane] + xch[512 + (warp + 4) * 32 + lane]);
+        } else if (row < p.M && p.rowstat != nullptr) p.rowstat[row] = make_float2(s1p[0] + s1p[1], s2p[0] + s2p[1]);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(a));
@@ -1250,7 +1268,8 @@ int run_norm(const gp_gemm_bf16x* g, float* rnorm, float* rowstat, int stat_relu
   p.rnorm = rnorm; p.rowstat = reinterpret_cast<float2*>(rowstat); p.stat_relu = stat_relu;
   p.cond = nullptr; p.cond_npairs = 0; p.cond_alpha = 1.f;
   p.adj_flags = nullptr; p.sym_total = 0; p.sym_per_graph = 0; p.order = nullptr; p.tri = 0; p.upper_only = 0;
-  if (BN == 512) return launch<512, 2, 2, 4>(maps, p, st);
+  static const bool one_group512 = getenv("GP_TAIL_EW4") != nullptr;
+  if (BN == 512) return one_group512 ? launch<512, 2, 2, 4>(maps, p, st) : launch<512, 2, 2, 8>(maps, p, st);
   static const bool one_group = getenv("GP_TAIL_EW4") != nullptr;
   if (one_group) return BN == 256 ? launch<256, 3, 2, 4>(maps, p, st) : launch<128, 4, 2, 4>(maps, p, st);
   if (BN == 256) return launch<256, 3, 2, 8>(maps, p, st);
