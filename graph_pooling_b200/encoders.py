@@ -102,7 +102,7 @@ def _fwd_tc(ctx, plan, x, adj, assign_x, params):
                 # level 0 with assign_x == x: both GCNs start from the same U = A.x -- compute it once
                 u0 = c_emb.layers[0][4] if (i == 0 and xab is xb) else None
                 za, zab, c_as = T.stack_forward(ws, xab, xa_d, cur_adjb, cur_nb, B, cur_N, wa, ba, True, u0=u0,
-                                                pad_last=pad)
+                                                pad_last=pad, h32=False)
             c_as.pad_grad_zero = True                   # S's pad rows are masked: no gradient reaches this stack's pad rows
             Fa = za.shape[2]
             wp, bp = _wb(params, plan.assign_pred[i])

@@ -200,6 +200,7 @@ def _stack_begin(ws, xb, din, adjb, nb, B, N, weights, biases, bn, pad_last=0):
     ctx.zb = bfbuf(ws, B, N, Fw)
     ctx.offs = [sum(douts[:l]) for l in range(L)]
     ctx.aligned = all(o % 8 == 0 for o in ctx.offs)
+    ctx.h32 = True           # write H = BN(relu(Y)) of the non-last layers as fp32 too (readout / dropout / unaligned concat)
     ctx.cur, ctx.cur_d = xb, din
     return ctx
 
@@ -246,7 +247,8 @@ def _layer_forward(ws, ctx, l, ub, hb2=None):
             mean, invstd = ws.f(N), ws.f(N)
             call('gp_bn_finalize', rowstat.data_ptr(), B, N, dout, mean.data_ptr(), invstd.data_ptr(), st)
         if not last:
-            call('gp_bn_apply', y_ptr, ldy, E._p(mean), E._p(invstd), B, N, dout, 1, int(use_bn), slot, Fw,
+            call('gp_bn_apply', y_ptr, ldy, E._p(mean), E._p(invstd), B, N, dout, 1, int(use_bn),
+                 slot if (ctx.h32 or not ctx.aligned) else None, Fw,
                  hb.ptr, hb.ld, None if hb2 is None else hb2.ptr, 0 if hb2 is None else hb2.ld, st)
     else:
         # wide layer (e.g. the assignment GCN's last layer, dout = K): plain GEMM, then one normalize pass
@@ -273,12 +275,15 @@ def _stack_end(ws, ctx):
     return ctx.zcat, ctx.zb, ctx
 
 
-def stack_forward(ws, xb, din, adjb, nb, B, N, weights, biases, bn, u0=None, pad_last=0, drops=None, seed=0):
+def stack_forward(ws, xb, din, adjb, nb, B, N, weights, biases, bn, u0=None, pad_last=0, drops=None, seed=0, h32=True):
     """TC version of engine.stack_forward (add_self unsupported).  xb/adjb: bf16 operands.
     Per layer:  U = A.X (tcgen05)  ->  _layer_forward.
     u0: optional precomputed U of the first layer (shared with another stack that has the same A and X).
     Returns (zcat fp32 [B,N,F], zb bf16 operand of the same concat, ctx)."""
     ctx = _stack_begin(ws, xb, din, adjb, nb, B, N, weights, biases, bn, pad_last)
+    # h32 = False (assignment GCNs: nobody reads the fp32 H of their inner layers -- the assignment head, the next layer
+    # and the backward all use the bf16 operand / the saved Y): 4 bytes per element less to write per inner layer
+    ctx.h32 = bool(h32) or (drops is not None and any(d > 0.0 for d in drops))
     nbp, lim = E._p(nb), int(nb is not None)
     ctx.drops = [None] * len(weights)
     for l in range(len(weights)):
@@ -318,6 +323,7 @@ def dual_stack_forward(ws, xb, din, xab, dina, adjb, nb, B, N, wE, bE, bnE, wA, 
     both U's (A.X at 128 columns is HBM-bound on reading A: sharing the pass halves that traffic)."""
     cE = _stack_begin(ws, xb, din, adjb, nb, B, N, wE, bE, bnE)
     cA = _stack_begin(ws, xab, dina, adjb, nb, B, N, wA, bA, bnA, pad_lastA)
+    cA.h32 = False           # the assignment GCN's inner H is consumed as bf16 only
     nbp, lim = E._p(nb), int(nb is not None)
     L = len(wE)
     hcat = None

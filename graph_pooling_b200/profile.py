@@ -98,8 +98,8 @@ class CallProfiler:
                 return ('layer_bwd d=%d bn=%d rows=%d' % (q.d, q.bn, int(rows)), 0.0, by, 'fp32 in, bf16/fp32 dV out')
             if name == 'gp_bn_apply':
                 B, N, d = _ival(args[4]), _ival(args[5]), _ival(args[6])
-                outs = 4.0 + (2.0 if _ival(args[11]) else 0.0) + (2.0 if _ival(args[13]) else 0.0)
-                return ('bn_apply d=%d rows=%d' % (d, B * N), 0.0, float(B) * N * d * (4.0 + outs), 'fp32 in, fp32 + bf16 out')
+                outs = (4.0 if _ival(args[9]) else 0.0) + (2.0 if _ival(args[11]) else 0.0) + (2.0 if _ival(args[13]) else 0.0)
+                return ('bn_apply d=%d rows=%d' % (d, B * N), 0.0, float(B) * N * d * (4.0 + outs), 'fp32 in, fp32 (embedding stack only) + bf16 out')
             if name in ('gp_softmax_mask_fwd_x', 'gp_softmax_mask_bwd_x'):
                 o = 2 if name.endswith('fwd_x') else 3
                 B, N, K = _ival(args[o]), _ival(args[o + 1]), _ival(args[o + 2])
