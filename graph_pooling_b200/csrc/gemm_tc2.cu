@@ -1231,7 +1231,10 @@ int run(const gp_gemm_bf16x* g, cudaStream_t st) {
   static const int ew16 = getenv("GP_GEMM_EW16") ? atoi(getenv("GP_GEMM_EW16")) : 3;    // bit 0: BN = 128, bit 1: CTA pairs
   int ksum = 0;
   for (int q = 0; q < g->npairs; ++q) ksum += g->pair[q].K;
-  if (pair) return ((ew16 & 2) && ksum <= 1024) ? launch_pair<4, 16>(maps, p, st) : launch_pair<6, 8>(maps, p, st);
+  // CTA pairs: also the read-modify-write launches (beta != 0 into an fp32 C: the three-pair dS, 0.72 -> 0.61 ms); long
+  // contractions with a plain store are better off with six stages and eight warps (A.[h|a] 1.83 vs 2.00 ms)
+  const bool heavy_epi = ksum <= 1024 || (g->C != nullptr && g->beta != 0.f);
+  if (pair) return ((ew16 & 2) && heavy_epi) ? launch_pair<4, 16>(maps, p, st) : launch_pair<6, 8>(maps, p, st);
   if (BN == 256) return launch<256, 4, 0, 8>(maps, p, st);
   if (BN == 128 && (ew16 & 1) && ksum <= 256 && split == 1) return launch<128, 4, 0, 16>(maps, p, st);
   if (BN == 128) return launch<128, 6, 0, 8>(maps, p, st);
