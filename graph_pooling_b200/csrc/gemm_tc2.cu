@@ -1128,7 +1128,7 @@ static int launch_pair(const Maps& maps, Params& p, cudaStream_t st) {
   p.pair = 1;
   p.tiles_m = (p.M + 2 * BM - 1) / (2 * BM);
   p.tiles_n = (p.N + 255) / 256;
-  p.total_work = (long long)p.tiles_m * p.tiles_n * p.batch;
+  p.total_work = (long long)p.tiles_m * p.tiles_n * p.batch * (p.split_k > 1 ? p.split_k : 1);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.blockDim = dim3((EW + 2) * 32);
@@ -1181,11 +1181,11 @@ int run(const gp_gemm_bf16x* g, cudaStream_t st) {
   Maps maps;
   Params p;
   const int BN = pick_bn(g->N);
-  // CTA pair (cta_group::2, UMMA M = 256): plain epilogue, 256-column tiles, no split-K, and a row count whose last
+  // CTA pair (cta_group::2, UMMA M = 256): plain epilogue, 256-column tiles (split-K included), and a row count whose last
   // 256-row block is not mostly padding
   static const bool no_pair = getenv("GP_NO_PAIR") != nullptr;
   const int t128 = (g->M + BM - 1) / BM, t256 = (g->M + 2 * BM - 1) / (2 * BM);
-  const bool pair = !no_pair && BN == 256 && split == 1 && t128 >= 2 && 2 * t256 * 16 <= t128 * 17;
+  const bool pair = !no_pair && BN == 256 && t128 >= 2 && 2 * t256 * 16 <= t128 * 17;
   for (int q = 0; q < g->npairs; ++q) {
     const gp_operand_pair& o = g->pair[q];
     GP_REQUIRE(o.A && o.B && o.K > 0, "bgemm_bf16x: pair %d: null operand or K <= 0", q);
@@ -1233,7 +1233,7 @@ int run(const gp_gemm_bf16x* g, cudaStream_t st) {
   for (int q = 0; q < g->npairs; ++q) ksum += g->pair[q].K;
   // CTA pairs: also the read-modify-write launches (beta != 0 into an fp32 C: the three-pair dS, 0.72 -> 0.61 ms); long
   // contractions with a plain store are better off with six stages and eight warps (A.[h|a] 1.83 vs 2.00 ms)
-  const bool heavy_epi = ksum <= 1024 || (g->C != nullptr && g->beta != 0.f);
+  const bool heavy_epi = (ksum <= 1024 || (g->C != nullptr && g->beta != 0.f)) && split == 1;
   if (pair) return ((ew16 & 2) && heavy_epi) ? launch_pair<4, 16>(maps, p, st) : launch_pair<6, 8>(maps, p, st);
   if (BN == 256) return launch<256, 4, 0, 8>(maps, p, st);
   if (BN == 128 && (ew16 & 1) && ksum <= 256 && split == 1) return launch<128, 4, 0, 16>(maps, p, st);
