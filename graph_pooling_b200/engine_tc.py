@@ -150,9 +150,25 @@ def tcgemm(A, a_major, Bo, b_major, M, N, K, batch, Cf=None, Cb=None, lim=None, 
 
 
 def pick_split(M, N, K):
-    tiles = ((M + 127) // 128) * ((N + 255) // 256 if N > 128 else 1)
-    kt = max(1, K // 64)
-    return int(max(1, min(kt, 1024, (296 + tiles - 1) // tiles)))
+    """Split-K factor of a weight-gradient GEMM (few output tiles, a contraction over all B*N rows): the one whose work
+    items fill the persistent grid best in at most three rounds.  The grid is 148 CTAs, or 74 CTA pairs when the launch is
+    pair-eligible (gemm_tc2.cu `run`: 256-column tiles, >= 2 row blocks, last 256-row block not mostly padding) -- e.g. cfg4's
+    dWp (512 x 768): 6 pair tiles, 37 splits = 222 items = exactly three rounds (25 splits were 2.03 rounds: 68 %)."""
+    t128, t256 = (M + 127) // 128, (M + 255) // 256
+    pair = N > 128 and t128 >= 2 and 2 * t256 * 16 <= t128 * 17 and not os.environ.get('GP_NO_PAIR')
+    tiles = (t256 if pair else t128) * ((N + 255) // 256 if N > 128 else 1)
+    units = 74 if pair else 148
+    smax = int(max(1, min(K // 256, 1024)))              # at least four 64-wide k-steps per split
+    best, best_eff = 1, 0.0
+    for sp in range(1, min(smax, (3 * units) // tiles + 1) + 1):
+        items = tiles * sp
+        rounds = -(-items // units)
+        if rounds > 3:
+            break
+        eff = items / float(units * rounds)
+        if eff > best_eff + 1e-9:
+            best, best_eff = sp, eff
+    return best
 
 
 # ------------------------------------------------------------------------------------------
