@@ -575,7 +575,8 @@ def main():
                 gstep._eager(next(iter(gstep._graphs.values())))
             else:
                 step(x, adj, label)
-        rows_, prof_ms = cp.table(hbm, tf_burst if prec == 'bf16' else FFMA_TF)
+        rows_, prof_ms = cp.table(hbm, tf_burst if prec == 'bf16' else FFMA_TF,
+                                  min_share=float(os.environ.get('GP_BENCH_MIN_SHARE', 0.03)))
         kernels_tab = [{k: (round(v, 6) if isinstance(v, float) else v) for k, v in r.items()
                         if k in ('entry', 'shape', 'launches', 'ms', 'ms_per_launch', 'share', 'bound', 'achieved',
                                  'peak', 'unit', 'frac', 'flops', 'bytes', 'counted_at')} for r in rows_]
