@@ -62,7 +62,7 @@ class GpLayerBwd(C.Structure):
                 ('rnorm', c_f), ('mean', c_f), ('invstd', c_f),
                 ('B', c_i), ('N', c_i), ('d', c_i), ('relu', c_i), ('bn', c_i), ('normalize', c_i),
                 ('dv', c_f), ('dv_bf16', c_f), ('lddvb', c_ll), ('db', c_f), ('ws', c_f), ('lddxn', c_ll),
-                ('nb_zero', c_f)]
+                ('nb_zero', c_f), ('dz_bf16', c_i), ('dxn_bf16', c_i)]
 
 
 # ---- packed small-graph schedule (include/gp_b200.h "PACKED schedule") ---------------------------------------------
@@ -177,6 +177,7 @@ _PROTOS = {
     'gp_mul_add_dev': [c_f, c_f, c_f, c_f, c_f, c_f],
     'gp_add_scaled': [c_f, c_f, C.c_float, c_f, c_f],
     'gp_linkloss_tc_partials': [c_i, c_i],
+    'gp_gcn_layer_bwd_vectorised': [c_i, c_i, c_i],
     'gp_pool_chain_bf16': [c_f, c_ll, c_f, c_ll, c_f, c_f, c_i, c_i, c_i, c_f, c_ll, c_f, c_ll, c_f, c_ll, c_f],
     'gp_linkloss_from_q_partials': [c_i, c_i],
     'gp_linkloss_from_q': [c_f, c_f, c_f, c_i, c_i, c_f, c_f, c_f],

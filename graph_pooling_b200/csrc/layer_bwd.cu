@@ -37,6 +37,7 @@ struct LbArgs {
   float* dv; __nv_bfloat16* dvb; long long lddvb;
   float* part;          // [blocks][d] partial column sums or NULL
   const int32_t* nbz;   // rows n >= nbz[b] have zero upstream gradient (row kernels: dV = 0 written without reading)
+  int dz_bf16, dxn_bf16;   // dz / dxn point to bf16 data (strides in elements): gradient intermediates of the bf16 schedule
 };
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -48,13 +49,26 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 // read-once operands: streaming (evict-first) loads keep them from displacing the Y rows the kernel reads twice
 __device__ __forceinline__ float4 ld4s(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
 
+// 4 consecutive bf16 values as floats (8-byte load)
+template <bool STREAM>
+__device__ __forceinline__ float4 ld4h(const __nv_bfloat16* p) {
+  const uint2 w = STREAM ? __ldcs(reinterpret_cast<const uint2*>(p)) : *reinterpret_cast<const uint2*>(p);
+  return make_float4(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xffff0000u), __uint_as_float(w.y << 16),
+                     __uint_as_float(w.y & 0xffff0000u));
+}
+
 // combined upstream gradient of 4 consecutive columns of row (b, n)
 template <bool STREAM = false>
 __device__ __forceinline__ float4 load_g(const LbArgs& a, int b, int n, long long row, int c) {
   float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (a.dz != nullptr) g = STREAM ? ld4s(a.dz + row * a.lddz + c) : ld4(a.dz + row * a.lddz + c);
+  if (a.dz != nullptr) {
+    if (a.dz_bf16) g = ld4h<STREAM>(reinterpret_cast<const __nv_bfloat16*>(a.dz) + row * a.lddz + c);
+    else g = STREAM ? ld4s(a.dz + row * a.lddz + c) : ld4(a.dz + row * a.lddz + c);
+  }
   if (a.dxn != nullptr) {
-    const float4 t = STREAM ? ld4s(a.dxn + row * a.lddxn + c) : ld4(a.dxn + row * a.lddxn + c);
+    float4 t;
+    if (a.dxn_bf16) t = ld4h<STREAM>(reinterpret_cast<const __nv_bfloat16*>(a.dxn) + row * a.lddxn + c);
+    else t = STREAM ? ld4s(a.dxn + row * a.lddxn + c) : ld4(a.dxn + row * a.lddxn + c);
     g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
   }
   if (a.dout != nullptr) {
@@ -764,6 +778,7 @@ __global__ void __launch_bounds__(128, MINB) layer_bwd_row_wide_kernel(const LbA
 }
 
 static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static bool al8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0; }
 
 // shape-level eligibility for the vectorised kernels (pointer alignment is checked per call)
 static bool shape_fast(int B, int d, int bn, int* CS_out) {
@@ -818,8 +833,8 @@ static int launch_bn(const LbArgs& a, int CS, int rpc, cudaStream_t st) {
 // full eligibility of one call for the vectorised kernels: shape AND pointer / stride alignment
 static bool fast_eligible(const gp_layer_bwd* q, int* CS_out) {
   if (!al16(q->y) || q->ldy % 4 != 0) return false;
-  if (q->dz != nullptr && (!al16(q->dz) || q->lddz % 4 != 0)) return false;
-  if (q->dxn != nullptr && (!al16(q->dxn) || q->lddxn % 4 != 0)) return false;
+  if (q->dz != nullptr && (!(q->dz_bf16 ? al8(q->dz) : al16(q->dz)) || q->lddz % 4 != 0)) return false;
+  if (q->dxn != nullptr && (!(q->dxn_bf16 ? al8(q->dxn) : al16(q->dxn)) || q->lddxn % 4 != 0)) return false;
   if (q->dout != nullptr && (!al16(q->dout) || !al16(q->argidx) || q->ldo % 4 != 0)) return false;
   if (q->h != nullptr && (!al16(q->h) || q->ldh % 4 != 0)) return false;
   if (q->dv != nullptr && !al16(q->dv)) return false;
@@ -840,6 +855,7 @@ int layer_bwd_fast(const gp_layer_bwd* q, cudaStream_t st, bool* handled) {
   a.dv = q->dv; a.dvb = reinterpret_cast<__nv_bfloat16*>(q->dv_bf16); a.lddvb = q->lddvb;
   a.part = q->db != nullptr ? q->ws : nullptr;
   a.nbz = q->bn ? nullptr : q->nb_zero;
+  a.dz_bf16 = q->dz != nullptr && q->dz_bf16; a.dxn_bf16 = q->dxn != nullptr && q->dxn_bf16;
   long long part_rows = 0;
   static int use_cta = -1;
   if (use_cta < 0) { const char* e = getenv("GP_LBWD_CTA"); use_cta = (e == nullptr || atoi(e) != 0) ? 1 : 0; }
@@ -883,7 +899,7 @@ int layer_bwd_fast(const gp_layer_bwd* q, cudaStream_t st, bool* handled) {
   // the one-node-per-cluster kernel -- both ~2.5 TB/s; the per-node cluster sync + reduction chain bounds them,
   // not HBM.  Kept for the next step (several nodes per iteration to amortise the sync).
   if (use_pipe < 0) { const char* e = getenv("GP_LBWD_PIPE"); use_pipe = (e != nullptr && atoi(e) != 0) ? 1 : 0; }
-  if (q->bn && use_pipe && q->h == nullptr && q->mean != nullptr) {
+  if (q->bn && use_pipe && q->h == nullptr && q->mean != nullptr && !a.dz_bf16 && !a.dxn_bf16) {
     // persistent pipelined variant when two stages of a CTA's rows fit in shared memory
     int PCS = 1;
     const int nstreams = 1 + (q->dz ? 1 : 0) + (q->dxn ? 1 : 0);
@@ -993,6 +1009,8 @@ int layer_bwd_fast(const gp_layer_bwd* q, cudaStream_t st, bool* handled) {
 using namespace gp;
 
 extern "C" long long gp_gcn_layer_bwd_ws(int B, int N, int d, int bn) { return ws_floats(B, N, d, bn); }
+// 1 if a layer of this shape runs on the vectorised kernels (given aligned operands): the only ones that take bf16 dz / dxn
+extern "C" int gp_gcn_layer_bwd_vectorised(int B, int d, int bn) { return shape_fast(B, d, bn, nullptr) ? 1 : 0; }
 
 // exact workspace of ONE call (ws / db fields ignored): the generic kernel borrows an fp32 dV from ws when the
 // caller asked for the bias gradient without an fp32 dV and the operands miss the vectorised path's alignment.
@@ -1014,6 +1032,7 @@ extern "C" int gp_gcn_layer_bwd_x(const gp_layer_bwd* q, gp_stream_t stream) {
   bool handled = false;
   GP_TRY(layer_bwd_fast(q, S(stream), &handled));
   if (handled) return GP_OK;
+  GP_REQUIRE(!q->dz_bf16 && !q->dxn_bf16, "gcn_layer_bwd_x: bf16 gradient sources need the vectorised path (d %% 4 == 0, aligned rows)");
   // generic path: with db but no fp32 dV it borrows B*N*d floats from ws -- size ws with gp_gcn_layer_bwd_ws_x
   return layer_bwd_generic(q, S(stream));
 }

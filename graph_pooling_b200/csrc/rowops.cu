@@ -706,6 +706,7 @@ extern "C" int gp_gcn_layer_bwd(const float* dz, long long lddz, const float* dx
   q.h = h; q.ldh = ldh; q.y = y; q.ldy = ldy; q.rnorm = rnorm; q.mean = nullptr; q.invstd = invstd;
   q.B = B; q.N = N; q.d = d; q.relu = relu; q.bn = bn; q.normalize = normalize;
   q.dv = dv; q.dv_bf16 = nullptr; q.lddvb = 0; q.db = nullptr; q.ws = nullptr; q.lddxn = 0; q.nb_zero = nullptr;
+  q.dz_bf16 = q.dxn_bf16 = 0;
   return gp_gcn_layer_bwd_x(&q, stream);
 }
 

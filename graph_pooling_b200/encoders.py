@@ -199,18 +199,26 @@ def _bwd_tc(ctx, tape, dypred, dS0):
                 ds, acc_ds = _padded_grad(ws, plan, dS0, B, Ni, lv['Kr'], K), 1
             else:
                 ds, acc_ds = ws.f(B, Ni, K), 0
+            # level 0 with lock-step stacks: dZ, dza and the per-layer dX stay bf16 between the GEMM epilogues and the
+            # layer-backward row kernels (needs 16-byte aligned concat slots: Fw % 8 == 0 and Fa % 8 == 0)
+            g16 = bool(i == 0 and tape['dual'] and T.bf16_grads() and Fw % 8 == 0 and lv['Fa'] % 8 == 0 and
+                       T.stack_takes_bf16_grads(tape['emb']) and T.stack_takes_bf16_grads(lv['c_as']))
             dz = T.pool_backward(ws, dxp, d_ap[i], lv['sb'], lv['zb'], lv['adjb'], lv['tb'], lv['nb'], B, Ni, K, Fw,
-                                 ds, acc_ds, None if i == 0 else d_ap[i - 1], asym=lv['asym'])
+                                 ds, acc_ds, None if i == 0 else d_ap[i - 1], asym=lv['asym'], dz_bf16=g16)
             dwp, dbp, dza = T.assign_head_bwd(ws, lv['S'], ds, lv['nb'], B, Ni, lv['zab'], lv['Fa'], lv['wpb'], K,
-                                              lv['has_bp'], Kreal=lv['Kr'], Fa_real=lv['Fa_r'])
+                                              lv['has_bp'], Kreal=lv['Kr'], Fa_real=lv['Fa_r'], dza_bf16=g16)
             iw, ib = plan.assign_pred[i]
             grads[iw] = dwp
             if ib is not None:
                 grads[ib] = dbp
             if i == 0 and tape['dual']:
                 # embedding + assignment GCN backward in lock-step (one A^T.dU pass per layer for both)
-                gE, gA = T.dual_stack_backward(ws, tape['emb'], lv['c_as'], dz.data_ptr(), Fw, dout_p, arg_p, ldo,
-                                               dza.data_ptr(), lv['Fa'])
+                if g16:
+                    gE, gA = T.dual_stack_backward(ws, tape['emb'], lv['c_as'], dz.ptr, dz.ld, dout_p, arg_p, ldo,
+                                                   dza.ptr, dza.ld, dz_bf16=True)
+                else:
+                    gE, gA = T.dual_stack_backward(ws, tape['emb'], lv['c_as'], dz.data_ptr(), Fw, dout_p, arg_p, ldo,
+                                                   dza.data_ptr(), lv['Fa'])
                 put(plan.emb, gE)
                 put(plan.assign[0], gA)
                 return (None, None, None, None, None) + tuple(_deliver(plan, params, grads))

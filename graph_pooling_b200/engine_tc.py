@@ -369,7 +369,7 @@ def dual_stack_forward(ws, xb, din, xab, dina, adjb, nb, B, N, wE, bE, bnE, wA, 
     return _stack_end(ws, cE), _stack_end(ws, cA)
 
 
-def _layer_backward_head(ws, ctx, l, dz_ptr, lddz, dxn, lddxn, dout_ptr, arg_ptr, ldo):
+def _layer_backward_head(ws, ctx, l, dz_ptr, lddz, dxn, lddxn, dout_ptr, arg_ptr, ldo, dz_bf16=False, dxn_bf16=False):
     """Element-wise tail backward of layer l (bf16 dV + db in ONE pass over HBM; Hhat is recomputed from Y and the
     saved statistics) and dW = U^T dV.  Returns (dvb, dw, db)."""
     st = E._stream()
@@ -384,8 +384,9 @@ def _layer_backward_head(ws, ctx, l, dz_ptr, lddz, dxn, lddxn, dout_ptr, arg_ptr
     has_b = ctx.biases[l] is not None
     db = ws.f(dout) if has_b else None
     q = GpLayerBwd()
-    q.dz, q.lddz = (None if dz_ptr is None else dz_ptr + off * 4), lddz
+    q.dz, q.lddz = (None if dz_ptr is None else dz_ptr + off * (2 if dz_bf16 else 4)), lddz
     q.dxn, q.lddxn = dxn, lddxn
+    q.dz_bf16, q.dxn_bf16 = int(bool(dz_bf16 and dz_ptr is not None)), int(bool(dxn_bf16 and dxn is not None))
     q.dout = None if dout_ptr is None else dout_ptr + off * 4
     q.argidx = None if arg_ptr is None else arg_ptr + off * 4
     q.ldo = ldo
@@ -452,32 +453,43 @@ def stack_backward(ws, ctx, dz_ptr, lddz, dout_ptr, arg_ptr, ldo, need_dx, dadj)
     return grads, dxn
 
 
-def dual_stack_backward(ws, cE, cA, dzE_ptr, lddzE, doutE_ptr, argE_ptr, ldo, dzA_ptr, lddzA):
+def dual_stack_backward(ws, cE, cA, dzE_ptr, lddzE, doutE_ptr, argE_ptr, ldo, dzA_ptr, lddzA, dz_bf16=False):
     """Backward of dual_stack_forward (level 0: no dX of the first layer, no dA): per layer both tails, then ONE
-    dX = A^T [dU_e | dU_a] pass over the adjacency for both stacks."""
+    dX = A^T [dU_e | dU_a] pass over the adjacency for both stacks.  dz_bf16: both dz sources are bf16 buffers (lddz in
+    elements); the lock-step dX is then kept in bf16 as well."""
     B, N = cE.B, cE.N
+    xb16 = bool(dz_bf16)
+    esz = 2 if xb16 else 4
     L = len(cE.layers)
     gE, gA = [None] * L, [None] * L
     nbp, lim = E._p(cE.nb), int(cE.nb is not None)
-    dxcat, wcat, de_in = None, 0, 0
+    dxcat, wcat, de_in, dx_ptr, dx_ld = None, 0, 0, None, 0
     for l in reversed(range(L)):
         dinE, dinA = cE.layers[l][1], cA.layers[l][1]
         if dxcat is None:
             xE = xA = None
         else:
-            xE, xA = dxcat.data_ptr(), dxcat.data_ptr() + de_in * 4
-        dvE, dw, db = _layer_backward_head(ws, cE, l, dzE_ptr, lddzE, xE, wcat, doutE_ptr, argE_ptr, ldo)
+            xE, xA = dx_ptr, dx_ptr + de_in * esz
+        dvE, dw, db = _layer_backward_head(ws, cE, l, dzE_ptr, lddzE, xE, dx_ld, doutE_ptr, argE_ptr, ldo,
+                                           dz_bf16=dz_bf16, dxn_bf16=xb16)
         gE[l] = (dw, db)
-        dvA, dw, db = _layer_backward_head(ws, cA, l, dzA_ptr, lddzA, xA, wcat, None, None, 0)
+        dvA, dw, db = _layer_backward_head(ws, cA, l, dzA_ptr, lddzA, xA, dx_ld, None, None, 0,
+                                           dz_bf16=dz_bf16, dxn_bf16=xb16)
         gA[l] = (dw, db)
         if l > 0:
             wcat, de_in = dinE + dinA, dinE
             ducat = bfbuf(ws, B, N, wcat)
             _layer_du(ws, cE, l, dvE, Op(ducat.ptr, ducat.ld, 0))
             _layer_du(ws, cA, l, dvA, Op(ducat.ptr + dinE * 2, ducat.ld, 0))
-            dxcat = ws.f(B, N, wcat)
-            tcgemm(cE.adjb, MN, ducat, MN, N, wcat, N, B, Cf=(dxcat.data_ptr(), wcat, N * wcat), lim=nbp, lim_m=lim,
-                   lim_k=lim)
+            if xb16:
+                dxcat = bfbuf(ws, B, N, wcat)
+                dx_ptr, dx_ld = dxcat.ptr, dxcat.ld
+                tcgemm(cE.adjb, MN, ducat, MN, N, wcat, N, B, Cb=dxcat, lim=nbp, lim_m=lim, lim_k=lim)
+            else:
+                dxcat = ws.f(B, N, wcat)
+                dx_ptr, dx_ld = dxcat.data_ptr(), wcat
+                tcgemm(cE.adjb, MN, ducat, MN, N, wcat, N, B, Cf=(dx_ptr, wcat, N * wcat), lim=nbp, lim_m=lim,
+                       lim_k=lim)
     return gE, gA
 
 
@@ -494,6 +506,21 @@ def softmax_forward(ws, S, nb, B, N, K):
 
 
 CHAIN_POOLING = None     # None: decided by GP_CHAIN; True / False: set by the caller (tests, bench)
+
+
+def bf16_grads():
+    """Gradient intermediates between GEMM epilogues and the layer-backward row kernels (dZ of the pooling backward, dza
+    of the assignment head, the lock-step dX) are kept in bf16 -- like dV always was: half the bytes to write and to read
+    (-3.5 GB per cfg4 step).  GP_F32_GRADS=1 keeps them in fp32."""
+    return not os.environ.get('GP_F32_GRADS')
+
+
+def stack_takes_bf16_grads(ctx):
+    """Every layer of the stack runs on the vectorised layer-backward kernels (the only ones that read bf16 dz / dxn)."""
+    L = len(ctx.layers)
+    lib = load()
+    return ctx.aligned and all(lib.gp_gcn_layer_bwd_vectorised(ctx.B, ctx.douts[l], int(bool(ctx.bn and l < L - 1)))
+                               for l in range(L))
 
 
 def chain_ok(sb, adjb, N, K):
@@ -527,7 +554,7 @@ def pool_forward(ws, sb, zb, adjb, nb, B, N, K, Fw, keep_t=True):
     return sb, xp, xpb, tb, ap, apb
 
 
-def pool_backward(ws, dxp, dap, sb, zb, adjb, tb, nb, B, N, K, Fw, ds, acc_ds, dadj, asym=None):
+def pool_backward(ws, dxp, dap, sb, zb, adjb, tb, nb, B, N, K, Fw, ds, acc_ds, dadj, asym=None, dz_bf16=False):
     """asym: device flag from adj_prepare (0 = every adjacency of the batch is symmetric) or None.  For a symmetric
     A, T^T = A S, so T^T dA' + A (S dA'^T) = T^T (dA' + dA'^T): the N x N x K product and S dA'^T are skipped
     on the device (no host sync): the kernels read the flag."""
@@ -535,8 +562,12 @@ def pool_backward(ws, dxp, dap, sb, zb, adjb, tb, nb, B, N, K, Fw, ds, acc_ds, d
     dxpb = cvt(ws, dxp.data_ptr(), Fw, B * K, Fw, B=B)
     ldap = dap.shape[2]                                  # dA' rows may be padded (see _bwd_tc)
     dapb = cvt(ws, dap.data_ptr(), ldap, B * K, K, B=B)
-    dz = ws.f(B, N, Fw)
-    tcgemm(sb, KM, dxpb, MN, N, Fw, K, B, Cf=(dz.data_ptr(), Fw, N * Fw), lim=nbp, lim_m=lim)
+    if dz_bf16:                                          # dZ = S dX' as a bf16 buffer (an Op; consumed by gp_gcn_layer_bwd_x)
+        dz = bfbuf(ws, B, N, Fw)
+        tcgemm(sb, KM, dxpb, MN, N, Fw, K, B, Cb=dz, lim=nbp, lim_m=lim)
+    else:
+        dz = ws.f(B, N, Fw)
+        tcgemm(sb, KM, dxpb, MN, N, Fw, K, B, Cf=(dz.data_ptr(), Fw, N * Fw), lim=nbp, lim_m=lim)
     dsf = (ds.data_ptr(), K, N * K)
     wsb = bfbuf(ws, B, N, K)
     cond = E._p(asym)
@@ -583,7 +614,7 @@ def assign_linear_fwd(ws, zab, Fa, rows, wp, bp, Kp=0):
     return T, wpb
 
 
-def assign_head_bwd(ws, S, ds, nb, B, N, zab, Fa, wpb, K, has_bias, Kreal=0, Fa_real=0):
+def assign_head_bwd(ws, S, ds, nb, B, N, zab, Fa, wpb, K, has_bias, Kreal=0, Fa_real=0, dza_bf16=False):
     """Backward of S = softmax(assign_pred(za)) * mask: dT (bf16 operand + bias gradient in one pass), then
     dWp = dT^T za (split-K) and dza = dT Wp.  K / Fa may be the padded widths; the parameter gradients are produced
     at the real ones (Kreal x Fa_real: the real clusters / concat columns come first)."""
@@ -608,8 +639,12 @@ def assign_head_bwd(ws, S, ds, nb, B, N, zab, Fa, wpb, K, has_bias, Kreal=0, Fa_
            Cf=(dwp.data_ptr(), Fa_real, 0), split_k=pick_split(Kreal, Fa_real, rows))
     if has_bias and Kreal != K:
         dbp = dbp[:Kreal]
-    dza = ws.f(rows, Fa)
-    tcgemm(Op(dtb.ptr, dtb.ld, 0), KM, Op(wpb.ptr, wpb.ld, 0), MN, rows, Fa, K, 1, Cf=(dza.data_ptr(), Fa, 0))
+    if dza_bf16:                                         # bf16 buffer (an Op with ld = r8(Fa))
+        dza = bfbuf(ws, 1, rows, Fa)
+        tcgemm(Op(dtb.ptr, dtb.ld, 0), KM, Op(wpb.ptr, wpb.ld, 0), MN, rows, Fa, K, 1, Cb=Op(dza.ptr, dza.ld, 0))
+    else:
+        dza = ws.f(rows, Fa)
+        tcgemm(Op(dtb.ptr, dtb.ld, 0), KM, Op(wpb.ptr, wpb.ld, 0), MN, rows, Fa, K, 1, Cf=(dza.data_ptr(), Fa, 0))
     return dwp, dbp, dza
 
 

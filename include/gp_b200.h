@@ -271,10 +271,16 @@ typedef struct gp_layer_bwd {
   const int32_t* nb_zero;    /* optional, layers without BN only: the caller guarantees that rows n >= nb_zero[b] receive
                                 no upstream gradient (masked level: encoders.py:1080, 1275) -- their dV is written as
                                 zero without reading the operands (padding-aware row pass) */
+  int dz_bf16, dxn_bf16;     /* 1: dz / dxn point to bf16 data (row strides still in elements): the tensor-core schedule
+                                keeps these gradient intermediates (dza, dZ, the lock-step dX) in bf16 -- half the bytes
+                                to write and to read; vectorised path only */
 } gp_layer_bwd;
 int gp_gcn_layer_bwd_x(const gp_layer_bwd* q, gp_stream_t stream);
 long long gp_gcn_layer_bwd_ws(int B, int N, int d, int bn);
 long long gp_gcn_layer_bwd_ws_x(const gp_layer_bwd* q);
+/* 1 if a layer of this shape runs on the vectorised kernels (given 16-byte aligned operands) -- the precondition of
+ * dz_bf16 / dxn_bf16. */
+int gp_gcn_layer_bwd_vectorised(int B, int d, int bn);
 
 /* ---------------------------------------------------------------------------------------------
  * Max readout (encoders.py:1097,1257,1287): out[b,f] = max_n Z[b,n,f], pad rows (n >= nb[b])

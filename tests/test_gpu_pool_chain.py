@@ -129,9 +129,22 @@ def test_model_chain_equals_three_launch_schedule(monkeypatch):
     N, D, H, Cc, B = 300, 16, 32, 3, 4
     x, adj, nb, label = synth_batch(2, B, N, D, 40, N, Cc, 0.05)
     outs = []
-    from graph_pooling_b200 import engine_tc
+    from graph_pooling_b200 import engine_tc, _lib
+
+    class Names:                                  # records which C-ABI entry points the step calls
+        def __init__(self):
+            self.seen = set()
+
+        def begin(self, name, args):
+            self.seen.add(name)
+
+        def end(self, tok):
+            pass
+
     for no_chain in ('', '1'):
         monkeypatch.setattr(engine_tc, 'CHAIN_POOLING', not no_chain)
+        rec = Names()
+        _lib.set_hook(rec)
         torch.manual_seed(0)
         m = enc.SoftPoolingGcnEncoder(N, D, H, H, Cc, 3, H, assign_ratio=0.25, num_pooling=2).cuda()
         m.precision = 1
@@ -143,6 +156,8 @@ def test_model_chain_equals_three_launch_schedule(monkeypatch):
         with torch.no_grad():
             y_ng = m(xt, at, nb, assign_x=xt)
         assert torch.equal(y_ng, y.detach())
+        _lib.set_hook(None)
+        assert ('gp_pool_chain_bf16' in rec.seen) == (not no_chain)       # the schedule under test really ran
         outs.append((y.detach().clone(), loss.detach().clone(), g.clone()))
     (y0, l0, g0), (y1, l1, g1) = outs
     assert rel_l2(y0.cpu().numpy(), y1.cpu().numpy()) < 1e-5
