@@ -336,7 +336,9 @@ __global__ void __launch_bounds__(1024, 1) layer_bwd_bn_cta_kernel(const LbArgs 
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
-template <int VPT>
+// FULL: B == VPT * rows-per-pass, so no row of any pass falls outside the batch -- straight-line passes without bounds
+// branches, which also lets the compiler batch the loads of several passes (the kernel waits on load latency: ncu r2)
+template <int VPT, bool FULL = false>
 __global__ void __launch_bounds__(512, 2) layer_bwd_bn_cta2_kernel(const LbArgs a) {
   constexpr int T = 512;
   __shared__ float red[2][T / 32];
@@ -360,7 +362,7 @@ __global__ void __launch_bounds__(512, 2) layer_bwd_bn_cta2_kernel(const LbArgs 
   for (int j = 0; j < VPT; ++j) {
     const int b = r0 + j * rstep;
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f), yv = g;
-    if (b < a.B) {
+    if (FULL || b < a.B) {
       const long long row = (long long)b * a.N + n;
       g = load_g<true>(a, b, n, row, c);
       yv = ld4(a.y + row * a.ldy + c);
@@ -386,7 +388,7 @@ __global__ void __launch_bounds__(512, 2) layer_bwd_bn_cta2_kernel(const LbArgs 
 #pragma unroll
   for (int j = 0; j < VPT; ++j) {
     const int b = r0 + j * rstep;
-    const bool live = b < a.B;
+    const bool live = FULL || b < a.B;
     const long long row = (long long)(live ? b : 0) * a.N + n;
     float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
     float r = 1.f;
@@ -867,8 +869,10 @@ int layer_bwd_fast(const gp_layer_bwd* q, cudaStream_t st, bool* handled) {
     const int rstep2 = 512 / d4;
     const int vpt2 = (q->B + rstep2 - 1) / rstep2;
     if (use_cta2 && a.dv == nullptr && a.dvb != nullptr && vpt2 > 4 && vpt2 <= 16 && d <= 512) {
-      if (vpt2 <= 8) layer_bwd_bn_cta2_kernel<8><<<q->N, 512, 0, st>>>(a);
-      else layer_bwd_bn_cta2_kernel<16><<<q->N, 512, 0, st>>>(a);
+      static const bool no_full = getenv("GP_LBWD_NOFULL") != nullptr;
+      const bool full = !no_full && q->B == (vpt2 <= 8 ? 8 : 16) * rstep2;
+      if (vpt2 <= 8) { if (full) layer_bwd_bn_cta2_kernel<8, true><<<q->N, 512, 0, st>>>(a); else layer_bwd_bn_cta2_kernel<8><<<q->N, 512, 0, st>>>(a); }
+      else { if (full) layer_bwd_bn_cta2_kernel<16, true><<<q->N, 512, 0, st>>>(a); else layer_bwd_bn_cta2_kernel<16><<<q->N, 512, 0, st>>>(a); }
       GP_LAUNCHED();
       part_rows = q->N;
       if (q->db != nullptr)
