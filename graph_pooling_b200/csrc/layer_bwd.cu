@@ -82,6 +82,32 @@ __device__ __forceinline__ float4 load_g(const LbArgs& a, int b, int n, long lon
   return g;
 }
 
+// The same with the source configuration known at compile time (CFG >= 0: dz and dxn both present; bit 0: dz is bf16,
+// bit 1: dxn is bf16, bit 2: the readout scatter is present): no per-pass branches, so the loads of several passes can
+// be issued back to back.  CFG < 0: the run-time form above.
+template <bool STREAM, int CFG>
+__device__ __forceinline__ float4 load_g_cfg(const LbArgs& a, int b, int n, long long row, int c) {
+  if constexpr (CFG < 0) {
+    return load_g<STREAM>(a, b, n, row, c);
+  } else {
+    float4 g, t;
+    if constexpr ((CFG & 1) != 0) g = ld4h<STREAM>(reinterpret_cast<const __nv_bfloat16*>(a.dz) + row * a.lddz + c);
+    else g = STREAM ? ld4s(a.dz + row * a.lddz + c) : ld4(a.dz + row * a.lddz + c);
+    if constexpr ((CFG & 2) != 0) t = ld4h<STREAM>(reinterpret_cast<const __nv_bfloat16*>(a.dxn) + row * a.lddxn + c);
+    else t = STREAM ? ld4s(a.dxn + row * a.lddxn + c) : ld4(a.dxn + row * a.lddxn + c);
+    g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+    if constexpr ((CFG & 4) != 0) {
+      const int4 i4 = *reinterpret_cast<const int4*>(a.argidx + (long long)b * a.ldo + c);
+      const float4 o = ld4(a.dout + (long long)b * a.ldo + c);
+      if (i4.x == n) g.x += o.x;
+      if (i4.y == n) g.y += o.y;
+      if (i4.z == n) g.z += o.z;
+      if (i4.w == n) g.w += o.w;
+    }
+    return g;
+  }
+}
+
 __device__ __forceinline__ void store_dv(const LbArgs& a, long long row, int c, float4 v) {
   if (a.dv != nullptr) *reinterpret_cast<float4*>(a.dv + row * a.d + c) = v;
   if (a.dvb != nullptr)
@@ -338,8 +364,12 @@ __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 
 
 // FULL: B == VPT * rows-per-pass, so no row of any pass falls outside the batch -- straight-line passes without bounds
 // branches, which also lets the compiler batch the loads of several passes (the kernel waits on load latency: ncu r2)
-template <int VPT, bool FULL = false>
+// CFG >= 0: gradient sources fixed at compile time (load_g_cfg) and ReLU + normalize both on (every BatchNorm layer of
+// the tensor-core schedule): branch-free passes.
+template <int VPT, bool FULL = false, int CFG = -1>
 __global__ void __launch_bounds__(512, 2) layer_bwd_bn_cta2_kernel(const LbArgs a) {
+  constexpr bool FIX = CFG >= 0;
+  const bool relu = FIX ? true : (a.relu != 0), normalize = FIX ? true : (a.normalize != 0);
   constexpr int T = 512;
   __shared__ float red[2][T / 32];
   __shared__ float tot[2];
@@ -353,8 +383,8 @@ __global__ void __launch_bounds__(512, 2) layer_bwd_bn_cta2_kernel(const LbArgs 
   const int r0 = tid >> lg4;
   const float mu = a.mean[n], is = a.invstd[n];
   auto hhat4 = [&](const float4 y) -> float4 {
-    return make_float4(((a.relu ? fmaxf(y.x, 0.f) : y.x) - mu) * is, ((a.relu ? fmaxf(y.y, 0.f) : y.y) - mu) * is,
-                       ((a.relu ? fmaxf(y.z, 0.f) : y.z) - mu) * is, ((a.relu ? fmaxf(y.w, 0.f) : y.w) - mu) * is);
+    return make_float4(((relu ? fmaxf(y.x, 0.f) : y.x) - mu) * is, ((relu ? fmaxf(y.y, 0.f) : y.y) - mu) * is,
+                       ((relu ? fmaxf(y.z, 0.f) : y.z) - mu) * is, ((relu ? fmaxf(y.w, 0.f) : y.w) - mu) * is);
   };
   uint2 gs[VPT];                                         // g as 4 x bf16
   float s1 = 0.f, s2 = 0.f;
@@ -364,7 +394,7 @@ __global__ void __launch_bounds__(512, 2) layer_bwd_bn_cta2_kernel(const LbArgs 
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f), yv = g;
     if (FULL || b < a.B) {
       const long long row = (long long)b * a.N + n;
-      g = load_g<true>(a, b, n, row, c);
+      g = load_g_cfg<true, CFG>(a, b, n, row, c);
       yv = ld4(a.y + row * a.ldy + c);
     }
     const float4 hj = hhat4(yv);                         // rows beyond B have g == 0: they add nothing
@@ -394,20 +424,20 @@ __global__ void __launch_bounds__(512, 2) layer_bwd_bn_cta2_kernel(const LbArgs 
     float r = 1.f;
     if (live) {
       y = ld4(a.y + row * a.ldy + c);                    // second read of Y: L2 (this CTA just read it)
-      if (a.normalize) r = a.rnorm[row];
+      if (normalize) r = a.rnorm[row];
     }
     const float4 hj = hhat4(y);
     const float4 g = make_float4(bf_lo(gs[j].x), bf_hi(gs[j].x), bf_lo(gs[j].y), bf_hi(gs[j].y));
     float4 v;
     v.x = (g.x - m1 - hj.x * m2) * is; v.y = (g.y - m1 - hj.y * m2) * is;
     v.z = (g.z - m1 - hj.z * m2) * is; v.w = (g.w - m1 - hj.w * m2) * is;
-    if (a.relu) {
+    if (relu) {
       if (!(y.x > 0.f)) v.x = 0.f;
       if (!(y.y > 0.f)) v.y = 0.f;
       if (!(y.z > 0.f)) v.z = 0.f;
       if (!(y.w > 0.f)) v.w = 0.f;
     }
-    if (a.normalize) {
+    if (normalize) {
       float dot = fmaf(v.x, y.x, fmaf(v.y, y.y, fmaf(v.z, y.z, v.w * y.w)));
       for (int o = d4 >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
       if (!(r > kEpsNormB)) {
@@ -870,9 +900,23 @@ int layer_bwd_fast(const gp_layer_bwd* q, cudaStream_t st, bool* handled) {
     const int vpt2 = (q->B + rstep2 - 1) / rstep2;
     if (use_cta2 && a.dv == nullptr && a.dvb != nullptr && vpt2 > 4 && vpt2 <= 16 && d <= 512) {
       static const bool no_full = getenv("GP_LBWD_NOFULL") != nullptr;
+      static const bool no_cfg = getenv("GP_LBWD_NOCFG") != nullptr;
       const bool full = !no_full && q->B == (vpt2 <= 8 ? 8 : 16) * rstep2;
-      if (vpt2 <= 8) { if (full) layer_bwd_bn_cta2_kernel<8, true><<<q->N, 512, 0, st>>>(a); else layer_bwd_bn_cta2_kernel<8><<<q->N, 512, 0, st>>>(a); }
-      else { if (full) layer_bwd_bn_cta2_kernel<16, true><<<q->N, 512, 0, st>>>(a); else layer_bwd_bn_cta2_kernel<16><<<q->N, 512, 0, st>>>(a); }
+      // compile-time source configuration: both gradient sources present with the same element type, ReLU + normalize
+      int cfg = -1;
+      if (full && !no_cfg && a.dz != nullptr && a.dxn != nullptr && a.relu && a.normalize && a.dz_bf16 == a.dxn_bf16)
+        cfg = (a.dz_bf16 ? 3 : 0) | (a.dout != nullptr ? 4 : 0);
+#define GP_CTA2(V_) \
+      do { \
+        if (cfg == 0) layer_bwd_bn_cta2_kernel<V_, true, 0><<<q->N, 512, 0, st>>>(a); \
+        else if (cfg == 4) layer_bwd_bn_cta2_kernel<V_, true, 4><<<q->N, 512, 0, st>>>(a); \
+        else if (cfg == 3) layer_bwd_bn_cta2_kernel<V_, true, 3><<<q->N, 512, 0, st>>>(a); \
+        else if (cfg == 7) layer_bwd_bn_cta2_kernel<V_, true, 7><<<q->N, 512, 0, st>>>(a); \
+        else if (full) layer_bwd_bn_cta2_kernel<V_, true><<<q->N, 512, 0, st>>>(a); \
+        else layer_bwd_bn_cta2_kernel<V_><<<q->N, 512, 0, st>>>(a); \
+      } while (0)
+      if (vpt2 <= 8) GP_CTA2(8); else GP_CTA2(16);
+#undef GP_CTA2
       GP_LAUNCHED();
       part_rows = q->N;
       if (q->db != nullptr)
