@@ -654,8 +654,12 @@ layer_bwd_bn_pipe_kernel(const LbArgs a, int CS, int rows_per_cta, int nclusters
 // ---------------------------------------------------------------------------------------------------------
 // No BN: one warp per row, lane owns float4 columns lane, lane+32, ... (VPL of them).
 // ---------------------------------------------------------------------------------------------------------
-template <int VPL, int MINB = 1>
+// CFG >= 0 (the last layer of a stack in the tensor-core schedule): dz present (bit 0: bf16), no dxn, bit 2: readout
+// scatter present, no ReLU, normalize on, row width exactly 128 * VPL floats -- no per-element branches.
+template <int VPL, int MINB = 1, int CFG = -1>
 __global__ void __launch_bounds__(256, MINB) layer_bwd_row_kernel(const LbArgs a, long long rows) {
+  constexpr bool FIX = CFG >= 0;
+  const bool relu = FIX ? false : (a.relu != 0), normalize = FIX ? true : (a.normalize != 0);
   __shared__ __align__(16) float colacc[8][VPL * 128];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int d4 = a.d >> 2;
@@ -678,16 +682,29 @@ __global__ void __launch_bounds__(256, MINB) layer_bwd_row_kernel(const LbArgs a
     for (int k = 0; k < VPL; ++k) {
       const int c4 = lane + 32 * k;
       g[k] = yv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (c4 < d4) {
-        g[k] = load_g<true>(a, b, n, row, c4 * 4);       // every operand of a row is read exactly once: streaming
+      if (FIX || c4 < d4) {
+        if constexpr (FIX) {                             // every operand of a row is read exactly once: streaming
+          if constexpr ((CFG & 1) != 0) g[k] = ld4h<true>(reinterpret_cast<const __nv_bfloat16*>(a.dz) + row * a.lddz + c4 * 4);
+          else g[k] = ld4s(a.dz + row * a.lddz + c4 * 4);
+          if constexpr ((CFG & 4) != 0) {
+            const int4 i4 = *reinterpret_cast<const int4*>(a.argidx + (long long)b * a.ldo + c4 * 4);
+            const float4 o = ld4(a.dout + (long long)b * a.ldo + c4 * 4);
+            if (i4.x == n) g[k].x += o.x;
+            if (i4.y == n) g[k].y += o.y;
+            if (i4.z == n) g[k].z += o.z;
+            if (i4.w == n) g[k].w += o.w;
+          }
+        } else {
+          g[k] = load_g<true>(a, b, n, row, c4 * 4);
+        }
         yv[k] = ld4s(a.y + row * a.ldy + c4 * 4);
       }
     }
-    const float r = a.normalize ? a.rnorm[row] : 1.f;
+    const float r = normalize ? a.rnorm[row] : 1.f;
     float dot = 0.f;
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
-      if (a.relu) {
+      if (relu) {
         if (!(yv[k].x > 0.f)) g[k].x = 0.f;
         if (!(yv[k].y > 0.f)) g[k].y = 0.f;
         if (!(yv[k].z > 0.f)) g[k].z = 0.f;
@@ -695,7 +712,7 @@ __global__ void __launch_bounds__(256, MINB) layer_bwd_row_kernel(const LbArgs a
       }
       dot = fmaf(g[k].x, yv[k].x, fmaf(g[k].y, yv[k].y, fmaf(g[k].z, yv[k].z, fmaf(g[k].w, yv[k].w, dot))));
     }
-    if (a.normalize) {
+    if (normalize) {
       dot = warp_sum(dot);
       const bool clamped = !(r > kEpsNormB);
       const float ir = clamped ? 1.f / kEpsNormB : 1.f / r;
@@ -712,7 +729,7 @@ __global__ void __launch_bounds__(256, MINB) layer_bwd_row_kernel(const LbArgs a
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
       const int c4 = lane + 32 * k;
-      if (c4 < d4) {
+      if (FIX || c4 < d4) {
         store_dv(a, row, c4 * 4, g[k]);
         cs[k].x += g[k].x; cs[k].y += g[k].y; cs[k].z += g[k].z; cs[k].w += g[k].w;
       }
@@ -1025,6 +1042,22 @@ int layer_bwd_fast(const gp_layer_bwd* q, cudaStream_t st, bool* handled) {
     const int d4 = d / 4;
     // four 256-thread blocks per SM (64 registers) is the measured optimum for every row width: wider rows are capped
     // there with launch bounds (d = 256: 0.329 -> 0.262 ms; d = 512: 0.741 -> 0.535 ms at [B*N = 524288] rows)
+    // compile-time source configuration (see the kernel): dz only (+ readout scatter), no ReLU, normalize, full-width rows
+    static const bool no_cfg_row = getenv("GP_LBWD_NOCFG") != nullptr;
+    int rcfg = -1;
+    if (!no_cfg_row && a.dz != nullptr && a.dxn == nullptr && !a.relu && a.normalize && a.dv == nullptr && (d4 == 32 || d4 == 128))
+      rcfg = (a.dz_bf16 ? 1 : 0) | (a.dout != nullptr ? 4 : 0);
+    if (rcfg >= 0 && d4 == 32) {
+      if (rcfg == 0) layer_bwd_row_kernel<1, 1, 0><<<(int)blocks, 256, 0, st>>>(a, rows);
+      else if (rcfg == 1) layer_bwd_row_kernel<1, 1, 1><<<(int)blocks, 256, 0, st>>>(a, rows);
+      else if (rcfg == 4) layer_bwd_row_kernel<1, 1, 4><<<(int)blocks, 256, 0, st>>>(a, rows);
+      else layer_bwd_row_kernel<1, 1, 5><<<(int)blocks, 256, 0, st>>>(a, rows);
+    } else if (rcfg >= 0 && d4 == 128) {
+      if (rcfg == 0) layer_bwd_row_kernel<4, 4, 0><<<(int)blocks, 256, 0, st>>>(a, rows);
+      else if (rcfg == 1) layer_bwd_row_kernel<4, 4, 1><<<(int)blocks, 256, 0, st>>>(a, rows);
+      else if (rcfg == 4) layer_bwd_row_kernel<4, 4, 4><<<(int)blocks, 256, 0, st>>>(a, rows);
+      else layer_bwd_row_kernel<4, 4, 5><<<(int)blocks, 256, 0, st>>>(a, rows);
+    } else
     if (d4 <= 32) layer_bwd_row_kernel<1><<<(int)blocks, 256, 0, st>>>(a, rows);
     else if (d4 <= 64) layer_bwd_row_kernel<2, 4><<<(int)blocks, 256, 0, st>>>(a, rows);
     else if (d4 <= 128) {
