@@ -93,9 +93,10 @@ class CallProfiler:
             if name == 'gp_gcn_layer_bwd_x':
                 q = args[0]._obj
                 rows = float(q.B) * q.N
-                srcs = sum(1 for p in (q.dz, q.dxn) if p)
-                by = rows * q.d * (4.0 * (srcs + 1) + (2.0 if q.dv_bf16 else 0.0) + (4.0 if q.dv else 0.0))
-                return ('layer_bwd d=%d bn=%d rows=%d' % (q.d, q.bn, int(rows)), 0.0, by, 'fp32 in, bf16/fp32 dV out')
+                src_b = (0.0 if not q.dz else (2.0 if q.dz_bf16 else 4.0)) + (0.0 if not q.dxn else (2.0 if q.dxn_bf16 else 4.0))
+                by = rows * q.d * (src_b + 4.0 + (2.0 if q.dv_bf16 else 0.0) + (4.0 if q.dv else 0.0))
+                return ('layer_bwd d=%d bn=%d rows=%d%s' % (q.d, q.bn, int(rows), ' (bf16 gradient sources)' if (q.dz_bf16 or q.dxn_bf16) else ''),
+                        0.0, by, 'fp32 Y + fp32 / bf16 gradient sources in, bf16/fp32 dV out')
             if name == 'gp_bn_apply':
                 B, N, d = _ival(args[4]), _ival(args[5]), _ival(args[6])
                 outs = (4.0 if _ival(args[9]) else 0.0) + (2.0 if _ival(args[11]) else 0.0) + (2.0 if _ival(args[13]) else 0.0)
