@@ -178,6 +178,7 @@ _PROTOS = {
     'gp_add_scaled': [c_f, c_f, C.c_float, c_f, c_f],
     'gp_linkloss_tc_partials': [c_i, c_i],
     'gp_gcn_layer_bwd_vectorised': [c_i, c_i, c_i],
+    'gp_gcn_layer_bwd_bf16_sources_fast': [c_i, c_i, c_i],
     'gp_pool_chain_bf16': [c_f, c_ll, c_f, c_ll, c_f, c_f, c_i, c_i, c_i, c_f, c_ll, c_f, c_ll, c_f, c_ll, c_f],
     'gp_linkloss_from_q_partials': [c_i, c_i],
     'gp_linkloss_from_q': [c_f, c_f, c_f, c_i, c_i, c_f, c_f, c_f],

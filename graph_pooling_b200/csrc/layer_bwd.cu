@@ -1092,6 +1092,17 @@ using namespace gp;
 extern "C" long long gp_gcn_layer_bwd_ws(int B, int N, int d, int bn) { return ws_floats(B, N, d, bn); }
 // 1 if a layer of this shape runs on the vectorised kernels (given aligned operands): the only ones that take bf16 dz / dxn
 extern "C" int gp_gcn_layer_bwd_vectorised(int B, int d, int bn) { return shape_fast(B, d, bn, nullptr) ? 1 : 0; }
+// 1 if a layer of this shape is served by a kernel instantiated for bf16 gradient sources (compile-time source
+// configuration): BatchNorm layers on the two-CTAs-per-SM kernel with a batch that fills its passes exactly, last layers
+// with rows of 128 or 512 floats.  Elsewhere bf16 sources run through run-time branches and are SLOWER than fp32 ones
+// (measured: 1256-wide rows 2.8 vs 1.9 ms), so callers keep fp32 intermediates there.
+extern "C" int gp_gcn_layer_bwd_bf16_sources_fast(int B, int d, int bn) {
+  if (!shape_fast(B, d, bn, nullptr)) return 0;
+  if (!bn) return (d == 128 || d == 512) ? 1 : 0;
+  if (d > 512) return 0;
+  const int rstep2 = 512 / (d / 4);
+  return (B == 8 * rstep2 || B == 16 * rstep2) ? 1 : 0;
+}
 
 // exact workspace of ONE call (ws / db fields ignored): the generic kernel borrows an fp32 dV from ws when the
 // caller asked for the bias gradient without an fp32 dV and the operands miss the vectorised path's alignment.

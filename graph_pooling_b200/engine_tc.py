@@ -516,10 +516,11 @@ def bf16_grads():
 
 
 def stack_takes_bf16_grads(ctx):
-    """Every layer of the stack runs on the vectorised layer-backward kernels (the only ones that read bf16 dz / dxn)."""
+    """Every layer of the stack is served by a layer-backward kernel instantiated for bf16 dz / dxn (elsewhere bf16
+    sources go through run-time branches and are slower than fp32 ones: the caller then keeps fp32 intermediates)."""
     L = len(ctx.layers)
     lib = load()
-    return ctx.aligned and all(lib.gp_gcn_layer_bwd_vectorised(ctx.B, ctx.douts[l], int(bool(ctx.bn and l < L - 1)))
+    return ctx.aligned and all(lib.gp_gcn_layer_bwd_bf16_sources_fast(ctx.B, ctx.douts[l], int(bool(ctx.bn and l < L - 1)))
                                for l in range(L))
 
 

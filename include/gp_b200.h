@@ -281,6 +281,8 @@ long long gp_gcn_layer_bwd_ws_x(const gp_layer_bwd* q);
 /* 1 if a layer of this shape runs on the vectorised kernels (given 16-byte aligned operands) -- the precondition of
  * dz_bf16 / dxn_bf16. */
 int gp_gcn_layer_bwd_vectorised(int B, int d, int bn);
+/* 1 if this shape is served by a kernel instantiated for bf16 gradient sources (otherwise they are slower than fp32). */
+int gp_gcn_layer_bwd_bf16_sources_fast(int B, int d, int bn);
 
 /* ---------------------------------------------------------------------------------------------
  * Max readout (encoders.py:1097,1257,1287): out[b,f] = max_n Z[b,n,f], pad rows (n >= nb[b])

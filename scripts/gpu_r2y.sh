@@ -1,11 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for c in 0 1 0; do
-if [ $c = 1 ]; then export GP_LBWD_NOCFG=1; else unset GP_LBWD_NOCFG; fi
-GP_BENCH_MIN_SHARE=0.012 timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r2y_bench_c$c.json 2> gpurun_out/r2y_bench_c$c.err
+timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/r2y_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r2y_pytest.log
+for w in cfg5_ragged_64x5000 cfg4_diffpool_256x2048; do
+timeout 600 python bench.py --workload $w --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r2y_bench_$w.json 2> gpurun_out/r2y_bench_$w.err; echo "bench $w rc=$?"
 python -c "
-import json; d=json.loads([l for l in open('gpurun_out/r2y_bench_c$c.json') if l.startswith('{')][-1]); print('nocfg=$c:', d['ms_per_step'], d['roofline']['frac'], d['clocks']['sm_mhz'])"
+import json; d=json.loads([l for l in open('gpurun_out/r2y_bench_$w.json') if l.startswith('{')][-1]); print('$w:', d['ms_per_step'], d['value'], d['roofline']['frac'], d['clocks']['sm_mhz'])"
 done
-python -c "
-import json; d=json.loads([l for l in open('gpurun_out/r2y_bench_c0.json') if l.startswith('{')][-1])
-for r in d['roofline']['kernels']: print('  %-22s %-64s %2d %.3f %s %.3f'%(r['entry'][3:], r['shape'][:64], r['launches'], r['ms'], r.get('bound'), r.get('frac',0)))"

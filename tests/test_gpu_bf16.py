@@ -329,3 +329,58 @@ def test_host_adjacency_feed_pipeline():
     with pytest.raises(ValueError):
         fd.copy(0)
     fd.close()
+
+
+def test_bf16_gradient_intermediates_at_a_shape_that_takes_them(monkeypatch):
+    """The lock-step backward keeps dZ / dza / dX in bf16 only where every layer is served by a layer-backward kernel
+    instantiated for bf16 sources (gp_gcn_layer_bwd_bf16_sources_fast): B = 128 graphs, H = 128, K = 128 is such a
+    shape.  Checks that the path is really taken (hook), that it stays within the mode's bounds against the fp64 oracle
+    and within 1e-3 of the fp32-intermediate schedule."""
+    from graph_pooling_b200 import encoders, _lib
+    N, D, H, C, B = 512, 16, 128, 3, 128
+    torch.manual_seed(11)
+    mo = orc.SoftPoolingGcnEncoder(N, D, H, H, C, 3, H, assign_ratio=0.25, num_pooling=1)
+    mc = encoders.SoftPoolingGcnEncoder(N, D, H, H, C, 3, H, assign_ratio=0.25, num_pooling=1)
+    mc.load_state_dict(mo.state_dict())
+    mc = mc.cuda()
+    mc.precision = 1
+    x, adj, nb, label = synth_batch(17, B, N, D, 100, N, C, 0.02)
+    m64 = copy.deepcopy(mo).double()
+    yo, lo = orc.train_step(m64, torch.tensor(x).double(), torch.tensor(adj).double(), torch.tensor(label), nb)
+    go = np.concatenate([p.grad.numpy().ravel() for p in m64.parameters()])
+
+    class Rec:
+        def __init__(self):
+            self.bf16_calls = 0
+
+        def begin(self, name, args):
+            if name == 'gp_gcn_layer_bwd_x' and args[0]._obj.dz_bf16:
+                self.bf16_calls += 1
+
+        def end(self, tok):
+            pass
+
+    grads = {}
+    for f32 in (False, True):
+        if f32:
+            monkeypatch.setenv('GP_F32_GRADS', '1')
+        else:
+            monkeypatch.delenv('GP_F32_GRADS', raising=False)
+        mc.zero_grad()
+        rec = Rec()
+        _lib.set_hook(rec)
+        xc, ac = torch.tensor(x).cuda(), torch.tensor(adj).cuda()
+        yp = mc(xc, ac, nb, assign_x=xc)
+        loss = mc.loss(yp, torch.tensor(label).cuda(), ac, nb)
+        loss.backward()
+        torch.cuda.synchronize()
+        _lib.set_hook(None)
+        assert (rec.bf16_calls > 0) == (not f32)
+        grads[f32] = np.concatenate([p.grad.cpu().numpy().ravel() for p in mc.parameters()]).astype(np.float64)
+        assert rel_l2(yp.detach().cpu().numpy(), yo.detach().numpy()) < BF16_OUT
+        assert abs(loss.item() - lo.item()) < BF16_LOSS * abs(lo.item())
+    for f32 in (False, True):
+        g = grads[f32]
+        cos = float(g @ go / (np.linalg.norm(g) * np.linalg.norm(go)))
+        assert rel_l2(g, go) < BF16_GRAD and cos > BF16_COS, (f32, rel_l2(g, go), cos)
+    assert rel_l2(grads[False], grads[True]) < 1e-3
