@@ -751,8 +751,16 @@ __global__ void __launch_bounds__(256, MINB) layer_bwd_row_kernel(const LbArgs a
 // Rows wider than 512 floats (the assignment GCN's last layer at K = 1250 -> 1256 / 1280 clusters): the row no longer
 // fits the registers twice over, so the dot product is taken in a first pass and the operands are read again (L1 / L2
 // hits: a row is a few KB) for the update.  4 warps per block; VPL float4 per lane hold the column sums only.
-template <int VPL, int MINB = 1>
+// CFG >= 0: dz is the only gradient source (CFG 0: fp32, 1: bf16), no ReLU, normalize on (the assignment GCN's last layer)
+template <int VPL, int MINB = 1, int CFG = -1>
 __global__ void __launch_bounds__(128, MINB) layer_bwd_row_wide_kernel(const LbArgs a, long long rows) {
+  constexpr bool FIX = CFG >= 0;
+  const bool relu = FIX ? false : (a.relu != 0), normalize = FIX ? true : (a.normalize != 0);
+  auto ldg = [&](int b, int n, long long row, int c) -> float4 {
+    if constexpr (CFG == 0) return ld4(a.dz + row * a.lddz + c);
+    else if constexpr (CFG == 1) return ld4h<false>(reinterpret_cast<const __nv_bfloat16*>(a.dz) + row * a.lddz + c);
+    else return load_g(a, b, n, row, c);
+  };
   __shared__ __align__(16) float colacc[4][VPL * 128];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int d4 = a.d >> 2;
@@ -770,16 +778,16 @@ __global__ void __launch_bounds__(128, MINB) layer_bwd_row_wide_kernel(const LbA
       }
       continue;
     }
-    const float r = a.normalize ? a.rnorm[row] : 1.f;
+    const float r = normalize ? a.rnorm[row] : 1.f;
     float dot = 0.f;
-    if (a.normalize) {
+    if (normalize) {
 #pragma unroll 4
       for (int k = 0; k < VPL; ++k) {
         const int c4 = lane + 32 * k;
         if (c4 < d4) {
-          float4 g = load_g(a, b, n, row, c4 * 4);
+          float4 g = ldg(b, n, row, c4 * 4);
           const float4 yv = ld4(a.y + row * a.ldy + c4 * 4);
-          if (a.relu) {
+          if (relu) {
             if (!(yv.x > 0.f)) g.x = 0.f;
             if (!(yv.y > 0.f)) g.y = 0.f;
             if (!(yv.z > 0.f)) g.z = 0.f;
@@ -796,15 +804,15 @@ __global__ void __launch_bounds__(128, MINB) layer_bwd_row_wide_kernel(const LbA
     for (int k = 0; k < VPL; ++k) {
       const int c4 = lane + 32 * k;
       if (c4 < d4) {
-        float4 g = load_g(a, b, n, row, c4 * 4);
+        float4 g = ldg(b, n, row, c4 * 4);
         const float4 yv = ld4(a.y + row * a.ldy + c4 * 4);
-        if (a.relu) {
+        if (relu) {
           if (!(yv.x > 0.f)) g.x = 0.f;
           if (!(yv.y > 0.f)) g.y = 0.f;
           if (!(yv.z > 0.f)) g.z = 0.f;
           if (!(yv.w > 0.f)) g.w = 0.f;
         }
-        if (a.normalize) {
+        if (normalize) {
           if (clamped) {
             g.x /= kEpsNormB; g.y /= kEpsNormB; g.z /= kEpsNormB; g.w /= kEpsNormB;
           } else {
@@ -1070,6 +1078,10 @@ int layer_bwd_fast(const gp_layer_bwd* q, cudaStream_t st, bool* handled) {
       else layer_bwd_row_kernel<4><<<(int)blocks, 256, 0, st>>>(a, rows);
     }
     else if (d4 <= 256) layer_bwd_row_wide_kernel<8><<<(int)blocks, 128, 0, st>>>(a, rows);
+    else if (!no_cfg_row && a.dz != nullptr && a.dxn == nullptr && a.dout == nullptr && !a.relu && a.normalize) {
+      if (a.dz_bf16) layer_bwd_row_wide_kernel<16, 6, 1><<<(int)blocks, 128, 0, st>>>(a, rows);
+      else layer_bwd_row_wide_kernel<16, 6, 0><<<(int)blocks, 128, 0, st>>>(a, rows);
+    }
     else {
       static int wminb = -1;
       if (wminb < 0) { const char* e = getenv("GP_WIDE_MINB"); wminb = e != nullptr ? atoi(e) : 1; }   /* 80 registers: six / three blocks per SM, measured 2.31 -> 1.95 ms at cfg5 */
