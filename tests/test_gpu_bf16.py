@@ -368,13 +368,13 @@ def test_bf16_gradient_intermediates_at_a_shape_that_takes_them(monkeypatch):
             monkeypatch.delenv('GP_F32_GRADS', raising=False)
         mc.zero_grad()
         rec = Rec()
-        _lib.set_hook(rec)
+        monkeypatch.setattr(_lib, '_hook', rec)          # restored by monkeypatch even if an assertion fails
         xc, ac = torch.tensor(x).cuda(), torch.tensor(adj).cuda()
         yp = mc(xc, ac, nb, assign_x=xc)
         loss = mc.loss(yp, torch.tensor(label).cuda(), ac, nb)
         loss.backward()
         torch.cuda.synchronize()
-        _lib.set_hook(None)
+        monkeypatch.setattr(_lib, '_hook', None)
         assert (rec.bf16_calls > 0) == (not f32)
         grads[f32] = np.concatenate([p.grad.cpu().numpy().ravel() for p in mc.parameters()]).astype(np.float64)
         assert rel_l2(yp.detach().cpu().numpy(), yo.detach().numpy()) < BF16_OUT

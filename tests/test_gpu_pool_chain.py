@@ -144,7 +144,7 @@ def test_model_chain_equals_three_launch_schedule(monkeypatch):
     for no_chain in ('', '1'):
         monkeypatch.setattr(engine_tc, 'CHAIN_POOLING', not no_chain)
         rec = Names()
-        _lib.set_hook(rec)
+        monkeypatch.setattr(_lib, '_hook', rec)          # restored by monkeypatch even if an assertion fails
         torch.manual_seed(0)
         m = enc.SoftPoolingGcnEncoder(N, D, H, H, Cc, 3, H, assign_ratio=0.25, num_pooling=2).cuda()
         m.precision = 1
@@ -156,7 +156,7 @@ def test_model_chain_equals_three_launch_schedule(monkeypatch):
         with torch.no_grad():
             y_ng = m(xt, at, nb, assign_x=xt)
         assert torch.equal(y_ng, y.detach())
-        _lib.set_hook(None)
+        monkeypatch.setattr(_lib, '_hook', None)
         assert ('gp_pool_chain_bf16' in rec.seen) == (not no_chain)       # the schedule under test really ran
         outs.append((y.detach().clone(), loss.detach().clone(), g.clone()))
     (y0, l0, g0), (y1, l1, g1) = outs
