@@ -55,6 +55,16 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {
   return sh[32];
 }
 
+// (graph, node) of a flattened row index r = b * N + n.  Every caller has B * N < 2^31 rows (checked on the host), so the
+// division runs in 32 bits: a 64-bit division by a run-time divisor costs ~60 instructions per row and lane, as much as
+// the useful work of a 128-float row.
+__device__ __forceinline__ void row_split(long long r, int N, int& b, int& n) {
+  const unsigned ur = (unsigned)r, un = (unsigned)N;
+  const unsigned ub = ur / un;
+  b = (int)ub;
+  n = (int)(ur - ub * un);
+}
+
 constexpr int kNumSMs = 148;   // B200 (grid sizing only: a device with another SM count runs the same kernels correctly)
 
 // "Configure once per DEVICE": cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device / context, so the

@@ -668,7 +668,8 @@ __global__ void __launch_bounds__(256, MINB) layer_bwd_row_kernel(const LbArgs a
 #pragma unroll
   for (int k = 0; k < VPL; ++k) cs[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (long long row = gw; row < rows; row += nw) {
-    const int b = (int)(row / a.N), n = (int)(row - (long long)b * a.N);
+    int b, n;
+    row_split(row, a.N, b, n);
     if (a.nbz != nullptr && n >= a.nbz[b]) {             // pad row of a masked level: dV = 0, nothing to read
 #pragma unroll
       for (int k = 0; k < VPL; ++k) {
@@ -769,7 +770,8 @@ __global__ void __launch_bounds__(128, MINB) layer_bwd_row_wide_kernel(const LbA
 #pragma unroll
   for (int k = 0; k < VPL; ++k) cs[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (long long row = gw; row < rows; row += nw) {
-    const int b = (int)(row / a.N), n = (int)(row - (long long)b * a.N);
+    int b, n;
+    row_split(row, a.N, b, n);
     if (a.nbz != nullptr && n >= a.nbz[b]) {             // pad row of a masked level: dV = 0, nothing to read
 #pragma unroll
       for (int k = 0; k < VPL; ++k) {
@@ -1129,6 +1131,7 @@ extern "C" long long gp_gcn_layer_bwd_ws_x(const gp_layer_bwd* q) {
 extern "C" int gp_gcn_layer_bwd_x(const gp_layer_bwd* q, gp_stream_t stream) {
   GP_REQUIRE(q != nullptr, "gcn_layer_bwd_x: null descriptor");
   GP_REQUIRE(q->y && (q->dv || q->dv_bf16) && q->B > 0 && q->N > 0 && q->d > 0, "gcn_layer_bwd_x: bad args");
+  GP_REQUIRE((long long)q->B * q->N <= 0x7fffffffLL, "gcn_layer_bwd_x: B * N must stay below 2^31 rows");
   GP_REQUIRE(!q->bn || (q->invstd && (q->h || q->mean)), "gcn_layer_bwd_x: bn needs invstd and h or mean");
   GP_REQUIRE(!q->normalize || q->rnorm, "gcn_layer_bwd_x: normalize needs rnorm");
   GP_REQUIRE(!q->dout || q->argidx, "gcn_layer_bwd_x: dout needs argidx");

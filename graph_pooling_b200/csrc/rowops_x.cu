@@ -55,7 +55,8 @@ __global__ void bn_apply_kernel(const float* __restrict__ y, long long ldy, cons
   const long long gw = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
   for (long long r = gw; r < rows; r += nw) {
-    const int n = (int)(r % N);
+    int b_, n;
+    row_split(r, N, b_, n);
     const float mu = bn ? mean[n] : 0.f, is = bn ? invstd[n] : 1.f;
     if (VEC) {
       for (int c = lane * 4; c < d; c += 128) {
@@ -131,7 +132,8 @@ __global__ void softmax_fwd_x_kernel(float* __restrict__ t, const int32_t* __res
   const long long gw = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
   for (long long r = gw; r < rows; r += nw) {
-    const int b = (int)(r / N), n = (int)(r - (long long)b * N);
+    int b, n;
+    row_split(r, N, b, n);
     const bool pad = nb != nullptr && n >= nb[b];
     float4 x[VPL];
     float mx = -INFINITY;
@@ -182,7 +184,8 @@ __global__ void softmax_bwd_x_kernel(const float* __restrict__ s, const float* _
 #pragma unroll
   for (int k = 0; k < VPL; ++k) cs[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (long long r = gw; r < rows; r += nw) {
-    const int b = (int)(r / N), n = (int)(r - (long long)b * N);
+    int b, n;
+    row_split(r, N, b, n);
     const bool pad = nb != nullptr && n >= nb[b];
     float4 sv[VPL], gv[VPL];
     float dot = 0.f;
@@ -237,7 +240,8 @@ __global__ void __launch_bounds__(128) softmax_bwd_wide_kernel(const float* __re
 #pragma unroll
   for (int k = 0; k < VPL; ++k) cs[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (long long r = gw; r < rows; r += nw) {
-    const int b = (int)(r / N), n = (int)(r - (long long)b * N);
+    int b, n;
+    row_split(r, N, b, n);
     const bool pad = nb != nullptr && n >= nb[b];
     float dot = 0.f;
     if (!pad) {
@@ -301,6 +305,7 @@ extern "C" int gp_bn_apply(const float* y, long long ldy, const float* mean, con
   GP_REQUIRE(y && (h || h_bf16) && B > 0 && N > 0 && d > 0 && ldy >= d, "bn_apply: bad args");
   GP_REQUIRE(!bn || (mean && invstd), "bn_apply: bn needs mean/invstd");
   const long long rows = (long long)B * N;
+  GP_REQUIRE(rows <= 0x7fffffffLL, "B * N must stay below 2^31 rows");
   __nv_bfloat16* hb = reinterpret_cast<__nv_bfloat16*>(h_bf16);
   __nv_bfloat16* hb2 = reinterpret_cast<__nv_bfloat16*>(h_bf16_2);
   const bool vec = d % 4 == 0 && al16x(y) && ldy % 4 == 0 && (!h || (al16x(h) && ldh % 4 == 0)) &&
@@ -345,6 +350,7 @@ extern "C" int gp_softmax_mask_fwd_x(float* t, const int32_t* nb, int B, int N, 
     return gp_softmax_mask_fwd(t, nb, B, N, K, stream);
   }
   const long long rows = (long long)B * N;
+  GP_REQUIRE(rows <= 0x7fffffffLL, "B * N must stay below 2^31 rows");
   const int g = row_grid(rows);
   if (K <= 128)      softmax_fwd_x_kernel<1><<<g, 256, 0, S(stream)>>>(t, nb, rows, N, K, sb, ldsb);
   else if (K <= 256) softmax_fwd_x_kernel<2><<<g, 256, 0, S(stream)>>>(t, nb, rows, N, K, sb, ldsb);
@@ -365,6 +371,7 @@ extern "C" int gp_softmax_mask_bwd_x(const float* s, const float* ds, const int3
   const bool vec = K % 4 == 0 && K <= 2048 && al16x(s) && al16x(ds) && (!dt || al16x(dt)) &&
                    (!dtb || (al8x(dtb) && lddtb % 4 == 0));
   const long long rows = (long long)B * N;
+  GP_REQUIRE(rows <= 0x7fffffffLL, "B * N must stay below 2^31 rows");
   if (!vec) {
     GP_REQUIRE(dtb == nullptr && dt != nullptr, "softmax_mask_bwd_x: the bf16 copy needs K %% 4 == 0 and K <= 2048");
     GP_TRY(gp_softmax_mask_bwd(s, ds, nb, B, N, K, dt, stream));

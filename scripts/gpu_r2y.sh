@@ -1,4 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"layer_bwd_bn_cta2_kernel" --launch-skip 3 --launch-count 1 -o gpurun_out/prof_r2f_lbwd -f python scripts/lbwd_probe.py 256 2048 128 1 bf16 > gpurun_out/ncu_r2f_lbwd.log 2>&1; echo "ncu rc=$?"
-GP_BENCH_NO_ENZ=1 GP_PROFILE=1 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2f_launches_cfg4.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --graph off > gpurun_out/ncu_r2f_launches.log 2>&1; echo "launch list rc=$?"
+timeout 300 python scripts/lbwd_probe.py 256 2048 128 0 bf16; timeout 300 python scripts/lbwd_probe.py 256 2048 512 0 bf16
+timeout 900 python -m pytest tests/test_gpu_layer_bwd.py tests/test_gpu_fused_rows.py tests/test_gpu_bf16.py tests/test_gpu_baseline_shapes.py tests/test_gpu_ops.py -q -m gpu 2>&1 | tail -2
+GP_BENCH_MIN_SHARE=0.012 timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r2y_bench_d.json 2> gpurun_out/r2y_bench_d.err
+python -c "
+import json; d=json.loads([l for l in open('gpurun_out/r2y_bench_d.json') if l.startswith('{')][-1]); print(d['ms_per_step'], d['roofline']['frac'], d['clocks']['sm_mhz'])
+for r in d['roofline']['kernels']:
+  if any(k in r['entry'] for k in ('bn_apply','softmax','layer_bwd')): print('  %-22s %-58s %2d %.3f %.3f'%(r['entry'][3:], r['shape'][:58], r['launches'], r['ms'], r.get('frac',0)))"
